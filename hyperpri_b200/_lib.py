@@ -1,0 +1,74 @@
+"""ctypes binding of the C ABI declared in include/hyperpri_b200.h.
+
+The shared library is built in-tree by ``hyperpri_b200.build`` (nvcc, sm_100a) and MUST be
+present: there is no CPU or PyTorch fallback -- a missing library raises at first use.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libhyperpri_b200.so")
+
+
+class View(C.Structure):
+    """hpri_view_t: NHWC bf16 view with element strides."""
+    _fields_ = [("ptr", C.c_void_p), ("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("c", C.c_int),
+                ("pix_stride", C.c_longlong), ("row_stride", C.c_longlong), ("img_stride", C.c_longlong)]
+
+
+_VP = C.POINTER(View)
+_p, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
+
+# name -> argtypes; every symbol include/hyperpri_b200.h declares
+SIGNATURES = {
+    "hpri_abi_version": [],
+    "hpri_igemm_fwd": [_VP, _p, _i, _i, _i, _VP, _i, _p, _p, _i, _p],
+    "hpri_convT2x2_fwd": [_VP, _p, _i, _i, _VP, _p, _i, _p],
+    "hpri_convT2x2_dgrad": [_VP, _p, _i, _i, _VP, _i, _p],
+    "hpri_igemm_wgrad": [_VP, _VP, _i, _i, _p, _i, _i, _i, _p],
+    "hpri_pack_weights": [_p, _p, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _p],
+    "hpri_unpack_grads": [_p, _p, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _f, _p],
+    "hpri_hsi_ingest": [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _i, _p],
+    "hpri_absmax": [_p, _ll, _p, _p],
+    "hpri_bn_finalize": [_p, _ll, _p, _p, _p, _p, _p, _p, _f, _f, _i, _p, _p, _p, _p, _i, _p],
+    "hpri_bn_relu_apply": [_VP, _p, _p, _VP, _VP, _p],
+    "hpri_bn_relu_bwd_reduce": [_VP, _p, _p, _p, _p, _VP, _VP, _p, _p, _p, _p],
+    "hpri_bn_relu_bwd_apply": [_VP, _p, _p, _p, _p, _p, _VP, _VP, _p, _p, _p, _ll, _VP, _p, _p, _p, _p],
+    "hpri_head_fwd": [_VP, _p, _p, _p, _p, _p, _p],
+    "hpri_bce_fwd_bwd": [_p, _p, _ll, _f, _f, _p, _p, _p, _p],
+    "hpri_colsum": [_VP, _p, _f, _p],
+    "hpri_sum_f32": [_p, _ll, _p, _p],
+}
+
+ERRORS = {-1: "HPRI_ERR_ARG", -2: "HPRI_ERR_ALIGN", -3: "HPRI_ERR_DRIVER", -4: "HPRI_ERR_TENSORMAP",
+          -5: "HPRI_ERR_CUDA"}
+
+_lib = None
+
+
+class NativeLibraryMissing(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the CDLL; raise loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeLibraryMissing(
+                f"{LIB_PATH} not found: run `python -m hyperpri_b200.build` (nvcc, sm_100a). "
+                "hyperpri_b200 has no CPU/PyTorch fallback.")
+        l = C.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(l, name)          # AttributeError if the .so is stale
+            fn.argtypes = args
+            fn.restype = C.c_int
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed: {ERRORS.get(rc, rc)}")

@@ -1,0 +1,652 @@
+// Memory-bound kernels of the hot path: weight (un)packing, HSI ingest, BatchNorm finalize /
+// apply(+ReLU, +MaxPool) / backward, 1x1 head, sigmoid-BCE, channel sums.
+// All are HBM-bandwidth bound: 16-byte vector accesses along the NHWC channel axis, one pass
+// over each tensor, fp32 math, double accumulation where a reduction spans the whole image.
+#include "ptx.cuh"
+#include "hyperpri_b200.h"
+
+namespace hpri {
+
+static inline int check_view_e(const hpri_view_t* v) {
+  if (!v || !v->ptr || v->n <= 0 || v->h <= 0 || v->w <= 0 || v->c <= 0) return HPRI_ERR_ARG;
+  if ((reinterpret_cast<uintptr_t>(v->ptr) & 15) || (v->pix_stride & 7) || (v->row_stride & 7) || (v->img_stride & 7))
+    return HPRI_ERR_ALIGN;
+  if (v->pix_stride < ((v->c + 7) & ~7)) return HPRI_ERR_ARG;
+  return HPRI_OK;
+}
+static inline int last_err() { return cudaGetLastError() == cudaSuccess ? HPRI_OK : HPRI_ERR_CUDA; }
+
+struct V {   // device-side copy of a view
+  __nv_bfloat16* p;
+  int n, h, w, c;
+  long long sp, sr, si;
+};
+static inline V mk(const hpri_view_t* v) {
+  V o{};
+  if (v) { o.p = static_cast<__nv_bfloat16*>(v->ptr); o.n = v->n; o.h = v->h; o.w = v->w; o.c = v->c;
+           o.sp = v->pix_stride; o.sr = v->row_stride; o.si = v->img_stride; }
+  return o;
+}
+__device__ __forceinline__ __nv_bfloat16* at(const V& v, int n, int y, int x, int c) {
+  return v.p + n * v.si + y * v.sr + x * v.sp + c;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  return u;
+}
+__device__ __forceinline__ void ld8p(const float* p, int c0, int C, float (&f)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = (p != nullptr && c0 + j < C) ? __ldg(p + c0 + j) : 0.f;
+}
+
+// ------------------------------------------------------------------ weight pack / unpack
+__global__ void pack_weights_k(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int G, int R, int T,
+                               int C, int kc64, long long sg, long long sr, long long st, long long sc, int flip) {
+  const long long total = (long long)G * R * T * kc64;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % kc64);
+    const long long j = i / kc64;
+    const int t = (int)(j % T);
+    const long long row = j / T;
+    const int g = (int)(row / R), r = (int)(row % R);
+    const int tm = flip ? T - 1 - t : t;
+    float v = 0.f;
+    if (c < C) v = __ldg(src + g * sg + r * sr + tm * st + c * sc);
+    dst[i] = __float2bfloat16_rn(v);
+  }
+}
+__global__ void unpack_grads_k(const float* __restrict__ packed, float* __restrict__ dst, int G, int R, int T, int C,
+                               int kc64, long long sg, long long sr, long long st, long long sc, int flip,
+                               float beta) {
+  const long long total = (long long)G * R * T * kc64;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % kc64);
+    if (c >= C) continue;
+    const long long j = i / kc64;
+    const int t = (int)(j % T);
+    const long long row = j / T;
+    const int g = (int)(row / R), r = (int)(row % R);
+    const int tm = flip ? T - 1 - t : t;
+    float* d = dst + g * sg + r * sr + tm * st + c * sc;
+    const float v = packed[i];
+    *d = beta == 0.f ? v : beta * (*d) + v;
+  }
+}
+
+// ------------------------------------------------------------------ ingest
+// One block = 64 consecutive pixels of one output row, all bands.  Band-major coalesced fp32 reads
+// (128 B per warp request), transposed through shared memory, pixel-major coalesced bf16 writes.
+__global__ void __launch_bounds__(256)
+hsi_ingest_k(const float* __restrict__ src, int bands_total, int H, int W, int lo, int nb, int i0, int j0, int h,
+             int w, int flip_h, int flip_w, float scale, const float* __restrict__ bmean,
+             const float* __restrict__ bstd, __nv_bfloat16* __restrict__ dst, int c_pad) {
+  extern __shared__ uint32_t tile_w[];          // [64][c_pad/2 + 1] words (odd stride -> conflict-free)
+  const int wstride = c_pad / 2 + 1;
+  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(tile_w);
+  const int xt = blockIdx.x, y = blockIdx.y, n = blockIdx.z;
+  const int x0 = xt * 64;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sy = i0 + (flip_h ? h - 1 - y : y);
+  const float* img = src + ((long long)n * bands_total + lo) * H * W + (long long)sy * W;
+  for (int b = warp; b < c_pad; b += 8) {
+    float v0 = 0.f, v1 = 0.f;
+    if (b < nb) {
+      const float* row = img + (long long)b * H * W;
+      const int xa = x0 + lane, xb = x0 + lane + 32;
+      if (xa < w) v0 = __ldg(row + j0 + (flip_w ? w - 1 - xa : xa));
+      if (xb < w) v1 = __ldg(row + j0 + (flip_w ? w - 1 - xb : xb));
+      v0 *= scale; v1 *= scale;
+      if (bmean != nullptr) {
+        const float m = __ldg(bmean + b), is = 1.f / __ldg(bstd + b);
+        v0 = (v0 - m) * is; v1 = (v1 - m) * is;
+      }
+    }
+    tile[(lane) * (2 * wstride) + b] = __float2bfloat16_rn(v0);
+    tile[(lane + 32) * (2 * wstride) + b] = __float2bfloat16_rn(v1);
+  }
+  __syncthreads();
+  const int wpp = c_pad / 2;                    // words per pixel
+  const int npix = min(64, w - x0);
+  uint32_t* out = reinterpret_cast<uint32_t*>(dst + (((long long)n * h + y) * w + x0) * c_pad);
+  for (int i = threadIdx.x; i < npix * wpp; i += 256) {
+    const int px = i / wpp, k = i - px * wpp;
+    out[i] = tile_w[px * wstride + k];
+  }
+}
+
+__global__ void absmax_k(const float* __restrict__ x, long long n, float* out) {
+  float m = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(__ldg(x + i)));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));
+}
+
+// ------------------------------------------------------------------ BatchNorm finalize
+__global__ void bn_finalize_k(double* stats, long long count, const float* gamma, const float* beta,
+                              const float* conv_bias, float* rmean, float* rvar, long long* nbt, float momentum,
+                              float eps, int training, float* scale, float* shift, float* smean, float* sinv, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  const float cb = conv_bias ? conv_bias[c] : 0.f;
+  if (training) {
+    const double s = stats[2 * c], ss = stats[2 * c + 1];
+    const double mean = s / (double)count;
+    double var = ss / (double)count - mean * mean;
+    if (var < 0) var = 0;
+    const float inv = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = g * inv;
+    scale[c] = sc;
+    shift[c] = b - (float)mean * sc;
+    if (smean) smean[c] = (float)mean;
+    if (sinv) sinv[c] = inv;
+    if (rmean) rmean[c] = (1.f - momentum) * rmean[c] + momentum * ((float)mean + cb);
+    if (rvar) {
+      const double unb = count > 1 ? var * (double)count / (double)(count - 1) : var;
+      rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unb;
+    }
+    stats[2 * c] = 0.0; stats[2 * c + 1] = 0.0;
+    if (c == 0 && nbt) *nbt += 1;
+  } else {
+    const float inv = rsqrtf(rvar[c] + eps);
+    const float sc = g * inv;
+    scale[c] = sc;
+    shift[c] = b + (cb - rmean[c]) * sc;
+    if (smean) smean[c] = rmean[c] - cb;
+    if (sinv) sinv[c] = inv;
+  }
+}
+
+// ------------------------------------------------------------------ BN apply + ReLU (+ 2x2 max pool)
+// One thread = one 2x2 pixel window x 8 channels.
+__global__ void __launch_bounds__(256)
+bn_relu_apply_k(V x, const float* __restrict__ scale, const float* __restrict__ shift, V y, V pool) {
+  const int CG = (x.c + 7) >> 3;
+  const int wh = (x.h + 1) >> 1, ww = (x.w + 1) >> 1;
+  const long long total = (long long)x.n * wh * ww * CG;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    long long j = i / CG;
+    const int wx = (int)(j % ww); j /= ww;
+    const int wy = (int)(j % wh);
+    const int n = (int)(j / wh);
+    const int c0 = cg * 8;
+    float sc[8], sh[8];
+    ld8p(scale, c0, x.c, sc);
+    ld8p(shift, c0, x.c, sh);
+    float mx[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) mx[k] = -INFINITY;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int yy = 2 * wy + dy, xx = 2 * wx + dx;
+        if (yy >= x.h || xx >= x.w) continue;
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(at(x, n, yy, xx, c0))), f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          f[k] = fmaxf(fmaf(f[k], sc[k], sh[k]), 0.f);
+          mx[k] = fmaxf(mx[k], f[k]);
+        }
+        *reinterpret_cast<uint4*>(at(y, n, yy, xx, c0)) = pack8(f);
+      }
+    if (pool.p != nullptr && wy < pool.h && wx < pool.w) *reinterpret_cast<uint4*>(at(pool, n, wy, wx, c0)) = pack8(mx);
+  }
+}
+
+// ------------------------------------------------------------------ backward of relu(bn(x)) (+pool, +head)
+// Shared traversal: for a 2x2 window x 8 channels compute dz (gradient at the BN output after the
+// ReLU mask) for each of the 4 pixels.  The post-ReLU activation is re-derived from the raw conv
+// output x, so no activation mask is stored.
+struct BwdIn {
+  V x, dy, dpool;
+  const float *scale, *shift, *mean, *invstd, *head_w, *dlogit;
+};
+__device__ __forceinline__ void window_dz(const BwdIn& a, int n, int wy, int wx, int c0, float (&xr)[4][8],
+                                          float (&act)[4][8], float (&dz)[4][8], bool (&inb)[4], float (&dl)[4]) {
+  float sc[8], sh[8];
+  ld8p(a.scale, c0, a.x.c, sc);
+  ld8p(a.shift, c0, a.x.c, sh);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int yy = 2 * wy + (q >> 1), xx = 2 * wx + (q & 1);
+    inb[q] = yy < a.x.h && xx < a.x.w;
+    dl[q] = 0.f;
+    if (!inb[q]) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { xr[q][k] = 0.f; act[q][k] = 0.f; dz[q][k] = 0.f; }
+      continue;
+    }
+    unpack8(__ldg(reinterpret_cast<const uint4*>(at(a.x, n, yy, xx, c0))), xr[q]);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) act[q][k] = fmaxf(fmaf(xr[q][k], sc[k], sh[k]), 0.f);
+    if (a.dy.p != nullptr) unpack8(__ldg(reinterpret_cast<const uint4*>(at(a.dy, n, yy, xx, c0))), dz[q]);
+    else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dz[q][k] = 0.f;
+    }
+    if (a.dlogit != nullptr) {
+      dl[q] = __ldg(a.dlogit + ((long long)n * a.x.h + yy) * a.x.w + xx);
+      float hw[8];
+      ld8p(a.head_w, c0, a.x.c, hw);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dz[q][k] = fmaf(dl[q], hw[k], dz[q][k]);
+    }
+  }
+  if (a.dpool.p != nullptr && wy < a.dpool.h && wx < a.dpool.w) {
+    float dp[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(at(a.dpool, n, wy, wx, c0))), dp);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      int best = 0;
+      float m = act[0][k];
+#pragma unroll
+      for (int q = 1; q < 4; ++q)
+        if (act[q][k] > m) { m = act[q][k]; best = q; }     // first maximum wins (ATen max_pool2d order)
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (q == best) dz[q][k] += dp[k];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (!(act[q][k] > 0.f)) dz[q][k] = 0.f;
+}
+
+// pass 1: sums[c] = {sum dz, sum dz*xhat, sum dlogit*act}
+__global__ void __launch_bounds__(256) bn_bwd_reduce_k(BwdIn a, double* sums, int slots, int CG) {
+  extern __shared__ float red[];                 // [slots][CG*8][3]
+  const int cg = threadIdx.x % CG, slot = threadIdx.x / CG;
+  const bool active = slot < slots;
+  const int wh = (a.x.h + 1) >> 1, ww = (a.x.w + 1) >> 1;
+  const long long nwin = (long long)a.x.n * wh * ww;
+  float s1[8], s2[8], s3[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; s3[k] = 0.f; }
+  if (active) {
+    const int c0 = cg * 8;
+    float mu[8], is[8];
+    ld8p(a.mean, c0, a.x.c, mu);
+    ld8p(a.invstd, c0, a.x.c, is);
+    for (long long wi = (long long)blockIdx.x * slots + slot; wi < nwin; wi += (long long)gridDim.x * slots) {
+      long long j = wi;
+      const int wx = (int)(j % ww); j /= ww;
+      const int wy = (int)(j % wh);
+      const int n = (int)(j / wh);
+      float xr[4][8], act[4][8], dz[4][8], dl[4];
+      bool inb[4];
+      window_dz(a, n, wy, wx, c0, xr, act, dz, inb, dl);
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          s1[k] += dz[q][k];
+          s2[k] = fmaf(dz[q][k], (xr[q][k] - mu[k]) * is[k], s2[k]);
+          s3[k] = fmaf(dl[q], act[q][k], s3[k]);
+        }
+    }
+    float* r = red + ((long long)slot * CG + cg) * 24;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { r[k * 3] = s1[k]; r[k * 3 + 1] = s2[k]; r[k * 3 + 2] = s3[k]; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < CG * 24; i += blockDim.x) {
+    float t = 0.f;
+    for (int s = 0; s < slots; ++s) t += red[(long long)s * CG * 24 + i];
+    const int c = (i / 24) * 8 + (i % 24) / 3, which = i % 3;
+    if (c < a.x.c) atomicAdd(sums + 3 * c + which, (double)t);
+  }
+}
+
+// pass 2: dx = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat))
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_k(BwdIn a, const float* __restrict__ gamma, const double* __restrict__ sums, long long count, V dx,
+               float* dgamma, float* dbeta, float* dhead_w) {
+  const int CG = (a.x.c + 7) >> 3;
+  const int wh = (a.x.h + 1) >> 1, ww = (a.x.w + 1) >> 1;
+  const long long total = (long long)a.x.n * wh * ww * CG;
+  if (blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < a.x.c; c += blockDim.x) {
+      if (dbeta) dbeta[c] = (float)sums[3 * c];
+      if (dgamma) dgamma[c] = (float)sums[3 * c + 1];
+      if (dhead_w) dhead_w[c] = (float)sums[3 * c + 2];
+    }
+  }
+  const float rc = 1.f / (float)count;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    long long j = i / CG;
+    const int wx = (int)(j % ww); j /= ww;
+    const int wy = (int)(j % wh);
+    const int n = (int)(j / wh);
+    const int c0 = cg * 8;
+    float xr[4][8], act[4][8], dz[4][8], dl[4];
+    bool inb[4];
+    window_dz(a, n, wy, wx, c0, xr, act, dz, inb, dl);
+    float mu[8], is[8], g[8], m1[8], m2[8];
+    ld8p(a.mean, c0, a.x.c, mu);
+    ld8p(a.invstd, c0, a.x.c, is);
+    ld8p(gamma, c0, a.x.c, g);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = c0 + k;
+      m1[k] = c < a.x.c ? (float)sums[3 * c] * rc : 0.f;
+      m2[k] = c < a.x.c ? (float)sums[3 * c + 1] * rc : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (!inb[q]) continue;
+      float o[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float xh = (xr[q][k] - mu[k]) * is[k];
+        o[k] = g[k] * is[k] * (dz[q][k] - m1[k] - xh * m2[k]);
+      }
+      *reinterpret_cast<uint4*>(at(dx, n, 2 * wy + (q >> 1), 2 * wx + (q & 1), c0)) = pack8(o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ 1x1 head (n_classes = 1)
+// LPP lanes cooperate on one pixel (8 channels each, loops if C > 8*LPP), shuffle-reduce.
+__global__ void __launch_bounds__(256)
+head_fwd_k(V x, const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ w,
+           const float* __restrict__ b, float* __restrict__ logits, int LPP) {
+  const int CG = (x.c + 7) >> 3;
+  const long long npix = (long long)x.n * x.h * x.w;
+  const int ppb = blockDim.x / LPP;
+  const int sub = threadIdx.x % LPP, slot = threadIdx.x / LPP;
+  const float bias = b ? __ldg(b) : 0.f;
+  const long long iters = (npix + (long long)gridDim.x * ppb - 1) / ((long long)gridDim.x * ppb);
+  for (long long it = 0; it < iters; ++it) {
+    const long long pi = (it * gridDim.x + blockIdx.x) * ppb + slot;
+    float acc = 0.f;
+    if (pi < npix) {
+      long long j = pi;
+      const int xx = (int)(j % x.w); j /= x.w;
+      const int yy = (int)(j % x.h);
+      const int n = (int)(j / x.h);
+      for (int cg = sub; cg < CG; cg += LPP) {
+        const int c0 = cg * 8;
+        float f[8], wv[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(at(x, n, yy, xx, c0))), f);
+        ld8p(w, c0, x.c, wv);
+        if (scale != nullptr) {
+          float sc[8], sh[8];
+          ld8p(scale, c0, x.c, sc);
+          ld8p(shift, c0, x.c, sh);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) f[k] = fmaxf(fmaf(f[k], sc[k], sh[k]), 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc = fmaf(f[k], wv[k], acc);
+      }
+    }
+    for (int o = LPP >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (pi < npix && sub == 0) logits[pi] = acc + bias;
+  }
+}
+
+// ------------------------------------------------------------------ sigmoid-BCE forward + gradient + counters
+__global__ void __launch_bounds__(256)
+bce_k(const float* __restrict__ x, const float* __restrict__ t, long long n, float gscale, float thr,
+      double* loss_sum, float* __restrict__ dlogit, unsigned long long* counts) {
+  float l = 0.f;
+  unsigned tp = 0, fp = 0, fn = 0, tn = 0;
+  const float inv_n = gscale / (float)n;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = __ldg(x + i), y = __ldg(t + i);
+    const float e = __expf(-fabsf(v));
+    l += fmaxf(v, 0.f) - v * y + log1pf(e);
+    const float sig = v >= 0.f ? 1.f / (1.f + e) : e / (1.f + e);
+    if (dlogit) dlogit[i] = (sig - y) * inv_n;
+    const bool seg = sig > thr, pos = y > 0.5f;
+    tp += seg && pos; fp += seg && !pos; fn += !seg && pos; tn += !seg && !pos;
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    l += __shfl_xor_sync(0xffffffffu, l, o);
+    tp += __shfl_xor_sync(0xffffffffu, tp, o); fp += __shfl_xor_sync(0xffffffffu, fp, o);
+    fn += __shfl_xor_sync(0xffffffffu, fn, o); tn += __shfl_xor_sync(0xffffffffu, tn, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(loss_sum, (double)l);
+    if (counts) {
+      atomicAdd(counts + 0, (unsigned long long)tp); atomicAdd(counts + 1, (unsigned long long)fp);
+      atomicAdd(counts + 2, (unsigned long long)fn); atomicAdd(counts + 3, (unsigned long long)tn);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ channel sums
+__global__ void __launch_bounds__(256) colsum_k(V x, float* out, int slots, int CG) {
+  extern __shared__ float red[];                 // [slots][CG*8]
+  const int cg = threadIdx.x % CG, slot = threadIdx.x / CG;
+  const long long npix = (long long)x.n * x.h * x.w;
+  if (slot < slots) {
+    float s[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s[k] = 0.f;
+    for (long long pi = (long long)blockIdx.x * slots + slot; pi < npix; pi += (long long)gridDim.x * slots) {
+      long long j = pi;
+      const int xx = (int)(j % x.w); j /= x.w;
+      const int yy = (int)(j % x.h);
+      const int n = (int)(j / x.h);
+      float f[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(at(x, n, yy, xx, cg * 8))), f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s[k] += f[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[((long long)slot * CG + cg) * 8 + k] = s[k];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < CG * 8; i += blockDim.x) {
+    float t = 0.f;
+    for (int s = 0; s < slots; ++s) t += red[(long long)s * CG * 8 + i];
+    if (i < x.c) atomicAdd(out + i, t);
+  }
+}
+__global__ void scale_f32_k(float* p, int n, float beta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = beta == 0.f ? 0.f : p[i] * beta;
+}
+__global__ void sum_f32_k(const float* __restrict__ x, long long n, float* out) {
+  float s = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    s += __ldg(x + i);
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+}
+
+static inline int grid_for(long long work_items, int per_block, int cap = 148 * 16) {
+  long long g = (work_items + per_block - 1) / per_block;
+  if (g < 1) g = 1;
+  if (g > cap) g = cap;
+  return (int)g;
+}
+
+}  // namespace hpri
+
+using namespace hpri;
+
+extern "C" int hpri_abi_version(void) { return 1; }
+
+extern "C" int hpri_pack_weights(const float* src, void* dst, int G, int R, int T, int C, int kc64, long long sg,
+                                 long long sr, long long st, long long sc, int flip, void* stream) {
+  if (!src || !dst || G <= 0 || R <= 0 || T <= 0 || C <= 0 || kc64 < C || (kc64 & 63)) return HPRI_ERR_ARG;
+  const long long total = (long long)G * R * T * kc64;
+  pack_weights_k<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, G, R, T, C, kc64,
+                                                                       sg, sr, st, sc, flip);
+  return last_err();
+}
+extern "C" int hpri_unpack_grads(const float* packed, float* dst, int G, int R, int T, int C, int kc64, long long sg,
+                                 long long sr, long long st, long long sc, int flip, float beta, void* stream) {
+  if (!packed || !dst || G <= 0 || R <= 0 || T <= 0 || C <= 0 || kc64 < C) return HPRI_ERR_ARG;
+  const long long total = (long long)G * R * T * kc64;
+  unpack_grads_k<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(packed, dst, G, R, T, C, kc64, sg, sr, st,
+                                                                        sc, flip, beta);
+  return last_err();
+}
+
+extern "C" int hpri_hsi_ingest(const float* src, int n, int bands_total, int H, int W, int lo, int hi, int i0,
+                               int j0, int h, int w, int flip_h, int flip_w, float scale, const float* band_mean,
+                               const float* band_std, void* dst, int c_pad, void* stream) {
+  const int nb = hi - lo;
+  if (!src || !dst || n <= 0 || lo < 0 || hi > bands_total || nb <= 0 || c_pad < nb || (c_pad & 7)) return HPRI_ERR_ARG;
+  if (i0 < 0 || j0 < 0 || i0 + h > H || j0 + w > W || h <= 0 || w <= 0 || h > 65535 || n > 65535) return HPRI_ERR_ARG;
+  if ((band_mean == nullptr) != (band_std == nullptr)) return HPRI_ERR_ARG;
+  if (reinterpret_cast<uintptr_t>(dst) & 15) return HPRI_ERR_ALIGN;
+  const size_t smem = 64 * (c_pad / 2 + 1) * 4;
+  static bool attr_done = false;
+  if (!attr_done && smem > 48 * 1024) {
+    if (cudaFuncSetAttribute(hsi_ingest_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
+      return HPRI_ERR_CUDA;
+    attr_done = true;
+  }
+  if (smem > 100 * 1024) return HPRI_ERR_ARG;
+  dim3 grid((w + 63) / 64, h, n);
+  hsi_ingest_k<<<grid, 256, smem, (cudaStream_t)stream>>>(src, bands_total, H, W, lo, nb, i0, j0, h, w, flip_h,
+                                                         flip_w, scale, band_mean, band_std, (__nv_bfloat16*)dst,
+                                                         c_pad);
+  return last_err();
+}
+extern "C" int hpri_absmax(const float* src, long long numel, float* out_max, void* stream) {
+  if (!src || !out_max || numel <= 0) return HPRI_ERR_ARG;
+  if (cudaMemsetAsync(out_max, 0, sizeof(float), (cudaStream_t)stream) != cudaSuccess) return HPRI_ERR_CUDA;
+  absmax_k<<<grid_for(numel, 256 * 8), 256, 0, (cudaStream_t)stream>>>(src, numel, out_max);
+  return last_err();
+}
+
+extern "C" int hpri_bn_finalize(double* stats, long long count, const float* gamma, const float* beta,
+                                const float* conv_bias, float* running_mean, float* running_var,
+                                long long* num_batches_tracked, float momentum, float eps, int training, float* scale,
+                                float* shift, float* save_mean, float* save_invstd, int C, void* stream) {
+  if (!scale || !shift || C <= 0) return HPRI_ERR_ARG;
+  if (training && (!stats || count <= 0)) return HPRI_ERR_ARG;
+  if (!training && (!running_mean || !running_var)) return HPRI_ERR_ARG;
+  bn_finalize_k<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, count, gamma, beta, conv_bias, running_mean,
+                                                                  running_var, num_batches_tracked, momentum, eps,
+                                                                  training, scale, shift, save_mean, save_invstd, C);
+  return last_err();
+}
+
+extern "C" int hpri_bn_relu_apply(const hpri_view_t* x, const float* scale, const float* shift, const hpri_view_t* y,
+                                  const hpri_view_t* pooled, void* stream) {
+  int rc;
+  if ((rc = check_view_e(x)) != HPRI_OK || (rc = check_view_e(y)) != HPRI_OK) return rc;
+  if (pooled && (rc = check_view_e(pooled)) != HPRI_OK) return rc;
+  if (!scale || !shift || x->n != y->n || x->h != y->h || x->w != y->w || x->c != y->c) return HPRI_ERR_ARG;
+  if (pooled && (pooled->n != x->n || pooled->h != x->h / 2 || pooled->w != x->w / 2 || pooled->c != x->c))
+    return HPRI_ERR_ARG;
+  const long long total = (long long)x->n * ((x->h + 1) / 2) * ((x->w + 1) / 2) * ((x->c + 7) / 8);
+  bn_relu_apply_k<<<grid_for(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(mk(x), scale, shift, mk(y),
+                                                                                  mk(pooled));
+  return last_err();
+}
+
+static int bwd_common(const hpri_view_t* x, const hpri_view_t* dy, const hpri_view_t* dpool, const float* head_w,
+                      const float* dlogit) {
+  int rc;
+  if ((rc = check_view_e(x)) != HPRI_OK) return rc;
+  if (dy && ((rc = check_view_e(dy)) != HPRI_OK)) return rc;
+  if (dpool && ((rc = check_view_e(dpool)) != HPRI_OK)) return rc;
+  if (dy && (dy->n != x->n || dy->h != x->h || dy->w != x->w || dy->c != x->c)) return HPRI_ERR_ARG;
+  if (dpool && (dpool->n != x->n || dpool->h != x->h / 2 || dpool->w != x->w / 2 || dpool->c != x->c))
+    return HPRI_ERR_ARG;
+  if ((head_w == nullptr) != (dlogit == nullptr)) return HPRI_ERR_ARG;
+  if (!dy && !dpool && !dlogit) return HPRI_ERR_ARG;
+  return HPRI_OK;
+}
+
+extern "C" int hpri_bn_relu_bwd_reduce(const hpri_view_t* x, const float* scale, const float* shift,
+                                       const float* save_mean, const float* save_invstd, const hpri_view_t* dy,
+                                       const hpri_view_t* dpool, const float* head_w, const float* dlogit,
+                                       double* sums, void* stream) {
+  int rc;
+  if ((rc = bwd_common(x, dy, dpool, head_w, dlogit)) != HPRI_OK) return rc;
+  if (!scale || !shift || !save_mean || !save_invstd || !sums) return HPRI_ERR_ARG;
+  const int CG = (x->c + 7) / 8;
+  if (CG > 256) return HPRI_ERR_ARG;
+  const int slots = 256 / CG;
+  const size_t smem = (size_t)slots * CG * 24 * 4;
+  if (smem > 48 * 1024) return HPRI_ERR_ARG;
+  if (cudaMemsetAsync(sums, 0, sizeof(double) * 3 * x->c, (cudaStream_t)stream) != cudaSuccess) return HPRI_ERR_CUDA;
+  BwdIn a{mk(x), mk(dy), mk(dpool), scale, shift, save_mean, save_invstd, head_w, dlogit};
+  const long long nwin = (long long)x->n * ((x->h + 1) / 2) * ((x->w + 1) / 2);
+  bn_bwd_reduce_k<<<grid_for(nwin, slots * 4, 148 * 8), 256, smem, (cudaStream_t)stream>>>(a, sums, slots, CG);
+  return last_err();
+}
+
+extern "C" int hpri_bn_relu_bwd_apply(const hpri_view_t* x, const float* scale, const float* shift,
+                                      const float* save_mean, const float* save_invstd, const float* gamma,
+                                      const hpri_view_t* dy, const hpri_view_t* dpool, const float* head_w,
+                                      const float* dlogit, double* sums, long long count, const hpri_view_t* dx,
+                                      float* dgamma, float* dbeta, float* dhead_w, void* stream) {
+  int rc;
+  if ((rc = bwd_common(x, dy, dpool, head_w, dlogit)) != HPRI_OK) return rc;
+  if ((rc = check_view_e(dx)) != HPRI_OK) return rc;
+  if (!scale || !shift || !save_mean || !save_invstd || !gamma || !sums || count <= 0) return HPRI_ERR_ARG;
+  if (dx->n != x->n || dx->h != x->h || dx->w != x->w || dx->c != x->c) return HPRI_ERR_ARG;
+  BwdIn a{mk(x), mk(dy), mk(dpool), scale, shift, save_mean, save_invstd, head_w, dlogit};
+  const long long total = (long long)x->n * ((x->h + 1) / 2) * ((x->w + 1) / 2) * ((x->c + 7) / 8);
+  bn_bwd_apply_k<<<grid_for(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(a, gamma, sums, count, mk(dx),
+                                                                                 dgamma, dbeta, dhead_w);
+  return last_err();
+}
+
+extern "C" int hpri_head_fwd(const hpri_view_t* x, const float* scale, const float* shift, const float* w,
+                             const float* b, float* logits, void* stream) {
+  int rc;
+  if ((rc = check_view_e(x)) != HPRI_OK) return rc;
+  if (!w || !logits || ((scale == nullptr) != (shift == nullptr))) return HPRI_ERR_ARG;
+  const int CG = (x->c + 7) / 8;
+  int LPP = 1;
+  while (LPP < CG && LPP < 32) LPP <<= 1;
+  const long long npix = (long long)x->n * x->h * x->w;
+  head_fwd_k<<<grid_for(npix, 256 / LPP, 148 * 32), 256, 0, (cudaStream_t)stream>>>(mk(x), scale, shift, w, b, logits,
+                                                                                  LPP);
+  return last_err();
+}
+
+extern "C" int hpri_bce_fwd_bwd(const float* logits, const float* target, long long numel, float grad_scale,
+                                float thr, double* loss_sum, float* dlogit, unsigned long long* counts,
+                                void* stream) {
+  if (!logits || !target || !loss_sum || numel <= 0) return HPRI_ERR_ARG;
+  if (cudaMemsetAsync(loss_sum, 0, sizeof(double), (cudaStream_t)stream) != cudaSuccess) return HPRI_ERR_CUDA;
+  if (counts && cudaMemsetAsync(counts, 0, 4 * sizeof(unsigned long long), (cudaStream_t)stream) != cudaSuccess)
+    return HPRI_ERR_CUDA;
+  bce_k<<<grid_for(numel, 256 * 4), 256, 0, (cudaStream_t)stream>>>(logits, target, numel, grad_scale, thr, loss_sum,
+                                                                   dlogit, counts);
+  return last_err();
+}
+
+extern "C" int hpri_colsum(const hpri_view_t* x, float* out, float beta, void* stream) {
+  int rc;
+  if ((rc = check_view_e(x)) != HPRI_OK) return rc;
+  if (!out) return HPRI_ERR_ARG;
+  const int CG = (x->c + 7) / 8;
+  if (CG > 256) return HPRI_ERR_ARG;
+  const int slots = 256 / CG;
+  scale_f32_k<<<(x->c + 255) / 256, 256, 0, (cudaStream_t)stream>>>(out, x->c, beta);
+  const long long npix = (long long)x->n * x->h * x->w;
+  colsum_k<<<grid_for(npix, slots * 16, 148 * 4), 256, (size_t)slots * CG * 32, (cudaStream_t)stream>>>(mk(x), out,
+                                                                                                       slots, CG);
+  return last_err();
+}
+extern "C" int hpri_sum_f32(const float* x, long long numel, float* out, void* stream) {
+  if (!x || !out || numel <= 0) return HPRI_ERR_ARG;
+  if (cudaMemsetAsync(out, 0, sizeof(float), (cudaStream_t)stream) != cudaSuccess) return HPRI_ERR_CUDA;
+  sum_f32_k<<<grid_for(numel, 256 * 8, 148 * 4), 256, 0, (cudaStream_t)stream>>>(x, numel, out);
+  return last_err();
+}

@@ -1,0 +1,200 @@
+"""Tensor-level wrappers over the C ABI (include/hyperpri_b200.h).
+
+Every function takes CUDA torch tensors, passes raw pointers / strides / the current stream to
+the native library and returns immediately (stream-ordered).  torch is used for device memory
+and streams only; no arithmetic on the hot path is done by torch here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import View, check
+
+bf16 = torch.bfloat16
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def view(t: Optional[torch.Tensor], c: Optional[int] = None) -> Optional[View]:
+    """hpri_view_t of an NHWC bf16 tensor (any strided slice whose channel stride is 1).
+    `c` overrides the logical channel count (e.g. 1650 of a 1664-wide buffer)."""
+    if t is None:
+        return None
+    assert t.dtype == bf16 and t.dim() == 4 and t.is_cuda, (t.dtype, t.shape)
+    assert t.stride(3) == 1
+    n, h, w, cc = t.shape
+    return View(t.data_ptr(), n, h, w, cc if c is None else c, t.stride(2), t.stride(1), t.stride(0))
+
+
+def _vp(v: Optional[View]):
+    return None if v is None else C.byref(v)
+
+
+def kpad(c: int) -> int:
+    return (c + 63) // 64 * 64
+
+
+# ----------------------------------------------------------------------------- weights
+def pack(src: torch.Tensor, G, R, T, Cc, sg, sr, st, sc, flip=False, out: Optional[torch.Tensor] = None):
+    """Generic fp32 parameter -> bf16 operand [(G*R), T*kpad(C)] (see hpri_pack_weights)."""
+    assert src.dtype == torch.float32 and src.is_cuda and src.is_contiguous()
+    kc = kpad(Cc)
+    if out is None:
+        out = torch.empty((G * R, T * kc), dtype=bf16, device=src.device)
+    check(_lib.lib().hpri_pack_weights(_ptr(src), _ptr(out), G, R, T, Cc, kc, sg, sr, st, sc, int(flip), _stream()),
+          "hpri_pack_weights")
+    return out
+
+
+def unpack(packed: torch.Tensor, dst: torch.Tensor, G, R, T, Cc, sg, sr, st, sc, flip=False, beta=0.0):
+    assert packed.dtype == torch.float32 and dst.dtype == torch.float32 and dst.is_contiguous()
+    check(_lib.lib().hpri_unpack_grads(_ptr(packed), _ptr(dst), G, R, T, Cc, kpad(Cc), sg, sr, st, sc, int(flip),
+                                       float(beta), _stream()), "hpri_unpack_grads")
+    return dst
+
+
+class WeightSpec:
+    """Index maps between a torch-layout fp32 parameter and the packed GEMM operands."""
+
+    def __init__(self, kind: str, cout: int, cin: int, split: int = 0):
+        self.kind, self.cout, self.cin, self.split = kind, cout, cin, split
+        if kind == "conv3x3":          # W[co, ci, 3, 3]
+            self.fwd = dict(G=1, R=cout, T=9, Cc=cin, sg=0, sr=cin * 9, st=1, sc=9)
+            self.dgr = dict(G=1, R=cin, T=9, Cc=cout, sg=0, sr=9, st=1, sc=cin * 9, flip=True)
+            self.rows, self.taps = cout, 9
+        elif kind == "linear":         # W[out, in]; split>0: input is cat of two `split`-wide halves,
+            if split:                  # each padded to kpad(split) in the activation buffer
+                assert cin == 2 * split
+                self.fwd = dict(G=1, R=cout, T=2, Cc=split, sg=0, sr=cin, st=split, sc=1)
+                self.dgr = None        # dgrad of a concat input is done per half
+            else:
+                self.fwd = dict(G=1, R=cout, T=1, Cc=cin, sg=0, sr=cin, st=0, sc=1)
+                self.dgr = dict(G=1, R=cin, T=1, Cc=cout, sg=0, sr=1, st=0, sc=cin)
+            self.rows, self.taps = cout, 1
+        elif kind == "convT2x2":       # W[ci, co, 2, 2]; fwd rows (a*2+b)*co, K = ci
+            self.fwd = dict(G=4, R=cout, T=1, Cc=cin, sg=1, sr=4, st=0, sc=cout * 4)
+            self.dgr = dict(G=1, R=cin, T=4, Cc=cout, sg=0, sr=cout * 4, st=1, sc=4)
+            self.rows, self.taps = 4 * cout, 1
+        else:
+            raise ValueError(kind)
+
+    def pack_fwd(self, w, out=None):
+        return pack(w, out=out, **self.fwd)
+
+    def pack_dgrad(self, w, out=None):
+        return pack(w, out=out, **self.dgr)
+
+    def grad_buffer(self, device):
+        f = self.fwd
+        return torch.zeros((f["G"] * f["R"], f["T"] * kpad(f["Cc"])), dtype=torch.float32, device=device)
+
+    def unpack_grad(self, packed, dst, beta=0.0):
+        f = dict(self.fwd)
+        return unpack(packed, dst, beta=beta, **f)
+
+
+# ----------------------------------------------------------------------------- contractions
+def igemm_fwd(x, wpack, rows, taps, y, n_store, bias=None, stats=None, block_n=0, x_c=None, y_c=None):
+    xv, yv = view(x, x_c), view(y, y_c)
+    check(_lib.lib().hpri_igemm_fwd(_vp(xv), _ptr(wpack), rows, wpack.shape[1], taps, _vp(yv), n_store, _ptr(bias),
+                                    _ptr(stats), block_n, _stream()), "hpri_igemm_fwd")
+
+
+def convT_fwd(x, wpack, cout, y, bias=None, block_n=0):
+    xv, yv = view(x), view(y)
+    check(_lib.lib().hpri_convT2x2_fwd(_vp(xv), _ptr(wpack), cout, wpack.shape[1], _vp(yv), _ptr(bias), block_n,
+                                       _stream()), "hpri_convT2x2_fwd")
+
+
+def convT_dgrad(dy, wpack, cin, dx, block_n=0):
+    dv, xv = view(dy), view(dx)
+    check(_lib.lib().hpri_convT2x2_dgrad(_vp(dv), _ptr(wpack), cin, wpack.shape[1], _vp(xv), block_n, _stream()),
+          "hpri_convT2x2_dgrad")
+
+
+def igemm_wgrad(x, dy, mode, n_total, dw, block_n=0, splits=0, x_c=None, dy_c=None):
+    xv, dv = view(x, x_c), view(dy, dy_c)
+    assert dw.dtype == torch.float32 and dw.is_contiguous()
+    check(_lib.lib().hpri_igemm_wgrad(_vp(xv), _vp(dv), mode, n_total, _ptr(dw), dw.shape[1], block_n, splits,
+                                      _stream()), "hpri_igemm_wgrad")
+
+
+# ----------------------------------------------------------------------------- ingest
+def hsi_ingest(src, lo, hi, crop=None, flip_h=False, flip_w=False, scale=1.0, band_mean=None, band_std=None,
+               c_pad=None, out=None):
+    """src fp32 [N, bands, H, W] -> NHWC bf16 [N, h, w, c_pad]."""
+    assert src.dtype == torch.float32 and src.is_contiguous() and src.dim() == 4
+    n, bt, H, W = src.shape
+    i0, j0, h, w = crop if crop is not None else (0, 0, H, W)
+    nb = hi - lo
+    c_pad = c_pad or (nb + 7) // 8 * 8
+    if out is None:
+        out = torch.empty((n, h, w, c_pad), dtype=bf16, device=src.device)
+    check(_lib.lib().hpri_hsi_ingest(_ptr(src), n, bt, H, W, lo, hi, i0, j0, h, w, int(flip_h), int(flip_w),
+                                     float(scale), _ptr(band_mean), _ptr(band_std), _ptr(out), c_pad, _stream()),
+          "hpri_hsi_ingest")
+    return out
+
+
+def absmax(src):
+    out = torch.empty(1, dtype=torch.float32, device=src.device)
+    check(_lib.lib().hpri_absmax(_ptr(src), src.numel(), _ptr(out), _stream()), "hpri_absmax")
+    return out
+
+
+# ----------------------------------------------------------------------------- BN / ReLU / pool
+def bn_finalize(stats, count, gamma, beta, conv_bias, rmean, rvar, nbt, training, scale, shift, smean, sinv,
+                C_, momentum=0.1, eps=1e-5):
+    check(_lib.lib().hpri_bn_finalize(_ptr(stats), count, _ptr(gamma), _ptr(beta), _ptr(conv_bias), _ptr(rmean),
+                                      _ptr(rvar), _ptr(nbt), momentum, eps, int(training), _ptr(scale), _ptr(shift),
+                                      _ptr(smean), _ptr(sinv), C_, _stream()), "hpri_bn_finalize")
+
+
+def bn_relu_apply(x, scale, shift, y, pooled=None, c=None):
+    xv, yv, pv = view(x, c), view(y, c), view(pooled, c)
+    check(_lib.lib().hpri_bn_relu_apply(_vp(xv), _ptr(scale), _ptr(shift), _vp(yv), _vp(pv), _stream()),
+          "hpri_bn_relu_apply")
+
+
+def bn_relu_bwd(x, scale, shift, smean, sinv, gamma, dx, sums, count, dy=None, dpool=None, head_w=None,
+                dlogit=None, dgamma=None, dbeta=None, dhead_w=None, c=None):
+    xv, dyv, dpv, dxv = view(x, c), view(dy, c), view(dpool, c), view(dx, c)
+    L = _lib.lib()
+    check(L.hpri_bn_relu_bwd_reduce(_vp(xv), _ptr(scale), _ptr(shift), _ptr(smean), _ptr(sinv), _vp(dyv), _vp(dpv),
+                                    _ptr(head_w), _ptr(dlogit), _ptr(sums), _stream()), "hpri_bn_relu_bwd_reduce")
+    check(L.hpri_bn_relu_bwd_apply(_vp(xv), _ptr(scale), _ptr(shift), _ptr(smean), _ptr(sinv), _ptr(gamma), _vp(dyv),
+                                   _vp(dpv), _ptr(head_w), _ptr(dlogit), _ptr(sums), count, _vp(dxv), _ptr(dgamma),
+                                   _ptr(dbeta), _ptr(dhead_w), _stream()), "hpri_bn_relu_bwd_apply")
+
+
+# ----------------------------------------------------------------------------- head / loss
+def head_fwd(x, scale, shift, w, b, logits, c=None):
+    xv = view(x, c)
+    check(_lib.lib().hpri_head_fwd(_vp(xv), _ptr(scale), _ptr(shift), _ptr(w), _ptr(b), _ptr(logits), _stream()),
+          "hpri_head_fwd")
+
+
+def bce_fwd_bwd(logits, target, loss_sum, dlogit=None, counts=None, grad_scale=1.0, thr=0.5):
+    assert logits.dtype == torch.float32 and target.dtype == torch.float32
+    assert logits.is_contiguous() and target.is_contiguous()
+    check(_lib.lib().hpri_bce_fwd_bwd(_ptr(logits), _ptr(target), logits.numel(), grad_scale, thr, _ptr(loss_sum),
+                                      _ptr(dlogit), _ptr(counts), _stream()), "hpri_bce_fwd_bwd")
+
+
+def colsum(x, out, beta=0.0, c=None):
+    xv = view(x, c)
+    check(_lib.lib().hpri_colsum(_vp(xv), _ptr(out), beta, _stream()), "hpri_colsum")
+
+
+def sum_f32(x, out):
+    check(_lib.lib().hpri_sum_f32(_ptr(x), x.numel(), _ptr(out), _stream()), "hpri_sum_f32")

@@ -1,0 +1,112 @@
+/* hyperpri_b200 -- C ABI of the B200-native HyperPRI segmentation hot path.
+ *
+ * The reference (GatorSense/HyperPRI) has no FFI: every FLOP on its hot path is a stock
+ * torch.nn call (cuDNN / cuBLAS / ATen).  Each entry point below replaces one of those
+ * library call sites (cited file:line, relative to the reference root).  All functions
+ *   - take raw DEVICE pointers, plain sizes and a cudaStream_t passed as void*,
+ *   - enqueue work on that stream and return immediately (no allocation, no host sync),
+ *   - return HPRI_OK (0) or a negative HPRI_ERR_* code; they never fall back to a CPU path.
+ *
+ * Activations are NHWC bf16, described by hpri_view_t so that channel sub-ranges of a concat
+ * buffer and cropped windows are expressed with strides instead of copies.
+ */
+#ifndef HYPERPRI_B200_H
+#define HYPERPRI_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HPRI_OK 0
+#define HPRI_ERR_ARG (-1)       /* inconsistent shapes / null pointer / unsupported option */
+#define HPRI_ERR_ALIGN (-2)     /* pointer or stride not 16-byte aligned */
+#define HPRI_ERR_DRIVER (-3)    /* cuTensorMapEncodeTiled not obtainable from the driver */
+#define HPRI_ERR_TENSORMAP (-4) /* the driver rejected a tensor map */
+#define HPRI_ERR_CUDA (-5)      /* launch failed; see cudaGetLastError */
+
+/* NHWC bf16 view: element strides; c = logical channels visible through the view. */
+typedef struct {
+  void* ptr;
+  int n, h, w, c;
+  long long pix_stride, row_stride, img_stride;
+} hpri_view_t;
+
+int hpri_abi_version(void);
+
+/* ---- tensor-core contractions (tcgen05 implicit GEMM, csrc/igemm.cu) ------------------- */
+
+/* y[n,h,w,:] = sum_{tap,c} x[n,h+dh,w+dw,c] * wpack[:, tap*kc*64+c] (+bias); taps = 9 (3x3, pad 1)
+ * or 1 (1x1 / Linear).  Replaces nn.Conv2d 3x3 fprop AND dgrad (model_parts.py:22,25 -- dgrad uses a
+ * transposed/flipped pack), Conv3d(1,64,(D,3,3)) (models.py:169), nn.Linear (models.py:108,102).
+ * stats (nullable): double[w_rows][2] accumulating per-channel sum / sum-of-squares of the bf16
+ * outputs for train-mode BatchNorm (model_parts.py:23,26; models.py:113,172,178). */
+int hpri_igemm_fwd(const hpri_view_t* x, const void* wpack, int w_rows, int kpad, int taps, const hpri_view_t* y,
+                   int n_store, const float* bias, double* stats, int block_n, void* stream);
+
+/* nn.ConvTranspose2d(k=2,s=2) fprop writing straight into the concat buffer (model_parts.py:63-64,
+ * 74-87: pad + cat are absorbed by the destination view) and its dgrad. */
+int hpri_convT2x2_fwd(const hpri_view_t* x, const void* wpack, int cout, int kpad, const hpri_view_t* y,
+                      const float* bias, int block_n, void* stream);
+int hpri_convT2x2_dgrad(const hpri_view_t* dy, const void* wpack, int cin, int kpad, const hpri_view_t* dx,
+                        int block_n, void* stream);
+
+/* Weight gradients (autograd of the three layer kinds above). mode 0 Linear/1x1, 1 conv3x3, 2 convT2x2.
+ * dw: fp32 [n_total][dw_ld] in forward-pack layout, accumulated into. */
+int hpri_igemm_wgrad(const hpri_view_t* x, const hpri_view_t* dy, int mode, int n_total, float* dw, int dw_ld,
+                     int block_n, int splits, void* stream);
+
+/* ---- weight layout conversion (csrc/elementwise.cu) -------------------------------------
+ * dst[(g*R + r)][t*kc64 + c] = c < C ? src[g*sg + r*sr + tm(t)*st + c*sc] : 0,  tm(t) = flip ? T-1-t : t.
+ * pack: fp32 torch-layout parameter -> bf16 operand.  unpack: fp32 packed gradient -> fp32 torch layout. */
+int hpri_pack_weights(const float* src, void* dst_bf16, int G, int R, int T, int C, int kc64, long long sg,
+                      long long sr, long long st, long long sc, int flip, void* stream);
+int hpri_unpack_grads(const float* packed, float* dst, int G, int R, int T, int C, int kc64, long long sg,
+                      long long sr, long long st, long long sc, int flip, float beta, void* stream);
+
+/* ---- ingest (src/dataset.py:266-270, 284-289) -------------------------------------------
+ * src: fp32 [n][bands_total][H][W]; keeps bands [lo,hi), crops the (i0,j0,h,w) window, optional
+ * horizontal / vertical flip, optional scalar rescale (the '/255 if max>10' rule is decided by the caller
+ * with hpri_absmax), optional per-band (x-mean)/std; writes NHWC bf16 with c_pad channels (zero filled). */
+int hpri_hsi_ingest(const float* src, int n, int bands_total, int H, int W, int lo, int hi, int i0, int j0, int h,
+                    int w, int flip_h, int flip_w, float scale, const float* band_mean, const float* band_std,
+                    void* dst_bf16, int c_pad, void* stream);
+int hpri_absmax(const float* src, long long numel, float* out_max, void* stream);
+
+/* ---- BatchNorm / ReLU / MaxPool family ---------------------------------------------------- */
+/* Turn accumulated (sum, sumsq) into scale/shift, saved mean/invstd, and the running-stat update
+ * (biased var to normalise, unbiased for running_var, momentum 0.1, conv bias re-added to the mean);
+ * zeroes stats for the next step.  training=0: coefficients from the running stats. */
+int hpri_bn_finalize(double* stats, long long count, const float* gamma, const float* beta, const float* conv_bias,
+                     float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
+                     float eps, int training, float* scale, float* shift, float* save_mean, float* save_invstd,
+                     int C, void* stream);
+/* y = relu(x*scale+shift) (model_parts.py:23-24); optional fused MaxPool2d(2) output (model_parts.py:40). */
+int hpri_bn_relu_apply(const hpri_view_t* x, const float* scale, const float* shift, const hpri_view_t* y,
+                       const hpri_view_t* pooled, void* stream);
+/* Backward of relu(bn(x)): pass 1 reduces sum(dz), sum(dz*xhat); pass 2 writes dx.
+ * dy (nullable) direct gradient; dpool (nullable) gradient of the pooled output, routed to the arg-max;
+ * head_w/dlogit (nullable): dy[p,c] += dlogit[p]*head_w[c] (OutConv backward, model_parts.py:96). */
+int hpri_bn_relu_bwd_reduce(const hpri_view_t* x, const float* scale, const float* shift, const float* save_mean,
+                            const float* save_invstd, const hpri_view_t* dy, const hpri_view_t* dpool,
+                            const float* head_w, const float* dlogit, double* sums /*[C][3]*/, void* stream);
+int hpri_bn_relu_bwd_apply(const hpri_view_t* x, const float* scale, const float* shift, const float* save_mean,
+                           const float* save_invstd, const float* gamma, const hpri_view_t* dy,
+                           const hpri_view_t* dpool, const float* head_w, const float* dlogit, double* sums,
+                           long long count, const hpri_view_t* dx, float* dgamma, float* dbeta, float* dhead_w,
+                           void* stream);
+
+/* ---- head + loss (model_parts.py:96; PLTrainer.py:86) ------------------------------------ */
+/* logits[n,0,h,w] = b + sum_c relu(x*scale+shift)[c]*w[c]; fp32 NCHW output. */
+int hpri_head_fwd(const hpri_view_t* x, const float* scale, const float* shift, const float* w, const float* b,
+                  float* logits, void* stream);
+/* mean BCE-with-logits and dlogit = grad_scale*(sigmoid(x)-t)/numel; counts = TP,FP,FN,TN at thr. */
+int hpri_bce_fwd_bwd(const float* logits, const float* target, long long numel, float grad_scale, float thr,
+                     double* loss_sum, float* dlogit, unsigned long long* counts, void* stream);
+/* out[c] (+)= sum over pixels of the view (ConvT bias grad; Linear bias grad). */
+int hpri_colsum(const hpri_view_t* x, float* out, float beta, void* stream);
+int hpri_sum_f32(const float* x, long long numel, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,304 @@
+"""Per-kernel parity on a B200: every C-ABI entry point against a plain PyTorch fp32 reference of
+the same op on identical (bf16-rounded) inputs.  Tolerances are stated per test."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from hyperpri_b200 import ops  # noqa: E402
+
+DEV = "cuda"
+
+
+@pytest.fixture(autouse=True, scope="module")
+def _no_tf32():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+
+
+def nhwc(x_nchw, cpad=None):
+    n, c, h, w = x_nchw.shape
+    cpad = cpad or c
+    out = torch.zeros((n, h, w, cpad), dtype=torch.bfloat16, device=x_nchw.device)
+    out[..., :c] = x_nchw.permute(0, 2, 3, 1).to(torch.bfloat16)
+    return out
+
+
+def nchw(x_nhwc, c=None):
+    x = x_nhwc.float().permute(0, 3, 1, 2)
+    return x if c is None else x[:, :c]
+
+
+def rnd(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed + sum(shape))
+    return (torch.randn(*shape, generator=g) * scale).to(DEV)
+
+
+def relerr(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-20)).item()
+
+
+CONV_CASES = [
+    # n, h, w, cin, cout, block_n
+    (2, 16, 24, 64, 64, 0),
+    (1, 20, 40, 240, 64, 0),
+    (2, 9, 13, 128, 256, 0),
+    (1, 11, 70, 128, 128, 0),
+    (1, 38, 60, 512, 1024, 0),
+    (1, 16, 16, 8, 64, 0),
+    (1, 24, 40, 256, 256, 128),
+]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,bn", CONV_CASES)
+def test_conv3x3_fwd_and_stats(n, h, w, cin, cout, bn):
+    x = rnd(n, cin, h, w, seed=1)
+    wt = rnd(cout, cin, 3, 3, scale=1 / math.sqrt(cin * 9), seed=2)
+    xb = nhwc(x)
+    spec = ops.WeightSpec("conv3x3", cout, cin)
+    wp = spec.pack_fwd(wt)
+    y = torch.full((n, h, w, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
+    stats = torch.zeros((cout, 2), dtype=torch.float64, device=DEV)
+    ops.igemm_fwd(xb, wp, cout, 9, y, cout, stats=stats, block_n=bn)
+    torch.cuda.synchronize()
+    ref = F.conv2d(nchw(xb), wt.to(torch.bfloat16).float(), padding=1)
+    got = nchw(y)
+    assert torch.isfinite(got).all()
+    # bf16 output rounding: half-ulp relative 2^-9 of each value, fp32 accumulation order differences
+    assert relerr(got, ref) < 6e-3
+    g64 = y.double().reshape(-1, cout)
+    assert torch.allclose(stats[:, 0], g64.sum(0), rtol=1e-6, atol=1e-3)
+    assert torch.allclose(stats[:, 1], (g64 * g64).sum(0), rtol=1e-6, atol=1e-3)
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,bn", CONV_CASES[:5])
+def test_conv3x3_dgrad(n, h, w, cin, cout, bn):
+    dy = rnd(n, cout, h, w, seed=3)
+    wt = rnd(cout, cin, 3, 3, scale=1 / math.sqrt(cout * 9), seed=4)
+    dyb = nhwc(dy)
+    spec = ops.WeightSpec("conv3x3", cout, cin)
+    wp = spec.pack_dgrad(wt)
+    cpad = (cin + 7) // 8 * 8
+    dx = torch.full((n, h, w, cpad), float("nan"), dtype=torch.bfloat16, device=DEV)
+    ops.igemm_fwd(dyb, wp, cin, 9, dx, cpad, block_n=bn)
+    torch.cuda.synchronize()
+    ref = F.conv_transpose2d(nchw(dyb), wt.to(torch.bfloat16).float(), padding=1)
+    assert relerr(nchw(dx, cin), ref) < 6e-3
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,bn", CONV_CASES)
+def test_conv3x3_wgrad(n, h, w, cin, cout, bn):
+    x = rnd(n, cin, h, w, seed=5)
+    dy = rnd(n, cout, h, w, seed=6)
+    xb, dyb = nhwc(x), nhwc(dy)
+    spec = ops.WeightSpec("conv3x3", cout, cin)
+    dwp = spec.grad_buffer(DEV)
+    ops.igemm_wgrad(xb, dyb, 1, cout, dwp, block_n=bn)
+    dw = torch.empty((cout, cin, 3, 3), dtype=torch.float32, device=DEV)
+    spec.unpack_grad(dwp, dw)
+    torch.cuda.synchronize()
+    ref = torch.nn.grad.conv2d_weight(nchw(xb), (cout, cin, 3, 3), nchw(dyb), padding=1)
+    # fp32 accumulate of exact bf16 products; split-K changes summation order only
+    assert relerr(dw, ref) < 2e-4
+
+
+CONVT_CASES = [(2, 8, 12, 128, 64, 16, 25), (1, 19, 30, 1024, 512, 38, 61), (1, 5, 7, 256, 128, 10, 14)]
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout,H2,W2", CONVT_CASES)
+def test_convT(n, h, w, cin, cout, H2, W2):
+    x = rnd(n, cin, h, w, seed=7)
+    wt = rnd(cin, cout, 2, 2, scale=1 / math.sqrt(cin), seed=8)
+    bias = rnd(cout, seed=9)
+    xb = nhwc(x)
+    spec = ops.WeightSpec("convT2x2", cout, cin)
+    # destination: second half of a (2*cout)-channel concat buffer at skip resolution H2 x W2
+    cat = torch.zeros((n, H2, W2, 2 * cout), dtype=torch.bfloat16, device=DEV)
+    ops.convT_fwd(xb, spec.pack_fwd(wt), cout, cat[..., cout:], bias=bias)
+    torch.cuda.synchronize()
+    wq = wt.to(torch.bfloat16).float()
+    ref = F.conv_transpose2d(nchw(xb), wq, bias, stride=2)
+    ref = F.pad(ref, [0, W2 - 2 * w, 0, H2 - 2 * h])
+    assert relerr(nchw(cat[..., cout:]), ref) < 6e-3
+    assert (cat[..., :cout] == 0).all()
+    # dgrad / wgrad against autograd
+    dcat = torch.zeros((n, H2, W2, 2 * cout), dtype=torch.bfloat16, device=DEV)
+    dcat[..., cout:] = nhwc(rnd(n, cout, H2, W2, seed=10))
+    dyv = dcat[..., cout:]
+    dx = torch.full((n, h, w, cin), float("nan"), dtype=torch.bfloat16, device=DEV)
+    ops.convT_dgrad(dyv, spec.pack_dgrad(wt), cin, dx)
+    dwp = spec.grad_buffer(DEV)
+    ops.igemm_wgrad(xb, dyv, 2, 4 * cout, dwp)
+    dw = torch.empty_like(wt)
+    spec.unpack_grad(dwp, dw)
+    db = torch.empty(cout, dtype=torch.float32, device=DEV)
+    ops.colsum(dyv[:, :2 * h, :2 * w], db)
+    torch.cuda.synchronize()
+    xr = nchw(xb).requires_grad_(True)
+    wr = wq.clone().requires_grad_(True)
+    br = bias.clone().requires_grad_(True)
+    out = F.conv_transpose2d(xr, wr, br, stride=2)
+    out.backward(nchw(dyv)[:, :, :2 * h, :2 * w].contiguous())
+    assert relerr(nchw(dx), xr.grad) < 6e-3
+    assert relerr(dw, wr.grad) < 2e-4
+    assert relerr(db, br.grad) < 1e-4
+
+
+@pytest.mark.parametrize("m,fin,fout,split", [(3000, 238, 1650, 0), (1000, 1650, 1650, 0), (777, 3300, 1650, 1650),
+                                              (4096, 64, 128, 0)])
+def test_linear(m, fin, fout, split):
+    """nn.Linear over M pixels (SpectralUNET blocks): fwd, dgrad, wgrad with padded feature strides."""
+    pad = lambda f: (f + 63) // 64 * 64
+    if split:
+        xa, xb_ = rnd(m, split, seed=11), rnd(m, split, seed=12)
+        buf = torch.zeros((1, 1, m, 2 * pad(split)), dtype=torch.bfloat16, device=DEV)
+        buf[0, 0, :, :split] = xa.to(torch.bfloat16)
+        buf[0, 0, :, pad(split):pad(split) + split] = xb_.to(torch.bfloat16)
+        xfull = torch.cat([buf[0, 0, :, :split], buf[0, 0, :, pad(split):pad(split) + split]], 1).float()
+    else:
+        buf = torch.zeros((1, 1, m, pad(fin)), dtype=torch.bfloat16, device=DEV)
+        buf[0, 0, :, :fin] = rnd(m, fin, seed=11).to(torch.bfloat16)
+        xfull = buf[0, 0, :, :fin].float()
+    wt = rnd(fout, fin, scale=1 / math.sqrt(fin), seed=13)
+    spec = ops.WeightSpec("linear", fout, fin, split=split)
+    y = torch.full((1, 1, m, pad(fout)), float("nan"), dtype=torch.bfloat16, device=DEV)
+    stats = torch.zeros((fout, 2), dtype=torch.float64, device=DEV)
+    ops.igemm_fwd(buf, spec.pack_fwd(wt), fout, 1, y, pad(fout), stats=stats)
+    torch.cuda.synchronize()
+    wq = wt.to(torch.bfloat16).float()
+    ref = xfull @ wq.t()
+    assert relerr(y[0, 0, :, :fout].float(), ref) < 6e-3
+    assert (y[0, 0, :, fout:] == 0).all()          # pad features are written as exact zeros
+    assert torch.allclose(stats[:, 0], y[0, 0, :, :fout].double().sum(0), rtol=1e-6, atol=1e-3)
+    dy = torch.zeros((1, 1, m, pad(fout)), dtype=torch.bfloat16, device=DEV)
+    dy[0, 0, :, :fout] = rnd(m, fout, seed=14).to(torch.bfloat16)
+    dwp = spec.grad_buffer(DEV)
+    ops.igemm_wgrad(buf, dy, 0, fout, dwp, dy_c=fout)
+    dw = torch.empty_like(wt)
+    spec.unpack_grad(dwp, dw)
+    torch.cuda.synchronize()
+    assert relerr(dw, dy[0, 0, :, :fout].float().t() @ xfull) < 2e-4
+    if not split:
+        dx = torch.full((1, 1, m, pad(fin)), float("nan"), dtype=torch.bfloat16, device=DEV)
+        ops.igemm_fwd(dy, spec.pack_dgrad(wt), fin, 1, dx, pad(fin), x_c=fout)
+        torch.cuda.synchronize()
+        assert relerr(dx[0, 0, :, :fin].float(), dy[0, 0, :, :fout].float() @ wq) < 6e-3
+
+
+def test_ingest_exact():
+    """Band slice / crop / flip / layout are pure indexing: exact up to the bf16 cast (dataset.py:266-270)."""
+    src = torch.rand((2, 299, 20, 37), device=DEV)
+    out = ops.hsi_ingest(src, 25, 263, c_pad=240)
+    ref = src[:, 25:263].permute(0, 2, 3, 1).to(torch.bfloat16)
+    assert torch.equal(out[..., :238], ref) and (out[..., 238:] == 0).all()
+    out = ops.hsi_ingest(src, 25, 263, crop=(3, 5, 12, 30), flip_w=True, c_pad=240)
+    ref = src[:, 25:263, 3:15, 5:35].flip(-1).permute(0, 2, 3, 1).to(torch.bfloat16)
+    assert torch.equal(out[..., :238], ref)
+    mean = torch.rand(238, device=DEV)
+    std = torch.rand(238, device=DEV) + 0.5
+    out = ops.hsi_ingest(src * 255, 25, 263, flip_h=True, scale=1 / 255, band_mean=mean, band_std=std, c_pad=240)
+    ref = ((src[:, 25:263] * 255 * (1 / 255) - mean[:, None, None]) / std[:, None, None]).flip(-2)
+    assert (out[..., :238].float() - ref.permute(0, 2, 3, 1)).abs().max() < 2e-2
+    assert ops.absmax(src * 255).item() == (src * 255).abs().max().item()
+    rgb = torch.rand((2, 3, 9, 70), device=DEV)
+    out = ops.hsi_ingest(rgb, 0, 3, c_pad=8)
+    assert torch.equal(out[..., :3], rgb.permute(0, 2, 3, 1).to(torch.bfloat16)) and (out[..., 3:] == 0).all()
+
+
+@pytest.mark.parametrize("n,h,w,c,pool", [(2, 12, 17, 64, True), (1, 7, 9, 128, False), (2, 6, 10, 1024, True),
+                                          (1, 1, 500, 1650, False)])
+def test_bn_relu_fwd_bwd(n, h, w, c, pool):
+    cp = (c + 63) // 64 * 64
+    raw = torch.zeros((n, h, w, cp), dtype=torch.bfloat16, device=DEV)
+    raw[..., :c] = nhwc(rnd(n, c, h, w, seed=20))
+    gamma = (torch.rand(c, device=DEV) + 0.5)
+    beta = (torch.rand(c, device=DEV) - 0.5) * 0.4
+    cbias = torch.rand(c, device=DEV)
+    rmean = torch.zeros(c, device=DEV)
+    rvar = torch.ones(c, device=DEV)
+    nbt = torch.zeros((), dtype=torch.long, device=DEV)
+    xs = raw[..., :c].double().reshape(-1, c)
+    stats = torch.stack([xs.sum(0), (xs * xs).sum(0)], 1).contiguous()
+    scale = torch.zeros(cp, device=DEV); shift = torch.zeros(cp, device=DEV)
+    smean = torch.zeros(cp, device=DEV); sinv = torch.zeros(cp, device=DEV)
+    cnt = n * h * w
+    ops.bn_finalize(stats, cnt, gamma, beta, cbias, rmean, rvar, nbt, True, scale, shift, smean, sinv, c)
+    y = torch.full((n, h, w, cp), float("nan"), dtype=torch.bfloat16, device=DEV)
+    pooled = torch.full((n, h // 2, w // 2, cp), float("nan"), dtype=torch.bfloat16, device=DEV) if pool else None
+    ops.bn_relu_apply(raw, scale, shift, y, pooled, c=c)
+    torch.cuda.synchronize()
+    xr = nchw(raw, c).clone().requires_grad_(True)
+    g = gamma.clone().requires_grad_(True)
+    b = beta.clone().requires_grad_(True)
+    bnr = torch.ones(c, device=DEV)
+    bnm = torch.zeros(c, device=DEV)
+    yr = F.relu(F.batch_norm(xr + cbias[None, :, None, None], bnm, bnr, g, b, True, 0.1, 1e-5))
+    assert (nchw(y, c) - yr).abs().max() < 2e-2 * max(1.0, yr.abs().max().item())
+    assert torch.allclose(rmean, bnm, rtol=1e-4, atol=1e-5) and torch.allclose(rvar, bnr, rtol=1e-4, atol=1e-5)
+    assert nbt.item() == 1 and (stats == 0).all()
+    if pool:
+        pr = F.max_pool2d(nchw(y, c), 2)
+        assert torch.equal(nchw(pooled, c), pr)
+    # backward: dy direct (+ pooled gradient routed through the arg-max)
+    dy = torch.zeros((n, h, w, cp), dtype=torch.bfloat16, device=DEV)
+    dy[..., :c] = nhwc(rnd(n, c, h, w, seed=21))
+    dpool = None
+    if pool:
+        dpool = torch.zeros((n, h // 2, w // 2, cp), dtype=torch.bfloat16, device=DEV)
+        dpool[..., :c] = nhwc(rnd(n, c, h // 2, w // 2, seed=22))
+    dx = torch.full((n, h, w, cp), float("nan"), dtype=torch.bfloat16, device=DEV)
+    sums = torch.zeros((c, 3), dtype=torch.float64, device=DEV)
+    dgamma = torch.zeros(c, device=DEV); dbeta = torch.zeros(c, device=DEV)
+    ops.bn_relu_bwd(raw, scale, shift, smean, sinv, gamma, dx, sums, cnt, dy=dy, dpool=dpool, dgamma=dgamma,
+                    dbeta=dbeta, c=c)
+    torch.cuda.synchronize()
+    loss = (yr * nchw(dy, c)).sum()
+    if pool:
+        loss = loss + (F.max_pool2d(yr, 2) * nchw(dpool, c)).sum()
+    loss.backward()
+    assert relerr(nchw(dx, c), xr.grad) < 1.5e-2
+    assert relerr(dgamma, g.grad) < 2e-3 and relerr(dbeta, b.grad) < 2e-3
+
+
+def test_head_and_bce():
+    n, h, w, c = 2, 13, 21, 64
+    raw = nhwc(rnd(n, c, h, w, seed=30))
+    scale = torch.rand(c, device=DEV) + 0.5
+    shift = torch.rand(c, device=DEV) - 0.5
+    hw = rnd(c, scale=0.2, seed=31)
+    hb = rnd(1, seed=32)
+    logits = torch.empty((n, 1, h, w), dtype=torch.float32, device=DEV)
+    ops.head_fwd(raw, scale, shift, hw, hb, logits)
+    act = F.relu(nchw(raw) * scale[None, :, None, None] + shift[None, :, None, None])
+    ref = (act * hw[None, :, None, None]).sum(1, keepdim=True) + hb
+    assert (logits - ref).abs().max() < 1e-4 * max(1.0, ref.abs().max().item())
+    target = (torch.rand((n, 1, h, w), device=DEV) > 0.7).float()
+    loss_sum = torch.zeros((), dtype=torch.float64, device=DEV)
+    dlogit = torch.empty_like(logits)
+    counts = torch.zeros(4, dtype=torch.int64, device=DEV)
+    ops.bce_fwd_bwd(logits, target, loss_sum, dlogit, counts)
+    torch.cuda.synchronize()
+    lr = logits.clone().requires_grad_(True)
+    lref = F.binary_cross_entropy_with_logits(lr, target)
+    lref.backward()
+    assert abs(loss_sum.item() / logits.numel() - lref.item()) < 1e-6
+    assert (dlogit - lr.grad).abs().max() < 1e-8
+    seg = torch.sigmoid(logits) > 0.5
+    tp = (seg & (target > 0.5)).sum().item()
+    assert counts[0].item() == tp and counts.sum().item() == logits.numel()
+    # head backward through bn_relu_bwd (dy = dlogit * w) incl. d(head weight)
+    gamma = torch.ones(c, device=DEV)
+    smean = torch.zeros(c, device=DEV)
+    sinv = scale.clone()          # scale = gamma*invstd with gamma = 1, mean = 0 -> shift = beta
+    dx = torch.empty_like(raw)
+    sums = torch.zeros((c, 3), dtype=torch.float64, device=DEV)
+    dhw = torch.zeros(c, device=DEV)
+    ops.bn_relu_bwd(raw, scale, shift, smean, sinv, gamma, dx, sums, n * h * w, head_w=hw, dlogit=dlogit,
+                    dhead_w=dhw)
+    torch.cuda.synchronize()
+    ref_dhw = (act * dlogit).sum((0, 2, 3))
+    assert relerr(dhw, ref_dhw) < 1e-3
