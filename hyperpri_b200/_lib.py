@@ -15,7 +15,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "libhyperpri_b200.so")
 class View(C.Structure):
     """hpri_view_t: NHWC bf16 view with element strides."""
     _fields_ = [("ptr", C.c_void_p), ("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("c", C.c_int),
-                ("pix_stride", C.c_longlong), ("row_stride", C.c_longlong), ("img_stride", C.c_longlong)]
+                ("pix_stride", C.c_longlong), ("row_stride", C.c_longlong), ("img_stride", C.c_longlong),
+                ("dtype", C.c_int)]
 
 
 _VP = C.POINTER(View)
@@ -24,14 +25,15 @@ _p, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 # name -> argtypes; every symbol include/hyperpri_b200.h declares
 SIGNATURES = {
     "hpri_abi_version": [],
-    "hpri_igemm_fwd": [_VP, _p, _i, _i, _i, _VP, _i, _p, _p, _i, _p],
-    "hpri_convT2x2_fwd": [_VP, _p, _i, _i, _VP, _p, _i, _p],
-    "hpri_convT2x2_dgrad": [_VP, _p, _i, _i, _VP, _i, _p],
+    "hpri_igemm_fwd": [_VP, _p, _i, _i, _i, _i, _VP, _i, _p, _p, _i, _i, _p],
+    "hpri_convT2x2_fwd": [_VP, _p, _i, _i, _i, _VP, _p, _i, _p],
+    "hpri_convT2x2_dgrad": [_VP, _p, _i, _i, _i, _VP, _i, _p],
     "hpri_igemm_wgrad": [_VP, _VP, _i, _i, _p, _i, _i, _i, _p],
-    "hpri_pack_weights": [_p, _p, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _p],
+    "hpri_pack_weights": [_p, _p, _i, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _p],
     "hpri_unpack_grads": [_p, _p, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _f, _p],
-    "hpri_hsi_ingest": [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _i, _p],
+    "hpri_hsi_ingest": [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _i, _i, _p],
     "hpri_absmax": [_p, _ll, _p, _p],
+    "hpri_convert16": [_VP, _VP, _p],
     "hpri_bn_finalize": [_p, _ll, _p, _p, _p, _p, _p, _p, _f, _f, _i, _p, _p, _p, _p, _i, _p],
     "hpri_bn_relu_apply": [_VP, _p, _p, _VP, _VP, _p],
     "hpri_bn_relu_bwd_reduce": [_VP, _p, _p, _p, _p, _VP, _VP, _p, _p, _p, _p],

@@ -12,33 +12,42 @@ static inline int check_view_e(const hpri_view_t* v) {
   if ((reinterpret_cast<uintptr_t>(v->ptr) & 15) || (v->pix_stride & 7) || (v->row_stride & 7) || (v->img_stride & 7))
     return HPRI_ERR_ALIGN;
   if (v->pix_stride < ((v->c + 7) & ~7)) return HPRI_ERR_ARG;
+  if (v->dtype != DT_BF16 && v->dtype != DT_F16) return HPRI_ERR_ARG;
   return HPRI_OK;
 }
 static inline int last_err() { return cudaGetLastError() == cudaSuccess ? HPRI_OK : HPRI_ERR_CUDA; }
 
-struct V {   // device-side copy of a view
-  __nv_bfloat16* p;
+struct V {   // device-side copy of a view (16-bit elements, format dt)
+  uint16_t* p;
   int n, h, w, c;
   long long sp, sr, si;
+  int dt;
 };
 static inline V mk(const hpri_view_t* v) {
   V o{};
-  if (v) { o.p = static_cast<__nv_bfloat16*>(v->ptr); o.n = v->n; o.h = v->h; o.w = v->w; o.c = v->c;
-           o.sp = v->pix_stride; o.sr = v->row_stride; o.si = v->img_stride; }
+  if (v) { o.p = static_cast<uint16_t*>(v->ptr); o.n = v->n; o.h = v->h; o.w = v->w; o.c = v->c;
+           o.sp = v->pix_stride; o.sr = v->row_stride; o.si = v->img_stride; o.dt = v->dtype; }
   return o;
 }
-__device__ __forceinline__ __nv_bfloat16* at(const V& v, int n, int y, int x, int c) {
+__device__ __forceinline__ uint16_t* at(const V& v, int n, int y, int x, int c) {
   return v.p + n * v.si + y * v.sr + x * v.sp + c;
 }
-__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
-  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
-  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8], int dt) {
+  float2 t;
+  t = unpack2(u.x, dt); f[0] = t.x; f[1] = t.y;
+  t = unpack2(u.y, dt); f[2] = t.x; f[3] = t.y;
+  t = unpack2(u.z, dt); f[4] = t.x; f[5] = t.y;
+  t = unpack2(u.w, dt); f[6] = t.x; f[7] = t.y;
 }
-__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+__device__ __forceinline__ uint4 pack8(const float (&f)[8], int dt) {
   uint4 u;
-  u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
-  u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+  u.x = pack2(f[0], f[1], dt); u.y = pack2(f[2], f[3], dt);
+  u.z = pack2(f[4], f[5], dt); u.w = pack2(f[6], f[7], dt);
   return u;
+}
+__device__ __forceinline__ uint16_t cvt16(float v, int dt) {
+  if (dt == DT_F16) return __half_as_ushort(__float2half_rn(v));
+  return __bfloat16_as_ushort(__float2bfloat16_rn(v));
 }
 __device__ __forceinline__ void ld8p(const float* p, int c0, int C, float (&f)[8]) {
 #pragma unroll
@@ -46,7 +55,7 @@ __device__ __forceinline__ void ld8p(const float* p, int c0, int C, float (&f)[8
 }
 
 // ------------------------------------------------------------------ weight pack / unpack
-__global__ void pack_weights_k(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int G, int R, int T,
+__global__ void pack_weights_k(const float* __restrict__ src, uint16_t* __restrict__ dst, int dt, int G, int R, int T,
                                int C, int kc64, long long sg, long long sr, long long st, long long sc, int flip) {
   const long long total = (long long)G * R * T * kc64;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -58,7 +67,7 @@ __global__ void pack_weights_k(const float* __restrict__ src, __nv_bfloat16* __r
     const int tm = flip ? T - 1 - t : t;
     float v = 0.f;
     if (c < C) v = __ldg(src + g * sg + r * sr + tm * st + c * sc);
-    dst[i] = __float2bfloat16_rn(v);
+    dst[i] = cvt16(v, dt);
   }
 }
 __global__ void unpack_grads_k(const float* __restrict__ packed, float* __restrict__ dst, int G, int R, int T, int C,
@@ -85,10 +94,10 @@ __global__ void unpack_grads_k(const float* __restrict__ packed, float* __restri
 __global__ void __launch_bounds__(256)
 hsi_ingest_k(const float* __restrict__ src, int bands_total, int H, int W, int lo, int nb, int i0, int j0, int h,
              int w, int flip_h, int flip_w, float scale, const float* __restrict__ bmean,
-             const float* __restrict__ bstd, __nv_bfloat16* __restrict__ dst, int c_pad) {
+             const float* __restrict__ bstd, uint16_t* __restrict__ dst, int dt, int c_pad) {
   extern __shared__ uint32_t tile_w[];          // [64][c_pad/2 + 1] words (odd stride -> conflict-free)
   const int wstride = c_pad / 2 + 1;
-  __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(tile_w);
+  uint16_t* tile = reinterpret_cast<uint16_t*>(tile_w);
   const int xt = blockIdx.x, y = blockIdx.y, n = blockIdx.z;
   const int x0 = xt * 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -107,8 +116,8 @@ hsi_ingest_k(const float* __restrict__ src, int bands_total, int H, int W, int l
         v0 = (v0 - m) * is; v1 = (v1 - m) * is;
       }
     }
-    tile[(lane) * (2 * wstride) + b] = __float2bfloat16_rn(v0);
-    tile[(lane + 32) * (2 * wstride) + b] = __float2bfloat16_rn(v1);
+    tile[(lane) * (2 * wstride) + b] = cvt16(v0, dt);
+    tile[(lane + 32) * (2 * wstride) + b] = cvt16(v1, dt);
   }
   __syncthreads();
   const int wpp = c_pad / 2;                    // words per pixel
@@ -126,6 +135,22 @@ __global__ void absmax_k(const float* __restrict__ x, long long n, float* out) {
     m = fmaxf(m, fabsf(__ldg(x + i)));
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));
+}
+
+// ------------------------------------------------------------------ fp16 <-> bf16 copy of a view
+__global__ void __launch_bounds__(256) convert16_k(V x, V y) {
+  const int CG = (x.c + 7) >> 3;
+  const long long total = (long long)x.n * x.h * x.w * CG;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    long long j = i / CG;
+    const int xx = (int)(j % x.w); j /= x.w;
+    const int yy = (int)(j % x.h);
+    const int n = (int)(j / x.h);
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(at(x, n, yy, xx, cg * 8))), f, x.dt);
+    *reinterpret_cast<uint4*>(at(y, n, yy, xx, cg * 8)) = pack8(f, y.dt);
+  }
 }
 
 // ------------------------------------------------------------------ BatchNorm finalize
@@ -191,15 +216,15 @@ bn_relu_apply_k(V x, const float* __restrict__ scale, const float* __restrict__ 
         const int yy = 2 * wy + dy, xx = 2 * wx + dx;
         if (yy >= x.h || xx >= x.w) continue;
         float f[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(at(x, n, yy, xx, c0))), f);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(at(x, n, yy, xx, c0))), f, x.dt);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           f[k] = fmaxf(fmaf(f[k], sc[k], sh[k]), 0.f);
           mx[k] = fmaxf(mx[k], f[k]);
         }
-        *reinterpret_cast<uint4*>(at(y, n, yy, xx, c0)) = pack8(f);
+        *reinterpret_cast<uint4*>(at(y, n, yy, xx, c0)) = pack8(f, y.dt);
       }
-    if (pool.p != nullptr && wy < pool.h && wx < pool.w) *reinterpret_cast<uint4*>(at(pool, n, wy, wx, c0)) = pack8(mx);
+    if (pool.p != nullptr && wy < pool.h && wx < pool.w) *reinterpret_cast<uint4*>(at(pool, n, wy, wx, c0)) = pack8(mx, pool.dt);
   }
 }
 
@@ -226,10 +251,10 @@ __device__ __forceinline__ void window_dz(const BwdIn& a, int n, int wy, int wx,
       for (int k = 0; k < 8; ++k) { xr[q][k] = 0.f; act[q][k] = 0.f; dz[q][k] = 0.f; }
       continue;
     }
-    unpack8(__ldg(reinterpret_cast<const uint4*>(at(a.x, n, yy, xx, c0))), xr[q]);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(at(a.x, n, yy, xx, c0))), xr[q], a.x.dt);
 #pragma unroll
     for (int k = 0; k < 8; ++k) act[q][k] = fmaxf(fmaf(xr[q][k], sc[k], sh[k]), 0.f);
-    if (a.dy.p != nullptr) unpack8(__ldg(reinterpret_cast<const uint4*>(at(a.dy, n, yy, xx, c0))), dz[q]);
+    if (a.dy.p != nullptr) unpack8(__ldg(reinterpret_cast<const uint4*>(at(a.dy, n, yy, xx, c0))), dz[q], a.dy.dt);
     else {
 #pragma unroll
       for (int k = 0; k < 8; ++k) dz[q][k] = 0.f;
@@ -244,7 +269,7 @@ __device__ __forceinline__ void window_dz(const BwdIn& a, int n, int wy, int wx,
   }
   if (a.dpool.p != nullptr && wy < a.dpool.h && wx < a.dpool.w) {
     float dp[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(at(a.dpool, n, wy, wx, c0))), dp);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(at(a.dpool, n, wy, wx, c0))), dp, a.dpool.dt);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       int best = 0;
@@ -353,7 +378,7 @@ bn_bwd_apply_k(BwdIn a, const float* __restrict__ gamma, const double* __restric
         const float xh = (xr[q][k] - mu[k]) * is[k];
         o[k] = g[k] * is[k] * (dz[q][k] - m1[k] - xh * m2[k]);
       }
-      *reinterpret_cast<uint4*>(at(dx, n, 2 * wy + (q >> 1), 2 * wx + (q & 1), c0)) = pack8(o);
+      *reinterpret_cast<uint4*>(at(dx, n, 2 * wy + (q >> 1), 2 * wx + (q & 1), c0)) = pack8(o, dx.dt);
     }
   }
 }
@@ -380,7 +405,7 @@ head_fwd_k(V x, const float* __restrict__ scale, const float* __restrict__ shift
       for (int cg = sub; cg < CG; cg += LPP) {
         const int c0 = cg * 8;
         float f[8], wv[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(at(x, n, yy, xx, c0))), f);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(at(x, n, yy, xx, c0))), f, x.dt);
         ld8p(w, c0, x.c, wv);
         if (scale != nullptr) {
           float sc[8], sh[8];
@@ -443,7 +468,7 @@ __global__ void __launch_bounds__(256) colsum_k(V x, float* out, int slots, int 
       const int yy = (int)(j % x.h);
       const int n = (int)(j / x.h);
       float f[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(at(x, n, yy, xx, cg * 8))), f);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(at(x, n, yy, xx, cg * 8))), f, x.dt);
 #pragma unroll
       for (int k = 0; k < 8; ++k) s[k] += f[k];
     }
@@ -482,11 +507,12 @@ using namespace hpri;
 
 extern "C" int hpri_abi_version(void) { return 1; }
 
-extern "C" int hpri_pack_weights(const float* src, void* dst, int G, int R, int T, int C, int kc64, long long sg,
-                                 long long sr, long long st, long long sc, int flip, void* stream) {
+extern "C" int hpri_pack_weights(const float* src, void* dst, int dst_dtype, int G, int R, int T, int C, int kc64,
+                                 long long sg, long long sr, long long st, long long sc, int flip, void* stream) {
+  if (dst_dtype != DT_BF16 && dst_dtype != DT_F16) return HPRI_ERR_ARG;
   if (!src || !dst || G <= 0 || R <= 0 || T <= 0 || C <= 0 || kc64 < C || (kc64 & 63)) return HPRI_ERR_ARG;
   const long long total = (long long)G * R * T * kc64;
-  pack_weights_k<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, G, R, T, C, kc64,
+  pack_weights_k<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, (uint16_t*)dst, dst_dtype, G, R, T, C, kc64,
                                                                        sg, sr, st, sc, flip);
   return last_err();
 }
@@ -501,7 +527,8 @@ extern "C" int hpri_unpack_grads(const float* packed, float* dst, int G, int R, 
 
 extern "C" int hpri_hsi_ingest(const float* src, int n, int bands_total, int H, int W, int lo, int hi, int i0,
                                int j0, int h, int w, int flip_h, int flip_w, float scale, const float* band_mean,
-                               const float* band_std, void* dst, int c_pad, void* stream) {
+                               const float* band_std, void* dst, int dst_dtype, int c_pad, void* stream) {
+  if (dst_dtype != DT_BF16 && dst_dtype != DT_F16) return HPRI_ERR_ARG;
   const int nb = hi - lo;
   if (!src || !dst || n <= 0 || lo < 0 || hi > bands_total || nb <= 0 || c_pad < nb || (c_pad & 7)) return HPRI_ERR_ARG;
   if (i0 < 0 || j0 < 0 || i0 + h > H || j0 + w > W || h <= 0 || w <= 0 || h > 65535 || n > 65535) return HPRI_ERR_ARG;
@@ -517,14 +544,23 @@ extern "C" int hpri_hsi_ingest(const float* src, int n, int bands_total, int H, 
   if (smem > 100 * 1024) return HPRI_ERR_ARG;
   dim3 grid((w + 63) / 64, h, n);
   hsi_ingest_k<<<grid, 256, smem, (cudaStream_t)stream>>>(src, bands_total, H, W, lo, nb, i0, j0, h, w, flip_h,
-                                                         flip_w, scale, band_mean, band_std, (__nv_bfloat16*)dst,
-                                                         c_pad);
+                                                         flip_w, scale, band_mean, band_std, (uint16_t*)dst,
+                                                         dst_dtype, c_pad);
   return last_err();
 }
 extern "C" int hpri_absmax(const float* src, long long numel, float* out_max, void* stream) {
   if (!src || !out_max || numel <= 0) return HPRI_ERR_ARG;
   if (cudaMemsetAsync(out_max, 0, sizeof(float), (cudaStream_t)stream) != cudaSuccess) return HPRI_ERR_CUDA;
   absmax_k<<<grid_for(numel, 256 * 8), 256, 0, (cudaStream_t)stream>>>(src, numel, out_max);
+  return last_err();
+}
+
+extern "C" int hpri_convert16(const hpri_view_t* x, const hpri_view_t* y, void* stream) {
+  int rc;
+  if ((rc = check_view_e(x)) != HPRI_OK || (rc = check_view_e(y)) != HPRI_OK) return rc;
+  if (x->n != y->n || x->h != y->h || x->w != y->w || x->c != y->c) return HPRI_ERR_ARG;
+  const long long total = (long long)x->n * x->h * x->w * ((x->c + 7) / 8);
+  convert16_k<<<grid_for(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(mk(x), mk(y));
   return last_err();
 }
 

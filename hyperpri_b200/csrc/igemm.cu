@@ -32,16 +32,18 @@ struct IgemmArgs {
   int taps, tap_mode, kchunks;
   int n_total;            // logical extent of the GEMM N dimension
   // ---- fwd epilogue
-  __nv_bfloat16* out;
+  uint16_t* out;          // 16-bit elements, format out_dt
   long long out_pix_stride, out_row_stride, out_img_stride;   // elements
   int out_h, out_w;       // store bounds (for up2: the upsampled extent)
   int n_store;            // channels to store per pixel (multiple of 8)
   int up2, cout;          // ConvT pixel shuffle: n = (a*2+b)*cout + co
   const float* bias;      // [n_total] (up2: [cout]) or null
+  int accum;              // 1: y += result (read-modify-write of the bf16 destination)
   double* stats;          // [n_total][2] sum / sumsq or null
   // ---- wgrad epilogue
   float* dw;              // [n_total][dw_ld] fp32, accumulated with red.add
   int dw_ld, splits, total_chunks;
+  int a_dt, b_dt, out_dt; // element formats (DT_BF16 / DT_F16) of the A, B operands and the fwd output
 };
 
 constexpr int kThreads = 192;
@@ -199,7 +201,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, BLOCK_N, MODE == MODE_WGRAD, MODE == MODE_WGRAD);
+      const uint32_t idesc = make_idesc_16(128, BLOCK_N, MODE == MODE_WGRAD, MODE == MODE_WGRAD, p.a_dt, p.b_dt);
       for (int i = 0; i < num_kb; ++i) {
         const int s = i % STAGES;
         const uint32_t ph = (i / STAGES) & 1;
@@ -257,10 +259,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint4 o;
-          o.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]), __uint_as_float(v[8 * i + 1]));
-          o.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]));
-          o.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]));
-          o.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]));
+          o.x = pack2(__uint_as_float(v[8 * i + 0]), __uint_as_float(v[8 * i + 1]), p.out_dt);
+          o.y = pack2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]), p.out_dt);
+          o.z = pack2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]), p.out_dt);
+          o.w = pack2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]), p.out_dt);
           const int chunk = c * 4 + i;
           *reinterpret_cast<uint4*>(stage + row * ROWB + (((chunk & ~7) | ((chunk ^ row) & 7)) << 4)) = o;
         }
@@ -277,8 +279,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
             if (!row_valid[r]) continue;
             const uint32_t u = *reinterpret_cast<const uint32_t*>(
                 stage + r * ROWB + (((chunk & ~7) | ((chunk ^ r) & 7)) << 4) + word * 4);
-            const float a = bf16_lo(u), b = bf16_hi(u);
-            s0 += a; s1 += b; q0 += a * a; q1 += b * b;
+            const float2 ab = unpack2(u, p.out_dt);
+            s0 += ab.x; s1 += ab.y; q0 += ab.x * ab.x; q1 += ab.y * ab.y;
           }
           atomicAdd(&ssum[2 * cp], s0);
           atomicAdd(&ssum[2 * cp + 1], s1);
@@ -307,9 +309,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         int oh = h0 + rh, ow = w0 + rw;
         if (p.up2) { oh = 2 * oh + a_off; ow = 2 * ow + b_off; }
         if (oh >= p.out_h || ow >= p.out_w) continue;
-        const uint4 val = *reinterpret_cast<const uint4*>(stage + r * ROWB + (((chunk & ~7) | ((chunk ^ r) & 7)) << 4));
-        __nv_bfloat16* dst = p.out + img * p.out_img_stride + oh * p.out_row_stride + ow * p.out_pix_stride +
-                             co_base + chunk * 8;
+        uint4 val = *reinterpret_cast<const uint4*>(stage + r * ROWB + (((chunk & ~7) | ((chunk ^ r) & 7)) << 4));
+        uint16_t* dst = p.out + img * p.out_img_stride + oh * p.out_row_stride + ow * p.out_pix_stride +
+                        co_base + chunk * 8;
+        if (p.accum) {
+          const uint4 old = *reinterpret_cast<const uint4*>(dst);
+          const int dt = p.out_dt;
+          float2 a, b;
+          a = unpack2(val.x, dt); b = unpack2(old.x, dt); val.x = pack2(a.x + b.x, a.y + b.y, dt);
+          a = unpack2(val.y, dt); b = unpack2(old.y, dt); val.y = pack2(a.x + b.x, a.y + b.y, dt);
+          a = unpack2(val.z, dt); b = unpack2(old.z, dt); val.z = pack2(a.x + b.x, a.y + b.y, dt);
+          a = unpack2(val.w, dt); b = unpack2(old.w, dt); val.w = pack2(a.x + b.x, a.y + b.y, dt);
+        }
         *reinterpret_cast<uint4*>(dst) = val;
       }
     } else {
@@ -367,7 +378,7 @@ static EncodeTiledFn get_encode() {
 
 // bf16 tensor map, 128B swizzle, zero OOB fill.  dims/strides innermost first; strides in bytes for dims 1..rank-1.
 static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
-                    const uint32_t* box) {
+                    const uint32_t* box, int dt) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return HPRI_ERR_DRIVER;
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
@@ -375,7 +386,7 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* 
   cuuint32_t b[5];
   for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; }
   for (int i = 0; i + 1 < rank; ++i) s[i] = strides[i];
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), d, s, b, estr,
+  CUresult r = enc(m, dt == DT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), d, s, b, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? HPRI_OK : HPRI_ERR_TENSORMAP;
@@ -385,6 +396,7 @@ static int check_view(const hpri_view_t& v) {
   if (!v.ptr || v.n <= 0 || v.h <= 0 || v.w <= 0 || v.c <= 0) return HPRI_ERR_ARG;
   if ((reinterpret_cast<uintptr_t>(v.ptr) & 15) || (v.pix_stride & 7) || (v.row_stride & 7) || (v.img_stride & 7))
     return HPRI_ERR_ALIGN;
+  if (v.dtype != DT_BF16 && v.dtype != DT_F16) return HPRI_ERR_ARG;
   return HPRI_OK;
 }
 
@@ -393,7 +405,7 @@ static int map_nhwc(CUtensorMap* m, const hpri_view_t& v, int th, int tw) {
   uint64_t dims[4] = {(uint64_t)v.c, (uint64_t)v.w, (uint64_t)v.h, (uint64_t)v.n};
   uint64_t str[3] = {(uint64_t)v.pix_stride * 2, (uint64_t)v.row_stride * 2, (uint64_t)v.img_stride * 2};
   uint32_t box[4] = {64, (uint32_t)tw, (uint32_t)th, 1};
-  return make_map(m, v.ptr, 4, dims, str, box);
+  return make_map(m, v.ptr, 4, dims, str, box, v.dtype);
 }
 // 2x2 stride-2 gather view of a high-res tensor: (c, w, a, h, n) for a fixed column parity b.
 // v describes the HIGH-res tensor; (hl, wl) is the low-res pixel grid.
@@ -403,14 +415,14 @@ static int map_up2(CUtensorMap* m, const hpri_view_t& v, int hl, int wl, int b, 
   uint64_t str[4] = {(uint64_t)v.pix_stride * 4, (uint64_t)v.row_stride * 2, (uint64_t)v.row_stride * 4,
                      (uint64_t)v.img_stride * 2};
   uint32_t box[5] = {64, (uint32_t)tw, 1, (uint32_t)th, 1};
-  const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(v.ptr) + (long long)b * v.pix_stride;
-  return make_map(m, base, 5, dims, str, box);
+  const uint16_t* base = static_cast<const uint16_t*>(v.ptr) + (long long)b * v.pix_stride;
+  return make_map(m, base, 5, dims, str, box, v.dtype);
 }
-static int map_weights(CUtensorMap* m, const void* w, int rows, int kpad, int block_n) {
+static int map_weights(CUtensorMap* m, const void* w, int rows, int kpad, int block_n, int dt) {
   uint64_t dims[2] = {(uint64_t)kpad, (uint64_t)rows};
   uint64_t str[1] = {(uint64_t)kpad * 2};
   uint32_t box[2] = {64, (uint32_t)block_n};
-  return make_map(m, w, 2, dims, str, box);
+  return make_map(m, w, 2, dims, str, box, dt);
 }
 
 // pick a th x tw = P pixel tile (powers of two) minimising the tile count; ties -> wider rows
@@ -466,9 +478,9 @@ using namespace hpri;
 // -------------------------------------------------------------------------------------
 // C ABI
 // -------------------------------------------------------------------------------------
-extern "C" int hpri_igemm_fwd(const hpri_view_t* x, const void* wpack, int w_rows, int kpad, int taps,
-                              const hpri_view_t* y, int n_store, const float* bias, double* stats, int block_n,
-                              void* stream_) {
+extern "C" int hpri_igemm_fwd(const hpri_view_t* x, const void* wpack, int w_dtype, int w_rows, int kpad, int taps,
+                              const hpri_view_t* y, int n_store, const float* bias, double* stats, int accumulate,
+                              int block_n, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !y || !wpack) return HPRI_ERR_ARG;
   int rc;
@@ -484,22 +496,25 @@ extern "C" int hpri_igemm_fwd(const hpri_view_t* x, const void* wpack, int w_row
   a.tiles_h = (a.H + a.th - 1) / a.th; a.tiles_w = (a.W + a.tw - 1) / a.tw;
   a.taps = taps; a.tap_mode = taps == 9 ? TAP_3X3 : TAP_NONE; a.kchunks = kchunks;
   a.n_total = w_rows;
-  a.out = static_cast<__nv_bfloat16*>(y->ptr);
+  a.out = static_cast<uint16_t*>(y->ptr);
   a.out_pix_stride = y->pix_stride; a.out_row_stride = y->row_stride; a.out_img_stride = y->img_stride;
   a.out_h = y->h; a.out_w = y->w; a.n_store = n_store; a.up2 = 0; a.cout = w_rows;
-  a.bias = bias; a.stats = stats;
+  a.a_dt = x->dtype; a.b_dt = w_dtype; a.out_dt = y->dtype;
+  if (x->dtype != w_dtype) return HPRI_ERR_ARG;     // kind::f16 takes A and B in one format
+  a.bias = bias; a.stats = stats; a.accum = accumulate ? 1 : 0;
+  if (accumulate && stats) return HPRI_ERR_ARG;
   const int bn = pick_block_n(w_rows, block_n);
   CUtensorMap ma, mb;
   if ((rc = map_nhwc(&ma, *x, a.th, a.tw)) != HPRI_OK) return rc;
-  if ((rc = map_weights(&mb, wpack, w_rows, kpad, bn)) != HPRI_OK) return rc;
+  if ((rc = map_weights(&mb, wpack, w_rows, kpad, bn, w_dtype)) != HPRI_OK) return rc;
   const long long grid = (long long)a.N * a.tiles_h * a.tiles_w * ((w_rows + bn - 1) / bn);
   return launch<MODE_FWD>(bn, ma, ma, mb, mb, a, grid, stream);
 }
 
 // ConvTranspose2d(k=2, s=2) forward: y[n, 2h+a, 2w+b, co] = bias[co] + sum_ci x[n,h,w,ci] W[ci,co,a,b]
 // wpack rows are (a*2+b)*cout + co, K = ci.  y is the high-res destination view (channel offset baked in ptr).
-extern "C" int hpri_convT2x2_fwd(const hpri_view_t* x, const void* wpack, int cout, int kpad, const hpri_view_t* y,
-                                 const float* bias, int block_n, void* stream_) {
+extern "C" int hpri_convT2x2_fwd(const hpri_view_t* x, const void* wpack, int w_dtype, int cout, int kpad,
+                                 const hpri_view_t* y, const float* bias, int block_n, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !y || !wpack) return HPRI_ERR_ARG;
   int rc;
@@ -511,23 +526,25 @@ extern "C" int hpri_convT2x2_fwd(const hpri_view_t* x, const void* wpack, int co
   pick_tile(a.H, a.W, 128, &a.th, &a.tw);
   a.tiles_h = (a.H + a.th - 1) / a.th; a.tiles_w = (a.W + a.tw - 1) / a.tw;
   a.taps = 1; a.tap_mode = TAP_NONE; a.kchunks = kchunks; a.n_total = 4 * cout;
-  a.out = static_cast<__nv_bfloat16*>(y->ptr);
+  a.out = static_cast<uint16_t*>(y->ptr);
   a.out_pix_stride = y->pix_stride; a.out_row_stride = y->row_stride; a.out_img_stride = y->img_stride;
   a.out_h = y->h; a.out_w = y->w; a.n_store = cout; a.up2 = 1; a.cout = cout;
+  a.a_dt = x->dtype; a.b_dt = w_dtype; a.out_dt = y->dtype;
+  if (x->dtype != w_dtype) return HPRI_ERR_ARG;
   a.bias = bias; a.stats = nullptr;
   int bn = pick_block_n(cout, block_n);
   while (cout % bn) bn >>= 1;
   CUtensorMap ma, mb;
   if ((rc = map_nhwc(&ma, *x, a.th, a.tw)) != HPRI_OK) return rc;
-  if ((rc = map_weights(&mb, wpack, 4 * cout, kpad, bn)) != HPRI_OK) return rc;
+  if ((rc = map_weights(&mb, wpack, 4 * cout, kpad, bn, w_dtype)) != HPRI_OK) return rc;
   const long long grid = (long long)a.N * a.tiles_h * a.tiles_w * (4 * cout / bn);
   return launch<MODE_FWD>(bn, ma, ma, mb, mb, a, grid, stream);
 }
 
 // ConvTranspose2d dgrad: dx[n,h,w,ci] = sum_{a,b,co} dy[n,2h+a,2w+b,co] W[ci,co,a,b]
 // wpack rows = ci, K = (a*2+b)*kc*64 + co  (kc = ceil(cout/64)).
-extern "C" int hpri_convT2x2_dgrad(const hpri_view_t* dy, const void* wpack, int cin, int kpad, const hpri_view_t* dx,
-                                   int block_n, void* stream_) {
+extern "C" int hpri_convT2x2_dgrad(const hpri_view_t* dy, const void* wpack, int w_dtype, int cin, int kpad,
+                                   const hpri_view_t* dx, int block_n, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!dy || !dx || !wpack) return HPRI_ERR_ARG;
   int rc;
@@ -539,14 +556,16 @@ extern "C" int hpri_convT2x2_dgrad(const hpri_view_t* dy, const void* wpack, int
   pick_tile(a.H, a.W, 128, &a.th, &a.tw);
   a.tiles_h = (a.H + a.th - 1) / a.th; a.tiles_w = (a.W + a.tw - 1) / a.tw;
   a.taps = 4; a.tap_mode = TAP_UP2; a.kchunks = kchunks; a.n_total = cin;
-  a.out = static_cast<__nv_bfloat16*>(dx->ptr);
+  a.out = static_cast<uint16_t*>(dx->ptr);
   a.out_pix_stride = dx->pix_stride; a.out_row_stride = dx->row_stride; a.out_img_stride = dx->img_stride;
   a.out_h = dx->h; a.out_w = dx->w; a.n_store = (cin + 7) & ~7; a.up2 = 0; a.cout = cin;
+  a.a_dt = dy->dtype; a.b_dt = w_dtype; a.out_dt = dx->dtype;
+  if (dy->dtype != w_dtype) return HPRI_ERR_ARG;
   const int bn = pick_block_n(cin, block_n);
   CUtensorMap m0, m1, mb;
   if ((rc = map_up2(&m0, *dy, a.H, a.W, 0, a.th, a.tw)) != HPRI_OK) return rc;
   if ((rc = map_up2(&m1, *dy, a.H, a.W, 1, a.th, a.tw)) != HPRI_OK) return rc;
-  if ((rc = map_weights(&mb, wpack, cin, kpad, bn)) != HPRI_OK) return rc;
+  if ((rc = map_weights(&mb, wpack, cin, kpad, bn, w_dtype)) != HPRI_OK) return rc;
   const long long grid = (long long)a.N * a.tiles_h * a.tiles_w * ((cin + bn - 1) / bn);
   return launch<MODE_FWD>(bn, m0, m1, mb, mb, a, grid, stream);
 }
@@ -569,6 +588,8 @@ extern "C" int hpri_igemm_wgrad(const hpri_view_t* x, const hpri_view_t* dy, int
   a.total_chunks = a.taps * a.kchunks;
   if (dw_ld != a.total_chunks * 64) return HPRI_ERR_ARG;
   a.n_total = n_total; a.dw = dw; a.dw_ld = dw_ld;
+  a.a_dt = x->dtype; a.b_dt = dy->dtype; a.out_dt = DT_BF16;
+  if (x->dtype != dy->dtype) return HPRI_ERR_ARG;   // kind::f16 takes A and B in one format
   int bn;
   if (mode == 2) {
     a.cout = n_total / 4;

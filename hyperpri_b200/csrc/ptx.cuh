@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -140,9 +141,13 @@ __host__ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
-// Instruction descriptor for kind::f16: fp32 accumulate, bf16 A and B.
-__host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+// Element formats of 16-bit tensors (hpri_view_t.dtype).
+enum { DT_BF16 = 0, DT_F16 = 1 };
+// Instruction descriptor for kind::f16: fp32 accumulate; A / B each f16 (format 0) or bf16 (format 1).
+__host__ __device__ __forceinline__ uint32_t make_idesc_16(int M, int N, int a_mn_major, int b_mn_major, int a_dt,
+                                                           int b_dt) {
+  return (1u << 4) | ((a_dt == DT_BF16 ? 1u : 0u) << 7) | ((b_dt == DT_BF16 ? 1u : 0u) << 10) |
+         (static_cast<uint32_t>(a_mn_major) << 15) |
          (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }
@@ -154,6 +159,17 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t pack2(float lo, float hi, int dt) {
+  if (dt == DT_F16) {
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  return pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ float2 unpack2(uint32_t v, int dt) {
+  if (dt == DT_F16) return __half22float2(*reinterpret_cast<__half2*>(&v));
+  return make_float2(bf16_lo(v), bf16_hi(v));
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }

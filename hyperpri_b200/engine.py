@@ -1,0 +1,488 @@
+"""Hand-scheduled forward / backward plans over the native kernels.
+
+``UNetEngine`` runs UNet and CubeNET-64 (reference models.py:23-68, 148-247 with
+model_parts.py:14-99); ``SpectralEngine`` runs SpectralUNET (models.py:71-145).  An engine
+owns the NHWC bf16 activation workspace for one input shape, packed bf16 copies of the fp32
+master parameters (refreshed when a parameter's version changes) and fp32 gradient buffers.
+The nn.Modules in ``hyperpri_b200.src.Experiments.models`` call it through one
+autograd.Function, so ``loss.backward()`` fills ``.grad`` on the module's own Parameters.
+
+Dataflow decisions:
+  * conv -> (raw bf16 + per-channel sum/sumsq in the GEMM epilogue) -> bn_finalize ->
+    bn_relu_apply writes the activation straight into its consumer's buffer (the first half of
+    the decoder's concat buffer for skips, plus the 2x2-pooled tensor in the same pass);
+  * ConvTranspose2d writes the second half of the concat buffer (pixel-shuffle epilogue); the
+    zero-pad column/row of odd sizes is zeroed once at workspace creation;
+  * the train-mode conv bias is cancelled by BatchNorm: it is skipped in the GEMM and re-added to
+    running_mean; its gradient is identically zero and returned as zeros;
+  * backward recomputes ReLU masks / pool arg-max from the saved raw conv outputs;
+  * forward tensors (activations, forward weight operands) are fp16, gradients and dgrad weight
+    operands bf16, every accumulation fp32 (wgrad multiplies fp16 x by bf16 dy in one tcgen05.mma).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from .ops import ACT, GRAD, WeightSpec, kpad
+
+
+def _z(shape, dev, dtype=ACT):
+    return torch.zeros(shape, dtype=dtype, device=dev)
+
+
+def _e(shape, dev, dtype=ACT):
+    return torch.empty(shape, dtype=dtype, device=dev)
+
+
+class _PackedParam:
+    """bf16 GEMM operand(s) of one fp32 parameter, re-packed when the parameter changes."""
+
+    def __init__(self, spec: WeightSpec, need_dgrad: bool):
+        self.spec, self.need_dgrad = spec, need_dgrad
+        self.key = None
+        self.fwd = self.dgr = None
+        self.gpack = None
+
+    def refresh(self, w: torch.Tensor):
+        key = (w.data_ptr(), w._version)
+        if key != self.key:
+            wc = w.detach().reshape(-1)
+            self.fwd = self.spec.pack_fwd(wc, out=self.fwd)
+            if self.need_dgrad:
+                self.dgr = self.spec.pack_dgrad(wc, out=self.dgr)
+            self.key = key
+
+
+class _CBR:
+    """conv3x3 (or Linear) -> BatchNorm -> ReLU unit: parameter names + per-layer BN state."""
+
+    def __init__(self, conv: str, bn: str, cin: int, cout: int, dev, kind="conv3x3", need_dgrad=True, split=0):
+        self.conv, self.bn, self.cin, self.cout = conv, bn, cin, cout
+        self.pp = _PackedParam(WeightSpec(kind, cout, cin, split=split), need_dgrad and not split)
+        cp = kpad(cout)
+        self.stats = _z((cout, 2), dev, torch.float64)
+        self.sums = _z((cout, 3), dev, torch.float64)
+        self.scale, self.shift = _z((cp,), dev, torch.float32), _z((cp,), dev, torch.float32)
+        self.smean, self.sinv = _z((cp,), dev, torch.float32), _z((cp,), dev, torch.float32)
+        self.gw = self.pp.spec.grad_buffer(dev)
+
+
+class UNetEngine:
+    CH = [64, 128, 256, 512, 1024]
+
+    def __init__(self, params: Dict[str, torch.Tensor], first: str, in_ch: int, device):
+        """params: name -> Parameter/buffer of the owning module (reference state-dict names).
+        first: 'unet' (DoubleConv(in_ch, 64)) or 'cube' (Conv3d over in_ch bands, then inc2)."""
+        self.P, self.first, self.in_ch, self.dev = params, first, in_ch, device
+        d = device
+        C = self.CH
+        if first == "unet":
+            self.cin_pad = (in_ch + 7) // 8 * 8
+            enc0 = [_CBR("inc.double_conv.0", "inc.double_conv.1", self.cin_pad, 64, d, need_dgrad=False),
+                    _CBR("inc.double_conv.3", "inc.double_conv.4", 64, 64, d)]
+            enc0[0].true_cin = in_ch
+        else:
+            self.cin_pad = (in_ch + 7) // 8 * 8
+            enc0 = [_CBR("first_conv", "inc.1", self.cin_pad, 64, d, need_dgrad=False),
+                    _CBR("inc2.0", "inc2.1", 64, 64, d)]
+            enc0[0].true_cin = in_ch
+        self.enc: List[List[_CBR]] = [enc0]
+        for i in range(1, 5):
+            p = f"down{i}.maxpool_conv.1.double_conv"
+            self.enc.append([_CBR(p + ".0", p + ".1", C[i - 1], C[i], d), _CBR(p + ".3", p + ".4", C[i], C[i], d)])
+        self.dec: Dict[int, List[_CBR]] = {}
+        self.up: Dict[int, _PackedParam] = {}
+        self.up_gw: Dict[int, torch.Tensor] = {}
+        for i in range(1, 5):
+            lvl = 4 - i
+            p = f"up{i}.conv.double_conv"
+            self.dec[lvl] = [_CBR(p + ".0", p + ".1", 2 * C[lvl], C[lvl], d), _CBR(p + ".3", p + ".4", C[lvl], C[lvl], d)]
+            self.up[lvl] = _PackedParam(WeightSpec("convT2x2", C[lvl], C[lvl + 1]), True)
+            self.up_gw[lvl] = self.up[lvl].spec.grad_buffer(d)
+        # the first conv's real input-channel count differs from the padded view: pack from the true layout
+        self.enc[0][0].pp = _PackedParam(_first_spec(in_ch, self.cin_pad), False)
+        self.enc[0][0].gw = self.enc[0][0].pp.spec.grad_buffer(d)
+        self.ws = None
+        self.ws_key = None
+        self.grads: Dict[str, torch.Tensor] = {}
+        self.training_fwd = False
+
+    # ------------------------------------------------------------------ workspace
+    def _workspace(self, n, h, w):
+        key = (n, h, w)
+        if self.ws_key == key:
+            return self.ws
+        d, C = self.dev, self.CH
+        H, W = [h], [w]
+        for _ in range(4):
+            H.append(H[-1] // 2)
+            W.append(W[-1] // 2)
+        if H[4] < 1 or W[4] < 1:
+            raise ValueError(f"input {h}x{w} too small for four 2x2 poolings")
+        ws = {"H": H, "W": W, "n": n}
+        ws["x"] = _e((n, h, w, self.cin_pad), d)
+        for l in range(5):
+            ws[f"enc_raw_a{l}"] = _e((n, H[l], W[l], C[l]), d)
+            ws[f"enc_act_a{l}"] = _e((n, H[l], W[l], C[l]), d)
+            ws[f"enc_raw_b{l}"] = _e((n, H[l], W[l], C[l]), d)
+            if l < 4:
+                ws[f"cat{l}"] = _z((n, H[l], W[l], 2 * C[l]), d)          # [skip | upsampled], pad stays zero
+                ws[f"gcat{l}"] = _z((n, H[l], W[l], 2 * C[l]), d, GRAD)
+                ws[f"pool{l + 1}"] = _e((n, H[l + 1], W[l + 1], C[l]), d)
+                ws[f"gpool{l + 1}"] = _e((n, H[l + 1], W[l + 1], C[l]), d, GRAD)
+                ws[f"dec_raw_a{l}"] = _e((n, H[l], W[l], C[l]), d)
+                ws[f"dec_act_a{l}"] = _e((n, H[l], W[l], C[l]), d)
+                ws[f"dec_raw_b{l}"] = _e((n, H[l], W[l], C[l]), d)
+                if l > 0:
+                    ws[f"dec_act_b{l}"] = _e((n, H[l], W[l], C[l]), d)
+            else:
+                ws["act_b4"] = _e((n, H[4], W[4], C[4]), d)
+            ws[f"R{l}"] = _e((n, H[l], W[l], C[l]), d, GRAD)      # grad wrt a raw conv output
+            ws[f"A{l}"] = _e((n, H[l], W[l], C[l]), d, GRAD)      # grad wrt an activation
+        ws["cvt"] = _e((n * h * w * max(self.cin_pad, 2 * C[0]),), d, GRAD)
+        ws["logits"] = _e((n, 1, h, w), d, torch.float32)
+        ws["dlogit"] = _e((n, 1, h, w), d, torch.float32)
+        ws["loss_sum"] = _z((), d, torch.float64)
+        ws["counts"] = _z((4,), d, torch.int64)
+        self.ws, self.ws_key = ws, key
+        return ws
+
+    # ------------------------------------------------------------------ helpers
+    def _cbr_fwd(self, L: _CBR, x, raw, act, training, pooled=None, apply=True):
+        P = self.P
+        L.pp.refresh(P[L.conv + ".weight"])
+        n, h, w, _ = raw.shape
+        ops.igemm_fwd(x, L.pp.fwd, L.cout, 9, raw, L.cout, stats=L.stats if training else None)
+        ops.bn_finalize(L.stats, n * h * w, P[L.bn + ".weight"], P[L.bn + ".bias"], P[L.conv + ".bias"],
+                        P[L.bn + ".running_mean"], P[L.bn + ".running_var"], P[L.bn + ".num_batches_tracked"],
+                        training, L.scale, L.shift, L.smean, L.sinv, L.cout)
+        if apply:
+            ops.bn_relu_apply(raw, L.scale, L.shift, act, pooled)
+
+    def _grad(self, name, like):
+        g = self.grads.get(name)
+        if g is None or g.shape != like.shape:
+            g = torch.zeros_like(like, dtype=torch.float32)
+            self.grads[name] = g
+        return g
+
+    def _as_grad_dtype(self, x):
+        """bf16 copy of an fp16 activation view in the shared scratch buffer: wgrad needs x and dy in
+        one format (tcgen05 kind::f16 faults on mixed f16 x bf16 operands)."""
+        n, h, w, c = x.shape
+        buf = self.ws["cvt"][: n * h * w * c].view(n, h, w, c)
+        return ops.convert16(x, buf)
+
+    def _cbr_bwd(self, L: _CBR, x_in, raw, R, count, dy=None, dpool=None, head_w=None, dlogit=None, dhead_w=None,
+                 dx_out=None):
+        """BN+ReLU backward -> R, wgrad, optional dgrad into dx_out."""
+        P = self.P
+        ops.bn_relu_bwd(raw, L.scale, L.shift, L.smean, L.sinv, P[L.bn + ".weight"], R, L.sums, count, dy=dy,
+                        dpool=dpool, head_w=head_w, dlogit=dlogit, dgamma=self._grad(L.bn + ".weight", L.scale[:L.cout]),
+                        dbeta=self._grad(L.bn + ".bias", L.scale[:L.cout]), dhead_w=dhead_w)
+        L.gw.zero_()
+        ops.igemm_wgrad(self._as_grad_dtype(x_in), R, 1, L.cout, L.gw)
+        wname = L.conv + ".weight"
+        L.pp.spec.unpack_grad(L.gw, self._grad(wname, self.P[wname]).view(-1))
+        self._grad(L.conv + ".bias", self.P[L.conv + ".bias"])          # identically zero under train-mode BN
+        if dx_out is not None:
+            ops.igemm_fwd(R, L.pp.dgr, L.cin, 9, dx_out, L.cin)
+
+    # ------------------------------------------------------------------ forward
+    def ingest(self, x: torch.Tensor, ws):
+        if x.dim() == 5:                       # CubeNET: N x 1 x D x H x W  (reshape is a no-copy squeeze)
+            x = x.reshape(x.shape[0], x.shape[2], x.shape[3], x.shape[4])
+        x = x.contiguous().float()
+        ops.hsi_ingest(x, 0, x.shape[1], c_pad=self.cin_pad, out=ws["x"])
+
+    def forward(self, x: torch.Tensor, training: bool) -> torch.Tensor:
+        n = x.shape[0]
+        h, w = x.shape[-2], x.shape[-1]
+        ws = self._workspace(n, h, w)
+        self.ingest(x, ws)
+        return self.forward_ingested(ws, training)
+
+    def forward_ingested(self, ws, training: bool) -> torch.Tensor:
+        P, C = self.P, self.CH
+        self.training_fwd = training
+        cur = ws["x"]
+        for l in range(5):
+            a, b = self.enc[l]
+            self._cbr_fwd(a, cur, ws[f"enc_raw_a{l}"], ws[f"enc_act_a{l}"], training)
+            if l < 4:
+                self._cbr_fwd(b, ws[f"enc_act_a{l}"], ws[f"enc_raw_b{l}"], ws[f"cat{l}"][..., :C[l]], training,
+                              pooled=ws[f"pool{l + 1}"])
+                cur = ws[f"pool{l + 1}"]
+            else:
+                self._cbr_fwd(b, ws["enc_act_a4"], ws["enc_raw_b4"], ws["act_b4"], training)
+                cur = ws["act_b4"]
+        for l in (3, 2, 1, 0):
+            up = self.up[l]
+            i = 4 - l
+            up.refresh(P[f"up{i}.up.weight"])
+            ops.convT_fwd(cur, up.fwd, C[l], ws[f"cat{l}"][..., C[l]:], bias=P[f"up{i}.up.bias"])
+            a, b = self.dec[l]
+            self._cbr_fwd(a, ws[f"cat{l}"], ws[f"dec_raw_a{l}"], ws[f"dec_act_a{l}"], training)
+            if l > 0:
+                self._cbr_fwd(b, ws[f"dec_act_a{l}"], ws[f"dec_raw_b{l}"], ws[f"dec_act_b{l}"], training)
+                cur = ws[f"dec_act_b{l}"]
+            else:
+                self._cbr_fwd(b, ws["dec_act_a0"], ws["dec_raw_b0"], None, training, apply=False)
+        last = self.dec[0][1]
+        ops.head_fwd(ws["dec_raw_b0"], last.scale, last.shift, P["outc.conv.weight"].detach().reshape(-1),
+                     P["outc.conv.bias"], ws["logits"])
+        return ws["logits"]
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, dlogit: torch.Tensor) -> Dict[str, torch.Tensor]:
+        if not self.training_fwd:
+            raise NotImplementedError("backward through eval-mode BatchNorm is not on the hot path")
+        ws, P, C = self.ws, self.P, self.CH
+        n, H, W = ws["n"], ws["H"], ws["W"]
+        dlogit = dlogit.contiguous().float()
+        cnt = [n * H[l] * W[l] for l in range(5)]
+        head_w = P["outc.conv.weight"].detach().reshape(-1)
+        ops.sum_f32(dlogit, self._grad("outc.conv.bias", P["outc.conv.bias"]))
+        g_in = None                        # gradient wrt the activation feeding the next (deeper-first) stage
+        for l in (0, 1, 2, 3):
+            a, b = self.dec[l]
+            if l == 0:
+                dhw = self._grad("outc.conv.weight", P["outc.conv.weight"]).view(-1)
+                self._cbr_bwd(b, ws["dec_act_a0"], ws["dec_raw_b0"], ws["R0"], cnt[0], head_w=head_w, dlogit=dlogit,
+                              dhead_w=dhw, dx_out=ws["A0"])
+            else:
+                self._cbr_bwd(b, ws[f"dec_act_a{l}"], ws[f"dec_raw_b{l}"], ws[f"R{l}"], cnt[l], dy=g_in,
+                              dx_out=ws[f"A{l}"])
+            self._cbr_bwd(a, ws[f"cat{l}"], ws[f"dec_raw_a{l}"], ws[f"R{l}"], cnt[l], dy=ws[f"A{l}"],
+                          dx_out=ws[f"gcat{l}"])
+            # ConvTranspose2d backward: its output is the second half of cat[l] over the 2h x 2w region
+            i = 4 - l
+            up = self.up[l]
+            dy_up = ws[f"gcat{l}"][:, :2 * H[l + 1], :2 * W[l + 1], C[l]:]
+            x_up = ws[f"dec_act_b{l + 1}"] if l < 3 else ws["act_b4"]
+            ops.convT_dgrad(dy_up, up.dgr, C[l + 1], ws[f"A{l + 1}"])
+            gw = self.up_gw[l]
+            gw.zero_()
+            ops.igemm_wgrad(self._as_grad_dtype(x_up), dy_up, 2, 4 * C[l], gw)
+            wn = f"up{i}.up.weight"
+            up.spec.unpack_grad(gw, self._grad(wn, P[wn]).view(-1))
+            ops.colsum(dy_up, self._grad(f"up{i}.up.bias", P[f"up{i}.up.bias"]))
+            g_in = ws[f"A{l + 1}"]
+        # encoder, deepest first
+        for l in (4, 3, 2, 1, 0):
+            a, b = self.enc[l]
+            if l == 4:
+                self._cbr_bwd(b, ws["enc_act_a4"], ws["enc_raw_b4"], ws["R4"], cnt[4], dy=g_in, dx_out=ws["A4"])
+            else:
+                self._cbr_bwd(b, ws[f"enc_act_a{l}"], ws[f"enc_raw_b{l}"], ws[f"R{l}"], cnt[l],
+                              dy=ws[f"gcat{l}"][..., :C[l]], dpool=ws[f"gpool{l + 1}"], dx_out=ws[f"A{l}"])
+            x_in = ws[f"pool{l}"] if l > 0 else ws["x"]
+            self._cbr_bwd(a, x_in, ws[f"enc_raw_a{l}"], ws[f"R{l}"], cnt[l], dy=ws[f"A{l}"],
+                          dx_out=ws[f"gpool{l}"] if l > 0 else None)
+        if self.first == "cube":               # module registered twice (models.py:169-171): same tensor
+            self.grads["inc.0.weight"] = self.grads["first_conv.weight"]
+            self.grads["inc.0.bias"] = self.grads["first_conv.bias"]
+        return self.grads
+
+    # ------------------------------------------------------------------ fused training step
+    def loss_and_dlogit(self, logits, mask, grad_scale=1.0, thr=0.5):
+        ws = self.ws
+        ops.bce_fwd_bwd(logits, mask.contiguous().float(), ws["loss_sum"], ws["dlogit"], ws["counts"],
+                        grad_scale=grad_scale, thr=thr)
+        return ws["loss_sum"], ws["dlogit"], ws["counts"]
+
+
+def _first_spec(true_cin: int, cin_pad: int) -> WeightSpec:
+    """First conv: the parameter has `true_cin` input channels, the activation view `cin_pad`."""
+    s = WeightSpec("conv3x3", 64, true_cin)
+    assert kpad(true_cin) == kpad(cin_pad)
+    return s
+
+
+# =======================================================================================
+class SpectralEngine:
+    """SpectralUNET: nine Linear->BatchNorm1d->ReLU blocks on an (R*C) x D pixel matrix per image
+    (models.py:105-115,132-144), concat by writing into halves of shared buffers."""
+    BLOCKS = ["tail", "down1", "down2", "down3", "down4", "up1", "up2", "up3", "up4"]
+
+    def __init__(self, params: Dict[str, torch.Tensor], hsi_depth: int, feats: int, device):
+        self.P, self.D, self.F, self.dev = params, hsi_depth, feats, device
+        self.Fp = kpad(feats)
+        self.Dp = (hsi_depth + 7) // 8 * 8
+        d = device
+        self.L: Dict[str, _CBR] = {}
+        for nm in self.BLOCKS:
+            cin = hsi_depth if nm == "tail" else (2 * feats if nm in ("up2", "up3", "up4") else feats)
+            split = feats if nm in ("up2", "up3", "up4") else 0
+            L = _CBR(nm + ".0", nm + ".1", cin, feats, d, kind="linear", need_dgrad=(nm != "tail"), split=split)
+            if split:
+                L.dgr_cat = _z((2 * self.Fp, kpad(feats)), d, GRAD)     # rows = cat-buffer feature index
+            self.L[nm] = L
+        self.ws = None
+        self.ws_key = None
+        self.grads: Dict[str, torch.Tensor] = {}
+        self.training_fwd = False
+        self.w_outc = _z((2 * self.Fp,), d, torch.float32)
+        self.dw_outc = _z((2 * self.Fp,), d, torch.float32)
+
+    def _workspace(self, n, r, c):
+        key = (n, r, c)
+        if self.ws_key == key:
+            return self.ws
+        d, m, Fp = self.dev, r * c, self.Fp
+        ws = {"n": n, "m": m, "r": r, "c": c, "img": []}
+        ws["x"] = _e((n, r, c, self.Dp), d)
+        for _ in range(n):
+            im = {nm: _e((1, 1, m, Fp), d) for nm in ("raw_" + b for b in self.BLOCKS)}
+            for k in (1, 2, 3, 4):
+                im[f"cat{k}"] = _z((1, 1, m, 2 * Fp), d)
+            im["x4"] = _z((1, 1, m, Fp), d)
+            im["bn"] = {b: [_z((Fp,), d, torch.float32) for _ in range(4)] for b in self.BLOCKS}
+            ws["img"].append(im)
+        for k in (2, 3, 4):
+            ws[f"gcat{k}"] = _z((1, 1, m, 2 * Fp), d, GRAD)
+        ws["R"] = _z((1, 1, m, Fp), d, GRAD)
+        ws["cvt"] = _z((1, 1, m, 2 * Fp), d, GRAD)
+        ws["g4"] = _z((1, 1, m, Fp), d, GRAD)
+        ws["gt"] = _z((1, 1, m, Fp), d, GRAD)
+        ws["logits"] = _e((n, 1, r, c), d, torch.float32)
+        ws["dlogit"] = _e((n, 1, r, c), d, torch.float32)
+        ws["loss_sum"] = _z((), d, torch.float64)
+        ws["counts"] = _z((4,), d, torch.int64)
+        self.ws, self.ws_key = ws, key
+        return ws
+
+    def _refresh(self):
+        P, F, Fp = self.P, self.F, self.Fp
+        for nm, L in self.L.items():
+            w = P[nm + ".0.weight"]
+            key = (w.data_ptr(), w._version)
+            if L.pp.key != key:
+                L.pp.refresh(w)
+                if L.pp.spec.split:
+                    wc = w.detach().reshape(-1)
+                    for half in (0, 1):   # dgrad operand rows follow the cat buffer: [0,F) and [Fp, Fp+F)
+                        ops.pack(wc, G=1, R=F, T=1, Cc=F, sg=0, sr=1, st=0, sc=2 * F, src_offset=half * F,
+                                 out=L.dgr_cat[half * Fp: half * Fp + F])
+        wo = P["outc.weight"].detach().reshape(-1)
+        self.w_outc.zero_()
+        self.w_outc[:F].copy_(wo[:F])
+        self.w_outc[Fp:Fp + F].copy_(wo[F:])
+
+    def _grad(self, name, like):
+        g = self.grads.get(name)
+        if g is None or g.shape != like.shape:
+            g = torch.zeros_like(like, dtype=torch.float32)
+            self.grads[name] = g
+        return g
+
+    def _io(self, im, nm):
+        """(input view, logical in-features, output activation view) of block nm."""
+        Fp = self.Fp
+        src = {"down1": im["cat1"][..., :Fp], "down2": im["cat2"][..., :Fp], "down3": im["cat3"][..., :Fp],
+               "down4": im["cat4"][..., :Fp], "up1": im["x4"], "up2": im["cat4"], "up3": im["cat3"],
+               "up4": im["cat2"]}
+        dst = {"tail": im["cat1"][..., :Fp], "down1": im["cat2"][..., :Fp], "down2": im["cat3"][..., :Fp],
+               "down3": im["cat4"][..., :Fp], "down4": im["x4"], "up1": im["cat4"][..., Fp:],
+               "up2": im["cat3"][..., Fp:], "up3": im["cat2"][..., Fp:], "up4": im["cat1"][..., Fp:]}
+        return src.get(nm), dst[nm]
+
+    def forward(self, x: torch.Tensor, training: bool) -> torch.Tensor:
+        n, dch, r, c = x.shape
+        ws = self._workspace(n, r, c)
+        ops.hsi_ingest(x.contiguous().float(), 0, dch, c_pad=self.Dp, out=ws["x"])
+        return self.forward_ingested(ws, training)
+
+    def forward_ingested(self, ws, training: bool) -> torch.Tensor:
+        P, F, Fp, m = self.P, self.F, self.Fp, ws["m"]
+        self.training_fwd = training
+        self._refresh()
+        for i in range(ws["n"]):
+            im = ws["img"][i]
+            xin = ws["x"][i].reshape(1, 1, m, self.Dp)
+            for nm in self.BLOCKS:
+                L = self.L[nm]
+                src, dst = self._io(im, nm)
+                if nm == "tail":
+                    src = xin
+                raw = im["raw_" + nm]
+                scale, shift, smean, sinv = im["bn"][nm]
+                ops.igemm_fwd(src, L.pp.fwd, F, 1, raw, Fp, stats=L.stats if training else None,
+                              x_c=(self.D if nm == "tail" else None))
+                ops.bn_finalize(L.stats, m, P[nm + ".1.weight"], P[nm + ".1.bias"], P[nm + ".0.bias"],
+                                P[nm + ".1.running_mean"], P[nm + ".1.running_var"],
+                                P[nm + ".1.num_batches_tracked"], training, scale, shift, smean, sinv, F)
+                ops.bn_relu_apply(raw, scale, shift, dst, None, c=F)
+            ops.head_fwd(im["cat1"], None, None, self.w_outc, P["outc.bias"], ws["logits"][i])
+        return ws["logits"]
+
+    def backward(self, dlogit: torch.Tensor) -> Dict[str, torch.Tensor]:
+        if not self.training_fwd:
+            raise NotImplementedError("backward through eval-mode BatchNorm is not on the hot path")
+        ws, P, F, Fp, m = self.ws, self.P, self.F, self.Fp, self.ws["m"]
+        dlogit = dlogit.contiguous().float()
+        ops.sum_f32(dlogit, self._grad("outc.bias", P["outc.bias"]))
+        for L in self.L.values():
+            L.gw.zero_()
+        first_img = True
+        dwo_acc = torch.zeros_like(self.dw_outc)
+        for i in range(ws["n"]):
+            im = ws["img"][i]
+            dl = dlogit[i].reshape(-1)
+            xin = ws["x"][i].reshape(1, 1, m, self.Dp)
+            R = ws["R"]
+            # (block, dy source, dgrad destination, accumulate?)
+            plan = [("up4", None, ws["gcat2"], False), ("up3", ws["gcat2"][..., Fp:], ws["gcat3"], False),
+                    ("up2", ws["gcat3"][..., Fp:], ws["gcat4"], False), ("up1", ws["gcat4"][..., Fp:], ws["g4"], False),
+                    ("down4", ws["g4"], ws["gcat4"][..., :Fp], True), ("down3", ws["gcat4"][..., :Fp], ws["gcat3"][..., :Fp], True),
+                    ("down2", ws["gcat3"][..., :Fp], ws["gcat2"][..., :Fp], True), ("down1", ws["gcat2"][..., :Fp], ws["gt"], False),
+                    ("tail", ws["gt"], None, False)]
+            for nm, dy, dx_dst, acc in plan:
+                L = self.L[nm]
+                src, _ = self._io(im, nm)
+                if nm == "tail":
+                    src = xin
+                scale, shift, smean, sinv = im["bn"][nm]
+                head = nm in ("up4", "tail")
+                hw = None
+                dhw = None
+                if head:
+                    off = Fp if nm == "up4" else 0
+                    hw = self.w_outc[off:off + Fp]
+                    dhw = self.dw_outc[off:off + Fp]
+                dg = torch.empty(F, dtype=torch.float32, device=self.dev)
+                db = torch.empty(F, dtype=torch.float32, device=self.dev)
+                ops.bn_relu_bwd(im["raw_" + nm], scale, shift, smean, sinv, P[nm + ".1.weight"], R, L.sums, m, dy=dy,
+                                head_w=hw, dlogit=dl if head else None, dgamma=dg, dbeta=db, dhead_w=dhw, c=F)
+                g_g = self._grad(nm + ".1.weight", P[nm + ".1.weight"])
+                g_b = self._grad(nm + ".1.bias", P[nm + ".1.bias"])
+                if first_img:
+                    g_g.copy_(dg); g_b.copy_(db)
+                else:
+                    g_g.add_(dg); g_b.add_(db)
+                xg = ops.convert16(src, ws["cvt"][..., :src.shape[-1]])
+                ops.igemm_wgrad(xg, R, 0, F, L.gw, x_c=(self.D if nm == "tail" else None), dy_c=F)
+                if dx_dst is not None:
+                    if L.pp.spec.split:
+                        ops.igemm_fwd(R, L.dgr_cat, 2 * Fp, 1, dx_dst, 2 * Fp, x_c=F, accumulate=acc)
+                    else:
+                        ops.igemm_fwd(R, L.pp.dgr, F, 1, dx_dst, Fp, x_c=F, accumulate=acc)
+            dwo_acc.add_(self.dw_outc)
+            first_img = False
+        for nm, L in self.L.items():
+            wn = nm + ".0.weight"
+            L.pp.spec.unpack_grad(L.gw, self._grad(wn, P[wn]).view(-1))
+            self._grad(nm + ".0.bias", P[nm + ".0.bias"])
+        go = self._grad("outc.weight", P["outc.weight"]).view(-1)
+        go[:F].copy_(dwo_acc[:F])
+        go[F:].copy_(dwo_acc[Fp:Fp + F])
+        return self.grads
+
+    def loss_and_dlogit(self, logits, mask, grad_scale=1.0, thr=0.5):
+        ws = self.ws
+        ops.bce_fwd_bwd(logits, mask.contiguous().float(), ws["loss_sum"], ws["dlogit"], ws["counts"],
+                        grad_scale=grad_scale, thr=thr)
+        return ws["loss_sum"], ws["dlogit"], ws["counts"]

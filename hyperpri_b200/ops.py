@@ -15,6 +15,10 @@ from . import _lib
 from ._lib import View, check
 
 bf16 = torch.bfloat16
+f16 = torch.float16
+ACT = f16        # forward activations and forward weight operands (11-bit mantissa; BN keeps them O(1))
+GRAD = bf16      # gradients and dgrad weight operands (fp32 exponent range, no loss scaling)
+_DT = {bf16: 0, f16: 1}
 
 
 def _stream() -> C.c_void_p:
@@ -30,10 +34,10 @@ def view(t: Optional[torch.Tensor], c: Optional[int] = None) -> Optional[View]:
     `c` overrides the logical channel count (e.g. 1650 of a 1664-wide buffer)."""
     if t is None:
         return None
-    assert t.dtype == bf16 and t.dim() == 4 and t.is_cuda, (t.dtype, t.shape)
+    assert t.dtype in _DT and t.dim() == 4 and t.is_cuda, (t.dtype, t.shape)
     assert t.stride(3) == 1
     n, h, w, cc = t.shape
-    return View(t.data_ptr(), n, h, w, cc if c is None else c, t.stride(2), t.stride(1), t.stride(0))
+    return View(t.data_ptr(), n, h, w, cc if c is None else c, t.stride(2), t.stride(1), t.stride(0), _DT[t.dtype])
 
 
 def _vp(v: Optional[View]):
@@ -45,14 +49,16 @@ def kpad(c: int) -> int:
 
 
 # ----------------------------------------------------------------------------- weights
-def pack(src: torch.Tensor, G, R, T, Cc, sg, sr, st, sc, flip=False, out: Optional[torch.Tensor] = None):
-    """Generic fp32 parameter -> bf16 operand [(G*R), T*kpad(C)] (see hpri_pack_weights)."""
+def pack(src: torch.Tensor, G, R, T, Cc, sg, sr, st, sc, flip=False, out: Optional[torch.Tensor] = None,
+         src_offset: int = 0, dtype=None):
+    """Generic fp32 parameter -> 16-bit operand [(G*R), T*kpad(C)] (see hpri_pack_weights)."""
     assert src.dtype == torch.float32 and src.is_cuda and src.is_contiguous()
     kc = kpad(Cc)
     if out is None:
-        out = torch.empty((G * R, T * kc), dtype=bf16, device=src.device)
-    check(_lib.lib().hpri_pack_weights(_ptr(src), _ptr(out), G, R, T, Cc, kc, sg, sr, st, sc, int(flip), _stream()),
-          "hpri_pack_weights")
+        out = torch.empty((G * R, T * kc), dtype=dtype or ACT, device=src.device)
+    assert out.is_contiguous() and out.shape == (G * R, T * kc)
+    check(_lib.lib().hpri_pack_weights(C.c_void_p(src.data_ptr() + 4 * src_offset), _ptr(out), _DT[out.dtype], G, R, T,
+                                       Cc, kc, sg, sr, st, sc, int(flip), _stream()), "hpri_pack_weights")
     return out
 
 
@@ -88,11 +94,11 @@ class WeightSpec:
         else:
             raise ValueError(kind)
 
-    def pack_fwd(self, w, out=None):
-        return pack(w, out=out, **self.fwd)
+    def pack_fwd(self, w, out=None, dtype=None):
+        return pack(w, out=out, dtype=dtype or ACT, **self.fwd)
 
-    def pack_dgrad(self, w, out=None):
-        return pack(w, out=out, **self.dgr)
+    def pack_dgrad(self, w, out=None, dtype=None):
+        return pack(w, out=out, dtype=dtype or GRAD, **self.dgr)
 
     def grad_buffer(self, device):
         f = self.fwd
@@ -104,21 +110,22 @@ class WeightSpec:
 
 
 # ----------------------------------------------------------------------------- contractions
-def igemm_fwd(x, wpack, rows, taps, y, n_store, bias=None, stats=None, block_n=0, x_c=None, y_c=None):
+def igemm_fwd(x, wpack, rows, taps, y, n_store, bias=None, stats=None, block_n=0, x_c=None, y_c=None,
+              accumulate=False):
     xv, yv = view(x, x_c), view(y, y_c)
-    check(_lib.lib().hpri_igemm_fwd(_vp(xv), _ptr(wpack), rows, wpack.shape[1], taps, _vp(yv), n_store, _ptr(bias),
-                                    _ptr(stats), block_n, _stream()), "hpri_igemm_fwd")
+    check(_lib.lib().hpri_igemm_fwd(_vp(xv), _ptr(wpack), _DT[wpack.dtype], rows, wpack.shape[1], taps, _vp(yv), n_store, _ptr(bias),
+                                    _ptr(stats), int(accumulate), block_n, _stream()), "hpri_igemm_fwd")
 
 
 def convT_fwd(x, wpack, cout, y, bias=None, block_n=0):
     xv, yv = view(x), view(y)
-    check(_lib.lib().hpri_convT2x2_fwd(_vp(xv), _ptr(wpack), cout, wpack.shape[1], _vp(yv), _ptr(bias), block_n,
+    check(_lib.lib().hpri_convT2x2_fwd(_vp(xv), _ptr(wpack), _DT[wpack.dtype], cout, wpack.shape[1], _vp(yv), _ptr(bias), block_n,
                                        _stream()), "hpri_convT2x2_fwd")
 
 
 def convT_dgrad(dy, wpack, cin, dx, block_n=0):
     dv, xv = view(dy), view(dx)
-    check(_lib.lib().hpri_convT2x2_dgrad(_vp(dv), _ptr(wpack), cin, wpack.shape[1], _vp(xv), block_n, _stream()),
+    check(_lib.lib().hpri_convT2x2_dgrad(_vp(dv), _ptr(wpack), _DT[wpack.dtype], cin, wpack.shape[1], _vp(xv), block_n, _stream()),
           "hpri_convT2x2_dgrad")
 
 
@@ -131,19 +138,26 @@ def igemm_wgrad(x, dy, mode, n_total, dw, block_n=0, splits=0, x_c=None, dy_c=No
 
 # ----------------------------------------------------------------------------- ingest
 def hsi_ingest(src, lo, hi, crop=None, flip_h=False, flip_w=False, scale=1.0, band_mean=None, band_std=None,
-               c_pad=None, out=None):
-    """src fp32 [N, bands, H, W] -> NHWC bf16 [N, h, w, c_pad]."""
+               c_pad=None, out=None, dtype=None):
+    """src fp32 [N, bands, H, W] -> NHWC 16-bit [N, h, w, c_pad]."""
     assert src.dtype == torch.float32 and src.is_contiguous() and src.dim() == 4
     n, bt, H, W = src.shape
     i0, j0, h, w = crop if crop is not None else (0, 0, H, W)
     nb = hi - lo
     c_pad = c_pad or (nb + 7) // 8 * 8
     if out is None:
-        out = torch.empty((n, h, w, c_pad), dtype=bf16, device=src.device)
+        out = torch.empty((n, h, w, c_pad), dtype=dtype or ACT, device=src.device)
     check(_lib.lib().hpri_hsi_ingest(_ptr(src), n, bt, H, W, lo, hi, i0, j0, h, w, int(flip_h), int(flip_w),
-                                     float(scale), _ptr(band_mean), _ptr(band_std), _ptr(out), c_pad, _stream()),
+                                     float(scale), _ptr(band_mean), _ptr(band_std), _ptr(out), _DT[out.dtype], c_pad,
+                                     _stream()),
           "hpri_hsi_ingest")
     return out
+
+
+def convert16(x, y, c=None):
+    xv, yv = view(x, c), view(y, c)
+    check(_lib.lib().hpri_convert16(_vp(xv), _vp(yv), _stream()), "hpri_convert16")
+    return y
 
 
 def absmax(src):

@@ -1,0 +1,198 @@
+"""UNet, SpectralUNET, CubeNET and the model factories with the reference's public surface
+(reference src/Experiments/models.py:23-292): same constructor signatures, attributes,
+``state_dict`` keys/shapes and default torch initialisation, so existing checkpoints load and
+``optim.Adam(model.parameters())`` keeps working.  ``forward`` hands the whole network to the
+B200 engine through one autograd.Function; there is no torch-op fallback.
+"""
+import torch
+import torch.nn as nn
+
+from .model_parts import DoubleConv, Down, Up, OutConv
+from ... import engine as _engine
+
+
+def set_parameter_requires_grad(model, feature_extraction):
+    if feature_extraction:
+        for param in model.parameters():
+            param.requires_grad = False
+
+
+class _NetFn(torch.autograd.Function):
+    """forward: engine forward (NHWC bf16 workspace) -> fp32 logits; backward: engine backward ->
+    one fp32 gradient per parameter, in the order the parameters were passed."""
+
+    @staticmethod
+    def forward(ctx, net, x, *params):
+        eng = net._get_engine(x.device)
+        logits = eng.forward(x, net.training)
+        ctx.net, ctx.dev = net, x.device
+        return logits.clone()
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        net = ctx.net
+        grads = net._get_engine(ctx.dev).backward(dlogits)
+        out = []
+        for name, p in net._hot_params():
+            out.append(grads[name].clone() if p.requires_grad else None)
+        return (None, None, *out)
+
+
+class _EngineNet(nn.Module):
+    """Shared plumbing: lazily built engine keyed by device, parameter/buffer name table."""
+
+    def _hot_params(self):
+        return list(self.named_parameters())
+
+    def _tensor_table(self):
+        table = {}
+        for k, v in self.named_parameters(remove_duplicate=False):
+            table[k] = v
+        for k, v in self.named_buffers(remove_duplicate=False):
+            table[k] = v
+        return table
+
+    def _make_engine(self, device):
+        raise NotImplementedError
+
+    def _get_engine(self, device):
+        eng = self.__dict__.get("_eng")
+        if eng is None or eng.dev != device:
+            if device.type != "cuda":
+                raise RuntimeError("hyperpri_b200 models run on a CUDA (sm_100a) device only; got " + str(device))
+            eng = self._make_engine(device)
+            self.__dict__["_eng"] = eng
+        eng.P = self._tensor_table()          # parameters may have been re-assigned (load_state_dict, .to())
+        return eng
+
+    def _run(self, x):
+        if x.device != next(self.parameters()).device:
+            raise RuntimeError("input and parameters are on different devices")
+        params = [p for _, p in self._hot_params()]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            return _NetFn.apply(self, x, *params)
+        return self._get_engine(x.device).forward(x, self.training).clone()
+
+    def _finish(self, logits):
+        if getattr(self, "analyze", False):
+            return (logits, logits, torch.sigmoid(logits))
+        return logits
+
+
+class UNet(_EngineNet):
+    """models.py:23-68.  31,043,521 parameters for n_channels=3."""
+
+    def __init__(self, n_channels, n_classes, bilinear=True, feature_extraction=False, use_attention=False,
+                 analyze=False):
+        super().__init__()
+        self.n_channels, self.n_classes = n_channels, n_classes
+        self.bilinear, self.use_attention, self.analyze = bilinear, use_attention, analyze
+        if n_classes != 1:
+            raise NotImplementedError("the B200 head kernel is built for n_classes=1 (every reference config)")
+        w = [64 * 2 ** i for i in range(5)]
+        self.inc = DoubleConv(n_channels, w[0])
+        self.down1, self.down2 = Down(w[0], w[1]), Down(w[1], w[2])
+        self.down3, self.down4 = Down(w[2], w[3]), Down(w[3], w[4])
+        self.up1 = Up(w[4], w[3], bilinear, use_attention=use_attention)
+        self.up2 = Up(w[3], w[2], bilinear, use_attention=use_attention)
+        self.up3 = Up(w[2], w[1], bilinear, use_attention=use_attention)
+        self.up4 = Up(w[1], w[0], bilinear, use_attention=use_attention)
+        self.outc = OutConv(w[0], n_classes)
+
+    def _make_engine(self, device):
+        return _engine.UNetEngine(self._tensor_table(), "unet", self.n_channels, device)
+
+    def forward(self, x):
+        return self._finish(self._run(x))
+
+
+class CubeNET(_EngineNet):
+    """models.py:148-247, first_depth=64.  The Conv3d spanning all bands is executed as the 2-D
+    3x3 conv over `hsi_depth` channels it equals; `first_conv` stays an nn.Conv3d so the
+    (64,1,D,3,3) weight and the aliased `first_conv.*` / `inc.0.*` keys are preserved."""
+
+    def __init__(self, hsi_depth, n_classes, first_depth=64, bilinear=True, use_attention=False, analyze=False):
+        super().__init__()
+        self.n_channels = 1
+        self.depth, self.first_depth, self.n_classes = hsi_depth, first_depth, n_classes
+        self.bilinear, self.use_attention, self.analyze = bilinear, use_attention, analyze
+        if first_depth != 64:
+            raise NotImplementedError("CubeNET first_depth != 64 (models.py:193-199) is not built")
+        if n_classes != 1:
+            raise NotImplementedError("the B200 head kernel is built for n_classes=1 (every reference config)")
+        self.first_conv = nn.Conv3d(1, first_depth, kernel_size=(hsi_depth, 3, 3), padding=(0, 1, 1))
+        self.inc = nn.Sequential(self.first_conv, nn.BatchNorm3d(first_depth), nn.ReLU(inplace=True))
+        self.inc2 = nn.Sequential(nn.Conv2d(first_depth, first_depth, kernel_size=3, padding=1),
+                                  nn.BatchNorm2d(first_depth), nn.ReLU(inplace=True))
+        c = 128
+        self.down1, self.down2 = Down(first_depth, c), Down(c, 2 * c)
+        self.down3, self.down4 = Down(2 * c, 4 * c), Down(4 * c, 8 * c)
+        self.up1 = Up(8 * c, 4 * c, bilinear, use_attention=use_attention)
+        self.up2 = Up(4 * c, 2 * c, bilinear, use_attention=use_attention)
+        self.up3 = Up(2 * c, c, bilinear, use_attention=use_attention)
+        self.up4 = Up(c, 64, bilinear, use_attention=use_attention)
+        self.outc = OutConv(64, n_classes)
+
+    def _make_engine(self, device):
+        return _engine.UNetEngine(self._tensor_table(), "cube", self.depth, device)
+
+    def forward(self, x):
+        """x: N x 1 x D x R x C (a depth mismatch is not raised by the reference either, models.py:211)."""
+        return self._finish(self._run(x))
+
+
+class SpectralUNET(_EngineNet):
+    """models.py:71-145: per-pixel MLP U-Net, BatchNorm1d statistics per image."""
+
+    def __init__(self, hsi_depth, n_classes, bn_feats=16, bnorm=True):
+        super().__init__()
+        self.hsi_depth = self.n_channels = hsi_depth
+        self.n_classes = n_classes
+        if not bnorm:
+            raise NotImplementedError("bnorm=False is not used by the reference factories and is not built")
+        if n_classes != 1:
+            raise NotImplementedError("the B200 head kernel is built for n_classes=1 (every reference config)")
+        f = bn_feats
+        self.layer_feats = [f] * 5
+        self.tail = self._basic_module(hsi_depth, f)
+        self.down1, self.down2 = self._basic_module(f, f), self._basic_module(f, f)
+        self.down3, self.down4 = self._basic_module(f, f), self._basic_module(f, f)
+        self.up1 = self._basic_module(f, f)
+        self.up2, self.up3, self.up4 = (self._basic_module(2 * f, f) for _ in range(3))
+        self.outc = nn.Linear(2 * f, n_classes)
+
+    def _basic_module(self, in_feats, out_feats, bn=True):
+        return nn.Sequential(nn.Linear(in_feats, out_feats), nn.BatchNorm1d(out_feats), nn.ReLU())
+
+    def _make_engine(self, device):
+        return _engine.SpectralEngine(self._tensor_table(), self.hsi_depth, self.layer_feats[0], device)
+
+    def forward(self, x):
+        """x: N x D x R x C -> N x n_classes x R x C."""
+        return self._run(x)
+
+
+def initialize_model(model_name, num_classes, Network_parameters, analyze=False):
+    """models.py:250-276."""
+    if model_name == 'UNET':
+        return UNet(Network_parameters['channels'], num_classes, bilinear=Network_parameters['bilinear'],
+                    feature_extraction=Network_parameters['feature_extraction'],
+                    use_attention=Network_parameters['use_attention'], analyze=analyze)
+    if model_name == 'SpectralUNET':
+        depth = Network_parameters['hsi_hi'] - Network_parameters['hsi_lo']
+        return SpectralUNET(depth, num_classes, bn_feats=Network_parameters['spectral_bn_size'])
+    if model_name == 'CubeNET':
+        depth = Network_parameters['hsi_hi'] - Network_parameters['hsi_lo']
+        return CubeNET(depth, num_classes, first_depth=Network_parameters['3d_featmaps'],
+                       bilinear=Network_parameters['bilinear'], use_attention=Network_parameters['use_attention'],
+                       analyze=analyze)
+    raise RuntimeError('Invalid model')
+
+
+def translate_load_dir(model_name, net_params):
+    """models.py:279-292."""
+    if model_name == 'SpectralUNET':
+        return f"{model_name}_{net_params['spectral_bn_size']}"
+    if model_name == 'CubeNET':
+        return f"{model_name}_{net_params['3d_featmaps']}"
+    return "UNET"

@@ -24,11 +24,17 @@ extern "C" {
 #define HPRI_ERR_TENSORMAP (-4) /* the driver rejected a tensor map */
 #define HPRI_ERR_CUDA (-5)      /* launch failed; see cudaGetLastError */
 
-/* NHWC bf16 view: element strides; c = logical channels visible through the view. */
+#define HPRI_BF16 0
+#define HPRI_F16 1
+
+/* NHWC view of a 16-bit tensor (dtype HPRI_BF16 or HPRI_F16): element strides; c = logical channels
+ * visible through the view.  Forward activations are fp16 (BatchNorm keeps them O(1); 11-bit mantissa),
+ * gradients bf16 (fp32 exponent range, no loss scaling); all accumulation is fp32. */
 typedef struct {
   void* ptr;
   int n, h, w, c;
   long long pix_stride, row_stride, img_stride;
+  int dtype;
 } hpri_view_t;
 
 int hpri_abi_version(void);
@@ -39,15 +45,16 @@ int hpri_abi_version(void);
  * or 1 (1x1 / Linear).  Replaces nn.Conv2d 3x3 fprop AND dgrad (model_parts.py:22,25 -- dgrad uses a
  * transposed/flipped pack), Conv3d(1,64,(D,3,3)) (models.py:169), nn.Linear (models.py:108,102).
  * stats (nullable): double[w_rows][2] accumulating per-channel sum / sum-of-squares of the bf16
- * outputs for train-mode BatchNorm (model_parts.py:23,26; models.py:113,172,178). */
-int hpri_igemm_fwd(const hpri_view_t* x, const void* wpack, int w_rows, int kpad, int taps, const hpri_view_t* y,
-                   int n_store, const float* bias, double* stats, int block_n, void* stream);
+ * outputs for train-mode BatchNorm (model_parts.py:23,26; models.py:113,172,178).
+ * accumulate=1: y += result (skip-gradient accumulation), not combinable with stats. */
+int hpri_igemm_fwd(const hpri_view_t* x, const void* wpack, int w_dtype, int w_rows, int kpad, int taps, const hpri_view_t* y,
+                   int n_store, const float* bias, double* stats, int accumulate, int block_n, void* stream);
 
 /* nn.ConvTranspose2d(k=2,s=2) fprop writing straight into the concat buffer (model_parts.py:63-64,
  * 74-87: pad + cat are absorbed by the destination view) and its dgrad. */
-int hpri_convT2x2_fwd(const hpri_view_t* x, const void* wpack, int cout, int kpad, const hpri_view_t* y,
+int hpri_convT2x2_fwd(const hpri_view_t* x, const void* wpack, int w_dtype, int cout, int kpad, const hpri_view_t* y,
                       const float* bias, int block_n, void* stream);
-int hpri_convT2x2_dgrad(const hpri_view_t* dy, const void* wpack, int cin, int kpad, const hpri_view_t* dx,
+int hpri_convT2x2_dgrad(const hpri_view_t* dy, const void* wpack, int w_dtype, int cin, int kpad, const hpri_view_t* dx,
                         int block_n, void* stream);
 
 /* Weight gradients (autograd of the three layer kinds above). mode 0 Linear/1x1, 1 conv3x3, 2 convT2x2.
@@ -57,8 +64,8 @@ int hpri_igemm_wgrad(const hpri_view_t* x, const hpri_view_t* dy, int mode, int 
 
 /* ---- weight layout conversion (csrc/elementwise.cu) -------------------------------------
  * dst[(g*R + r)][t*kc64 + c] = c < C ? src[g*sg + r*sr + tm(t)*st + c*sc] : 0,  tm(t) = flip ? T-1-t : t.
- * pack: fp32 torch-layout parameter -> bf16 operand.  unpack: fp32 packed gradient -> fp32 torch layout. */
-int hpri_pack_weights(const float* src, void* dst_bf16, int G, int R, int T, int C, int kc64, long long sg,
+ * pack: fp32 torch-layout parameter -> 16-bit operand (dst_dtype).  unpack: fp32 packed gradient -> fp32 torch layout. */
+int hpri_pack_weights(const float* src, void* dst, int dst_dtype, int G, int R, int T, int C, int kc64, long long sg,
                       long long sr, long long st, long long sc, int flip, void* stream);
 int hpri_unpack_grads(const float* packed, float* dst, int G, int R, int T, int C, int kc64, long long sg,
                       long long sr, long long st, long long sc, int flip, float beta, void* stream);
@@ -66,11 +73,15 @@ int hpri_unpack_grads(const float* packed, float* dst, int G, int R, int T, int 
 /* ---- ingest (src/dataset.py:266-270, 284-289) -------------------------------------------
  * src: fp32 [n][bands_total][H][W]; keeps bands [lo,hi), crops the (i0,j0,h,w) window, optional
  * horizontal / vertical flip, optional scalar rescale (the '/255 if max>10' rule is decided by the caller
- * with hpri_absmax), optional per-band (x-mean)/std; writes NHWC bf16 with c_pad channels (zero filled). */
+ * with hpri_absmax), optional per-band (x-mean)/std; writes NHWC 16-bit (dst_dtype) with c_pad channels (zero filled). */
 int hpri_hsi_ingest(const float* src, int n, int bands_total, int H, int W, int lo, int hi, int i0, int j0, int h,
                     int w, int flip_h, int flip_w, float scale, const float* band_mean, const float* band_std,
-                    void* dst_bf16, int c_pad, void* stream);
+                    void* dst, int dst_dtype, int c_pad, void* stream);
 int hpri_absmax(const float* src, long long numel, float* out_max, void* stream);
+
+/* y = x converted between HPRI_F16 and HPRI_BF16 (tcgen05 kind::f16 requires both operands of one
+ * MMA in the same format: wgrad pairs a bf16 copy of the fp16 activations with the bf16 gradients). */
+int hpri_convert16(const hpri_view_t* x, const hpri_view_t* y, void* stream);
 
 /* ---- BatchNorm / ReLU / MaxPool family ---------------------------------------------------- */
 /* Turn accumulated (sum, sumsq) into scale/shift, saved mean/invstd, and the running-stat update

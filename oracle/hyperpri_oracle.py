@@ -62,6 +62,8 @@ def synth_state_dict(schema: Dict[str, Tuple[int, ...]], seed: int = 0) -> Dict[
             out[k] = torch.from_numpy(r.uniform(0.5, 1.5, shp).astype(np.float32))
         else:                                      # BN beta
             out[k] = torch.from_numpy(r.uniform(-0.2, 0.2, shp).astype(np.float32))
+    if "first_conv.weight" in out and "inc.0.weight" in out:   # CubeNET registers one Conv3d twice
+        out["inc.0.weight"], out["inc.0.bias"] = out["first_conv.weight"], out["first_conv.bias"]
     return out
 
 
@@ -166,6 +168,39 @@ def band_normalise(x: torch.Tensor, mean_b: torch.Tensor, std_b: torch.Tensor) -
 
 
 # --------------------------------------------------------------------------------------
+# storage-precision emulation
+# --------------------------------------------------------------------------------------
+class _RoundBF16(torch.autograd.Function):
+    """Round to fp16 in forward AND round the incoming gradient to bf16 in backward: models a
+    tensor the B200 path stores in fp16 between kernels and whose gradient it stores in bf16."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.to(torch.float16).to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.bfloat16).to(torch.float32)
+
+
+_QUANT = False
+
+
+def emulate_bf16_storage(on: bool):
+    """With emulation on, the oracle rounds weights, conv/linear outputs and activations to fp16 and
+    their gradients to bf16 at exactly the points where hyperpri_b200 stores them (fp32 accumulation
+    and fp32 BatchNorm statistics are kept).  The fp32 oracle (off, default) is the parity
+    reference; the emulated oracle separates implementation errors from storage-precision
+    effects in tests."""
+    global _QUANT
+    _QUANT = bool(on)
+
+
+def q(x):
+    return _RoundBF16.apply(x) if _QUANT else x
+
+
+# --------------------------------------------------------------------------------------
 # layers
 # --------------------------------------------------------------------------------------
 def batch_norm(x, sd, pre, training, stats_out=None, ch_axis=1):
@@ -191,43 +226,55 @@ def batch_norm(x, sd, pre, training, stats_out=None, ch_axis=1):
     return xh * sd[pre + ".weight"].view(shp) + sd[pre + ".bias"].view(shp)
 
 
-def double_conv(x, sd, pre, training, stats_out=None):
-    """(conv3x3 pad 1 -> BN -> ReLU) x 2  (model_parts.py:14-31)."""
-    for i in (0, 3):
-        x = F.conv2d(x, sd[f"{pre}.{i}.weight"], sd[f"{pre}.{i}.bias"], padding=1)
-        x = torch.relu(batch_norm(x, sd, f"{pre}.{i + 1}", training, stats_out))
-    return x
+def _cbr(x, w, b, sd, bn, training, stats_out, quant_out=True):
+    """conv3x3 pad 1 -> BatchNorm -> ReLU.  (Emulation: the bias-free conv output is what is stored.)"""
+    x = q(F.conv2d(x, q(w), None, padding=1)) + b.view(1, -1, 1, 1)
+    x = torch.relu(batch_norm(x, sd, bn, training, stats_out))
+    return q(x) if quant_out else x
 
 
-def down(x, sd, pre, training, stats_out=None):
-    """MaxPool2d(2) (floor) -> DoubleConv  (model_parts.py:34-45)."""
-    return double_conv(F.max_pool2d(x, 2), sd, pre + ".maxpool_conv.1.double_conv", training, stats_out)
+def double_conv(x, sd, pre, training, stats_out=None, quant_out=True):
+    """(conv3x3 pad 1 -> BN -> ReLU) x 2  (model_parts.py:14-31).  With quant_out=False the last
+    activation stays fp32 (the B200 path never stores the tensor the 1x1 head or a pool+skip pair
+    consumes; see emulate_bf16_storage)."""
+    x = _cbr(x, sd[f"{pre}.0.weight"], sd[f"{pre}.0.bias"], sd, f"{pre}.1", training, stats_out)
+    return _cbr(x, sd[f"{pre}.3.weight"], sd[f"{pre}.3.bias"], sd, f"{pre}.4", training, stats_out, quant_out)
 
 
-def up(x1, x2, sd, pre, training, stats_out=None):
+def down(x, sd, pre, training, stats_out=None, quant_out=True):
+    """MaxPool2d(2) (floor) -> DoubleConv  (model_parts.py:34-45).  x is the fp32 activation of the
+    level above; the pooled copy and the skip copy are separately stored tensors."""
+    return double_conv(q(F.max_pool2d(x, 2)), sd, pre + ".maxpool_conv.1.double_conv", training, stats_out,
+                       quant_out)
+
+
+def up(x1, x2, sd, pre, training, stats_out=None, quant_out=True):
     """ConvTranspose2d(k2,s2) -> zero pad to the skip's size (left/top floor(d/2), rest
     right/bottom) -> cat([skip, up]) -> DoubleConv  (model_parts.py:71-90)."""
-    x1 = F.conv_transpose2d(x1, sd[pre + ".up.weight"], sd[pre + ".up.bias"], stride=2)
+    x1 = q(F.conv_transpose2d(x1, q(sd[pre + ".up.weight"]), sd[pre + ".up.bias"], stride=2))
     dy, dx = x2.shape[2] - x1.shape[2], x2.shape[3] - x1.shape[3]
     x1 = F.pad(x1, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])
-    return double_conv(torch.cat([x2, x1], dim=1), sd, pre + ".conv.double_conv", training, stats_out)
+    return double_conv(torch.cat([q(x2), x1], dim=1), sd, pre + ".conv.double_conv", training, stats_out, quant_out)
 
 
 def _unet_body(x1, sd, training, stats_out):
-    x2 = down(x1, sd, "down1", training, stats_out)
-    x3 = down(x2, sd, "down2", training, stats_out)
-    x4 = down(x3, sd, "down3", training, stats_out)
+    """x1 and the other encoder outputs are kept fp32 here: their stored copies are the pooled
+    tensor (down) and the skip half of the concat buffer (up)."""
+    x2 = down(x1, sd, "down1", training, stats_out, quant_out=False)
+    x3 = down(x2, sd, "down2", training, stats_out, quant_out=False)
+    x4 = down(x3, sd, "down3", training, stats_out, quant_out=False)
     x5 = down(x4, sd, "down4", training, stats_out)
     x = up(x5, x4, sd, "up1", training, stats_out)
     x = up(x, x3, sd, "up2", training, stats_out)
     x = up(x, x2, sd, "up3", training, stats_out)
-    x = up(x, x1, sd, "up4", training, stats_out)
+    x = up(x, x1, sd, "up4", training, stats_out, quant_out=False)
     return F.conv2d(x, sd["outc.conv.weight"], sd["outc.conv.bias"])      # model_parts.py:93-99
 
 
 def unet_forward(x, sd, training=True, stats_out=None):
     """UNet.forward (models.py:53-68), bilinear=False, use_attention=False."""
-    return _unet_body(double_conv(x, sd, "inc.double_conv", training, stats_out), sd, training, stats_out)
+    return _unet_body(double_conv(q(x), sd, "inc.double_conv", training, stats_out, quant_out=False), sd, training,
+                      stats_out)
 
 
 def cubenet_forward(x, sd, training=True, stats_out=None):
@@ -235,10 +282,8 @@ def cubenet_forward(x, sd, training=True, stats_out=None):
     spanning every band and pad (0,1,1) is restated as the 2-D conv it equals
     (SURVEY.md appendix B.3): x is N x 1 x D x R x C."""
     w = sd["first_conv.weight"]
-    x1 = F.conv2d(x[:, 0], w[:, 0], sd["first_conv.bias"], padding=1)
-    x1 = torch.relu(batch_norm(x1, sd, "inc.1", training, stats_out))
-    x1 = F.conv2d(x1, sd["inc2.0.weight"], sd["inc2.0.bias"], padding=1)
-    x1 = torch.relu(batch_norm(x1, sd, "inc2.1", training, stats_out))
+    x1 = _cbr(q(x[:, 0]), w[:, 0], sd["first_conv.bias"], sd, "inc.1", training, stats_out)
+    x1 = _cbr(x1, sd["inc2.0.weight"], sd["inc2.0.bias"], sd, "inc2.1", training, stats_out, quant_out=False)
     return _unet_body(x1, sd, training, stats_out)
 
 
@@ -252,14 +297,14 @@ def spectralunet_forward(x, sd, training=True, stats_out=None):
 
     def blk(t, nm):
         so = {} if stats_out is not None else None
-        t = F.linear(t, sd[nm + ".0.weight"], sd[nm + ".0.bias"])
-        t = torch.relu(batch_norm(t, cur, nm + ".1", training, so, ch_axis=1))
+        t = q(F.linear(t, q(sd[nm + ".0.weight"]), None)) + sd[nm + ".0.bias"]
+        t = q(torch.relu(batch_norm(t, cur, nm + ".1", training, so, ch_axis=1)))
         if so:
             cur.update(so)        # running stats advance once per image
         return t
 
     for i in range(n):
-        x0 = blk(rast[i], "tail")
+        x0 = blk(q(rast[i]), "tail")
         x1 = blk(x0, "down1")
         x2 = blk(x1, "down2")
         x3 = blk(x2, "down3")

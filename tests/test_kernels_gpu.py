@@ -20,11 +20,14 @@ def _no_tf32():
     yield
 
 
-def nhwc(x_nchw, cpad=None):
+BF, FH = torch.bfloat16, torch.float16
+
+
+def nhwc(x_nchw, cpad=None, dt=BF):
     n, c, h, w = x_nchw.shape
     cpad = cpad or c
-    out = torch.zeros((n, h, w, cpad), dtype=torch.bfloat16, device=x_nchw.device)
-    out[..., :c] = x_nchw.permute(0, 2, 3, 1).to(torch.bfloat16)
+    out = torch.zeros((n, h, w, cpad), dtype=dt, device=x_nchw.device)
+    out[..., :c] = x_nchw.permute(0, 2, 3, 1).to(dt)
     return out
 
 
@@ -54,22 +57,23 @@ CONV_CASES = [
 ]
 
 
+@pytest.mark.parametrize("dt", [BF, FH])
 @pytest.mark.parametrize("n,h,w,cin,cout,bn", CONV_CASES)
-def test_conv3x3_fwd_and_stats(n, h, w, cin, cout, bn):
+def test_conv3x3_fwd_and_stats(n, h, w, cin, cout, bn, dt):
     x = rnd(n, cin, h, w, seed=1)
     wt = rnd(cout, cin, 3, 3, scale=1 / math.sqrt(cin * 9), seed=2)
-    xb = nhwc(x)
+    xb = nhwc(x, dt=dt)
     spec = ops.WeightSpec("conv3x3", cout, cin)
-    wp = spec.pack_fwd(wt)
-    y = torch.full((n, h, w, cout), float("nan"), dtype=torch.bfloat16, device=DEV)
+    wp = spec.pack_fwd(wt, dtype=dt)
+    y = torch.full((n, h, w, cout), float("nan"), dtype=dt, device=DEV)
     stats = torch.zeros((cout, 2), dtype=torch.float64, device=DEV)
     ops.igemm_fwd(xb, wp, cout, 9, y, cout, stats=stats, block_n=bn)
     torch.cuda.synchronize()
-    ref = F.conv2d(nchw(xb), wt.to(torch.bfloat16).float(), padding=1)
+    ref = F.conv2d(nchw(xb), wt.to(dt).float(), padding=1)
     got = nchw(y)
     assert torch.isfinite(got).all()
-    # bf16 output rounding: half-ulp relative 2^-9 of each value, fp32 accumulation order differences
-    assert relerr(got, ref) < 6e-3
+    # output rounding: half-ulp relative 2^-9 (bf16) / 2^-12 (fp16); fp32 accumulation order differences
+    assert relerr(got, ref) < (6e-3 if dt == BF else 8e-4)
     g64 = y.double().reshape(-1, cout)
     assert torch.allclose(stats[:, 0], g64.sum(0), rtol=1e-6, atol=1e-3)
     assert torch.allclose(stats[:, 1], (g64 * g64).sum(0), rtol=1e-6, atol=1e-3)
@@ -81,7 +85,7 @@ def test_conv3x3_dgrad(n, h, w, cin, cout, bn):
     wt = rnd(cout, cin, 3, 3, scale=1 / math.sqrt(cout * 9), seed=4)
     dyb = nhwc(dy)
     spec = ops.WeightSpec("conv3x3", cout, cin)
-    wp = spec.pack_dgrad(wt)
+    wp = spec.pack_dgrad(wt, dtype=BF)
     cpad = (cin + 7) // 8 * 8
     dx = torch.full((n, h, w, cpad), float("nan"), dtype=torch.bfloat16, device=DEV)
     ops.igemm_fwd(dyb, wp, cin, 9, dx, cpad, block_n=bn)
@@ -90,11 +94,13 @@ def test_conv3x3_dgrad(n, h, w, cin, cout, bn):
     assert relerr(nchw(dx, cin), ref) < 6e-3
 
 
+@pytest.mark.parametrize("xdt,gdt", [(BF, BF), (FH, FH)])
 @pytest.mark.parametrize("n,h,w,cin,cout,bn", CONV_CASES)
-def test_conv3x3_wgrad(n, h, w, cin, cout, bn):
+def test_conv3x3_wgrad(n, h, w, cin, cout, bn, xdt, gdt):
+    """Both operands of one tcgen05.mma kind::f16 must share a format (mixed f16 x bf16 faults on B200)."""
     x = rnd(n, cin, h, w, seed=5)
     dy = rnd(n, cout, h, w, seed=6)
-    xb, dyb = nhwc(x), nhwc(dy)
+    xb, dyb = nhwc(x, dt=xdt), nhwc(dy, dt=gdt)
     spec = ops.WeightSpec("conv3x3", cout, cin)
     dwp = spec.grad_buffer(DEV)
     ops.igemm_wgrad(xb, dyb, 1, cout, dwp, block_n=bn)
@@ -118,7 +124,7 @@ def test_convT(n, h, w, cin, cout, H2, W2):
     spec = ops.WeightSpec("convT2x2", cout, cin)
     # destination: second half of a (2*cout)-channel concat buffer at skip resolution H2 x W2
     cat = torch.zeros((n, H2, W2, 2 * cout), dtype=torch.bfloat16, device=DEV)
-    ops.convT_fwd(xb, spec.pack_fwd(wt), cout, cat[..., cout:], bias=bias)
+    ops.convT_fwd(xb, spec.pack_fwd(wt, dtype=BF), cout, cat[..., cout:], bias=bias)
     torch.cuda.synchronize()
     wq = wt.to(torch.bfloat16).float()
     ref = F.conv_transpose2d(nchw(xb), wq, bias, stride=2)
@@ -130,7 +136,7 @@ def test_convT(n, h, w, cin, cout, H2, W2):
     dcat[..., cout:] = nhwc(rnd(n, cout, H2, W2, seed=10))
     dyv = dcat[..., cout:]
     dx = torch.full((n, h, w, cin), float("nan"), dtype=torch.bfloat16, device=DEV)
-    ops.convT_dgrad(dyv, spec.pack_dgrad(wt), cin, dx)
+    ops.convT_dgrad(dyv, spec.pack_dgrad(wt, dtype=BF), cin, dx)
     dwp = spec.grad_buffer(DEV)
     ops.igemm_wgrad(xb, dyv, 2, 4 * cout, dwp)
     dw = torch.empty_like(wt)
@@ -167,7 +173,7 @@ def test_linear(m, fin, fout, split):
     spec = ops.WeightSpec("linear", fout, fin, split=split)
     y = torch.full((1, 1, m, pad(fout)), float("nan"), dtype=torch.bfloat16, device=DEV)
     stats = torch.zeros((fout, 2), dtype=torch.float64, device=DEV)
-    ops.igemm_fwd(buf, spec.pack_fwd(wt), fout, 1, y, pad(fout), stats=stats)
+    ops.igemm_fwd(buf, spec.pack_fwd(wt, dtype=BF), fout, 1, y, pad(fout), stats=stats)
     torch.cuda.synchronize()
     wq = wt.to(torch.bfloat16).float()
     ref = xfull @ wq.t()
@@ -184,28 +190,42 @@ def test_linear(m, fin, fout, split):
     assert relerr(dw, dy[0, 0, :, :fout].float().t() @ xfull) < 2e-4
     if not split:
         dx = torch.full((1, 1, m, pad(fin)), float("nan"), dtype=torch.bfloat16, device=DEV)
-        ops.igemm_fwd(dy, spec.pack_dgrad(wt), fin, 1, dx, pad(fin), x_c=fout)
+        ops.igemm_fwd(dy, spec.pack_dgrad(wt, dtype=BF), fin, 1, dx, pad(fin), x_c=fout)
         torch.cuda.synchronize()
         assert relerr(dx[0, 0, :, :fin].float(), dy[0, 0, :, :fout].float() @ wq) < 6e-3
+
+
+def test_mixed_format_rejected_and_convert():
+    x = nhwc(rnd(1, 64, 8, 8, seed=40), dt=FH)
+    dy = nhwc(rnd(1, 64, 8, 8, seed=41), dt=BF)
+    spec = ops.WeightSpec("conv3x3", 64, 64)
+    with pytest.raises(RuntimeError, match="HPRI_ERR_ARG"):
+        ops.igemm_wgrad(x, dy, 1, 64, spec.grad_buffer(DEV))
+    xb = torch.empty_like(x, dtype=BF)
+    ops.convert16(x, xb)
+    assert torch.equal(xb, x.to(BF))
 
 
 def test_ingest_exact():
     """Band slice / crop / flip / layout are pure indexing: exact up to the bf16 cast (dataset.py:266-270)."""
     src = torch.rand((2, 299, 20, 37), device=DEV)
-    out = ops.hsi_ingest(src, 25, 263, c_pad=240)
+    out = ops.hsi_ingest(src, 25, 263, c_pad=240, dtype=FH)
+    assert torch.equal(out[..., :238], src[:, 25:263].permute(0, 2, 3, 1).to(FH))
+    out = ops.hsi_ingest(src, 25, 263, c_pad=240, dtype=BF)
     ref = src[:, 25:263].permute(0, 2, 3, 1).to(torch.bfloat16)
     assert torch.equal(out[..., :238], ref) and (out[..., 238:] == 0).all()
-    out = ops.hsi_ingest(src, 25, 263, crop=(3, 5, 12, 30), flip_w=True, c_pad=240)
+    out = ops.hsi_ingest(src, 25, 263, crop=(3, 5, 12, 30), flip_w=True, c_pad=240, dtype=BF)
     ref = src[:, 25:263, 3:15, 5:35].flip(-1).permute(0, 2, 3, 1).to(torch.bfloat16)
     assert torch.equal(out[..., :238], ref)
     mean = torch.rand(238, device=DEV)
     std = torch.rand(238, device=DEV) + 0.5
-    out = ops.hsi_ingest(src * 255, 25, 263, flip_h=True, scale=1 / 255, band_mean=mean, band_std=std, c_pad=240)
+    out = ops.hsi_ingest(src * 255, 25, 263, flip_h=True, scale=1 / 255, band_mean=mean, band_std=std, c_pad=240,
+                         dtype=BF)
     ref = ((src[:, 25:263] * 255 * (1 / 255) - mean[:, None, None]) / std[:, None, None]).flip(-2)
     assert (out[..., :238].float() - ref.permute(0, 2, 3, 1)).abs().max() < 2e-2
     assert ops.absmax(src * 255).item() == (src * 255).abs().max().item()
     rgb = torch.rand((2, 3, 9, 70), device=DEV)
-    out = ops.hsi_ingest(rgb, 0, 3, c_pad=8)
+    out = ops.hsi_ingest(rgb, 0, 3, c_pad=8, dtype=BF)
     assert torch.equal(out[..., :3], rgb.permute(0, 2, 3, 1).to(torch.bfloat16)) and (out[..., 3:] == 0).all()
 
 
