@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""Headline benchmark: train images/s (238x608x968 HSI cubes, forward + loss + backward) of CubeNET-64,
+batch 2 per GPU, data-parallel over N B200s (BASELINE.json configs[2]; metric quoted at 1/2/4/8 GPUs).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+For N > 1 launch with torchrun (one rank per GPU, NCCL).  Rank 0 prints ONE JSON line.
+  value     images/s with the fp32 cube already resident in HBM (ingest, weight re-pack, forward, BCE, backward,
+            gradient all-reduce are all inside the timed region; optimizer excluded, as SURVEY.md section 8d defines)
+  e2e       the same through the public nn.Module API with PINNED HOST inputs: H2D of every step's cube + mask and
+            a D2H read of the loss inside the timed region (double-buffered copy stream)
+  roofline  the tcgen05 implicit-GEMM family (every conv / convT fwd, dgrad, wgrad launch): algorithmic FLOPs per
+            step / summed CUDA-event durations of those launches, against the measured sustained bf16 peak
+  cpu_baseline  the CPU oracle (a port of the reference's arithmetic) on this box's host cores, bounded sample
+--impl reference times that CPU path alone (the reference is pure Python/PyTorch).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GF_PER_IMG = {"CubeNET": 2910.2, "UNET": 2591.5}          # fwd+bwd GFLOP / image at 608x968
+H, W, BANDS = 608, 968, 238
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("bf16_tflops_sustained", 1393.2), d.get("hbm_gbs", 6543.7), "measured (MEASURED_PEAKS.json, sustained)"
+    return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.path = gpu_index, None, f"/tmp/hpri_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [s.strip() for s in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if sm:
+            sm.sort()
+            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return out
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+def cpu_steps(model, n_img, h, w, steps, warmup):
+    """Time `steps` fwd+bwd passes of the CPU oracle on n_img x 238 x h x w; returns (sec/step list)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import hyperpri_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    schema = O.unet_schema(1, 1, "cube", hsi_depth=BANDS) if model == "CubeNET" else O.unet_schema(3, 1, "unet")
+    sd = O.synth_state_dict(schema, 0)
+    bands = BANDS if model == "CubeNET" else 3
+    x = O.synth_cube(0, n_img, bands, h, w)
+    x = x[:, None] if model == "CubeNET" else x
+    mask = O.synth_mask(0, n_img, h, w)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.forward_backward(model, x, mask, sd, training=True)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count()
+    # bounded sample: one image per step; shrink to a row strip if K+W full images would take too long
+    t_probe = cpu_steps(args.model, 1, 64, W, 1, 0)[0]                 # 64-row strip probe
+    est_full = t_probe * H / 64.0
+    budget = 150.0
+    rows = H
+    if est_full * (args.steps + args.warmup) > budget:
+        rows = max(64, int(H * budget / (est_full * (args.steps + args.warmup))) // 16 * 16)
+    times = cpu_steps(args.model, 1, rows, W, args.steps, args.warmup)
+    sec = sum(times) / len(times)
+    img_s = (rows / H) / sec
+    sample = f"1 image x {BANDS} x {rows} x {W} per step (rows/{H} of an image, throughput scaled by pixel count), fp32, train mode"
+    line = {
+        "impl": "reference", "metric": "train images/s (238x608x968 HSI, fwd+bwd)", "value": img_s, "unit": "images/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.model}-64 fwd+loss+bwd, CPU, reference arithmetic (oracle port; the reference is "
+                               "pure PyTorch and cannot travel to the GPU box)", "threads": torch.get_num_threads()},
+        "cpu_baseline": {"value": img_s, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": img_s, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--model", default="CubeNET", choices=["CubeNET", "UNET"])
+    ap.add_argument("--batch", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--breakdown", default=None, help="write a per-kernel time breakdown JSON here")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from hyperpri_b200 import _lib, ops, parallel
+    from hyperpri_b200.src.Experiments.models import CubeNET, UNet
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W_ = max(3, args.warmup)
+
+    torch.manual_seed(1234 + rank)
+    n = args.batch
+    if args.model == "CubeNET":
+        net = CubeNET(BANDS, 1, first_depth=64, bilinear=False).to(dev).train()
+        x = torch.rand((n, 1, BANDS, H, W), device=dev)
+    else:
+        net = UNet(3, 1, bilinear=False).to(dev).train()
+        x = torch.rand((n, 3, H, W), device=dev)
+    mask = (torch.rand((n, 1, H, W), device=dev) > 0.95).float()
+    eng = net._get_engine(dev)
+    red = parallel.attach(eng)
+    gscale = red.grad_scale()
+
+    def invalidate():
+        for grp in list(eng.enc) + list(eng.dec.values()):
+            for L in grp:
+                L.pp.key = None
+        for u in eng.up.values():
+            u.key = None
+
+    def step():
+        invalidate()                                   # weights change every optimizer step: re-pack inside the step
+        logits = eng.forward(x, True)
+        _, dlogit, _ = eng.loss_and_dlogit(logits, mask, grad_scale=gscale)
+        eng.backward(dlogit)
+        red.finish()
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W_):
+        step()
+    sync()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.lib().hpri_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    sync()
+    launches = _lib.lib().hpri_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = ms.item()
+    ms_step = ms_total / args.steps
+    value = n * world * args.steps / (ms_total / 1e3)
+
+    # ---------------- per-kernel durations (CUDA events around every native call; separate pass)
+    prof_steps = 2
+    ops.PROFILE = []
+    for _ in range(prof_steps):
+        step()
+    torch.cuda.synchronize()
+    rec, ops.PROFILE = ops.PROFILE, None
+    per = {}
+    for name, a, b in rec:
+        t = a.elapsed_time(b)
+        d = per.setdefault(name, [0.0, 0])
+        d[0] += t / prof_steps
+        d[1] += 1
+    tensor_ms = sum(v[0] for k, v in per.items() if k in ops.TENSOR_KERNELS)
+    tensor_launches = sum(v[1] for k, v in per.items() if k in ops.TENSOR_KERNELS) // prof_steps
+    all_ms = sum(v[0] for v in per.values())
+    peak_tf, peak_gbs, peak_src = peaks()
+    flops_step = GF_PER_IMG[args.model] * 1e9 * n
+    achieved = flops_step / (tensor_ms / 1e3) / 1e12 if tensor_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "kernel": "igemm_kernel<BLOCK_N,STAGES,MODE> (tcgen05 implicit GEMM: conv3x3/convT fwd, dgrad, wgrad)",
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                "peak_source": peak_src, "flops_per_step": flops_step, "kernel_ms_per_step": tensor_ms,
+                "launches_per_step": tensor_launches, "share_of_step": tensor_ms / all_ms if all_ms else None}
+    if args.breakdown and rank == 0:
+        with open(args.breakdown, "w") as f:
+            json.dump({"ms_per_step_sum_of_kernels": all_ms, "ms_per_step_wall": ms_step,
+                       "kernels": {k: {"ms_per_step": v[0], "launches_per_step": v[1] / prof_steps} for k, v in
+                                   sorted(per.items(), key=lambda kv: -kv[1][0])}}, f, indent=1)
+
+    # ---------------- end to end through the public API with host inputs
+    e2e = None
+    if not args.no_e2e:
+        crit = torch.nn.BCEWithLogitsLoss()
+        xh = [torch.rand(x.shape).pin_memory() for _ in range(2)]
+        mh = [(torch.rand(mask.shape) > 0.95).float().pin_memory() for _ in range(2)]
+        xd = [torch.empty_like(x) for _ in range(2)]
+        md = [torch.empty_like(mask) for _ in range(2)]
+        copy_stream = torch.cuda.Stream()
+        ready = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+
+        def prefetch(i):
+            b = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[b])
+                xd[b].copy_(xh[b], non_blocking=True)
+                md[b].copy_(mh[b], non_blocking=True)
+                ready[b].record(copy_stream)
+
+        def e2e_step(i):
+            b = i % 2
+            prefetch(i + 1)                         # next step's H2D overlaps this step's compute
+            torch.cuda.current_stream().wait_event(ready[b])
+            net.zero_grad(set_to_none=True)
+            logits = net(xd[b])
+            loss = crit(logits, md[b])
+            loss.backward()
+            red.finish()
+            consumed[b].record()
+            return loss.item()                      # D2H read of the step's result
+
+        total = W_ + args.steps
+        for b in range(2):
+            consumed[b].record()
+        prefetch(0)
+        for i in range(W_):
+            e2e_step(i)
+        sync()
+        t0 = time.perf_counter()
+        for i in range(W_, total):
+            e2e_step(i)
+        sync()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": n * world * args.steps / dt.item(), "unit": "images/s",
+               "h2d_bytes_per_step": x.numel() * 4 + mask.numel() * 4, "d2h_bytes_per_step": 4,
+               "ms_per_step": dt.item() / args.steps * 1e3}
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        t = cpu_steps(args.model, 1, H, W, 1, 0)[0]
+        cpu_base = {"value": 1.0 / t, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+                    "sample": f"1 step of 1 x {BANDS} x {H} x {W} (one full image), fp32 oracle fwd+loss+bwd, no warm-up"}
+
+    if rank == 0:
+        line = {
+            "metric": "train images/s (238x608x968 HSI, fwd+bwd)", "value": value, "unit": "images/s", "n_gpus": world,
+            "steps": args.steps, "warmup": W_, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16 activations / bf16 gradients, f32 accumulate (tcgen05 kind::f16)",
+            "data": "synthetic",
+            "config": {"workload": f"{args.model}-64 n_channels=238 (hsi 25..263), patch 608x968, batch {n} per GPU, "
+                                   "data-parallel (BASELINE.json configs[2])",
+                       "global_batch": n * world, "parallelism": f"dp{world}",
+                       "l2": "inputs larger than L2 (1.1 GB fp32 cube + >3 GB activations per step); no explicit flush",
+                       "timed_region": "weight re-pack + ingest + forward + BCE + backward + grad all-reduce"},
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_base, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -25,6 +25,7 @@ _p, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 # name -> argtypes; every symbol include/hyperpri_b200.h declares
 SIGNATURES = {
     "hpri_abi_version": [],
+    "hpri_launch_count": [],
     "hpri_igemm_fwd": [_VP, _p, _i, _i, _i, _i, _VP, _i, _p, _p, _i, _i, _p],
     "hpri_convT2x2_fwd": [_VP, _p, _i, _i, _i, _VP, _p, _i, _p],
     "hpri_convT2x2_dgrad": [_VP, _p, _i, _i, _i, _VP, _i, _p],
@@ -66,7 +67,7 @@ def lib():
         for name, args in SIGNATURES.items():
             fn = getattr(l, name)          # AttributeError if the .so is stale
             fn.argtypes = args
-            fn.restype = C.c_int
+            fn.restype = C.c_longlong if name == "hpri_launch_count" else C.c_int
         _lib = l
     return _lib
 

@@ -7,6 +7,8 @@
 
 namespace hpri {
 
+long long g_launch_count = 0;
+
 static inline int check_view_e(const hpri_view_t* v) {
   if (!v || !v->ptr || v->n <= 0 || v->h <= 0 || v->w <= 0 || v->c <= 0) return HPRI_ERR_ARG;
   if ((reinterpret_cast<uintptr_t>(v->ptr) & 15) || (v->pix_stride & 7) || (v->row_stride & 7) || (v->img_stride & 7))
@@ -15,7 +17,10 @@ static inline int check_view_e(const hpri_view_t* v) {
   if (v->dtype != DT_BF16 && v->dtype != DT_F16) return HPRI_ERR_ARG;
   return HPRI_OK;
 }
-static inline int last_err() { return cudaGetLastError() == cudaSuccess ? HPRI_OK : HPRI_ERR_CUDA; }
+static inline int last_err(int launches = 1) {
+  g_launch_count += launches;
+  return cudaGetLastError() == cudaSuccess ? HPRI_OK : HPRI_ERR_CUDA;
+}
 
 struct V {   // device-side copy of a view (16-bit elements, format dt)
   uint16_t* p;
@@ -505,7 +510,8 @@ static inline int grid_for(long long work_items, int per_block, int cap = 148 * 
 
 using namespace hpri;
 
-extern "C" int hpri_abi_version(void) { return 1; }
+extern "C" int hpri_abi_version(void) { return 2; }
+extern "C" long long hpri_launch_count(void) { return g_launch_count; }
 
 extern "C" int hpri_pack_weights(const float* src, void* dst, int dst_dtype, int G, int R, int T, int C, int kc64,
                                  long long sg, long long sr, long long st, long long sc, int flip, void* stream) {
@@ -678,7 +684,7 @@ extern "C" int hpri_colsum(const hpri_view_t* x, float* out, float beta, void* s
   const long long npix = (long long)x->n * x->h * x->w;
   colsum_k<<<grid_for(npix, slots * 16, 148 * 4), 256, (size_t)slots * CG * 32, (cudaStream_t)stream>>>(mk(x), out,
                                                                                                        slots, CG);
-  return last_err();
+  return last_err(2);
 }
 extern "C" int hpri_sum_f32(const float* x, long long numel, float* out, void* stream) {
   if (!x || !out || numel <= 0) return HPRI_ERR_ARG;

@@ -449,6 +449,7 @@ static int launch_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensor
   if (attr_err != cudaSuccess) return HPRI_ERR_CUDA;
   if (grid <= 0 || grid > 0x7FFFFFFFLL) return HPRI_ERR_ARG;
   kern<<<(unsigned)grid, kThreads, L::ALLOC, stream>>>(a0, a1, b0, b1, args);
+  ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? HPRI_OK : HPRI_ERR_CUDA;
 }
 

@@ -10,6 +10,8 @@
 
 namespace hpri {
 
+extern long long g_launch_count;   // host-side count of kernels this library launched (hpri_launch_count)
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }

@@ -107,8 +107,44 @@ class UNetEngine:
         self.enc[0][0].gw = self.enc[0][0].pp.spec.grad_buffer(d)
         self.ws = None
         self.ws_key = None
-        self.grads: Dict[str, torch.Tensor] = {}
         self.training_fwd = False
+        self._build_grad_arena()
+        self.bucket_hook = None      # callable(flat_slice) invoked as each gradient bucket is complete
+
+    def _build_grad_arena(self):
+        """One flat fp32 buffer for every parameter gradient, ordered by backward completion
+        (head, decoder top-down, encoder bottom-up) so that contiguous buckets can be all-reduced
+        while the rest of backward is still running."""
+        order, buckets = [], []
+
+        def cbr_names(L):
+            return [L.bn + ".weight", L.bn + ".bias", L.conv + ".weight", L.conv + ".bias"]
+
+        start = 0
+        order += ["outc.conv.bias", "outc.conv.weight"]
+        for l in (0, 1, 2, 3):
+            a, b = self.dec[l]
+            order += cbr_names(b) + cbr_names(a) + [f"up{4 - l}.up.weight", f"up{4 - l}.up.bias"]
+            buckets.append(len(order))
+        for l in (4, 3, 2, 1, 0):
+            a, b = self.enc[l]
+            order += cbr_names(b) + cbr_names(a)
+            buckets.append(len(order))
+        offs, total = {}, 0
+        for nm in order:
+            offs[nm] = total
+            total += self.P[nm].numel()
+        self.arena = torch.zeros(total, dtype=torch.float32, device=self.dev)
+        self.grads = {nm: self.arena[offs[nm]: offs[nm] + self.P[nm].numel()].view(self.P[nm].shape) for nm in order}
+        ends = [offs[order[i]] if i < len(order) else total for i in buckets]
+        self.bucket_bounds = list(zip([0] + ends[:-1], ends))
+        del start
+
+    def _bucket_done(self, idx):
+        if self.bucket_hook is not None:
+            a, b = self.bucket_bounds[idx]
+            if b > a:
+                self.bucket_hook(self.arena[a:b])
 
     # ------------------------------------------------------------------ workspace
     def _workspace(self, n, h, w):
@@ -162,12 +198,8 @@ class UNetEngine:
         if apply:
             ops.bn_relu_apply(raw, L.scale, L.shift, act, pooled)
 
-    def _grad(self, name, like):
-        g = self.grads.get(name)
-        if g is None or g.shape != like.shape:
-            g = torch.zeros_like(like, dtype=torch.float32)
-            self.grads[name] = g
-        return g
+    def _grad(self, name, like=None):
+        return self.grads[name]
 
     def _as_grad_dtype(self, x):
         """bf16 copy of an fp16 activation view in the shared scratch buffer: wgrad needs x and dy in
@@ -271,6 +303,7 @@ class UNetEngine:
             up.spec.unpack_grad(gw, self._grad(wn, P[wn]).view(-1))
             ops.colsum(dy_up, self._grad(f"up{i}.up.bias", P[f"up{i}.up.bias"]))
             g_in = ws[f"A{l + 1}"]
+            self._bucket_done(l)
         # encoder, deepest first
         for l in (4, 3, 2, 1, 0):
             a, b = self.enc[l]
@@ -282,6 +315,7 @@ class UNetEngine:
             x_in = ws[f"pool{l}"] if l > 0 else ws["x"]
             self._cbr_bwd(a, x_in, ws[f"enc_raw_a{l}"], ws[f"R{l}"], cnt[l], dy=ws[f"A{l}"],
                           dx_out=ws[f"gpool{l}"] if l > 0 else None)
+            self._bucket_done(4 + (4 - l))
         if self.first == "cube":               # module registered twice (models.py:169-171): same tensor
             self.grads["inc.0.weight"] = self.grads["first_conv.weight"]
             self.grads["inc.0.bias"] = self.grads["first_conv.bias"]

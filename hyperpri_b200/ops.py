@@ -21,6 +21,27 @@ GRAD = bf16      # gradients and dgrad weight operands (fp32 exponent range, no 
 _DT = {bf16: 0, f16: 1}
 
 
+PROFILE = None          # set to a list to record (kernel family, start event, end event) per native call
+TENSOR_KERNELS = {"igemm_fwd", "convT_fwd", "convT_dgrad", "igemm_wgrad"}
+
+
+def _timed(fn):
+    name = fn.__name__
+
+    def wrapper(*a, **k):
+        if PROFILE is None:
+            return fn(*a, **k)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        r = fn(*a, **k)
+        e1.record()
+        PROFILE.append((name, e0, e1))
+        return r
+
+    wrapper.__name__, wrapper.__doc__ = name, fn.__doc__
+    return wrapper
+
+
 def _stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -49,6 +70,7 @@ def kpad(c: int) -> int:
 
 
 # ----------------------------------------------------------------------------- weights
+@_timed
 def pack(src: torch.Tensor, G, R, T, Cc, sg, sr, st, sc, flip=False, out: Optional[torch.Tensor] = None,
          src_offset: int = 0, dtype=None):
     """Generic fp32 parameter -> 16-bit operand [(G*R), T*kpad(C)] (see hpri_pack_weights)."""
@@ -62,6 +84,7 @@ def pack(src: torch.Tensor, G, R, T, Cc, sg, sr, st, sc, flip=False, out: Option
     return out
 
 
+@_timed
 def unpack(packed: torch.Tensor, dst: torch.Tensor, G, R, T, Cc, sg, sr, st, sc, flip=False, beta=0.0):
     assert packed.dtype == torch.float32 and dst.dtype == torch.float32 and dst.is_contiguous()
     check(_lib.lib().hpri_unpack_grads(_ptr(packed), _ptr(dst), G, R, T, Cc, kpad(Cc), sg, sr, st, sc, int(flip),
@@ -110,6 +133,7 @@ class WeightSpec:
 
 
 # ----------------------------------------------------------------------------- contractions
+@_timed
 def igemm_fwd(x, wpack, rows, taps, y, n_store, bias=None, stats=None, block_n=0, x_c=None, y_c=None,
               accumulate=False):
     xv, yv = view(x, x_c), view(y, y_c)
@@ -117,18 +141,21 @@ def igemm_fwd(x, wpack, rows, taps, y, n_store, bias=None, stats=None, block_n=0
                                     _ptr(stats), int(accumulate), block_n, _stream()), "hpri_igemm_fwd")
 
 
+@_timed
 def convT_fwd(x, wpack, cout, y, bias=None, block_n=0):
     xv, yv = view(x), view(y)
     check(_lib.lib().hpri_convT2x2_fwd(_vp(xv), _ptr(wpack), _DT[wpack.dtype], cout, wpack.shape[1], _vp(yv), _ptr(bias), block_n,
                                        _stream()), "hpri_convT2x2_fwd")
 
 
+@_timed
 def convT_dgrad(dy, wpack, cin, dx, block_n=0):
     dv, xv = view(dy), view(dx)
     check(_lib.lib().hpri_convT2x2_dgrad(_vp(dv), _ptr(wpack), _DT[wpack.dtype], cin, wpack.shape[1], _vp(xv), block_n, _stream()),
           "hpri_convT2x2_dgrad")
 
 
+@_timed
 def igemm_wgrad(x, dy, mode, n_total, dw, block_n=0, splits=0, x_c=None, dy_c=None):
     xv, dv = view(x, x_c), view(dy, dy_c)
     assert dw.dtype == torch.float32 and dw.is_contiguous()
@@ -137,6 +164,7 @@ def igemm_wgrad(x, dy, mode, n_total, dw, block_n=0, splits=0, x_c=None, dy_c=No
 
 
 # ----------------------------------------------------------------------------- ingest
+@_timed
 def hsi_ingest(src, lo, hi, crop=None, flip_h=False, flip_w=False, scale=1.0, band_mean=None, band_std=None,
                c_pad=None, out=None, dtype=None):
     """src fp32 [N, bands, H, W] -> NHWC 16-bit [N, h, w, c_pad]."""
@@ -154,6 +182,7 @@ def hsi_ingest(src, lo, hi, crop=None, flip_h=False, flip_w=False, scale=1.0, ba
     return out
 
 
+@_timed
 def convert16(x, y, c=None):
     xv, yv = view(x, c), view(y, c)
     check(_lib.lib().hpri_convert16(_vp(xv), _vp(yv), _stream()), "hpri_convert16")
@@ -167,6 +196,7 @@ def absmax(src):
 
 
 # ----------------------------------------------------------------------------- BN / ReLU / pool
+@_timed
 def bn_finalize(stats, count, gamma, beta, conv_bias, rmean, rvar, nbt, training, scale, shift, smean, sinv,
                 C_, momentum=0.1, eps=1e-5):
     check(_lib.lib().hpri_bn_finalize(_ptr(stats), count, _ptr(gamma), _ptr(beta), _ptr(conv_bias), _ptr(rmean),
@@ -174,12 +204,14 @@ def bn_finalize(stats, count, gamma, beta, conv_bias, rmean, rvar, nbt, training
                                       _ptr(smean), _ptr(sinv), C_, _stream()), "hpri_bn_finalize")
 
 
+@_timed
 def bn_relu_apply(x, scale, shift, y, pooled=None, c=None):
     xv, yv, pv = view(x, c), view(y, c), view(pooled, c)
     check(_lib.lib().hpri_bn_relu_apply(_vp(xv), _ptr(scale), _ptr(shift), _vp(yv), _vp(pv), _stream()),
           "hpri_bn_relu_apply")
 
 
+@_timed
 def bn_relu_bwd(x, scale, shift, smean, sinv, gamma, dx, sums, count, dy=None, dpool=None, head_w=None,
                 dlogit=None, dgamma=None, dbeta=None, dhead_w=None, c=None):
     xv, dyv, dpv, dxv = view(x, c), view(dy, c), view(dpool, c), view(dx, c)
@@ -192,12 +224,14 @@ def bn_relu_bwd(x, scale, shift, smean, sinv, gamma, dx, sums, count, dy=None, d
 
 
 # ----------------------------------------------------------------------------- head / loss
+@_timed
 def head_fwd(x, scale, shift, w, b, logits, c=None):
     xv = view(x, c)
     check(_lib.lib().hpri_head_fwd(_vp(xv), _ptr(scale), _ptr(shift), _ptr(w), _ptr(b), _ptr(logits), _stream()),
           "hpri_head_fwd")
 
 
+@_timed
 def bce_fwd_bwd(logits, target, loss_sum, dlogit=None, counts=None, grad_scale=1.0, thr=0.5):
     assert logits.dtype == torch.float32 and target.dtype == torch.float32
     assert logits.is_contiguous() and target.is_contiguous()
@@ -205,10 +239,12 @@ def bce_fwd_bwd(logits, target, loss_sum, dlogit=None, counts=None, grad_scale=1
                                       _ptr(dlogit), _ptr(counts), _stream()), "hpri_bce_fwd_bwd")
 
 
+@_timed
 def colsum(x, out, beta=0.0, c=None):
     xv = view(x, c)
     check(_lib.lib().hpri_colsum(_vp(xv), _ptr(out), beta, _stream()), "hpri_colsum")
 
 
+@_timed
 def sum_f32(x, out):
     check(_lib.lib().hpri_sum_f32(_ptr(x), x.numel(), _ptr(out), _stream()), "hpri_sum_f32")

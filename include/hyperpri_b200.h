@@ -38,6 +38,8 @@ typedef struct {
 } hpri_view_t;
 
 int hpri_abi_version(void);
+/* number of CUDA kernels this library has launched in this process (bench.py's gpu_launches) */
+long long hpri_launch_count(void);
 
 /* ---- tensor-core contractions (tcgen05 implicit GEMM, csrc/igemm.cu) ------------------- */
 
