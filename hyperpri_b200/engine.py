@@ -379,7 +379,7 @@ class SpectralEngine:
         for k in (2, 3, 4):
             ws[f"gcat{k}"] = _z((1, 1, m, 2 * Fp), d, GRAD)
         ws["R"] = _z((1, 1, m, Fp), d, GRAD)
-        ws["cvt"] = _z((1, 1, m, 2 * Fp), d, GRAD)
+        ws["cvt"] = _z((1, 1, m, max(2 * Fp, self.Dp)), d, GRAD)
         ws["g4"] = _z((1, 1, m, Fp), d, GRAD)
         ws["gt"] = _z((1, 1, m, Fp), d, GRAD)
         ws["logits"] = _e((n, 1, r, c), d, torch.float32)

@@ -1,0 +1,152 @@
+"""Experiment parameter classes with the reference's attribute names and defaults
+(reference src/Experiments/params_HyperPRI.py:15-356).  The attributes ARE the flag system: users edit
+them per model.  `get_network()` returns the B200-backed modules of ``models.py``."""
+import datetime
+import os
+
+import torch
+from torchvision import transforms
+
+from ..dataset import HyperpriDataset
+from .models import UNet, SpectralUNET, CubeNET
+
+
+class _ExpBase:
+    def _common(self, calling_path, split_no, seed_num, comet_logging):
+        self.now = datetime.datetime.now()
+        self.device, self.epochs = 'gpu', 2000
+        self.rescale, self.rotate, self.num_classes = 1, False, 1
+        self.label_set = None
+        self.json_dir = {k: f"{self.data_dir}/data_splits/{v}{split_no}.json"
+                         for k, v in (('train', 'train'), ('val', 'val'), ('test', 'val'))}
+        self.run_num = 10 * seed_num + split_no
+        self.bilinear = self.use_attention = self.use_pretrained = False
+        self.criterion = torch.nn.BCEWithLogitsLoss()
+        self.optimizer, self.learn_rate, self.weight_decay, self.momentum = "adam", 0.001, 0, 0.9
+        self.task, self.threshold = "binary", 0.5
+        self.consecutive, self.overall = None, 500
+
+    def _paths(self, calling_path, comet_logging):
+        self.model_param_str = self.translate_load_dir()
+        base = f"{calling_path}/Saved_Models/{self.dataset}"
+        self.save_path = f"{base}/{self.model_param_str}/Run_{self.run_num}/"
+        self.fig_dir = f"{base}/Val_Segmentation_Maps/Run_{self.run_num}/{self.model_param_str}/"
+        self.comet_params = {
+            "api_key": os.environ.get("COMET_API_KEY") if comet_logging else None,
+            "workspace": os.environ.get("COMET_WORKSPACE") if comet_logging else None,
+            "offline_dir": f"{calling_path}/comet_offline/", "project_name": "hyperpri",
+            "experiment_name": f"{self.dataset}-{self.model_name}-{self.run_num}",
+        }
+
+    def change_network_param(self, new_model_name, calling_path, split_no, seed_num=0, model_params=None):
+        """Overwrite only attributes that already exist and are not None (params_HyperPRI.py:95-100,257-261)."""
+        if model_params is not None:
+            for k in model_params:
+                if getattr(self, k, None) is not None:
+                    setattr(self, k, model_params[k])
+        self.run_num = 10 * seed_num + split_no
+        self.model_name = new_model_name
+        self.model_param_str = self.translate_load_dir()
+        base = f"{calling_path}/Saved_Models/{self.dataset}"
+        self.save_path = f"{base}/{self.model_param_str}/Run_{self.run_num}/"
+        self.fig_dir = f"{base}/Val_Segmentation_Maps/Run_{self.run_num}/{self.model_param_str}/"
+
+    def _dataset(self, img_tf, gt_tf, split, mode, **kw):
+        compose = lambda t: None if t is None else transforms.Compose(t)
+        return HyperpriDataset(root=self.data_dir, img_transform=compose(img_tf), label_transform=compose(gt_tf),
+                               subset=self.label_set, mode=mode, json_file=self.json_dir.get(split, None), **kw)
+
+
+class ExpRedGreenBluePRI(_ExpBase):
+    """RGB experiments (params_HyperPRI.py:15-165): UNET on 3-channel 608x968 images."""
+
+    def __init__(self, calling_path, split_no=1, seed_num=0, augment=False, comet_logging=True):
+        self.dataset = "RGB"
+        self.b_size = {'train': 2, 'val': 2, 'test': 1}
+        self.patch_size, self.color_mode = (608, 968), 'rgb'
+        self.channels = 3 if self.color_mode.lower() != 'gray' else 1
+        self.augment = augment
+        self.data_dir = f"{calling_path}/Datasets/HyperPRI/"
+        self._common(calling_path, split_no, seed_num, comet_logging)
+        self.train_transforms = [transforms.RandomCrop(self.patch_size), transforms.ToTensor()]
+        self.gt_transforms = [transforms.RandomCrop(self.patch_size), transforms.ToTensor()]
+        self.test_transforms = [transforms.ToTensor()]
+        self.gt_test_transforms = [transforms.ToTensor()]
+        self.model_name, self.feature_extraction, self.test_deepspeed = "UNET", False, None
+        self._paths(calling_path, comet_logging)
+
+    def translate_load_dir(self):
+        return "UNET"
+
+    def get_network(self):
+        if self.model_name in ('UNET', 'UNET+'):
+            return UNet(self.channels, self.num_classes, bilinear=self.bilinear,
+                        feature_extraction=self.feature_extraction, use_attention=self.use_attention)
+        raise RuntimeError('ExpRedGreenBluePRI: Invalid model')
+
+    def get_train_data(self):
+        return self._dataset(self.train_transforms, self.gt_transforms, 'train', self.color_mode)
+
+    def get_val_data(self):
+        return self._dataset(self.test_transforms, self.gt_test_transforms, 'val', self.color_mode)
+
+    def get_test_data(self):
+        return self._dataset(self.test_transforms, self.gt_test_transforms, 'test', self.color_mode)
+
+
+class ExpHyperspectralPRI(_ExpBase):
+    """HSI experiments (params_HyperPRI.py:168-356): SpectralUNET / CubeNET on bands hsi_lo..hsi_hi."""
+
+    def __init__(self, calling_path, split_no=1, seed_num=0, comet_logging=True):
+        self.dataset = "HSI"
+        self.b_size = {'train': 2, 'val': 2, 'test': 2}
+        self.patch_size = (608, 968)
+        self.hsi_lo, self.hsi_hi, self.channels = 25, 263, 238
+        self.augment = False
+        self.data_dir = f"{calling_path}/Datasets/HyperPRI"
+        self._common(calling_path, split_no, seed_num, comet_logging)
+        self.test_transforms = None
+        self.gt_test_transforms = [transforms.ToTensor()]
+        if self.augment:
+            self.train_transforms = [transforms.RandomCrop(self.patch_size)]
+            self.gt_transforms = [transforms.RandomCrop(self.patch_size), transforms.ToTensor()]
+        else:
+            self.train_transforms = None
+            self.gt_transforms = [transforms.ToTensor()]
+        self.model_name = "CubeNET"
+        self.mlp_layers, self.test_deepspeed = [1650] * 10, False
+        self.spectral_bn_size, self.cube_featmaps = 1650, 64
+        self._paths(calling_path, comet_logging)
+
+    def translate_load_dir(self):
+        name = self.model_name.lower()
+        if name == 'spectralunet':
+            return f"{self.model_name}_{self.spectral_bn_size}"
+        if name == 'cubenet':
+            return f"{self.model_name}_{self.cube_featmaps}"
+        if name in ('unet', 'unet+'):
+            return self.model_name
+        return None            # the reference builds a ValueError here without raising it (:279-281)
+
+    def get_network(self):
+        depth = self.hsi_hi - self.hsi_lo
+        name = self.model_name.lower()
+        if name == 'spectralunet':
+            return SpectralUNET(depth, self.num_classes, bn_feats=self.spectral_bn_size)
+        if name == 'cubenet':
+            return CubeNET(depth, self.num_classes, first_depth=self.cube_featmaps, bilinear=self.bilinear,
+                           use_attention=self.use_attention)
+        raise RuntimeError('ExpHyperspectralPRI: Invalid model')
+
+    def _hsi(self, img_tf, gt_tf, split):
+        return self._dataset(img_tf, gt_tf, split, 'HSI', unsqueeze_img=self.model_name.lower() == 'cubenet',
+                             hsi_lo=self.hsi_lo, hsi_hi=self.hsi_hi)
+
+    def get_train_data(self):
+        return self._hsi(self.train_transforms, self.gt_transforms, 'train')
+
+    def get_val_data(self):
+        return self._hsi(self.test_transforms, self.gt_test_transforms, 'val')
+
+    def get_test_data(self):
+        return self._hsi(self.test_transforms, self.gt_test_transforms, 'test')

@@ -1,0 +1,171 @@
+"""CPU: host-side logic of the drop-in -- the C-ABI library loads and exports every declared symbol, state-dict
+schemas equal the reference's, parameter classes keep names/defaults, dataset + ENVI reader + metrics."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+import hyperpri_oracle as O
+from hyperpri_b200 import _lib, envi, metrics as M
+from hyperpri_b200.src.Experiments import models as mdl
+from hyperpri_b200.src.Experiments.params_HyperPRI import ExpHyperspectralPRI, ExpRedGreenBluePRI
+from hyperpri_b200.src.dataset import HyperpriDataset
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    import __graft_entry__ as ge
+    ge.build()
+    hdr = open(os.path.join(ROOT, "include", "hyperpri_b200.h")).read()
+    declared = set(re.findall(r"\b(hpri_[a-zA-Z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.hpri_abi_version() == 2
+    assert ctypes.sizeof(_lib.View) == 56          # ptr, 4 ints, 3 int64, dtype (+pad)
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libhyperpri_b200.so")
+    with pytest.raises(_lib.NativeLibraryMissing):
+        _lib.lib()
+
+
+@pytest.mark.parametrize("net,schema,nparam", [
+    (lambda: mdl.UNet(3, 1, bilinear=False), lambda: O.unet_schema(3, 1, "unet"), 31043521),
+    (lambda: mdl.CubeNET(238, 1, bilinear=False), lambda: O.unet_schema(1, 1, "cube", 238), 31178881),
+    (lambda: mdl.SpectralUNET(238, 1, bn_feats=1650), lambda: O.spectral_schema(238, 1, 1650), 30388051),
+])
+def test_state_dict_schema_matches_reference(net, schema, nparam):
+    n, s = net(), schema()
+    sd = n.state_dict()
+    assert {k: tuple(v.shape) for k, v in sd.items()} == {k: tuple(v) for k, v in s.items()}
+    assert sum(p.numel() for p in n.parameters()) == nparam      # SURVEY.md section 4 known answers
+    n.load_state_dict(O.synth_state_dict(s, 0))                    # reference-style state dict loads
+
+
+def test_cubenet_aliases_first_conv():
+    n = mdl.CubeNET(238, 1, bilinear=False)
+    assert n.inc[0] is n.first_conv and n.n_channels == 1 and n.depth == 238
+    assert len(n.state_dict()) == 138 and len(list(n.named_parameters())) == 82
+
+
+def test_factories_and_unsupported_flags():
+    p = dict(channels=3, bilinear=False, feature_extraction=False, use_attention=False, hsi_lo=25, hsi_hi=263,
+             spectral_bn_size=1650, **{"3d_featmaps": 64})
+    assert isinstance(mdl.initialize_model("UNET", 1, p), mdl.UNet)
+    assert isinstance(mdl.initialize_model("CubeNET", 1, p), mdl.CubeNET)
+    assert mdl.initialize_model("SpectralUNET", 1, p).layer_feats == [1650] * 5
+    with pytest.raises(RuntimeError, match="Invalid model"):
+        mdl.initialize_model("nope", 1, p)
+    assert mdl.translate_load_dir("SpectralUNET", p) == "SpectralUNET_1650"
+    assert mdl.translate_load_dir("CubeNET", p) == "CubeNET_64" and mdl.translate_load_dir("UNET", p) == "UNET"
+    with pytest.raises(NotImplementedError):
+        mdl.UNet(3, 1, bilinear=True)
+    with pytest.raises(NotImplementedError):
+        mdl.CubeNET(238, 1, first_depth=32, bilinear=False)
+
+
+def test_cpu_forward_is_refused_not_emulated():
+    n = mdl.UNet(3, 1, bilinear=False)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        n(torch.zeros(1, 3, 16, 16))
+
+
+def test_param_classes_keep_reference_knobs(tmp_path):
+    p = ExpHyperspectralPRI(str(tmp_path), split_no=3, seed_num=1, comet_logging=False)
+    assert (p.hsi_lo, p.hsi_hi, p.channels, p.spectral_bn_size, p.cube_featmaps) == (25, 263, 238, 1650, 64)
+    assert p.b_size == {'train': 2, 'val': 2, 'test': 2} and p.patch_size == (608, 968) and p.run_num == 13
+    assert p.model_name == "CubeNET" and p.model_param_str == "CubeNET_64" and p.optimizer == "adam"
+    assert p.learn_rate == 0.001 and p.threshold == 0.5 and isinstance(p.criterion, torch.nn.BCEWithLogitsLoss)
+    assert p.save_path.endswith("Saved_Models/HSI/CubeNET_64/Run_13/")
+    p.change_network_param("SpectralUNET", str(tmp_path), 3, model_params={"spectral_bn_size": 64, "nonexistent": 1})
+    assert p.model_param_str == "SpectralUNET_64" and not hasattr(p, "nonexistent")
+    assert isinstance(p.get_network(), mdl.SpectralUNET)
+    r = ExpRedGreenBluePRI(str(tmp_path), comet_logging=False)
+    assert r.channels == 3 and r.b_size['test'] == 1 and isinstance(r.get_network(), mdl.UNet)
+
+
+def _make_dataset(root, n_dates=2, h=12, w=20):
+    base = os.path.join(root, "Peanut_968x608")
+    for d in ("rgb_files", "hsi_files", "mask_files", "../data_splits"):
+        os.makedirs(os.path.join(base, d), exist_ok=True)
+    dates = [f"2022070{i}" for i in range(n_dates)]
+    rs = np.random.RandomState(0)
+    cubes = {}
+    for date in dates:
+        stem = f"{date}_box37_ref"
+        cube = rs.random_sample((h, w, 299)).astype(np.float32)
+        cubes[stem] = cube
+        envi.save(os.path.join(base, "hsi_files", "hinalea_hsi.hdr"), os.path.join(base, "hsi_files", stem + ".dat"), cube)
+        Image.fromarray((rs.random_sample((h, w)) > 0.8).astype(np.uint8) * 3).save(os.path.join(base, "mask_files", stem + "_mask.png"))
+        Image.fromarray((rs.random_sample((h, w, 3)) * 255).astype(np.uint8)).save(os.path.join(base, "rgb_files", stem + ".png"))
+    js = {"img_dir": "rgb_files", "hsi_dir": "hsi_files", "mask_dir": "mask_files", "notes": "x",
+          "box37": {"plant_folder": "Peanut", "resolution": "968x608", "box_no": 37, "phenotype": 1, "dates": dates + ["19990101"],
+                    "weights": None}}
+    jp = os.path.join(root, "data_splits", "val1.json")
+    with open(jp, "w") as f:
+        json.dump(js, f)
+    return jp, cubes
+
+
+@pytest.mark.parametrize("inter", ["bil", "bsq", "bip"])
+def test_envi_roundtrip(tmp_path, inter):
+    cube = np.random.RandomState(1).random_sample((5, 7, 9)).astype(np.float32)
+    envi.save(str(tmp_path / "a.hdr"), str(tmp_path / "a.dat"), cube, inter)
+    assert np.array_equal(envi.load(str(tmp_path / "a.hdr"), str(tmp_path / "a.dat")), cube)
+
+
+def test_dataset_hsi_items_match_oracle_ingest(tmp_path):
+    from torchvision import transforms
+    jp, cubes = _make_dataset(str(tmp_path))
+    ds = HyperpriDataset(root=str(tmp_path), mode='HSI', img_transform=None,
+                         label_transform=transforms.Compose([transforms.ToTensor()]), unsqueeze_img=True, hsi_lo=25,
+                         hsi_hi=263, json_file=jp)
+    assert len(ds) == 2                         # the date without files is skipped
+    it = ds[0]
+    assert set(it) == {'image', 'mask', 'index', 'label'} and it['index'] == "20220700_box37_ref"
+    assert tuple(it['image'].shape) == (1, 238, 12, 20) and it['image'].dtype == torch.float32
+    assert np.array_equal(it['image'].numpy(), O.ingest_hsi(cubes[it['index']], 25, 263, True))
+    m = np.asarray(it['mask'])
+    assert m.shape == (1, 12, 20) and set(np.unique(m)) <= {0.0, 1.0}
+    # crop transform: image and mask share the drawn window (RNG-state replay)
+    ds2 = HyperpriDataset(root=str(tmp_path), mode='HSI', img_transform=transforms.Compose([transforms.RandomCrop((8, 10))]),
+                          label_transform=transforms.Compose([transforms.RandomCrop((8, 10)), transforms.ToTensor()]),
+                          unsqueeze_img=False, hsi_lo=25, hsi_hi=263, json_file=jp)
+    torch.manual_seed(5)
+    it2 = ds2[1]
+    full = O.ingest_hsi(cubes[it2['index']], 25, 263, False)
+    found = [(i, j) for i in range(5) for j in range(11) if np.array_equal(full[:, i:i + 8, j:j + 10], it2['image'].numpy())]
+    assert len(found) == 1
+    i, j = found[0]
+    full_mask = np.asarray(ds[1]['mask'])
+    assert np.array_equal(np.asarray(it2['mask']), full_mask[:, i:i + 8, j:j + 10])
+
+
+def test_metrics_against_bruteforce():
+    g = torch.Generator().manual_seed(0)
+    probs = torch.rand(5000, generator=g)
+    tgt = (torch.rand(5000, generator=g) < probs * 0.6).long()
+    prec, rec, thr = M.binned_pr_curve(probs, tgt, 500)
+    assert prec.shape == (501,) and rec.shape == (501,) and thr.shape == (500,)
+    for i in (0, 17, 250, 499):
+        pred = probs >= thr[i]
+        tp = (pred & (tgt > 0)).sum().item(); fp = (pred & (tgt == 0)).sum().item()
+        assert abs(prec[i].item() - (tp / (tp + fp) if tp + fp else 0.0)) < 1e-6
+        assert abs(rec[i].item() - tp / (tgt > 0).sum().item()) < 1e-6
+    assert prec[-1] == 1 and rec[-1] == 0 and 0 < M.average_precision(prec, rec) < 1
+    c = M.confusion_counts(probs > 0.5, tgt)
+    tp, fp, fn, tn = [v.item() for v in c]
+    assert tp + fp + fn + tn == 5000
+    assert abs(M.dice(*c).item() - 2 * tp / (2 * tp + fp + fn)) < 1e-6
+    assert abs(M.jaccard(*c).item() - tp / (tp + fp + fn)) < 1e-6
+    assert O.seg_counts(torch.logit(probs), tgt.float()) == (tp, fp, fn, tn)

@@ -1,0 +1,92 @@
+"""CPU: the oracle restatement replayed against the golden fixtures generated from the REFERENCE modules
+(oracle/gen_golden.py, run where /root/reference exists).  Inputs and weights are regenerated from seeds;
+the fixtures hold reference outputs only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import hyperpri_oracle as O
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+CASES = {
+    "unet_2x3x32x40": dict(model="UNET", n=2, h=32, w=40, bands=3, seed=0),
+    "cubenet_2x238x32x40": dict(model="CubeNET", n=2, h=32, w=40, bands=238, seed=1),
+    "cubenet_1x238x48x72": dict(model="CubeNET", n=1, h=48, w=72, bands=238, seed=2),
+    "spectral32_2x238x6x10": dict(model="SpectralUNET", n=2, h=6, w=10, bands=238, seed=3, feats=32),
+    "spectral1650_2x238x4x5": dict(model="SpectralUNET", n=2, h=4, w=5, bands=238, seed=4, feats=1650),
+}
+
+
+def _inputs(c):
+    if c["model"] == "UNET":
+        schema = O.unet_schema(c["bands"], 1, "unet")
+    elif c["model"] == "CubeNET":
+        schema = O.unet_schema(1, 1, "cube", hsi_depth=c["bands"])
+    else:
+        schema = O.spectral_schema(c["bands"], 1, c["feats"])
+    sd = O.synth_state_dict(schema, c["seed"])
+    x = O.synth_cube(c["seed"], c["n"], c["bands"], c["h"], c["w"])
+    if c["model"] == "CubeNET":
+        x = x[:, None]
+    return sd, x, O.synth_mask(c["seed"], c["n"], c["h"], c["w"])
+
+
+@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_oracle_matches_reference_golden(name, mode):
+    c = CASES[name]
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    sd, x, mask = _inputs(c)
+    torch.set_num_threads(min(8, os.cpu_count()))
+    logits, loss, grads, stats = O.forward_backward(c["model"], x, mask, sd, training=(mode == "train"))
+    ref = torch.from_numpy(g[f"{mode}.logits"])
+    assert (logits - ref).abs().max().item() <= 2e-4 * ref.abs().max().item()     # fp32, different op order
+    assert abs(loss.item() - float(g[f"{mode}.loss"])) < 1e-5
+    keys, vals = list(g[f"{mode}.gradnorm.keys"]), g[f"{mode}.gradnorm.vals"]
+    for k, v in zip(keys, vals):
+        got = grads[str(k)].norm().item()
+        # tiny-batch BN gradients are ill-conditioned in fp32; conv biases in front of a train-mode BN have a
+        # mathematically zero gradient, so both sides hold ~1e-4 rounding noise there (absolute floor)
+        assert abs(got - v) <= 3e-2 * v + 2e-3, (k, got, v)
+    for key in g.files:
+        if key.startswith(f"{mode}.grad.") and not key.startswith(f"{mode}.gradnorm"):
+            k = key[len(mode) + 6:]
+            r = torch.from_numpy(g[key])
+            assert (grads[k] - r).abs().max().item() <= 3e-2 * r.abs().max().item() + 5e-4, k
+    if mode == "train":
+        for key in g.files:
+            if key.startswith("train.buf."):
+                k = key[len("train.buf."):]
+                assert np.allclose(stats[k].numpy(), g[key], rtol=1e-4, atol=1e-6), k
+
+
+def test_ingest_golden():
+    g = np.load(os.path.join(GOLD, "ingest_12x20x299.npz"))
+    cube = np.random.RandomState(7).random_sample((12, 20, 299)).astype(np.float32)
+    img = O.ingest_hsi(cube, 25, 263, False)
+    assert img.shape == (238, 12, 20) and O.ingest_hsi(cube, 25, 263, True).shape == (1, 238, 12, 20)
+    assert np.array_equal(img[:, 0, 0], g["first"]) and np.array_equal(img[:, -1, -1], g["last"])
+    assert np.allclose(img.sum(axis=(1, 2), dtype=np.float64), g["sum_per_band"])
+    # crop + rescale rule and mask binarisation (dataset.py:284-295)
+    big = img * 255
+    out = O.crop_and_rescale(big, 2, 3, 8, 10)
+    assert out.shape == (238, 8, 10) and np.allclose(out, img[:, 2:10, 3:13], atol=1e-6)
+    assert np.array_equal(O.crop_and_rescale(img, 0, 0, 12, 20), img)
+    lab = np.array([[0, 3, 255], [1, 0, 0]], dtype=np.uint8)
+    assert np.array_equal(O.binarise_mask(lab), np.array([[0, 1, 1], [1, 0, 0]], dtype=np.float32))
+
+
+def test_emulation_is_off_by_default_and_close():
+    c = CASES["unet_2x3x32x40"]
+    sd, x, mask = _inputs(c)
+    l0 = O.forward_backward("UNET", x, mask, sd)[0]
+    O.emulate_bf16_storage(True)
+    try:
+        l1 = O.forward_backward("UNET", x, mask, sd)[0]
+    finally:
+        O.emulate_bf16_storage(False)
+    l2 = O.forward_backward("UNET", x, mask, sd)[0]
+    assert torch.equal(l0, l2)
+    assert 0 < (l1 - l0).abs().max().item() < 5e-2 * l0.abs().max().item()

@@ -1,0 +1,62 @@
+"""CPU, world_size 2 (gloo): the bucketed gradient all-reduce hook used by the data-parallel path."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from hyperpri_b200 import parallel
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+class _FakeEngine:
+    def __init__(self, rank):
+        self.arena = torch.arange(100, dtype=torch.float32) * (rank + 1)
+        self.bucket_bounds = [(0, 10), (10, 60), (60, 100)]
+        self.bucket_hook = None
+
+    def backward(self):
+        for a, b in self.bucket_bounds:
+            self.bucket_hook(self.arena[a:b])
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    eng = _FakeEngine(rank)
+    red = parallel.attach(eng)
+    assert red.world_size == world and abs(red.grad_scale() - 1.0 / world) < 1e-12
+    eng.arena.mul_(red.grad_scale())          # the engine folds 1/world into the loss gradient
+    eng.backward()
+    red.finish()
+    q.put((rank, eng.arena.clone(), red.bytes))
+    dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    expect = torch.arange(100, dtype=torch.float32) * (1 + 2) / 2       # mean over ranks
+    for rank, arena, nbytes in res:
+        assert torch.allclose(arena, expect) and nbytes == 400
+
+
+def test_single_process_is_a_noop():
+    eng = _FakeEngine(0)
+    red = parallel.attach(eng)
+    before = eng.arena.clone()
+    eng.backward(); red.finish()
+    assert torch.equal(eng.arena, before) and red.grad_scale() == 1.0
