@@ -234,113 +234,137 @@ bn_relu_apply_k(V x, const float* __restrict__ scale, const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------ backward of relu(bn(x)) (+pool, +head)
-// Shared traversal: for a 2x2 window x 8 channels compute dz (gradient at the BN output after the
-// ReLU mask) for each of the 4 pixels.  The post-ReLU activation is re-derived from the raw conv
-// output x, so no activation mask is stored.
+// One thread = one 2x2 pixel window x 8 channels.  All 16-byte loads of the window are issued first
+// (up to 9 in flight per thread), then channels are processed pairwise from the packed words.  The
+// post-ReLU activation (mask, pool arg-max) is re-derived from the raw conv output x, so no mask is stored.
 struct BwdIn {
   V x, dy, dpool;
   const float *scale, *shift, *mean, *invstd, *head_w, *dlogit;
 };
-__device__ __forceinline__ void window_dz(const BwdIn& a, int n, int wy, int wx, int c0, float (&xr)[4][8],
-                                          float (&act)[4][8], float (&dz)[4][8], bool (&inb)[4], float (&dl)[4]) {
-  float sc[8], sh[8];
-  ld8p(a.scale, c0, a.x.c, sc);
-  ld8p(a.shift, c0, a.x.c, sh);
+struct Win {
+  uint4 x[4], dy[4], dp;
+  float dl[4];
+  bool inb[4], has_dp;
+};
+__device__ __forceinline__ uint32_t wsel(const uint4& u, int j) { return j == 0 ? u.x : j == 1 ? u.y : j == 2 ? u.z : u.w; }
+
+__device__ __forceinline__ void load_window(const BwdIn& a, int n, int wy, int wx, int c0, Win& w) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int yy = 2 * wy + (q >> 1), xx = 2 * wx + (q & 1);
-    inb[q] = yy < a.x.h && xx < a.x.w;
-    dl[q] = 0.f;
-    if (!inb[q]) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { xr[q][k] = 0.f; act[q][k] = 0.f; dz[q][k] = 0.f; }
-      continue;
-    }
-    unpack8(__ldg(reinterpret_cast<const uint4*>(at(a.x, n, yy, xx, c0))), xr[q], a.x.dt);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) act[q][k] = fmaxf(fmaf(xr[q][k], sc[k], sh[k]), 0.f);
-    if (a.dy.p != nullptr) unpack8(__ldg(reinterpret_cast<const uint4*>(at(a.dy, n, yy, xx, c0))), dz[q], a.dy.dt);
-    else {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) dz[q][k] = 0.f;
-    }
-    if (a.dlogit != nullptr) {
-      dl[q] = __ldg(a.dlogit + ((long long)n * a.x.h + yy) * a.x.w + xx);
-      float hw[8];
-      ld8p(a.head_w, c0, a.x.c, hw);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) dz[q][k] = fmaf(dl[q], hw[k], dz[q][k]);
+    w.inb[q] = yy < a.x.h && xx < a.x.w;
+    w.x[q] = make_uint4(0, 0, 0, 0);
+    w.dy[q] = make_uint4(0, 0, 0, 0);
+    w.dl[q] = 0.f;
+    if (w.inb[q]) {
+      w.x[q] = __ldg(reinterpret_cast<const uint4*>(at(a.x, n, yy, xx, c0)));
+      if (a.dy.p != nullptr) w.dy[q] = __ldg(reinterpret_cast<const uint4*>(at(a.dy, n, yy, xx, c0)));
+      if (a.dlogit != nullptr) w.dl[q] = __ldg(a.dlogit + ((long long)n * a.x.h + yy) * a.x.w + xx);
     }
   }
-  if (a.dpool.p != nullptr && wy < a.dpool.h && wx < a.dpool.w) {
-    float dp[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(at(a.dpool, n, wy, wx, c0))), dp, a.dpool.dt);
+  w.has_dp = a.dpool.p != nullptr && wy < a.dpool.h && wx < a.dpool.w;
+  w.dp = make_uint4(0, 0, 0, 0);
+  if (w.has_dp) w.dp = __ldg(reinterpret_cast<const uint4*>(at(a.dpool, n, wy, wx, c0)));
+}
+
+// dz (gradient at the BN output after the ReLU mask) and z = x*scale+shift for word j (channels 2j, 2j+1).
+__device__ __forceinline__ void window_word(const BwdIn& a, const Win& w, int j, const float* sc, const float* sh,
+                                            const float* hw, float (&xv)[4][2], float (&z)[4][2], float (&dz)[4][2]) {
+  const float2 dpv = w.has_dp ? unpack2(wsel(w.dp, j), a.dpool.dt) : make_float2(0.f, 0.f);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+  for (int q = 0; q < 4; ++q) {
+    const float2 xq = unpack2(wsel(w.x[q], j), a.x.dt);
+    const float2 dq = a.dy.p != nullptr ? unpack2(wsel(w.dy[q], j), a.dy.dt) : make_float2(0.f, 0.f);
+    xv[q][0] = xq.x; xv[q][1] = xq.y;
+    dz[q][0] = dq.x; dz[q][1] = dq.y;
+  }
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int k = 2 * j + e;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      z[q][e] = w.inb[q] ? fmaf(xv[q][e], sc[k], sh[k]) : -1.f;
+      if (hw != nullptr) dz[q][e] = fmaf(w.dl[q], hw[k], dz[q][e]);
+    }
+    if (w.has_dp) {
       int best = 0;
-      float m = act[0][k];
+      float m = fmaxf(z[0][e], 0.f);
 #pragma unroll
-      for (int q = 1; q < 4; ++q)
-        if (act[q][k] > m) { m = act[q][k]; best = q; }     // first maximum wins (ATen max_pool2d order)
+      for (int q = 1; q < 4; ++q) {
+        const float v = fmaxf(z[q][e], 0.f);
+        if (v > m) { m = v; best = q; }                 // first maximum wins (ATen max_pool2d order)
+      }
+      const float g = e == 0 ? dpv.x : dpv.y;
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        if (q == best) dz[q][k] += dp[k];
+        if (q == best) dz[q][e] += g;
     }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (!(z[q][e] > 0.f)) dz[q][e] = 0.f;
   }
-#pragma unroll
-  for (int q = 0; q < 4; ++q)
-#pragma unroll
-    for (int k = 0; k < 8; ++k)
-      if (!(act[q][k] > 0.f)) dz[q][k] = 0.f;
 }
 
 // pass 1: sums[c] = {sum dz, sum dz*xhat, sum dlogit*act}
-__global__ void __launch_bounds__(256) bn_bwd_reduce_k(BwdIn a, double* sums, int slots, int CG) {
+__global__ void __launch_bounds__(256, 2) bn_bwd_reduce_k(BwdIn a, double* sums, int slots, int CG) {
   extern __shared__ float red[];                 // [slots][CG*8][3]
   const int cg = threadIdx.x % CG, slot = threadIdx.x / CG;
   const bool active = slot < slots;
   const int wh = (a.x.h + 1) >> 1, ww = (a.x.w + 1) >> 1;
   const long long nwin = (long long)a.x.n * wh * ww;
-  float s1[8], s2[8], s3[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; s3[k] = 0.f; }
   if (active) {
     const int c0 = cg * 8;
-    float mu[8], is[8];
-    ld8p(a.mean, c0, a.x.c, mu);
-    ld8p(a.invstd, c0, a.x.c, is);
+    float sc[8], sh[8], hwv[8];
+    ld8p(a.scale, c0, a.x.c, sc);
+    ld8p(a.shift, c0, a.x.c, sh);
+    ld8p(a.head_w, c0, a.x.c, hwv);
+    const float* hw = a.dlogit != nullptr ? hwv : nullptr;
+    float s1[8], s2[8], s3[8];                   // s2 holds sum dz*x; centred and scaled at the end
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; s3[k] = 0.f; }
     for (long long wi = (long long)blockIdx.x * slots + slot; wi < nwin; wi += (long long)gridDim.x * slots) {
       long long j = wi;
       const int wx = (int)(j % ww); j /= ww;
       const int wy = (int)(j % wh);
       const int n = (int)(j / wh);
-      float xr[4][8], act[4][8], dz[4][8], dl[4];
-      bool inb[4];
-      window_dz(a, n, wy, wx, c0, xr, act, dz, inb, dl);
+      Win w;
+      load_window(a, n, wy, wx, c0, w);
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
+      for (int jw = 0; jw < 4; ++jw) {
+        float xv[4][2], z[4][2], dz[4][2];
+        window_word(a, w, jw, sc, sh, hw, xv, z, dz);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          s1[k] += dz[q][k];
-          s2[k] = fmaf(dz[q][k], (xr[q][k] - mu[k]) * is[k], s2[k]);
-          s3[k] = fmaf(dl[q], act[q][k], s3[k]);
-        }
+        for (int e = 0; e < 2; ++e)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int k = 2 * jw + e;
+            s1[k] += dz[q][e];
+            s2[k] = fmaf(dz[q][e], xv[q][e], s2[k]);
+            s3[k] = fmaf(w.dl[q], fmaxf(z[q][e], 0.f), s3[k]);
+          }
+      }
     }
     float* r = red + ((long long)slot * CG + cg) * 24;
 #pragma unroll
     for (int k = 0; k < 8; ++k) { r[k * 3] = s1[k]; r[k * 3 + 1] = s2[k]; r[k * 3 + 2] = s3[k]; }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < CG * 24; i += blockDim.x) {
-    float t = 0.f;
-    for (int s = 0; s < slots; ++s) t += red[(long long)s * CG * 24 + i];
-    const int c = (i / 24) * 8 + (i % 24) / 3, which = i % 3;
-    if (c < a.x.c) atomicAdd(sums + 3 * c + which, (double)t);
+  for (int c = threadIdx.x; c < CG * 8; c += blockDim.x) {
+    if (c >= a.x.c) continue;
+    float t1 = 0.f, t2 = 0.f, t3 = 0.f;
+    for (int s = 0; s < slots; ++s) {
+      const float* r = red + ((long long)s * CG * 8 + c) * 3;
+      t1 += r[0]; t2 += r[1]; t3 += r[2];
+    }
+    const float mu = __ldg(a.mean + c), is = __ldg(a.invstd + c);
+    atomicAdd(sums + 3 * c, (double)t1);
+    atomicAdd(sums + 3 * c + 1, (double)is * ((double)t2 - (double)mu * (double)t1));
+    atomicAdd(sums + 3 * c + 2, (double)t3);
   }
 }
 
-// pass 2: dx = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat))
-__global__ void __launch_bounds__(256)
+// pass 2: dx = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)) = ca*dz + cb*x + cc
+__global__ void __launch_bounds__(256, 2)
 bn_bwd_apply_k(BwdIn a, const float* __restrict__ gamma, const double* __restrict__ sums, long long count, V dx,
                float* dgamma, float* dbeta, float* dhead_w) {
   const int CG = (a.x.c + 7) >> 3;
@@ -354,6 +378,8 @@ bn_bwd_apply_k(BwdIn a, const float* __restrict__ gamma, const double* __restric
     }
   }
   const float rc = 1.f / (float)count;
+  int cg_cached = -1;
+  float sc[8], sh[8], hwv[8], ca[8], cb[8], cc[8];
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int cg = (int)(i % CG);
     long long j = i / CG;
@@ -361,30 +387,44 @@ bn_bwd_apply_k(BwdIn a, const float* __restrict__ gamma, const double* __restric
     const int wy = (int)(j % wh);
     const int n = (int)(j / wh);
     const int c0 = cg * 8;
-    float xr[4][8], act[4][8], dz[4][8], dl[4];
-    bool inb[4];
-    window_dz(a, n, wy, wx, c0, xr, act, dz, inb, dl);
-    float mu[8], is[8], g[8], m1[8], m2[8];
-    ld8p(a.mean, c0, a.x.c, mu);
-    ld8p(a.invstd, c0, a.x.c, is);
-    ld8p(gamma, c0, a.x.c, g);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int c = c0 + k;
-      m1[k] = c < a.x.c ? (float)sums[3 * c] * rc : 0.f;
-      m2[k] = c < a.x.c ? (float)sums[3 * c + 1] * rc : 0.f;
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (!inb[q]) continue;
-      float o[8];
+    if (cg != cg_cached) {                       // constant per thread when the grid stride is a multiple of CG
+      cg_cached = cg;
+      ld8p(a.scale, c0, a.x.c, sc);
+      ld8p(a.shift, c0, a.x.c, sh);
+      ld8p(a.head_w, c0, a.x.c, hwv);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        const float xh = (xr[q][k] - mu[k]) * is[k];
-        o[k] = g[k] * is[k] * (dz[q][k] - m1[k] - xh * m2[k]);
+        const int c = c0 + k;
+        float g = 0.f, mu = 0.f, is = 0.f, m1 = 0.f, m2 = 0.f;
+        if (c < a.x.c) {
+          g = __ldg(gamma + c); mu = __ldg(a.mean + c); is = __ldg(a.invstd + c);
+          m1 = (float)sums[3 * c] * rc; m2 = (float)sums[3 * c + 1] * rc;
+        }
+        ca[k] = g * is;
+        cb[k] = -g * is * is * m2;
+        cc[k] = -g * is * m1 - cb[k] * mu;
       }
-      *reinterpret_cast<uint4*>(at(dx, n, 2 * wy + (q >> 1), 2 * wx + (q & 1), c0)) = pack8(o, dx.dt);
     }
+    const float* hw = a.dlogit != nullptr ? hwv : nullptr;
+    Win w;
+    load_window(a, n, wy, wx, c0, w);
+    uint32_t o[4][4];
+#pragma unroll
+    for (int jw = 0; jw < 4; ++jw) {
+      float xv[4][2], z[4][2], dz[4][2];
+      window_word(a, w, jw, sc, sh, hw, xv, z, dz);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float o0 = fmaf(ca[2 * jw], dz[q][0], fmaf(cb[2 * jw], xv[q][0], cc[2 * jw]));
+        const float o1 = fmaf(ca[2 * jw + 1], dz[q][1], fmaf(cb[2 * jw + 1], xv[q][1], cc[2 * jw + 1]));
+        o[q][jw] = pack2(o0, o1, dx.dt);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (w.inb[q])
+        *reinterpret_cast<uint4*>(at(dx, n, 2 * wy + (q >> 1), 2 * wx + (q & 1), c0)) =
+            make_uint4(o[q][0], o[q][1], o[q][2], o[q][3]);
   }
 }
 

@@ -47,81 +47,60 @@ struct IgemmArgs {
 };
 
 constexpr int kThreads = 192;
-constexpr int A_BYTES = 16384;  // 128 rows x 128 B (fwd) or 2 chunks x 64 rows x 128 B (wgrad)
+constexpr int kMaxStatCh = 2048;   // per-CTA BatchNorm partial sums live in smem for the whole kernel
 
-template <int BLOCK_N, int STAGES>
+// fwd: k-block = 64 channels of one tap: A 128 pixels x 128 B, B BLOCK_N rows x 128 B.
+// wgrad: k-block = 128 pixels: A 2 channel chunks x 128 pixel rows x 128 B, B BLOCK_N/64 chunks likewise.
+template <int BLOCK_N, int STAGES, int MODE>
 struct SmemLayout {
-  static constexpr int B_BYTES = BLOCK_N * 128;
+  static constexpr int KPIX = 128;                                         // wgrad pixels per k-block
+  static constexpr int A_BYTES = MODE == MODE_FWD ? 16384 : 2 * KPIX * 128;
+  static constexpr int B_BYTES = MODE == MODE_FWD ? BLOCK_N * 128 : (BLOCK_N / 64) * KPIX * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
-  static constexpr int BAR_OFF = PIPE_BYTES;                 // full[STAGES], empty[STAGES], tmem_full
-  static constexpr int TMEMPTR_OFF = BAR_OFF + (2 * STAGES + 1) * 8;
-  static constexpr int VALID_OFF = TMEMPTR_OFF + 8;          // 128 row-valid bytes
-  static constexpr int SSUM_OFF = VALID_OFF + 128;           // float[BLOCK_N] x 2
-  static constexpr int TOTAL = SSUM_OFF + 2 * BLOCK_N * 4;
-  static constexpr int ALLOC = TOTAL + 1024;                 // slack for manual 1024 B alignment
-  static_assert(128 * BLOCK_N * 2 <= PIPE_BYTES, "epilogue staging must fit in the pipeline buffers");
+  static constexpr int STAGING_OFF = PIPE_BYTES;                 // 128 rows x 64 columns x 2 B epilogue staging
+  static constexpr int STAGING_BYTES = MODE == MODE_FWD ? 128 * 128 : 0;
+  static constexpr int BAR_OFF = STAGING_OFF + STAGING_BYTES;    // full[S], empty[S], tmem_full[2], tmem_empty[2]
+  static constexpr int TMEMPTR_OFF = BAR_OFF + (2 * STAGES + 4) * 8;
+  static constexpr int VALID_OFF = TMEMPTR_OFF + 8;              // 128 row-valid bytes
+  static constexpr int SSUM_OFF = VALID_OFF + 128;               // float[kMaxStatCh] sum, float[kMaxStatCh] sumsq
+  static constexpr int TOTAL = SSUM_OFF + (MODE == MODE_FWD ? 2 * kMaxStatCh * 4 : 0);
+  static constexpr int ALLOC = TOTAL + 1024;                     // slack for manual 1024 B alignment
+  static_assert(ALLOC <= 227 * 1024, "shared memory budget exceeded");
 };
 
+// Persistent kernel: grid = min(tiles, #SMs); each CTA walks tiles blockIdx.x, +gridDim.x, ...
+// The smem ring runs continuously across tiles; the accumulator is double-buffered in TMEM
+// (2 x BLOCK_N columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
 template <int BLOCK_N, int STAGES, int MODE>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
              const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
              const IgemmArgs p) {
-  using L = SmemLayout<BLOCK_N, STAGES>;
+  using L = SmemLayout<BLOCK_N, STAGES, MODE>;
+  constexpr int A_BYTES = L::A_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;      // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::TMEMPTR_OFF);
   uint8_t* row_valid = smem + L::VALID_OFF;
   float* ssum = reinterpret_cast<float*>(smem + L::SSUM_OFF);
-  float* ssq = ssum + BLOCK_N;
+  float* ssq = ssum + kMaxStatCh;
+  uint8_t* stage = smem + L::STAGING_OFF;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // ---------------- tile coordinates
+  // ---------------- tile space
   const int n_tiles = (p.n_total + BLOCK_N - 1) / BLOCK_N;
-  int n_tile, m_tile, split = 0;
-  {
-    int bid = blockIdx.x;
-    if (MODE == MODE_FWD) {
-      n_tile = bid % n_tiles;
-      m_tile = bid / n_tiles;
-    } else {
-      const int m_tiles = (p.total_chunks + 1) / 2;
-      const int per_split = m_tiles * n_tiles;
-      split = bid / per_split;
-      bid -= split * per_split;
-      n_tile = bid % n_tiles;
-      m_tile = bid / n_tiles;
-    }
-  }
-  const int n0 = n_tile * BLOCK_N;
   const int tiles_per_img = p.tiles_h * p.tiles_w;
-
-  // K-loop extent
-  int kb_begin, kb_end;   // fwd: k-blocks (tap, chunk); wgrad: pixel tiles
-  if (MODE == MODE_FWD) {
-    kb_begin = 0;
-    kb_end = p.taps * p.kchunks;
-  } else {
-    const long long T = static_cast<long long>(p.N) * tiles_per_img;
-    kb_begin = static_cast<int>(T * split / p.splits);
-    kb_end = static_cast<int>(T * (split + 1) / p.splits);
-  }
-  const int num_kb = kb_end - kb_begin;
-
-  // fwd: pixel tile of this CTA
-  int img = 0, h0 = 0, w0 = 0;
-  if (MODE == MODE_FWD) {
-    img = m_tile / tiles_per_img;
-    const int r = m_tile - img * tiles_per_img;
-    h0 = (r / p.tiles_w) * p.th;
-    w0 = (r % p.tiles_w) * p.tw;
-  }
+  const long long T = static_cast<long long>(p.N) * tiles_per_img;        // pixel tiles
+  const int m_tiles_w = (p.total_chunks + 1) / 2;                          // wgrad: M tiles (pairs of 64-ch chunks)
+  const long long total_tiles =
+      MODE == MODE_FWD ? T * n_tiles : static_cast<long long>(m_tiles_w) * n_tiles * p.splits;
 
   // ---------------- one-time setup
   if (threadIdx.x == 0) {
@@ -131,68 +110,101 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full, 1);
+    mbar_init(&tmem_full[0], 1);
+    mbar_init(&tmem_full[1], 1);
+    mbar_init(&tmem_empty[0], 4);     // one arrival per epilogue warp
+    mbar_init(&tmem_empty[1], 4);
     fence_mbar_init();
     fence_proxy_async_smem();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr, BLOCK_N);
+    tmem_alloc(tmem_ptr, 2 * BLOCK_N);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < 2 * BLOCK_N; i += kThreads) ssum[i] = 0.f;
+  if (MODE == MODE_FWD)
+    for (int i = threadIdx.x; i < 2 * kMaxStatCh; i += kThreads) ssum[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
+  // decode a tile index into (m_tile, n_tile, [kb_begin, kb_end))
+  auto decode = [&](long long tile, int& m_tile, int& n_tile, int& kb_begin, int& kb_end) {
+    if (MODE == MODE_FWD) {
+      n_tile = static_cast<int>(tile % n_tiles);
+      m_tile = static_cast<int>(tile / n_tiles);
+      kb_begin = 0;
+      kb_end = p.taps * p.kchunks;
+    } else {
+      const int per_split = m_tiles_w * n_tiles;
+      const int split = static_cast<int>(tile / per_split);
+      const int r = static_cast<int>(tile - static_cast<long long>(split) * per_split);
+      n_tile = r % n_tiles;
+      m_tile = r / n_tiles;
+      kb_begin = static_cast<int>(T * split / p.splits);
+      kb_end = static_cast<int>(T * (split + 1) / p.splits);
+    }
+  };
+
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
-        uint8_t* sA = smem + s * L::STAGE_BYTES;
-        uint8_t* sB = sA + A_BYTES;
+      uint32_t it = 0;
+      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int m_tile, n_tile, kb_begin, kb_end;
+        decode(tile, m_tile, n_tile, kb_begin, kb_end);
+        const int n0 = n_tile * BLOCK_N;
+        int img = 0, h0 = 0, w0 = 0;
         if (MODE == MODE_FWD) {
-          const int kb = i;
-          const int tap = kb / p.kchunks;
-          const int cc = kb - tap * p.kchunks;
-          if (p.tap_mode == TAP_UP2) {
-            // ConvT dgrad: gather dy[2h+a, 2w+b]; 5-D view (c, w, a, h, n), one map per b
-            tma_load_5d(sA, (tap & 1) ? &tmA1 : &tmA0, &full_bar[s], cc * 64, w0, tap >> 1, h0, img);
-          } else {
-            int dh = 0, dw = 0;
-            if (p.tap_mode == TAP_3X3) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
-            tma_load_4d(sA, &tmA0, &full_bar[s], cc * 64, w0 + dw, h0 + dh, img);
-          }
-          tma_load_2d(sB, &tmB0, &full_bar[s], kb * 64, n0);
-        } else {
-          // wgrad: k-block = one pixel tile of 64 pixels
-          const int t = kb_begin + i;
-          const int im = t / tiles_per_img;
-          const int r = t - im * tiles_per_img;
-          const int ph0 = (r / p.tiles_w) * p.th;
-          const int pw0 = (r % p.tiles_w) * p.tw;
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const int q = 2 * m_tile + half;
-            int tap = q / p.kchunks;
-            int cc = q - tap * p.kchunks;
-            int dh = 0, dw = 0;
-            if (p.tap_mode == TAP_3X3) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
-            if (q >= p.total_chunks) cc = 0x100000;   // fully out of bounds -> zero fill
-            tma_load_4d(sA + half * 8192, &tmA0, &full_bar[s], cc * 64, pw0 + dw, ph0 + dh, im);
-          }
-#pragma unroll
-          for (int j = 0; j < BLOCK_N / 64; ++j) {
+          img = m_tile / tiles_per_img;
+          const int r = m_tile - img * tiles_per_img;
+          h0 = (r / p.tiles_w) * p.th;
+          w0 = (r % p.tiles_w) * p.tw;
+        }
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
+          uint8_t* sA = smem + s * L::STAGE_BYTES;
+          uint8_t* sB = sA + A_BYTES;
+          if (MODE == MODE_FWD) {
+            const int tap = kb / p.kchunks;
+            const int cc = kb - tap * p.kchunks;
             if (p.tap_mode == TAP_UP2) {
-              const int ab = n0 / p.cout;
-              const int co0 = n0 - ab * p.cout;
-              tma_load_5d(sB + j * 8192, (ab & 1) ? &tmB1 : &tmB0, &full_bar[s], co0 + j * 64, pw0, ab >> 1, ph0, im);
+              // ConvT dgrad: gather dy[2h+a, 2w+b]; 5-D view (c, w, a, h, n), one map per b
+              tma_load_5d(sA, (tap & 1) ? &tmA1 : &tmA0, &full_bar[s], cc * 64, w0, tap >> 1, h0, img);
             } else {
-              tma_load_4d(sB + j * 8192, &tmB0, &full_bar[s], n0 + j * 64, pw0, ph0, im);
+              int dh = 0, dw = 0;
+              if (p.tap_mode == TAP_3X3) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
+              tma_load_4d(sA, &tmA0, &full_bar[s], cc * 64, w0 + dw, h0 + dh, img);
+            }
+            tma_load_2d(sB, &tmB0, &full_bar[s], kb * 64, n0);
+          } else {
+            // wgrad: k-block = one pixel tile of 128 pixels
+            const int im = kb / tiles_per_img;
+            const int r = kb - im * tiles_per_img;
+            const int ph0 = (r / p.tiles_w) * p.th;
+            const int pw0 = (r % p.tiles_w) * p.tw;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const int q = 2 * m_tile + half;
+              int tap = q / p.kchunks;
+              int cc = q - tap * p.kchunks;
+              int dh = 0, dw = 0;
+              if (p.tap_mode == TAP_3X3) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
+              if (q >= p.total_chunks) cc = 0x100000;   // fully out of bounds -> zero fill
+              tma_load_4d(sA + half * 16384, &tmA0, &full_bar[s], cc * 64, pw0 + dw, ph0 + dh, im);
+            }
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 64; ++j) {
+              if (p.tap_mode == TAP_UP2) {
+                const int ab = n0 / p.cout;
+                const int co0 = n0 - ab * p.cout;
+                tma_load_5d(sB + j * 16384, (ab & 1) ? &tmB1 : &tmB0, &full_bar[s], co0 + j * 64, pw0, ab >> 1, ph0, im);
+              } else {
+                tma_load_4d(sB + j * 16384, &tmB0, &full_bar[s], n0 + j * 64, pw0, ph0, im);
+              }
             }
           }
         }
@@ -202,131 +214,151 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       const uint32_t idesc = make_idesc_16(128, BLOCK_N, MODE == MODE_WGRAD, MODE == MODE_WGRAD, p.a_dt, p.b_dt);
-      for (int i = 0; i < num_kb; ++i) {
-        const int s = i % STAGES;
-        const uint32_t ph = (i / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, lt = 0;
+      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int m_tile, n_tile, kb_begin, kb_end;
+        decode(tile, m_tile, n_tile, kb_begin, kb_end);
+        if (kb_end <= kb_begin) continue;
+        const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
+        ++lt;
+        mbar_wait(&tmem_empty[as], aph ^ 1);       // epilogue has drained this accumulator buffer
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
-        const uint32_t b_addr = a_addr + A_BYTES;
-        uint64_t da, db;
-        uint32_t kstep;   // descriptor start-address advance (in 16 B units) per UMMA_K = 16
-        if (MODE == MODE_FWD) {
-          da = make_smem_desc_sw128(a_addr, 16, 1024);
-          db = make_smem_desc_sw128(b_addr, 16, 1024);
-          kstep = 32 >> 4;          // 16 bf16 along the 128 B swizzle row
-        } else {
-          da = make_smem_desc_sw128(a_addr, 8192, 1024);   // LBO: next 64-channel group, SBO: next 8 pixel rows
-          db = make_smem_desc_sw128(b_addr, 8192, 1024);
-          kstep = 2048 >> 4;        // 16 pixel rows x 128 B
-        }
+        const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + A_BYTES;
+          uint64_t da, db;
+          uint32_t kstep;   // descriptor start-address advance (in 16 B units) per UMMA_K = 16
+          if (MODE == MODE_FWD) {
+            da = make_smem_desc_sw128(a_addr, 16, 1024);
+            db = make_smem_desc_sw128(b_addr, 16, 1024);
+            kstep = 32 >> 4;          // 16 elements along the 128 B swizzle row
+          } else {
+            da = make_smem_desc_sw128(a_addr, 16384, 1024);  // LBO: next 64-channel group, SBO: next 8 pixel rows
+            db = make_smem_desc_sw128(b_addr, 16384, 1024);
+            kstep = 2048 >> 4;        // 16 pixel rows x 128 B
+          }
+          constexpr int KSTEPS = MODE == MODE_FWD ? 4 : 8;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          umma_bf16(tmem_base, da + static_cast<uint64_t>(k * kstep), db + static_cast<uint64_t>(k * kstep), idesc,
-                    (i | k) != 0);
+          for (int k = 0; k < KSTEPS; ++k) {
+            umma_bf16(tmem_d, da + static_cast<uint64_t>(k * kstep), db + static_cast<uint64_t>(k * kstep), idesc,
+                      (kb > kb_begin || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);      // frees the smem slot once these MMAs have read it
         }
-        umma_commit(&empty_bar[s]);      // frees the smem slot once these MMAs have read it
+        umma_commit(&tmem_full[as]);       // accumulator complete
       }
-      umma_commit(tmem_full);            // accumulator complete
     }
   } else {
     // =========================== epilogue (warps 2..5) ===========================
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 64;        // 0..127
-    if (MODE == MODE_FWD) {
-      const int hl = row / p.tw, wl = row - hl * p.tw;
-      const bool valid = (h0 + hl < p.H) && (w0 + wl < p.W);
-      row_valid[row] = valid ? 1 : 0;
-      mbar_wait(tmem_full, 0);
-      tc_fence_after();
-      uint8_t* stage = smem;                // pipeline buffers are idle once tmem_full fired
-      constexpr int ROWB = BLOCK_N * 2;
-      const int co_base = p.up2 ? (n0 % p.cout) : n0;
+    const int ew = warp - 2;
+    uint32_t lt = 0;
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int m_tile, n_tile, kb_begin, kb_end;
+      decode(tile, m_tile, n_tile, kb_begin, kb_end);
+      if (kb_end <= kb_begin) continue;
+      const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
+      ++lt;
+      const int n0 = n_tile * BLOCK_N;
+      const uint32_t tmem_acc = tmem_base + as * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
+      if (MODE == MODE_FWD) {
+        const int img = m_tile / tiles_per_img;
+        const int rr = m_tile - img * tiles_per_img;
+        const int h0 = (rr / p.tiles_w) * p.th;
+        const int w0 = (rr % p.tiles_w) * p.tw;
+        const int hl = row / p.tw, wl = row - hl * p.tw;
+        row_valid[row] = ((h0 + hl < p.H) && (w0 + wl < p.W)) ? 1 : 0;
+        const int co_tile = p.up2 ? (n0 % p.cout) : n0;
+        int a_off = 0, b_off = 0;
+        if (p.up2) { const int ab = n0 / p.cout; a_off = ab >> 1; b_off = ab & 1; }
+        mbar_wait(&tmem_full[as], aph);
+        tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, v);
-        tmem_ld_wait();
-        if (p.bias != nullptr) {
+        for (int c64 = 0; c64 < BLOCK_N / 64; ++c64) {
+          // ---- TMEM -> registers -> 16-bit -> swizzled staging (128 rows x 128 B)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int ch = co_base + c * 32 + j;
-            const float b = (ch < (p.up2 ? p.cout : p.n_total)) ? __ldg(p.bias + ch) : 0.f;
-            v[j] = __float_as_uint(__uint_as_float(v[j]) + b);
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t v[32];
+            tmem_ld32(tmem_acc + c64 * 64 + hh * 32, v);
+            tmem_ld_wait();
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int ch = co_tile + c64 * 64 + hh * 32 + j;
+                const float b = (ch < (p.up2 ? p.cout : p.n_total)) ? __ldg(p.bias + ch) : 0.f;
+                v[j] = __float_as_uint(__uint_as_float(v[j]) + b);
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 o;
+              o.x = pack2(__uint_as_float(v[8 * i + 0]), __uint_as_float(v[8 * i + 1]), p.out_dt);
+              o.y = pack2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]), p.out_dt);
+              o.z = pack2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]), p.out_dt);
+              o.w = pack2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]), p.out_dt);
+              const int chunk = hh * 4 + i;
+              *reinterpret_cast<uint4*>(stage + row * 128 + (((chunk ^ row) & 7) << 4)) = o;
+            }
           }
-        }
+          if (c64 == BLOCK_N / 64 - 1) {           // all TMEM reads of this tile are done: release the buffer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+          }
+          named_bar_sync(1, 128);
+          // ---- per-channel statistics over the valid rows of the staged (rounded) values
+          if (p.stats != nullptr) {
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+            const int chunk = lane >> 2, word = lane & 3;
+#pragma unroll 8
+            for (int r = ew * 32; r < ew * 32 + 32; ++r) {
+              if (!row_valid[r]) continue;
+              const uint32_t u = *reinterpret_cast<const uint32_t*>(stage + r * 128 + (((chunk ^ r) & 7) << 4) + word * 4);
+              const float2 ab = unpack2(u, p.out_dt);
+              s0 += ab.x; s1 += ab.y; q0 += ab.x * ab.x; q1 += ab.y * ab.y;
+            }
+            const int ch = n0 + c64 * 64 + 2 * lane;   // host guarantees n_total <= kMaxStatCh when stats are on
+            if (ch < p.n_total) { atomicAdd(&ssum[ch], s0); atomicAdd(&ssq[ch], q0); }
+            if (ch + 1 < p.n_total) { atomicAdd(&ssum[ch + 1], s1); atomicAdd(&ssq[ch + 1], q1); }
+          }
+          // ---- coalesced store: consecutive threads take consecutive 16 B chunks of a pixel row
+          const int co_base = co_tile + c64 * 64;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          uint4 o;
-          o.x = pack2(__uint_as_float(v[8 * i + 0]), __uint_as_float(v[8 * i + 1]), p.out_dt);
-          o.y = pack2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]), p.out_dt);
-          o.z = pack2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]), p.out_dt);
-          o.w = pack2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]), p.out_dt);
-          const int chunk = c * 4 + i;
-          *reinterpret_cast<uint4*>(stage + row * ROWB + (((chunk & ~7) | ((chunk ^ row) & 7)) << 4)) = o;
-        }
-      }
-      tc_fence_before();
-      named_bar_sync(1, 128);
-      // ---- per-channel statistics over the valid rows of the staged (bf16-rounded) tile
-      if (p.stats != nullptr) {
-        const int ew = warp - 2;
-        for (int cp = lane; cp < BLOCK_N / 2; cp += 32) {
-          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-          const int chunk = cp >> 2, word = cp & 3;
-          for (int r = ew * 32; r < ew * 32 + 32; ++r) {
+          for (int i = 0; i < 8; ++i) {
+            const int idx = et + 128 * i;
+            const int r = idx >> 3, chunk = idx & 7;
             if (!row_valid[r]) continue;
-            const uint32_t u = *reinterpret_cast<const uint32_t*>(
-                stage + r * ROWB + (((chunk & ~7) | ((chunk ^ r) & 7)) << 4) + word * 4);
-            const float2 ab = unpack2(u, p.out_dt);
-            s0 += ab.x; s1 += ab.y; q0 += ab.x * ab.x; q1 += ab.y * ab.y;
+            if (co_base + chunk * 8 >= p.n_store) continue;
+            const int rh = r / p.tw, rw = r - rh * p.tw;
+            int oh = h0 + rh, ow = w0 + rw;
+            if (p.up2) { oh = 2 * oh + a_off; ow = 2 * ow + b_off; }
+            if (oh >= p.out_h || ow >= p.out_w) continue;
+            uint4 val = *reinterpret_cast<const uint4*>(stage + r * 128 + (((chunk ^ r) & 7) << 4));
+            uint16_t* dst = p.out + img * p.out_img_stride + oh * p.out_row_stride + ow * p.out_pix_stride +
+                            co_base + chunk * 8;
+            if (p.accum) {
+              const uint4 old = *reinterpret_cast<const uint4*>(dst);
+              const int dt = p.out_dt;
+              float2 a, b;
+              a = unpack2(val.x, dt); b = unpack2(old.x, dt); val.x = pack2(a.x + b.x, a.y + b.y, dt);
+              a = unpack2(val.y, dt); b = unpack2(old.y, dt); val.y = pack2(a.x + b.x, a.y + b.y, dt);
+              a = unpack2(val.z, dt); b = unpack2(old.z, dt); val.z = pack2(a.x + b.x, a.y + b.y, dt);
+              a = unpack2(val.w, dt); b = unpack2(old.w, dt); val.w = pack2(a.x + b.x, a.y + b.y, dt);
+            }
+            *reinterpret_cast<uint4*>(dst) = val;
           }
-          atomicAdd(&ssum[2 * cp], s0);
-          atomicAdd(&ssum[2 * cp + 1], s1);
-          atomicAdd(&ssq[2 * cp], q0);
-          atomicAdd(&ssq[2 * cp + 1], q1);
+          named_bar_sync(1, 128);              // staging free again
         }
-        named_bar_sync(1, 128);
-        for (int ch = et; ch < BLOCK_N; ch += 128) {
-          if (n0 + ch < p.n_total) {
-            atomicAdd(p.stats + 2 * (n0 + ch), static_cast<double>(ssum[ch]));
-            atomicAdd(p.stats + 2 * (n0 + ch) + 1, static_cast<double>(ssq[ch]));
-          }
-        }
-      }
-      // ---- coalesced store: consecutive threads take consecutive 16 B chunks of a pixel row
-      constexpr int CPR = BLOCK_N / 8;
-      int a_off = 0, b_off = 0;
-      if (p.up2) { const int ab = n0 / p.cout; a_off = ab >> 1; b_off = ab & 1; }
-#pragma unroll 4
-      for (int i = 0; i < CPR; ++i) {
-        const int idx = et + 128 * i;
-        const int r = idx / CPR, chunk = idx % CPR;
-        if (!row_valid[r]) continue;
-        if (co_base + chunk * 8 >= p.n_store) continue;
-        const int rh = r / p.tw, rw = r - rh * p.tw;
-        int oh = h0 + rh, ow = w0 + rw;
-        if (p.up2) { oh = 2 * oh + a_off; ow = 2 * ow + b_off; }
-        if (oh >= p.out_h || ow >= p.out_w) continue;
-        uint4 val = *reinterpret_cast<const uint4*>(stage + r * ROWB + (((chunk & ~7) | ((chunk ^ r) & 7)) << 4));
-        uint16_t* dst = p.out + img * p.out_img_stride + oh * p.out_row_stride + ow * p.out_pix_stride +
-                        co_base + chunk * 8;
-        if (p.accum) {
-          const uint4 old = *reinterpret_cast<const uint4*>(dst);
-          const int dt = p.out_dt;
-          float2 a, b;
-          a = unpack2(val.x, dt); b = unpack2(old.x, dt); val.x = pack2(a.x + b.x, a.y + b.y, dt);
-          a = unpack2(val.y, dt); b = unpack2(old.y, dt); val.y = pack2(a.x + b.x, a.y + b.y, dt);
-          a = unpack2(val.z, dt); b = unpack2(old.z, dt); val.z = pack2(a.x + b.x, a.y + b.y, dt);
-          a = unpack2(val.w, dt); b = unpack2(old.w, dt); val.w = pack2(a.x + b.x, a.y + b.y, dt);
-        }
-        *reinterpret_cast<uint4*>(dst) = val;
-      }
-    } else {
-      // wgrad: rows = (chunk half, channel j); columns = n.  fp32 red.add into dW[n][k]
-      if (num_kb > 0) {
-        mbar_wait(tmem_full, 0);
+      } else {
+        // wgrad: rows = (chunk half, channel j); columns = n.  fp32 red.add into dW[n][k]
+        mbar_wait(&tmem_full[as], aph);
         tc_fence_after();
         const int qc = 2 * m_tile + (row >> 6);
         const bool row_ok = qc < p.total_chunks;
@@ -334,8 +366,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 32; ++c) {
           uint32_t v[32];
-          tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, v);
+          tmem_ld32(tmem_acc + c * 32, v);
           tmem_ld_wait();
+          if (c == BLOCK_N / 32 - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+          }
           if (row_ok) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -344,18 +381,30 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
             }
           }
         }
-        tc_fence_before();
+      }
+    }
+  }
+  if (MODE == MODE_FWD && warp >= 2 && p.stats != nullptr) {
+    // one flush per CTA: per-channel partial sums of every tile this CTA produced -> fp64 global atomics
+    named_bar_sync(1, 128);
+    for (int ch = threadIdx.x - 64; ch < p.n_total; ch += 128) {
+      const float a = ssum[ch], b = ssq[ch];
+      if (a != 0.f || b != 0.f) {
+        atomicAdd(p.stats + 2 * ch, static_cast<double>(a));
+        atomicAdd(p.stats + 2 * ch + 1, static_cast<double>(b));
       }
     }
   }
   __syncwarp();
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BLOCK_N);
+    tmem_dealloc(tmem_base, 2 * BLOCK_N);
   }
 }
 
+// =====================================================================================
 // =====================================================================================
 // host side
 // =====================================================================================
@@ -439,7 +488,7 @@ static void pick_tile(int H, int W, int P, int* th, int* tw) {
 template <int BLOCK_N, int STAGES, int MODE>
 static int launch_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1,
                     const IgemmArgs& args, long long grid, cudaStream_t stream) {
-  using L = SmemLayout<BLOCK_N, STAGES>;
+  using L = SmemLayout<BLOCK_N, STAGES, MODE>;
   auto kern = igemm_kernel<BLOCK_N, STAGES, MODE>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
@@ -448,6 +497,13 @@ static int launch_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensor
   });
   if (attr_err != cudaSuccess) return HPRI_ERR_CUDA;
   if (grid <= 0 || grid > 0x7FFFFFFFLL) return HPRI_ERR_ARG;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+  }
+  if (grid > num_sms) grid = num_sms;          // persistent: one CTA per SM walks the tile list
   kern<<<(unsigned)grid, kThreads, L::ALLOC, stream>>>(a0, a1, b0, b1, args);
   ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? HPRI_OK : HPRI_ERR_CUDA;
@@ -457,9 +513,9 @@ template <int MODE>
 static int launch(int block_n, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0,
                   const CUtensorMap& b1, const IgemmArgs& args, long long grid, cudaStream_t stream) {
   switch (block_n) {
-    case 64: return launch_t<64, 4, MODE>(a0, a1, b0, b1, args, grid, stream);
-    case 128: return launch_t<128, 3, MODE>(a0, a1, b0, b1, args, grid, stream);
-    case 256: return launch_t<256, 4, MODE>(a0, a1, b0, b1, args, grid, stream);
+    case 64: return launch_t<64, MODE == MODE_FWD ? 7 : 4, MODE>(a0, a1, b0, b1, args, grid, stream);
+    case 128: return launch_t<128, MODE == MODE_FWD ? 5 : 3, MODE>(a0, a1, b0, b1, args, grid, stream);
+    case 256: return launch_t<256, MODE == MODE_FWD ? 4 : 2, MODE>(a0, a1, b0, b1, args, grid, stream);
   }
   return HPRI_ERR_ARG;
 }
@@ -504,6 +560,7 @@ extern "C" int hpri_igemm_fwd(const hpri_view_t* x, const void* wpack, int w_dty
   if (x->dtype != w_dtype) return HPRI_ERR_ARG;     // kind::f16 takes A and B in one format
   a.bias = bias; a.stats = stats; a.accum = accumulate ? 1 : 0;
   if (accumulate && stats) return HPRI_ERR_ARG;
+  if (stats && w_rows > kMaxStatCh) return HPRI_ERR_ARG;
   const int bn = pick_block_n(w_rows, block_n);
   CUtensorMap ma, mb;
   if ((rc = map_nhwc(&ma, *x, a.th, a.tw)) != HPRI_OK) return rc;
@@ -582,7 +639,7 @@ extern "C" int hpri_igemm_wgrad(const hpri_view_t* x, const hpri_view_t* dy, int
   if (mode < 0 || mode > 2) return HPRI_ERR_ARG;
   IgemmArgs a{};
   a.N = x->n; a.H = x->h; a.W = x->w;
-  pick_tile(a.H, a.W, 64, &a.th, &a.tw);
+  pick_tile(a.H, a.W, 128, &a.th, &a.tw);
   a.tiles_h = (a.H + a.th - 1) / a.th; a.tiles_w = (a.W + a.tw - 1) / a.tw;
   a.taps = mode == 1 ? 9 : 1; a.tap_mode = mode == 1 ? TAP_3X3 : (mode == 2 ? TAP_UP2 : TAP_NONE);
   a.kchunks = (x->c + 63) / 64;
@@ -605,9 +662,9 @@ extern "C" int hpri_igemm_wgrad(const hpri_view_t* x, const hpri_view_t* dy, int
   const long long T = (long long)a.N * a.tiles_h * a.tiles_w;
   const int m_tiles = (a.total_chunks + 1) / 2, n_tiles = (n_total + bn - 1) / bn;
   if (splits <= 0) {
-    // enough CTAs for ~4 waves of 148 SMs x 2 resident, at least 8 pixel tiles per CTA
-    long long want = (4LL * 296 + m_tiles * n_tiles - 1) / (m_tiles * n_tiles);
-    long long cap = T / 8 > 0 ? T / 8 : 1;
+    // persistent CTAs: aim at ~2 tiles per SM, at least 4 pixel tiles (k-blocks) per tile
+    long long want = (2LL * 148 + m_tiles * n_tiles / 2) / (m_tiles * n_tiles);
+    long long cap = T / 4 > 0 ? T / 4 : 1;
     splits = (int)(want < cap ? want : cap);
     if (splits < 1) splits = 1;
   }
