@@ -19,6 +19,7 @@
 #include "ptx.cuh"
 #include "hyperpri_b200.h"
 
+#include <cstdlib>
 #include <mutex>
 
 namespace hpri {
@@ -405,6 +406,273 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
 }
 
 // =====================================================================================
+
+// =====================================================================================
+// 3x3 convolution with halo reuse (fprop and dgrad of the U-Net blocks at the high resolutions).
+//
+// The generic kernel above re-reads the activation tile from L2 once per filter tap (9x) and the
+// weight tile once per 128 output pixels; measured on B200 every layer then sits on the L2->SM
+// bandwidth (10-13 TB/s) instead of the tensor pipe.  Here one CTA owns a 256-pixel tile
+// (th x tw, tw in {8,16,32}, two M=128 accumulator halves) and, per 64-channel chunk, loads the
+// (th+2) x tw halo block only three times (one per horizontal shift s); the three vertical taps r are
+// descriptor offsets of r*tw*128 B into that block -- a multiple of the 1024 B swizzle atom, so the
+// 128B-swizzle phase is preserved.  The weight tile of each tap is shared by both halves.
+// L2->smem bytes per MAC drop 2.2-2.5x.  Accumulators: 2 buffers x 2 halves x BLOCK_N TMEM columns.
+// =====================================================================================
+constexpr int kHaloStatCh = 1024;
+constexpr int kHaloABytes = 40960;          // (th+2)*tw rows x 128 B, worst case tw = 32
+
+template <int BLOCK_N, int STAGES>
+struct HaloSmem {
+  static constexpr int B_TILE = BLOCK_N * 128;
+  static constexpr int STAGE_BYTES = kHaloABytes + 3 * B_TILE;
+  static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int STAGING_OFF = PIPE_BYTES;
+  static constexpr int BAR_OFF = STAGING_OFF + 128 * 128;
+  static constexpr int TMEMPTR_OFF = BAR_OFF + (2 * STAGES + 4) * 8;
+  static constexpr int SSUM_OFF = TMEMPTR_OFF + 8;
+  static constexpr int TOTAL = SSUM_OFF + 2 * kHaloStatCh * 4;
+  static constexpr int ALLOC = TOTAL + 1024;
+  static_assert(ALLOC <= 227 * 1024, "shared memory budget exceeded");
+};
+
+template <int DT>
+__device__ __forceinline__ uint32_t pack2_t(float lo, float hi) {
+  if (DT == DT_F16) {
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  return pack_bf16x2(lo, hi);
+}
+// 32 fp32 accumulator columns -> 16-bit pairs -> swizzled staging row (zeros for invalid rows)
+template <int DT>
+__device__ __forceinline__ void stage_row32(uint8_t* stage, int row, int hh, const uint32_t (&v)[32], bool valid) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (valid) {
+      o.x = pack2_t<DT>(__uint_as_float(v[8 * i + 0]), __uint_as_float(v[8 * i + 1]));
+      o.y = pack2_t<DT>(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]));
+      o.z = pack2_t<DT>(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]));
+      o.w = pack2_t<DT>(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]));
+    }
+    const int chunk = hh * 4 + i;
+    *reinterpret_cast<uint4*>(stage + row * 128 + (((chunk ^ row) & 7) << 4)) = o;
+  }
+}
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const IgemmArgs p) {
+  using L = HaloSmem<BLOCK_N, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::TMEMPTR_OFF);
+  float* ssum = reinterpret_cast<float*>(smem + L::SSUM_OFF);
+  float* ssq = ssum + kHaloStatCh;
+  uint8_t* stage = smem + L::STAGING_OFF;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tiles = (p.n_total + BLOCK_N - 1) / BLOCK_N;
+  const int tiles_per_img = p.tiles_h * p.tiles_w;
+  const long long total_tiles = static_cast<long long>(p.N) * tiles_per_img * n_tiles;
+  const int steps_per_tile = 3 * p.kchunks;                    // (channel chunk, horizontal shift)
+  const uint32_t a_bytes = static_cast<uint32_t>((p.th + 2) * p.tw * 128);
+  const int ltw = 31 - __clz(p.tw);
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full[0], 1);
+    mbar_init(&tmem_full[1], 1);
+    mbar_init(&tmem_empty[0], 4);
+    mbar_init(&tmem_empty[1], 4);
+    fence_mbar_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 4 * BLOCK_N);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < 2 * kHaloStatCh; i += kThreads) ssum[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = static_cast<int>(tile % n_tiles);
+        const int m_tile = static_cast<int>(tile / n_tiles);
+        const int img = m_tile / tiles_per_img;
+        const int rr = m_tile - img * tiles_per_img;
+        const int h0 = (rr / p.tiles_w) * p.th, w0 = (rr % p.tiles_w) * p.tw;
+        const int n0 = n_tile * BLOCK_N;
+        for (int st = 0; st < steps_per_tile; ++st, ++it) {
+          const int cc = st / 3, sft = st - cc * 3;
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full_bar[s], a_bytes + 3 * L::B_TILE);
+          uint8_t* sA = smem + s * L::STAGE_BYTES;
+          uint8_t* sB = sA + kHaloABytes;
+          tma_load_4d(sA, &tmA, &full_bar[s], cc * 64, w0 + sft - 1, h0 - 1, img);
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+            tma_load_2d(sB + r * L::B_TILE, &tmB, &full_bar[s], ((r * 3 + sft) * p.kchunks + cc) * 64, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_16(128, BLOCK_N, 0, 0, p.a_dt, p.b_dt);
+      const uint32_t row_shift = static_cast<uint32_t>(p.tw * 128) >> 4;       // one image row of the halo block
+      uint32_t it = 0, lt = 0;
+      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
+        mbar_wait(&tmem_empty[as], aph ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + as * (2 * BLOCK_N);
+        for (int st = 0; st < steps_per_tile; ++st, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint64_t da0 = make_smem_desc_sw128(a_addr, 16, 1024);
+          const uint64_t db0 = make_smem_desc_sw128(a_addr + kHaloABytes, 16, 1024);
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              const uint64_t da = da0 + static_cast<uint64_t>(r * row_shift + hf * (16384 >> 4));
+              const uint64_t db = db0 + static_cast<uint64_t>(r * (L::B_TILE >> 4));
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem_d + hf * BLOCK_N, da + 2 * k, db + 2 * k, idesc, (st > 0 || r > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full[as]);
+      }
+    }
+  } else {
+    // =========================== epilogue (warps 2..5) ===========================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 64;
+    const int ew = warp - 2;
+    const int my_chunk = et & 7, my_r0 = et >> 3;        // store duty: 16 B chunk my_chunk of rows my_r0 + 16 i
+    uint32_t lt = 0;
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
+      const int n_tile = static_cast<int>(tile % n_tiles);
+      const int m_tile = static_cast<int>(tile / n_tiles);
+      const int img = m_tile / tiles_per_img;
+      const int rr = m_tile - img * tiles_per_img;
+      const int h0 = (rr / p.tiles_w) * p.th, w0 = (rr % p.tiles_w) * p.tw;
+      const int n0 = n_tile * BLOCK_N;
+      uint16_t* out_img = p.out + img * p.out_img_stride;
+      mbar_wait(&tmem_full[as], aph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int hf = 0; hf < 2; ++hf) {
+        const int pix = hf * 128 + row;
+        const bool valid = (h0 + (pix >> ltw) < p.H) && (w0 + (pix & (p.tw - 1)) < p.W);
+        const uint32_t tmem_acc = tmem_base + as * (2 * BLOCK_N) + hf * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+        for (int c64 = 0; c64 < BLOCK_N / 64; ++c64) {
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t v[32];
+            tmem_ld32(tmem_acc + c64 * 64 + hh * 32, v);
+            tmem_ld_wait();
+            if (p.out_dt == DT_F16) stage_row32<DT_F16>(stage, row, hh, v, valid);
+            else stage_row32<DT_BF16>(stage, row, hh, v, valid);
+          }
+          if (hf == 1 && c64 == BLOCK_N / 64 - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+          }
+          named_bar_sync(1, 128);
+          if (p.stats != nullptr) {
+            // invalid rows were staged as zeros: unconditional column sums over this warp's 32 rows
+            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+            const int chunk = lane >> 2;
+            const uint8_t* base = stage + (ew * 32) * 128 + (lane & 3) * 4;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const uint32_t u = *reinterpret_cast<const uint32_t*>(base + i * 128 + (((chunk ^ i) & 7) << 4));
+              const float2 ab = unpack2(u, p.out_dt);
+              s0 += ab.x; s1 += ab.y; q0 = fmaf(ab.x, ab.x, q0); q1 = fmaf(ab.y, ab.y, q1);
+            }
+            const int ch = n0 + c64 * 64 + 2 * lane;
+            if (ch < p.n_total) { atomicAdd(&ssum[ch], s0); atomicAdd(&ssq[ch], q0); }
+            if (ch + 1 < p.n_total) { atomicAdd(&ssum[ch + 1], s1); atomicAdd(&ssq[ch + 1], q1); }
+          }
+          const int co = n0 + c64 * 64 + my_chunk * 8;
+          if (co < p.n_store) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = my_r0 + 16 * i;
+              const int px = hf * 128 + r;
+              const int oh = h0 + (px >> ltw), ow = w0 + (px & (p.tw - 1));
+              if (oh < p.out_h && ow < p.out_w) {
+                uint4 val = *reinterpret_cast<const uint4*>(stage + r * 128 + (((my_chunk ^ r) & 7) << 4));
+                uint16_t* dst = out_img + oh * p.out_row_stride + ow * p.out_pix_stride + co;
+                if (p.accum) {
+                  const uint4 old = *reinterpret_cast<const uint4*>(dst);
+                  const int dt = p.out_dt;
+                  float2 a, b;
+                  a = unpack2(val.x, dt); b = unpack2(old.x, dt); val.x = pack2(a.x + b.x, a.y + b.y, dt);
+                  a = unpack2(val.y, dt); b = unpack2(old.y, dt); val.y = pack2(a.x + b.x, a.y + b.y, dt);
+                  a = unpack2(val.z, dt); b = unpack2(old.z, dt); val.z = pack2(a.x + b.x, a.y + b.y, dt);
+                  a = unpack2(val.w, dt); b = unpack2(old.w, dt); val.w = pack2(a.x + b.x, a.y + b.y, dt);
+                }
+                *reinterpret_cast<uint4*>(dst) = val;
+              }
+            }
+          }
+          named_bar_sync(1, 128);
+        }
+      }
+    }
+    if (p.stats != nullptr) {
+      named_bar_sync(1, 128);
+      for (int ch = et; ch < p.n_total; ch += 128) {
+        const float a = ssum[ch], b = ssq[ch];
+        if (a != 0.f || b != 0.f) {
+          atomicAdd(p.stats + 2 * ch, static_cast<double>(a));
+          atomicAdd(p.stats + 2 * ch + 1, static_cast<double>(b));
+        }
+      }
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 4 * BLOCK_N);
+  }
+}
+
 // =====================================================================================
 // host side
 // =====================================================================================
@@ -528,9 +796,61 @@ static int pick_block_n(int n_total, int forced) {
   return 128;
 }
 
+
+// halo kernel launcher -------------------------------------------------------------------
+template <int BLOCK_N, int STAGES>
+static int launch_halo_t(const CUtensorMap& ma, const CUtensorMap& mb, const IgemmArgs& args, long long tiles,
+                         cudaStream_t stream) {
+  using L = HaloSmem<BLOCK_N, STAGES>;
+  auto kern = conv3x3_halo_kernel<BLOCK_N, STAGES>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [&] {
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::ALLOC);
+  });
+  if (attr_err != cudaSuccess) return HPRI_ERR_CUDA;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+  }
+  long long grid = tiles < num_sms ? tiles : num_sms;
+  if (grid <= 0) return HPRI_ERR_ARG;
+  kern<<<(unsigned)grid, kThreads, L::ALLOC, stream>>>(ma, mb, args);
+  ++g_launch_count;
+  return cudaGetLastError() == cudaSuccess ? HPRI_OK : HPRI_ERR_CUDA;
+}
+
+// choose tw in {8,16,32} (th = 256/tw) minimising padded pixels; returns waste fraction
+static double pick_halo_tile(int H, int W, int* th, int* tw) {
+  double best = 1e30;
+  for (int w = 8; w <= 32; w *= 2) {
+    const int h = 256 / w;
+    const double padded = (double)((H + h - 1) / h) * h * ((W + w - 1) / w) * w;
+    if (padded < best) { best = padded; *th = h; *tw = w; }
+  }
+  return best / ((double)H * W) - 1.0;
+}
+
+static int g_conv_algo = -2;               // -1 heuristic, 0 generic kernel, 1 halo-reuse kernel
+static int conv_algo_override() {          // env HPRI_CONV_ALGO seeds it; hpri_set_conv_algo overrides
+  if (g_conv_algo == -2) {
+    const char* e = getenv("HPRI_CONV_ALGO");
+    g_conv_algo = e ? atoi(e) : -1;
+  }
+  return g_conv_algo;
+}
+
 }  // namespace hpri
 
 using namespace hpri;
+
+extern "C" int hpri_set_conv_algo(int algo) {
+  if (algo < -1 || algo > 1) return HPRI_ERR_ARG;
+  g_conv_algo = algo;
+  return HPRI_OK;
+}
 
 // -------------------------------------------------------------------------------------
 // C ABI
@@ -561,6 +881,26 @@ extern "C" int hpri_igemm_fwd(const hpri_view_t* x, const void* wpack, int w_dty
   a.bias = bias; a.stats = stats; a.accum = accumulate ? 1 : 0;
   if (accumulate && stats) return HPRI_ERR_ARG;
   if (stats && w_rows > kMaxStatCh) return HPRI_ERR_ARG;
+  if (taps == 9 && bias == nullptr) {
+    // halo-reuse kernel where the 256-pixel tiles fit the image well (the high-resolution levels)
+    int hth = 0, htw = 0;
+    const double waste = pick_halo_tile(a.H, a.W, &hth, &htw);
+    const int ov = conv_algo_override();
+    const bool stats_ok = !stats || w_rows <= kHaloStatCh;
+    if (stats_ok && (ov == 1 || (ov < 0 && waste <= 1.0))) {
+      a.th = hth; a.tw = htw;
+      a.tiles_h = (a.H + hth - 1) / hth; a.tiles_w = (a.W + htw - 1) / htw;
+      const int hbn = w_rows <= 64 ? 64 : 128;
+      CUtensorMap ma, mb;
+      uint64_t dims[4] = {(uint64_t)x->c, (uint64_t)x->w, (uint64_t)x->h, (uint64_t)x->n};
+      uint64_t str[3] = {(uint64_t)x->pix_stride * 2, (uint64_t)x->row_stride * 2, (uint64_t)x->img_stride * 2};
+      uint32_t box[4] = {64, (uint32_t)htw, (uint32_t)(hth + 2), 1};
+      if ((rc = make_map(&ma, x->ptr, 4, dims, str, box, x->dtype)) != HPRI_OK) return rc;
+      if ((rc = map_weights(&mb, wpack, w_rows, kpad, hbn, w_dtype)) != HPRI_OK) return rc;
+      const long long tiles = (long long)a.N * a.tiles_h * a.tiles_w * ((w_rows + hbn - 1) / hbn);
+      return hbn == 64 ? launch_halo_t<64, 3>(ma, mb, a, tiles, stream) : launch_halo_t<128, 2>(ma, mb, a, tiles, stream);
+    }
+  }
   const int bn = pick_block_n(w_rows, block_n);
   CUtensorMap ma, mb;
   if ((rc = map_nhwc(&ma, *x, a.th, a.tw)) != HPRI_OK) return rc;

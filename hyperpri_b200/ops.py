@@ -141,6 +141,11 @@ def igemm_fwd(x, wpack, rows, taps, y, n_store, bias=None, stats=None, block_n=0
                                     _ptr(stats), int(accumulate), block_n, _stream()), "hpri_igemm_fwd")
 
 
+def set_conv_algo(algo: int):
+    """-1 heuristic, 0 generic per-tap kernel, 1 halo-reuse kernel (tests / benchmarks)."""
+    check(_lib.lib().hpri_set_conv_algo(int(algo)), "hpri_set_conv_algo")
+
+
 @_timed
 def convT_fwd(x, wpack, cout, y, bias=None, block_n=0):
     xv, yv = view(x), view(y)

@@ -52,6 +52,9 @@ long long hpri_launch_count(void);
 int hpri_igemm_fwd(const hpri_view_t* x, const void* wpack, int w_dtype, int w_rows, int kpad, int taps, const hpri_view_t* y,
                    int n_store, const float* bias, double* stats, int accumulate, int block_n, void* stream);
 
+/* 3x3 kernel selection: -1 heuristic (default), 0 generic per-tap kernel, 1 halo-reuse kernel. */
+int hpri_set_conv_algo(int algo);
+
 /* nn.ConvTranspose2d(k=2,s=2) fprop writing straight into the concat buffer (model_parts.py:63-64,
  * 74-87: pad + cat are absorbed by the destination view) and its dgrad. */
 int hpri_convT2x2_fwd(const hpri_view_t* x, const void* wpack, int w_dtype, int cout, int kpad, const hpri_view_t* y,

@@ -57,9 +57,20 @@ CONV_CASES = [
 ]
 
 
+@pytest.fixture(params=[0, 1], ids=["generic", "halo"])
+def conv_algo(request):
+    ops.set_conv_algo(request.param)
+    yield request.param
+    ops.set_conv_algo(-1)
+
+
+HALO_CASES = [(2, 32, 24, 64, 64, 0), (1, 40, 50, 128, 64, 0), (1, 33, 70, 240, 64, 0), (2, 16, 33, 64, 128, 0),
+              (1, 70, 37, 128, 256, 0), (1, 8, 96, 256, 128, 0)]
+
+
 @pytest.mark.parametrize("dt", [BF, FH])
-@pytest.mark.parametrize("n,h,w,cin,cout,bn", CONV_CASES)
-def test_conv3x3_fwd_and_stats(n, h, w, cin, cout, bn, dt):
+@pytest.mark.parametrize("n,h,w,cin,cout,bn", CONV_CASES + HALO_CASES)
+def test_conv3x3_fwd_and_stats(n, h, w, cin, cout, bn, dt, conv_algo):
     x = rnd(n, cin, h, w, seed=1)
     wt = rnd(cout, cin, 3, 3, scale=1 / math.sqrt(cin * 9), seed=2)
     xb = nhwc(x, dt=dt)
@@ -79,8 +90,8 @@ def test_conv3x3_fwd_and_stats(n, h, w, cin, cout, bn, dt):
     assert torch.allclose(stats[:, 1], (g64 * g64).sum(0), rtol=1e-6, atol=1e-3)
 
 
-@pytest.mark.parametrize("n,h,w,cin,cout,bn", CONV_CASES[:5])
-def test_conv3x3_dgrad(n, h, w, cin, cout, bn):
+@pytest.mark.parametrize("n,h,w,cin,cout,bn", CONV_CASES[:5] + HALO_CASES[:3])
+def test_conv3x3_dgrad(n, h, w, cin, cout, bn, conv_algo):
     dy = rnd(n, cout, h, w, seed=3)
     wt = rnd(cout, cin, 3, 3, scale=1 / math.sqrt(cout * 9), seed=4)
     dyb = nhwc(dy)

@@ -32,7 +32,7 @@ def conv_case(n, h, w, cin, cout, taps=9, bn=0):
     # wgrad
     xg = x.to(ops.GRAD); dy = torch.randn((n, h, w, cout), device=DEV).to(ops.GRAD)
     gw = spec.grad_buffer(DEV)
-    if taps == 9:
+    if taps == 9 and os.environ.get("WGRAD", "0") == "1":
         res["wgrad"] = t_ms(lambda: ops.igemm_wgrad(xg, dy, 1, cout, gw, block_n=bn))
     return gf, res
 
@@ -51,6 +51,9 @@ CASES = [
 ]
 if __name__ == "__main__":
     out = []
+    algo = int(os.environ.get("ALGO", "-1"))
+    ops.set_conv_algo(algo)
+    print("conv algo", algo)
     for name, n, h, w, ci, co, taps, bn in CASES:
         gf, r = conv_case(n, h, w, ci, co, taps, bn)
         line = f"{name:44s} {gf:7.1f} GF | " + " | ".join(f"{k} {v*1e3:7.1f} us {gf/v:6.0f} TF/s" for k, v in r.items())
