@@ -195,7 +195,7 @@ def main():
         invalidate()                                   # weights change every optimizer step: re-pack inside the step
         logits = eng.forward(x, True)
         _, dlogit, _ = eng.loss_and_dlogit(logits, mask, grad_scale=gscale)
-        eng.backward(dlogit)
+        eng.backward(dlogit, prescaled=True)
         red.finish()
 
     def sync():

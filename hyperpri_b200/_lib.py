@@ -44,6 +44,7 @@ SIGNATURES = {
     "hpri_bce_fwd_bwd": [_p, _p, _ll, _f, _f, _p, _p, _p, _p],
     "hpri_colsum": [_VP, _p, _f, _p],
     "hpri_sum_f32": [_p, _ll, _p, _p],
+    "hpri_scale_check": [_p, _ll, _f, _p, _p],
 }
 
 ERRORS = {-1: "HPRI_ERR_ARG", -2: "HPRI_ERR_ALIGN", -3: "HPRI_ERR_DRIVER", -4: "HPRI_ERR_TENSORMAP",

@@ -531,6 +531,24 @@ __global__ void scale_f32_k(float* p, int n, float beta) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = beta == 0.f ? 0.f : p[i] * beta;
 }
+// x *= scale; *flag |= 1 when a non-finite value is seen (loss-scaled fp16 gradients: unscale + overflow check)
+__global__ void __launch_bounds__(256) scale_check_k(float* __restrict__ x, long long n, float scale, int* flag) {
+  bool bad = false;
+  const long long n4 = n >> 2;
+  float4* x4 = reinterpret_cast<float4*>(x);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = x4[i];
+    v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    bad |= !(isfinite(v.x) && isfinite(v.y) && isfinite(v.z) && isfinite(v.w));
+    x4[i] = v;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const float v = x[(n4 << 2) + threadIdx.x] * scale;
+    bad |= !isfinite(v);
+    x[(n4 << 2) + threadIdx.x] = v;
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
 __global__ void sum_f32_k(const float* __restrict__ x, long long n, float* out) {
   float s = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -725,6 +743,11 @@ extern "C" int hpri_colsum(const hpri_view_t* x, float* out, float beta, void* s
   colsum_k<<<grid_for(npix, slots * 16, 148 * 4), 256, (size_t)slots * CG * 32, (cudaStream_t)stream>>>(mk(x), out,
                                                                                                        slots, CG);
   return last_err(2);
+}
+extern "C" int hpri_scale_check(float* x, long long numel, float scale, int* flag, void* stream) {
+  if (!x || !flag || numel <= 0 || (reinterpret_cast<uintptr_t>(x) & 15)) return HPRI_ERR_ARG;
+  scale_check_k<<<grid_for(numel, 256 * 16, 148 * 8), 256, 0, (cudaStream_t)stream>>>(x, numel, scale, flag);
+  return last_err();
 }
 extern "C" int hpri_sum_f32(const float* x, long long numel, float* out, void* stream) {
   if (!x || !out || numel <= 0) return HPRI_ERR_ARG;

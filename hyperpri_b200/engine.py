@@ -21,6 +21,7 @@ Dataflow decisions:
 """
 from __future__ import annotations
 
+import math
 from typing import Dict, List, Optional
 
 import torch
@@ -70,7 +71,44 @@ class _CBR:
         self.gw = self.pp.spec.grad_buffer(dev)
 
 
-class UNetEngine:
+class _EngineBase:
+    """Shared by both engines: loss scaling of the fp16 gradient path and arena finalisation."""
+    bucket_hook = None
+
+    def _init_scaling(self, device):
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=device)
+        self._pending_unscale, self._S = False, 1.0
+
+    def loss_scale(self) -> float:
+        """Power of two S with |S * dlogit| <= 2^-4 for a mean-reduced BCE (|dlogit| <= 1/numel): keeps the
+        fp16 gradient tensors in the normal range with 2^20 headroom before overflow."""
+        numel = self.ws["logits"].numel()
+        return float(2.0 ** (math.ceil(math.log2(numel)) - 4))
+
+    def _scaled_dlogit(self, dlogit, prescaled):
+        self._S = self.loss_scale()
+        dlogit = dlogit.contiguous().float()
+        if not prescaled:
+            dlogit = torch.mul(dlogit, self._S, out=self.ws["dlogit_s"])
+        self._pending_unscale = True
+        return dlogit
+
+    def finalize_grads(self):
+        """Unscale the flat gradient arena (and flag non-finite values); called once all buckets are reduced."""
+        if self._pending_unscale:
+            ops.scale_check(self.arena, 1.0 / self._S, self.overflow)
+            self._pending_unscale = False
+
+    def loss_and_dlogit(self, logits, mask, grad_scale=1.0, thr=0.5):
+        """Fused BCE forward + gradient.  The returned dlogit carries grad_scale * loss_scale():
+        pass it to backward(..., prescaled=True)."""
+        ws = self.ws
+        ops.bce_fwd_bwd(logits, mask.contiguous().float(), ws["loss_sum"], ws["dlogit"], ws["counts"],
+                        grad_scale=grad_scale * self.loss_scale(), thr=thr)
+        return ws["loss_sum"], ws["dlogit"], ws["counts"]
+
+
+class UNetEngine(_EngineBase):
     CH = [64, 128, 256, 512, 1024]
 
     def __init__(self, params: Dict[str, torch.Tensor], first: str, in_ch: int, device):
@@ -110,6 +148,7 @@ class UNetEngine:
         self.training_fwd = False
         self._build_grad_arena()
         self.bucket_hook = None      # callable(flat_slice) invoked as each gradient bucket is complete
+        self._init_scaling(device)
 
     def _build_grad_arena(self):
         """One flat fp32 buffer for every parameter gradient, ordered by backward completion
@@ -178,9 +217,11 @@ class UNetEngine:
                 ws["act_b4"] = _e((n, H[4], W[4], C[4]), d)
             ws[f"R{l}"] = _e((n, H[l], W[l], C[l]), d, GRAD)      # grad wrt a raw conv output
             ws[f"A{l}"] = _e((n, H[l], W[l], C[l]), d, GRAD)      # grad wrt an activation
-        ws["cvt"] = _e((n * h * w * max(self.cin_pad, 2 * C[0]),), d, GRAD)
+        if GRAD != ACT:
+            ws["cvt"] = _e((n * h * w * max(self.cin_pad, 2 * C[0]),), d, GRAD)
         ws["logits"] = _e((n, 1, h, w), d, torch.float32)
         ws["dlogit"] = _e((n, 1, h, w), d, torch.float32)
+        ws["dlogit_s"] = _e((n, 1, h, w), d, torch.float32)
         ws["loss_sum"] = _z((), d, torch.float64)
         ws["counts"] = _z((4,), d, torch.int64)
         self.ws, self.ws_key = ws, key
@@ -202,8 +243,10 @@ class UNetEngine:
         return self.grads[name]
 
     def _as_grad_dtype(self, x):
-        """bf16 copy of an fp16 activation view in the shared scratch buffer: wgrad needs x and dy in
-        one format (tcgen05 kind::f16 faults on mixed f16 x bf16 operands)."""
+        """wgrad needs x and dy in one format (tcgen05 kind::f16 faults on mixed f16 x bf16 operands).
+        With fp16 gradients this is the identity; a bf16-gradient build converts through a scratch buffer."""
+        if x.dtype == GRAD:
+            return x
         n, h, w, c = x.shape
         buf = self.ws["cvt"][: n * h * w * c].view(n, h, w, c)
         return ops.convert16(x, buf)
@@ -269,12 +312,15 @@ class UNetEngine:
         return ws["logits"]
 
     # ------------------------------------------------------------------ backward
-    def backward(self, dlogit: torch.Tensor) -> Dict[str, torch.Tensor]:
+    def backward(self, dlogit: torch.Tensor, prescaled: bool = False) -> Dict[str, torch.Tensor]:
+        """dlogit: gradient of the loss wrt the logits.  prescaled=True: it already carries loss_scale()
+        (the fused BCE kernel applies it for free).  Gradients come out of the kernels scaled; they are
+        unscaled in the arena by finalize_grads() (called here, or by the all-reduce hook owner)."""
         if not self.training_fwd:
             raise NotImplementedError("backward through eval-mode BatchNorm is not on the hot path")
         ws, P, C = self.ws, self.P, self.CH
         n, H, W = ws["n"], ws["H"], ws["W"]
-        dlogit = dlogit.contiguous().float()
+        dlogit = self._scaled_dlogit(dlogit, prescaled)
         cnt = [n * H[l] * W[l] for l in range(5)]
         head_w = P["outc.conv.weight"].detach().reshape(-1)
         ops.sum_f32(dlogit, self._grad("outc.conv.bias", P["outc.conv.bias"]))
@@ -319,14 +365,9 @@ class UNetEngine:
         if self.first == "cube":               # module registered twice (models.py:169-171): same tensor
             self.grads["inc.0.weight"] = self.grads["first_conv.weight"]
             self.grads["inc.0.bias"] = self.grads["first_conv.bias"]
+        if self.bucket_hook is None:
+            self.finalize_grads()
         return self.grads
-
-    # ------------------------------------------------------------------ fused training step
-    def loss_and_dlogit(self, logits, mask, grad_scale=1.0, thr=0.5):
-        ws = self.ws
-        ops.bce_fwd_bwd(logits, mask.contiguous().float(), ws["loss_sum"], ws["dlogit"], ws["counts"],
-                        grad_scale=grad_scale, thr=thr)
-        return ws["loss_sum"], ws["dlogit"], ws["counts"]
 
 
 def _first_spec(true_cin: int, cin_pad: int) -> WeightSpec:
@@ -337,7 +378,7 @@ def _first_spec(true_cin: int, cin_pad: int) -> WeightSpec:
 
 
 # =======================================================================================
-class SpectralEngine:
+class SpectralEngine(_EngineBase):
     """SpectralUNET: nine Linear->BatchNorm1d->ReLU blocks on an (R*C) x D pixel matrix per image
     (models.py:105-115,132-144), concat by writing into halves of shared buffers."""
     BLOCKS = ["tail", "down1", "down2", "down3", "down4", "up1", "up2", "up3", "up4"]
@@ -357,8 +398,17 @@ class SpectralEngine:
             self.L[nm] = L
         self.ws = None
         self.ws_key = None
-        self.grads: Dict[str, torch.Tensor] = {}
         self.training_fwd = False
+        self._init_scaling(device)
+        names = [k for nm in self.BLOCKS for k in (nm + ".0.weight", nm + ".0.bias", nm + ".1.weight", nm + ".1.bias")]
+        names += ["outc.weight", "outc.bias"]
+        offs, total = {}, 0
+        for k in names:
+            offs[k] = total
+            total += params[k].numel()
+        self.arena = torch.zeros(total, dtype=torch.float32, device=d)
+        self.grads = {k: self.arena[offs[k]: offs[k] + params[k].numel()].view(params[k].shape) for k in names}
+        self.bucket_bounds = [(0, total)]
         self.w_outc = _z((2 * self.Fp,), d, torch.float32)
         self.dw_outc = _z((2 * self.Fp,), d, torch.float32)
 
@@ -379,7 +429,9 @@ class SpectralEngine:
         for k in (2, 3, 4):
             ws[f"gcat{k}"] = _z((1, 1, m, 2 * Fp), d, GRAD)
         ws["R"] = _z((1, 1, m, Fp), d, GRAD)
-        ws["cvt"] = _z((1, 1, m, max(2 * Fp, self.Dp)), d, GRAD)
+        if GRAD != ACT:
+            ws["cvt"] = _z((1, 1, m, max(2 * Fp, self.Dp)), d, GRAD)
+        ws["dlogit_s"] = _e((n, 1, r, c), d, torch.float32)
         ws["g4"] = _z((1, 1, m, Fp), d, GRAD)
         ws["gt"] = _z((1, 1, m, Fp), d, GRAD)
         ws["logits"] = _e((n, 1, r, c), d, torch.float32)
@@ -406,12 +458,8 @@ class SpectralEngine:
         self.w_outc[:F].copy_(wo[:F])
         self.w_outc[Fp:Fp + F].copy_(wo[F:])
 
-    def _grad(self, name, like):
-        g = self.grads.get(name)
-        if g is None or g.shape != like.shape:
-            g = torch.zeros_like(like, dtype=torch.float32)
-            self.grads[name] = g
-        return g
+    def _grad(self, name, like=None):
+        return self.grads[name]
 
     def _io(self, im, nm):
         """(input view, logical in-features, output activation view) of block nm."""
@@ -453,11 +501,11 @@ class SpectralEngine:
             ops.head_fwd(im["cat1"], None, None, self.w_outc, P["outc.bias"], ws["logits"][i])
         return ws["logits"]
 
-    def backward(self, dlogit: torch.Tensor) -> Dict[str, torch.Tensor]:
+    def backward(self, dlogit: torch.Tensor, prescaled: bool = False) -> Dict[str, torch.Tensor]:
         if not self.training_fwd:
             raise NotImplementedError("backward through eval-mode BatchNorm is not on the hot path")
         ws, P, F, Fp, m = self.ws, self.P, self.F, self.Fp, self.ws["m"]
-        dlogit = dlogit.contiguous().float()
+        dlogit = self._scaled_dlogit(dlogit, prescaled)
         ops.sum_f32(dlogit, self._grad("outc.bias", P["outc.bias"]))
         for L in self.L.values():
             L.gw.zero_()
@@ -497,7 +545,7 @@ class SpectralEngine:
                     g_g.copy_(dg); g_b.copy_(db)
                 else:
                     g_g.add_(dg); g_b.add_(db)
-                xg = ops.convert16(src, ws["cvt"][..., :src.shape[-1]])
+                xg = src if src.dtype == GRAD else ops.convert16(src, ws["cvt"][..., :src.shape[-1]])
                 ops.igemm_wgrad(xg, R, 0, F, L.gw, x_c=(self.D if nm == "tail" else None), dy_c=F)
                 if dx_dst is not None:
                     if L.pp.spec.split:
@@ -513,10 +561,8 @@ class SpectralEngine:
         go = self._grad("outc.weight", P["outc.weight"]).view(-1)
         go[:F].copy_(dwo_acc[:F])
         go[F:].copy_(dwo_acc[Fp:Fp + F])
+        if self.bucket_hook is not None:
+            self.bucket_hook(self.arena)
+        else:
+            self.finalize_grads()
         return self.grads
-
-    def loss_and_dlogit(self, logits, mask, grad_scale=1.0, thr=0.5):
-        ws = self.ws
-        ops.bce_fwd_bwd(logits, mask.contiguous().float(), ws["loss_sum"], ws["dlogit"], ws["counts"],
-                        grad_scale=grad_scale, thr=thr)
-        return ws["loss_sum"], ws["dlogit"], ws["counts"]

@@ -17,7 +17,7 @@ from ._lib import View, check
 bf16 = torch.bfloat16
 f16 = torch.float16
 ACT = f16        # forward activations and forward weight operands (11-bit mantissa; BN keeps them O(1))
-GRAD = bf16      # gradients and dgrad weight operands (fp32 exponent range, no loss scaling)
+GRAD = f16       # gradients and dgrad weight operands; the loss gradient is scaled by a power of two (engine)
 _DT = {bf16: 0, f16: 1}
 
 
@@ -248,6 +248,12 @@ def bce_fwd_bwd(logits, target, loss_sum, dlogit=None, counts=None, grad_scale=1
 def colsum(x, out, beta=0.0, c=None):
     xv = view(x, c)
     check(_lib.lib().hpri_colsum(_vp(xv), _ptr(out), beta, _stream()), "hpri_colsum")
+
+
+@_timed
+def scale_check(x, scale, flag):
+    """x *= scale (fp32, in place); flag (int32 tensor) |= 1 on a non-finite result."""
+    check(_lib.lib().hpri_scale_check(_ptr(x), x.numel(), float(scale), _ptr(flag), _stream()), "hpri_scale_check")
 
 
 @_timed

@@ -16,8 +16,9 @@ import torch.distributed as dist
 
 
 class BucketedAllReduce:
-    def __init__(self, group=None):
+    def __init__(self, group=None, engine=None):
         self.group = group
+        self.engine = engine
         self.pending: List = []
         self.bytes = 0
 
@@ -37,12 +38,14 @@ class BucketedAllReduce:
         for w in self.pending:
             w.wait()
         self.pending.clear()
+        if self.engine is not None and hasattr(self.engine, "finalize_grads"):
+            self.engine.finalize_grads()       # unscale the loss-scaled gradients once every bucket is reduced
 
     def grad_scale(self) -> float:
         return 1.0 / self.world_size
 
 
 def attach(engine, group=None) -> BucketedAllReduce:
-    r = BucketedAllReduce(group)
+    r = BucketedAllReduce(group, engine)
     engine.bucket_hook = r.hook
     return r

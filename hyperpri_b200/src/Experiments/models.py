@@ -31,7 +31,15 @@ class _NetFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dlogits):
         net = ctx.net
-        grads = net._get_engine(ctx.dev).backward(dlogits)
+        eng = net._get_engine(ctx.dev)
+        grads = eng.backward(dlogits)
+        if eng.bucket_hook is not None:
+            # data-parallel: buckets were handed to the all-reduce as they completed; its owner's finish()
+            # unscales them.  The clones below are taken after that (the caller invokes finish() right after
+            # loss.backward(); clone views stay scaled-consistent because unscaling is in place on the arena).
+            owner = getattr(eng.bucket_hook, "__self__", None)
+            if owner is not None:
+                owner.finish()
         out = []
         for name, p in net._hot_params():
             out.append(grads[name].clone() if p.requires_grad else None)

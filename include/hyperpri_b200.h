@@ -28,8 +28,8 @@ extern "C" {
 #define HPRI_F16 1
 
 /* NHWC view of a 16-bit tensor (dtype HPRI_BF16 or HPRI_F16): element strides; c = logical channels
- * visible through the view.  Forward activations are fp16 (BatchNorm keeps them O(1); 11-bit mantissa),
- * gradients bf16 (fp32 exponent range, no loss scaling); all accumulation is fp32. */
+ * visible through the view.  Activations and gradients are fp16 (BatchNorm keeps activations O(1); the loss
+ * gradient is scaled by a power of two so gradients stay in fp16's normal range); all accumulation is fp32. */
 typedef struct {
   void* ptr;
   int n, h, w, c;
@@ -121,6 +121,8 @@ int hpri_bce_fwd_bwd(const float* logits, const float* target, long long numel, 
 /* out[c] (+)= sum over pixels of the view (ConvT bias grad; Linear bias grad). */
 int hpri_colsum(const hpri_view_t* x, float* out, float beta, void* stream);
 int hpri_sum_f32(const float* x, long long numel, float* out, void* stream);
+/* x *= scale in place; *flag |= 1 if any result is non-finite (unscaling of loss-scaled fp16 gradients). */
+int hpri_scale_check(float* x, long long numel, float scale, int* flag, void* stream);
 
 #ifdef __cplusplus
 }

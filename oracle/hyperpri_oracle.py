@@ -180,20 +180,24 @@ class _RoundBF16(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
+        if _GRAD_SCALE:        # loss-scaled fp16 gradient storage
+            return (g * _GRAD_SCALE).to(torch.float16).to(torch.float32) / _GRAD_SCALE
         return g.to(torch.bfloat16).to(torch.float32)
 
 
 _QUANT = False
+_GRAD_SCALE = 0.0
 
 
-def emulate_bf16_storage(on: bool):
+def emulate_bf16_storage(on: bool, grad_scale: float = 0.0):
     """With emulation on, the oracle rounds weights, conv/linear outputs and activations to fp16 and
     their gradients to bf16 at exactly the points where hyperpri_b200 stores them (fp32 accumulation
     and fp32 BatchNorm statistics are kept).  The fp32 oracle (off, default) is the parity
     reference; the emulated oracle separates implementation errors from storage-precision
     effects in tests."""
-    global _QUANT
+    global _QUANT, _GRAD_SCALE
     _QUANT = bool(on)
+    _GRAD_SCALE = float(grad_scale)   # 0: gradients rounded to bf16; S: gradients stored as fp16(S * g)
 
 
 def q(x):

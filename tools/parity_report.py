@@ -30,7 +30,8 @@ def build(model, bands, feats):
 
 
 def run(model, n, h, w, bands, feats=1650, seed=0, training=True, verbose=True, emulate=False):
-    O.emulate_bf16_storage(emulate)
+    import math
+    O.emulate_bf16_storage(emulate, grad_scale=2.0 ** (math.ceil(math.log2(n * h * w)) - 4))
     net, schema = build(model, bands, feats)
     sd = O.synth_state_dict(schema, seed)
     net.load_state_dict(sd)
