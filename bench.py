@@ -234,8 +234,11 @@ def main():
     torch.cuda.synchronize()
     rec, ops.PROFILE = ops.PROFILE, None
     per = {}
-    for name, a, b in rec:
+    per_launch = []
+    for name, a, b, desc in rec:
         t = a.elapsed_time(b)
+        if name in ops.TENSOR_KERNELS or t > 0.05:
+            per_launch.append((name, desc, t))
         d = per.setdefault(name, [0.0, 0])
         d[0] += t / prof_steps
         d[1] += 1
@@ -253,7 +256,9 @@ def main():
         with open(args.breakdown, "w") as f:
             json.dump({"ms_per_step_sum_of_kernels": all_ms, "ms_per_step_wall": ms_step,
                        "kernels": {k: {"ms_per_step": v[0], "launches_per_step": v[1] / prof_steps} for k, v in
-                                   sorted(per.items(), key=lambda kv: -kv[1][0])}}, f, indent=1)
+                                   sorted(per.items(), key=lambda kv: -kv[1][0])},
+                       "launches_last_step": [{"kernel": k, "args": d_, "ms": t} for k, d_, t in
+                                              per_launch[len(per_launch) // prof_steps:]]}, f, indent=1)
 
     # ---------------- end to end through the public API with host inputs
     e2e = None

@@ -93,6 +93,49 @@ __global__ void unpack_grads_k(const float* __restrict__ packed, float* __restri
   }
 }
 
+
+// ------------------------------------------------------------------ conv3x3 weight pack / grad unpack (tiled)
+// W[co][ci][9] fp32  ->  fwd operand [co][t*kcf + ci]  and (optional) dgrad operand [ci][(8-t)*kcd + co], both
+// 16-bit.  32 x 32 (co, ci) tile through shared memory: coalesced 288-float row reads, coalesced writes of
+// both layouts, the parameter is read once.  Padding columns are never written (buffers are zero-initialised).
+__global__ void __launch_bounds__(256)
+pack_conv3x3_k(const float* __restrict__ w, int Cout, int Cin, uint16_t* __restrict__ df, int kcf, int fdt,
+               uint16_t* __restrict__ dd, int kcd, int ddt) {
+  __shared__ float tile[32][289];
+  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+  const int nci = min(32, Cin - ci0), nco = min(32, Cout - co0);
+  for (int i = threadIdx.x; i < 32 * 288; i += 256) {
+    const int col = i / 288, rem = i - col * 288;
+    float v = 0.f;
+    if (col < nco && rem < nci * 9) v = __ldg(w + ((long long)(co0 + col) * Cin + ci0) * 9 + rem);
+    tile[col][rem] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * 288; i += 256) {
+    const int l = i & 31, t = (i >> 5) % 9, o = i / 288;
+    if (df != nullptr && o < nco && l < nci)          // lanes over ci
+      df[(long long)(co0 + o) * (9 * kcf) + t * kcf + ci0 + l] = cvt16(tile[o][l * 9 + t], fdt);
+    if (dd != nullptr && o < nci && l < nco)          // lanes over co (o indexes ci here)
+      dd[(long long)(ci0 + o) * (9 * kcd) + (8 - t) * kcd + co0 + l] = cvt16(tile[l][o * 9 + t], ddt);
+  }
+}
+// packed fp32 gradient [co][t*kcf + ci] -> W-layout [co][ci][9]
+__global__ void __launch_bounds__(256)
+unpack_conv3x3_k(const float* __restrict__ g, int Cout, int Cin, int kcf, float* __restrict__ dst) {
+  __shared__ float tile[32][289];
+  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+  const int nci = min(32, Cin - ci0), nco = min(32, Cout - co0);
+  for (int i = threadIdx.x; i < 32 * 288; i += 256) {
+    const int l = i & 31, t = (i >> 5) % 9, o = i / 288;
+    if (o < nco && l < nci) tile[o][l * 9 + t] = __ldg(g + (long long)(co0 + o) * (9 * kcf) + t * kcf + ci0 + l);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * 288; i += 256) {
+    const int col = i / 288, rem = i - col * 288;
+    if (col < nco && rem < nci * 9) dst[((long long)(co0 + col) * Cin + ci0) * 9 + rem] = tile[col][rem];
+  }
+}
+
 // ------------------------------------------------------------------ ingest
 // One block = 64 consecutive pixels of one output row, all bands.  Band-major coalesced fp32 reads
 // (128 B per warp request), transposed through shared memory, pixel-major coalesced bf16 writes.
@@ -735,6 +778,23 @@ extern "C" int hpri_unpack_grads(const float* packed, float* dst, int G, int R, 
   const long long total = (long long)G * R * T * kc64;
   unpack_grads_k<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(packed, dst, G, R, T, C, kc64, sg, sr, st,
                                                                         sc, flip, beta);
+  return last_err();
+}
+
+
+extern "C" int hpri_pack_conv3x3(const float* w, int cout, int cin, void* dst_fwd, int fwd_dtype, void* dst_dgrad,
+                                 int dgrad_dtype, void* stream) {
+  if (!w || cout <= 0 || cin <= 0 || (!dst_fwd && !dst_dgrad)) return HPRI_ERR_ARG;
+  dim3 grid((cin + 31) / 32, (cout + 31) / 32);
+  pack_conv3x3_k<<<grid, 256, 0, (cudaStream_t)stream>>>(w, cout, cin, (uint16_t*)dst_fwd, (cin + 63) / 64 * 64,
+                                                        fwd_dtype, (uint16_t*)dst_dgrad, (cout + 63) / 64 * 64,
+                                                        dgrad_dtype);
+  return last_err();
+}
+extern "C" int hpri_unpack_conv3x3(const float* packed, int cout, int cin, float* dst, void* stream) {
+  if (!packed || !dst || cout <= 0 || cin <= 0) return HPRI_ERR_ARG;
+  dim3 grid((cin + 31) / 32, (cout + 31) / 32);
+  unpack_conv3x3_k<<<grid, 256, 0, (cudaStream_t)stream>>>(packed, cout, cin, (cin + 63) / 64 * 64, dst);
   return last_err();
 }
 

@@ -51,9 +51,17 @@ class _PackedParam:
         key = (w.data_ptr(), w._version)
         if key != self.key:
             wc = w.detach().reshape(-1)
-            self.fwd = self.spec.pack_fwd(wc, out=self.fwd)
-            if self.need_dgrad:
-                self.dgr = self.spec.pack_dgrad(wc, out=self.dgr)
+            if self.spec.kind == "conv3x3":
+                if self.fwd is None:           # zero once: the tiled pack never writes padding
+                    f, g = self.spec.fwd, self.spec.dgr
+                    self.fwd = torch.zeros((f["R"], 9 * kpad(f["Cc"])), dtype=ACT, device=w.device)
+                    if self.need_dgrad:
+                        self.dgr = torch.zeros((g["R"], 9 * kpad(g["Cc"])), dtype=GRAD, device=w.device)
+                self.spec.pack_both(wc, self.fwd, self.dgr)
+            else:
+                self.fwd = self.spec.pack_fwd(wc, out=self.fwd)
+                if self.need_dgrad:
+                    self.dgr = self.spec.pack_dgrad(wc, out=self.dgr)
             self.key = key
 
 

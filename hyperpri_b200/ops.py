@@ -35,7 +35,9 @@ def _timed(fn):
         e0.record()
         r = fn(*a, **k)
         e1.record()
-        PROFILE.append((name, e0, e1))
+        desc = " ".join("x".join(map(str, t.shape)) for t in list(a) + list(k.values())
+                        if isinstance(t, torch.Tensor) and t.dim() >= 2)
+        PROFILE.append((name, e0, e1, desc))
         return r
 
     wrapper.__name__, wrapper.__doc__ = name, fn.__doc__
@@ -92,6 +94,20 @@ def unpack(packed: torch.Tensor, dst: torch.Tensor, G, R, T, Cc, sg, sr, st, sc,
     return dst
 
 
+@_timed
+def pack_conv3x3(w, cout, cin, fwd=None, dgrad=None):
+    """W[co][ci][3][3] fp32 -> fwd operand [co, 9*kpad(ci)] and/or dgrad operand [ci, 9*kpad(co)] (zero-initialised
+    once by the caller; only valid entries are written)."""
+    check(_lib.lib().hpri_pack_conv3x3(_ptr(w), cout, cin, _ptr(fwd), _DT[fwd.dtype] if fwd is not None else 0,
+                                       _ptr(dgrad), _DT[dgrad.dtype] if dgrad is not None else 0, _stream()),
+          "hpri_pack_conv3x3")
+
+
+@_timed
+def unpack_conv3x3(packed, cout, cin, dst):
+    check(_lib.lib().hpri_unpack_conv3x3(_ptr(packed), cout, cin, _ptr(dst), _stream()), "hpri_unpack_conv3x3")
+
+
 class WeightSpec:
     """Index maps between a torch-layout fp32 parameter and the packed GEMM operands."""
 
@@ -117,6 +133,11 @@ class WeightSpec:
         else:
             raise ValueError(kind)
 
+    def pack_both(self, w, fwd, dgrad):
+        """Refresh both operands of a conv3x3 in one tiled pass (buffers from zeros_like allocations)."""
+        assert self.kind == "conv3x3"
+        pack_conv3x3(w, self.cout, self.cin, fwd, dgrad)
+
     def pack_fwd(self, w, out=None, dtype=None):
         return pack(w, out=out, dtype=dtype or ACT, **self.fwd)
 
@@ -128,6 +149,8 @@ class WeightSpec:
         return torch.zeros((f["G"] * f["R"], f["T"] * kpad(f["Cc"])), dtype=torch.float32, device=device)
 
     def unpack_grad(self, packed, dst, beta=0.0):
+        if self.kind == "conv3x3" and beta == 0.0:
+            return unpack_conv3x3(packed, self.cout, self.cin, dst)
         f = dict(self.fwd)
         return unpack(packed, dst, beta=beta, **f)
 

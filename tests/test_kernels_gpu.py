@@ -206,6 +206,22 @@ def test_linear(m, fin, fout, split):
         assert relerr(dx[0, 0, :, :fin].float(), dy[0, 0, :, :fout].float() @ wq) < 6e-3
 
 
+@pytest.mark.parametrize("cout,cin", [(64, 238), (128, 64), (96, 40), (1024, 512)])
+def test_tiled_conv3x3_pack_matches_generic(cout, cin):
+    w = rnd(cout, cin, 3, 3, seed=50)
+    spec = ops.WeightSpec("conv3x3", cout, cin)
+    f = torch.zeros((cout, 9 * ops.kpad(cin)), dtype=FH, device=DEV)
+    d = torch.zeros((cin, 9 * ops.kpad(cout)), dtype=FH, device=DEV)
+    spec.pack_both(w.reshape(-1), f, d)
+    assert torch.equal(f, spec.pack_fwd(w.reshape(-1), dtype=FH))
+    assert torch.equal(d, spec.pack_dgrad(w.reshape(-1), dtype=FH))
+    g = torch.randn((cout, 9 * ops.kpad(cin)), device=DEV)
+    a, b = torch.empty_like(w), torch.empty_like(w)
+    ops.unpack_conv3x3(g, cout, cin, a)
+    ops.unpack(g, b.view(-1), **spec.fwd)
+    assert torch.equal(a, b)
+
+
 def test_mixed_format_rejected_and_convert():
     x = nhwc(rnd(1, 64, 8, 8, seed=40), dt=FH)
     dy = nhwc(rnd(1, 64, 8, 8, seed=41), dt=BF)
