@@ -32,7 +32,7 @@ SIGNATURES = {
     "hpri_convT2x2_dgrad": [_VP, _p, _i, _i, _i, _VP, _i, _p],
     "hpri_igemm_wgrad": [_VP, _VP, _i, _i, _p, _i, _i, _i, _p],
     "hpri_pack_weights": [_p, _p, _i, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _p],
-    "hpri_unpack_grads": [_p, _p, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _f, _p],
+    "hpri_unpack_grads": [_p, _p, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _f, _i, _p],
     "hpri_pack_conv3x3": [_p, _i, _i, _p, _i, _p, _i, _p],
     "hpri_unpack_conv3x3": [_p, _i, _i, _p, _p],
     "hpri_hsi_ingest": [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _i, _i, _p],

@@ -59,6 +59,17 @@ __device__ __forceinline__ void ld8p(const float* p, int c0, int C, float (&f)[8
   for (int j = 0; j < 8; ++j) f[j] = (p != nullptr && c0 + j < C) ? __ldg(p + c0 + j) : 0.f;
 }
 
+// 8 consecutive floats, two 16-byte loads when the run is complete and aligned
+__device__ __forceinline__ void ld8v(const float* p, int c0, int C, float (&f)[8]) {
+  if (p != nullptr && c0 + 8 <= C && ((reinterpret_cast<uintptr_t>(p + c0) & 15) == 0)) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p + c0));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p + c0 + 4));
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+    ld8p(p, c0, C, f);
+  }
+}
+
 // ------------------------------------------------------------------ weight pack / unpack
 __global__ void pack_weights_k(const float* __restrict__ src, uint16_t* __restrict__ dst, int dt, int G, int R, int T,
                                int C, int kc64, long long sg, long long sr, long long st, long long sc, int flip) {
@@ -75,9 +86,9 @@ __global__ void pack_weights_k(const float* __restrict__ src, uint16_t* __restri
     dst[i] = cvt16(v, dt);
   }
 }
-__global__ void unpack_grads_k(const float* __restrict__ packed, float* __restrict__ dst, int G, int R, int T, int C,
+__global__ void unpack_grads_k(float* __restrict__ packed, float* __restrict__ dst, int G, int R, int T, int C,
                                int kc64, long long sg, long long sr, long long st, long long sc, int flip,
-                               float beta) {
+                               float beta, int zero_src) {
   const long long total = (long long)G * R * T * kc64;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % kc64);
@@ -89,6 +100,7 @@ __global__ void unpack_grads_k(const float* __restrict__ packed, float* __restri
     const int tm = flip ? T - 1 - t : t;
     float* d = dst + g * sg + r * sr + tm * st + c * sc;
     const float v = packed[i];
+    if (zero_src) packed[i] = 0.f;
     *d = beta == 0.f ? v : beta * (*d) + v;
   }
 }
@@ -104,11 +116,22 @@ pack_conv3x3_k(const float* __restrict__ w, int Cout, int Cin, uint16_t* __restr
   __shared__ float tile[32][289];
   const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
   const int nci = min(32, Cin - ci0), nco = min(32, Cout - co0);
-  for (int i = threadIdx.x; i < 32 * 288; i += 256) {
-    const int col = i / 288, rem = i - col * 288;
-    float v = 0.f;
-    if (col < nco && rem < nci * 9) v = __ldg(w + ((long long)(co0 + col) * Cin + ci0) * 9 + rem);
-    tile[col][rem] = v;
+  // 36 elements per thread, loaded 12 at a time so that 12 global loads are in flight per thread
+#pragma unroll 1
+  for (int b = 0; b < 3; ++b) {
+    float v[12];
+#pragma unroll
+    for (int u = 0; u < 12; ++u) {
+      const int i = threadIdx.x + (b * 12 + u) * 256;
+      const int col = i / 288, rem = i - col * 288;
+      v[u] = (col < nco && rem < nci * 9) ? __ldg(w + ((long long)(co0 + col) * Cin + ci0) * 9 + rem) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 12; ++u) {
+      const int i = threadIdx.x + (b * 12 + u) * 256;
+      const int col = i / 288, rem = i - col * 288;
+      tile[col][rem] = v[u];
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 32 * 288; i += 256) {
@@ -119,15 +142,29 @@ pack_conv3x3_k(const float* __restrict__ w, int Cout, int Cin, uint16_t* __restr
       dd[(long long)(ci0 + o) * (9 * kcd) + (8 - t) * kcd + co0 + l] = cvt16(tile[l][o * 9 + t], ddt);
   }
 }
-// packed fp32 gradient [co][t*kcf + ci] -> W-layout [co][ci][9]
+// packed fp32 gradient [co][t*kcf + ci] -> W-layout [co][ci][9]; the packed buffer is reset to zero behind the
+// read so that the next split-K weight-gradient launch can accumulate into it without a separate memset.
 __global__ void __launch_bounds__(256)
-unpack_conv3x3_k(const float* __restrict__ g, int Cout, int Cin, int kcf, float* __restrict__ dst) {
+unpack_conv3x3_k(float* __restrict__ g, int Cout, int Cin, int kcf, float* __restrict__ dst) {
   __shared__ float tile[32][289];
   const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
   const int nci = min(32, Cin - ci0), nco = min(32, Cout - co0);
-  for (int i = threadIdx.x; i < 32 * 288; i += 256) {
-    const int l = i & 31, t = (i >> 5) % 9, o = i / 288;
-    if (o < nco && l < nci) tile[o][l * 9 + t] = __ldg(g + (long long)(co0 + o) * (9 * kcf) + t * kcf + ci0 + l);
+#pragma unroll 1
+  for (int b = 0; b < 3; ++b) {
+    float v[12];
+#pragma unroll
+    for (int u = 0; u < 12; ++u) {
+      const int i = threadIdx.x + (b * 12 + u) * 256;
+      const int l = i & 31, t = (i >> 5) % 9, o = i / 288;
+      v[u] = (o < nco && l < nci) ? __ldcs(g + (long long)(co0 + o) * (9 * kcf) + t * kcf + ci0 + l) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 12; ++u) {              // all twelve loads are issued before the first dependent store
+      const int i = threadIdx.x + (b * 12 + u) * 256;
+      const int l = i & 31, t = (i >> 5) % 9, o = i / 288;
+      tile[o][l * 9 + t] = v[u];
+      if (o < nco && l < nci) g[(long long)(co0 + o) * (9 * kcf) + t * kcf + ci0 + l] = 0.f;
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 32 * 288; i += 256) {
@@ -151,21 +188,36 @@ hsi_ingest_k(const float* __restrict__ src, int bands_total, int H, int W, int l
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sy = i0 + (flip_h ? h - 1 - y : y);
   const float* img = src + ((long long)n * bands_total + lo) * H * W + (long long)sy * W;
-  for (int b = warp; b < c_pad; b += 8) {
-    float v0 = 0.f, v1 = 0.f;
-    if (b < nb) {
-      const float* row = img + (long long)b * H * W;
-      const int xa = x0 + lane, xb = x0 + lane + 32;
-      if (xa < w) v0 = __ldg(row + j0 + (flip_w ? w - 1 - xa : xa));
-      if (xb < w) v1 = __ldg(row + j0 + (flip_w ? w - 1 - xb : xb));
-      v0 *= scale; v1 *= scale;
-      if (bmean != nullptr) {
-        const float m = __ldg(bmean + b), is = 1.f / __ldg(bstd + b);
-        v0 = (v0 - m) * is; v1 = (v1 - m) * is;
+  // bands are walked five at a time per warp: ten independent 128-byte row segments in flight per thread
+  const int xa = x0 + lane, xb = x0 + lane + 32;
+  const int ca = j0 + (flip_w ? w - 1 - xa : xa), cb = j0 + (flip_w ? w - 1 - xb : xb);
+  const bool ina = xa < w, inb = xb < w;
+  constexpr int UB = 5;
+  for (int b0 = warp; b0 < c_pad; b0 += 8 * UB) {
+    float v0[UB], v1[UB];
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const int b = b0 + 8 * u;
+      v0[u] = 0.f; v1[u] = 0.f;
+      if (b < nb) {
+        const float* row = img + (long long)b * H * W;
+        if (ina) v0[u] = __ldg(row + ca);
+        if (inb) v1[u] = __ldg(row + cb);
       }
     }
-    tile[(lane) * (2 * wstride) + b] = cvt16(v0, dt);
-    tile[(lane + 32) * (2 * wstride) + b] = cvt16(v1, dt);
+#pragma unroll
+    for (int u = 0; u < UB; ++u) {
+      const int b = b0 + 8 * u;
+      if (b >= c_pad) break;
+      float a0 = v0[u] * scale, a1 = v1[u] * scale;
+      if (bmean != nullptr && b < nb) {
+        const float m = __ldg(bmean + b), is = 1.f / __ldg(bstd + b);
+        a0 = (a0 - m) * is; a1 = (a1 - m) * is;
+      }
+      if (b >= nb) { a0 = 0.f; a1 = 0.f; }
+      tile[(lane) * (2 * wstride) + b] = cvt16(a0, dt);
+      tile[(lane + 32) * (2 * wstride) + b] = cvt16(a1, dt);
+    }
   }
   __syncthreads();
   const int wpp = c_pad / 2;                    // words per pixel
@@ -348,28 +400,28 @@ __device__ __forceinline__ void window_word(const BwdIn& a, const Win& w, int j,
   }
 }
 
+// Window kernels: grid.x tiles the (window column, channel group) plane, grid.y chunks of `rows` window rows,
+// grid.z the image.  A thread keeps one (wx, cg) and walks its rows: no per-element index arithmetic, per-channel
+// constants loaded once.
 // pass 1: sums[c] = {sum dz, sum dz*xhat, sum dlogit*act}
-__global__ void __launch_bounds__(256, 2) bn_bwd_reduce_k(BwdIn a, double* sums, int slots, int CG) {
-  extern __shared__ float red[];                 // [slots][CG*8][3]
-  const int cg = threadIdx.x % CG, slot = threadIdx.x / CG;
-  const bool active = slot < slots;
+__global__ void __launch_bounds__(256, 2) bn_bwd_reduce_k(BwdIn a, double* sums, int CG, int rows) {
+  __shared__ float red[256][25];                 // odd stride: conflict-free row writes
   const int wh = (a.x.h + 1) >> 1, ww = (a.x.w + 1) >> 1;
-  const long long nwin = (long long)a.x.n * wh * ww;
-  if (active) {
-    const int c0 = cg * 8;
+  const int g = blockIdx.x * 256 + threadIdx.x;
+  const int cg = g % CG, wx = g / CG;
+  const int n = blockIdx.z;
+  const int c0 = cg * 8;
+  float s1[8], s2[8], s3[8];                     // s2 holds sum dz*x; centred and scaled at the end
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; s3[k] = 0.f; }
+  if (wx < ww) {
     float sc[8], sh[8], hwv[8];
     ld8p(a.scale, c0, a.x.c, sc);
     ld8p(a.shift, c0, a.x.c, sh);
     ld8p(a.head_w, c0, a.x.c, hwv);
     const float* hw = a.dlogit != nullptr ? hwv : nullptr;
-    float s1[8], s2[8], s3[8];                   // s2 holds sum dz*x; centred and scaled at the end
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; s3[k] = 0.f; }
-    for (long long wi = (long long)blockIdx.x * slots + slot; wi < nwin; wi += (long long)gridDim.x * slots) {
-      long long j = wi;
-      const int wx = (int)(j % ww); j /= ww;
-      const int wy = (int)(j % wh);
-      const int n = (int)(j / wh);
+    const int wy1 = min(wh, (int)(blockIdx.y + 1) * rows);
+    for (int wy = blockIdx.y * rows; wy < wy1; ++wy) {
       Win w;
       load_window(a, n, wy, wx, c0, w);
 #pragma unroll
@@ -387,68 +439,64 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_k(BwdIn a, double* sums,
           }
       }
     }
-    float* r = red + ((long long)slot * CG + cg) * 24;
+  }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { r[k * 3] = s1[k]; r[k * 3 + 1] = s2[k]; r[k * 3 + 2] = s3[k]; }
+  for (int k = 0; k < 8; ++k) {
+    red[threadIdx.x][k * 3] = s1[k]; red[threadIdx.x][k * 3 + 1] = s2[k]; red[threadIdx.x][k * 3 + 2] = s3[k];
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < CG * 8; c += blockDim.x) {
-    if (c >= a.x.c) continue;
+  // channel c = (cg, k): partials live in the threads t with (blockIdx.x*256 + t) % CG == cg
+  for (int c = threadIdx.x; c < a.x.c; c += 256) {
+    const int mycg = c >> 3, k = c & 7;
+    const int base = (blockIdx.x * 256) % CG;
     float t1 = 0.f, t2 = 0.f, t3 = 0.f;
-    for (int s = 0; s < slots; ++s) {
-      const float* r = red + ((long long)s * CG * 8 + c) * 3;
-      t1 += r[0]; t2 += r[1]; t3 += r[2];
+    for (int t = (mycg - base + CG) % CG; t < 256; t += CG) {
+      t1 += red[t][k * 3]; t2 += red[t][k * 3 + 1]; t3 += red[t][k * 3 + 2];
     }
     const float mu = __ldg(a.mean + c), is = __ldg(a.invstd + c);
     atomicAdd(sums + 3 * c, (double)t1);
     atomicAdd(sums + 3 * c + 1, (double)is * ((double)t2 - (double)mu * (double)t1));
-    atomicAdd(sums + 3 * c + 2, (double)t3);
+    if (a.dlogit != nullptr) atomicAdd(sums + 3 * c + 2, (double)t3);
   }
 }
 
 // pass 2: dx = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)) = ca*dz + cb*x + cc
 __global__ void __launch_bounds__(256, 2)
 bn_bwd_apply_k(BwdIn a, const float* __restrict__ gamma, const double* __restrict__ sums, long long count, V dx,
-               float* dgamma, float* dbeta, float* dhead_w) {
-  const int CG = (a.x.c + 7) >> 3;
-  const int wh = (a.x.h + 1) >> 1, ww = (a.x.w + 1) >> 1;
-  const long long total = (long long)a.x.n * wh * ww * CG;
-  if (blockIdx.x == 0) {
+               float* dgamma, float* dbeta, float* dhead_w, int CG, int rows) {
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
     for (int c = threadIdx.x; c < a.x.c; c += blockDim.x) {
       if (dbeta) dbeta[c] = (float)sums[3 * c];
       if (dgamma) dgamma[c] = (float)sums[3 * c + 1];
       if (dhead_w) dhead_w[c] = (float)sums[3 * c + 2];
     }
   }
+  const int wh = (a.x.h + 1) >> 1, ww = (a.x.w + 1) >> 1;
+  const int g = blockIdx.x * 256 + threadIdx.x;
+  const int cg = g % CG, wx = g / CG;
+  if (wx >= ww) return;
+  const int n = blockIdx.z;
+  const int c0 = cg * 8;
   const float rc = 1.f / (float)count;
-  int cg_cached = -1;
   float sc[8], sh[8], hwv[8], ca[8], cb[8], cc[8];
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % CG);
-    long long j = i / CG;
-    const int wx = (int)(j % ww); j /= ww;
-    const int wy = (int)(j % wh);
-    const int n = (int)(j / wh);
-    const int c0 = cg * 8;
-    if (cg != cg_cached) {                       // constant per thread when the grid stride is a multiple of CG
-      cg_cached = cg;
-      ld8p(a.scale, c0, a.x.c, sc);
-      ld8p(a.shift, c0, a.x.c, sh);
-      ld8p(a.head_w, c0, a.x.c, hwv);
+  ld8p(a.scale, c0, a.x.c, sc);
+  ld8p(a.shift, c0, a.x.c, sh);
+  ld8p(a.head_w, c0, a.x.c, hwv);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int c = c0 + k;
-        float g = 0.f, mu = 0.f, is = 0.f, m1 = 0.f, m2 = 0.f;
-        if (c < a.x.c) {
-          g = __ldg(gamma + c); mu = __ldg(a.mean + c); is = __ldg(a.invstd + c);
-          m1 = (float)sums[3 * c] * rc; m2 = (float)sums[3 * c + 1] * rc;
-        }
-        ca[k] = g * is;
-        cb[k] = -g * is * is * m2;
-        cc[k] = -g * is * m1 - cb[k] * mu;
-      }
+  for (int k = 0; k < 8; ++k) {
+    const int c = c0 + k;
+    float gm = 0.f, mu = 0.f, is = 0.f, m1 = 0.f, m2 = 0.f;
+    if (c < a.x.c) {
+      gm = __ldg(gamma + c); mu = __ldg(a.mean + c); is = __ldg(a.invstd + c);
+      m1 = (float)sums[3 * c] * rc; m2 = (float)sums[3 * c + 1] * rc;
     }
-    const float* hw = a.dlogit != nullptr ? hwv : nullptr;
+    ca[k] = gm * is;
+    cb[k] = -gm * is * is * m2;
+    cc[k] = -gm * is * m1 - cb[k] * mu;
+  }
+  const float* hw = a.dlogit != nullptr ? hwv : nullptr;
+  const int wy1 = min(wh, (int)(blockIdx.y + 1) * rows);
+  for (int wy = blockIdx.y * rows; wy < wy1; ++wy) {
     Win w;
     load_window(a, n, wy, wx, c0, w);
     uint32_t o[4][4];
@@ -660,6 +708,77 @@ head_fwd_k(V x, const float* __restrict__ scale, const float* __restrict__ shift
   }
 }
 
+// Pixel-dense fast path: offset = pixel * pix_stride, no index arithmetic; when one pass of the LPP lanes covers all
+// channels the per-channel constants stay in registers and four pixels are in flight per thread.
+__global__ void __launch_bounds__(256)
+head_fwd_dense_k(const uint16_t* __restrict__ x, long long sp, int dt, int C, long long npix,
+                 const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ w,
+                 const float* __restrict__ b, float* __restrict__ logits, int LPP) {
+  const int CG = (C + 7) >> 3;
+  const int ppb = 256 / LPP;
+  const int sub = threadIdx.x % LPP, slot = threadIdx.x / LPP;
+  const float bias = b ? __ldg(b) : 0.f;
+  const long long stride = (long long)gridDim.x * ppb;
+  const long long first = (long long)blockIdx.x * ppb + slot;
+  if (CG <= LPP) {
+    float sc[8], sh[8], wv[8];
+    const bool mine = sub < CG;
+    ld8v(w, sub * 8, mine ? C : 0, wv);
+    ld8v(scale, sub * 8, mine ? C : 0, sc);
+    ld8v(shift, sub * 8, mine ? C : 0, sh);
+    const bool bn = scale != nullptr;
+    // block-uniform trip count (full-mask shuffles below); pixel validity is checked per access
+    for (long long base = (long long)blockIdx.x * ppb; base < npix; base += 4 * stride) {
+      const long long p0 = base + slot;
+      uint4 xr[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long pp = p0 + u * stride;
+        xr[u] = make_uint4(0, 0, 0, 0);
+        if (mine && pp < npix) xr[u] = __ldg(reinterpret_cast<const uint4*>(x + pp * sp + sub * 8));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long pp = p0 + u * stride;
+        float f[8], acc = 0.f;
+        unpack8(xr[u], f, dt);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float v = bn ? fmaxf(fmaf(f[k], sc[k], sh[k]), 0.f) : f[k];
+          acc = fmaf(v, wv[k], acc);
+        }
+        for (int o = LPP >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (pp < npix && sub == 0) logits[pp] = acc + bias;
+      }
+    }
+  } else {
+    const long long iters = (npix + stride - 1) / stride;
+    for (long long it = 0; it < iters; ++it) {
+      const long long pp = first + it * stride;
+      float acc = 0.f;
+      if (pp < npix) {
+        const uint16_t* px = x + pp * sp;
+        for (int cg = sub; cg < CG; cg += LPP) {
+          float f[8], wv[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(px + cg * 8)), f, dt);
+          ld8v(w, cg * 8, C, wv);
+          if (scale != nullptr) {
+            float sc[8], sh[8];
+            ld8v(scale, cg * 8, C, sc);
+            ld8v(shift, cg * 8, C, sh);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = fmaxf(fmaf(f[k], sc[k], sh[k]), 0.f);
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc = fmaf(f[k], wv[k], acc);
+        }
+      }
+      for (int o = LPP >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (pp < npix && sub == 0) logits[pp] = acc + bias;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ sigmoid-BCE forward + gradient + counters
 __global__ void __launch_bounds__(256)
 bce_k(const float* __restrict__ x, const float* __restrict__ t, long long n, float gscale, float thr,
@@ -694,20 +813,31 @@ bce_k(const float* __restrict__ x, const float* __restrict__ t, long long n, flo
 __global__ void __launch_bounds__(256) colsum_k(V x, float* out, int slots, int CG) {
   extern __shared__ float red[];                 // [slots][CG*8]
   const int cg = threadIdx.x % CG, slot = threadIdx.x / CG;
-  const long long npix = (long long)x.n * x.h * x.w;
   if (slot < slots) {
     float s[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) s[k] = 0.f;
-    for (long long pi = (long long)blockIdx.x * slots + slot; pi < npix; pi += (long long)gridDim.x * slots) {
-      long long j = pi;
-      const int xx = (int)(j % x.w); j /= x.w;
-      const int yy = (int)(j % x.h);
-      const int n = (int)(j / x.h);
-      float f[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(at(x, n, yy, xx, cg * 8))), f, x.dt);
+    // one image row per block iteration, four pixels in flight per thread
+    const int rows = x.n * x.h;
+    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+      const int n = r / x.h, yy = r - n * x.h;
+      const uint16_t* base = at(x, n, yy, 0, cg * 8);
+      for (int x0 = slot; x0 < x.w; x0 += 4 * slots) {
+        uint4 v[4];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) s[k] += f[k];
+        for (int u = 0; u < 4; ++u) {
+          const int xx = x0 + u * slots;
+          v[u] = make_uint4(0, 0, 0, 0);
+          if (xx < x.w) v[u] = __ldg(reinterpret_cast<const uint4*>(base + xx * x.sp));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float f[8];
+          unpack8(v[u], f, x.dt);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) s[k] += f[k];
+        }
+      }
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) red[((long long)slot * CG + cg) * 8 + k] = s[k];
@@ -749,6 +879,16 @@ __global__ void sum_f32_k(const float* __restrict__ x, long long n, float* out) 
   if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
 }
 
+// launch shape of the 2x2-window kernels: enough row chunks for >= 8 blocks per SM, at most 8 window rows a chunk
+static inline dim3 win_grid(const hpri_view_t* x, int CG, int* rows) {
+  const int wh = (x->h + 1) / 2, ww = (x->w + 1) / 2;
+  const int bx = (ww * CG + 255) / 256;
+  int r = 8;
+  while (r > 1 && (long long)bx * ((wh + r - 1) / r) * x->n < 148 * 8) r >>= 1;
+  *rows = r;
+  return dim3((unsigned)bx, (unsigned)((wh + r - 1) / r), (unsigned)x->n);
+}
+
 static inline int grid_for(long long work_items, int per_block, int cap = 148 * 16) {
   long long g = (work_items + per_block - 1) / per_block;
   if (g < 1) g = 1;
@@ -772,12 +912,13 @@ extern "C" int hpri_pack_weights(const float* src, void* dst, int dst_dtype, int
                                                                        sg, sr, st, sc, flip);
   return last_err();
 }
-extern "C" int hpri_unpack_grads(const float* packed, float* dst, int G, int R, int T, int C, int kc64, long long sg,
-                                 long long sr, long long st, long long sc, int flip, float beta, void* stream) {
+extern "C" int hpri_unpack_grads(float* packed, float* dst, int G, int R, int T, int C, int kc64, long long sg,
+                                 long long sr, long long st, long long sc, int flip, float beta, int zero_src,
+                                 void* stream) {
   if (!packed || !dst || G <= 0 || R <= 0 || T <= 0 || C <= 0 || kc64 < C) return HPRI_ERR_ARG;
   const long long total = (long long)G * R * T * kc64;
   unpack_grads_k<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(packed, dst, G, R, T, C, kc64, sg, sr, st,
-                                                                        sc, flip, beta);
+                                                                        sc, flip, beta, zero_src);
   return last_err();
 }
 
@@ -791,7 +932,7 @@ extern "C" int hpri_pack_conv3x3(const float* w, int cout, int cin, void* dst_fw
                                                         dgrad_dtype);
   return last_err();
 }
-extern "C" int hpri_unpack_conv3x3(const float* packed, int cout, int cin, float* dst, void* stream) {
+extern "C" int hpri_unpack_conv3x3(float* packed, int cout, int cin, float* dst, void* stream) {
   if (!packed || !dst || cout <= 0 || cin <= 0) return HPRI_ERR_ARG;
   dim3 grid((cin + 31) / 32, (cout + 31) / 32);
   unpack_conv3x3_k<<<grid, 256, 0, (cudaStream_t)stream>>>(packed, cout, cin, (cin + 63) / 64 * 64, dst);
@@ -901,8 +1042,9 @@ extern "C" int hpri_bn_relu_bwd_reduce(const hpri_view_t* x, const float* scale,
     return last_err();
   }
   BwdIn a{mk(x), mk(dy), mk(dpool), scale, shift, save_mean, save_invstd, head_w, dlogit};
-  const long long nwin = (long long)x->n * ((x->h + 1) / 2) * ((x->w + 1) / 2);
-  bn_bwd_reduce_k<<<grid_for(nwin, slots * 4, 148 * 8), 256, smem, (cudaStream_t)stream>>>(a, sums, slots, CG);
+  int rows = 0;
+  const dim3 grid = win_grid(x, CG, &rows);
+  bn_bwd_reduce_k<<<grid, 256, 0, (cudaStream_t)stream>>>(a, sums, CG, rows);
   return last_err();
 }
 
@@ -934,9 +1076,11 @@ extern "C" int hpri_bn_relu_bwd_apply(const hpri_view_t* x, const float* scale, 
     return last_err();
   }
   BwdIn a{mk(x), mk(dy), mk(dpool), scale, shift, save_mean, save_invstd, head_w, dlogit};
-  const long long total = (long long)x->n * ((x->h + 1) / 2) * ((x->w + 1) / 2) * ((x->c + 7) / 8);
-  bn_bwd_apply_k<<<grid_for(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(a, gamma, sums, count, mk(dx),
-                                                                                 dgamma, dbeta, dhead_w);
+  const int CGw = (x->c + 7) / 8;
+  int rows = 0;
+  const dim3 grid = win_grid(x, CGw, &rows);
+  bn_bwd_apply_k<<<grid, 256, 0, (cudaStream_t)stream>>>(a, gamma, sums, count, mk(dx), dgamma, dbeta, dhead_w, CGw,
+                                                        rows);
   return last_err();
 }
 
@@ -949,6 +1093,11 @@ extern "C" int hpri_head_fwd(const hpri_view_t* x, const float* scale, const flo
   int LPP = 1;
   while (LPP < CG && LPP < 32) LPP <<= 1;
   const long long npix = (long long)x->n * x->h * x->w;
+  if (pixel_dense(x)) {
+    head_fwd_dense_k<<<grid_for(npix, (256 / LPP) * 8, 148 * 8), 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const uint16_t*>(x->ptr), x->pix_stride, x->dtype, x->c, npix, scale, shift, w, b, logits, LPP);
+    return last_err();
+  }
   head_fwd_k<<<grid_for(npix, 256 / LPP, 148 * 32), 256, 0, (cudaStream_t)stream>>>(mk(x), scale, shift, w, b, logits,
                                                                                   LPP);
   return last_err();
@@ -974,8 +1123,7 @@ extern "C" int hpri_colsum(const hpri_view_t* x, float* out, float beta, void* s
   if (CG > 256) return HPRI_ERR_ARG;
   const int slots = 256 / CG;
   scale_f32_k<<<(x->c + 255) / 256, 256, 0, (cudaStream_t)stream>>>(out, x->c, beta);
-  const long long npix = (long long)x->n * x->h * x->w;
-  colsum_k<<<grid_for(npix, slots * 16, 148 * 4), 256, (size_t)slots * CG * 32, (cudaStream_t)stream>>>(mk(x), out,
+  colsum_k<<<grid_for((long long)x->n * x->h, 1, 148 * 8), 256, (size_t)slots * CG * 32, (cudaStream_t)stream>>>(mk(x), out,
                                                                                                        slots, CG);
   return last_err(2);
 }

@@ -1002,11 +1002,17 @@ extern "C" int hpri_igemm_wgrad(const hpri_view_t* x, const hpri_view_t* dy, int
   const long long T = (long long)a.N * a.tiles_h * a.tiles_w;
   const int m_tiles = (a.total_chunks + 1) / 2, n_tiles = (n_total + bn - 1) / bn;
   if (splits <= 0) {
-    // persistent CTAs: aim at ~2 tiles per SM, at least 4 pixel tiles (k-blocks) per tile
-    long long want = (2LL * 148 + m_tiles * n_tiles / 2) / (m_tiles * n_tiles);
-    long long cap = T / 4 > 0 ? T / 4 : 1;
-    splits = (int)(want < cap ? want : cap);
-    if (splits < 1) splits = 1;
+    // persistent CTAs walk (m, n, split) tiles in waves of #SMs: pick the split count that minimises
+    // waves x (k-blocks per tile + epilogue cost), i.e. never leave a wave with a single straggler tile.
+    const long long mn = (long long)m_tiles * n_tiles;
+    const double epi = 2.0;                             // tile epilogue (mostly overlapped) in k-block units
+    double best = 1e30;
+    splits = 1;
+    for (long long s = 1; s <= T && s * mn <= 4LL * 148 + mn; ++s) {
+      const long long waves = (s * mn + 147) / 148;
+      const double cost = (double)waves * ((double)((T + s - 1) / s) + epi);
+      if (cost < best) { best = cost; splits = (int)s; }
+    }
   }
   if (splits > T) splits = (int)T;
   a.splits = splits;

@@ -86,6 +86,21 @@ class _EngineBase:
     def _init_scaling(self, device):
         self.overflow = torch.zeros(1, dtype=torch.int32, device=device)
         self._pending_unscale, self._S = False, 1.0
+        self._gw_dirty = False
+
+    def _gw_buffers(self):
+        raise NotImplementedError
+
+    def _begin_backward(self):
+        """The packed weight-gradient buffers are accumulated into by split-K launches and reset to zero by the
+        unpack kernels, so they are clean at the start of every backward unless the previous one was interrupted."""
+        if self._gw_dirty:
+            for g in self._gw_buffers():
+                g.zero_()
+        self._gw_dirty = True
+
+    def _end_backward(self):
+        self._gw_dirty = False
 
     def loss_scale(self) -> float:
         """Power of two S with |S * dlogit| <= 2^-4 for a mean-reduced BCE (|dlogit| <= 1/numel): keeps the
@@ -266,7 +281,6 @@ class UNetEngine(_EngineBase):
         ops.bn_relu_bwd(raw, L.scale, L.shift, L.smean, L.sinv, P[L.bn + ".weight"], R, L.sums, count, dy=dy,
                         dpool=dpool, head_w=head_w, dlogit=dlogit, dgamma=self._grad(L.bn + ".weight", L.scale[:L.cout]),
                         dbeta=self._grad(L.bn + ".bias", L.scale[:L.cout]), dhead_w=dhead_w)
-        L.gw.zero_()
         ops.igemm_wgrad(self._as_grad_dtype(x_in), R, 1, L.cout, L.gw)
         wname = L.conv + ".weight"
         L.pp.spec.unpack_grad(L.gw, self._grad(wname, self.P[wname]).view(-1))
@@ -328,6 +342,7 @@ class UNetEngine(_EngineBase):
             raise NotImplementedError("backward through eval-mode BatchNorm is not on the hot path")
         ws, P, C = self.ws, self.P, self.CH
         n, H, W = ws["n"], ws["H"], ws["W"]
+        self._begin_backward()
         dlogit = self._scaled_dlogit(dlogit, prescaled)
         cnt = [n * H[l] * W[l] for l in range(5)]
         head_w = P["outc.conv.weight"].detach().reshape(-1)
@@ -351,7 +366,6 @@ class UNetEngine(_EngineBase):
             x_up = ws[f"dec_act_b{l + 1}"] if l < 3 else ws["act_b4"]
             ops.convT_dgrad(dy_up, up.dgr, C[l + 1], ws[f"A{l + 1}"])
             gw = self.up_gw[l]
-            gw.zero_()
             ops.igemm_wgrad(self._as_grad_dtype(x_up), dy_up, 2, 4 * C[l], gw)
             wn = f"up{i}.up.weight"
             up.spec.unpack_grad(gw, self._grad(wn, P[wn]).view(-1))
@@ -373,9 +387,13 @@ class UNetEngine(_EngineBase):
         if self.first == "cube":               # module registered twice (models.py:169-171): same tensor
             self.grads["inc.0.weight"] = self.grads["first_conv.weight"]
             self.grads["inc.0.bias"] = self.grads["first_conv.bias"]
+        self._end_backward()
         if self.bucket_hook is None:
             self.finalize_grads()
         return self.grads
+
+    def _gw_buffers(self):
+        return [L.gw for grp in list(self.enc) + list(self.dec.values()) for L in grp] + list(self.up_gw.values())
 
 
 def _first_spec(true_cin: int, cin_pad: int) -> WeightSpec:
@@ -419,6 +437,9 @@ class SpectralEngine(_EngineBase):
         self.bucket_bounds = [(0, total)]
         self.w_outc = _z((2 * self.Fp,), d, torch.float32)
         self.dw_outc = _z((2 * self.Fp,), d, torch.float32)
+
+    def _gw_buffers(self):
+        return [L.gw for L in self.L.values()]
 
     def _workspace(self, n, r, c):
         key = (n, r, c)
@@ -513,10 +534,9 @@ class SpectralEngine(_EngineBase):
         if not self.training_fwd:
             raise NotImplementedError("backward through eval-mode BatchNorm is not on the hot path")
         ws, P, F, Fp, m = self.ws, self.P, self.F, self.Fp, self.ws["m"]
+        self._begin_backward()
         dlogit = self._scaled_dlogit(dlogit, prescaled)
         ops.sum_f32(dlogit, self._grad("outc.bias", P["outc.bias"]))
-        for L in self.L.values():
-            L.gw.zero_()
         first_img = True
         dwo_acc = torch.zeros_like(self.dw_outc)
         for i in range(ws["n"]):
@@ -569,6 +589,7 @@ class SpectralEngine(_EngineBase):
         go = self._grad("outc.weight", P["outc.weight"]).view(-1)
         go[:F].copy_(dwo_acc[:F])
         go[F:].copy_(dwo_acc[Fp:Fp + F])
+        self._end_backward()
         if self.bucket_hook is not None:
             self.bucket_hook(self.arena)
         else:

@@ -87,10 +87,13 @@ def pack(src: torch.Tensor, G, R, T, Cc, sg, sr, st, sc, flip=False, out: Option
 
 
 @_timed
-def unpack(packed: torch.Tensor, dst: torch.Tensor, G, R, T, Cc, sg, sr, st, sc, flip=False, beta=0.0):
+def unpack(packed: torch.Tensor, dst: torch.Tensor, G, R, T, Cc, sg, sr, st, sc, flip=False, beta=0.0,
+           zero_src=False):
+    """Packed fp32 gradient -> torch layout.  zero_src: reset `packed` to zero behind the read (the split-K
+    weight-gradient kernel accumulates into it, so this replaces a memset before the next step)."""
     assert packed.dtype == torch.float32 and dst.dtype == torch.float32 and dst.is_contiguous()
     check(_lib.lib().hpri_unpack_grads(_ptr(packed), _ptr(dst), G, R, T, Cc, kpad(Cc), sg, sr, st, sc, int(flip),
-                                       float(beta), _stream()), "hpri_unpack_grads")
+                                       float(beta), int(zero_src), _stream()), "hpri_unpack_grads")
     return dst
 
 
@@ -105,6 +108,7 @@ def pack_conv3x3(w, cout, cin, fwd=None, dgrad=None):
 
 @_timed
 def unpack_conv3x3(packed, cout, cin, dst):
+    """Packed conv3x3 gradient -> W layout; always zeroes `packed` behind the read."""
     check(_lib.lib().hpri_unpack_conv3x3(_ptr(packed), cout, cin, _ptr(dst), _stream()), "hpri_unpack_conv3x3")
 
 
@@ -149,10 +153,11 @@ class WeightSpec:
         return torch.zeros((f["G"] * f["R"], f["T"] * kpad(f["Cc"])), dtype=torch.float32, device=device)
 
     def unpack_grad(self, packed, dst, beta=0.0):
+        """Unpack AND reset `packed` to zero (ready for the next accumulation)."""
         if self.kind == "conv3x3" and beta == 0.0:
             return unpack_conv3x3(packed, self.cout, self.cin, dst)
         f = dict(self.fwd)
-        return unpack(packed, dst, beta=beta, **f)
+        return unpack(packed, dst, beta=beta, zero_src=True, **f)
 
 
 # ----------------------------------------------------------------------------- contractions

@@ -72,15 +72,17 @@ int hpri_igemm_wgrad(const hpri_view_t* x, const hpri_view_t* dy, int mode, int 
  * pack: fp32 torch-layout parameter -> 16-bit operand (dst_dtype).  unpack: fp32 packed gradient -> fp32 torch layout. */
 int hpri_pack_weights(const float* src, void* dst, int dst_dtype, int G, int R, int T, int C, int kc64, long long sg,
                       long long sr, long long st, long long sc, int flip, void* stream);
-int hpri_unpack_grads(const float* packed, float* dst, int G, int R, int T, int C, int kc64, long long sg,
-                      long long sr, long long st, long long sc, int flip, float beta, void* stream);
+int hpri_unpack_grads(float* packed, float* dst, int G, int R, int T, int C, int kc64, long long sg,
+                      long long sr, long long st, long long sc, int flip, float beta, int zero_src, void* stream);
 
 /* Tiled conv3x3 specialisations: W[co][ci][3][3] -> forward operand and (optional) transposed, tap-flipped dgrad
  * operand in one pass (destination buffers must be zero-initialised once: padding is never written); and the
- * packed fp32 weight gradient back to W layout. */
+ * packed fp32 weight gradient back to W layout.  unpack (zero_src != 0 for the generic one, always for the conv3x3
+ * one) resets the packed buffer to zero behind the read, so the next split-K hpri_igemm_wgrad launch can accumulate
+ * into it without a memset. */
 int hpri_pack_conv3x3(const float* w, int cout, int cin, void* dst_fwd, int fwd_dtype, void* dst_dgrad,
                       int dgrad_dtype, void* stream);
-int hpri_unpack_conv3x3(const float* packed, int cout, int cin, float* dst, void* stream);
+int hpri_unpack_conv3x3(float* packed, int cout, int cin, float* dst, void* stream);
 
 /* ---- ingest (src/dataset.py:266-270, 284-289) -------------------------------------------
  * src: fp32 [n][bands_total][H][W]; keeps bands [lo,hi), crops the (i0,j0,h,w) window, optional

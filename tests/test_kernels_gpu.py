@@ -217,9 +217,11 @@ def test_tiled_conv3x3_pack_matches_generic(cout, cin):
     assert torch.equal(d, spec.pack_dgrad(w.reshape(-1), dtype=FH))
     g = torch.randn((cout, 9 * ops.kpad(cin)), device=DEV)
     a, b = torch.empty_like(w), torch.empty_like(w)
+    g2 = g.clone()
     ops.unpack_conv3x3(g, cout, cin, a)
-    ops.unpack(g, b.view(-1), **spec.fwd)
+    ops.unpack(g2, b.view(-1), **spec.fwd)
     assert torch.equal(a, b)
+    assert not g.view(cout, 9, -1)[:, :, :cin].any()      # the packed buffer is reset behind the read
 
 
 def test_mixed_format_rejected_and_convert():
