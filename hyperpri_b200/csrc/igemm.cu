@@ -2,20 +2,26 @@
 //
 // One warp-specialised kernel template covers every dense contraction on the hot path:
 //   MODE_FWD   D[pixels, n] = sum_k A[pixels (+tap shift), k] * B[n, k]        (K-major operands)
-//              3x3 pad-1 conv fprop and dgrad (model_parts.py:22,25), 1x1 / Linear (models.py:108),
-//              ConvTranspose2d k2 s2 fprop (pixel-shuffle epilogue) and dgrad (2x2 stride-2 gather)
-//              (model_parts.py:63-64).
+//              1x1 / Linear (models.py:108), ConvTranspose2d k2 s2 fprop (pixel-shuffle store) and
+//              dgrad (2x2 stride-2 gather) (model_parts.py:63-64), 3x3 convs whose tiles do not fit the
+//              halo kernel below.
 //   MODE_WGRAD dW[n, (tap, c)] += sum_pixels X[pixel (+tap shift), c] * dY[pixel, n]   (MN-major operands)
+// and conv3x3_halo_kernel runs the 3x3 pad-1 conv fprop and dgrad (model_parts.py:22,25).
 //
-// A operand tiles arrive by TMA straight from NHWC bf16 activations: a 4-D box {64 ch, tw, th, 1}
+// A operand tiles arrive by TMA straight from NHWC 16-bit activations: a 4-D box {64 ch, tw, th, 1}
 // at (c0, w0+dw, h0+dh, n).  Out-of-bounds box elements are zero-filled by the TMA unit, which
 // implements the conv's zero padding, ragged channel counts (238 -> 240 -> 4 chunks of 64) and
-// partial tiles at the image border for free.  Rows of 64 bf16 = 128 B land in the 128B-swizzled
+// partial tiles at the image border for free.  Rows of 64 elements = 128 B land in the 128B-swizzled
 // layout tcgen05.mma consumes.  Accumulators live in TMEM (128 lanes x BLOCK_N fp32 columns).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one
-// elected thread), warps 2..5 = epilogue (TMEM -> registers -> swizzled smem staging ->
-// coalesced 16 B global stores, per-channel BatchNorm statistics from the staged tile).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one
+// elected thread), warps 2..9 = two epilogue groups of four warps.  A group turns a 128-row x 64-column
+// accumulator chunk into 16-bit values in a 128B-swizzled staging tile (TMEM -> registers -> smem),
+// one elected thread hands the tile to the TMA unit (cp.async.bulk.tensor store: clipping at the image
+// border and at n_store comes from the tensor map), and meanwhile all its threads add the tile's
+// per-channel BatchNorm statistics to register accumulators kept across tiles.  Two groups work on
+// different chunks at the same time: one warp per scheduler cannot hide the TMEM / smem latencies
+// (measured: a 4-warp epilogue took 3.8 k cycles per chunk and bounded every Cout=64 layer).
 #include "ptx.cuh"
 #include "hyperpri_b200.h"
 
@@ -29,26 +35,91 @@ enum { TAP_NONE = 0, TAP_3X3 = 1, TAP_UP2 = 2 };
 
 struct IgemmArgs {
   int N, H, W;            // pixel grid walked by M (fwd) or K (wgrad)
-  int th, tw, tiles_h, tiles_w;
+  int th, tw, ltw, tiles_h, tiles_w;      // tw is a power of two, ltw = log2(tw)
   int taps, tap_mode, kchunks;
   int n_total;            // logical extent of the GEMM N dimension
   // ---- fwd epilogue
-  uint16_t* out;          // 16-bit elements, format out_dt
-  long long out_pix_stride, out_row_stride, out_img_stride;   // elements
-  int out_h, out_w;       // store bounds (for up2: the upsampled extent)
-  int n_store;            // channels to store per pixel (multiple of 8)
-  int up2, cout;          // ConvT pixel shuffle: n = (a*2+b)*cout + co
+  int up2, cout;          // ConvT pixel shuffle: n = (a*2+b)*cout + co, one output map per (a, b)
   const float* bias;      // [n_total] (up2: [cout]) or null
-  int accum;              // 1: y += result (read-modify-write of the bf16 destination)
+  int accum;              // 1: y += result (TMA reduce-add in the destination format)
   double* stats;          // [n_total][2] sum / sumsq or null
   // ---- wgrad epilogue
   float* dw;              // [n_total][dw_ld] fp32, accumulated with red.add
   int dw_ld, splits, total_chunks;
   int a_dt, b_dt, out_dt; // element formats (DT_BF16 / DT_F16) of the A, B operands and the fwd output
+  // ---- halo kernel pipeline shape (runtime: depends on the tile aspect)
+  int stages, a_bytes;
 };
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;
+constexpr int kEpiThreads = 256;
 constexpr int kMaxStatCh = 2048;   // per-CTA BatchNorm partial sums live in smem for the whole kernel
+constexpr int kStageTile = 16384;  // 128 rows x 64 columns x 2 B epilogue staging, one per epilogue group
+
+template <int DT>
+__device__ __forceinline__ uint32_t pack2_t(float lo, float hi) {
+  if (DT == DT_F16) {
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  return pack_bf16x2(lo, hi);
+}
+// 32 fp32 accumulator columns -> 16-bit pairs -> swizzled staging row (zeros for invalid rows)
+template <int DT>
+__device__ __forceinline__ void stage_row32(uint8_t* stage, int row, int hh, const uint32_t (&v)[32], bool valid) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (valid) {
+      o.x = pack2_t<DT>(__uint_as_float(v[8 * i + 0]), __uint_as_float(v[8 * i + 1]));
+      o.y = pack2_t<DT>(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]));
+      o.z = pack2_t<DT>(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]));
+      o.w = pack2_t<DT>(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]));
+    }
+    const int chunk = hh * 4 + i;
+    *reinterpret_cast<uint4*>(stage + row * 128 + (((chunk ^ row) & 7) << 4)) = o;
+  }
+}
+// Column sums of 32 staged rows (rows r0..r0+31, r0 a multiple of 8): lane l owns channels 2l, 2l+1.
+template <int DT>
+__device__ __forceinline__ void stats_rows32(const uint8_t* stage, int r0, int lane, float2& s, float2& q) {
+  const int chunk = lane >> 2;
+  const uint8_t* base = stage + r0 * 128 + (lane & 3) * 4;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const uint32_t u = *reinterpret_cast<const uint32_t*>(base + i * 128 + (((chunk ^ i) & 7) << 4));
+    acc_sum_sq2(s, q, unpack2_t<DT>(u));
+  }
+}
+// TMEM (this warp's 32 lanes, 64 columns at taddr) -> (+bias) -> 16-bit -> staging rows
+__device__ __forceinline__ void chunk_to_stage(uint32_t taddr, uint8_t* stage, int row, bool valid, int out_dt,
+                                               const float* bias64) {
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    uint32_t v[32];
+    tmem_ld32(taddr + hh * 32, v);
+    tmem_ld_wait();
+    if (bias64 != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(bias64 + hh * 32) + j);
+        v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + b.x);
+        v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + b.y);
+        v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + b.z);
+        v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + b.w);
+      }
+    }
+    if (out_dt == DT_F16) stage_row32<DT_F16>(stage, row, hh, v, valid);
+    else stage_row32<DT_BF16>(stage, row, hh, v, valid);
+  }
+}
+// per-thread statistics (channels ch, ch+1) -> the CTA's smem partial sums
+__device__ __forceinline__ void flush_stats(float* ssum, float* ssq, int ch, int n_total, float2& s, float2& q) {
+  if (ch < n_total && (s.x != 0.f || q.x != 0.f)) { atomicAdd(&ssum[ch], s.x); atomicAdd(&ssq[ch], q.x); }
+  if (ch + 1 < n_total && (s.y != 0.f || q.y != 0.f)) { atomicAdd(&ssum[ch + 1], s.y); atomicAdd(&ssq[ch + 1], q.y); }
+  s = make_float2(0.f, 0.f);
+  q = make_float2(0.f, 0.f);
+}
 
 // fwd: k-block = 64 channels of one tap: A 128 pixels x 128 B, B BLOCK_N rows x 128 B.
 // wgrad: k-block = 128 pixels: A 2 channel chunks x 128 pixel rows x 128 B, B BLOCK_N/64 chunks likewise.
@@ -59,12 +130,11 @@ struct SmemLayout {
   static constexpr int B_BYTES = MODE == MODE_FWD ? BLOCK_N * 128 : (BLOCK_N / 64) * KPIX * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
-  static constexpr int STAGING_OFF = PIPE_BYTES;                 // 128 rows x 64 columns x 2 B epilogue staging
-  static constexpr int STAGING_BYTES = MODE == MODE_FWD ? 128 * 128 : 0;
+  static constexpr int STAGING_OFF = PIPE_BYTES;                 // two epilogue staging tiles (fwd)
+  static constexpr int STAGING_BYTES = MODE == MODE_FWD ? 2 * kStageTile : 0;
   static constexpr int BAR_OFF = STAGING_OFF + STAGING_BYTES;    // full[S], empty[S], tmem_full[2], tmem_empty[2]
   static constexpr int TMEMPTR_OFF = BAR_OFF + (2 * STAGES + 4) * 8;
-  static constexpr int VALID_OFF = TMEMPTR_OFF + 8;              // 128 row-valid bytes
-  static constexpr int SSUM_OFF = VALID_OFF + 128;               // float[kMaxStatCh] sum, float[kMaxStatCh] sumsq
+  static constexpr int SSUM_OFF = TMEMPTR_OFF + 8;               // float[kMaxStatCh] sum, float[kMaxStatCh] sumsq
   static constexpr int TOTAL = SSUM_OFF + (MODE == MODE_FWD ? 2 * kMaxStatCh * 4 : 0);
   static constexpr int ALLOC = TOTAL + 1024;                     // slack for manual 1024 B alignment
   static_assert(ALLOC <= 227 * 1024, "shared memory budget exceeded");
@@ -77,9 +147,13 @@ template <int BLOCK_N, int STAGES, int MODE>
 __global__ void __launch_bounds__(kThreads, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
              const __grid_constant__ CUtensorMap tmB0, const __grid_constant__ CUtensorMap tmB1,
+             const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
+             const __grid_constant__ CUtensorMap tmO2, const __grid_constant__ CUtensorMap tmO3,
              const IgemmArgs p) {
   using L = SmemLayout<BLOCK_N, STAGES, MODE>;
   constexpr int A_BYTES = L::A_BYTES;
+  constexpr int NCH = BLOCK_N / 64;                 // 64-column chunks per accumulator
+  constexpr int GROUPS = MODE == MODE_WGRAD ? 2 : (NCH >= 2 ? 2 : 1);   // epilogue groups with work
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
@@ -87,10 +161,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
   uint64_t* tmem_full = empty_bar + STAGES;      // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::TMEMPTR_OFF);
-  uint8_t* row_valid = smem + L::VALID_OFF;
   float* ssum = reinterpret_cast<float*>(smem + L::SSUM_OFF);
   float* ssq = ssum + kMaxStatCh;
-  uint8_t* stage = smem + L::STAGING_OFF;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -107,14 +179,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA0);
     tma_prefetch_desc(&tmB0);
+    if (MODE == MODE_FWD) tma_prefetch_desc(&tmO0);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&tmem_full[0], 1);
     mbar_init(&tmem_full[1], 1);
-    mbar_init(&tmem_empty[0], 4);     // one arrival per epilogue warp
-    mbar_init(&tmem_empty[1], 4);
+    mbar_init(&tmem_empty[0], 4 * GROUPS);     // one arrival per epilogue warp that reads the accumulator
+    mbar_init(&tmem_empty[1], 4 * GROUPS);
     fence_mbar_init();
     fence_proxy_async_smem();
   }
@@ -255,121 +328,104 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
       }
     }
   } else {
-    // =========================== epilogue (warps 2..5) ===========================
+    // =========================== epilogue (warps 2..9, two groups) ===========================
+    const int g = (warp - 2) >> 2;          // group: takes the 64-column chunks c64 with (c64 & 1) == g
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;
-    const int et = threadIdx.x - 64;        // 0..127
-    const int ew = warp - 2;
+    const int gw = (warp - 2) & 3;          // warp within the group
+    const bool elected = gw == 0 && lane == 0;
+    uint8_t* stage = smem + L::STAGING_OFF + g * kStageTile;
+    const int bar_id = 1 + g;
     uint32_t lt = 0;
-    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      int m_tile, n_tile, kb_begin, kb_end;
-      decode(tile, m_tile, n_tile, kb_begin, kb_end);
-      if (kb_end <= kb_begin) continue;
-      const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
-      ++lt;
-      const int n0 = n_tile * BLOCK_N;
-      const uint32_t tmem_acc = tmem_base + as * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
-      if (MODE == MODE_FWD) {
-        const int img = m_tile / tiles_per_img;
-        const int rr = m_tile - img * tiles_per_img;
-        const int h0 = (rr / p.tiles_w) * p.th;
-        const int w0 = (rr % p.tiles_w) * p.tw;
-        const int hl = row / p.tw, wl = row - hl * p.tw;
-        row_valid[row] = ((h0 + hl < p.H) && (w0 + wl < p.W)) ? 1 : 0;
-        const int co_tile = p.up2 ? (n0 % p.cout) : n0;
-        int a_off = 0, b_off = 0;
-        if (p.up2) { const int ab = n0 / p.cout; a_off = ab >> 1; b_off = ab & 1; }
-        mbar_wait(&tmem_full[as], aph);
-        tc_fence_after();
-#pragma unroll 1
-        for (int c64 = 0; c64 < BLOCK_N / 64; ++c64) {
-          // ---- TMEM -> registers -> 16-bit -> swizzled staging (128 rows x 128 B)
+    if (MODE == MODE_FWD) {
+      constexpr int MYCH = (NCH + 1) / 2;   // chunks of one accumulator this group handles (at most)
+      float2 ssv[MYCH], sqv[MYCH];
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            uint32_t v[32];
-            tmem_ld32(tmem_acc + c64 * 64 + hh * 32, v);
-            tmem_ld_wait();
-            if (p.bias != nullptr) {
+      for (int j = 0; j < MYCH; ++j) { ssv[j] = make_float2(0.f, 0.f); sqv[j] = make_float2(0.f, 0.f); }
+      int acc_n0 = -1;
+      if (g < GROUPS) {
+        for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+          int m_tile, n_tile, kb_begin, kb_end;
+          decode(tile, m_tile, n_tile, kb_begin, kb_end);
+          if (kb_end <= kb_begin) continue;
+          const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
+          ++lt;
+          const int n0 = n_tile * BLOCK_N;
+          if (p.stats != nullptr && n0 != acc_n0) {       // this CTA moved to other output channels: flush
+            if (acc_n0 >= 0) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int ch = co_tile + c64 * 64 + hh * 32 + j;
-                const float b = (ch < (p.up2 ? p.cout : p.n_total)) ? __ldg(p.bias + ch) : 0.f;
-                v[j] = __float_as_uint(__uint_as_float(v[j]) + b);
+              for (int j = 0; j < MYCH; ++j)
+                flush_stats(ssum, ssq, acc_n0 + (2 * j + g) * 64 + 2 * lane, p.n_total, ssv[j], sqv[j]);
+            }
+            acc_n0 = n0;
+          }
+          const uint32_t tmem_acc = tmem_base + as * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
+          const int img = m_tile / tiles_per_img;
+          const int rr = m_tile - img * tiles_per_img;
+          const int h0 = (rr / p.tiles_w) * p.th;
+          const int w0 = (rr % p.tiles_w) * p.tw;
+          const bool valid = (h0 + (row >> p.ltw) < p.H) && (w0 + (row & (p.tw - 1)) < p.W);
+          mbar_wait(&tmem_full[as], aph);
+          tc_fence_after();
+#pragma unroll
+          for (int j = 0; j < MYCH; ++j) {
+            const int c64 = 2 * j + g;
+            if (c64 < NCH) {
+              const int nch = n0 + c64 * 64;            // first GEMM column of this chunk
+              int co = nch, ab = 0;
+              if (p.up2) { ab = nch / p.cout; co = nch - ab * p.cout; }
+              if (elected) bulk_wait_read0();            // the previous store has finished reading the staging tile
+              named_bar_sync(bar_id, 128);
+              chunk_to_stage(tmem_acc + c64 * 64, stage, row, valid, p.out_dt, p.bias != nullptr ? p.bias + co : nullptr);
+              if (c64 + 2 >= NCH) {                      // this warp's last TMEM read of the tile: release the buffer
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[as]);
+              }
+              fence_proxy_async_smem();
+              named_bar_sync(bar_id, 128);
+              if (elected && co < (p.up2 ? p.cout : p.n_total)) {
+                const CUtensorMap* mo = ab == 0 ? &tmO0 : ab == 1 ? &tmO1 : ab == 2 ? &tmO2 : &tmO3;
+                if (p.accum) tma_reduce_add_4d(mo, stage, co, w0, h0, img);
+                else tma_store_4d(mo, stage, co, w0, h0, img);
+                bulk_commit();
+              }
+              if (p.stats != nullptr) {
+                if (p.out_dt == DT_F16) stats_rows32<DT_F16>(stage, gw * 32, lane, ssv[j], sqv[j]);
+                else stats_rows32<DT_BF16>(stage, gw * 32, lane, ssv[j], sqv[j]);
               }
             }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint4 o;
-              o.x = pack2(__uint_as_float(v[8 * i + 0]), __uint_as_float(v[8 * i + 1]), p.out_dt);
-              o.y = pack2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]), p.out_dt);
-              o.z = pack2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]), p.out_dt);
-              o.w = pack2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]), p.out_dt);
-              const int chunk = hh * 4 + i;
-              *reinterpret_cast<uint4*>(stage + row * 128 + (((chunk ^ row) & 7) << 4)) = o;
-            }
           }
-          if (c64 == BLOCK_N / 64 - 1) {           // all TMEM reads of this tile are done: release the buffer
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[as]);
-          }
-          named_bar_sync(1, 128);
-          // ---- per-channel statistics over the valid rows of the staged (rounded) values
-          if (p.stats != nullptr) {
-            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-            const int chunk = lane >> 2, word = lane & 3;
-#pragma unroll 8
-            for (int r = ew * 32; r < ew * 32 + 32; ++r) {
-              if (!row_valid[r]) continue;
-              const uint32_t u = *reinterpret_cast<const uint32_t*>(stage + r * 128 + (((chunk ^ r) & 7) << 4) + word * 4);
-              const float2 ab = unpack2(u, p.out_dt);
-              s0 += ab.x; s1 += ab.y; q0 += ab.x * ab.x; q1 += ab.y * ab.y;
-            }
-            const int ch = n0 + c64 * 64 + 2 * lane;   // host guarantees n_total <= kMaxStatCh when stats are on
-            if (ch < p.n_total) { atomicAdd(&ssum[ch], s0); atomicAdd(&ssq[ch], q0); }
-            if (ch + 1 < p.n_total) { atomicAdd(&ssum[ch + 1], s1); atomicAdd(&ssq[ch + 1], q1); }
-          }
-          // ---- coalesced store: consecutive threads take consecutive 16 B chunks of a pixel row
-          const int co_base = co_tile + c64 * 64;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int idx = et + 128 * i;
-            const int r = idx >> 3, chunk = idx & 7;
-            if (!row_valid[r]) continue;
-            if (co_base + chunk * 8 >= p.n_store) continue;
-            const int rh = r / p.tw, rw = r - rh * p.tw;
-            int oh = h0 + rh, ow = w0 + rw;
-            if (p.up2) { oh = 2 * oh + a_off; ow = 2 * ow + b_off; }
-            if (oh >= p.out_h || ow >= p.out_w) continue;
-            uint4 val = *reinterpret_cast<const uint4*>(stage + r * 128 + (((chunk ^ r) & 7) << 4));
-            uint16_t* dst = p.out + img * p.out_img_stride + oh * p.out_row_stride + ow * p.out_pix_stride +
-                            co_base + chunk * 8;
-            if (p.accum) {
-              const uint4 old = *reinterpret_cast<const uint4*>(dst);
-              const int dt = p.out_dt;
-              float2 a, b;
-              a = unpack2(val.x, dt); b = unpack2(old.x, dt); val.x = pack2(a.x + b.x, a.y + b.y, dt);
-              a = unpack2(val.y, dt); b = unpack2(old.y, dt); val.y = pack2(a.x + b.x, a.y + b.y, dt);
-              a = unpack2(val.z, dt); b = unpack2(old.z, dt); val.z = pack2(a.x + b.x, a.y + b.y, dt);
-              a = unpack2(val.w, dt); b = unpack2(old.w, dt); val.w = pack2(a.x + b.x, a.y + b.y, dt);
-            }
-            *reinterpret_cast<uint4*>(dst) = val;
-          }
-          named_bar_sync(1, 128);              // staging free again
         }
-      } else {
-        // wgrad: rows = (chunk half, channel j); columns = n.  fp32 red.add into dW[n][k]
+        if (p.stats != nullptr && acc_n0 >= 0) {
+#pragma unroll
+          for (int j = 0; j < MYCH; ++j)
+            flush_stats(ssum, ssq, acc_n0 + (2 * j + g) * 64 + 2 * lane, p.n_total, ssv[j], sqv[j]);
+        }
+        if (elected) bulk_wait_read0();
+      }
+    } else {
+      // wgrad: rows = (chunk half, channel j); columns = n.  fp32 red.add into dW[n][k]; the groups split the
+      // 32-column slices of the accumulator.
+      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int m_tile, n_tile, kb_begin, kb_end;
+        decode(tile, m_tile, n_tile, kb_begin, kb_end);
+        if (kb_end <= kb_begin) continue;
+        const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
+        ++lt;
+        const int n0 = n_tile * BLOCK_N;
+        const uint32_t tmem_acc = tmem_base + as * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
         mbar_wait(&tmem_full[as], aph);
         tc_fence_after();
         const int qc = 2 * m_tile + (row >> 6);
         const bool row_ok = qc < p.total_chunks;
         const long long kidx = static_cast<long long>(qc) * 64 + (row & 63);
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N / 32; ++c) {
+        for (int c = g; c < BLOCK_N / 32; c += 2) {
           uint32_t v[32];
           tmem_ld32(tmem_acc + c * 32, v);
           tmem_ld_wait();
-          if (c == BLOCK_N / 32 - 1) {
+          if (c + 2 >= BLOCK_N / 32) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[as]);
@@ -384,15 +440,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         }
       }
     }
-  }
-  if (MODE == MODE_FWD && warp >= 2 && p.stats != nullptr) {
-    // one flush per CTA: per-channel partial sums of every tile this CTA produced -> fp64 global atomics
-    named_bar_sync(1, 128);
-    for (int ch = threadIdx.x - 64; ch < p.n_total; ch += 128) {
-      const float a = ssum[ch], b = ssq[ch];
-      if (a != 0.f || b != 0.f) {
-        atomicAdd(p.stats + 2 * ch, static_cast<double>(a));
-        atomicAdd(p.stats + 2 * ch + 1, static_cast<double>(b));
+    if (MODE == MODE_FWD && p.stats != nullptr) {
+      // one flush per CTA: per-channel partial sums of every tile this CTA produced -> fp64 global atomics
+      named_bar_sync(3, kEpiThreads);
+      for (int ch = threadIdx.x - 64; ch < p.n_total; ch += kEpiThreads) {
+        const float a = ssum[ch], b = ssq[ch];
+        if (a != 0.f || b != 0.f) {
+          atomicAdd(p.stats + 2 * ch, static_cast<double>(a));
+          atomicAdd(p.stats + 2 * ch + 1, static_cast<double>(b));
+        }
       }
     }
   }
@@ -406,9 +462,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
 }
 
 // =====================================================================================
-
-// =====================================================================================
-// 3x3 convolution with halo reuse (fprop and dgrad of the U-Net blocks at the high resolutions).
+// 3x3 convolution with halo reuse (fprop and dgrad of the U-Net blocks).
 //
 // The generic kernel above re-reads the activation tile from L2 once per filter tap (9x) and the
 // weight tile once per 128 output pixels; measured on B200 every layer then sits on the L2->SM
@@ -418,64 +472,44 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
 // descriptor offsets of r*tw*128 B into that block -- a multiple of the 1024 B swizzle atom, so the
 // 128B-swizzle phase is preserved.  The weight tile of each tap is shared by both halves.
 // L2->smem bytes per MAC drop 2.2-2.5x.  Accumulators: 2 buffers x 2 halves x BLOCK_N TMEM columns.
+// Epilogue group g owns accumulator half g (pixel rows g*128 .. g*128+127 of the tile).
+// Shared memory: [staging 2 x 16 KB][barriers][stats][pipeline: p.stages x (a_bytes + 3 weight tiles)].
 // =====================================================================================
 constexpr int kHaloStatCh = 1024;
-constexpr int kHaloABytes = 40960;          // (th+2)*tw rows x 128 B, worst case tw = 32
+constexpr int kHaloMaxStages = 4;
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N>
 struct HaloSmem {
   static constexpr int B_TILE = BLOCK_N * 128;
-  static constexpr int STAGE_BYTES = kHaloABytes + 3 * B_TILE;
-  static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
-  static constexpr int STAGING_OFF = PIPE_BYTES;
-  static constexpr int BAR_OFF = STAGING_OFF + 128 * 128;
-  static constexpr int TMEMPTR_OFF = BAR_OFF + (2 * STAGES + 4) * 8;
+  static constexpr int STAGING_OFF = 0;
+  static constexpr int BAR_OFF = 2 * kStageTile;                         // full[4], empty[4], tmem_full[2], tmem_empty[2]
+  static constexpr int TMEMPTR_OFF = BAR_OFF + (2 * kHaloMaxStages + 4) * 8;
   static constexpr int SSUM_OFF = TMEMPTR_OFF + 8;
-  static constexpr int TOTAL = SSUM_OFF + 2 * kHaloStatCh * 4;
-  static constexpr int ALLOC = TOTAL + 1024;
-  static_assert(ALLOC <= 227 * 1024, "shared memory budget exceeded");
+  static constexpr int PIPE_OFF = (SSUM_OFF + 2 * kHaloStatCh * 4 + 1023) / 1024 * 1024;
+  static constexpr int BUDGET = 227 * 1024 - 1024;                       // after manual 1024 B alignment
+  static int stage_bytes(int a_bytes) { return a_bytes + 3 * B_TILE; }
+  static int stages_for(int a_bytes) {
+    int s = (BUDGET - PIPE_OFF) / stage_bytes(a_bytes);
+    return s > kHaloMaxStages ? kHaloMaxStages : s;
+  }
 };
 
-template <int DT>
-__device__ __forceinline__ uint32_t pack2_t(float lo, float hi) {
-  if (DT == DT_F16) {
-    __half2 h = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<uint32_t*>(&h);
-  }
-  return pack_bf16x2(lo, hi);
-}
-// 32 fp32 accumulator columns -> 16-bit pairs -> swizzled staging row (zeros for invalid rows)
-template <int DT>
-__device__ __forceinline__ void stage_row32(uint8_t* stage, int row, int hh, const uint32_t (&v)[32], bool valid) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint4 o = make_uint4(0, 0, 0, 0);
-    if (valid) {
-      o.x = pack2_t<DT>(__uint_as_float(v[8 * i + 0]), __uint_as_float(v[8 * i + 1]));
-      o.y = pack2_t<DT>(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]));
-      o.z = pack2_t<DT>(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]));
-      o.w = pack2_t<DT>(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]));
-    }
-    const int chunk = hh * 4 + i;
-    *reinterpret_cast<uint4*>(stage + row * 128 + (((chunk ^ row) & 7) << 4)) = o;
-  }
-}
-
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const IgemmArgs p) {
-  using L = HaloSmem<BLOCK_N, STAGES>;
+                    const __grid_constant__ CUtensorMap tmO, const IgemmArgs p) {
+  using L = HaloSmem<BLOCK_N>;
+  constexpr int NCH = BLOCK_N / 64;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* empty_bar = full_bar + kHaloMaxStages;
+  uint64_t* tmem_full = empty_bar + kHaloMaxStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::TMEMPTR_OFF);
   float* ssum = reinterpret_cast<float*>(smem + L::SSUM_OFF);
   float* ssq = ssum + kHaloStatCh;
-  uint8_t* stage = smem + L::STAGING_OFF;
+  uint8_t* pipe = smem + L::PIPE_OFF;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -483,20 +517,23 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int tiles_per_img = p.tiles_h * p.tiles_w;
   const long long total_tiles = static_cast<long long>(p.N) * tiles_per_img * n_tiles;
   const int steps_per_tile = 3 * p.kchunks;                    // (channel chunk, horizontal shift)
-  const uint32_t a_bytes = static_cast<uint32_t>((p.th + 2) * p.tw * 128);
-  const int ltw = 31 - __clz(p.tw);
+  const int STG = p.stages;
+  const uint32_t a_bytes = static_cast<uint32_t>(p.a_bytes);   // (th+2)*tw rows x 128 B
+  const uint32_t stage_bytes = a_bytes + 3 * L::B_TILE;
+  const int ltw = p.ltw;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < STAGES; ++s) {
+    tma_prefetch_desc(&tmO);
+    for (int s = 0; s < STG; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(&tmem_full[0], 1);
     mbar_init(&tmem_full[1], 1);
-    mbar_init(&tmem_empty[0], 4);
-    mbar_init(&tmem_empty[1], 4);
+    mbar_init(&tmem_empty[0], 8);
+    mbar_init(&tmem_empty[1], 8);
     fence_mbar_init();
     fence_proxy_async_smem();
   }
@@ -513,7 +550,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
-      uint32_t it = 0;
+      uint32_t s = 0, ph = 0;
       for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_tile = static_cast<int>(tile % n_tiles);
         const int m_tile = static_cast<int>(tile / n_tiles);
@@ -521,18 +558,17 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int rr = m_tile - img * tiles_per_img;
         const int h0 = (rr / p.tiles_w) * p.th, w0 = (rr % p.tiles_w) * p.tw;
         const int n0 = n_tile * BLOCK_N;
-        for (int st = 0; st < steps_per_tile; ++st, ++it) {
+        for (int st = 0; st < steps_per_tile; ++st) {
           const int cc = st / 3, sft = st - cc * 3;
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], a_bytes + 3 * L::B_TILE);
-          uint8_t* sA = smem + s * L::STAGE_BYTES;
-          uint8_t* sB = sA + kHaloABytes;
+          mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
+          uint8_t* sA = pipe + s * stage_bytes;
+          uint8_t* sB = sA + a_bytes;
           tma_load_4d(sA, &tmA, &full_bar[s], cc * 64, w0 + sft - 1, h0 - 1, img);
 #pragma unroll
           for (int r = 0; r < 3; ++r)
             tma_load_2d(sB + r * L::B_TILE, &tmB, &full_bar[s], ((r * 3 + sft) * p.kchunks + cc) * 64, n0);
+          if (++s == static_cast<uint32_t>(STG)) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -541,20 +577,18 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       const uint32_t idesc = make_idesc_16(128, BLOCK_N, 0, 0, p.a_dt, p.b_dt);
       const uint32_t row_shift = static_cast<uint32_t>(p.tw * 128) >> 4;       // one image row of the halo block
-      uint32_t it = 0, lt = 0;
+      uint32_t s = 0, ph = 0, lt = 0;
       for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
         const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
         mbar_wait(&tmem_empty[as], aph ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * (2 * BLOCK_N);
-        for (int st = 0; st < steps_per_tile; ++st, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
+        for (int st = 0; st < steps_per_tile; ++st) {
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint32_t a_addr = smem_u32(pipe + s * stage_bytes);
           const uint64_t da0 = make_smem_desc_sw128(a_addr, 16, 1024);
-          const uint64_t db0 = make_smem_desc_sw128(a_addr + kHaloABytes, 16, 1024);
+          const uint64_t db0 = make_smem_desc_sw128(a_addr + a_bytes, 16, 1024);
 #pragma unroll
           for (int r = 0; r < 3; ++r) {
 #pragma unroll
@@ -567,17 +601,26 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
           }
           umma_commit(&empty_bar[s]);
+          if (++s == static_cast<uint32_t>(STG)) { s = 0; ph ^= 1; }
         }
         umma_commit(&tmem_full[as]);
       }
     }
   } else {
-    // =========================== epilogue (warps 2..5) ===========================
+    // =========================== epilogue (warps 2..9): group g owns accumulator half g ===========================
+    const int g = (warp - 2) >> 2;
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int et = threadIdx.x - 64;
-    const int ew = warp - 2;
-    const int my_chunk = et & 7, my_r0 = et >> 3;        // store duty: 16 B chunk my_chunk of rows my_r0 + 16 i
+    const int gw = (warp - 2) & 3;
+    const bool elected = gw == 0 && lane == 0;
+    uint8_t* stage = smem + L::STAGING_OFF + g * kStageTile;
+    const int bar_id = 1 + g;
+    const int pix = g * 128 + row;
+    const int ph_rows = 128 >> ltw;                       // image rows covered by one accumulator half
+    float2 ssv[NCH], sqv[NCH];
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) { ssv[j] = make_float2(0.f, 0.f); sqv[j] = make_float2(0.f, 0.f); }
+    int acc_n0 = -1;
     uint32_t lt = 0;
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
       const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
@@ -587,75 +630,46 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int rr = m_tile - img * tiles_per_img;
       const int h0 = (rr / p.tiles_w) * p.th, w0 = (rr % p.tiles_w) * p.tw;
       const int n0 = n_tile * BLOCK_N;
-      uint16_t* out_img = p.out + img * p.out_img_stride;
+      if (p.stats != nullptr && n0 != acc_n0) {
+        if (acc_n0 >= 0) {
+#pragma unroll
+          for (int j = 0; j < NCH; ++j) flush_stats(ssum, ssq, acc_n0 + j * 64 + 2 * lane, p.n_total, ssv[j], sqv[j]);
+        }
+        acc_n0 = n0;
+      }
+      const bool valid = (h0 + (pix >> ltw) < p.H) && (w0 + (pix & (p.tw - 1)) < p.W);
+      const uint32_t tmem_acc = tmem_base + as * (2 * BLOCK_N) + g * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
       mbar_wait(&tmem_full[as], aph);
       tc_fence_after();
-#pragma unroll 1
-      for (int hf = 0; hf < 2; ++hf) {
-        const int pix = hf * 128 + row;
-        const bool valid = (h0 + (pix >> ltw) < p.H) && (w0 + (pix & (p.tw - 1)) < p.W);
-        const uint32_t tmem_acc = tmem_base + as * (2 * BLOCK_N) + hf * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll 1
-        for (int c64 = 0; c64 < BLOCK_N / 64; ++c64) {
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            uint32_t v[32];
-            tmem_ld32(tmem_acc + c64 * 64 + hh * 32, v);
-            tmem_ld_wait();
-            if (p.out_dt == DT_F16) stage_row32<DT_F16>(stage, row, hh, v, valid);
-            else stage_row32<DT_BF16>(stage, row, hh, v, valid);
-          }
-          if (hf == 1 && c64 == BLOCK_N / 64 - 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[as]);
-          }
-          named_bar_sync(1, 128);
-          if (p.stats != nullptr) {
-            // invalid rows were staged as zeros: unconditional column sums over this warp's 32 rows
-            float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-            const int chunk = lane >> 2;
-            const uint8_t* base = stage + (ew * 32) * 128 + (lane & 3) * 4;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const uint32_t u = *reinterpret_cast<const uint32_t*>(base + i * 128 + (((chunk ^ i) & 7) << 4));
-              const float2 ab = unpack2(u, p.out_dt);
-              s0 += ab.x; s1 += ab.y; q0 = fmaf(ab.x, ab.x, q0); q1 = fmaf(ab.y, ab.y, q1);
-            }
-            const int ch = n0 + c64 * 64 + 2 * lane;
-            if (ch < p.n_total) { atomicAdd(&ssum[ch], s0); atomicAdd(&ssq[ch], q0); }
-            if (ch + 1 < p.n_total) { atomicAdd(&ssum[ch + 1], s1); atomicAdd(&ssq[ch + 1], q1); }
-          }
-          const int co = n0 + c64 * 64 + my_chunk * 8;
-          if (co < p.n_store) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int r = my_r0 + 16 * i;
-              const int px = hf * 128 + r;
-              const int oh = h0 + (px >> ltw), ow = w0 + (px & (p.tw - 1));
-              if (oh < p.out_h && ow < p.out_w) {
-                uint4 val = *reinterpret_cast<const uint4*>(stage + r * 128 + (((my_chunk ^ r) & 7) << 4));
-                uint16_t* dst = out_img + oh * p.out_row_stride + ow * p.out_pix_stride + co;
-                if (p.accum) {
-                  const uint4 old = *reinterpret_cast<const uint4*>(dst);
-                  const int dt = p.out_dt;
-                  float2 a, b;
-                  a = unpack2(val.x, dt); b = unpack2(old.x, dt); val.x = pack2(a.x + b.x, a.y + b.y, dt);
-                  a = unpack2(val.y, dt); b = unpack2(old.y, dt); val.y = pack2(a.x + b.x, a.y + b.y, dt);
-                  a = unpack2(val.z, dt); b = unpack2(old.z, dt); val.z = pack2(a.x + b.x, a.y + b.y, dt);
-                  a = unpack2(val.w, dt); b = unpack2(old.w, dt); val.w = pack2(a.x + b.x, a.y + b.y, dt);
-                }
-                *reinterpret_cast<uint4*>(dst) = val;
-              }
-            }
-          }
-          named_bar_sync(1, 128);
+      for (int c64 = 0; c64 < NCH; ++c64) {
+        if (elected) bulk_wait_read0();
+        named_bar_sync(bar_id, 128);
+        chunk_to_stage(tmem_acc + c64 * 64, stage, row, valid, p.out_dt, nullptr);
+        if (c64 == NCH - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(bar_id, 128);
+        if (elected && n0 + c64 * 64 < p.n_total && h0 + g * ph_rows < p.H) {
+          tma_store_4d(&tmO, stage, n0 + c64 * 64, w0, h0 + g * ph_rows, img);
+          bulk_commit();
+        }
+        if (p.stats != nullptr) {
+          if (p.out_dt == DT_F16) stats_rows32<DT_F16>(stage, gw * 32, lane, ssv[c64], sqv[c64]);
+          else stats_rows32<DT_BF16>(stage, gw * 32, lane, ssv[c64], sqv[c64]);
         }
       }
     }
     if (p.stats != nullptr) {
-      named_bar_sync(1, 128);
-      for (int ch = et; ch < p.n_total; ch += 128) {
+      if (acc_n0 >= 0) {
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) flush_stats(ssum, ssq, acc_n0 + j * 64 + 2 * lane, p.n_total, ssv[j], sqv[j]);
+      }
+      named_bar_sync(3, kEpiThreads);
+      for (int ch = threadIdx.x - 64; ch < p.n_total; ch += kEpiThreads) {
         const float a = ssum[ch], b = ssq[ch];
         if (a != 0.f || b != 0.f) {
           atomicAdd(p.stats + 2 * ch, static_cast<double>(a));
@@ -663,6 +677,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
     }
+    if (elected) bulk_wait_read0();
   }
   __syncwarp();
   tc_fence_before();
@@ -742,6 +757,34 @@ static int map_weights(CUtensorMap* m, const void* w, int rows, int kpad, int bl
   return make_map(m, w, 2, dims, str, box, dt);
 }
 
+// output map of a (channel-sliced) NHWC view: dims (n_store, w, h, n), box {64, bw, bh, 1}; the TMA unit clips
+// whatever part of a staged tile falls outside
+static int map_out(CUtensorMap* m, const hpri_view_t& v, int n_store, int bh, int bw) {
+  uint64_t dims[4] = {(uint64_t)n_store, (uint64_t)v.w, (uint64_t)v.h, (uint64_t)v.n};
+  uint64_t str[3] = {(uint64_t)v.pix_stride * 2, (uint64_t)v.row_stride * 2, (uint64_t)v.img_stride * 2};
+  uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, 1};
+  return make_map(m, v.ptr, 4, dims, str, box, v.dtype);
+}
+// ConvTranspose2d(k2, s2) destination for one (a, b): the pixels (2h+a, 2w+b) of the high-res view v, indexed by
+// the low-res (w, h) of an hl x wl grid
+static int map_out_up2(CUtensorMap* m, const hpri_view_t& v, int cout, int hl, int wl, int a, int b, int bh, int bw) {
+  int wv = (v.w - b + 1) / 2, hv = (v.h - a + 1) / 2;
+  if (wv > wl) wv = wl;
+  if (hv > hl) hv = hl;
+  if (wv <= 0 || hv <= 0) return HPRI_ERR_ARG;
+  uint64_t dims[4] = {(uint64_t)cout, (uint64_t)wv, (uint64_t)hv, (uint64_t)v.n};
+  uint64_t str[3] = {(uint64_t)v.pix_stride * 4, (uint64_t)v.row_stride * 4, (uint64_t)v.img_stride * 2};
+  uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, 1};
+  const uint16_t* base = static_cast<const uint16_t*>(v.ptr) + (long long)a * v.row_stride + (long long)b * v.pix_stride;
+  return make_map(m, base, 4, dims, str, box, v.dtype);
+}
+
+static int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+
 // pick a th x tw = P pixel tile (powers of two) minimising the tile count; ties -> wider rows
 static void pick_tile(int H, int W, int P, int* th, int* tw) {
   long long best = -1;
@@ -752,10 +795,26 @@ static void pick_tile(int H, int W, int P, int* th, int* tw) {
     if (best < 0 || cnt <= best) { best = cnt; *th = h; *tw = w; }
   }
 }
+static void set_tile(IgemmArgs& a, int th, int tw) {
+  a.th = th; a.tw = tw; a.ltw = ilog2(tw);
+  a.tiles_h = (a.H + th - 1) / th; a.tiles_w = (a.W + tw - 1) / tw;
+}
+
+static int sm_count() {
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+  }
+  return num_sms;
+}
+
+struct OutMaps { CUtensorMap m[4]; };
 
 template <int BLOCK_N, int STAGES, int MODE>
 static int launch_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1,
-                    const IgemmArgs& args, long long grid, cudaStream_t stream) {
+                    const OutMaps& o, const IgemmArgs& args, long long grid, cudaStream_t stream) {
   using L = SmemLayout<BLOCK_N, STAGES, MODE>;
   auto kern = igemm_kernel<BLOCK_N, STAGES, MODE>;
   static std::once_flag once;
@@ -765,25 +824,20 @@ static int launch_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensor
   });
   if (attr_err != cudaSuccess) return HPRI_ERR_CUDA;
   if (grid <= 0 || grid > 0x7FFFFFFFLL) return HPRI_ERR_ARG;
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
-  }
-  if (grid > num_sms) grid = num_sms;          // persistent: one CTA per SM walks the tile list
-  kern<<<(unsigned)grid, kThreads, L::ALLOC, stream>>>(a0, a1, b0, b1, args);
+  if (grid > sm_count()) grid = sm_count();          // persistent: one CTA per SM walks the tile list
+  kern<<<(unsigned)grid, kThreads, L::ALLOC, stream>>>(a0, a1, b0, b1, o.m[0], o.m[1], o.m[2], o.m[3], args);
   ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? HPRI_OK : HPRI_ERR_CUDA;
 }
 
 template <int MODE>
 static int launch(int block_n, const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0,
-                  const CUtensorMap& b1, const IgemmArgs& args, long long grid, cudaStream_t stream) {
+                  const CUtensorMap& b1, const OutMaps& o, const IgemmArgs& args, long long grid,
+                  cudaStream_t stream) {
   switch (block_n) {
-    case 64: return launch_t<64, MODE == MODE_FWD ? 7 : 4, MODE>(a0, a1, b0, b1, args, grid, stream);
-    case 128: return launch_t<128, MODE == MODE_FWD ? 5 : 3, MODE>(a0, a1, b0, b1, args, grid, stream);
-    case 256: return launch_t<256, MODE == MODE_FWD ? 4 : 2, MODE>(a0, a1, b0, b1, args, grid, stream);
+    case 64: return launch_t<64, MODE == MODE_FWD ? 7 : 4, MODE>(a0, a1, b0, b1, o, args, grid, stream);
+    case 128: return launch_t<128, MODE == MODE_FWD ? 5 : 3, MODE>(a0, a1, b0, b1, o, args, grid, stream);
+    case 256: return launch_t<256, MODE == MODE_FWD ? 3 : 2, MODE>(a0, a1, b0, b1, o, args, grid, stream);
   }
   return HPRI_ERR_ARG;
 }
@@ -798,26 +852,21 @@ static int pick_block_n(int n_total, int forced) {
 
 
 // halo kernel launcher -------------------------------------------------------------------
-template <int BLOCK_N, int STAGES>
-static int launch_halo_t(const CUtensorMap& ma, const CUtensorMap& mb, const IgemmArgs& args, long long tiles,
-                         cudaStream_t stream) {
-  using L = HaloSmem<BLOCK_N, STAGES>;
-  auto kern = conv3x3_halo_kernel<BLOCK_N, STAGES>;
+template <int BLOCK_N>
+static int launch_halo_t(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const IgemmArgs& args,
+                         long long tiles, cudaStream_t stream) {
+  using L = HaloSmem<BLOCK_N>;
+  auto kern = conv3x3_halo_kernel<BLOCK_N>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
-    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::ALLOC);
+    attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (attr_err != cudaSuccess) return HPRI_ERR_CUDA;
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
-  }
-  long long grid = tiles < num_sms ? tiles : num_sms;
+  long long grid = tiles < sm_count() ? tiles : sm_count();
   if (grid <= 0) return HPRI_ERR_ARG;
-  kern<<<(unsigned)grid, kThreads, L::ALLOC, stream>>>(ma, mb, args);
+  const size_t smem = (size_t)L::PIPE_OFF + (size_t)args.stages * L::stage_bytes(args.a_bytes) + 1024;
+  kern<<<(unsigned)grid, kThreads, smem, stream>>>(ma, mb, mo, args);
   ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? HPRI_OK : HPRI_ERR_CUDA;
 }
@@ -865,48 +914,59 @@ extern "C" int hpri_igemm_fwd(const hpri_view_t* x, const void* wpack, int w_dty
   if (taps != 1 && taps != 9) return HPRI_ERR_ARG;
   if (x->n != y->n || x->h != y->h || x->w != y->w) return HPRI_ERR_ARG;
   if ((reinterpret_cast<uintptr_t>(wpack) & 15) || (kpad & 63) || (n_store & 7) || n_store > y->c) return HPRI_ERR_ALIGN;
+  if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) return HPRI_ERR_ALIGN;
   const int kchunks = (x->c + 63) / 64;
   if (kpad != taps * kchunks * 64) return HPRI_ERR_ARG;
   IgemmArgs a{};
   a.N = x->n; a.H = x->h; a.W = x->w;
-  pick_tile(a.H, a.W, 128, &a.th, &a.tw);
-  a.tiles_h = (a.H + a.th - 1) / a.th; a.tiles_w = (a.W + a.tw - 1) / a.tw;
   a.taps = taps; a.tap_mode = taps == 9 ? TAP_3X3 : TAP_NONE; a.kchunks = kchunks;
   a.n_total = w_rows;
-  a.out = static_cast<uint16_t*>(y->ptr);
-  a.out_pix_stride = y->pix_stride; a.out_row_stride = y->row_stride; a.out_img_stride = y->img_stride;
-  a.out_h = y->h; a.out_w = y->w; a.n_store = n_store; a.up2 = 0; a.cout = w_rows;
+  a.up2 = 0; a.cout = w_rows;
   a.a_dt = x->dtype; a.b_dt = w_dtype; a.out_dt = y->dtype;
   if (x->dtype != w_dtype) return HPRI_ERR_ARG;     // kind::f16 takes A and B in one format
   a.bias = bias; a.stats = stats; a.accum = accumulate ? 1 : 0;
   if (accumulate && stats) return HPRI_ERR_ARG;
   if (stats && w_rows > kMaxStatCh) return HPRI_ERR_ARG;
-  if (taps == 9 && bias == nullptr) {
-    // halo-reuse kernel where the 256-pixel tiles fit the image well (the high-resolution levels)
+  if (bias && (w_rows & 63)) return HPRI_ERR_ARG;   // the epilogue reads the bias in 64-float runs
+  if (n_store <= 0) {                               // timing aid: run the contraction, store nothing
+    n_store = 8;
+    a.n_total = w_rows;
+  }
+  if (taps == 9 && bias == nullptr && !accumulate) {
+    // halo-reuse kernel (256-pixel tiles)
     int hth = 0, htw = 0;
     const double waste = pick_halo_tile(a.H, a.W, &hth, &htw);
     const int ov = conv_algo_override();
     const bool stats_ok = !stats || w_rows <= kHaloStatCh;
-    if (stats_ok && (ov == 1 || (ov < 0 && waste <= 1.0))) {
-      a.th = hth; a.tw = htw;
-      a.tiles_h = (a.H + hth - 1) / hth; a.tiles_w = (a.W + htw - 1) / htw;
-      const int hbn = w_rows <= 64 ? 64 : 128;
-      CUtensorMap ma, mb;
+    const int hbn = w_rows <= 64 ? 64 : 128;
+    const int a_bytes = (hth + 2) * htw * 128;
+    const int stages = hbn == 64 ? HaloSmem<64>::stages_for(a_bytes) : HaloSmem<128>::stages_for(a_bytes);
+    if (stats_ok && stages >= 2 && (ov == 1 || (ov < 0 && waste <= 1.0))) {
+      set_tile(a, hth, htw);
+      a.stages = stages; a.a_bytes = a_bytes;
+      CUtensorMap ma, mb, mo;
       uint64_t dims[4] = {(uint64_t)x->c, (uint64_t)x->w, (uint64_t)x->h, (uint64_t)x->n};
       uint64_t str[3] = {(uint64_t)x->pix_stride * 2, (uint64_t)x->row_stride * 2, (uint64_t)x->img_stride * 2};
       uint32_t box[4] = {64, (uint32_t)htw, (uint32_t)(hth + 2), 1};
       if ((rc = make_map(&ma, x->ptr, 4, dims, str, box, x->dtype)) != HPRI_OK) return rc;
       if ((rc = map_weights(&mb, wpack, w_rows, kpad, hbn, w_dtype)) != HPRI_OK) return rc;
+      if ((rc = map_out(&mo, *y, n_store, 128 / htw, htw)) != HPRI_OK) return rc;
       const long long tiles = (long long)a.N * a.tiles_h * a.tiles_w * ((w_rows + hbn - 1) / hbn);
-      return hbn == 64 ? launch_halo_t<64, 3>(ma, mb, a, tiles, stream) : launch_halo_t<128, 2>(ma, mb, a, tiles, stream);
+      return hbn == 64 ? launch_halo_t<64>(ma, mb, mo, a, tiles, stream) : launch_halo_t<128>(ma, mb, mo, a, tiles, stream);
     }
   }
+  int th, tw;
+  pick_tile(a.H, a.W, 128, &th, &tw);
+  set_tile(a, th, tw);
   const int bn = pick_block_n(w_rows, block_n);
   CUtensorMap ma, mb;
+  OutMaps o;
   if ((rc = map_nhwc(&ma, *x, a.th, a.tw)) != HPRI_OK) return rc;
   if ((rc = map_weights(&mb, wpack, w_rows, kpad, bn, w_dtype)) != HPRI_OK) return rc;
+  if ((rc = map_out(&o.m[0], *y, n_store, a.th, a.tw)) != HPRI_OK) return rc;
+  o.m[1] = o.m[2] = o.m[3] = o.m[0];
   const long long grid = (long long)a.N * a.tiles_h * a.tiles_w * ((w_rows + bn - 1) / bn);
-  return launch<MODE_FWD>(bn, ma, ma, mb, mb, a, grid, stream);
+  return launch<MODE_FWD>(bn, ma, ma, mb, mb, o, a, grid, stream);
 }
 
 // ConvTranspose2d(k=2, s=2) forward: y[n, 2h+a, 2w+b, co] = bias[co] + sum_ci x[n,h,w,ci] W[ci,co,a,b]
@@ -918,25 +978,28 @@ extern "C" int hpri_convT2x2_fwd(const hpri_view_t* x, const void* wpack, int w_
   int rc;
   if ((rc = check_view(*x)) != HPRI_OK || (rc = check_view(*y)) != HPRI_OK) return rc;
   const int kchunks = (x->c + 63) / 64;
-  if (kpad != kchunks * 64 || (cout & 63)) return HPRI_ERR_ARG;
+  if (kpad != kchunks * 64 || (cout & 63) || y->c < cout) return HPRI_ERR_ARG;
+  if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) return HPRI_ERR_ALIGN;
   IgemmArgs a{};
   a.N = x->n; a.H = x->h; a.W = x->w;
-  pick_tile(a.H, a.W, 128, &a.th, &a.tw);
-  a.tiles_h = (a.H + a.th - 1) / a.th; a.tiles_w = (a.W + a.tw - 1) / a.tw;
+  int th, tw;
+  pick_tile(a.H, a.W, 128, &th, &tw);
+  set_tile(a, th, tw);
   a.taps = 1; a.tap_mode = TAP_NONE; a.kchunks = kchunks; a.n_total = 4 * cout;
-  a.out = static_cast<uint16_t*>(y->ptr);
-  a.out_pix_stride = y->pix_stride; a.out_row_stride = y->row_stride; a.out_img_stride = y->img_stride;
-  a.out_h = y->h; a.out_w = y->w; a.n_store = cout; a.up2 = 1; a.cout = cout;
+  a.up2 = 1; a.cout = cout;
   a.a_dt = x->dtype; a.b_dt = w_dtype; a.out_dt = y->dtype;
   if (x->dtype != w_dtype) return HPRI_ERR_ARG;
   a.bias = bias; a.stats = nullptr;
-  int bn = pick_block_n(cout, block_n);
-  while (cout % bn) bn >>= 1;
+  // every 64-column chunk of a tile picks its own (a, b) output map, so wide tiles may span several of them
+  const int bn = block_n == 64 || block_n == 128 || block_n == 256 ? block_n : 256;
   CUtensorMap ma, mb;
+  OutMaps o;
   if ((rc = map_nhwc(&ma, *x, a.th, a.tw)) != HPRI_OK) return rc;
   if ((rc = map_weights(&mb, wpack, 4 * cout, kpad, bn, w_dtype)) != HPRI_OK) return rc;
-  const long long grid = (long long)a.N * a.tiles_h * a.tiles_w * (4 * cout / bn);
-  return launch<MODE_FWD>(bn, ma, ma, mb, mb, a, grid, stream);
+  for (int ab = 0; ab < 4; ++ab)
+    if ((rc = map_out_up2(&o.m[ab], *y, cout, a.H, a.W, ab >> 1, ab & 1, a.th, a.tw)) != HPRI_OK) return rc;
+  const long long grid = (long long)a.N * a.tiles_h * a.tiles_w * ((4 * cout + bn - 1) / bn);
+  return launch<MODE_FWD>(bn, ma, ma, mb, mb, o, a, grid, stream);
 }
 
 // ConvTranspose2d dgrad: dx[n,h,w,ci] = sum_{a,b,co} dy[n,2h+a,2w+b,co] W[ci,co,a,b]
@@ -951,21 +1014,25 @@ extern "C" int hpri_convT2x2_dgrad(const hpri_view_t* dy, const void* wpack, int
   if (kpad != 4 * kchunks * 64) return HPRI_ERR_ARG;
   IgemmArgs a{};
   a.N = dx->n; a.H = dx->h; a.W = dx->w;
-  pick_tile(a.H, a.W, 128, &a.th, &a.tw);
-  a.tiles_h = (a.H + a.th - 1) / a.th; a.tiles_w = (a.W + a.tw - 1) / a.tw;
+  int th, tw;
+  pick_tile(a.H, a.W, 128, &th, &tw);
+  set_tile(a, th, tw);
   a.taps = 4; a.tap_mode = TAP_UP2; a.kchunks = kchunks; a.n_total = cin;
-  a.out = static_cast<uint16_t*>(dx->ptr);
-  a.out_pix_stride = dx->pix_stride; a.out_row_stride = dx->row_stride; a.out_img_stride = dx->img_stride;
-  a.out_h = dx->h; a.out_w = dx->w; a.n_store = (cin + 7) & ~7; a.up2 = 0; a.cout = cin;
+  a.up2 = 0; a.cout = cin;
   a.a_dt = dy->dtype; a.b_dt = w_dtype; a.out_dt = dx->dtype;
   if (dy->dtype != w_dtype) return HPRI_ERR_ARG;
   const int bn = pick_block_n(cin, block_n);
+  int n_store = (cin + 7) & ~7;
+  if (n_store > dx->c) return HPRI_ERR_ARG;
   CUtensorMap m0, m1, mb;
+  OutMaps o;
   if ((rc = map_up2(&m0, *dy, a.H, a.W, 0, a.th, a.tw)) != HPRI_OK) return rc;
   if ((rc = map_up2(&m1, *dy, a.H, a.W, 1, a.th, a.tw)) != HPRI_OK) return rc;
   if ((rc = map_weights(&mb, wpack, cin, kpad, bn, w_dtype)) != HPRI_OK) return rc;
+  if ((rc = map_out(&o.m[0], *dx, n_store, a.th, a.tw)) != HPRI_OK) return rc;
+  o.m[1] = o.m[2] = o.m[3] = o.m[0];
   const long long grid = (long long)a.N * a.tiles_h * a.tiles_w * ((cin + bn - 1) / bn);
-  return launch<MODE_FWD>(bn, m0, m1, mb, mb, a, grid, stream);
+  return launch<MODE_FWD>(bn, m0, m1, mb, mb, o, a, grid, stream);
 }
 
 // Weight gradient.  mode 0: 1x1 / Linear, 1: 3x3 pad 1, 2: ConvTranspose2d 2x2 (x low-res, dy high-res).
@@ -979,8 +1046,9 @@ extern "C" int hpri_igemm_wgrad(const hpri_view_t* x, const hpri_view_t* dy, int
   if (mode < 0 || mode > 2) return HPRI_ERR_ARG;
   IgemmArgs a{};
   a.N = x->n; a.H = x->h; a.W = x->w;
-  pick_tile(a.H, a.W, 128, &a.th, &a.tw);
-  a.tiles_h = (a.H + a.th - 1) / a.th; a.tiles_w = (a.W + a.tw - 1) / a.tw;
+  int th, tw;
+  pick_tile(a.H, a.W, 128, &th, &tw);
+  set_tile(a, th, tw);
   a.taps = mode == 1 ? 9 : 1; a.tap_mode = mode == 1 ? TAP_3X3 : (mode == 2 ? TAP_UP2 : TAP_NONE);
   a.kchunks = (x->c + 63) / 64;
   a.total_chunks = a.taps * a.kchunks;
@@ -1006,10 +1074,11 @@ extern "C" int hpri_igemm_wgrad(const hpri_view_t* x, const hpri_view_t* dy, int
     // waves x (k-blocks per tile + epilogue cost), i.e. never leave a wave with a single straggler tile.
     const long long mn = (long long)m_tiles * n_tiles;
     const double epi = 2.0;                             // tile epilogue (mostly overlapped) in k-block units
+    const int sms = sm_count();
     double best = 1e30;
     splits = 1;
-    for (long long s = 1; s <= T && s * mn <= 4LL * 148 + mn; ++s) {
-      const long long waves = (s * mn + 147) / 148;
+    for (long long s = 1; s <= T && s * mn <= 4LL * sms + mn; ++s) {
+      const long long waves = (s * mn + sms - 1) / sms;
       const double cost = (double)waves * ((double)((T + s - 1) / s) + epi);
       if (cost < best) { best = cost; splits = (int)s; }
     }
@@ -1025,6 +1094,8 @@ extern "C" int hpri_igemm_wgrad(const hpri_view_t* x, const hpri_view_t* dy, int
     if ((rc = map_nhwc(&mb0, *dy, a.th, a.tw)) != HPRI_OK) return rc;
     mb1 = mb0;
   }
+  OutMaps o;
+  o.m[0] = o.m[1] = o.m[2] = o.m[3] = ma;             // unused by the wgrad epilogue
   const long long grid = (long long)m_tiles * n_tiles * splits;
-  return launch<MODE_WGRAD>(bn, ma, ma, mb0, mb1, a, grid, stream);
+  return launch<MODE_WGRAD>(bn, ma, ma, mb0, mb1, o, a, grid, stream);
 }

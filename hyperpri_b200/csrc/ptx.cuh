@@ -85,6 +85,25 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+// TMA stores (shared -> global, bulk-group completion).  Out-of-bounds box elements are clipped by the TMA unit.
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+// element-wise add into global memory in the tensor map's data type (f16 / bf16 here)
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2,
+                                                  int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// every committed bulk group has finished READING its shared-memory source
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
@@ -170,6 +189,20 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi, int dt) {
 }
 __device__ __forceinline__ float2 unpack2(uint32_t v, int dt) {
   if (dt == DT_F16) return __half22float2(*reinterpret_cast<__half2*>(&v));
+  return make_float2(bf16_lo(v), bf16_hi(v));
+}
+// packed fp32 pair arithmetic (FADD2 / FFMA2 on sm_100): s += v, q += v*v on two channels per instruction
+__device__ __forceinline__ void acc_sum_sq2(float2& s, float2& q, float2 v) {
+  unsigned long long us = *reinterpret_cast<unsigned long long*>(&s), uq = *reinterpret_cast<unsigned long long*>(&q);
+  const unsigned long long uv = *reinterpret_cast<unsigned long long*>(&v);
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(us) : "l"(uv));
+  asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(uq) : "l"(uv));
+  s = *reinterpret_cast<float2*>(&us);
+  q = *reinterpret_cast<float2*>(&uq);
+}
+template <int DT>
+__device__ __forceinline__ float2 unpack2_t(uint32_t v) {
+  if (DT == DT_F16) return __half22float2(*reinterpret_cast<__half2*>(&v));
   return make_float2(bf16_lo(v), bf16_hi(v));
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
