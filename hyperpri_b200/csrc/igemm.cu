@@ -221,8 +221,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
   };
 
   if (warp == 0) {
-    // =========================== TMA producer ===========================
-    if (lane == 0) {
+    // =========================== TMA producer (whole warp converged, one elected lane issues) ===========
+    {
       uint32_t it = 0;
       for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int m_tile, n_tile, kb_begin, kb_end;
@@ -239,7 +239,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
+          mbar_arrive_expect_tx_w(&full_bar[s], L::STAGE_BYTES);
           uint8_t* sA = smem + s * L::STAGE_BYTES;
           uint8_t* sB = sA + A_BYTES;
           if (MODE == MODE_FWD) {
@@ -247,13 +247,13 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
             const int cc = kb - tap * p.kchunks;
             if (p.tap_mode == TAP_UP2) {
               // ConvT dgrad: gather dy[2h+a, 2w+b]; 5-D view (c, w, a, h, n), one map per b
-              tma_load_5d(sA, (tap & 1) ? &tmA1 : &tmA0, &full_bar[s], cc * 64, w0, tap >> 1, h0, img);
+              tma_load_5d_w(sA, (tap & 1) ? &tmA1 : &tmA0, &full_bar[s], cc * 64, w0, tap >> 1, h0, img);
             } else {
               int dh = 0, dw = 0;
               if (p.tap_mode == TAP_3X3) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
-              tma_load_4d(sA, &tmA0, &full_bar[s], cc * 64, w0 + dw, h0 + dh, img);
+              tma_load_4d_w(sA, &tmA0, &full_bar[s], cc * 64, w0 + dw, h0 + dh, img);
             }
-            tma_load_2d(sB, &tmB0, &full_bar[s], kb * 64, n0);
+            tma_load_2d_w(sB, &tmB0, &full_bar[s], kb * 64, n0);
           } else {
             // wgrad: k-block = one pixel tile of 128 pixels
             const int im = kb / tiles_per_img;
@@ -268,16 +268,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
               int dh = 0, dw = 0;
               if (p.tap_mode == TAP_3X3) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
               if (q >= p.total_chunks) cc = 0x100000;   // fully out of bounds -> zero fill
-              tma_load_4d(sA + half * 16384, &tmA0, &full_bar[s], cc * 64, pw0 + dw, ph0 + dh, im);
+              tma_load_4d_w(sA + half * 16384, &tmA0, &full_bar[s], cc * 64, pw0 + dw, ph0 + dh, im);
             }
 #pragma unroll
             for (int j = 0; j < BLOCK_N / 64; ++j) {
               if (p.tap_mode == TAP_UP2) {
                 const int ab = n0 / p.cout;
                 const int co0 = n0 - ab * p.cout;
-                tma_load_5d(sB + j * 16384, (ab & 1) ? &tmB1 : &tmB0, &full_bar[s], co0 + j * 64, pw0, ab >> 1, ph0, im);
+                tma_load_5d_w(sB + j * 16384, (ab & 1) ? &tmB1 : &tmB0, &full_bar[s], co0 + j * 64, pw0, ab >> 1, ph0, im);
               } else {
-                tma_load_4d(sB + j * 16384, &tmB0, &full_bar[s], n0 + j * 64, pw0, ph0, im);
+                tma_load_4d_w(sB + j * 16384, &tmB0, &full_bar[s], n0 + j * 64, pw0, ph0, im);
               }
             }
           }
@@ -285,8 +285,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
       }
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    // =========================== MMA issuer (whole warp converged, one elected lane issues) ============
+    {
       const uint32_t idesc = make_idesc_16(128, BLOCK_N, MODE == MODE_WGRAD, MODE == MODE_WGRAD, p.a_dt, p.b_dt);
       uint32_t it = 0, lt = 0;
       for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -319,12 +319,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
           constexpr int KSTEPS = MODE == MODE_FWD ? 4 : 8;
 #pragma unroll
           for (int k = 0; k < KSTEPS; ++k) {
-            umma_bf16(tmem_d, da + static_cast<uint64_t>(k * kstep), db + static_cast<uint64_t>(k * kstep), idesc,
-                      (kb > kb_begin || k > 0) ? 1u : 0u);
+            umma_f16_w(tmem_d, da + static_cast<uint64_t>(k * kstep), db + static_cast<uint64_t>(k * kstep), idesc,
+                       (kb > kb_begin || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[s]);      // frees the smem slot once these MMAs have read it
+          umma_commit_w(&empty_bar[s]);    // frees the smem slot once these MMAs have read it
         }
-        umma_commit(&tmem_full[as]);       // accumulator complete
+        umma_commit_w(&tmem_full[as]);     // accumulator complete
       }
     }
   } else {
@@ -462,74 +462,84 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
 }
 
 // =====================================================================================
-// 3x3 convolution with halo reuse (fprop and dgrad of the U-Net blocks).
+// 3x3 convolution with full halo reuse (fprop and dgrad of the U-Net blocks).
 //
 // The generic kernel above re-reads the activation tile from L2 once per filter tap (9x) and the
 // weight tile once per 128 output pixels; measured on B200 every layer then sits on the L2->SM
-// bandwidth (10-13 TB/s) instead of the tensor pipe.  Here one CTA owns a 256-pixel tile
-// (th x tw, tw in {8,16,32}, two M=128 accumulator halves) and, per 64-channel chunk, loads the
-// (th+2) x tw halo block only three times (one per horizontal shift s); the three vertical taps r are
-// descriptor offsets of r*tw*128 B into that block -- a multiple of the 1024 B swizzle atom, so the
-// 128B-swizzle phase is preserved.  The weight tile of each tap is shared by both halves.
-// L2->smem bytes per MAC drop 2.2-2.5x.  Accumulators: 2 buffers x 2 halves x BLOCK_N TMEM columns.
-// Epilogue group g owns accumulator half g (pixel rows g*128 .. g*128+127 of the tile).
-// Shared memory: [staging 2 x 16 KB][barriers][stats][pipeline: p.stages x (a_bytes + 3 weight tiles)].
+// bandwidth (10-13 TB/s) instead of the tensor pipe.  Here one CTA owns a 256-pixel tile made of two
+// M=128 halves of 16 rows x 8 columns (stacked: 32x8 tile, or side by side: 16x16 tile) and, per
+// 64-channel chunk, loads the (th+2) x (tw+2) halo block ONCE.  All nine taps are descriptor start
+// offsets into that block: pixel (y+r, x+s) of the block is smem row (y+r)*(tw+2) + x+s, the eight
+// pixels of one tile row are eight consecutive 128-byte rows (one swizzle group), and consecutive tile
+// rows are (tw+2)*128 B apart (the descriptor's SBO).  tcgen05.mma applies the 128B swizzle to absolute
+// shared-memory address bits (tools/probes/umma_rowshift_probe.cu: any 128-byte row offset and
+// SBO = 1152 / 1280 read back exactly), so the TMA-written block is consumed in place.
+// Activation bytes per MAC drop 3x against per-shift loads, 6.6x against per-tap loads.
+// Two TMA rings: the A ring holds halo blocks (one per channel chunk, alive for three sub-steps), the
+// B ring the three weight tiles of one filter row.  Accumulators: 2 buffers x 2 halves x BLOCK_N TMEM
+// columns; epilogue group g owns half g.
+// Shared memory: [staging 2 x 16 KB][barriers][stats][A ring: 2 x a_bytes][B ring: p.stages x 3 weight tiles].
 // =====================================================================================
 constexpr int kHaloStatCh = 1024;
-constexpr int kHaloMaxStages = 4;
+constexpr int kHaloAStages = 2;
+constexpr int kHaloMaxBStages = 4;
 
 template <int BLOCK_N>
 struct HaloSmem {
   static constexpr int B_TILE = BLOCK_N * 128;
+  static constexpr int B_STAGE = 3 * B_TILE;
   static constexpr int STAGING_OFF = 0;
-  static constexpr int BAR_OFF = 2 * kStageTile;                         // full[4], empty[4], tmem_full[2], tmem_empty[2]
-  static constexpr int TMEMPTR_OFF = BAR_OFF + (2 * kHaloMaxStages + 4) * 8;
+  static constexpr int BAR_OFF = 2 * kStageTile;       // a_full[2], a_empty[2], b_full[4], b_empty[4], tmem_full[2], tmem_empty[2]
+  static constexpr int TMEMPTR_OFF = BAR_OFF + (2 * kHaloAStages + 2 * kHaloMaxBStages + 4) * 8;
   static constexpr int SSUM_OFF = TMEMPTR_OFF + 8;
   static constexpr int PIPE_OFF = (SSUM_OFF + 2 * kHaloStatCh * 4 + 1023) / 1024 * 1024;
   static constexpr int BUDGET = 227 * 1024 - 1024;                       // after manual 1024 B alignment
-  static int stage_bytes(int a_bytes) { return a_bytes + 3 * B_TILE; }
-  static int stages_for(int a_bytes) {
-    int s = (BUDGET - PIPE_OFF) / stage_bytes(a_bytes);
-    return s > kHaloMaxStages ? kHaloMaxStages : s;
+  static int b_stages_for(int a_bytes) {
+    int s = (BUDGET - PIPE_OFF - kHaloAStages * a_bytes) / B_STAGE;
+    return s > kHaloMaxBStages ? kHaloMaxBStages : s;
   }
+};
+
+struct HaloGeom {
+  int wb;                 // halo block width in pixels (tw + 2)
+  int hr[2], hc[2];       // tile-relative origin (row, column) of the two 16 x 8 halves
 };
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmO, const IgemmArgs p) {
+                    const __grid_constant__ CUtensorMap tmO, const IgemmArgs p, const HaloGeom geo) {
   using L = HaloSmem<BLOCK_N>;
   constexpr int NCH = BLOCK_N / 64;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
-  uint64_t* empty_bar = full_bar + kHaloMaxStages;
-  uint64_t* tmem_full = empty_bar + kHaloMaxStages;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* a_empty = a_full + kHaloAStages;
+  uint64_t* b_full = a_empty + kHaloAStages;
+  uint64_t* b_empty = b_full + kHaloMaxBStages;
+  uint64_t* tmem_full = b_empty + kHaloMaxBStages;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::TMEMPTR_OFF);
   float* ssum = reinterpret_cast<float*>(smem + L::SSUM_OFF);
   float* ssq = ssum + kHaloStatCh;
-  uint8_t* pipe = smem + L::PIPE_OFF;
+  const uint32_t a_bytes = static_cast<uint32_t>(p.a_bytes);   // halo block bytes rounded up to 1024
+  uint8_t* a_ring = smem + L::PIPE_OFF;
+  uint8_t* b_ring = a_ring + kHaloAStages * a_bytes;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n_tiles = (p.n_total + BLOCK_N - 1) / BLOCK_N;
   const int tiles_per_img = p.tiles_h * p.tiles_w;
   const long long total_tiles = static_cast<long long>(p.N) * tiles_per_img * n_tiles;
-  const int steps_per_tile = 3 * p.kchunks;                    // (channel chunk, horizontal shift)
-  const int STG = p.stages;
-  const uint32_t a_bytes = static_cast<uint32_t>(p.a_bytes);   // (th+2)*tw rows x 128 B
-  const uint32_t stage_bytes = a_bytes + 3 * L::B_TILE;
-  const int ltw = p.ltw;
+  const int BST = p.stages;
+  const uint32_t a_tx = static_cast<uint32_t>((p.th + 2) * geo.wb * 128);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmO);
-    for (int s = 0; s < STG; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
+    for (int s = 0; s < kHaloAStages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < BST; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     mbar_init(&tmem_full[0], 1);
     mbar_init(&tmem_full[1], 1);
     mbar_init(&tmem_empty[0], 8);
@@ -548,9 +558,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // =========================== TMA producer ===========================
-    if (lane == 0) {
-      uint32_t s = 0, ph = 0;
+    // =========================== TMA producer (whole warp converged) ===========================
+    {
+      uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
       for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_tile = static_cast<int>(tile % n_tiles);
         const int m_tile = static_cast<int>(tile / n_tiles);
@@ -558,52 +568,65 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int rr = m_tile - img * tiles_per_img;
         const int h0 = (rr / p.tiles_w) * p.th, w0 = (rr % p.tiles_w) * p.tw;
         const int n0 = n_tile * BLOCK_N;
-        for (int st = 0; st < steps_per_tile; ++st) {
-          const int cc = st / 3, sft = st - cc * 3;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full_bar[s], stage_bytes);
-          uint8_t* sA = pipe + s * stage_bytes;
-          uint8_t* sB = sA + a_bytes;
-          tma_load_4d(sA, &tmA, &full_bar[s], cc * 64, w0 + sft - 1, h0 - 1, img);
+        for (int cc = 0; cc < p.kchunks; ++cc) {
+          mbar_wait(&a_empty[sa], pha ^ 1);
+          mbar_arrive_expect_tx_w(&a_full[sa], a_tx);
+          tma_load_4d_w(a_ring + sa * a_bytes, &tmA, &a_full[sa], cc * 64, w0 - 1, h0 - 1, img);
+          if (++sa == kHaloAStages) { sa = 0; pha ^= 1; }
+#pragma unroll 1
+          for (int r = 0; r < 3; ++r) {
+            mbar_wait(&b_empty[sb], phb ^ 1);
+            mbar_arrive_expect_tx_w(&b_full[sb], L::B_STAGE);
+            uint8_t* sB = b_ring + sb * L::B_STAGE;
 #pragma unroll
-          for (int r = 0; r < 3; ++r)
-            tma_load_2d(sB + r * L::B_TILE, &tmB, &full_bar[s], ((r * 3 + sft) * p.kchunks + cc) * 64, n0);
-          if (++s == static_cast<uint32_t>(STG)) { s = 0; ph ^= 1; }
+            for (int sft = 0; sft < 3; ++sft)
+              tma_load_2d_w(sB + sft * L::B_TILE, &tmB, &b_full[sb], ((r * 3 + sft) * p.kchunks + cc) * 64, n0);
+            if (++sb == static_cast<uint32_t>(BST)) { sb = 0; phb ^= 1; }
+          }
         }
       }
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
-    if (lane == 0) {
+    // =========================== MMA issuer (whole warp converged) ===========================
+    {
       const uint32_t idesc = make_idesc_16(128, BLOCK_N, 0, 0, p.a_dt, p.b_dt);
-      const uint32_t row_shift = static_cast<uint32_t>(p.tw * 128) >> 4;       // one image row of the halo block
-      uint32_t s = 0, ph = 0, lt = 0;
+      const uint32_t sbo = static_cast<uint32_t>(geo.wb * 128);
+      // descriptor offsets (16-byte units) of the two halves' first pixel inside the halo block
+      const uint32_t half_off[2] = {static_cast<uint32_t>((geo.hr[0] * geo.wb + geo.hc[0]) * 8),
+                                    static_cast<uint32_t>((geo.hr[1] * geo.wb + geo.hc[1]) * 8)};
+      uint32_t sa = 0, pha = 0, sb = 0, phb = 0, lt = 0;
       for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
         const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
         mbar_wait(&tmem_empty[as], aph ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + as * (2 * BLOCK_N);
-        for (int st = 0; st < steps_per_tile; ++st) {
-          mbar_wait(&full_bar[s], ph);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(pipe + s * stage_bytes);
-          const uint64_t da0 = make_smem_desc_sw128(a_addr, 16, 1024);
-          const uint64_t db0 = make_smem_desc_sw128(a_addr + a_bytes, 16, 1024);
-#pragma unroll
+        for (int cc = 0; cc < p.kchunks; ++cc) {
+          mbar_wait(&a_full[sa], pha);
+          const uint64_t da0 = make_smem_desc_sw128(smem_u32(a_ring + sa * a_bytes), 16, sbo);
+#pragma unroll 1
           for (int r = 0; r < 3; ++r) {
+            mbar_wait(&b_full[sb], phb);
+            tc_fence_after();
+            const uint64_t db0 = make_smem_desc_sw128(smem_u32(b_ring + sb * L::B_STAGE), 16, 1024);
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
-              const uint64_t da = da0 + static_cast<uint64_t>(r * row_shift + hf * (16384 >> 4));
-              const uint64_t db = db0 + static_cast<uint64_t>(r * (L::B_TILE >> 4));
+            for (int sft = 0; sft < 3; ++sft) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(tmem_d + hf * BLOCK_N, da + 2 * k, db + 2 * k, idesc, (st > 0 || r > 0 || k > 0) ? 1u : 0u);
+              for (int hf = 0; hf < 2; ++hf) {
+                const uint64_t da = da0 + static_cast<uint64_t>(half_off[hf] + (r * geo.wb + sft) * 8);
+                const uint64_t db = db0 + static_cast<uint64_t>(sft * (L::B_TILE >> 4));
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_f16_w(tmem_d + hf * BLOCK_N, da + 2 * k, db + 2 * k, idesc,
+                             (cc > 0 || r > 0 || sft > 0 || k > 0) ? 1u : 0u);
+              }
             }
+            umma_commit_w(&b_empty[sb]);
+            if (++sb == static_cast<uint32_t>(BST)) { sb = 0; phb ^= 1; }
           }
-          umma_commit(&empty_bar[s]);
-          if (++s == static_cast<uint32_t>(STG)) { s = 0; ph ^= 1; }
+          umma_commit_w(&a_empty[sa]);        // the halo block is free once all nine taps have read it
+          if (++sa == kHaloAStages) { sa = 0; pha ^= 1; }
         }
-        umma_commit(&tmem_full[as]);
+        umma_commit_w(&tmem_full[as]);
       }
     }
   } else {
@@ -615,8 +638,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const bool elected = gw == 0 && lane == 0;
     uint8_t* stage = smem + L::STAGING_OFF + g * kStageTile;
     const int bar_id = 1 + g;
-    const int pix = g * 128 + row;
-    const int ph_rows = 128 >> ltw;                       // image rows covered by one accumulator half
+    const int my_r = geo.hr[g] + (row >> 3), my_c = geo.hc[g] + (row & 7);   // this thread's pixel inside the tile
     float2 ssv[NCH], sqv[NCH];
 #pragma unroll
     for (int j = 0; j < NCH; ++j) { ssv[j] = make_float2(0.f, 0.f); sqv[j] = make_float2(0.f, 0.f); }
@@ -637,7 +659,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         acc_n0 = n0;
       }
-      const bool valid = (h0 + (pix >> ltw) < p.H) && (w0 + (pix & (p.tw - 1)) < p.W);
+      const bool valid = (h0 + my_r < p.H) && (w0 + my_c < p.W);
       const uint32_t tmem_acc = tmem_base + as * (2 * BLOCK_N) + g * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
       mbar_wait(&tmem_full[as], aph);
       tc_fence_after();
@@ -653,8 +675,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         fence_proxy_async_smem();
         named_bar_sync(bar_id, 128);
-        if (elected && n0 + c64 * 64 < p.n_total && h0 + g * ph_rows < p.H) {
-          tma_store_4d(&tmO, stage, n0 + c64 * 64, w0, h0 + g * ph_rows, img);
+        if (elected && n0 + c64 * 64 < p.n_total && h0 + geo.hr[g] < p.H && w0 + geo.hc[g] < p.W) {
+          tma_store_4d(&tmO, stage, n0 + c64 * 64, w0 + geo.hc[g], h0 + geo.hr[g], img);
           bulk_commit();
         }
         if (p.stats != nullptr) {
@@ -854,7 +876,7 @@ static int pick_block_n(int n_total, int forced) {
 // halo kernel launcher -------------------------------------------------------------------
 template <int BLOCK_N>
 static int launch_halo_t(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const IgemmArgs& args,
-                         long long tiles, cudaStream_t stream) {
+                         const HaloGeom& geo, long long tiles, cudaStream_t stream) {
   using L = HaloSmem<BLOCK_N>;
   auto kern = conv3x3_halo_kernel<BLOCK_N>;
   static std::once_flag once;
@@ -865,17 +887,19 @@ static int launch_halo_t(const CUtensorMap& ma, const CUtensorMap& mb, const CUt
   if (attr_err != cudaSuccess) return HPRI_ERR_CUDA;
   long long grid = tiles < sm_count() ? tiles : sm_count();
   if (grid <= 0) return HPRI_ERR_ARG;
-  const size_t smem = (size_t)L::PIPE_OFF + (size_t)args.stages * L::stage_bytes(args.a_bytes) + 1024;
-  kern<<<(unsigned)grid, kThreads, smem, stream>>>(ma, mb, mo, args);
+  const size_t smem = (size_t)L::PIPE_OFF + (size_t)kHaloAStages * args.a_bytes + (size_t)args.stages * L::B_STAGE + 1024;
+  kern<<<(unsigned)grid, kThreads, smem, stream>>>(ma, mb, mo, args, geo);
   ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? HPRI_OK : HPRI_ERR_CUDA;
 }
 
-// choose tw in {8,16,32} (th = 256/tw) minimising padded pixels; returns waste fraction
+// 256-pixel tile = two 16 x 8 halves, stacked (32 x 8) or side by side (16 x 16): minimise padded pixels;
+// returns the waste fraction
 static double pick_halo_tile(int H, int W, int* th, int* tw) {
   double best = 1e30;
-  for (int w = 8; w <= 32; w *= 2) {
-    const int h = 256 / w;
+  const int cand[2][2] = {{32, 8}, {16, 16}};
+  for (auto& c : cand) {
+    const int h = c[0], w = c[1];
     const double padded = (double)((H + h - 1) / h) * h * ((W + w - 1) / w) * w;
     if (padded < best) { best = padded; *th = h; *tw = w; }
   }
@@ -939,20 +963,25 @@ extern "C" int hpri_igemm_fwd(const hpri_view_t* x, const void* wpack, int w_dty
     const int ov = conv_algo_override();
     const bool stats_ok = !stats || w_rows <= kHaloStatCh;
     const int hbn = w_rows <= 64 ? 64 : 128;
-    const int a_bytes = (hth + 2) * htw * 128;
-    const int stages = hbn == 64 ? HaloSmem<64>::stages_for(a_bytes) : HaloSmem<128>::stages_for(a_bytes);
+    const int a_bytes = ((hth + 2) * (htw + 2) * 128 + 1023) / 1024 * 1024;
+    const int stages = hbn == 64 ? HaloSmem<64>::b_stages_for(a_bytes) : HaloSmem<128>::b_stages_for(a_bytes);
     if (stats_ok && stages >= 2 && (ov == 1 || (ov < 0 && waste <= 1.0))) {
       set_tile(a, hth, htw);
       a.stages = stages; a.a_bytes = a_bytes;
+      HaloGeom geo{};
+      geo.wb = htw + 2;
+      geo.hr[0] = 0; geo.hc[0] = 0;
+      geo.hr[1] = htw == 8 ? 16 : 0; geo.hc[1] = htw == 8 ? 0 : 8;
       CUtensorMap ma, mb, mo;
       uint64_t dims[4] = {(uint64_t)x->c, (uint64_t)x->w, (uint64_t)x->h, (uint64_t)x->n};
       uint64_t str[3] = {(uint64_t)x->pix_stride * 2, (uint64_t)x->row_stride * 2, (uint64_t)x->img_stride * 2};
-      uint32_t box[4] = {64, (uint32_t)htw, (uint32_t)(hth + 2), 1};
+      uint32_t box[4] = {64, (uint32_t)(htw + 2), (uint32_t)(hth + 2), 1};
       if ((rc = make_map(&ma, x->ptr, 4, dims, str, box, x->dtype)) != HPRI_OK) return rc;
       if ((rc = map_weights(&mb, wpack, w_rows, kpad, hbn, w_dtype)) != HPRI_OK) return rc;
-      if ((rc = map_out(&mo, *y, n_store, 128 / htw, htw)) != HPRI_OK) return rc;
+      if ((rc = map_out(&mo, *y, n_store, 16, 8)) != HPRI_OK) return rc;
       const long long tiles = (long long)a.N * a.tiles_h * a.tiles_w * ((w_rows + hbn - 1) / hbn);
-      return hbn == 64 ? launch_halo_t<64>(ma, mb, mo, a, tiles, stream) : launch_halo_t<128>(ma, mb, mo, a, tiles, stream);
+      return hbn == 64 ? launch_halo_t<64>(ma, mb, mo, a, geo, tiles, stream)
+                       : launch_halo_t<128>(ma, mb, mo, a, geo, tiles, stream);
     }
   }
   int th, tw;
