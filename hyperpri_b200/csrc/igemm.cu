@@ -164,7 +164,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
   float* ssum = reinterpret_cast<float*>(smem + L::SSUM_OFF);
   float* ssq = ssum + kMaxStatCh;
 
-  const int warp = threadIdx.x >> 5;
+  // lane-0 broadcast: makes the role dispatch below provably warp-uniform, which is what lets ptxas keep the producer
+  // and MMA warps on the uniform datapath (with a plain threadIdx.x >> 5 it guards every UTCHMMA with ELECT + R2UR)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
 
   // ---------------- tile space
@@ -223,7 +225,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
   if (warp == 0) {
     // =========================== TMA producer (whole warp converged, one elected lane issues) ===========
     {
-      uint32_t it = 0;
+      const uint32_t pipe_u = uniform_u32(smem_u32(smem));
+      const uint32_t full_u = uniform_u32(smem_u32(full_bar)), empty_u = full_u + STAGES * 8;
+      uint32_t s = 0, ph = 0;
       for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int m_tile, n_tile, kb_begin, kb_end;
         decode(tile, m_tile, n_tile, kb_begin, kb_end);
@@ -235,25 +239,24 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
           h0 = (r / p.tiles_w) * p.th;
           w0 = (r % p.tiles_w) * p.tw;
         }
-        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          mbar_arrive_expect_tx_w(&full_bar[s], L::STAGE_BYTES);
-          uint8_t* sA = smem + s * L::STAGE_BYTES;
-          uint8_t* sB = sA + A_BYTES;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait_w(empty_u + s * 8, ph ^ 1);
+          const uint32_t fb = full_u + s * 8;
+          mbar_arrive_expect_tx_w(fb, L::STAGE_BYTES);
+          const uint32_t sA = pipe_u + s * L::STAGE_BYTES;
+          const uint32_t sB = sA + A_BYTES;
           if (MODE == MODE_FWD) {
             const int tap = kb / p.kchunks;
             const int cc = kb - tap * p.kchunks;
             if (p.tap_mode == TAP_UP2) {
               // ConvT dgrad: gather dy[2h+a, 2w+b]; 5-D view (c, w, a, h, n), one map per b
-              tma_load_5d_w(sA, (tap & 1) ? &tmA1 : &tmA0, &full_bar[s], cc * 64, w0, tap >> 1, h0, img);
+              tma_load_5d_w(sA, (tap & 1) ? &tmA1 : &tmA0, fb, cc * 64, w0, tap >> 1, h0, img);
             } else {
               int dh = 0, dw = 0;
               if (p.tap_mode == TAP_3X3) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
-              tma_load_4d_w(sA, &tmA0, &full_bar[s], cc * 64, w0 + dw, h0 + dh, img);
+              tma_load_4d_w(sA, &tmA0, fb, cc * 64, w0 + dw, h0 + dh, img);
             }
-            tma_load_2d_w(sB, &tmB0, &full_bar[s], kb * 64, n0);
+            tma_load_2d_w(sB, &tmB0, fb, kb * 64, n0);
           } else {
             // wgrad: k-block = one pixel tile of 128 pixels
             const int im = kb / tiles_per_img;
@@ -268,19 +271,20 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
               int dh = 0, dw = 0;
               if (p.tap_mode == TAP_3X3) { dh = tap / 3 - 1; dw = tap % 3 - 1; }
               if (q >= p.total_chunks) cc = 0x100000;   // fully out of bounds -> zero fill
-              tma_load_4d_w(sA + half * 16384, &tmA0, &full_bar[s], cc * 64, pw0 + dw, ph0 + dh, im);
+              tma_load_4d_w(sA + half * 16384, &tmA0, fb, cc * 64, pw0 + dw, ph0 + dh, im);
             }
 #pragma unroll
             for (int j = 0; j < BLOCK_N / 64; ++j) {
               if (p.tap_mode == TAP_UP2) {
                 const int ab = n0 / p.cout;
                 const int co0 = n0 - ab * p.cout;
-                tma_load_5d_w(sB + j * 16384, (ab & 1) ? &tmB1 : &tmB0, &full_bar[s], co0 + j * 64, pw0, ab >> 1, ph0, im);
+                tma_load_5d_w(sB + j * 16384, (ab & 1) ? &tmB1 : &tmB0, fb, co0 + j * 64, pw0, ab >> 1, ph0, im);
               } else {
-                tma_load_4d_w(sB + j * 16384, &tmB0, &full_bar[s], n0 + j * 64, pw0, ph0, im);
+                tma_load_4d_w(sB + j * 16384, &tmB0, fb, n0 + j * 64, pw0, ph0, im);
               }
             }
           }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -288,43 +292,39 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
     // =========================== MMA issuer (whole warp converged, one elected lane issues) ============
     {
       const uint32_t idesc = make_idesc_16(128, BLOCK_N, MODE == MODE_WGRAD, MODE == MODE_WGRAD, p.a_dt, p.b_dt);
-      uint32_t it = 0, lt = 0;
+      const uint32_t pipe_u = uniform_u32(smem_u32(smem));
+      const uint32_t full_u = uniform_u32(smem_u32(full_bar)), empty_u = full_u + STAGES * 8;
+      const uint32_t tfull_u = empty_u + STAGES * 8, tempty_u = tfull_u + 16;
+      const uint32_t tmem_u = uniform_u32(tmem_base);
+      uint32_t s = 0, ph = 0, lt = 0;
       for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         int m_tile, n_tile, kb_begin, kb_end;
         decode(tile, m_tile, n_tile, kb_begin, kb_end);
         if (kb_end <= kb_begin) continue;
         const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
         ++lt;
-        mbar_wait(&tmem_empty[as], aph ^ 1);       // epilogue has drained this accumulator buffer
+        mbar_wait_w(tempty_u + as * 8, aph ^ 1);   // epilogue has drained this accumulator buffer
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * BLOCK_N;
-        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(&full_bar[s], ph);
+        const uint32_t tmem_d = tmem_u + as * BLOCK_N;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          mbar_wait_w(full_u + s * 8, ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint32_t a_addr = pipe_u + s * L::STAGE_BYTES;
           const uint32_t b_addr = a_addr + A_BYTES;
-          uint64_t da, db;
-          uint32_t kstep;   // descriptor start-address advance (in 16 B units) per UMMA_K = 16
-          if (MODE == MODE_FWD) {
-            da = make_smem_desc_sw128(a_addr, 16, 1024);
-            db = make_smem_desc_sw128(b_addr, 16, 1024);
-            kstep = 32 >> 4;          // 16 elements along the 128 B swizzle row
-          } else {
-            da = make_smem_desc_sw128(a_addr, 16384, 1024);  // LBO: next 64-channel group, SBO: next 8 pixel rows
-            db = make_smem_desc_sw128(b_addr, 16384, 1024);
-            kstep = 2048 >> 4;        // 16 pixel rows x 128 B
-          }
+          // descriptor low words (start address >> 4, LBO) advance per UMMA_K = 16; high words are constant
+          const uint64_t d0 = MODE == MODE_FWD ? make_smem_desc_sw128(0, 16, 1024)
+                                               : make_smem_desc_sw128(0, 16384, 1024);   // wgrad: LBO = next 64-channel group
+          const uint32_t d_hi = static_cast<uint32_t>(d0 >> 32);
+          uint32_t a_lo = static_cast<uint32_t>(d0) | (a_addr >> 4), b_lo = static_cast<uint32_t>(d0) | (b_addr >> 4);
+          constexpr uint32_t kstep = MODE == MODE_FWD ? (32 >> 4) : (2048 >> 4);   // 16 elements / 16 pixel rows
           constexpr int KSTEPS = MODE == MODE_FWD ? 4 : 8;
 #pragma unroll
-          for (int k = 0; k < KSTEPS; ++k) {
-            umma_f16_w(tmem_d, da + static_cast<uint64_t>(k * kstep), db + static_cast<uint64_t>(k * kstep), idesc,
-                       (kb > kb_begin || k > 0) ? 1u : 0u);
-          }
-          umma_commit_w(&empty_bar[s]);    // frees the smem slot once these MMAs have read it
+          for (int k = 0; k < KSTEPS; ++k)
+            umma_f16_adv_w(tmem_d, a_lo, d_hi, b_lo, d_hi, idesc, (kb > kb_begin || k > 0) ? 1u : 0u, kstep, kstep);
+          umma_commit_w(empty_u + s * 8);  // frees the smem slot once these MMAs have read it
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit_w(&tmem_full[as]);     // accumulator complete
+        umma_commit_w(tfull_u + as * 8);   // accumulator complete
       }
     }
   } else {
@@ -524,9 +524,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   float* ssq = ssum + kHaloStatCh;
   const uint32_t a_bytes = static_cast<uint32_t>(p.a_bytes);   // halo block bytes rounded up to 1024
   uint8_t* a_ring = smem + L::PIPE_OFF;
-  uint8_t* b_ring = a_ring + kHaloAStages * a_bytes;
 
-  const int warp = threadIdx.x >> 5;
+  // lane-0 broadcast: makes the role dispatch below provably warp-uniform, which is what lets ptxas keep the producer
+  // and MMA warps on the uniform datapath (with a plain threadIdx.x >> 5 it guards every UTCHMMA with ELECT + R2UR)
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const int n_tiles = (p.n_total + BLOCK_N - 1) / BLOCK_N;
   const int tiles_per_img = p.tiles_h * p.tiles_w;
@@ -560,6 +561,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0) {
     // =========================== TMA producer (whole warp converged) ===========================
     {
+      const uint32_t a_ring_u = uniform_u32(smem_u32(a_ring)), b_ring_u = a_ring_u + kHaloAStages * a_bytes;
+      const uint32_t afull_u = uniform_u32(smem_u32(a_full)), aempty_u = afull_u + kHaloAStages * 8;
+      const uint32_t bfull_u = aempty_u + kHaloAStages * 8, bempty_u = bfull_u + kHaloMaxBStages * 8;
       uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
       for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_tile = static_cast<int>(tile % n_tiles);
@@ -569,18 +573,19 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int h0 = (rr / p.tiles_w) * p.th, w0 = (rr % p.tiles_w) * p.tw;
         const int n0 = n_tile * BLOCK_N;
         for (int cc = 0; cc < p.kchunks; ++cc) {
-          mbar_wait(&a_empty[sa], pha ^ 1);
-          mbar_arrive_expect_tx_w(&a_full[sa], a_tx);
-          tma_load_4d_w(a_ring + sa * a_bytes, &tmA, &a_full[sa], cc * 64, w0 - 1, h0 - 1, img);
+          mbar_wait_w(aempty_u + sa * 8, pha ^ 1);
+          mbar_arrive_expect_tx_w(afull_u + sa * 8, a_tx);
+          tma_load_4d_w(a_ring_u + sa * a_bytes, &tmA, afull_u + sa * 8, cc * 64, w0 - 1, h0 - 1, img);
           if (++sa == kHaloAStages) { sa = 0; pha ^= 1; }
 #pragma unroll 1
           for (int r = 0; r < 3; ++r) {
-            mbar_wait(&b_empty[sb], phb ^ 1);
-            mbar_arrive_expect_tx_w(&b_full[sb], L::B_STAGE);
-            uint8_t* sB = b_ring + sb * L::B_STAGE;
+            mbar_wait_w(bempty_u + sb * 8, phb ^ 1);
+            const uint32_t fb = bfull_u + sb * 8;
+            mbar_arrive_expect_tx_w(fb, L::B_STAGE);
+            const uint32_t sB = b_ring_u + sb * L::B_STAGE;
 #pragma unroll
             for (int sft = 0; sft < 3; ++sft)
-              tma_load_2d_w(sB + sft * L::B_TILE, &tmB, &b_full[sb], ((r * 3 + sft) * p.kchunks + cc) * 64, n0);
+              tma_load_2d_w(sB + sft * L::B_TILE, &tmB, fb, ((r * 3 + sft) * p.kchunks + cc) * 64, n0);
             if (++sb == static_cast<uint32_t>(BST)) { sb = 0; phb ^= 1; }
           }
         }
@@ -591,42 +596,56 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     {
       const uint32_t idesc = make_idesc_16(128, BLOCK_N, 0, 0, p.a_dt, p.b_dt);
       const uint32_t sbo = static_cast<uint32_t>(geo.wb * 128);
+      const uint32_t a_ring_u = uniform_u32(smem_u32(a_ring)), b_ring_u = a_ring_u + kHaloAStages * a_bytes;
+      const uint32_t afull_u = uniform_u32(smem_u32(a_full)), aempty_u = afull_u + kHaloAStages * 8;
+      const uint32_t bfull_u = aempty_u + kHaloAStages * 8, bempty_u = bfull_u + kHaloMaxBStages * 8;
+      const uint32_t tfull_u = bempty_u + kHaloMaxBStages * 8, tempty_u = tfull_u + 16;
+      const uint32_t tmem_u = uniform_u32(tmem_base);
       // descriptor offsets (16-byte units) of the two halves' first pixel inside the halo block
-      const uint32_t half_off[2] = {static_cast<uint32_t>((geo.hr[0] * geo.wb + geo.hc[0]) * 8),
-                                    static_cast<uint32_t>((geo.hr[1] * geo.wb + geo.hc[1]) * 8)};
+      const uint32_t half_off0 = static_cast<uint32_t>((geo.hr[0] * geo.wb + geo.hc[0]) * 8);
+      const uint32_t half_off1 = static_cast<uint32_t>((geo.hr[1] * geo.wb + geo.hc[1]) * 8);
+      const uint32_t half_d = half_off1 - half_off0;
+      const uint64_t dA = make_smem_desc_sw128(0, 16, sbo), dB = make_smem_desc_sw128(0, 16, 1024);
+      const uint32_t a_hi = static_cast<uint32_t>(dA >> 32), b_hi = static_cast<uint32_t>(dB >> 32);
       uint32_t sa = 0, pha = 0, sb = 0, phb = 0, lt = 0;
       for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
         const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
-        mbar_wait(&tmem_empty[as], aph ^ 1);
+        mbar_wait_w(tempty_u + as * 8, aph ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + as * (2 * BLOCK_N);
+        const uint32_t tmem_d = tmem_u + as * (2 * BLOCK_N);
         for (int cc = 0; cc < p.kchunks; ++cc) {
-          mbar_wait(&a_full[sa], pha);
-          const uint64_t da0 = make_smem_desc_sw128(smem_u32(a_ring + sa * a_bytes), 16, sbo);
+          mbar_wait_w(afull_u + sa * 8, pha);
+          const uint32_t a_lo0 = static_cast<uint32_t>(dA) | ((a_ring_u + sa * a_bytes) >> 4);
 #pragma unroll 1
           for (int r = 0; r < 3; ++r) {
-            mbar_wait(&b_full[sb], phb);
+            mbar_wait_w(bfull_u + sb * 8, phb);
             tc_fence_after();
-            const uint64_t db0 = make_smem_desc_sw128(smem_u32(b_ring + sb * L::B_STAGE), 16, 1024);
+            // running descriptors: MMAs go (shift, half, k); A jumps between the halves, B between the shift tiles
+            uint32_t a_lo = a_lo0 + half_off0 + static_cast<uint32_t>(r * geo.wb * 8);
+            uint32_t b_lo = static_cast<uint32_t>(dB) | ((b_ring_u + sb * L::B_STAGE) >> 4);
 #pragma unroll
             for (int sft = 0; sft < 3; ++sft) {
 #pragma unroll
               for (int hf = 0; hf < 2; ++hf) {
-                const uint64_t da = da0 + static_cast<uint64_t>(half_off[hf] + (r * geo.wb + sft) * 8);
-                const uint64_t db = db0 + static_cast<uint64_t>(sft * (L::B_TILE >> 4));
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_f16_w(tmem_d + hf * BLOCK_N, da + 2 * k, db + 2 * k, idesc,
-                             (cc > 0 || r > 0 || sft > 0 || k > 0) ? 1u : 0u);
+                for (int k = 0; k < 4; ++k) {
+                  uint32_t da = 2, db = 2;
+                  if (k == 3) {
+                    da = hf == 0 ? half_d - 6 : 8 - 6 - half_d;
+                    db = hf == 0 ? static_cast<uint32_t>(-6) : static_cast<uint32_t>((L::B_TILE >> 4) - 6);
+                  }
+                  umma_f16_adv_w(tmem_d + hf * BLOCK_N, a_lo, a_hi, b_lo, b_hi, idesc,
+                                 (cc > 0 || r > 0 || sft > 0 || k > 0) ? 1u : 0u, da, db);
+                }
               }
             }
-            umma_commit_w(&b_empty[sb]);
+            umma_commit_w(bempty_u + sb * 8);
             if (++sb == static_cast<uint32_t>(BST)) { sb = 0; phb ^= 1; }
           }
-          umma_commit_w(&a_empty[sa]);        // the halo block is free once all nine taps have read it
+          umma_commit_w(aempty_u + sa * 8);   // the halo block is free once all nine taps have read it
           if (++sa == kHaloAStages) { sa = 0; pha ^= 1; }
         }
-        umma_commit_w(&tmem_full[as]);
+        umma_commit_w(tfull_u + as * 8);
       }
     }
   } else {

@@ -59,45 +59,67 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 // ---------------------------------------------------------------- warp-converged single-thread issue
 // The *_w variants are called by ALL 32 lanes of a converged warp; elect.sync picks one lane (always the same one)
-// to execute the instruction.  Keeping the producer / MMA warps converged lets ptxas hold descriptors, barrier
-// addresses and loop counters in uniform registers and emit bare UTCHMMA / UTMALDG instructions; under a divergent
-// `if (lane == 0)` it wraps every one of them in an ELECT / BRA.U.ANY loop with R2UR moves (~45 issue cycles per MMA,
-// which bounded every BLOCK_N = 64 layer).
-__device__ __forceinline__ void mbar_arrive_expect_tx_w(uint64_t* bar, uint32_t bytes) {
+// to execute the instruction.  Keeping the producer / MMA warps converged -- every address derived from a lane-0
+// broadcast (uniform_u32), every loop condition a kernel parameter or a warp vote -- lets ptxas hold descriptors,
+// barrier addresses and loop counters in uniform registers and emit bare UTCHMMA / UTMALDG instructions.  Under a
+// divergent `if (lane == 0)` it wraps every one of them in an ELECT / BRA.U.ANY loop fed by R2UR moves (measured:
+// ~17 issue slots per MMA, which bounded every BLOCK_N = 64 layer at ~75 cycles per 32-cycle MMA).
+// Barriers and tiles are addressed by their 32-bit shared-window address.
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Wait executed by a converged warp: the loop condition is a warp vote, so the branch is provably uniform.
+// Bounded like mbar_wait (iteration count instead of a clock).
+__device__ __forceinline__ void mbar_wait_w(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!__all_sync(0xffffffffu, mbar_try_wait_a(bar, parity))) {
+    if (++spins > (1u << 26)) __trap();      // no printf here: a call in this loop evicts the uniform registers
+  }
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_w(uint32_t bar, uint32_t bytes) {
   asm volatile(
       "{\n\t.reg .pred q;\n\t"
       "elect.sync _|q, 0xffffffff;\n\t"
-      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(bar),
       "r"(bytes)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_2d_w(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+__device__ __forceinline__ void tma_load_2d_w(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
   asm volatile(
       "{\n\t.reg .pred q;\n\t"
       "elect.sync _|q, 0xffffffff;\n\t"
       "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}" ::"r"(
-          smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+          dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_4d_w(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+__device__ __forceinline__ void tma_load_4d_w(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
                                               int c3) {
   asm volatile(
       "{\n\t.reg .pred q;\n\t"
       "elect.sync _|q, 0xffffffff;\n\t"
       "@q cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
-      "[%2];\n\t}" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      "[%2];\n\t}" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_5d_w(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+__device__ __forceinline__ void tma_load_5d_w(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2,
                                               int c3, int c4) {
   asm volatile(
       "{\n\t.reg .pred q;\n\t"
       "elect.sync _|q, 0xffffffff;\n\t"
       "@q cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], "
-      "[%2];\n\t}" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      "[%2];\n\t}" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
 
@@ -184,11 +206,30 @@ __device__ __forceinline__ void umma_f16_w(uint32_t tmem_d, uint64_t desc_a, uin
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void umma_commit_w(uint64_t* bar) {
+// MMA with running descriptors: issues D (+)= A * B with the current 32-bit low descriptor words (start address,
+// LBO) and constant high words (SBO, version, swizzle), then advances both start addresses by da / db (16-byte
+// units) INSIDE the same volatile asm.  The next descriptor therefore cannot be precomputed early: ptxas otherwise
+// hoists all 24 descriptor pairs of an unrolled tap loop, runs out of uniform registers and shuttles them through
+// vector registers with R2UR (measured ~17 issue slots per MMA instead of ~4).
+__device__ __forceinline__ void umma_f16_adv_w(uint32_t tmem_d, uint32_t& a_lo, uint32_t a_hi, uint32_t& b_lo,
+                                               uint32_t b_hi, uint32_t idesc, uint32_t accumulate, uint32_t da,
+                                               uint32_t db) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 A, B;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 A, {%0, %2};\n\tmov.b64 B, {%1, %3};\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%4], A, B, %5, p;\n\t"
+      "add.u32 %0, %0, %7;\n\tadd.u32 %1, %1, %8;\n\t}"
+      : "+r"(a_lo), "+r"(b_lo)
+      : "r"(a_hi), "r"(b_hi), "r"(tmem_d), "r"(idesc), "r"(accumulate), "r"(da), "r"(db)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_w(uint32_t bar) {
   asm volatile(
       "{\n\t.reg .pred q;\n\t"
       "elect.sync _|q, 0xffffffff;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
       : "memory");
 }
 // Arrive on an mbarrier once every tcgen05.mma this thread issued so far has completed.
