@@ -315,12 +315,19 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
           const uint64_t d0 = MODE == MODE_FWD ? make_smem_desc_sw128(0, 16, 1024)
                                                : make_smem_desc_sw128(0, 16384, 1024);   // wgrad: LBO = next 64-channel group
           const uint32_t d_hi = static_cast<uint32_t>(d0 >> 32);
-          uint32_t a_lo = static_cast<uint32_t>(d0) | (a_addr >> 4), b_lo = static_cast<uint32_t>(d0) | (b_addr >> 4);
+          const uint32_t a_lo = static_cast<uint32_t>(d0) | (a_addr >> 4), b_lo = static_cast<uint32_t>(d0) | (b_addr >> 4);
           constexpr uint32_t kstep = MODE == MODE_FWD ? (32 >> 4) : (2048 >> 4);   // 16 elements / 16 pixel rows
-          constexpr int KSTEPS = MODE == MODE_FWD ? 4 : 8;
-#pragma unroll
-          for (int k = 0; k < KSTEPS; ++k)
-            umma_f16_adv_w(tmem_d, a_lo, d_hi, b_lo, d_hi, idesc, (kb > kb_begin || k > 0) ? 1u : 0u, kstep, kstep);
+          const uint32_t acc0 = kb > kb_begin ? 1u : 0u;
+          umma_f16_off_w<0 * kstep, 0 * kstep>(tmem_d, a_lo, d_hi, b_lo, d_hi, idesc, acc0);
+          umma_f16_off_w<1 * kstep, 1 * kstep>(tmem_d, a_lo, d_hi, b_lo, d_hi, idesc, 1u);
+          umma_f16_off_w<2 * kstep, 2 * kstep>(tmem_d, a_lo, d_hi, b_lo, d_hi, idesc, 1u);
+          umma_f16_off_w<3 * kstep, 3 * kstep>(tmem_d, a_lo, d_hi, b_lo, d_hi, idesc, 1u);
+          if (MODE == MODE_WGRAD) {
+            umma_f16_off_w<4 * kstep, 4 * kstep>(tmem_d, a_lo, d_hi, b_lo, d_hi, idesc, 1u);
+            umma_f16_off_w<5 * kstep, 5 * kstep>(tmem_d, a_lo, d_hi, b_lo, d_hi, idesc, 1u);
+            umma_f16_off_w<6 * kstep, 6 * kstep>(tmem_d, a_lo, d_hi, b_lo, d_hi, idesc, 1u);
+            umma_f16_off_w<7 * kstep, 7 * kstep>(tmem_d, a_lo, d_hi, b_lo, d_hi, idesc, 1u);
+          }
           umma_commit_w(empty_u + s * 8);  // frees the smem slot once these MMAs have read it
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
@@ -604,7 +611,6 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // descriptor offsets (16-byte units) of the two halves' first pixel inside the halo block
       const uint32_t half_off0 = static_cast<uint32_t>((geo.hr[0] * geo.wb + geo.hc[0]) * 8);
       const uint32_t half_off1 = static_cast<uint32_t>((geo.hr[1] * geo.wb + geo.hc[1]) * 8);
-      const uint32_t half_d = half_off1 - half_off0;
       const uint64_t dA = make_smem_desc_sw128(0, 16, sbo), dB = make_smem_desc_sw128(0, 16, 1024);
       const uint32_t a_hi = static_cast<uint32_t>(dA >> 32), b_hi = static_cast<uint32_t>(dB >> 32);
       uint32_t sa = 0, pha = 0, sb = 0, phb = 0, lt = 0;
@@ -620,25 +626,27 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int r = 0; r < 3; ++r) {
             mbar_wait_w(bfull_u + sb * 8, phb);
             tc_fence_after();
-            // running descriptors: MMAs go (shift, half, k); A jumps between the halves, B between the shift tiles
-            uint32_t a_lo = a_lo0 + half_off0 + static_cast<uint32_t>(r * geo.wb * 8);
-            uint32_t b_lo = static_cast<uint32_t>(dB) | ((b_ring_u + sb * L::B_STAGE) >> 4);
-#pragma unroll
-            for (int sft = 0; sft < 3; ++sft) {
-#pragma unroll
-              for (int hf = 0; hf < 2; ++hf) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  uint32_t da = 2, db = 2;
-                  if (k == 3) {
-                    da = hf == 0 ? half_d - 6 : 8 - 6 - half_d;
-                    db = hf == 0 ? static_cast<uint32_t>(-6) : static_cast<uint32_t>((L::B_TILE >> 4) - 6);
-                  }
-                  umma_f16_adv_w(tmem_d + hf * BLOCK_N, a_lo, a_hi, b_lo, b_hi, idesc,
-                                 (cc > 0 || r > 0 || sft > 0 || k > 0) ? 1u : 0u, da, db);
-                }
-              }
-            }
+            // three base descriptors per filter row (halo block row r for each half, weight stage); the horizontal
+            // shift (8 x 16 B per pixel), the weight tile of that shift and the K step are compile-time offsets
+            const uint32_t a_r = a_lo0 + static_cast<uint32_t>(r * geo.wb * 8);
+            const uint32_t aH0 = a_r + half_off0, aH1 = a_r + half_off1;
+            const uint32_t b_lo = static_cast<uint32_t>(dB) | ((b_ring_u + sb * L::B_STAGE) >> 4);
+            const uint32_t t0 = tmem_d, t1 = tmem_d + BLOCK_N;
+            const uint32_t acc0 = (cc > 0 || r > 0) ? 1u : 0u;
+            constexpr uint32_t BT = L::B_TILE >> 4;
+#define HPRI_TAP(S, ACC)                                                                        \
+            umma_f16_off_w<S * 8 + 0, S * BT + 0>(t0, aH0, a_hi, b_lo, b_hi, idesc, ACC);         \
+            umma_f16_off_w<S * 8 + 2, S * BT + 2>(t0, aH0, a_hi, b_lo, b_hi, idesc, 1u);          \
+            umma_f16_off_w<S * 8 + 4, S * BT + 4>(t0, aH0, a_hi, b_lo, b_hi, idesc, 1u);          \
+            umma_f16_off_w<S * 8 + 6, S * BT + 6>(t0, aH0, a_hi, b_lo, b_hi, idesc, 1u);          \
+            umma_f16_off_w<S * 8 + 0, S * BT + 0>(t1, aH1, a_hi, b_lo, b_hi, idesc, ACC);         \
+            umma_f16_off_w<S * 8 + 2, S * BT + 2>(t1, aH1, a_hi, b_lo, b_hi, idesc, 1u);          \
+            umma_f16_off_w<S * 8 + 4, S * BT + 4>(t1, aH1, a_hi, b_lo, b_hi, idesc, 1u);          \
+            umma_f16_off_w<S * 8 + 6, S * BT + 6>(t1, aH1, a_hi, b_lo, b_hi, idesc, 1u);
+            HPRI_TAP(0, acc0)
+            HPRI_TAP(1, 1u)
+            HPRI_TAP(2, 1u)
+#undef HPRI_TAP
             umma_commit_w(bempty_u + sb * 8);
             if (++sb == static_cast<uint32_t>(BST)) { sb = 0; phb ^= 1; }
           }

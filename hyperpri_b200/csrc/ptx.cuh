@@ -206,23 +206,22 @@ __device__ __forceinline__ void umma_f16_w(uint32_t tmem_d, uint64_t desc_a, uin
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// MMA with running descriptors: issues D (+)= A * B with the current 32-bit low descriptor words (start address,
-// LBO) and constant high words (SBO, version, swizzle), then advances both start addresses by da / db (16-byte
-// units) INSIDE the same volatile asm.  The next descriptor therefore cannot be precomputed early: ptxas otherwise
-// hoists all 24 descriptor pairs of an unrolled tap loop, runs out of uniform registers and shuttles them through
-// vector registers with R2UR (measured ~17 issue slots per MMA instead of ~4).
-__device__ __forceinline__ void umma_f16_adv_w(uint32_t tmem_d, uint32_t& a_lo, uint32_t a_hi, uint32_t& b_lo,
-                                               uint32_t b_hi, uint32_t idesc, uint32_t accumulate, uint32_t da,
-                                               uint32_t db) {
+// MMA whose descriptors are (base low word + compile-time offset), the add done INSIDE the volatile asm: nothing
+// can be precomputed early (ptxas otherwise hoists all 24 descriptor pairs of an unrolled tap loop, runs out of
+// uniform registers and shuttles them through vector registers with R2UR), and consecutive MMAs do not depend on
+// one another (a running `lo += delta` chain exposed the uniform-ALU latency twice per MMA).
+// High words (SBO, version, swizzle) are loop constants.  Offsets are in 16-byte units.
+template <uint32_t OFF_A, uint32_t OFF_B>
+__device__ __forceinline__ void umma_f16_off_w(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                               uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
-      "{\n\t.reg .pred p, q;\n\t.reg .b64 A, B;\n\t"
+      "{\n\t.reg .pred p, q;\n\t.reg .b32 la, lb;\n\t.reg .b64 A, B;\n\t"
       "setp.ne.b32 p, %6, 0;\n\t"
-      "mov.b64 A, {%0, %2};\n\tmov.b64 B, {%1, %3};\n\t"
+      "add.u32 la, %0, %7;\n\tadd.u32 lb, %1, %8;\n\t"
+      "mov.b64 A, {la, %2};\n\tmov.b64 B, {lb, %3};\n\t"
       "elect.sync _|q, 0xffffffff;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%4], A, B, %5, p;\n\t"
-      "add.u32 %0, %0, %7;\n\tadd.u32 %1, %1, %8;\n\t}"
-      : "+r"(a_lo), "+r"(b_lo)
-      : "r"(a_hi), "r"(b_hi), "r"(tmem_d), "r"(idesc), "r"(accumulate), "r"(da), "r"(db)
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%4], A, B, %5, p;\n\t}" ::"r"(a_lo),
+      "r"(b_lo), "r"(a_hi), "r"(b_hi), "r"(tmem_d), "r"(idesc), "r"(accumulate), "n"(OFF_A), "n"(OFF_B)
       : "memory");
 }
 __device__ __forceinline__ void umma_commit_w(uint32_t bar) {
