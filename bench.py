@@ -24,8 +24,10 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-GF_PER_IMG = {"CubeNET": 2910.2, "UNET": 2591.5}          # fwd+bwd GFLOP / image at 608x968
+# algorithmic GFLOP / image: (fwd+bwd, fwd only); SpectralUNET-1650 at its 608x700 patch
+GF_PER_IMG = {"CubeNET": (2910.2, 1023.8), "UNET": (2591.5, 864.5), "SpectralUNET": (77150.9, 25828.4)}
 H, W, BANDS = 608, 968, 238
+PATCH_W = {"CubeNET": 968, "UNET": 968, "SpectralUNET": 700}     # params_HyperPRI.py patch sizes
 
 
 def peaks():
@@ -86,27 +88,70 @@ class ClockSampler:
         return out
 
 
+METRIC = {"train": "train images/s (238x608x968 HSI, fwd+bwd)", "infer": "inference images/s (238x608x968 HSI, fwd)"}
+WORKLOAD = {
+    "CubeNET": "CubeNET-64 n_channels=238 (hsi 25..263), patch 608x968, batch {n} per GPU, data-parallel "
+               "(BASELINE.json configs[2])",
+    "UNET": "UNET RGB n_channels=3, patch 608x968, batch {n} per GPU (BASELINE.json configs[0] shape, on GPU)",
+    "SpectralUNET": "SpectralUNET n_channels=238, patch 608x700, spectral_bn_size=1650, batch {n} per GPU "
+                    "(BASELINE.json configs[1]; the reference's MODEL_SHARD is ZeRO-2 data parallelism)",
+}
+
+
 # ------------------------------------------------------------------------------------------- CPU arm
-def cpu_steps(model, n_img, h, w, steps, warmup):
-    """Time `steps` fwd+bwd passes of the CPU oracle on n_img x 238 x h x w; returns (sec/step list)."""
+def cpu_steps(model, n_img, h, w, steps, warmup, train=True):
+    """Time `steps` passes (fwd+loss+bwd, or eval-mode forward) of the CPU oracle on n_img x bands x h x w."""
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import hyperpri_oracle as O
     torch.set_num_threads(os.cpu_count())
-    schema = O.unet_schema(1, 1, "cube", hsi_depth=BANDS) if model == "CubeNET" else O.unet_schema(3, 1, "unet")
+    if model == "CubeNET":
+        schema, bands = O.unet_schema(1, 1, "cube", hsi_depth=BANDS), BANDS
+    elif model == "UNET":
+        schema, bands = O.unet_schema(3, 1, "unet"), 3
+    else:
+        schema, bands = O.spectral_schema(BANDS, 1, 1650), BANDS
     sd = O.synth_state_dict(schema, 0)
-    bands = BANDS if model == "CubeNET" else 3
     x = O.synth_cube(0, n_img, bands, h, w)
     x = x[:, None] if model == "CubeNET" else x
     mask = O.synth_mask(0, n_img, h, w)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        O.forward_backward(model, x, mask, sd, training=True)
+        if train:
+            O.forward_backward(model, x, mask, sd, training=True)
+        else:
+            with torch.no_grad():
+                O.bce_with_logits(O.FORWARDS[model](x, sd, False, None), mask)
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt)
     return times
+
+
+def cpu_sample(model, train, steps, warmup, budget_s):
+    """Bounded CPU sample of the same workload: one image per step, cut to a strip of rows (conv nets) or columns'
+    worth of pixels (SpectralUNET is per-pixel) so that all steps fit `budget_s`; throughput is scaled by the pixel
+    fraction.  Returns (images/s, seconds per step, description)."""
+    Wp = PATCH_W[model]
+    probe_rows = 16 if model == "SpectralUNET" else 64
+    t_probe = cpu_steps(model, 1, probe_rows, Wp, 1, 0, train)[0]
+    est_full = t_probe * H / probe_rows
+    rows = H
+    if est_full * (steps + warmup) > budget_s:
+        rows = max(probe_rows, int(H * budget_s / (est_full * (steps + warmup))) // 16 * 16)
+    times = cpu_steps(model, 1, rows, Wp, steps, warmup, train)
+    sec = sum(times) / len(times)
+    bands = 3 if model == "UNET" else BANDS
+    what = "fwd+loss+bwd, train mode" if train else "eval-mode forward + loss"
+    sample = (f"{steps} step(s) of 1 image x {bands} x {rows} x {Wp} ({rows}/{H} of the rows of one image; throughput "
+              f"scaled by pixel count), fp32 oracle, {what}")
+    return (rows / H) / sec, sec, sample
+
+
+def cpu_baseline(model, train):
+    v, _, sample = cpu_sample(model, train, 1, 0, 20.0)
+    return {"value": v, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": sample}
 
 
 def run_reference(args):
@@ -114,25 +159,16 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
-    cores = os.cpu_count()
-    # bounded sample: one image per step; shrink to a row strip if K+W full images would take too long
-    t_probe = cpu_steps(args.model, 1, 64, W, 1, 0)[0]                 # 64-row strip probe
-    est_full = t_probe * H / 64.0
-    budget = 150.0
-    rows = H
-    if est_full * (args.steps + args.warmup) > budget:
-        rows = max(64, int(H * budget / (est_full * (args.steps + args.warmup))) // 16 * 16)
-    times = cpu_steps(args.model, 1, rows, W, args.steps, args.warmup)
-    sec = sum(times) / len(times)
-    img_s = (rows / H) / sec
-    sample = f"1 image x {BANDS} x {rows} x {W} per step (rows/{H} of an image, throughput scaled by pixel count), fp32, train mode"
+    train = args.mode == "train"
+    img_s, sec, sample = cpu_sample(args.model, train, args.steps, args.warmup, 150.0)
     line = {
-        "impl": "reference", "metric": "train images/s (238x608x968 HSI, fwd+bwd)", "value": img_s, "unit": "images/s",
+        "impl": "reference", "metric": METRIC[args.mode], "value": img_s, "unit": "images/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.model}-64 fwd+loss+bwd, CPU, reference arithmetic (oracle port; the reference is "
-                               "pure PyTorch and cannot travel to the GPU box)", "threads": torch.get_num_threads()},
-        "cpu_baseline": {"value": img_s, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD[args.model].format(n=1) + " -- CPU, reference arithmetic (oracle port: the "
+                               "reference is pure PyTorch + Lightning and cannot be installed offline or travel to "
+                               "the GPU box)", "threads": torch.get_num_threads(), "mode": args.mode},
+        "cpu_baseline": {"value": img_s, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
         "e2e": {"value": img_s, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -146,8 +182,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--model", default="CubeNET", choices=["CubeNET", "UNET"])
+    ap.add_argument("--model", default="CubeNET", choices=["CubeNET", "UNET", "SpectralUNET"])
     ap.add_argument("--batch", type=int, default=2)
+    ap.add_argument("--mode", default="train", choices=["train", "infer"],
+                    help="train: fwd+loss+bwd (headline); infer: eval-mode forward only (kfold_validate-style sweep)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--breakdown", default=None, help="write a per-kernel time breakdown JSON here")
@@ -158,7 +196,7 @@ def main():
     import torch
     import torch.distributed as dist
     from hyperpri_b200 import _lib, ops, parallel
-    from hyperpri_b200.src.Experiments.models import CubeNET, UNet
+    from hyperpri_b200.src.Experiments.models import CubeNET, SpectralUNET, UNet
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -173,30 +211,31 @@ def main():
 
     torch.manual_seed(1234 + rank)
     n = args.batch
+    train = args.mode == "train"
+    Wp = PATCH_W[args.model]
     if args.model == "CubeNET":
-        net = CubeNET(BANDS, 1, first_depth=64, bilinear=False).to(dev).train()
-        x = torch.rand((n, 1, BANDS, H, W), device=dev)
+        net = CubeNET(BANDS, 1, first_depth=64, bilinear=False).to(dev)
+        x = torch.rand((n, 1, BANDS, H, Wp), device=dev)
+    elif args.model == "UNET":
+        net = UNet(3, 1, bilinear=False).to(dev)
+        x = torch.rand((n, 3, H, Wp), device=dev)
     else:
-        net = UNet(3, 1, bilinear=False).to(dev).train()
-        x = torch.rand((n, 3, H, W), device=dev)
-    mask = (torch.rand((n, 1, H, W), device=dev) > 0.95).float()
+        net = SpectralUNET(BANDS, 1, bn_feats=1650).to(dev)
+        x = torch.rand((n, BANDS, H, Wp), device=dev)
+    net.train(train)
+    mask = (torch.rand((n, 1, H, Wp), device=dev) > 0.95).float()
     eng = net._get_engine(dev)
     red = parallel.attach(eng)
     gscale = red.grad_scale()
 
-    def invalidate():
-        for grp in list(eng.enc) + list(eng.dec.values()):
-            for L in grp:
-                L.pp.key = None
-        for u in eng.up.values():
-            u.key = None
-
     def step():
-        invalidate()                                   # weights change every optimizer step: re-pack inside the step
-        logits = eng.forward(x, True)
-        _, dlogit, _ = eng.loss_and_dlogit(logits, mask, grad_scale=gscale)
-        eng.backward(dlogit, prescaled=True)
-        red.finish()
+        if train:
+            eng.invalidate_packed()                    # weights change every optimizer step: re-pack inside the step
+        logits = eng.forward(x, train)
+        if train:
+            _, dlogit, _ = eng.loss_and_dlogit(logits, mask, grad_scale=gscale)
+            eng.backward(dlogit, prescaled=True)
+            red.finish()
 
     def sync():
         if world > 1:
@@ -246,9 +285,10 @@ def main():
     tensor_launches = sum(v[1] for k, v in per.items() if k in ops.TENSOR_KERNELS) // prof_steps
     all_ms = sum(v[0] for v in per.values())
     peak_tf, peak_gbs, peak_src = peaks()
-    flops_step = GF_PER_IMG[args.model] * 1e9 * n
+    flops_step = GF_PER_IMG[args.model][0 if train else 1] * 1e9 * n
     achieved = flops_step / (tensor_ms / 1e3) / 1e12 if tensor_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "kernel": "igemm_kernel<BLOCK_N,STAGES,MODE> (tcgen05 implicit GEMM: conv3x3/convT fwd, dgrad, wgrad)",
+    roofline = {"bound": "tensor", "kernel": "conv3x3_halo_kernel<BLOCK_N> + igemm_kernel<BLOCK_N,STAGES,MODE> (tcgen05 implicit GEMM family: every "
+                          "conv3x3 / ConvTranspose / Linear fwd, dgrad and wgrad launch of the step)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
                 "peak_source": peak_src, "flops_per_step": flops_step, "kernel_ms_per_step": tensor_ms,
                 "launches_per_step": tensor_launches, "share_of_step": tensor_ms / all_ms if all_ms else None}
@@ -284,11 +324,15 @@ def main():
             b = i % 2
             prefetch(i + 1)                         # next step's H2D overlaps this step's compute
             torch.cuda.current_stream().wait_event(ready[b])
-            net.zero_grad(set_to_none=True)
-            logits = net(xd[b])
-            loss = crit(logits, md[b])
-            loss.backward()
-            red.finish()
+            if train:
+                net.zero_grad(set_to_none=True)
+                logits = net(xd[b])
+                loss = crit(logits, md[b])
+                loss.backward()
+                red.finish()
+            else:
+                with torch.no_grad():
+                    loss = crit(net(xd[b]), md[b])
             consumed[b].record()
             return loss.item()                      # D2H read of the step's result
 
@@ -312,21 +356,19 @@ def main():
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        t = cpu_steps(args.model, 1, H, W, 1, 0)[0]
-        cpu_base = {"value": 1.0 / t, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
-                    "sample": f"1 step of 1 x {BANDS} x {H} x {W} (one full image), fp32 oracle fwd+loss+bwd, no warm-up"}
+        cpu_base = cpu_baseline(args.model, train)
 
     if rank == 0:
         line = {
-            "metric": "train images/s (238x608x968 HSI, fwd+bwd)", "value": value, "unit": "images/s", "n_gpus": world,
+            "metric": METRIC[args.mode], "value": value, "unit": "images/s", "n_gpus": world,
             "steps": args.steps, "warmup": W_, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f16 activations / bf16 gradients, f32 accumulate (tcgen05 kind::f16)",
+            "vs_baseline": None, "dtype": "f16 (activations, weights, loss-scaled gradients), f32 accumulate (tcgen05 kind::f16)",
             "data": "synthetic",
-            "config": {"workload": f"{args.model}-64 n_channels=238 (hsi 25..263), patch 608x968, batch {n} per GPU, "
-                                   "data-parallel (BASELINE.json configs[2])",
-                       "global_batch": n * world, "parallelism": f"dp{world}",
-                       "l2": "inputs larger than L2 (1.1 GB fp32 cube + >3 GB activations per step); no explicit flush",
-                       "timed_region": "weight re-pack + ingest + forward + BCE + backward + grad all-reduce"},
+            "config": {"workload": WORKLOAD[args.model].format(n=n),
+                       "global_batch": n * world, "parallelism": f"dp{world}", "mode": args.mode,
+                       "l2": "inputs larger than L2 (>= 0.8 GB fp32 cube + > 3 GB activations per step); no explicit flush",
+                       "timed_region": ("weight re-pack + ingest + forward + BCE + backward + grad all-reduce" if train
+                                        else "ingest + eval-mode forward (running statistics)")},
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_base, "clocks": clocks,
         }
         print(json.dumps(line))

@@ -328,6 +328,40 @@ bn_relu_apply_k(V x, const float* __restrict__ scale, const float* __restrict__ 
   }
 }
 
+// "flat" fast path (no pooled output, pixel-dense views): a thread keeps one channel group (its scale / shift stay in
+// registers) and walks pixels with four 16-byte loads in flight; no index arithmetic per element.
+__global__ void __launch_bounds__(256)
+bn_relu_apply_flat_k(const uint16_t* __restrict__ x, long long sx, int xdt, uint16_t* __restrict__ y, long long sy,
+                     int ydt, int C, long long npix, const float* __restrict__ scale, const float* __restrict__ shift,
+                     int slots, int CG) {
+  const int cg = threadIdx.x % CG, slot = threadIdx.x / CG;
+  if (slot >= slots) return;
+  const int c0 = cg * 8;
+  float sc[8], sh[8];
+  ld8v(scale, c0, C, sc);
+  ld8v(shift, c0, C, sh);
+  const long long stride = (long long)gridDim.x * slots;
+  for (long long p0 = (long long)blockIdx.x * slots + slot; p0 < npix; p0 += 4 * stride) {
+    uint4 xr[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long pp = p0 + u * stride;
+      xr[u] = make_uint4(0, 0, 0, 0);
+      if (pp < npix) xr[u] = __ldg(reinterpret_cast<const uint4*>(x + pp * sx + c0));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long pp = p0 + u * stride;
+      if (pp >= npix) break;
+      float f[8];
+      unpack8(xr[u], f, xdt);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = fmaxf(fmaf(f[k], sc[k], sh[k]), 0.f);
+      *reinterpret_cast<uint4*>(y + pp * sy + c0) = pack8(f, ydt);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ backward of relu(bn(x)) (+pool, +head)
 // One thread = one 2x2 pixel window x 8 channels.  All 16-byte loads of the window are issued first
 // (up to 9 in flight per thread), then channels are processed pairwise from the packed words.  The
@@ -999,7 +1033,16 @@ extern "C" int hpri_bn_relu_apply(const hpri_view_t* x, const float* scale, cons
   if (!scale || !shift || x->n != y->n || x->h != y->h || x->w != y->w || x->c != y->c) return HPRI_ERR_ARG;
   if (pooled && (pooled->n != x->n || pooled->h != x->h / 2 || pooled->w != x->w / 2 || pooled->c != x->c))
     return HPRI_ERR_ARG;
-  const long long total = (long long)x->n * ((x->h + 1) / 2) * ((x->w + 1) / 2) * ((x->c + 7) / 8);
+  const int CG = (x->c + 7) / 8;
+  if (!pooled && CG <= 256 && pixel_dense(x) && pixel_dense(y)) {
+    const int slots = 256 / CG;
+    const long long npix = (long long)x->n * x->h * x->w;
+    bn_relu_apply_flat_k<<<grid_for(npix, slots * 8, 148 * 8), 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const uint16_t*>(x->ptr), x->pix_stride, x->dtype, static_cast<uint16_t*>(y->ptr), y->pix_stride,
+        y->dtype, x->c, npix, scale, shift, slots, CG);
+    return last_err();
+  }
+  const long long total = (long long)x->n * ((x->h + 1) / 2) * ((x->w + 1) / 2) * CG;
   bn_relu_apply_k<<<grid_for(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(mk(x), scale, shift, mk(y),
                                                                                   mk(pooled));
   return last_err();

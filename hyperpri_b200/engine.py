@@ -91,6 +91,11 @@ class _EngineBase:
     def _gw_buffers(self):
         raise NotImplementedError
 
+    def invalidate_packed(self):
+        """Force a re-pack of every 16-bit weight operand at the next forward (what an optimizer step causes)."""
+        for pp in self._packed_params():
+            pp.key = None
+
     def _begin_backward(self):
         """The packed weight-gradient buffers are accumulated into by split-K launches and reset to zero by the
         unpack kernels, so they are clean at the start of every backward unless the previous one was interrupted."""
@@ -395,6 +400,9 @@ class UNetEngine(_EngineBase):
     def _gw_buffers(self):
         return [L.gw for grp in list(self.enc) + list(self.dec.values()) for L in grp] + list(self.up_gw.values())
 
+    def _packed_params(self):
+        return [L.pp for grp in list(self.enc) + list(self.dec.values()) for L in grp] + list(self.up.values())
+
 
 def _first_spec(true_cin: int, cin_pad: int) -> WeightSpec:
     """First conv: the parameter has `true_cin` input channels, the activation view `cin_pad`."""
@@ -411,6 +419,10 @@ class SpectralEngine(_EngineBase):
 
     def __init__(self, params: Dict[str, torch.Tensor], hsi_depth: int, feats: int, device):
         self.P, self.D, self.F, self.dev = params, hsi_depth, feats, device
+        # N-tile of the forward / dgrad GEMMs: 256-column tcgen05.mma tiles are tensor-pipe bound (128 cycles per MMA
+        # against 96 of operand fetch) while 128-column ones sit on the shared-memory operand bandwidth; 1650 features
+        # are 6.45 such tiles (7 with the ragged last one), measured 15 % faster than 13 tiles of 128
+        self.bn_tile = 256
         self.Fp = kpad(feats)
         self.Dp = (hsi_depth + 7) // 8 * 8
         d = device
@@ -440,6 +452,9 @@ class SpectralEngine(_EngineBase):
 
     def _gw_buffers(self):
         return [L.gw for L in self.L.values()]
+
+    def _packed_params(self):
+        return [L.pp for L in self.L.values()]
 
     def _workspace(self, n, r, c):
         key = (n, r, c)
@@ -522,7 +537,7 @@ class SpectralEngine(_EngineBase):
                 raw = im["raw_" + nm]
                 scale, shift, smean, sinv = im["bn"][nm]
                 ops.igemm_fwd(src, L.pp.fwd, F, 1, raw, Fp, stats=L.stats if training else None,
-                              x_c=(self.D if nm == "tail" else None))
+                              x_c=(self.D if nm == "tail" else None), block_n=self.bn_tile)
                 ops.bn_finalize(L.stats, m, P[nm + ".1.weight"], P[nm + ".1.bias"], P[nm + ".0.bias"],
                                 P[nm + ".1.running_mean"], P[nm + ".1.running_var"],
                                 P[nm + ".1.num_batches_tracked"], training, scale, shift, smean, sinv, F)
@@ -579,7 +594,7 @@ class SpectralEngine(_EngineBase):
                     if L.pp.spec.split:
                         ops.igemm_fwd(R, L.dgr_cat, 2 * Fp, 1, dx_dst, 2 * Fp, x_c=F, accumulate=acc)
                     else:
-                        ops.igemm_fwd(R, L.pp.dgr, F, 1, dx_dst, Fp, x_c=F, accumulate=acc)
+                        ops.igemm_fwd(R, L.pp.dgr, F, 1, dx_dst, Fp, x_c=F, accumulate=acc, block_n=self.bn_tile)
             dwo_acc.add_(self.dw_outc)
             first_img = False
         for nm, L in self.L.items():

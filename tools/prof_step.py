@@ -26,11 +26,7 @@ def main():
     eng = net._get_engine(dev)
 
     def step():
-        for grp in list(eng.enc) + list(eng.dec.values()):
-            for L in grp:
-                L.pp.key = None
-        for u in eng.up.values():
-            u.key = None
+        eng.invalidate_packed()
         logits = eng.forward(x, True)
         _, dlogit, _ = eng.loss_and_dlogit(logits, mask)
         eng.backward(dlogit, prescaled=True)
