@@ -40,7 +40,9 @@ def peaks():
 
 
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi polled every 10 ms from before the warm-up; samples are attributed to the timed region by their
+    timestamp (the region is ~0.1-0.2 s, shorter than nvidia-smi's start-up)."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -51,12 +53,13 @@ class ClockSampler:
         try:
             self.f = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.idx), "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+                                          "-i", str(self.idx), "-lms", "10"], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
-    def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+    def stop(self, t_begin=None, t_end=None):
+        import datetime
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -65,22 +68,31 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         self.f.close()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in open(self.path):
-            parts = [s.strip() for s in line.split(",")]
-            if len(parts) < 8:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
                 continue
             try:
-                sm.append(float(parts[1])); mx.append(float(parts[2]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(parts[2]), float(parts[3]), float(parts[4]), parts[5:9]))
             except ValueError:
                 continue
-            for nm, v in zip(names, parts[4:8]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        if sm:
-            sm.sort()
-            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        sel, window = rows, "warm-up + timed region"
+        if t_begin is not None:
+            inside = [r for r in rows if t_begin <= r[0] <= t_end]
+            if inside:
+                sel, window = inside, "timed region"
+        if sel:
+            sm = sorted(r[1] for r in sel)
+            reasons = set()
+            for r in sel:
+                for nm, v in zip(names, r[4]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(r[2] for r in sel), "reasons": sorted(reasons),
+                   "samples": len(sel), "window": window, "power_w_max": max(r[3] for r in sel)}
         try:
             os.remove(self.path)
         except OSError:
@@ -150,7 +162,7 @@ def cpu_sample(model, train, steps, warmup, budget_s):
 
 
 def cpu_baseline(model, train):
-    v, _, sample = cpu_sample(model, train, 1, 0, 20.0)
+    v, _, sample = cpu_sample(model, train, 3, 1, 25.0)
     return {"value": v, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": sample}
 
 
@@ -242,22 +254,25 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(W_):
-        step()
-    sync()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        time.sleep(0.3)                      # nvidia-smi start-up
+    for _ in range(W_):
+        step()
+    sync()
     l0 = _lib.lib().hpri_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync()
+    t_begin = time.time()
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     sync()
+    t_end = time.time()
     launches = _lib.lib().hpri_launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -301,12 +316,12 @@ def main():
                                               per_launch[len(per_launch) // prof_steps:]]}, f, indent=1)
 
     # ---------------- end to end through the public API with host inputs
-    e2e = None
-    if not args.no_e2e:
+    def run_e2e(host_dtype):
+        """nn.Module API, pinned host cube + mask copied H2D every step (double-buffered copy stream), loss read back."""
         crit = torch.nn.BCEWithLogitsLoss()
-        xh = [torch.rand(x.shape).pin_memory() for _ in range(2)]
+        xh = [torch.rand(x.shape).to(host_dtype).pin_memory() for _ in range(2)]
         mh = [(torch.rand(mask.shape) > 0.95).float().pin_memory() for _ in range(2)]
-        xd = [torch.empty_like(x) for _ in range(2)]
+        xd = [torch.empty(x.shape, dtype=host_dtype, device=dev) for _ in range(2)]
         md = [torch.empty_like(mask) for _ in range(2)]
         copy_stream = torch.cuda.Stream()
         ready = [torch.cuda.Event() for _ in range(2)]
@@ -350,9 +365,19 @@ def main():
         dt = torch.tensor([time.perf_counter() - t0], device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": n * world * args.steps / dt.item(), "unit": "images/s",
-               "h2d_bytes_per_step": x.numel() * 4 + mask.numel() * 4, "d2h_bytes_per_step": 4,
-               "ms_per_step": dt.item() / args.steps * 1e3}
+        del xh, mh, xd, md
+        return {"value": n * world * args.steps / dt.item(), "unit": "images/s",
+                "h2d_bytes_per_step": x.numel() * xh_bytes[host_dtype] + mask.numel() * 4, "d2h_bytes_per_step": 4,
+                "ms_per_step": dt.item() / args.steps * 1e3}
+
+    xh_bytes = {torch.float32: 4, torch.float16: 2}
+    e2e = e2e16 = None
+    if not args.no_e2e:
+        e2e = run_e2e(torch.float32)                # the reference data loader's format (dataset.py:270: float32 cube)
+        e2e["host_format"] = "fp32 cube (reference dataset format); PCIe-bound: see h2d_bytes_per_step / ms_per_step"
+        if args.model != "UNET":
+            e2e16 = run_e2e(torch.float16)          # cube converted to fp16 by the loader before the copy (same result)
+            e2e16["host_format"] = "fp16 cube (HyperpriDataset(host_dtype=float16)); bit-identical network input"
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -369,7 +394,7 @@ def main():
                        "l2": "inputs larger than L2 (>= 0.8 GB fp32 cube + > 3 GB activations per step); no explicit flush",
                        "timed_region": ("weight re-pack + ingest + forward + BCE + backward + grad all-reduce" if train
                                         else "ingest + eval-mode forward (running statistics)")},
-            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_base, "clocks": clocks,
+            "e2e": e2e, "e2e_fp16_host": e2e16, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_base, "clocks": clocks,
         }
         print(json.dumps(line))
     if world > 1:

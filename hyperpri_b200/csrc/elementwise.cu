@@ -176,56 +176,74 @@ unpack_conv3x3_k(float* __restrict__ g, int Cout, int Cin, int kcf, float* __res
 // ------------------------------------------------------------------ ingest
 // One block = 64 consecutive pixels of one output row, all bands.  Band-major coalesced fp32 reads
 // (128 B per warp request), transposed through shared memory, pixel-major coalesced bf16 writes.
+__device__ __forceinline__ float ld_src(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ld_src(const __half* p) { return __half2float(__ldg(p)); }
+
+template <typename T>
 __global__ void __launch_bounds__(256)
-hsi_ingest_k(const float* __restrict__ src, int bands_total, int H, int W, int lo, int nb, int i0, int j0, int h,
+hsi_ingest_k(const T* __restrict__ src, int bands_total, int H, int W, int lo, int nb, int i0, int j0, int h,
              int w, int flip_h, int flip_w, float scale, const float* __restrict__ bmean,
              const float* __restrict__ bstd, uint16_t* __restrict__ dst, int dt, int c_pad) {
   extern __shared__ uint32_t tile_w[];          // [64][c_pad/2 + 1] words (odd stride -> conflict-free)
   const int wstride = c_pad / 2 + 1;
-  uint16_t* tile = reinterpret_cast<uint16_t*>(tile_w);
   const int xt = blockIdx.x, y = blockIdx.y, n = blockIdx.z;
   const int x0 = xt * 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sy = i0 + (flip_h ? h - 1 - y : y);
-  const float* img = src + ((long long)n * bands_total + lo) * H * W + (long long)sy * W;
-  // bands are walked five at a time per warp: ten independent 128-byte row segments in flight per thread
+  const T* img = src + ((long long)n * bands_total + lo) * H * W + (long long)sy * W;
+  // a warp takes band PAIRS (2j, 2j+1) so that one 32-bit shared-memory word carries both; three pairs are walked
+  // at a time: twelve independent 128-byte row segments in flight per thread
   const int xa = x0 + lane, xb = x0 + lane + 32;
   const int ca = j0 + (flip_w ? w - 1 - xa : xa), cb = j0 + (flip_w ? w - 1 - xb : xb);
   const bool ina = xa < w, inb = xb < w;
-  constexpr int UB = 5;
-  for (int b0 = warp; b0 < c_pad; b0 += 8 * UB) {
-    float v0[UB], v1[UB];
+  const int npairs = c_pad / 2;
+  constexpr int UB = 3;
+  for (int j0p = warp; j0p < npairs; j0p += 8 * UB) {
+    float v[UB][4];
 #pragma unroll
     for (int u = 0; u < UB; ++u) {
-      const int b = b0 + 8 * u;
-      v0[u] = 0.f; v1[u] = 0.f;
-      if (b < nb) {
-        const float* row = img + (long long)b * H * W;
-        if (ina) v0[u] = __ldg(row + ca);
-        if (inb) v1[u] = __ldg(row + cb);
+      const int b = 2 * (j0p + 8 * u);
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        v[u][2 * e] = 0.f; v[u][2 * e + 1] = 0.f;
+        if (b + e < nb) {
+          const T* row = img + (long long)(b + e) * H * W;
+          if (ina) v[u][2 * e] = ld_src(row + ca);
+          if (inb) v[u][2 * e + 1] = ld_src(row + cb);
+        }
       }
     }
 #pragma unroll
     for (int u = 0; u < UB; ++u) {
-      const int b = b0 + 8 * u;
-      if (b >= c_pad) break;
-      float a0 = v0[u] * scale, a1 = v1[u] * scale;
-      if (bmean != nullptr && b < nb) {
-        const float m = __ldg(bmean + b), is = 1.f / __ldg(bstd + b);
-        a0 = (a0 - m) * is; a1 = (a1 - m) * is;
+      const int jp = j0p + 8 * u;
+      if (jp >= npairs) break;
+      const int b = 2 * jp;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float a0 = v[u][2 * e] * scale, a1 = v[u][2 * e + 1] * scale;
+        if (bmean != nullptr && b + e < nb) {
+          const float m = __ldg(bmean + b + e), is = 1.f / __ldg(bstd + b + e);
+          a0 = (a0 - m) * is; a1 = (a1 - m) * is;
+        }
+        if (b + e >= nb) { a0 = 0.f; a1 = 0.f; }
+        v[u][2 * e] = a0; v[u][2 * e + 1] = a1;
       }
-      if (b >= nb) { a0 = 0.f; a1 = 0.f; }
-      tile[(lane) * (2 * wstride) + b] = cvt16(a0, dt);
-      tile[(lane + 32) * (2 * wstride) + b] = cvt16(a1, dt);
+      tile_w[lane * wstride + jp] = pack2(v[u][0], v[u][2], dt);            // pixel xa: bands b, b+1
+      tile_w[(lane + 32) * wstride + jp] = pack2(v[u][1], v[u][3], dt);     // pixel xb
     }
   }
   __syncthreads();
   const int wpp = c_pad / 2;                    // words per pixel
   const int npix = min(64, w - x0);
   uint32_t* out = reinterpret_cast<uint32_t*>(dst + (((long long)n * h + y) * w + x0) * c_pad);
-  for (int i = threadIdx.x; i < npix * wpp; i += 256) {
-    const int px = i / wpp, k = i - px * wpp;
+  // i = px * wpp + k walks the block's contiguous output; (px, k) are advanced without divisions
+  const int total = npix * wpp;
+  int px = threadIdx.x / wpp, k = threadIdx.x - px * wpp;
+  const int dpx = 256 / wpp, dk = 256 - dpx * wpp;
+  for (int i = threadIdx.x; i < total; i += 256) {
     out[i] = tile_w[px * wstride + k];
+    px += dpx; k += dk;
+    if (k >= wpp) { k -= wpp; ++px; }
   }
 }
 
@@ -973,9 +991,10 @@ extern "C" int hpri_unpack_conv3x3(float* packed, int cout, int cin, float* dst,
   return last_err();
 }
 
-extern "C" int hpri_hsi_ingest(const float* src, int n, int bands_total, int H, int W, int lo, int hi, int i0,
-                               int j0, int h, int w, int flip_h, int flip_w, float scale, const float* band_mean,
-                               const float* band_std, void* dst, int dst_dtype, int c_pad, void* stream) {
+template <typename T>
+static int ingest_launch(const T* src, int n, int bands_total, int H, int W, int lo, int hi, int i0, int j0, int h,
+                         int w, int flip_h, int flip_w, float scale, const float* band_mean, const float* band_std,
+                         void* dst, int dst_dtype, int c_pad, void* stream) {
   if (dst_dtype != DT_BF16 && dst_dtype != DT_F16) return HPRI_ERR_ARG;
   const int nb = hi - lo;
   if (!src || !dst || n <= 0 || lo < 0 || hi > bands_total || nb <= 0 || c_pad < nb || (c_pad & 7)) return HPRI_ERR_ARG;
@@ -985,16 +1004,28 @@ extern "C" int hpri_hsi_ingest(const float* src, int n, int bands_total, int H, 
   const size_t smem = 64 * (c_pad / 2 + 1) * 4;
   static bool attr_done = false;
   if (!attr_done && smem > 48 * 1024) {
-    if (cudaFuncSetAttribute(hsi_ingest_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(hsi_ingest_k<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
       return HPRI_ERR_CUDA;
     attr_done = true;
   }
   if (smem > 100 * 1024) return HPRI_ERR_ARG;
   dim3 grid((w + 63) / 64, h, n);
-  hsi_ingest_k<<<grid, 256, smem, (cudaStream_t)stream>>>(src, bands_total, H, W, lo, nb, i0, j0, h, w, flip_h,
-                                                         flip_w, scale, band_mean, band_std, (uint16_t*)dst,
-                                                         dst_dtype, c_pad);
+  hsi_ingest_k<T><<<grid, 256, smem, (cudaStream_t)stream>>>(src, bands_total, H, W, lo, nb, i0, j0, h, w, flip_h,
+                                                            flip_w, scale, band_mean, band_std, (uint16_t*)dst,
+                                                            dst_dtype, c_pad);
   return last_err();
+}
+extern "C" int hpri_hsi_ingest(const float* src, int n, int bands_total, int H, int W, int lo, int hi, int i0,
+                               int j0, int h, int w, int flip_h, int flip_w, float scale, const float* band_mean,
+                               const float* band_std, void* dst, int dst_dtype, int c_pad, void* stream) {
+  return ingest_launch(src, n, bands_total, H, W, lo, hi, i0, j0, h, w, flip_h, flip_w, scale, band_mean, band_std,
+                       dst, dst_dtype, c_pad, stream);
+}
+extern "C" int hpri_hsi_ingest_f16(const void* src, int n, int bands_total, int H, int W, int lo, int hi, int i0,
+                                   int j0, int h, int w, int flip_h, int flip_w, float scale, const float* band_mean,
+                                   const float* band_std, void* dst, int dst_dtype, int c_pad, void* stream) {
+  return ingest_launch(static_cast<const __half*>(src), n, bands_total, H, W, lo, hi, i0, j0, h, w, flip_h, flip_w,
+                       scale, band_mean, band_std, dst, dst_dtype, c_pad, stream);
 }
 extern "C" int hpri_absmax(const float* src, long long numel, float* out_max, void* stream) {
   if (!src || !out_max || numel <= 0) return HPRI_ERR_ARG;

@@ -297,7 +297,9 @@ class UNetEngine(_EngineBase):
     def ingest(self, x: torch.Tensor, ws):
         if x.dim() == 5:                       # CubeNET: N x 1 x D x H x W  (reshape is a no-copy squeeze)
             x = x.reshape(x.shape[0], x.shape[2], x.shape[3], x.shape[4])
-        x = x.contiguous().float()
+        x = x.contiguous()
+        if x.dtype != torch.float16:          # fp16 cubes (converted by the data loader before H2D) are ingested as is
+            x = x.float()
         ops.hsi_ingest(x, 0, x.shape[1], c_pad=self.cin_pad, out=ws["x"])
 
     def forward(self, x: torch.Tensor, training: bool) -> torch.Tensor:
@@ -519,7 +521,8 @@ class SpectralEngine(_EngineBase):
     def forward(self, x: torch.Tensor, training: bool) -> torch.Tensor:
         n, dch, r, c = x.shape
         ws = self._workspace(n, r, c)
-        ops.hsi_ingest(x.contiguous().float(), 0, dch, c_pad=self.Dp, out=ws["x"])
+        x = x.contiguous()
+        ops.hsi_ingest(x if x.dtype == torch.float16 else x.float(), 0, dch, c_pad=self.Dp, out=ws["x"])
         return self.forward_ingested(ws, training)
 
     def forward_ingested(self, ws, training: bool) -> torch.Tensor:

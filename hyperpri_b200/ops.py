@@ -200,15 +200,16 @@ def igemm_wgrad(x, dy, mode, n_total, dw, block_n=0, splits=0, x_c=None, dy_c=No
 @_timed
 def hsi_ingest(src, lo, hi, crop=None, flip_h=False, flip_w=False, scale=1.0, band_mean=None, band_std=None,
                c_pad=None, out=None, dtype=None):
-    """src fp32 [N, bands, H, W] -> NHWC 16-bit [N, h, w, c_pad]."""
-    assert src.dtype == torch.float32 and src.is_contiguous() and src.dim() == 4
+    """src fp32 (or host-pre-converted fp16) [N, bands, H, W] -> NHWC 16-bit [N, h, w, c_pad]."""
+    assert src.dtype in (torch.float32, torch.float16) and src.is_contiguous() and src.dim() == 4
     n, bt, H, W = src.shape
     i0, j0, h, w = crop if crop is not None else (0, 0, H, W)
     nb = hi - lo
     c_pad = c_pad or (nb + 7) // 8 * 8
     if out is None:
         out = torch.empty((n, h, w, c_pad), dtype=dtype or ACT, device=src.device)
-    check(_lib.lib().hpri_hsi_ingest(_ptr(src), n, bt, H, W, lo, hi, i0, j0, h, w, int(flip_h), int(flip_w),
+    fn = _lib.lib().hpri_hsi_ingest if src.dtype == torch.float32 else _lib.lib().hpri_hsi_ingest_f16
+    check(fn(_ptr(src), n, bt, H, W, lo, hi, i0, j0, h, w, int(flip_h), int(flip_w),
                                      float(scale), _ptr(band_mean), _ptr(band_std), _ptr(out), _DT[out.dtype], c_pad,
                                      _stream()),
           "hpri_hsi_ingest")

@@ -23,7 +23,11 @@ class HyperpriDataset(Dataset):
 
     def __init__(self, root, mode='RGB', img_transform=None, label_transform=None, subset: list = None,
                  label_subset: list = [3], unsqueeze_img=False, hsi_lo=0, hsi_hi=0, json_file: str = None,
-                 json_verb=False):
+                 json_verb=False, host_dtype=torch.float32):
+        # host_dtype (extension, default = reference behaviour): torch.float16 makes HSI items half-precision cubes,
+        # i.e. the fp32 -> fp16 rounding the device ingest would do happens before the PCIe copy (half the bytes,
+        # bit-identical network input when no rescale / normalisation is configured).
+        self.host_dtype = host_dtype
         self.class_list = list(subset) if subset is not None else ['Peanut', 'SweetCorn']
         ls = sorted(set(label_subset)) if label_subset else [0, 3]
         if 0 not in ls:
@@ -144,6 +148,8 @@ class HyperpriDataset(Dataset):
             if img.max() > 10:
                 img = img / 255
         torch.set_rng_state(state)
+        if mode == 'hsi' and self.host_dtype != torch.float32:
+            img = img.to(self.host_dtype)
         if self.label_transform is not None:
             label = self.label_transform(label)
         label = np.array(label) * 255

@@ -91,6 +91,12 @@ int hpri_unpack_conv3x3(float* packed, int cout, int cin, float* dst, void* stre
 int hpri_hsi_ingest(const float* src, int n, int bands_total, int H, int W, int lo, int hi, int i0, int j0, int h,
                     int w, int flip_h, int flip_w, float scale, const float* band_mean, const float* band_std,
                     void* dst, int dst_dtype, int c_pad, void* stream);
+/* Same for a cube that the host already holds in IEEE half precision (src: __half [n][bands_total][H][W]): the data
+ * loader converts fp32 -> fp16 before the PCIe copy, which halves the bytes of the only host->device transfer of the
+ * step; with scale == 1 and no normalisation the network input is bit-identical to the fp32 route (same rounding). */
+int hpri_hsi_ingest_f16(const void* src, int n, int bands_total, int H, int W, int lo, int hi, int i0, int j0, int h,
+                        int w, int flip_h, int flip_w, float scale, const float* band_mean, const float* band_std,
+                        void* dst, int dst_dtype, int c_pad, void* stream);
 int hpri_absmax(const float* src, long long numel, float* out_max, void* stream);
 
 /* y = x converted between HPRI_F16 and HPRI_BF16 (tcgen05 kind::f16 requires both operands of one

@@ -253,6 +253,10 @@ def test_ingest_exact():
     ref = ((src[:, 25:263] * 255 * (1 / 255) - mean[:, None, None]) / std[:, None, None]).flip(-2)
     assert (out[..., :238].float() - ref.permute(0, 2, 3, 1)).abs().max() < 2e-2
     assert ops.absmax(src * 255).item() == (src * 255).abs().max().item()
+    # a cube the host already holds in fp16 (converted before the PCIe copy) gives bit-identical network input
+    out16 = ops.hsi_ingest(src.to(FH), 25, 263, crop=(3, 5, 12, 30), flip_w=True, c_pad=240, dtype=FH)
+    out32 = ops.hsi_ingest(src, 25, 263, crop=(3, 5, 12, 30), flip_w=True, c_pad=240, dtype=FH)
+    assert torch.equal(out16, out32)
     rgb = torch.rand((2, 3, 9, 70), device=DEV)
     out = ops.hsi_ingest(rgb, 0, 3, c_pad=8, dtype=BF)
     assert torch.equal(out[..., :3], rgb.permute(0, 2, 3, 1).to(torch.bfloat16)) and (out[..., 3:] == 0).all()
