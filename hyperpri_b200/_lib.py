@@ -35,6 +35,8 @@ SIGNATURES = {
     "hpri_unpack_grads": [_p, _p, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _f, _i, _p],
     "hpri_pack_conv3x3": [_p, _i, _i, _p, _i, _p, _i, _p],
     "hpri_unpack_conv3x3": [_p, _i, _i, _p, _p],
+    "hpri_pack_convT2x2": [_p, _i, _i, _p, _i, _p],
+    "hpri_unpack_convT2x2": [_p, _i, _i, _p, _p],
     "hpri_hsi_ingest": [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _i, _i, _p],
     "hpri_hsi_ingest_f16": [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _i, _i, _p],
     "hpri_absmax": [_p, _ll, _p, _p],

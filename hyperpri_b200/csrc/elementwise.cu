@@ -173,6 +173,50 @@ unpack_conv3x3_k(float* __restrict__ g, int Cout, int Cin, int kcf, float* __res
   }
 }
 
+// ------------------------------------------------------------------ ConvTranspose2d(k2,s2) weight <-> GEMM operand
+// W[ci][co][a][b] fp32  <->  P[(ab*Cout + co)][ci]  (ab = a*2+b; row length kc = kpad(Cin)).  A (ci, co) transpose:
+// 32 x 32 tiles through shared memory so that both sides move whole 128-byte lines.
+__global__ void __launch_bounds__(256)
+pack_convT_k(const float* __restrict__ w, int Cin, int Cout, uint16_t* __restrict__ dst, int kc, int dt) {
+  __shared__ float tile[32][129];
+  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+  for (int i = threadIdx.x; i < 32 * 128; i += 256) {
+    const int r = i >> 7, q = i & 127;                      // ci row, (co, ab) column
+    float v = 0.f;
+    if (ci0 + r < Cin && co0 + (q >> 2) < Cout) v = __ldg(w + ((long long)(ci0 + r) * Cout + co0) * 4 + q);
+    tile[r][q] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * 128; i += 256) {
+    const int l = i & 31, q = i >> 5;                        // lanes over ci; q = ab * 32 + co
+    const int ab = q >> 5, co = q & 31;
+    if (ci0 + l < Cin && co0 + co < Cout)
+      dst[((long long)ab * Cout + co0 + co) * kc + ci0 + l] = cvt16(tile[l][co * 4 + ab], dt);
+  }
+}
+// packed fp32 gradient P[(ab*Cout + co)][ci] -> W layout; the packed buffer is zeroed behind the read
+__global__ void __launch_bounds__(256)
+unpack_convT_k(float* __restrict__ g, int Cin, int Cout, int kc, float* __restrict__ dst) {
+  __shared__ float tile[32][129];
+  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+  for (int i = threadIdx.x; i < 32 * 128; i += 256) {
+    const int l = i & 31, q = i >> 5;
+    const int ab = q >> 5, co = q & 31;
+    float v = 0.f;
+    if (ci0 + l < Cin && co0 + co < Cout) {
+      float* src = g + ((long long)ab * Cout + co0 + co) * kc + ci0 + l;
+      v = *src;
+      *src = 0.f;
+    }
+    tile[l][co * 4 + ab] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * 128; i += 256) {
+    const int r = i >> 7, q = i & 127;
+    if (ci0 + r < Cin && co0 + (q >> 2) < Cout) dst[((long long)(ci0 + r) * Cout + co0) * 4 + q] = tile[r][q];
+  }
+}
+
 // ------------------------------------------------------------------ ingest
 // One block = 64 consecutive pixels of one output row, all bands.  Band-major coalesced fp32 reads
 // (128 B per warp request), transposed through shared memory, pixel-major coalesced bf16 writes.
@@ -982,6 +1026,18 @@ extern "C" int hpri_pack_conv3x3(const float* w, int cout, int cin, void* dst_fw
   pack_conv3x3_k<<<grid, 256, 0, (cudaStream_t)stream>>>(w, cout, cin, (uint16_t*)dst_fwd, (cin + 63) / 64 * 64,
                                                         fwd_dtype, (uint16_t*)dst_dgrad, (cout + 63) / 64 * 64,
                                                         dgrad_dtype);
+  return last_err();
+}
+extern "C" int hpri_pack_convT2x2(const float* w, int cin, int cout, void* dst_fwd, int fwd_dtype, void* stream) {
+  if (!w || !dst_fwd || cout <= 0 || cin <= 0) return HPRI_ERR_ARG;
+  dim3 grid((cin + 31) / 32, (cout + 31) / 32);
+  pack_convT_k<<<grid, 256, 0, (cudaStream_t)stream>>>(w, cin, cout, (uint16_t*)dst_fwd, (cin + 63) / 64 * 64, fwd_dtype);
+  return last_err();
+}
+extern "C" int hpri_unpack_convT2x2(float* packed, int cin, int cout, float* dst, void* stream) {
+  if (!packed || !dst || cout <= 0 || cin <= 0) return HPRI_ERR_ARG;
+  dim3 grid((cin + 31) / 32, (cout + 31) / 32);
+  unpack_convT_k<<<grid, 256, 0, (cudaStream_t)stream>>>(packed, cin, cout, (cin + 63) / 64 * 64, dst);
   return last_err();
 }
 extern "C" int hpri_unpack_conv3x3(float* packed, int cout, int cin, float* dst, void* stream) {

@@ -112,6 +112,17 @@ def unpack_conv3x3(packed, cout, cin, dst):
     check(_lib.lib().hpri_unpack_conv3x3(_ptr(packed), cout, cin, _ptr(dst), _stream()), "hpri_unpack_conv3x3")
 
 
+@_timed
+def pack_convT(w, cin, cout, fwd):
+    """W[ci][co][2][2] fp32 -> forward operand [4*cout, kpad(cin)] (zero-initialised once by the caller)."""
+    check(_lib.lib().hpri_pack_convT2x2(_ptr(w), cin, cout, _ptr(fwd), _DT[fwd.dtype], _stream()), "hpri_pack_convT2x2")
+
+
+@_timed
+def unpack_convT(packed, cin, cout, dst):
+    check(_lib.lib().hpri_unpack_convT2x2(_ptr(packed), cin, cout, _ptr(dst), _stream()), "hpri_unpack_convT2x2")
+
+
 class WeightSpec:
     """Index maps between a torch-layout fp32 parameter and the packed GEMM operands."""
 
@@ -143,6 +154,11 @@ class WeightSpec:
         pack_conv3x3(w, self.cout, self.cin, fwd, dgrad)
 
     def pack_fwd(self, w, out=None, dtype=None):
+        if self.kind == "convT2x2" and self.cin % 64 == 0:      # no padding columns: the tiled transpose covers all
+            if out is None:
+                out = torch.empty((4 * self.cout, kpad(self.cin)), dtype=dtype or ACT, device=w.device)
+            pack_convT(w, self.cin, self.cout, out)
+            return out
         return pack(w, out=out, dtype=dtype or ACT, **self.fwd)
 
     def pack_dgrad(self, w, out=None, dtype=None):
@@ -156,6 +172,8 @@ class WeightSpec:
         """Unpack AND reset `packed` to zero (ready for the next accumulation)."""
         if self.kind == "conv3x3" and beta == 0.0:
             return unpack_conv3x3(packed, self.cout, self.cin, dst)
+        if self.kind == "convT2x2" and beta == 0.0:
+            return unpack_convT(packed, self.cin, self.cout, dst)
         f = dict(self.fwd)
         return unpack(packed, dst, beta=beta, zero_src=True, **f)
 

@@ -83,6 +83,10 @@ int hpri_unpack_grads(float* packed, float* dst, int G, int R, int T, int C, int
 int hpri_pack_conv3x3(const float* w, int cout, int cin, void* dst_fwd, int fwd_dtype, void* dst_dgrad,
                       int dgrad_dtype, void* stream);
 int hpri_unpack_conv3x3(float* packed, int cout, int cin, float* dst, void* stream);
+/* ConvTranspose2d(k=2,s=2): W[ci][co][2][2] <-> forward operand [(a*2+b)*cout + co][kpad(ci)] (a (ci, co) transpose,
+ * tiled through shared memory); unpack zeroes the packed gradient behind the read.  Padding columns are not written. */
+int hpri_pack_convT2x2(const float* w, int cin, int cout, void* dst_fwd, int fwd_dtype, void* stream);
+int hpri_unpack_convT2x2(float* packed, int cin, int cout, float* dst, void* stream);
 
 /* ---- ingest (src/dataset.py:266-270, 284-289) -------------------------------------------
  * src: fp32 [n][bands_total][H][W]; keeps bands [lo,hi), crops the (i0,j0,h,w) window, optional

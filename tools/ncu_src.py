@@ -14,7 +14,13 @@ for h, u, v in zip(hdr, units, vals):
         print(f"{h} [{u}] = {v}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
-hdr, data = rows[1], rows[2:]
+hdr = rows[1]
+data = []
+for r in rows[2:]:                      # first kernel of the report only (sections start with a "Kernel Name" row)
+    if r and r[0] == "Kernel Name":
+        break
+    if len(r) == len(hdr):
+        data.append(r)
 ix = {h: i for i, h in enumerate(hdr)}
 stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
 tot = sum(int(r[ix["# Samples"]]) for r in data)
