@@ -738,6 +738,215 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 }
 
 // =====================================================================================
+// 3x3 weight gradient with halo reuse (the two highest resolutions, Cout = 64 / 128).
+//
+//   dW[n][(tap, ci)] += sum_pixels X[pixel + tap][ci] * dY[pixel][n]           (MN-major operands, K = pixels)
+//
+// The generic MODE_WGRAD kernel re-loads the X tile once per tap and the dY tile once per pair of channel chunks:
+// 48 KB of L2->SM traffic per 8 MMAs at N = 64, which pins those launches at 36-38 % tensor-pipe activity
+// (profiles/ncu_full_r1e_summary.csv).  Here a k-block is one 16 x 8 pixel tile: the (16+2) x (8+2) halo block of X
+// (per 64-channel chunk) and the dY tile are loaded ONCE and every tap is a descriptor start offset of
+// (r*10 + s)*128 B into the halo block; eight consecutive pixels of a tile row are one 8-row swizzle group and tile
+// rows are 10*128 B apart (SBO).  An M = 128 tile is two 64-channel groups LBO bytes apart: the two chunks of a
+// chunk pair at one tap (LBO = halo block stride), or, when the layer has a single chunk (Cin = 64), two taps of the
+// same block (LBO = their offset difference).  A CTA keeps the accumulators of up to 512 / BLOCK_N such tiles in
+// TMEM (single-buffered: a work item is a long pixel range, its epilogue runs once) and walks its share of the
+// pixel tiles (split-K), so one k-block of loads feeds 8 K-steps x up to 8 tiles of MMAs.
+// Work item = (chunk pair, tap group, split).  fp32 red.add into the packed gradient, as the generic kernel.
+// =====================================================================================
+struct WgHaloArgs {
+  int N, H, W, tiles_h, tiles_w;      // 16 x 8 pixel tiles
+  int kchunks, nblk;                  // 64-channel chunks of X; halo blocks per work item (1 or 2)
+  int units, n_tg;                    // M-tile units per chunk pair (9 taps, or 5 tap pairs when kchunks == 1); tap groups
+  int npairs, splits;
+  int n_total;                        // Cout
+  float* dw;
+  int dw_ld;
+  int a_stride, stages;               // halo block bytes rounded to 1024; pipeline depth
+  int a_dt, b_dt;
+};
+constexpr int kWgMaxStages = 6;
+constexpr int kWgBlockBytes = 18 * 10 * 128;
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1)
+wgrad3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY,
+                     const WgHaloArgs p) {
+  constexpr int B_BYTES = (BLOCK_N / 64) * 16384;     // dY tile: 128 pixels x BLOCK_N channels
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);           // [6] full, [6] empty, tmem_full, tmem_empty
+  uint64_t* empty_bar = full_bar + kWgMaxStages;
+  uint64_t* tmem_full = empty_bar + kWgMaxStages;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  uint8_t* pipe = smem + 1024;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int STG = p.stages;
+  const uint32_t stage_bytes = static_cast<uint32_t>(p.nblk * p.a_stride + B_BYTES);
+  const int tiles_per_img = p.tiles_h * p.tiles_w;
+  const long long T = static_cast<long long>(p.N) * tiles_per_img;
+  const int items_per_split = p.npairs * p.n_tg;
+  const long long total_items = static_cast<long long>(items_per_split) * p.splits;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmDY);
+    for (int s = 0; s < STG; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 8);
+    fence_mbar_init();
+    fence_proxy_async_smem();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  // work item -> (pair, first unit, unit count, k-block range)
+  auto decode = [&](long long item, int& pair, int& u0, int& nu, int& kb_begin, int& kb_end) {
+    const int split = static_cast<int>(item / items_per_split);
+    const int r = static_cast<int>(item - static_cast<long long>(split) * items_per_split);
+    pair = r / p.n_tg;
+    const int tg = r - pair * p.n_tg;
+    u0 = (p.units * tg) / p.n_tg;
+    nu = (p.units * (tg + 1)) / p.n_tg - u0;
+    kb_begin = static_cast<int>(T * split / p.splits);
+    kb_end = static_cast<int>(T * (split + 1) / p.splits);
+  };
+
+  if (warp == 0) {
+    // =========================== TMA producer (whole warp converged) ===========================
+    const uint32_t pipe_u = uniform_u32(smem_u32(pipe));
+    const uint32_t full_u = uniform_u32(smem_u32(full_bar)), empty_u = full_u + kWgMaxStages * 8;
+    uint32_t s = 0, ph = 0;
+    for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
+      int pair, u0, nu, kb_begin, kb_end;
+      decode(item, pair, u0, nu, kb_begin, kb_end);
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        const int im = kb / tiles_per_img;
+        const int r = kb - im * tiles_per_img;
+        const int h0 = (r / p.tiles_w) * 16, w0 = (r % p.tiles_w) * 8;
+        mbar_wait_w(empty_u + s * 8, ph ^ 1);
+        const uint32_t fb = full_u + s * 8;
+        mbar_arrive_expect_tx_w(fb, static_cast<uint32_t>(p.nblk * kWgBlockBytes + B_BYTES));
+        const uint32_t st = pipe_u + s * stage_bytes;
+        for (int b = 0; b < p.nblk; ++b)
+          tma_load_4d_w(st + b * p.a_stride, &tmX, fb, (2 * pair + b) * 64, w0 - 1, h0 - 1, im);
+#pragma unroll
+        for (int j = 0; j < BLOCK_N / 64; ++j)
+          tma_load_4d_w(st + p.nblk * p.a_stride + j * 16384, &tmDY, fb, j * 64, w0, h0, im);
+        if (++s == static_cast<uint32_t>(STG)) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer (whole warp converged) ===========================
+    const uint32_t idesc = make_idesc_16(128, BLOCK_N, 1, 1, p.a_dt, p.b_dt);
+    const uint32_t pipe_u = uniform_u32(smem_u32(pipe));
+    const uint32_t full_u = uniform_u32(smem_u32(full_bar)), empty_u = full_u + kWgMaxStages * 8;
+    const uint32_t tfull_u = empty_u + kWgMaxStages * 8, tempty_u = tfull_u + 8;
+    const uint32_t tmem_u = uniform_u32(tmem_base);
+    const uint64_t dA = make_smem_desc_sw128(0, 0, 1280), dB = make_smem_desc_sw128(0, 16384, 1024);
+    const uint32_t a_hi = static_cast<uint32_t>(dA >> 32), b_hi = static_cast<uint32_t>(dB >> 32);
+    uint32_t s = 0, ph = 0, lt = 0;
+    for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
+      int pair, u0, nu, kb_begin, kb_end;
+      decode(item, pair, u0, nu, kb_begin, kb_end);
+      if (kb_end <= kb_begin) continue;
+      mbar_wait_w(tempty_u, (lt & 1) ^ 1);          // the epilogue has drained the accumulators of the previous item
+      ++lt;
+      tc_fence_after();
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait_w(full_u + s * 8, ph);
+        tc_fence_after();
+        const uint32_t st = pipe_u + s * stage_bytes;
+        const uint32_t b_lo = static_cast<uint32_t>(dB) | ((st + p.nblk * p.a_stride) >> 4);
+        const uint32_t acc0 = kb > kb_begin ? 1u : 0u;
+#pragma unroll 1
+        for (int i = 0; i < nu; ++i) {
+          // start offset (rows of 128 B) of the first 64-row group and byte distance to the second one
+          int off0, lbo;
+          if (p.kchunks == 1) {
+            const int t0 = 2 * (u0 + i), t1 = t0 + 1;
+            off0 = (t0 / 3) * 10 + t0 % 3;
+            lbo = t1 < 9 ? ((t1 / 3) * 10 + t1 % 3 - off0) * 128 : 0;
+          } else {
+            const int t0 = u0 + i;
+            off0 = (t0 / 3) * 10 + t0 % 3;
+            lbo = p.a_stride;
+          }
+          const uint32_t a_lo = ((st + off0 * 128) >> 4) | (static_cast<uint32_t>(lbo >> 4) << 16);
+          const uint32_t td = tmem_u + i * BLOCK_N;
+          // K = 16 pixels per MMA = two tile rows: 2 * 1280 B of the halo block, 2 * 1024 B of the dY tile
+          umma_f16_off_w<0 * 160, 0 * 128>(td, a_lo, a_hi, b_lo, b_hi, idesc, acc0);
+          umma_f16_off_w<1 * 160, 1 * 128>(td, a_lo, a_hi, b_lo, b_hi, idesc, 1u);
+          umma_f16_off_w<2 * 160, 2 * 128>(td, a_lo, a_hi, b_lo, b_hi, idesc, 1u);
+          umma_f16_off_w<3 * 160, 3 * 128>(td, a_lo, a_hi, b_lo, b_hi, idesc, 1u);
+          umma_f16_off_w<4 * 160, 4 * 128>(td, a_lo, a_hi, b_lo, b_hi, idesc, 1u);
+          umma_f16_off_w<5 * 160, 5 * 128>(td, a_lo, a_hi, b_lo, b_hi, idesc, 1u);
+          umma_f16_off_w<6 * 160, 6 * 128>(td, a_lo, a_hi, b_lo, b_hi, idesc, 1u);
+          umma_f16_off_w<7 * 160, 7 * 128>(td, a_lo, a_hi, b_lo, b_hi, idesc, 1u);
+        }
+        umma_commit_w(empty_u + s * 8);
+        if (++s == static_cast<uint32_t>(STG)) { s = 0; ph ^= 1; }
+      }
+      umma_commit_w(tfull_u);
+    }
+  } else {
+    // =========================== epilogue (warps 2..9): the groups split the 32-column slices ===========
+    const int g = (warp - 2) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    uint32_t lt = 0;
+    for (long long item = blockIdx.x; item < total_items; item += gridDim.x) {
+      int pair, u0, nu, kb_begin, kb_end;
+      decode(item, pair, u0, nu, kb_begin, kb_end);
+      if (kb_end <= kb_begin) continue;
+      mbar_wait(tmem_full, lt & 1);
+      ++lt;
+      tc_fence_after();
+      for (int i = 0; i < nu; ++i) {
+        // packed-gradient column of this accumulator row: group (tap, chunk) * 64 + channel
+        int tap, cc;
+        if (p.kchunks == 1) { tap = 2 * (u0 + i) + (row >> 6); cc = 0; }
+        else { tap = u0 + i; cc = 2 * pair + (row >> 6); }
+        const bool row_ok = tap < 9 && cc < p.kchunks;
+        const long long kidx = static_cast<long long>(tap * p.kchunks + cc) * 64 + (row & 63);
+        const uint32_t tmem_acc = tmem_base + i * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+        for (int c = g; c < BLOCK_N / 32; c += 2) {
+          uint32_t v[32];
+          tmem_ld32(tmem_acc + c * 32, v);
+          tmem_ld_wait();
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = c * 32 + j;
+              if (n < p.n_total) red_add_f32(p.dw + static_cast<long long>(n) * p.dw_ld + kidx, __uint_as_float(v[j]));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty);
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// =====================================================================================
 // host side
 // =====================================================================================
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -942,6 +1151,15 @@ static int conv_algo_override() {          // env HPRI_CONV_ALGO seeds it; hpri_
   return g_conv_algo;
 }
 
+static int g_wgrad_algo = -2;              // -1 heuristic, 0 generic kernel only
+static int wgrad_algo_override() {
+  if (g_wgrad_algo == -2) {
+    const char* e = getenv("HPRI_WGRAD_ALGO");
+    g_wgrad_algo = e ? atoi(e) : -1;
+  }
+  return g_wgrad_algo;
+}
+
 }  // namespace hpri
 
 using namespace hpri;
@@ -1112,6 +1330,63 @@ extern "C" int hpri_igemm_wgrad(const hpri_view_t* x, const hpri_view_t* dy, int
   a.n_total = n_total; a.dw = dw; a.dw_ld = dw_ld;
   a.a_dt = x->dtype; a.b_dt = dy->dtype; a.out_dt = DT_BF16;
   if (x->dtype != dy->dtype) return HPRI_ERR_ARG;   // kind::f16 takes A and B in one format
+  if (mode == 1 && (n_total == 64 || n_total == 128) && (a.kchunks == 1 || a.kchunks % 2 == 0) && splits <= 0 &&
+      block_n == 0 && wgrad_algo_override() != 0 && dy->c >= n_total) {
+    // halo-reuse weight gradient (one X halo block + one dY tile per 128-pixel k-block feed every tap)
+    if (dy->n != x->n || dy->h != x->h || dy->w != x->w) return HPRI_ERR_ARG;
+    WgHaloArgs g{};
+    g.N = x->n; g.H = x->h; g.W = x->w;
+    g.tiles_h = (g.H + 15) / 16; g.tiles_w = (g.W + 7) / 8;
+    g.kchunks = a.kchunks; g.nblk = a.kchunks == 1 ? 1 : 2;
+    g.npairs = a.kchunks == 1 ? 1 : a.kchunks / 2;
+    g.units = a.kchunks == 1 ? 5 : 9;
+    const int tmax = 512 / n_total;
+    g.n_tg = (g.units + tmax - 1) / tmax;
+    g.n_total = n_total; g.dw = dw; g.dw_ld = dw_ld;
+    g.a_stride = (kWgBlockBytes + 1023) / 1024 * 1024;
+    g.a_dt = x->dtype; g.b_dt = dy->dtype;
+    const int stage_bytes = g.nblk * g.a_stride + (n_total / 64) * 16384;
+    g.stages = (227 * 1024 - 2048) / stage_bytes;
+    if (g.stages > kWgMaxStages) g.stages = kWgMaxStages;
+    const long long Tp = (long long)g.N * g.tiles_h * g.tiles_w;
+    const long long mn = (long long)g.npairs * g.n_tg;
+    const int sms = sm_count();
+    double best = 1e30;
+    int sp = 1;
+    for (long long s = 1; s <= Tp && s * mn <= 2LL * sms + mn; ++s) {     // the epilogue is not overlapped: few, long items
+      const long long waves = (s * mn + sms - 1) / sms;
+      const double cost = (double)waves * ((double)((Tp + s - 1) / s) + 8.0);
+      if (cost < best) { best = cost; sp = (int)s; }
+    }
+    g.splits = sp;
+    if (g.stages >= 2) {
+      CUtensorMap mx, mdy;
+      uint64_t dims[4] = {(uint64_t)x->c, (uint64_t)x->w, (uint64_t)x->h, (uint64_t)x->n};
+      uint64_t str[3] = {(uint64_t)x->pix_stride * 2, (uint64_t)x->row_stride * 2, (uint64_t)x->img_stride * 2};
+      uint32_t box[4] = {64, 10, 18, 1};
+      if ((rc = make_map(&mx, x->ptr, 4, dims, str, box, x->dtype)) != HPRI_OK) return rc;
+      hpri_view_t dyv = *dy;
+      dyv.c = n_total;
+      if ((rc = map_nhwc(&mdy, dyv, 16, 8)) != HPRI_OK) return rc;
+      const long long items = mn * g.splits;
+      const long long grid = items < sms ? items : sms;
+      const size_t smem = 2048 + (size_t)g.stages * stage_bytes;
+      auto kern64 = wgrad3x3_halo_kernel<64>;
+      auto kern128 = wgrad3x3_halo_kernel<128>;
+      static std::once_flag once;
+      static cudaError_t attr_err = cudaSuccess;
+      std::call_once(once, [&] {
+        attr_err = cudaFuncSetAttribute(kern64, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (attr_err == cudaSuccess)
+          attr_err = cudaFuncSetAttribute(kern128, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      });
+      if (attr_err != cudaSuccess) return HPRI_ERR_CUDA;
+      if (n_total == 64) kern64<<<(unsigned)grid, kThreads, smem, stream>>>(mx, mdy, g);
+      else kern128<<<(unsigned)grid, kThreads, smem, stream>>>(mx, mdy, g);
+      ++g_launch_count;
+      return cudaGetLastError() == cudaSuccess ? HPRI_OK : HPRI_ERR_CUDA;
+    }
+  }
   int bn;
   if (mode == 2) {
     a.cout = n_total / 4;
