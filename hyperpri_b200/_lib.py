@@ -12,6 +12,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libhyperpri_b200.so")
 
 
+class Conv3x3Job(C.Structure):
+    """hpri_conv3x3_job_t (include/hyperpri_b200.h)."""
+    _fields_ = [("w", C.c_void_p), ("dst_fwd", C.c_void_p), ("dst_dgrad", C.c_void_p), ("grad_packed", C.c_void_p),
+                ("grad_dst", C.c_void_p), ("cout", C.c_int), ("cin", C.c_int), ("fwd_dtype", C.c_int),
+                ("dgrad_dtype", C.c_int), ("tile0", C.c_int), ("pad_", C.c_int)]
+
+
 class View(C.Structure):
     """hpri_view_t: NHWC bf16 view with element strides."""
     _fields_ = [("ptr", C.c_void_p), ("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("c", C.c_int),
@@ -35,6 +42,8 @@ SIGNATURES = {
     "hpri_unpack_grads": [_p, _p, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _f, _i, _p],
     "hpri_pack_conv3x3": [_p, _i, _i, _p, _i, _p, _i, _p],
     "hpri_unpack_conv3x3": [_p, _i, _i, _p, _p],
+    "hpri_pack_conv3x3_batch": [_p, _i, _i, _p],
+    "hpri_unpack_conv3x3_batch": [_p, _i, _i, _p],
     "hpri_pack_convT2x2": [_p, _i, _i, _p, _i, _p],
     "hpri_unpack_convT2x2": [_p, _i, _i, _p, _p],
     "hpri_hsi_ingest": [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _i, _i, _p],

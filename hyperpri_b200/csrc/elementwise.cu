@@ -110,11 +110,10 @@ __global__ void unpack_grads_k(float* __restrict__ packed, float* __restrict__ d
 // W[co][ci][9] fp32  ->  fwd operand [co][t*kcf + ci]  and (optional) dgrad operand [ci][(8-t)*kcd + co], both
 // 16-bit.  32 x 32 (co, ci) tile through shared memory: coalesced 288-float row reads, coalesced writes of
 // both layouts, the parameter is read once.  Padding columns are never written (buffers are zero-initialised).
-__global__ void __launch_bounds__(256)
-pack_conv3x3_k(const float* __restrict__ w, int Cout, int Cin, uint16_t* __restrict__ df, int kcf, int fdt,
-               uint16_t* __restrict__ dd, int kcd, int ddt) {
-  __shared__ float tile[32][289];
-  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+__device__ __forceinline__ void pack_conv3x3_tile(float (*tile)[289], int bx, int by, const float* __restrict__ w,
+                                                  int Cout, int Cin, uint16_t* __restrict__ df, int kcf, int fdt,
+                                                  uint16_t* __restrict__ dd, int kcd, int ddt) {
+  const int ci0 = bx * 32, co0 = by * 32;
   const int nci = min(32, Cin - ci0), nco = min(32, Cout - co0);
   // 36 elements per thread, loaded 12 at a time so that 12 global loads are in flight per thread
 #pragma unroll 1
@@ -142,12 +141,32 @@ pack_conv3x3_k(const float* __restrict__ w, int Cout, int Cin, uint16_t* __restr
       dd[(long long)(ci0 + o) * (9 * kcd) + (8 - t) * kcd + co0 + l] = cvt16(tile[l][o * 9 + t], ddt);
   }
 }
+__global__ void __launch_bounds__(256)
+pack_conv3x3_k(const float* __restrict__ w, int Cout, int Cin, uint16_t* __restrict__ df, int kcf, int fdt,
+               uint16_t* __restrict__ dd, int kcd, int ddt) {
+  __shared__ float tile[32][289];
+  pack_conv3x3_tile(tile, blockIdx.x, blockIdx.y, w, Cout, Cin, df, kcf, fdt, dd, kcd, ddt);
+}
+// job lookup for the table-driven launches: the job whose tile range contains `t`
+__device__ __forceinline__ int find_job(const hpri_conv3x3_job_t* __restrict__ jobs, int njobs, int t) {
+  int j = 0;
+  while (j + 1 < njobs && jobs[j + 1].tile0 <= t) ++j;
+  return j;
+}
+__global__ void __launch_bounds__(256) pack_conv3x3_batch_k(const hpri_conv3x3_job_t* __restrict__ jobs, int njobs) {
+  __shared__ float tile[32][289];
+  const int j = find_job(jobs, njobs, blockIdx.x);
+  const hpri_conv3x3_job_t jb = jobs[j];
+  const int t = blockIdx.x - jb.tile0, tx = (jb.cin + 31) / 32;
+  pack_conv3x3_tile(tile, t % tx, t / tx, jb.w, jb.cout, jb.cin, static_cast<uint16_t*>(jb.dst_fwd),
+                    (jb.cin + 63) / 64 * 64, jb.fwd_dtype, static_cast<uint16_t*>(jb.dst_dgrad),
+                    (jb.cout + 63) / 64 * 64, jb.dgrad_dtype);
+}
 // packed fp32 gradient [co][t*kcf + ci] -> W-layout [co][ci][9]; the packed buffer is reset to zero behind the
 // read so that the next split-K weight-gradient launch can accumulate into it without a separate memset.
-__global__ void __launch_bounds__(256)
-unpack_conv3x3_k(float* __restrict__ g, int Cout, int Cin, int kcf, float* __restrict__ dst) {
-  __shared__ float tile[32][289];
-  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+__device__ __forceinline__ void unpack_conv3x3_tile(float (*tile)[289], int bx, int by, float* __restrict__ g, int Cout,
+                                                    int Cin, int kcf, float* __restrict__ dst) {
+  const int ci0 = bx * 32, co0 = by * 32;
   const int nci = min(32, Cin - ci0), nco = min(32, Cout - co0);
 #pragma unroll 1
   for (int b = 0; b < 3; ++b) {
@@ -171,6 +190,18 @@ unpack_conv3x3_k(float* __restrict__ g, int Cout, int Cin, int kcf, float* __res
     const int col = i / 288, rem = i - col * 288;
     if (col < nco && rem < nci * 9) dst[((long long)(co0 + col) * Cin + ci0) * 9 + rem] = tile[col][rem];
   }
+}
+__global__ void __launch_bounds__(256)
+unpack_conv3x3_k(float* __restrict__ g, int Cout, int Cin, int kcf, float* __restrict__ dst) {
+  __shared__ float tile[32][289];
+  unpack_conv3x3_tile(tile, blockIdx.x, blockIdx.y, g, Cout, Cin, kcf, dst);
+}
+__global__ void __launch_bounds__(256) unpack_conv3x3_batch_k(const hpri_conv3x3_job_t* __restrict__ jobs, int njobs) {
+  __shared__ float tile[32][289];
+  const int j = find_job(jobs, njobs, blockIdx.x);
+  const hpri_conv3x3_job_t jb = jobs[j];
+  const int t = blockIdx.x - jb.tile0, tx = (jb.cin + 31) / 32;
+  unpack_conv3x3_tile(tile, t % tx, t / tx, jb.grad_packed, jb.cout, jb.cin, (jb.cin + 63) / 64 * 64, jb.grad_dst);
 }
 
 // ------------------------------------------------------------------ ConvTranspose2d(k2,s2) weight <-> GEMM operand
@@ -1026,6 +1057,16 @@ extern "C" int hpri_pack_conv3x3(const float* w, int cout, int cin, void* dst_fw
   pack_conv3x3_k<<<grid, 256, 0, (cudaStream_t)stream>>>(w, cout, cin, (uint16_t*)dst_fwd, (cin + 63) / 64 * 64,
                                                         fwd_dtype, (uint16_t*)dst_dgrad, (cout + 63) / 64 * 64,
                                                         dgrad_dtype);
+  return last_err();
+}
+extern "C" int hpri_pack_conv3x3_batch(const hpri_conv3x3_job_t* jobs, int njobs, int total_tiles, void* stream) {
+  if (!jobs || njobs <= 0 || total_tiles <= 0) return HPRI_ERR_ARG;
+  pack_conv3x3_batch_k<<<total_tiles, 256, 0, (cudaStream_t)stream>>>(jobs, njobs);
+  return last_err();
+}
+extern "C" int hpri_unpack_conv3x3_batch(const hpri_conv3x3_job_t* jobs, int njobs, int total_tiles, void* stream) {
+  if (!jobs || njobs <= 0 || total_tiles <= 0) return HPRI_ERR_ARG;
+  unpack_conv3x3_batch_k<<<total_tiles, 256, 0, (cudaStream_t)stream>>>(jobs, njobs);
   return last_err();
 }
 extern "C" int hpri_pack_convT2x2(const float* w, int cin, int cout, void* dst_fwd, int fwd_dtype, void* stream) {

@@ -47,16 +47,22 @@ class _PackedParam:
         self.fwd = self.dgr = None
         self.gpack = None
 
+    def alloc3x3(self, device):
+        if self.fwd is None:                   # zero once: the tiled pack never writes padding
+            f, g = self.spec.fwd, self.spec.dgr
+            self.fwd = torch.zeros((f["R"], 9 * kpad(f["Cc"])), dtype=ACT, device=device)
+            if self.need_dgrad:
+                self.dgr = torch.zeros((g["R"], 9 * kpad(g["Cc"])), dtype=GRAD, device=device)
+
+    def stale(self, w: torch.Tensor) -> bool:
+        return (w.data_ptr(), w._version) != self.key
+
     def refresh(self, w: torch.Tensor):
         key = (w.data_ptr(), w._version)
         if key != self.key:
             wc = w.detach().reshape(-1)
             if self.spec.kind == "conv3x3":
-                if self.fwd is None:           # zero once: the tiled pack never writes padding
-                    f, g = self.spec.fwd, self.spec.dgr
-                    self.fwd = torch.zeros((f["R"], 9 * kpad(f["Cc"])), dtype=ACT, device=w.device)
-                    if self.need_dgrad:
-                        self.dgr = torch.zeros((g["R"], 9 * kpad(g["Cc"])), dtype=GRAD, device=w.device)
+                self.alloc3x3(w.device)
                 self.spec.pack_both(wc, self.fwd, self.dgr)
             else:
                 self.fwd = self.spec.pack_fwd(wc, out=self.fwd)
@@ -174,6 +180,7 @@ class UNetEngine(_EngineBase):
         self.ws = None
         self.ws_key = None
         self.training_fwd = False
+        self._tables = {}
         self._build_grad_arena()
         self.bucket_hook = None      # callable(flat_slice) invoked as each gradient bucket is complete
         self._init_scaling(device)
@@ -208,6 +215,7 @@ class UNetEngine(_EngineBase):
         del start
 
     def _bucket_done(self, idx):
+        self._unpack_bucket(idx)
         if self.bucket_hook is not None:
             a, b = self.bucket_bounds[idx]
             if b > a:
@@ -287,9 +295,8 @@ class UNetEngine(_EngineBase):
                         dpool=dpool, head_w=head_w, dlogit=dlogit, dgamma=self._grad(L.bn + ".weight", L.scale[:L.cout]),
                         dbeta=self._grad(L.bn + ".bias", L.scale[:L.cout]), dhead_w=dhead_w)
         ops.igemm_wgrad(self._as_grad_dtype(x_in), R, 1, L.cout, L.gw)
-        wname = L.conv + ".weight"
-        L.pp.spec.unpack_grad(L.gw, self._grad(wname, self.P[wname]).view(-1))
-        self._grad(L.conv + ".bias", self.P[L.conv + ".bias"])          # identically zero under train-mode BN
+        # the packed gradient is unpacked into the arena per bucket (_unpack_bucket); the conv bias gradient is
+        # identically zero under train-mode BN
         if dx_out is not None:
             ops.igemm_fwd(R, L.pp.dgr, L.cin, 9, dx_out, L.cin)
 
@@ -309,9 +316,53 @@ class UNetEngine(_EngineBase):
         self.ingest(x, ws)
         return self.forward_ingested(ws, training)
 
+    # ------------------------------------------------------------------ table-driven weight pack / gradient unpack
+    def _conv_layers(self):
+        return [L for grp in list(self.enc) + [self.dec[l] for l in (3, 2, 1, 0)] for L in grp]
+
+    def _jobs(self, layers):
+        jobs = []
+        for L in layers:
+            w = self.P[L.conv + ".weight"]
+            L.pp.alloc3x3(w.device)
+            jobs.append(dict(w=w, fwd=L.pp.fwd, dgrad=L.pp.dgr, gpacked=L.gw, gdst=self.grads[L.conv + ".weight"],
+                             cout=L.pp.spec.cout, cin=L.pp.spec.cin))
+        return jobs
+
+    def _table(self, name, layers):
+        """Cached device job table for a fixed list of layers (rebuilt if a parameter's storage moved)."""
+        key = tuple(self.P[L.conv + ".weight"].data_ptr() for L in layers)
+        t = self._tables.get(name)
+        if t is None or t.key != key:
+            t = ops.Conv3x3JobTable(self._jobs(layers), self.dev)
+            self._tables[name] = t
+        return t
+
+    def _refresh_packed(self):
+        """Re-pack stale 16-bit weight operands: one table-driven launch when every 3x3 layer is stale (the normal
+        case after an optimizer step), per layer otherwise."""
+        layers = self._conv_layers()
+        P = self.P
+        if all(L.pp.stale(P[L.conv + ".weight"]) for L in layers):
+            ops.pack_conv3x3_batch(self._table("all", layers))
+            for L in layers:
+                w = P[L.conv + ".weight"]
+                L.pp.key = (w.data_ptr(), w._version)
+
+    def _unpack_bucket(self, idx):
+        """Gradients of the 3x3 layers of bucket idx: packed fp32 -> arena.  Without an all-reduce hook the nine
+        buckets are unpacked by ONE launch at the end of backward."""
+        if self.bucket_hook is not None:
+            l = idx if idx < 4 else 8 - idx
+            grp = self.dec[l] if idx < 4 else self.enc[l]
+            ops.unpack_conv3x3_batch(self._table(f"bucket{idx}", [grp[1], grp[0]]))
+        elif idx == 8:
+            ops.unpack_conv3x3_batch(self._table("all", self._conv_layers()))
+
     def forward_ingested(self, ws, training: bool) -> torch.Tensor:
         P, C = self.P, self.CH
         self.training_fwd = training
+        self._refresh_packed()
         cur = ws["x"]
         for l in range(5):
             a, b = self.enc[l]

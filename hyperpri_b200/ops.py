@@ -112,6 +112,41 @@ def unpack_conv3x3(packed, cout, cin, dst):
     check(_lib.lib().hpri_unpack_conv3x3(_ptr(packed), cout, cin, _ptr(dst), _stream()), "hpri_unpack_conv3x3")
 
 
+class Conv3x3JobTable:
+    """Device table of hpri_conv3x3_job_t for the table-driven pack / unpack launches.  jobs: dicts with keys
+    w, fwd, dgrad (or None), gpacked, gdst, cout, cin."""
+
+    def __init__(self, jobs, device):
+        arr = (_lib.Conv3x3Job * len(jobs))()
+        tiles = 0
+        for i, j in enumerate(jobs):
+            arr[i].w = j["w"].data_ptr()
+            arr[i].dst_fwd = j["fwd"].data_ptr()
+            arr[i].dst_dgrad = 0 if j.get("dgrad") is None else j["dgrad"].data_ptr()
+            arr[i].grad_packed = j["gpacked"].data_ptr()
+            arr[i].grad_dst = j["gdst"].data_ptr()
+            arr[i].cout, arr[i].cin = j["cout"], j["cin"]
+            arr[i].fwd_dtype = _DT[j["fwd"].dtype]
+            arr[i].dgrad_dtype = 0 if j.get("dgrad") is None else _DT[j["dgrad"].dtype]
+            arr[i].tile0 = tiles
+            tiles += ((j["cin"] + 31) // 32) * ((j["cout"] + 31) // 32)
+        raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        self.dev = raw.to(device)
+        self.n, self.tiles = len(jobs), tiles
+        self.key = tuple(j["w"].data_ptr() for j in jobs)
+
+
+@_timed
+def pack_conv3x3_batch(table: Conv3x3JobTable):
+    check(_lib.lib().hpri_pack_conv3x3_batch(_ptr(table.dev), table.n, table.tiles, _stream()), "hpri_pack_conv3x3_batch")
+
+
+@_timed
+def unpack_conv3x3_batch(table: Conv3x3JobTable):
+    check(_lib.lib().hpri_unpack_conv3x3_batch(_ptr(table.dev), table.n, table.tiles, _stream()),
+          "hpri_unpack_conv3x3_batch")
+
+
 @_timed
 def pack_convT(w, cin, cout, fwd):
     """W[ci][co][2][2] fp32 -> forward operand [4*cout, kpad(cin)] (zero-initialised once by the caller)."""

@@ -47,5 +47,6 @@ class BucketedAllReduce:
 
 def attach(engine, group=None) -> BucketedAllReduce:
     r = BucketedAllReduce(group, engine)
-    engine.bucket_hook = r.hook
+    # a single process has nothing to exchange: leave the engine on its one-launch gradient unpack / unscale path
+    engine.bucket_hook = r.hook if r.world_size > 1 else None
     return r

@@ -83,6 +83,21 @@ int hpri_unpack_grads(float* packed, float* dst, int G, int R, int T, int C, int
 int hpri_pack_conv3x3(const float* w, int cout, int cin, void* dst_fwd, int fwd_dtype, void* dst_dgrad,
                       int dgrad_dtype, void* stream);
 int hpri_unpack_conv3x3(float* packed, int cout, int cin, float* dst, void* stream);
+/* Table-driven variants: ONE launch refreshes the 16-bit operands of every 3x3 layer after an optimizer step / unpacks
+ * the gradients of a whole bucket (18 launches of ~14 us each were latency-, not bandwidth-bound).  `jobs` is a DEVICE
+ * array; tile0 = number of 32x32 (co, ci) tiles of all previous jobs; total_tiles = tiles of all jobs. */
+typedef struct {
+  const float* w;       /* [cout][cin][3][3] */
+  void* dst_fwd;        /* [cout][9*kpad(cin)] or null */
+  void* dst_dgrad;      /* [cin][9*kpad(cout)] or null */
+  float* grad_packed;   /* unpack: [cout][9*kpad(cin)] fp32 (zeroed behind the read) */
+  float* grad_dst;      /* unpack: [cout][cin][3][3] */
+  int cout, cin, fwd_dtype, dgrad_dtype;
+  int tile0, pad_;
+} hpri_conv3x3_job_t;
+int hpri_pack_conv3x3_batch(const hpri_conv3x3_job_t* jobs, int njobs, int total_tiles, void* stream);
+int hpri_unpack_conv3x3_batch(const hpri_conv3x3_job_t* jobs, int njobs, int total_tiles, void* stream);
+
 /* ConvTranspose2d(k=2,s=2): W[ci][co][2][2] <-> forward operand [(a*2+b)*cout + co][kpad(ci)] (a (ci, co) transpose,
  * tiled through shared memory); unpack zeroes the packed gradient behind the read.  Padding columns are not written. */
 int hpri_pack_convT2x2(const float* w, int cin, int cout, void* dst_fwd, int fwd_dtype, void* stream);
