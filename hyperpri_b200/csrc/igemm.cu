@@ -489,12 +489,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
 // =====================================================================================
 constexpr int kHaloStatCh = 1024;
 constexpr int kHaloAStages = 2;
-constexpr int kHaloMaxBStages = 4;
+constexpr int kHaloMaxBStages = 12;     // weight ring slots: ONE tap tile each (fine-grained: more bytes in flight)
 
 template <int BLOCK_N>
 struct HaloSmem {
   static constexpr int B_TILE = BLOCK_N * 128;
-  static constexpr int B_STAGE = 3 * B_TILE;
+  static constexpr int B_STAGE = B_TILE;
   static constexpr int STAGING_OFF = 0;
   static constexpr int BAR_OFF = 2 * kStageTile;       // a_full[2], a_empty[2], b_full[4], b_empty[4], tmem_full[2], tmem_empty[2]
   static constexpr int TMEMPTR_OFF = BAR_OFF + (2 * kHaloAStages + 2 * kHaloMaxBStages + 4) * 8;
@@ -585,14 +585,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           tma_load_4d_w(a_ring_u + sa * a_bytes, &tmA, afull_u + sa * 8, cc * 64, w0 - 1, h0 - 1, img);
           if (++sa == kHaloAStages) { sa = 0; pha ^= 1; }
 #pragma unroll 1
-          for (int r = 0; r < 3; ++r) {
+          for (int tap = 0; tap < 9; ++tap) {
             mbar_wait_w(bempty_u + sb * 8, phb ^ 1);
             const uint32_t fb = bfull_u + sb * 8;
-            mbar_arrive_expect_tx_w(fb, L::B_STAGE);
-            const uint32_t sB = b_ring_u + sb * L::B_STAGE;
-#pragma unroll
-            for (int sft = 0; sft < 3; ++sft)
-              tma_load_2d_w(sB + sft * L::B_TILE, &tmB, fb, ((r * 3 + sft) * p.kchunks + cc) * 64, n0);
+            mbar_arrive_expect_tx_w(fb, L::B_TILE);
+            tma_load_2d_w(b_ring_u + sb * L::B_TILE, &tmB, fb, (tap * p.kchunks + cc) * 64, n0);
             if (++sb == static_cast<uint32_t>(BST)) { sb = 0; phb ^= 1; }
           }
         }
@@ -624,31 +621,32 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t a_lo0 = static_cast<uint32_t>(dA) | ((a_ring_u + sa * a_bytes) >> 4);
 #pragma unroll 1
           for (int r = 0; r < 3; ++r) {
-            mbar_wait_w(bfull_u + sb * 8, phb);
-            tc_fence_after();
-            // three base descriptors per filter row (halo block row r for each half, weight stage); the horizontal
-            // shift (8 x 16 B per pixel), the weight tile of that shift and the K step are compile-time offsets
+            // two base descriptors per filter row (halo block row r for each half); the horizontal shift
+            // (8 x 16 B per pixel) and the K step are compile-time offsets; one weight-ring slot per tap
             const uint32_t a_r = a_lo0 + static_cast<uint32_t>(r * geo.wb * 8);
             const uint32_t aH0 = a_r + half_off0, aH1 = a_r + half_off1;
-            const uint32_t b_lo = static_cast<uint32_t>(dB) | ((b_ring_u + sb * L::B_STAGE) >> 4);
             const uint32_t t0 = tmem_d, t1 = tmem_d + BLOCK_N;
             const uint32_t acc0 = (cc > 0 || r > 0) ? 1u : 0u;
-            constexpr uint32_t BT = L::B_TILE >> 4;
-#define HPRI_TAP(S, ACC)                                                                        \
-            umma_f16_off_w<S * 8 + 0, S * BT + 0>(t0, aH0, a_hi, b_lo, b_hi, idesc, ACC);         \
-            umma_f16_off_w<S * 8 + 2, S * BT + 2>(t0, aH0, a_hi, b_lo, b_hi, idesc, 1u);          \
-            umma_f16_off_w<S * 8 + 4, S * BT + 4>(t0, aH0, a_hi, b_lo, b_hi, idesc, 1u);          \
-            umma_f16_off_w<S * 8 + 6, S * BT + 6>(t0, aH0, a_hi, b_lo, b_hi, idesc, 1u);          \
-            umma_f16_off_w<S * 8 + 0, S * BT + 0>(t1, aH1, a_hi, b_lo, b_hi, idesc, ACC);         \
-            umma_f16_off_w<S * 8 + 2, S * BT + 2>(t1, aH1, a_hi, b_lo, b_hi, idesc, 1u);          \
-            umma_f16_off_w<S * 8 + 4, S * BT + 4>(t1, aH1, a_hi, b_lo, b_hi, idesc, 1u);          \
-            umma_f16_off_w<S * 8 + 6, S * BT + 6>(t1, aH1, a_hi, b_lo, b_hi, idesc, 1u);
+#define HPRI_TAP(S, ACC)                                                                          \
+            {                                                                                     \
+              mbar_wait_w(bfull_u + sb * 8, phb);                                                 \
+              tc_fence_after();                                                                   \
+              const uint32_t b_lo = static_cast<uint32_t>(dB) | ((b_ring_u + sb * L::B_TILE) >> 4); \
+              umma_f16_off_w<S * 8 + 0, 0>(t0, aH0, a_hi, b_lo, b_hi, idesc, ACC);                  \
+              umma_f16_off_w<S * 8 + 2, 2>(t0, aH0, a_hi, b_lo, b_hi, idesc, 1u);                   \
+              umma_f16_off_w<S * 8 + 4, 4>(t0, aH0, a_hi, b_lo, b_hi, idesc, 1u);                   \
+              umma_f16_off_w<S * 8 + 6, 6>(t0, aH0, a_hi, b_lo, b_hi, idesc, 1u);                   \
+              umma_f16_off_w<S * 8 + 0, 0>(t1, aH1, a_hi, b_lo, b_hi, idesc, ACC);                  \
+              umma_f16_off_w<S * 8 + 2, 2>(t1, aH1, a_hi, b_lo, b_hi, idesc, 1u);                   \
+              umma_f16_off_w<S * 8 + 4, 4>(t1, aH1, a_hi, b_lo, b_hi, idesc, 1u);                   \
+              umma_f16_off_w<S * 8 + 6, 6>(t1, aH1, a_hi, b_lo, b_hi, idesc, 1u);                   \
+              umma_commit_w(bempty_u + sb * 8);                                                   \
+              if (++sb == static_cast<uint32_t>(BST)) { sb = 0; phb ^= 1; }                       \
+            }
             HPRI_TAP(0, acc0)
             HPRI_TAP(1, 1u)
             HPRI_TAP(2, 1u)
 #undef HPRI_TAP
-            umma_commit_w(bempty_u + sb * 8);
-            if (++sb == static_cast<uint32_t>(BST)) { sb = 0; phb ^= 1; }
           }
           umma_commit_w(aempty_u + sa * 8);   // the halo block is free once all nine taps have read it
           if (++sa == kHaloAStages) { sa = 0; pha ^= 1; }

@@ -3,7 +3,8 @@ import csv, io, subprocess, sys
 rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
-hdr, units, vals = rows[0], rows[1], rows[2]
+hdr, units = rows[0], rows[1]
+vals = rows[2 + (int(sys.argv[3]) if len(sys.argv) > 3 else 0)]
 keys = ["Kernel Name", "gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct",
         "l1tex__throughput.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum",
@@ -14,12 +15,14 @@ for h, u, v in zip(hdr, units, vals):
         print(f"{h} [{u}] = {v}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
+which = int(sys.argv[3]) if len(sys.argv) > 3 else 0      # k-th profiled launch of the report
 hdr = rows[1]
-data = []
-for r in rows[2:]:                      # first kernel of the report only (sections start with a "Kernel Name" row)
+data, sec = [], -1
+for r in rows:                          # sections start with a "Kernel Name" row, followed by the header row
     if r and r[0] == "Kernel Name":
-        break
-    if len(r) == len(hdr):
+        sec += 1
+        continue
+    if sec == which and len(r) == len(hdr) and r[0] != "Address":
         data.append(r)
 ix = {h: i for i, h in enumerate(hdr)}
 stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
