@@ -1027,7 +1027,7 @@ static inline int grid_for(long long work_items, int per_block, int cap = 148 * 
 
 using namespace hpri;
 
-extern "C" int hpri_abi_version(void) { return 2; }
+extern "C" int hpri_abi_version(void) { return 3; }
 extern "C" long long hpri_launch_count(void) { return g_launch_count; }
 
 extern "C" int hpri_pack_weights(const float* src, void* dst, int dst_dtype, int G, int R, int T, int C, int kc64,

@@ -224,6 +224,57 @@ def test_tiled_conv3x3_pack_matches_generic(cout, cin):
     assert not g.view(cout, 9, -1)[:, :, :cin].any()      # the packed buffer is reset behind the read
 
 
+def test_table_driven_pack_and_unpack_match_per_layer():
+    """One launch over a device job table == the per-layer kernels, for ragged layer sizes."""
+    shapes = [(64, 238), (128, 64), (96, 40), (256, 128)]
+    ws = [rnd(co, ci, 3, 3, seed=60 + i) for i, (co, ci) in enumerate(shapes)]
+    jobs, ref = [], []
+    for (co, ci), w in zip(shapes, ws):
+        spec = ops.WeightSpec("conv3x3", co, ci)
+        f = torch.zeros((co, 9 * ops.kpad(ci)), dtype=FH, device=DEV)
+        d = torch.zeros((ci, 9 * ops.kpad(co)), dtype=FH, device=DEV)
+        g = torch.randn((co, 9 * ops.kpad(ci)), device=DEV)
+        g.view(co, 9, -1)[:, :, ci:] = 0                      # padding columns of a packed gradient are always zero
+        gd = torch.empty_like(w)
+        jobs.append(dict(w=w.reshape(-1), fwd=f, dgrad=d, gpacked=g, gdst=gd, cout=co, cin=ci))
+        gref = torch.empty_like(w)
+        ops.unpack(g.clone(), gref.view(-1), **spec.fwd)
+        ref.append((spec.pack_fwd(w.reshape(-1), dtype=FH), spec.pack_dgrad(w.reshape(-1), dtype=FH), gref))
+    table = ops.Conv3x3JobTable(jobs, DEV)
+    ops.pack_conv3x3_batch(table)
+    ops.unpack_conv3x3_batch(table)
+    torch.cuda.synchronize()
+    for j, (f, d, g) in zip(jobs, ref):
+        assert torch.equal(j["fwd"], f) and torch.equal(j["dgrad"], d) and torch.equal(j["gdst"], g)
+        assert not j["gpacked"].any()                           # zeroed behind the read
+
+
+@pytest.mark.parametrize("cin,cout", [(128, 64), (1024, 512), (64, 192)])
+def test_tiled_convT_pack_matches_generic(cin, cout):
+    w = rnd(cin, cout, 2, 2, seed=70)
+    spec = ops.WeightSpec("convT2x2", cout, cin)
+    got = spec.pack_fwd(w.reshape(-1), dtype=FH)                # tiled transpose
+    want = ops.pack(w.reshape(-1), dtype=FH, **spec.fwd)        # generic index-map kernel
+    assert torch.equal(got, want)
+    g = torch.randn((4 * cout, ops.kpad(cin)), device=DEV)
+    a, b = torch.empty_like(w), torch.empty_like(w)
+    ops.unpack(g.clone(), b.view(-1), **spec.fwd)
+    spec.unpack_grad(g, a)
+    assert torch.equal(a, b) and not g.any()
+
+
+def test_scale_check_unscales_and_flags_overflow():
+    x = torch.randn(100003, device=DEV)
+    want = x * 0.125
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    xs = x.clone()
+    ops.scale_check(xs, 0.125, flag)
+    assert torch.equal(xs, want) and flag.item() == 0
+    xs[77777] = float("inf")
+    ops.scale_check(xs, 1.0, flag)
+    assert flag.item() == 1
+
+
 def test_mixed_format_rejected_and_convert():
     x = nhwc(rnd(1, 64, 8, 8, seed=40), dt=FH)
     dy = nhwc(rnd(1, 64, 8, 8, seed=41), dt=BF)

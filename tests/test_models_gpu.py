@@ -140,6 +140,26 @@ def test_state_dict_roundtrip_and_optimizer_step_changes_output():
     assert losses[-1] < losses[0] - 0.05, losses
 
 
+def test_partial_weight_change_and_fp16_host_input():
+    """A single changed parameter goes through the per-layer re-pack path (the table-driven launch needs every
+    layer stale); an fp16 cube (host-side conversion before H2D) gives bit-identical logits."""
+    net, sd = build("CubeNET", 238)
+    x = O.synth_cube(3, 1, 238, 48, 40)[:, None].cuda()
+    net.eval()
+    with torch.no_grad():
+        a = net(x)
+        assert torch.equal(net(x.half()), a)
+        with torch.no_grad():
+            net.up3.conv.double_conv[0].weight.mul_(1.5)        # bumps one parameter version
+        b = net(x)
+        net2, _ = build("CubeNET", 238)
+        sd2 = {k: v.clone() for k, v in sd.items()}
+        sd2["up3.conv.double_conv.0.weight"] *= 1.5
+        net2.load_state_dict(sd2)
+        net2.cuda().eval()
+        assert not torch.equal(a, b) and torch.equal(net2(x), b)
+
+
 def test_full_size_properties():
     """BASELINE size (2 x 238 x 608 x 968): size-independent properties instead of an oracle run --
     finite logits, loss consistent with the logits, per-image independence of the forward in eval mode."""
