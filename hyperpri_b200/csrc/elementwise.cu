@@ -50,6 +50,14 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8], int dt) {
   u.z = pack2(f[4], f[5], dt); u.w = pack2(f[6], f[7], dt);
   return u;
 }
+template <int DT>
+__device__ __forceinline__ uint32_t pack2_e(float lo, float hi) {
+  if (DT == DT_F16) {
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  return pack_bf16x2(lo, hi);
+}
 __device__ __forceinline__ uint16_t cvt16(float v, int dt) {
   if (dt == DT_F16) return __half_as_ushort(__float2half_rn(v));
   return __bfloat16_as_ushort(__float2bfloat16_rn(v));
@@ -490,13 +498,21 @@ __device__ __forceinline__ void load_window(const BwdIn& a, int n, int wy, int w
 }
 
 // dz (gradient at the BN output after the ReLU mask) and z = x*scale+shift for word j (channels 2j, 2j+1).
+// DT: element format of x / dy / dpool when all three agree (compile-time unpack), -1: per-view runtime formats.
+// HEAD: the 1x1 OutConv gradient dlogit * head_w is added.  Branch-free: the pooled gradient goes to the FIRST
+// maximum of the 2x2 window (ATen max_pool2d order) through comparisons and selects only.
+template <int DT>
+__device__ __forceinline__ float2 unp(uint32_t v, int rt_dt) {
+  return DT < 0 ? unpack2(v, rt_dt) : unpack2_t<(DT < 0 ? 0 : DT)>(v);
+}
+template <int DT, bool HEAD>
 __device__ __forceinline__ void window_word(const BwdIn& a, const Win& w, int j, const float* sc, const float* sh,
                                             const float* hw, float (&xv)[4][2], float (&z)[4][2], float (&dz)[4][2]) {
-  const float2 dpv = w.has_dp ? unpack2(wsel(w.dp, j), a.dpool.dt) : make_float2(0.f, 0.f);
+  const float2 dpv = w.has_dp ? unp<DT>(wsel(w.dp, j), a.dpool.dt) : make_float2(0.f, 0.f);
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const float2 xq = unpack2(wsel(w.x[q], j), a.x.dt);
-    const float2 dq = a.dy.p != nullptr ? unpack2(wsel(w.dy[q], j), a.dy.dt) : make_float2(0.f, 0.f);
+    const float2 xq = unp<DT>(wsel(w.x[q], j), a.x.dt);
+    const float2 dq = a.dy.p != nullptr ? unp<DT>(wsel(w.dy[q], j), a.dy.dt) : make_float2(0.f, 0.f);
     xv[q][0] = xq.x; xv[q][1] = xq.y;
     dz[q][0] = dq.x; dz[q][1] = dq.y;
   }
@@ -506,24 +522,18 @@ __device__ __forceinline__ void window_word(const BwdIn& a, const Win& w, int j,
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       z[q][e] = w.inb[q] ? fmaf(xv[q][e], sc[k], sh[k]) : -1.f;
-      if (hw != nullptr) dz[q][e] = fmaf(w.dl[q], hw[k], dz[q][e]);
+      if (HEAD) dz[q][e] = fmaf(w.dl[q], hw[k], dz[q][e]);
     }
-    if (w.has_dp) {
-      int best = 0;
-      float m = fmaxf(z[0][e], 0.f);
+    const float v0 = fmaxf(z[0][e], 0.f), v1 = fmaxf(z[1][e], 0.f), v2 = fmaxf(z[2][e], 0.f), v3 = fmaxf(z[3][e], 0.f);
+    const float m = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
+    const float g = e == 0 ? dpv.x : dpv.y;                 // zero when there is no pooled gradient
+    const bool b0 = v0 == m, b1 = !b0 && v1 == m, b2 = !b0 && !b1 && v2 == m, b3 = !b0 && !b1 && !b2;
+    dz[0][e] += b0 ? g : 0.f;
+    dz[1][e] += b1 ? g : 0.f;
+    dz[2][e] += b2 ? g : 0.f;
+    dz[3][e] += b3 ? g : 0.f;
 #pragma unroll
-      for (int q = 1; q < 4; ++q) {
-        const float v = fmaxf(z[q][e], 0.f);
-        if (v > m) { m = v; best = q; }                 // first maximum wins (ATen max_pool2d order)
-      }
-      const float g = e == 0 ? dpv.x : dpv.y;
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-        if (q == best) dz[q][e] += g;
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (!(z[q][e] > 0.f)) dz[q][e] = 0.f;
+    for (int q = 0; q < 4; ++q) dz[q][e] = z[q][e] > 0.f ? dz[q][e] : 0.f;
   }
 }
 
@@ -531,6 +541,7 @@ __device__ __forceinline__ void window_word(const BwdIn& a, const Win& w, int j,
 // grid.z the image.  A thread keeps one (wx, cg) and walks its rows: no per-element index arithmetic, per-channel
 // constants loaded once.
 // pass 1: sums[c] = {sum dz, sum dz*xhat, sum dlogit*act}
+template <int DT, bool HEAD>
 __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_k(BwdIn a, double* sums, int CG, int rows) {
   __shared__ float red[256][25];                 // odd stride: conflict-free row writes
   const int wh = (a.x.h + 1) >> 1, ww = (a.x.w + 1) >> 1;
@@ -543,10 +554,9 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_k(BwdIn a, double* sums,
   for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; s3[k] = 0.f; }
   if (wx < ww) {
     float sc[8], sh[8], hwv[8];
-    ld8p(a.scale, c0, a.x.c, sc);
-    ld8p(a.shift, c0, a.x.c, sh);
-    ld8p(a.head_w, c0, a.x.c, hwv);
-    const float* hw = a.dlogit != nullptr ? hwv : nullptr;
+    ld8v(a.scale, c0, a.x.c, sc);
+    ld8v(a.shift, c0, a.x.c, sh);
+    ld8v(a.head_w, c0, a.x.c, hwv);
     const int wy1 = min(wh, (int)(blockIdx.y + 1) * rows);
     for (int wy = blockIdx.y * rows; wy < wy1; ++wy) {
       Win w;
@@ -554,7 +564,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_k(BwdIn a, double* sums,
 #pragma unroll
       for (int jw = 0; jw < 4; ++jw) {
         float xv[4][2], z[4][2], dz[4][2];
-        window_word(a, w, jw, sc, sh, hw, xv, z, dz);
+        window_word<DT, HEAD>(a, w, jw, sc, sh, hwv, xv, z, dz);
 #pragma unroll
         for (int e = 0; e < 2; ++e)
 #pragma unroll
@@ -562,7 +572,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_k(BwdIn a, double* sums,
             const int k = 2 * jw + e;
             s1[k] += dz[q][e];
             s2[k] = fmaf(dz[q][e], xv[q][e], s2[k]);
-            s3[k] = fmaf(w.dl[q], fmaxf(z[q][e], 0.f), s3[k]);
+            if (HEAD) s3[k] = fmaf(w.dl[q], fmaxf(z[q][e], 0.f), s3[k]);
           }
       }
     }
@@ -583,11 +593,12 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_k(BwdIn a, double* sums,
     const float mu = __ldg(a.mean + c), is = __ldg(a.invstd + c);
     atomicAdd(sums + 3 * c, (double)t1);
     atomicAdd(sums + 3 * c + 1, (double)is * ((double)t2 - (double)mu * (double)t1));
-    if (a.dlogit != nullptr) atomicAdd(sums + 3 * c + 2, (double)t3);
+    if (HEAD) atomicAdd(sums + 3 * c + 2, (double)t3);
   }
 }
 
 // pass 2: dx = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)) = ca*dz + cb*x + cc
+template <int DT, bool HEAD>
 __global__ void __launch_bounds__(256, 2)
 bn_bwd_apply_k(BwdIn a, const float* __restrict__ gamma, const double* __restrict__ sums, long long count, V dx,
                float* dgamma, float* dbeta, float* dhead_w, int CG, int rows) {
@@ -606,9 +617,9 @@ bn_bwd_apply_k(BwdIn a, const float* __restrict__ gamma, const double* __restric
   const int c0 = cg * 8;
   const float rc = 1.f / (float)count;
   float sc[8], sh[8], hwv[8], ca[8], cb[8], cc[8];
-  ld8p(a.scale, c0, a.x.c, sc);
-  ld8p(a.shift, c0, a.x.c, sh);
-  ld8p(a.head_w, c0, a.x.c, hwv);
+  ld8v(a.scale, c0, a.x.c, sc);
+  ld8v(a.shift, c0, a.x.c, sh);
+  ld8v(a.head_w, c0, a.x.c, hwv);
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int c = c0 + k;
@@ -621,7 +632,6 @@ bn_bwd_apply_k(BwdIn a, const float* __restrict__ gamma, const double* __restric
     cb[k] = -gm * is * is * m2;
     cc[k] = -gm * is * m1 - cb[k] * mu;
   }
-  const float* hw = a.dlogit != nullptr ? hwv : nullptr;
   const int wy1 = min(wh, (int)(blockIdx.y + 1) * rows);
   for (int wy = blockIdx.y * rows; wy < wy1; ++wy) {
     Win w;
@@ -630,12 +640,12 @@ bn_bwd_apply_k(BwdIn a, const float* __restrict__ gamma, const double* __restric
 #pragma unroll
     for (int jw = 0; jw < 4; ++jw) {
       float xv[4][2], z[4][2], dz[4][2];
-      window_word(a, w, jw, sc, sh, hw, xv, z, dz);
+      window_word<DT, HEAD>(a, w, jw, sc, sh, hwv, xv, z, dz);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float o0 = fmaf(ca[2 * jw], dz[q][0], fmaf(cb[2 * jw], xv[q][0], cc[2 * jw]));
         const float o1 = fmaf(ca[2 * jw + 1], dz[q][1], fmaf(cb[2 * jw + 1], xv[q][1], cc[2 * jw + 1]));
-        o[q][jw] = pack2(o0, o1, dx.dt);
+        o[q][jw] = DT < 0 ? pack2(o0, o1, dx.dt) : pack2_e<(DT < 0 ? 0 : DT)>(o0, o1);
       }
     }
 #pragma unroll
@@ -1006,6 +1016,12 @@ __global__ void sum_f32_k(const float* __restrict__ x, long long n, float* out) 
   if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
 }
 
+// common element format of the views of a window kernel (-1: they differ -> runtime unpack)
+static inline int win_dtype(const hpri_view_t* x, const hpri_view_t* dy, const hpri_view_t* dpool, const hpri_view_t* dx) {
+  const int dt = x->dtype;
+  if ((dy && dy->dtype != dt) || (dpool && dpool->dtype != dt) || (dx && dx->dtype != dt)) return -1;
+  return dt;
+}
 // launch shape of the 2x2-window kernels: enough row chunks for >= 8 blocks per SM, at most 8 window rows a chunk
 static inline dim3 win_grid(const hpri_view_t* x, int CG, int* rows) {
   const int wh = (x->h + 1) / 2, ww = (x->w + 1) / 2;
@@ -1215,7 +1231,13 @@ extern "C" int hpri_bn_relu_bwd_reduce(const hpri_view_t* x, const float* scale,
   BwdIn a{mk(x), mk(dy), mk(dpool), scale, shift, save_mean, save_invstd, head_w, dlogit};
   int rows = 0;
   const dim3 grid = win_grid(x, CG, &rows);
-  bn_bwd_reduce_k<<<grid, 256, 0, (cudaStream_t)stream>>>(a, sums, CG, rows);
+  const int dt = win_dtype(x, dy, dpool, nullptr);
+  const bool head = dlogit != nullptr;
+#define HPRI_RED(DT, HD) bn_bwd_reduce_k<DT, HD><<<grid, 256, 0, (cudaStream_t)stream>>>(a, sums, CG, rows)
+  if (dt == DT_F16) { if (head) HPRI_RED(DT_F16, true); else HPRI_RED(DT_F16, false); }
+  else if (dt == DT_BF16) { if (head) HPRI_RED(DT_BF16, true); else HPRI_RED(DT_BF16, false); }
+  else { if (head) HPRI_RED(-1, true); else HPRI_RED(-1, false); }
+#undef HPRI_RED
   return last_err();
 }
 
@@ -1250,8 +1272,15 @@ extern "C" int hpri_bn_relu_bwd_apply(const hpri_view_t* x, const float* scale, 
   const int CGw = (x->c + 7) / 8;
   int rows = 0;
   const dim3 grid = win_grid(x, CGw, &rows);
-  bn_bwd_apply_k<<<grid, 256, 0, (cudaStream_t)stream>>>(a, gamma, sums, count, mk(dx), dgamma, dbeta, dhead_w, CGw,
-                                                        rows);
+  const int dt = win_dtype(x, dy, dpool, dx);
+  const bool head = dlogit != nullptr;
+#define HPRI_APP(DT, HD)                                                                                          \
+  bn_bwd_apply_k<DT, HD><<<grid, 256, 0, (cudaStream_t)stream>>>(a, gamma, sums, count, mk(dx), dgamma, dbeta, dhead_w, \
+                                                                CGw, rows)
+  if (dt == DT_F16) { if (head) HPRI_APP(DT_F16, true); else HPRI_APP(DT_F16, false); }
+  else if (dt == DT_BF16) { if (head) HPRI_APP(DT_BF16, true); else HPRI_APP(DT_BF16, false); }
+  else { if (head) HPRI_APP(-1, true); else HPRI_APP(-1, false); }
+#undef HPRI_APP
   return last_err();
 }
 
