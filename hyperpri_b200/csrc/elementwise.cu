@@ -58,6 +58,24 @@ __device__ __forceinline__ uint32_t pack2_e(float lo, float hi) {
   }
   return pack_bf16x2(lo, hi);
 }
+// compile-time element format when DT >= 0, the runtime one otherwise
+template <int DT>
+__device__ __forceinline__ void unpack8_t(const uint4& u, float (&f)[8], int rt) {
+  if (DT < 0) { unpack8(u, f, rt); return; }
+  float2 t;
+  t = unpack2_t<(DT < 0 ? 0 : DT)>(u.x); f[0] = t.x; f[1] = t.y;
+  t = unpack2_t<(DT < 0 ? 0 : DT)>(u.y); f[2] = t.x; f[3] = t.y;
+  t = unpack2_t<(DT < 0 ? 0 : DT)>(u.z); f[4] = t.x; f[5] = t.y;
+  t = unpack2_t<(DT < 0 ? 0 : DT)>(u.w); f[6] = t.x; f[7] = t.y;
+}
+template <int DT>
+__device__ __forceinline__ uint4 pack8_t(const float (&f)[8], int rt) {
+  if (DT < 0) return pack8(f, rt);
+  uint4 u;
+  u.x = pack2_e<(DT < 0 ? 0 : DT)>(f[0], f[1]); u.y = pack2_e<(DT < 0 ? 0 : DT)>(f[2], f[3]);
+  u.z = pack2_e<(DT < 0 ? 0 : DT)>(f[4], f[5]); u.w = pack2_e<(DT < 0 ? 0 : DT)>(f[6], f[7]);
+  return u;
+}
 __device__ __forceinline__ uint16_t cvt16(float v, int dt) {
   if (dt == DT_F16) return __half_as_ushort(__float2half_rn(v));
   return __bfloat16_as_ushort(__float2bfloat16_rn(v));
@@ -392,6 +410,7 @@ __global__ void bn_finalize_k(double* stats, long long count, const float* gamma
 
 // ------------------------------------------------------------------ BN apply + ReLU (+ 2x2 max pool)
 // One thread = one 2x2 pixel window x 8 channels.
+template <int DT>
 __global__ void __launch_bounds__(256)
 bn_relu_apply_k(V x, const float* __restrict__ scale, const float* __restrict__ shift, V y, V pool) {
   const int CG = (x.c + 7) >> 3;
@@ -417,20 +436,22 @@ bn_relu_apply_k(V x, const float* __restrict__ scale, const float* __restrict__ 
         const int yy = 2 * wy + dy, xx = 2 * wx + dx;
         if (yy >= x.h || xx >= x.w) continue;
         float f[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(at(x, n, yy, xx, c0))), f, x.dt);
+        unpack8_t<DT>(__ldg(reinterpret_cast<const uint4*>(at(x, n, yy, xx, c0))), f, x.dt);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           f[k] = fmaxf(fmaf(f[k], sc[k], sh[k]), 0.f);
           mx[k] = fmaxf(mx[k], f[k]);
         }
-        *reinterpret_cast<uint4*>(at(y, n, yy, xx, c0)) = pack8(f, y.dt);
+        *reinterpret_cast<uint4*>(at(y, n, yy, xx, c0)) = pack8_t<DT>(f, y.dt);
       }
-    if (pool.p != nullptr && wy < pool.h && wx < pool.w) *reinterpret_cast<uint4*>(at(pool, n, wy, wx, c0)) = pack8(mx, pool.dt);
+    if (pool.p != nullptr && wy < pool.h && wx < pool.w)
+      *reinterpret_cast<uint4*>(at(pool, n, wy, wx, c0)) = pack8_t<DT>(mx, pool.dt);
   }
 }
 
 // "flat" fast path (no pooled output, pixel-dense views): a thread keeps one channel group (its scale / shift stay in
 // registers) and walks pixels with four 16-byte loads in flight; no index arithmetic per element.
+template <int DT>
 __global__ void __launch_bounds__(256)
 bn_relu_apply_flat_k(const uint16_t* __restrict__ x, long long sx, int xdt, uint16_t* __restrict__ y, long long sy,
                      int ydt, int C, long long npix, const float* __restrict__ scale, const float* __restrict__ shift,
@@ -455,10 +476,10 @@ bn_relu_apply_flat_k(const uint16_t* __restrict__ x, long long sx, int xdt, uint
       const long long pp = p0 + u * stride;
       if (pp >= npix) break;
       float f[8];
-      unpack8(xr[u], f, xdt);
+      unpack8_t<DT>(xr[u], f, xdt);
 #pragma unroll
       for (int k = 0; k < 8; ++k) f[k] = fmaxf(fmaf(f[k], sc[k], sh[k]), 0.f);
-      *reinterpret_cast<uint4*>(y + pp * sy + c0) = pack8(f, ydt);
+      *reinterpret_cast<uint4*>(y + pp * sy + c0) = pack8_t<DT>(f, ydt);
     }
   }
 }
@@ -666,11 +687,11 @@ struct FlatIn {
   long long npix;
   const float *scale, *shift, *mean, *invstd, *head_w, *dlogit;
 };
-template <bool HEAD>
+template <bool HEAD, int DT>
 __device__ __forceinline__ void flat_dz(const FlatIn& a, const uint4& xr, const uint4& dr, float dl, const float* sc,
                                         const float* sh, const float* hw, float (&xv)[8], float (&z)[8], float (&dz)[8]) {
-  unpack8(xr, xv, a.xdt);
-  if (a.dy != nullptr) unpack8(dr, dz, a.dydt);
+  unpack8_t<DT>(xr, xv, a.xdt);
+  if (a.dy != nullptr) unpack8_t<DT>(dr, dz, a.dydt);
   else {
 #pragma unroll
     for (int k = 0; k < 8; ++k) dz[k] = 0.f;
@@ -683,7 +704,7 @@ __device__ __forceinline__ void flat_dz(const FlatIn& a, const uint4& xr, const 
   }
 }
 
-template <bool HEAD>
+template <bool HEAD, int DT>
 __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_flat_k(FlatIn a, double* sums, int slots, int CG) {
   extern __shared__ float red[];                 // [slots][CG*8][3]
   const int cg = threadIdx.x % CG, slot = threadIdx.x / CG;
@@ -714,7 +735,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_flat_k(FlatIn a, double*
       for (int u = 0; u < 4; ++u) {
         if (p0 + u * stride >= a.npix) break;
         float xv[8], z[8], dz[8];
-        flat_dz<HEAD>(a, xr[u], dr[u], dl[u], sc, sh, hw, xv, z, dz);
+        flat_dz<HEAD, DT>(a, xr[u], dr[u], dl[u], sc, sh, hw, xv, z, dz);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           s1[k] += dz[k];
@@ -742,7 +763,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_flat_k(FlatIn a, double*
   }
 }
 
-template <bool HEAD>
+template <bool HEAD, int DT>
 __global__ void __launch_bounds__(256, 2)
 bn_bwd_apply_flat_k(FlatIn a, const float* __restrict__ gamma, const double* __restrict__ sums, long long count,
                     uint16_t* __restrict__ dx, long long sdx, int dxdt, float* dgamma, float* dbeta, float* dhead_w,
@@ -793,10 +814,10 @@ bn_bwd_apply_flat_k(FlatIn a, const float* __restrict__ gamma, const double* __r
       const long long pp = p0 + u * stride;
       if (pp >= a.npix) break;
       float xv[8], z[8], dz[8], o[8];
-      flat_dz<HEAD>(a, xr[u], dr[u], dl[u], sc, sh, hw, xv, z, dz);
+      flat_dz<HEAD, DT>(a, xr[u], dr[u], dl[u], sc, sh, hw, xv, z, dz);
 #pragma unroll
       for (int k = 0; k < 8; ++k) o[k] = fmaf(ca[k], dz[k], fmaf(cb[k], xv[k], cc[k]));
-      *reinterpret_cast<uint4*>(dx + pp * sdx + c0) = pack8(o, dxdt);
+      *reinterpret_cast<uint4*>(dx + pp * sdx + c0) = pack8_t<DT>(o, dxdt);
     }
   }
 }
@@ -1181,14 +1202,22 @@ extern "C" int hpri_bn_relu_apply(const hpri_view_t* x, const float* scale, cons
   if (!pooled && CG <= 256 && pixel_dense(x) && pixel_dense(y)) {
     const int slots = 256 / CG;
     const long long npix = (long long)x->n * x->h * x->w;
-    bn_relu_apply_flat_k<<<grid_for(npix, slots * 8, 148 * 8), 256, 0, (cudaStream_t)stream>>>(
-        static_cast<const uint16_t*>(x->ptr), x->pix_stride, x->dtype, static_cast<uint16_t*>(y->ptr), y->pix_stride,
-        y->dtype, x->c, npix, scale, shift, slots, CG);
+#define HPRI_AF(DT)                                                                                              \
+    bn_relu_apply_flat_k<DT><<<grid_for(npix, slots * 8, 148 * 8), 256, 0, (cudaStream_t)stream>>>(                    \
+        static_cast<const uint16_t*>(x->ptr), x->pix_stride, x->dtype, static_cast<uint16_t*>(y->ptr), y->pix_stride, \
+        y->dtype, x->c, npix, scale, shift, slots, CG)
+    const int dtf = win_dtype(x, y, nullptr, nullptr);
+    if (dtf == DT_F16) HPRI_AF(DT_F16); else if (dtf == DT_BF16) HPRI_AF(DT_BF16); else HPRI_AF(-1);
+#undef HPRI_AF
     return last_err();
   }
   const long long total = (long long)x->n * ((x->h + 1) / 2) * ((x->w + 1) / 2) * CG;
-  bn_relu_apply_k<<<grid_for(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(mk(x), scale, shift, mk(y),
-                                                                                  mk(pooled));
+#define HPRI_AW(DT)                                                                                             \
+  bn_relu_apply_k<DT><<<grid_for(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(mk(x), scale, shift, mk(y), \
+                                                                                      mk(pooled))
+  const int dtw = win_dtype(x, y, pooled, nullptr);
+  if (dtw == DT_F16) HPRI_AW(DT_F16); else if (dtw == DT_BF16) HPRI_AW(DT_BF16); else HPRI_AW(-1);
+#undef HPRI_AW
   return last_err();
 }
 
@@ -1224,8 +1253,12 @@ extern "C" int hpri_bn_relu_bwd_reduce(const hpri_view_t* x, const float* scale,
              dy ? dy->pix_stride : 0, x->dtype, dy ? dy->dtype : 0, x->c, (long long)x->n * x->h * x->w, scale, shift,
              save_mean, save_invstd, head_w, dlogit};
     const int grid = grid_for(f.npix, slots * 8, 148 * 3);
-    if (dlogit) bn_bwd_reduce_flat_k<true><<<grid, 256, smem, (cudaStream_t)stream>>>(f, sums, slots, CG);
-    else bn_bwd_reduce_flat_k<false><<<grid, 256, smem, (cudaStream_t)stream>>>(f, sums, slots, CG);
+    const int dtf = win_dtype(x, dy, nullptr, nullptr);
+#define HPRI_RF(HD, DT) bn_bwd_reduce_flat_k<HD, DT><<<grid, 256, smem, (cudaStream_t)stream>>>(f, sums, slots, CG)
+    if (dtf == DT_F16) { if (dlogit) HPRI_RF(true, DT_F16); else HPRI_RF(false, DT_F16); }
+    else if (dtf == DT_BF16) { if (dlogit) HPRI_RF(true, DT_BF16); else HPRI_RF(false, DT_BF16); }
+    else { if (dlogit) HPRI_RF(true, -1); else HPRI_RF(false, -1); }
+#undef HPRI_RF
     return last_err();
   }
   BwdIn a{mk(x), mk(dy), mk(dpool), scale, shift, save_mean, save_invstd, head_w, dlogit};
@@ -1260,12 +1293,14 @@ extern "C" int hpri_bn_relu_bwd_apply(const hpri_view_t* x, const float* scale, 
     const int slots = 256 / CG;
     const int grid = grid_for(f.npix, slots * 8, 148 * 6);
     uint16_t* dxp = static_cast<uint16_t*>(dx->ptr);
-    if (dlogit)
-      bn_bwd_apply_flat_k<true><<<grid, 256, 0, (cudaStream_t)stream>>>(f, gamma, sums, count, dxp, dx->pix_stride,
-                                                                        dx->dtype, dgamma, dbeta, dhead_w, slots, CG);
-    else
-      bn_bwd_apply_flat_k<false><<<grid, 256, 0, (cudaStream_t)stream>>>(f, gamma, sums, count, dxp, dx->pix_stride,
-                                                                         dx->dtype, dgamma, dbeta, dhead_w, slots, CG);
+    const int dtf = win_dtype(x, dy, nullptr, dx);
+#define HPRI_PF(HD, DT)                                                                                            \
+    bn_bwd_apply_flat_k<HD, DT><<<grid, 256, 0, (cudaStream_t)stream>>>(f, gamma, sums, count, dxp, dx->pix_stride,   \
+                                                                       dx->dtype, dgamma, dbeta, dhead_w, slots, CG)
+    if (dtf == DT_F16) { if (dlogit) HPRI_PF(true, DT_F16); else HPRI_PF(false, DT_F16); }
+    else if (dtf == DT_BF16) { if (dlogit) HPRI_PF(true, DT_BF16); else HPRI_PF(false, DT_BF16); }
+    else { if (dlogit) HPRI_PF(true, -1); else HPRI_PF(false, -1); }
+#undef HPRI_PF
     return last_err();
   }
   BwdIn a{mk(x), mk(dy), mk(dpool), scale, shift, save_mean, save_invstd, head_w, dlogit};
