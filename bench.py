@@ -302,9 +302,17 @@ def main():
     peak_tf, peak_gbs, peak_src = peaks()
     flops_step = GF_PER_IMG[args.model][0 if train else 1] * 1e9 * n
     achieved = flops_step / (tensor_ms / 1e3) / 1e12 if tensor_ms > 0 else 0.0
+    # DRAM traffic of the same launches from the committed ncu capture (same workload only: CubeNET-64, batch 2, train)
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "traffic_r1g.json")
+    if args.model == "CubeNET" and n == 2 and train and os.path.exists(tp):
+        with open(tp) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj["tensor_family_dram_bytes_per_launch"], "profiles/traffic_r1g.json (ncu, per launch)"
     roofline = {"bound": "tensor", "kernel": "conv3x3_halo_kernel<BLOCK_N> + igemm_kernel<BLOCK_N,STAGES,MODE> (tcgen05 implicit GEMM family: every "
                           "conv3x3 / ConvTranspose / Linear fwd, dgrad and wgrad launch of the step)",
-                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
+                "traffic_source": traffic_src,
                 "peak_source": peak_src, "flops_per_step": flops_step, "kernel_ms_per_step": tensor_ms,
                 "launches_per_step": tensor_launches, "share_of_step": tensor_ms / all_ms if all_ms else None}
     if args.breakdown and rank == 0:

@@ -256,16 +256,22 @@ __global__ void __launch_bounds__(256)
 unpack_convT_k(float* __restrict__ g, int Cin, int Cout, int kc, float* __restrict__ dst) {
   __shared__ float tile[32][129];
   const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
-  for (int i = threadIdx.x; i < 32 * 128; i += 256) {
+  // sixteen elements per thread: all loads are issued before the first (possibly aliasing) zeroing store
+  float v[16];
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const int i = threadIdx.x + u * 256;
     const int l = i & 31, q = i >> 5;
     const int ab = q >> 5, co = q & 31;
-    float v = 0.f;
-    if (ci0 + l < Cin && co0 + co < Cout) {
-      float* src = g + ((long long)ab * Cout + co0 + co) * kc + ci0 + l;
-      v = *src;
-      *src = 0.f;
-    }
-    tile[l][co * 4 + ab] = v;
+    v[u] = (ci0 + l < Cin && co0 + co < Cout) ? __ldcs(g + ((long long)ab * Cout + co0 + co) * kc + ci0 + l) : 0.f;
+  }
+#pragma unroll
+  for (int u = 0; u < 16; ++u) {
+    const int i = threadIdx.x + u * 256;
+    const int l = i & 31, q = i >> 5;
+    const int ab = q >> 5, co = q & 31;
+    tile[l][co * 4 + ab] = v[u];
+    if (ci0 + l < Cin && co0 + co < Cout) g[((long long)ab * Cout + co0 + co) * kc + ci0 + l] = 0.f;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 32 * 128; i += 256) {
