@@ -19,6 +19,12 @@ class Conv3x3Job(C.Structure):
                 ("dgrad_dtype", C.c_int), ("tile0", C.c_int), ("pad_", C.c_int)]
 
 
+class AdamJob(C.Structure):
+    """hpri_adam_job_t (include/hyperpri_b200.h)."""
+    _fields_ = [("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+                ("numel", C.c_longlong), ("block0", C.c_int), ("pad_", C.c_int)]
+
+
 class View(C.Structure):
     """hpri_view_t: NHWC bf16 view with element strides."""
     _fields_ = [("ptr", C.c_void_p), ("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("c", C.c_int),
@@ -42,6 +48,7 @@ SIGNATURES = {
     "hpri_unpack_grads": [_p, _p, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _f, _i, _p],
     "hpri_pack_conv3x3": [_p, _i, _i, _p, _i, _p, _i, _p],
     "hpri_unpack_conv3x3": [_p, _i, _i, _p, _p],
+    "hpri_adam_step": [_p, _i, _i, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _i, _p],
     "hpri_pack_conv3x3_batch": [_p, _i, _i, _p],
     "hpri_unpack_conv3x3_batch": [_p, _i, _i, _p],
     "hpri_pack_convT2x2": [_p, _i, _i, _p, _i, _p],

@@ -280,6 +280,30 @@ unpack_convT_k(float* __restrict__ g, int Cin, int Cout, int kc, float* __restri
   }
 }
 
+// ------------------------------------------------------------------ multi-tensor Adam (torch.optim.Adam semantics)
+__global__ void __launch_bounds__(256)
+adam_k(const hpri_adam_job_t* __restrict__ jobs, int njobs, float lr, float b1, float b2, float omb1, float omb2,
+       float eps, float wd, float inv_bc1, float inv_sqrt_bc2) {
+  int j = 0;
+  while (j + 1 < njobs && jobs[j + 1].block0 <= (int)blockIdx.x) ++j;
+  const hpri_adam_job_t jb = jobs[j];
+  const long long base = (long long)(blockIdx.x - jb.block0) * 1024;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const long long i = base + u * 256 + threadIdx.x;
+    if (i >= jb.numel) break;
+    float g = jb.grad[i];
+    const float p = jb.param[i];
+    g = fmaf(wd, p, g);
+    const float m = fmaf(b1, jb.exp_avg[i], omb1 * g);          // omb = 1 - beta, rounded from double like torch
+    const float v = fmaf(b2, jb.exp_avg_sq[i], omb2 * g * g);
+    jb.exp_avg[i] = m;
+    jb.exp_avg_sq[i] = v;
+    const float denom = sqrtf(v) * inv_sqrt_bc2 + eps;
+    jb.param[i] = p - lr * inv_bc1 * (m / denom);
+  }
+}
+
 // ------------------------------------------------------------------ ingest
 // One block = 64 consecutive pixels of one output row, all bands.  Band-major coalesced fp32 reads
 // (128 B per warp request), transposed through shared memory, pixel-major coalesced bf16 writes.
@@ -1110,6 +1134,17 @@ extern "C" int hpri_pack_conv3x3_batch(const hpri_conv3x3_job_t* jobs, int njobs
 extern "C" int hpri_unpack_conv3x3_batch(const hpri_conv3x3_job_t* jobs, int njobs, int total_tiles, void* stream) {
   if (!jobs || njobs <= 0 || total_tiles <= 0) return HPRI_ERR_ARG;
   unpack_conv3x3_batch_k<<<total_tiles, 256, 0, (cudaStream_t)stream>>>(jobs, njobs);
+  return last_err();
+}
+extern "C" int hpri_adam_step(const hpri_adam_job_t* jobs, int njobs, int total_blocks, double lr, double beta1,
+                              double beta2, double eps, double weight_decay, int step, void* stream) {
+  if (!jobs || njobs <= 0 || total_blocks <= 0 || step <= 0) return HPRI_ERR_ARG;
+  // hyper-parameters arrive as doubles and are rounded once, like torch's scalar arguments
+  const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
+  adam_k<<<total_blocks, 256, 0, (cudaStream_t)stream>>>(jobs, njobs, (float)lr, (float)beta1, (float)beta2,
+                                                        (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps,
+                                                        (float)weight_decay, (float)(1.0 / bc1),
+                                                        (float)(1.0 / sqrt(bc2)));
   return last_err();
 }
 extern "C" int hpri_pack_convT2x2(const float* w, int cin, int cout, void* dst_fwd, int fwd_dtype, void* stream) {

@@ -92,7 +92,11 @@ class RootLightningModel(_Base):
     def configure_optimizers(self):
         name = self.p_optimizer.upper()
         if name == 'ADAM':
-            return optim.Adam(self.m_network.parameters(), lr=self.p_learn_rate, weight_decay=self.p_decay)
+            params = list(self.m_network.parameters())
+            if params and params[0].is_cuda:       # one native launch per step (same update rule and state_dict)
+                from ..optim import FusedAdam
+                return FusedAdam(params, lr=self.p_learn_rate, weight_decay=self.p_decay)
+            return optim.Adam(params, lr=self.p_learn_rate, weight_decay=self.p_decay)
         if name == 'SGD':
             return optim.SGD(self.m_network.parameters(), lr=self.p_learn_rate, momentum=self.p_momentum,
                              weight_decay=self.p_decay)

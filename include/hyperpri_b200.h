@@ -98,6 +98,21 @@ typedef struct {
 int hpri_pack_conv3x3_batch(const hpri_conv3x3_job_t* jobs, int njobs, int total_tiles, void* stream);
 int hpri_unpack_conv3x3_batch(const hpri_conv3x3_job_t* jobs, int njobs, int total_tiles, void* stream);
 
+/* ---- optimizer (src/PLTrainer.py:171-174: optim.Adam(lr, weight_decay)) --------------------------------
+ * One launch updates every parameter tensor (torch.optim.Adam semantics: L2 weight decay added to the gradient,
+ * bias-corrected moments, denom = sqrt(v)/sqrt(1-beta2^t) + eps).  `jobs` is a DEVICE array; block0 = number of
+ * 1024-element blocks of all previous jobs. */
+typedef struct {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  long long numel;
+  int block0, pad_;
+} hpri_adam_job_t;
+int hpri_adam_step(const hpri_adam_job_t* jobs, int njobs, int total_blocks, double lr, double beta1, double beta2,
+                   double eps, double weight_decay, int step, void* stream);
+
 /* ConvTranspose2d(k=2,s=2): W[ci][co][2][2] <-> forward operand [(a*2+b)*cout + co][kpad(ci)] (a (ci, co) transpose,
  * tiled through shared memory); unpack zeroes the packed gradient behind the read.  Padding columns are not written. */
 int hpri_pack_convT2x2(const float* w, int cin, int cout, void* dst_fwd, int fwd_dtype, void* stream);

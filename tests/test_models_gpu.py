@@ -129,7 +129,8 @@ def test_state_dict_roundtrip_and_optimizer_step_changes_output():
     out = net.state_dict()
     assert set(out) == set(sd) and all(torch.equal(out[k].cpu(), sd[k]) for k in sd if "num_batches" not in k)
     x, mask = O.synth_cube(2, 2, 3, 64, 64), O.synth_mask(2, 2, 64, 64)
-    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    from hyperpri_b200.optim import FusedAdam
+    opt = FusedAdam(net.parameters(), lr=1e-3)
     losses = []
     for _ in range(6):
         opt.zero_grad(set_to_none=True)
@@ -138,6 +139,32 @@ def test_state_dict_roundtrip_and_optimizer_step_changes_output():
         opt.step()                       # in-place update bumps param versions -> operands are re-packed
         losses.append(loss.item())
     assert losses[-1] < losses[0] - 0.05, losses
+
+
+@pytest.mark.parametrize("wd", [0.0, 1e-2])
+def test_fused_adam_matches_torch_adam(wd):
+    """hpri_adam_step (one launch for all tensors) == torch.optim.Adam step for step; state_dicts interchange."""
+    from hyperpri_b200.optim import FusedAdam
+    g = torch.Generator(device="cpu").manual_seed(5)
+    shapes = [(64, 238, 3, 3), (1000,), (7,), (3, 5, 2, 2), (1025,)]
+    pa = [torch.randn(s, generator=g).cuda().requires_grad_(True) for s in shapes]
+    pb = [p.detach().clone().requires_grad_(True) for p in pa]
+    oa, ob = FusedAdam(pa, lr=1e-2, weight_decay=wd), torch.optim.Adam(pb, lr=1e-2, weight_decay=wd)
+    for it in range(5):
+        for a, b in zip(pa, pb):
+            gr = torch.randn(a.shape, generator=g).cuda()
+            a.grad, b.grad = gr.clone(), gr.clone()
+        v0 = pa[0]._version
+        oa.step(); ob.step()
+        assert pa[0]._version > v0                     # version bump -> the engine re-packs its fp16 operands
+        for a, b in zip(pa, pb):
+            assert torch.allclose(a, b, rtol=2e-6, atol=2e-7), (it, (a - b).abs().max())
+    sa, sb = oa.state_dict(), ob.state_dict()
+    assert sa["state"].keys() == sb["state"].keys()
+    for k in sa["state"]:
+        assert set(sa["state"][k]) == {"step", "exp_avg", "exp_avg_sq"}
+        assert torch.allclose(sa["state"][k]["exp_avg_sq"], sb["state"][k]["exp_avg_sq"], rtol=1e-5, atol=1e-9)
+    ob.load_state_dict(sa)                             # a FusedAdam checkpoint resumes under torch.optim.Adam
 
 
 def test_partial_weight_change_and_fp16_host_input():
