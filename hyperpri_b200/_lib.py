@@ -48,6 +48,7 @@ SIGNATURES = {
     "hpri_unpack_grads": [_p, _p, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _f, _i, _p],
     "hpri_pack_conv3x3": [_p, _i, _i, _p, _i, _p, _i, _p],
     "hpri_unpack_conv3x3": [_p, _i, _i, _p, _p],
+    "hpri_pr_hist": [_p, _p, _ll, _p, _i, _p, _i, _p, _p, _p, _p, _p, _p],
     "hpri_adam_step": [_p, _i, _i, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _i, _p],
     "hpri_pack_conv3x3_batch": [_p, _i, _i, _p],
     "hpri_unpack_conv3x3_batch": [_p, _i, _i, _p],

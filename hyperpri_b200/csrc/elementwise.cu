@@ -997,6 +997,46 @@ bce_k(const float* __restrict__ x, const float* __restrict__ t, long long n, flo
   }
 }
 
+// ------------------------------------------------------------------ validation histograms (binned PR curve)
+__global__ void __launch_bounds__(256)
+pr_hist_k(const float* __restrict__ x, const float* __restrict__ t, long long n, const float* __restrict__ thr, int nt,
+          const float* __restrict__ cut, int nc, unsigned long long* hp, unsigned long long* hn,
+          unsigned long long* cp, unsigned long long* cn, double* bce) {
+  extern __shared__ unsigned sh[];                 // hist_pos[nt] hist_neg[nt] cut_pos[nc+1] cut_neg[nc+1] | thr | cut
+  unsigned* shp = sh; unsigned* shn = sh + nt; unsigned* scp = sh + 2 * nt; unsigned* scn = scp + nc + 1;
+  float* sthr = reinterpret_cast<float*>(scn + nc + 1);
+  float* scut = sthr + nt;
+  for (int i = threadIdx.x; i < 2 * nt + 2 * (nc + 1); i += blockDim.x) sh[i] = 0;
+  for (int i = threadIdx.x; i < nt; i += blockDim.x) sthr[i] = thr[i];
+  for (int i = threadIdx.x; i < nc; i += blockDim.x) scut[i] = cut[i];
+  __syncthreads();
+  float l = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = __ldg(x + i), y = __ldg(t + i);
+    l += fmaxf(v, 0.f) - v * y + log1pf(expf(-fabsf(v)));
+    const float p = 1.f / (1.f + expf(-v));        // torch.sigmoid's formula, precise expf and IEEE division
+    int b = min((int)(p * (float)(nt - 1)), nt - 1);
+    while (b + 1 < nt && sthr[b + 1] <= p) ++b;
+    while (b > 0 && sthr[b] > p) --b;
+    int k = min((int)(p * (float)(nc - 1)), nc);
+    while (k < nc && scut[k] < p) ++k;
+    while (k > 0 && scut[k - 1] >= p) --k;
+    if (y > 0.5f) { atomicAdd(shp + b, 1u); atomicAdd(scp + k, 1u); }
+    else { atomicAdd(shn + b, 1u); atomicAdd(scn + k, 1u); }
+  }
+  for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(bce, (double)l);
+  __syncthreads();
+  for (int i = threadIdx.x; i < nt; i += blockDim.x) {
+    if (shp[i]) atomicAdd(hp + i, (unsigned long long)shp[i]);
+    if (shn[i]) atomicAdd(hn + i, (unsigned long long)shn[i]);
+  }
+  for (int i = threadIdx.x; i <= nc; i += blockDim.x) {
+    if (scp[i]) atomicAdd(cp + i, (unsigned long long)scp[i]);
+    if (scn[i]) atomicAdd(cn + i, (unsigned long long)scn[i]);
+  }
+}
+
 // ------------------------------------------------------------------ channel sums
 __global__ void __launch_bounds__(256) colsum_k(V x, float* out, int slots, int CG) {
   extern __shared__ float red[];                 // [slots][CG*8]
@@ -1134,6 +1174,16 @@ extern "C" int hpri_pack_conv3x3_batch(const hpri_conv3x3_job_t* jobs, int njobs
 extern "C" int hpri_unpack_conv3x3_batch(const hpri_conv3x3_job_t* jobs, int njobs, int total_tiles, void* stream) {
   if (!jobs || njobs <= 0 || total_tiles <= 0) return HPRI_ERR_ARG;
   unpack_conv3x3_batch_k<<<total_tiles, 256, 0, (cudaStream_t)stream>>>(jobs, njobs);
+  return last_err();
+}
+extern "C" int hpri_pr_hist(const float* logits, const float* target, long long numel, const float* thr, int n_thr,
+                            const float* cut, int n_cut, unsigned long long* hist_pos, unsigned long long* hist_neg,
+                            unsigned long long* cut_pos, unsigned long long* cut_neg, double* bce_sum, void* stream) {
+  if (!logits || !target || !thr || !cut || !hist_pos || !hist_neg || !cut_pos || !cut_neg || !bce_sum) return HPRI_ERR_ARG;
+  if (numel <= 0 || n_thr < 2 || n_cut < 1 || n_thr > 4096 || n_cut > 1024) return HPRI_ERR_ARG;
+  const size_t smem = (size_t)(2 * n_thr + 2 * (n_cut + 1)) * 4 + (size_t)(n_thr + n_cut) * 4;
+  pr_hist_k<<<grid_for(numel, 256 * 16, 148 * 4), 256, smem, (cudaStream_t)stream>>>(
+      logits, target, numel, thr, n_thr, cut, n_cut, hist_pos, hist_neg, cut_pos, cut_neg, bce_sum);
   return last_err();
 }
 extern "C" int hpri_adam_step(const hpri_adam_job_t* jobs, int njobs, int total_blocks, double lr, double beta1,

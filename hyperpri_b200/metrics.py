@@ -52,3 +52,50 @@ def binned_pr_curve(probs: torch.Tensor, target: torch.Tensor, n_thresholds: int
 def average_precision(precision, recall):
     """-sum((r[i+1]-r[i]) * p[i]) over the curve (torchmetrics' reduction)."""
     return -torch.sum((recall[1:] - recall[:-1]) * precision[:-1])
+
+
+class DevicePRCurve:
+    """Validation maths without moving predictions to the host (reference PLTrainer.py:538-583 concatenates every
+    prediction on the CPU): per batch one kernel accumulates the 500-bin probability histograms by mask class, a
+    second family of bins at the two-decimal thresholds the best-Dice search can return, and the BCE sum.
+    compute() gives the same (precision, recall, thresholds) as binned_pr_curve; counts_at(thr) the confusion
+    counts for seg = p > thr at any two-decimal threshold."""
+
+    def __init__(self, device, n_thresholds: int = 500):
+        from . import ops
+        self._ops = ops
+        self.thr = torch.linspace(0, 1, n_thresholds, device=device)
+        self.cut = torch.round(torch.arange(0, 101, device=device, dtype=torch.float32) / 100, decimals=2)
+        z = lambda n: torch.zeros(n, dtype=torch.int64, device=device)
+        self.hp, self.hn = z(n_thresholds), z(n_thresholds)
+        self.cp, self.cn = z(102), z(102)
+        self.bce = torch.zeros((), dtype=torch.float64, device=device)
+        self.numel = 0
+
+    def update(self, logits: torch.Tensor, mask: torch.Tensor):
+        lg = logits.detach().reshape(-1).float().contiguous()
+        mk = mask.reshape(-1).float().contiguous()
+        self._ops.pr_hist(lg, mk, self.thr, self.cut, self.hp, self.hn, self.cp, self.cn, self.bce)
+        self.numel += lg.numel()
+
+    def bce_loss(self):
+        return (self.bce / max(self.numel, 1)).float()
+
+    def compute(self):
+        hp, hn = self.hp.double(), self.hn.double()
+        tps = hp.flip(0).cumsum(0).flip(0)
+        fps = hn.flip(0).cumsum(0).flip(0)
+        npos = hp.sum()
+        precision = torch.where(tps + fps > 0, tps / (tps + fps).clamp_min(1e-30), torch.zeros_like(tps))
+        recall = torch.where(npos > 0, tps / npos.clamp_min(1e-30), torch.zeros_like(tps))
+        one = torch.ones(1, dtype=precision.dtype, device=precision.device)
+        return (torch.cat([precision, one]).float(), torch.cat([recall, torch.zeros_like(one)]).float(), self.thr)
+
+    def counts_at(self, threshold):
+        """(tp, fp, fn, tn) for seg = sigmoid(logit) > threshold; threshold must be one of 0.00, 0.01, ..., 1.00."""
+        k = int(torch.argmin((self.cut - float(threshold)).abs()).item())
+        if abs(float(self.cut[k]) - float(threshold)) > 1e-6:
+            raise ValueError("counts_at needs a two-decimal threshold")
+        cp, cn = self.cp.double(), self.cn.double()
+        tp, fp = cp[k + 1:].sum(), cn[k + 1:].sum()          # bins k+1.. hold p > cut[k]
+        return tp, fp, cp.sum() - tp, cn.sum() - fp

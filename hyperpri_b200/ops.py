@@ -341,3 +341,14 @@ def scale_check(x, scale, flag):
 @_timed
 def sum_f32(x, out):
     check(_lib.lib().hpri_sum_f32(_ptr(x), x.numel(), _ptr(out), _stream()), "hpri_sum_f32")
+
+
+# ----------------------------------------------------------------------------- validation histograms
+@_timed
+def pr_hist(logits, target, thr, cut, hist_pos, hist_neg, cut_pos, cut_neg, bce_sum):
+    """Accumulate the binned-PR-curve histograms of one batch (see hpri_pr_hist)."""
+    assert logits.dtype == torch.float32 and target.dtype == torch.float32 and logits.is_contiguous()
+    assert target.is_contiguous() and logits.numel() == target.numel()
+    check(_lib.lib().hpri_pr_hist(_ptr(logits), _ptr(target), logits.numel(), _ptr(thr), thr.numel(), _ptr(cut),
+                                  cut.numel(), _ptr(hist_pos), _ptr(hist_neg), _ptr(cut_pos), _ptr(cut_neg),
+                                  _ptr(bce_sum), _stream()), "hpri_pr_hist")

@@ -207,23 +207,44 @@ def _collect(model, loader, trainer):
     return logits, masks
 
 
+def _sweep_device(model, loader, trainer):
+    """Prediction sweep that keeps everything on the GPU: per batch, forward + one histogram kernel
+    (metrics.DevicePRCurve).  The reference moves every prediction to the host and concatenates (:142-162, :538)."""
+    model.to(trainer.device).eval()
+    curve = M.DevicePRCurve(trainer.device, 500)
+    with torch.no_grad():
+        for batch in loader:
+            b = _to_device(batch, trainer.device)
+            curve.update(model._pred(b), b['mask'])
+    return curve
+
+
+def _use_device_sweep(trainer, save_segmaps):
+    return isinstance(trainer, _Loop) and trainer.device.type == "cuda" and not save_segmaps
+
+
 def validate_net(val_data, params, pl_trainer=None, save_segmaps=False):
     """PLTrainer.py:463-609: predict, BCE, 500-threshold PR curve, best-Dice threshold, Acc/IoU/AP/confusion.
     Returns (precision, recall, thresholds)."""
     loader = DataLoader(val_data, batch_size=params.b_size['test'], shuffle=False)
     model = getattr(pl_trainer, "model", None) or load_val_model(params)
     trainer = pl_trainer if isinstance(pl_trainer, _Loop) else _Loop(params, 0)
-    logits, masks = _collect(model, loader, trainer)
-    bce = params.criterion(logits, masks.float())
-    probs = torch.sigmoid(logits)
-    prec, rec, thr = M.binned_pr_curve(probs, masks, 500)
+    curve = None
+    if _use_device_sweep(trainer, save_segmaps):
+        curve = _sweep_device(model, loader, trainer)
+        bce = curve.bce_loss()
+        prec, rec, thr = curve.compute()
+    else:
+        logits, masks = _collect(model, loader, trainer)
+        bce = params.criterion(logits, masks.float())
+        probs = torch.sigmoid(logits)
+        prec, rec, thr = M.binned_pr_curve(probs, masks, 500)
     crop = int(len(prec) // 100)
     tp_, tr_, tt_ = prec[crop:-crop], rec[crop:-crop], thr[crop:-crop]     # top/bottom thresholds excluded (:547-550)
     dice_curve = 2 * tp_ * tr_ / (tp_ + tr_).clamp_min(1e-30)
     bi = torch.argmax(dice_curve)
     best_thr = torch.round(tt_[min(bi, len(tt_) - 1)].float(), decimals=2)
-    seg = probs > best_thr
-    c = M.confusion_counts(seg, masks)
+    c = curve.counts_at(best_thr) if curve is not None else M.confusion_counts(probs > best_thr, masks)
     ap = M.average_precision(prec, rec)
     print(f"\n{params.model_name}\n   Best Threshold {best_thr:.3f}:")
     print(f"      BCE Loss : {bce:.3f}\n      Pixel Acc: {M.accuracy(*c):.3f}\n      Precision: {tp_[bi]:.3f}")
@@ -243,10 +264,16 @@ def test_net(test_data, params, best_threshold, pl_trainer=None, save_segmaps=Fa
     loader = DataLoader(test_data, batch_size=params.b_size['test'], shuffle=False)
     model = getattr(pl_trainer, "model", None) or load_val_model(params)
     trainer = pl_trainer if isinstance(pl_trainer, _Loop) else _Loop(params, 0)
-    logits, masks = _collect(model, loader, trainer)
-    probs = torch.sigmoid(logits)
-    c = M.confusion_counts(probs > best_threshold, masks)
-    prec, rec, _ = M.binned_pr_curve(probs, masks, 500)
+    thr2 = round(float(best_threshold), 2)
+    if _use_device_sweep(trainer, save_segmaps) and abs(thr2 - float(best_threshold)) < 1e-6:
+        curve = _sweep_device(model, loader, trainer)
+        c = curve.counts_at(thr2)
+        prec, rec, _ = curve.compute()
+    else:
+        logits, masks = _collect(model, loader, trainer)
+        probs = torch.sigmoid(logits)
+        c = M.confusion_counts(probs > best_threshold, masks)
+        prec, rec, _ = M.binned_pr_curve(probs, masks, 500)
     out = {"acc": float(M.accuracy(*c)), "dice": float(M.dice(*c)), "pos_iou": float(M.jaccard(*c)),
            "avg_prec": float(M.average_precision(prec, rec))}
     print(f"Threshold {float(best_threshold):.3f}:")

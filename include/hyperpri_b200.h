@@ -98,6 +98,18 @@ typedef struct {
 int hpri_pack_conv3x3_batch(const hpri_conv3x3_job_t* jobs, int njobs, int total_tiles, void* stream);
 int hpri_unpack_conv3x3_batch(const hpri_conv3x3_job_t* jobs, int njobs, int total_tiles, void* stream);
 
+/* ---- validation maths (src/PLTrainer.py:538-583: binned PR curve with thresholds=500, best-Dice threshold, counts) ----
+ * One pass over a batch of logits accumulates (+=, caller zeroes once per sweep):
+ *   hist_pos / hist_neg [n_thr]   : pixels whose p = sigmoid(logit) falls in bin i = max{i : thr[i] <= p}, by mask class
+ *                                   (torchmetrics' binned curve: tps[i] = sum_{j>=i} hist_pos[j])
+ *   cut_pos / cut_neg [n_cut + 1] : pixels with exactly k of the cuts below p (cut[k-1] < p <= cut[k]), so the
+ *                                   confusion counts at ANY threshold cut[k] (p > cut[k]) follow without a second pass
+ *   bce_sum                       : sum of the stable BCE-with-logits terms (double)
+ * thr and cut are ascending device arrays. */
+int hpri_pr_hist(const float* logits, const float* target, long long numel, const float* thr, int n_thr,
+                 const float* cut, int n_cut, unsigned long long* hist_pos, unsigned long long* hist_neg,
+                 unsigned long long* cut_pos, unsigned long long* cut_neg, double* bce_sum, void* stream);
+
 /* ---- optimizer (src/PLTrainer.py:171-174: optim.Adam(lr, weight_decay)) --------------------------------
  * One launch updates every parameter tensor (torch.optim.Adam semantics: L2 weight decay added to the gradient,
  * bias-corrected moments, denom = sqrt(v)/sqrt(1-beta2^t) + eps).  `jobs` is a DEVICE array; block0 = number of

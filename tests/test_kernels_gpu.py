@@ -275,6 +275,32 @@ def test_scale_check_unscales_and_flags_overflow():
     assert flag.item() == 1
 
 
+def test_device_pr_curve_matches_torch_restatement():
+    """hpri_pr_hist + DevicePRCurve == metrics.binned_pr_curve / confusion_counts on the concatenated predictions."""
+    from hyperpri_b200 import metrics as M
+    g = torch.Generator(device="cpu").manual_seed(11)
+    curve = M.DevicePRCurve(torch.device(DEV), 500)
+    all_l, all_m = [], []
+    for n in (70001, 123457, 5):
+        lg = (torch.randn(n, generator=g) * 3).to(DEV)
+        mk = (torch.rand(n, generator=g) > 0.9).float().to(DEV)
+        lg[:3] = torch.tensor([0.0, 40.0, -40.0], device=DEV)[: min(3, n)]     # p = 0.5, 1.0, ~0
+        curve.update(lg, mk)
+        all_l.append(lg); all_m.append(mk)
+    lg, mk = torch.cat(all_l), torch.cat(all_m)
+    probs = torch.sigmoid(lg)
+    p0, r0, t0 = M.binned_pr_curve(probs, mk, 500)
+    p1, r1, t1 = curve.compute()
+    assert torch.equal(t0, t1) and torch.equal(p0, p1) and torch.equal(r0, r1)
+    ref_loss = torch.nn.functional.binary_cross_entropy_with_logits(lg, mk)
+    assert abs(curve.bce_loss().item() - ref_loss.item()) < 1e-5
+    for thr in (0.0, 0.31, 0.5, 0.77, 1.0):
+        t = torch.round(torch.tensor(thr), decimals=2).to(DEV)
+        want = [float(v) for v in M.confusion_counts(probs > t, mk)]
+        got = [float(v) for v in curve.counts_at(thr)]
+        assert got == want, (thr, got, want)
+
+
 def test_mixed_format_rejected_and_convert():
     x = nhwc(rnd(1, 64, 8, 8, seed=40), dt=FH)
     dy = nhwc(rnd(1, 64, 8, 8, seed=41), dt=BF)
