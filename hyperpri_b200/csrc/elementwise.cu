@@ -305,76 +305,66 @@ adam_k(const hpri_adam_job_t* __restrict__ jobs, int njobs, float lr, float b1, 
 }
 
 // ------------------------------------------------------------------ ingest
-// One block = 64 consecutive pixels of one output row, all bands.  Band-major coalesced fp32 reads
-// (128 B per warp request), transposed through shared memory, pixel-major coalesced bf16 writes.
+// One block = 64 consecutive pixels of one output row, all bands.  A thread gathers 8 consecutive bands of ONE pixel
+// (eight coalesced 4-byte loads: the lanes of a warp are 32 neighbouring pixels of a band plane), packs them into one
+// 16-byte chunk and stores it to shared memory at [pixel][chunk ^ (pixel & 7)] (conflict-free 16-byte accesses both
+// ways); the block's output -- 64 pixels x c_pad channels, contiguous in NHWC -- then leaves as 16-byte stores.
+// ~5 instructions per element (the first version spent 42, mostly 64-bit address arithmetic, and was issue-bound at
+// 51 % of DRAM peak: profiles/ncu_full_r1g_summary.csv).
 __device__ __forceinline__ float ld_src(const float* p) { return __ldg(p); }
 __device__ __forceinline__ float ld_src(const __half* p) { return __half2float(__ldg(p)); }
 
-template <typename T>
+template <typename T, bool PLAIN>
 __global__ void __launch_bounds__(256)
 hsi_ingest_k(const T* __restrict__ src, int bands_total, int H, int W, int lo, int nb, int i0, int j0, int h,
              int w, int flip_h, int flip_w, float scale, const float* __restrict__ bmean,
              const float* __restrict__ bstd, uint16_t* __restrict__ dst, int dt, int c_pad) {
-  extern __shared__ uint32_t tile_w[];          // [64][c_pad/2 + 1] words (odd stride -> conflict-free)
-  const int wstride = c_pad / 2 + 1;
+  extern __shared__ uint4 tile4[];               // [64 pixels][row_chunks] 16-byte chunks
+  const int chunks = c_pad >> 3;                 // 8 channels per chunk
+  const int row_chunks = (chunks + 7) & ~7;
   const int xt = blockIdx.x, y = blockIdx.y, n = blockIdx.z;
   const int x0 = xt * 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sy = i0 + (flip_h ? h - 1 - y : y);
-  const T* img = src + ((long long)n * bands_total + lo) * H * W + (long long)sy * W;
-  // a warp takes band PAIRS (2j, 2j+1) so that one 32-bit shared-memory word carries both; three pairs are walked
-  // at a time: twelve independent 128-byte row segments in flight per thread
-  const int xa = x0 + lane, xb = x0 + lane + 32;
-  const int ca = j0 + (flip_w ? w - 1 - xa : xa), cb = j0 + (flip_w ? w - 1 - xb : xb);
-  const bool ina = xa < w, inb = xb < w;
-  const int npairs = c_pad / 2;
-  constexpr int UB = 3;
-  for (int j0p = warp; j0p < npairs; j0p += 8 * UB) {
-    float v[UB][4];
+  const long long HW = (long long)H * W;
+  const T* img = src + ((long long)n * bands_total + lo) * HW + (long long)sy * W + j0;
+  const int units = 2 * chunks;                  // (pixel half, chunk)
+  for (int u = warp; u < units; u += 8) {
+    const int half = u >= chunks ? 1 : 0;
+    const int q = u - half * chunks;
+    const int px = half * 32 + lane;
+    const int x = x0 + px;
+    const bool in = x < w;
+    const T* p = img + (flip_w ? w - 1 - x : x) + (long long)(q * 8) * HW;
+    float v[8];
 #pragma unroll
-    for (int u = 0; u < UB; ++u) {
-      const int b = 2 * (j0p + 8 * u);
+    for (int k = 0; k < 8; ++k) {
+      v[k] = (in && q * 8 + k < nb) ? ld_src(p) : 0.f;
+      p += HW;
+    }
+    if (!PLAIN) {
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        v[u][2 * e] = 0.f; v[u][2 * e + 1] = 0.f;
-        if (b + e < nb) {
-          const T* row = img + (long long)(b + e) * H * W;
-          if (ina) v[u][2 * e] = ld_src(row + ca);
-          if (inb) v[u][2 * e + 1] = ld_src(row + cb);
-        }
+      for (int k = 0; k < 8; ++k) {
+        const int b = q * 8 + k;
+        float a = v[k] * scale;
+        if (bmean != nullptr && b < nb) a = (a - __ldg(bmean + b)) * (1.f / __ldg(bstd + b));
+        v[k] = b < nb ? a : 0.f;
       }
     }
-#pragma unroll
-    for (int u = 0; u < UB; ++u) {
-      const int jp = j0p + 8 * u;
-      if (jp >= npairs) break;
-      const int b = 2 * jp;
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        float a0 = v[u][2 * e] * scale, a1 = v[u][2 * e + 1] * scale;
-        if (bmean != nullptr && b + e < nb) {
-          const float m = __ldg(bmean + b + e), is = 1.f / __ldg(bstd + b + e);
-          a0 = (a0 - m) * is; a1 = (a1 - m) * is;
-        }
-        if (b + e >= nb) { a0 = 0.f; a1 = 0.f; }
-        v[u][2 * e] = a0; v[u][2 * e + 1] = a1;
-      }
-      tile_w[lane * wstride + jp] = pack2(v[u][0], v[u][2], dt);            // pixel xa: bands b, b+1
-      tile_w[(lane + 32) * wstride + jp] = pack2(v[u][1], v[u][3], dt);     // pixel xb
-    }
+    uint4 o;
+    o.x = pack2(v[0], v[1], dt); o.y = pack2(v[2], v[3], dt); o.z = pack2(v[4], v[5], dt); o.w = pack2(v[6], v[7], dt);
+    tile4[px * row_chunks + (q ^ (px & 7))] = o;
   }
   __syncthreads();
-  const int wpp = c_pad / 2;                    // words per pixel
   const int npix = min(64, w - x0);
-  uint32_t* out = reinterpret_cast<uint32_t*>(dst + (((long long)n * h + y) * w + x0) * c_pad);
-  // i = px * wpp + k walks the block's contiguous output; (px, k) are advanced without divisions
-  const int total = npix * wpp;
-  int px = threadIdx.x / wpp, k = threadIdx.x - px * wpp;
-  const int dpx = 256 / wpp, dk = 256 - dpx * wpp;
+  uint4* out = reinterpret_cast<uint4*>(dst + (((long long)n * h + y) * w + x0) * c_pad);
+  const int total = npix * chunks;
+  int px = threadIdx.x / chunks, q = threadIdx.x - px * chunks;
+  const int dpx = 256 / chunks, dq = 256 - dpx * chunks;
   for (int i = threadIdx.x; i < total; i += 256) {
-    out[i] = tile_w[px * wstride + k];
-    px += dpx; k += dk;
-    if (k >= wpp) { k -= wpp; ++px; }
+    out[i] = tile4[px * row_chunks + (q ^ (px & 7))];
+    px += dpx; q += dq;
+    if (q >= chunks) { q -= chunks; ++px; }
   }
 }
 
@@ -1226,18 +1216,25 @@ static int ingest_launch(const T* src, int n, int bands_total, int H, int W, int
   if (i0 < 0 || j0 < 0 || i0 + h > H || j0 + w > W || h <= 0 || w <= 0 || h > 65535 || n > 65535) return HPRI_ERR_ARG;
   if ((band_mean == nullptr) != (band_std == nullptr)) return HPRI_ERR_ARG;
   if (reinterpret_cast<uintptr_t>(dst) & 15) return HPRI_ERR_ALIGN;
-  const size_t smem = 64 * (c_pad / 2 + 1) * 4;
+  const size_t smem = (size_t)64 * (((c_pad >> 3) + 7) & ~7) * 16;
+  if (smem > 100 * 1024) return HPRI_ERR_ARG;
+  const bool plain = scale == 1.0f && band_mean == nullptr;
   static bool attr_done = false;
-  if (!attr_done && smem > 48 * 1024) {
-    if (cudaFuncSetAttribute(hsi_ingest_k<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(hsi_ingest_k<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(hsi_ingest_k<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
       return HPRI_ERR_CUDA;
     attr_done = true;
   }
-  if (smem > 100 * 1024) return HPRI_ERR_ARG;
   dim3 grid((w + 63) / 64, h, n);
-  hsi_ingest_k<T><<<grid, 256, smem, (cudaStream_t)stream>>>(src, bands_total, H, W, lo, nb, i0, j0, h, w, flip_h,
-                                                            flip_w, scale, band_mean, band_std, (uint16_t*)dst,
-                                                            dst_dtype, c_pad);
+  if (plain)
+    hsi_ingest_k<T, true><<<grid, 256, smem, (cudaStream_t)stream>>>(src, bands_total, H, W, lo, nb, i0, j0, h, w, flip_h,
+                                                                    flip_w, scale, band_mean, band_std, (uint16_t*)dst,
+                                                                    dst_dtype, c_pad);
+  else
+    hsi_ingest_k<T, false><<<grid, 256, smem, (cudaStream_t)stream>>>(src, bands_total, H, W, lo, nb, i0, j0, h, w, flip_h,
+                                                                     flip_w, scale, band_mean, band_std, (uint16_t*)dst,
+                                                                     dst_dtype, c_pad);
   return last_err();
 }
 extern "C" int hpri_hsi_ingest(const float* src, int n, int bands_total, int H, int W, int lo, int hi, int i0,
