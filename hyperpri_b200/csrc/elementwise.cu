@@ -1340,7 +1340,7 @@ extern "C" int hpri_bn_relu_bwd_reduce(const hpri_view_t* x, const float* scale,
     FlatIn f{static_cast<const uint16_t*>(x->ptr), dy ? static_cast<const uint16_t*>(dy->ptr) : nullptr, x->pix_stride,
              dy ? dy->pix_stride : 0, x->dtype, dy ? dy->dtype : 0, x->c, (long long)x->n * x->h * x->w, scale, shift,
              save_mean, save_invstd, head_w, dlogit};
-    const int grid = grid_for(f.npix, slots * 8, 148 * 3);
+    const int grid = grid_for(f.npix, slots * 8, 148 * 4);
     const int dtf = win_dtype(x, dy, nullptr, nullptr);
 #define HPRI_RF(HD, DT) bn_bwd_reduce_flat_k<HD, DT><<<grid, 256, smem, (cudaStream_t)stream>>>(f, sums, slots, CG)
     if (dtf == DT_F16) { if (dlogit) HPRI_RF(true, DT_F16); else HPRI_RF(false, DT_F16); }
