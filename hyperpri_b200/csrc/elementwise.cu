@@ -432,38 +432,44 @@ __global__ void bn_finalize_k(double* stats, long long count, const float* gamma
 // One thread = one 2x2 pixel window x 8 channels.
 template <int DT>
 __global__ void __launch_bounds__(256)
-bn_relu_apply_k(V x, const float* __restrict__ scale, const float* __restrict__ shift, V y, V pool) {
-  const int CG = (x.c + 7) >> 3;
+bn_relu_apply_k(V x, const float* __restrict__ scale, const float* __restrict__ shift, V y, V pool, int CG, int rows) {
+  // grid.x tiles the (window column, channel group) plane, grid.y chunks of `rows` window rows, grid.z the image:
+  // a thread keeps its scale / shift in registers and walks rows without index arithmetic
   const int wh = (x.h + 1) >> 1, ww = (x.w + 1) >> 1;
-  const long long total = (long long)x.n * wh * ww * CG;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % CG);
-    long long j = i / CG;
-    const int wx = (int)(j % ww); j /= ww;
-    const int wy = (int)(j % wh);
-    const int n = (int)(j / wh);
-    const int c0 = cg * 8;
-    float sc[8], sh[8];
-    ld8p(scale, c0, x.c, sc);
-    ld8p(shift, c0, x.c, sh);
+  const int g = blockIdx.x * 256 + threadIdx.x;
+  const int cg = g % CG, wx = g / CG;
+  if (wx >= ww) return;
+  const int n = blockIdx.z;
+  const int c0 = cg * 8;
+  float sc[8], sh[8];
+  ld8v(scale, c0, x.c, sc);
+  ld8v(shift, c0, x.c, sh);
+  const int wy1 = min(wh, (int)(blockIdx.y + 1) * rows);
+  for (int wy = blockIdx.y * rows; wy < wy1; ++wy) {
+    uint4 r[4];
+    bool inb[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int yy = 2 * wy + (q >> 1), xx = 2 * wx + (q & 1);
+      inb[q] = yy < x.h && xx < x.w;
+      r[q] = make_uint4(0, 0, 0, 0);
+      if (inb[q]) r[q] = __ldg(reinterpret_cast<const uint4*>(at(x, n, yy, xx, c0)));
+    }
     float mx[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) mx[k] = -INFINITY;
 #pragma unroll
-    for (int dy = 0; dy < 2; ++dy)
+    for (int q = 0; q < 4; ++q) {
+      if (!inb[q]) continue;
+      float f[8];
+      unpack8_t<DT>(r[q], f, x.dt);
 #pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        const int yy = 2 * wy + dy, xx = 2 * wx + dx;
-        if (yy >= x.h || xx >= x.w) continue;
-        float f[8];
-        unpack8_t<DT>(__ldg(reinterpret_cast<const uint4*>(at(x, n, yy, xx, c0))), f, x.dt);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          f[k] = fmaxf(fmaf(f[k], sc[k], sh[k]), 0.f);
-          mx[k] = fmaxf(mx[k], f[k]);
-        }
-        *reinterpret_cast<uint4*>(at(y, n, yy, xx, c0)) = pack8_t<DT>(f, y.dt);
+      for (int k = 0; k < 8; ++k) {
+        f[k] = fmaxf(fmaf(f[k], sc[k], sh[k]), 0.f);
+        mx[k] = fmaxf(mx[k], f[k]);
       }
+      *reinterpret_cast<uint4*>(at(y, n, 2 * wy + (q >> 1), 2 * wx + (q & 1), c0)) = pack8_t<DT>(f, y.dt);
+    }
     if (pool.p != nullptr && wy < pool.h && wx < pool.w)
       *reinterpret_cast<uint4*>(at(pool, n, wy, wx, c0)) = pack8_t<DT>(mx, pool.dt);
   }
@@ -1299,10 +1305,10 @@ extern "C" int hpri_bn_relu_apply(const hpri_view_t* x, const float* scale, cons
 #undef HPRI_AF
     return last_err();
   }
-  const long long total = (long long)x->n * ((x->h + 1) / 2) * ((x->w + 1) / 2) * CG;
-#define HPRI_AW(DT)                                                                                             \
-  bn_relu_apply_k<DT><<<grid_for(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(mk(x), scale, shift, mk(y), \
-                                                                                      mk(pooled))
+  int rows = 0;
+  const dim3 wgrid = win_grid(x, CG, &rows);
+#define HPRI_AW(DT) \
+  bn_relu_apply_k<DT><<<wgrid, 256, 0, (cudaStream_t)stream>>>(mk(x), scale, shift, mk(y), mk(pooled), CG, rows)
   const int dtw = win_dtype(x, y, pooled, nullptr);
   if (dtw == DT_F16) HPRI_AW(DT_F16); else if (dtw == DT_BF16) HPRI_AW(DT_BF16); else HPRI_AW(-1);
 #undef HPRI_AW
