@@ -25,6 +25,14 @@ class AdamJob(C.Structure):
                 ("numel", C.c_longlong), ("block0", C.c_int), ("pad_", C.c_int)]
 
 
+class BnFin(C.Structure):
+    """hpri_bn_fin_t (include/hyperpri_b200.h)."""
+    _fields_ = [("gamma", C.c_void_p), ("beta", C.c_void_p), ("conv_bias", C.c_void_p), ("running_mean", C.c_void_p),
+                ("running_var", C.c_void_p), ("num_batches_tracked", C.c_void_p), ("scale", C.c_void_p),
+                ("shift", C.c_void_p), ("save_mean", C.c_void_p), ("save_invstd", C.c_void_p),
+                ("counter", C.c_void_p), ("count", C.c_longlong), ("momentum", C.c_float), ("eps", C.c_float)]
+
+
 class View(C.Structure):
     """hpri_view_t: NHWC bf16 view with element strides."""
     _fields_ = [("ptr", C.c_void_p), ("n", C.c_int), ("h", C.c_int), ("w", C.c_int), ("c", C.c_int),
@@ -39,7 +47,7 @@ _p, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 SIGNATURES = {
     "hpri_abi_version": [],
     "hpri_launch_count": [],
-    "hpri_igemm_fwd": [_VP, _p, _i, _i, _i, _i, _VP, _i, _p, _p, _i, _i, _p],
+    "hpri_igemm_fwd": [_VP, _p, _i, _i, _i, _i, _VP, _i, _p, _p, _i, _i, C.POINTER(BnFin), _p],
     "hpri_set_conv_algo": [_i],
     "hpri_convT2x2_fwd": [_VP, _p, _i, _i, _i, _VP, _p, _i, _p],
     "hpri_convT2x2_dgrad": [_VP, _p, _i, _i, _i, _VP, _i, _p],

@@ -49,6 +49,9 @@ struct IgemmArgs {
   int a_dt, b_dt, out_dt; // element formats (DT_BF16 / DT_F16) of the A, B operands and the fwd output
   // ---- halo kernel pipeline shape (runtime: depends on the tile aspect)
   int stages, a_bytes;
+  // ---- fused train-mode BatchNorm finalisation (has_fin): done by the last CTA to flush its statistics
+  int has_fin;
+  hpri_bn_fin_t fin;
 };
 
 constexpr int kThreads = 320;
@@ -119,6 +122,44 @@ __device__ __forceinline__ void flush_stats(float* ssum, float* ssq, int ch, int
   if (ch + 1 < n_total && (s.y != 0.f || q.y != 0.f)) { atomicAdd(&ssum[ch + 1], s.y); atomicAdd(&ssq[ch + 1], q.y); }
   s = make_float2(0.f, 0.f);
   q = make_float2(0.f, 0.f);
+}
+
+// Called by the 256 epilogue threads after their CTA's statistics went to global memory: the last CTA of the grid
+// (ticket counter) turns (sum, sumsq) into scale / shift / saved mean / invstd and the running-stat update -- the
+// arithmetic of bn_finalize_k -- and leaves stats and the counter zeroed for the next step.
+__device__ __forceinline__ void bn_finalize_tail(const IgemmArgs& p, int et, int* flag_smem) {
+  __threadfence();
+  named_bar_sync(3, kEpiThreads);
+  if (et == 0) *flag_smem = atomicAdd(p.fin.counter, 1u) == gridDim.x - 1 ? 1 : 0;
+  named_bar_sync(3, kEpiThreads);
+  if (*flag_smem == 0) return;
+  __threadfence();
+  const hpri_bn_fin_t& f = p.fin;
+  for (int c = et; c < p.n_total; c += kEpiThreads) {
+    const double s = __ldcg(p.stats + 2 * c), ss = __ldcg(p.stats + 2 * c + 1);
+    const double mean = s / (double)f.count;
+    double var = ss / (double)f.count - mean * mean;
+    if (var < 0) var = 0;
+    const float g = f.gamma ? f.gamma[c] : 1.f, b = f.beta ? f.beta[c] : 0.f;
+    const float cb = f.conv_bias ? f.conv_bias[c] : 0.f;
+    const float inv = (float)(1.0 / sqrt(var + (double)f.eps));
+    const float sc = g * inv;
+    f.scale[c] = sc;
+    f.shift[c] = b - (float)mean * sc;
+    if (f.save_mean) f.save_mean[c] = (float)mean;
+    if (f.save_invstd) f.save_invstd[c] = inv;
+    if (f.running_mean) f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * ((float)mean + cb);
+    if (f.running_var) {
+      const double unb = f.count > 1 ? var * (double)f.count / (double)(f.count - 1) : var;
+      f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * (float)unb;
+    }
+    p.stats[2 * c] = 0.0;
+    p.stats[2 * c + 1] = 0.0;
+  }
+  if (et == 0) {
+    if (f.num_batches_tracked) *f.num_batches_tracked += 1;
+    *f.counter = 0u;
+  }
 }
 
 // fwd: k-block = 64 channels of one tap: A 128 pixels x 128 B, B BLOCK_N rows x 128 B.
@@ -457,6 +498,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
           atomicAdd(p.stats + 2 * ch + 1, static_cast<double>(b));
         }
       }
+      if (p.has_fin) bn_finalize_tail(p, threadIdx.x - 64, reinterpret_cast<int*>(tmem_ptr + 1));
     }
   }
   __syncwarp();
@@ -723,6 +765,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           atomicAdd(p.stats + 2 * ch + 1, static_cast<double>(b));
         }
       }
+      if (p.has_fin) bn_finalize_tail(p, threadIdx.x - 64, reinterpret_cast<int*>(tmem_ptr + 1));
     }
     if (elected) bulk_wait_read0();
   }
@@ -1173,7 +1216,7 @@ extern "C" int hpri_set_conv_algo(int algo) {
 // -------------------------------------------------------------------------------------
 extern "C" int hpri_igemm_fwd(const hpri_view_t* x, const void* wpack, int w_dtype, int w_rows, int kpad, int taps,
                               const hpri_view_t* y, int n_store, const float* bias, double* stats, int accumulate,
-                              int block_n, void* stream_) {
+                              int block_n, const hpri_bn_fin_t* fin, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !y || !wpack) return HPRI_ERR_ARG;
   int rc;
@@ -1194,6 +1237,11 @@ extern "C" int hpri_igemm_fwd(const hpri_view_t* x, const void* wpack, int w_dty
   a.bias = bias; a.stats = stats; a.accum = accumulate ? 1 : 0;
   if (accumulate && stats) return HPRI_ERR_ARG;
   if (stats && w_rows > kMaxStatCh) return HPRI_ERR_ARG;
+  if (fin) {
+    if (!stats || !fin->scale || !fin->shift || !fin->counter || fin->count <= 0) return HPRI_ERR_ARG;
+    a.has_fin = 1;
+    a.fin = *fin;
+  }
   if (bias && (w_rows & 63)) return HPRI_ERR_ARG;   // the epilogue reads the bias in 64-float runs
   if (n_store <= 0) {                               // timing aid: run the contraction, store nothing
     n_store = 8;

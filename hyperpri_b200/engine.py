@@ -82,6 +82,7 @@ class _CBR:
         self.sums = _z((cout, 3), dev, torch.float64)
         self.scale, self.shift = _z((cp,), dev, torch.float32), _z((cp,), dev, torch.float32)
         self.smean, self.sinv = _z((cp,), dev, torch.float32), _z((cp,), dev, torch.float32)
+        self.ticket = _z((1,), dev, torch.int32)        # last-CTA-done counter of the fused BatchNorm finalisation
         self.gw = self.pp.spec.grad_buffer(dev)
 
 
@@ -268,10 +269,16 @@ class UNetEngine(_EngineBase):
         P = self.P
         L.pp.refresh(P[L.conv + ".weight"])
         n, h, w, _ = raw.shape
-        ops.igemm_fwd(x, L.pp.fwd, L.cout, 9, raw, L.cout, stats=L.stats if training else None)
-        ops.bn_finalize(L.stats, n * h * w, P[L.bn + ".weight"], P[L.bn + ".bias"], P[L.conv + ".bias"],
-                        P[L.bn + ".running_mean"], P[L.bn + ".running_var"], P[L.bn + ".num_batches_tracked"],
-                        training, L.scale, L.shift, L.smean, L.sinv, L.cout)
+        if training:     # statistics in the GEMM epilogue, finalised by the launch's last CTA
+            fin = ops.bn_fin(n * h * w, P[L.bn + ".weight"], P[L.bn + ".bias"], P[L.conv + ".bias"],
+                             P[L.bn + ".running_mean"], P[L.bn + ".running_var"], P[L.bn + ".num_batches_tracked"],
+                             L.scale, L.shift, L.smean, L.sinv, L.ticket)
+            ops.igemm_fwd(x, L.pp.fwd, L.cout, 9, raw, L.cout, stats=L.stats, fin=fin)
+        else:
+            ops.igemm_fwd(x, L.pp.fwd, L.cout, 9, raw, L.cout)
+            ops.bn_finalize(L.stats, n * h * w, P[L.bn + ".weight"], P[L.bn + ".bias"], P[L.conv + ".bias"],
+                            P[L.bn + ".running_mean"], P[L.bn + ".running_var"], P[L.bn + ".num_batches_tracked"],
+                            False, L.scale, L.shift, L.smean, L.sinv, L.cout)
         if apply:
             ops.bn_relu_apply(raw, L.scale, L.shift, act, pooled)
 
@@ -590,11 +597,18 @@ class SpectralEngine(_EngineBase):
                     src = xin
                 raw = im["raw_" + nm]
                 scale, shift, smean, sinv = im["bn"][nm]
-                ops.igemm_fwd(src, L.pp.fwd, F, 1, raw, Fp, stats=L.stats if training else None,
-                              x_c=(self.D if nm == "tail" else None), block_n=self.bn_tile)
-                ops.bn_finalize(L.stats, m, P[nm + ".1.weight"], P[nm + ".1.bias"], P[nm + ".0.bias"],
-                                P[nm + ".1.running_mean"], P[nm + ".1.running_var"],
-                                P[nm + ".1.num_batches_tracked"], training, scale, shift, smean, sinv, F)
+                if training:
+                    fin = ops.bn_fin(m, P[nm + ".1.weight"], P[nm + ".1.bias"], P[nm + ".0.bias"],
+                                     P[nm + ".1.running_mean"], P[nm + ".1.running_var"],
+                                     P[nm + ".1.num_batches_tracked"], scale, shift, smean, sinv, L.ticket)
+                    ops.igemm_fwd(src, L.pp.fwd, F, 1, raw, Fp, stats=L.stats, x_c=(self.D if nm == "tail" else None),
+                                  block_n=self.bn_tile, fin=fin)
+                else:
+                    ops.igemm_fwd(src, L.pp.fwd, F, 1, raw, Fp, x_c=(self.D if nm == "tail" else None),
+                                  block_n=self.bn_tile)
+                    ops.bn_finalize(L.stats, m, P[nm + ".1.weight"], P[nm + ".1.bias"], P[nm + ".0.bias"],
+                                    P[nm + ".1.running_mean"], P[nm + ".1.running_var"],
+                                    P[nm + ".1.num_batches_tracked"], False, scale, shift, smean, sinv, F)
                 ops.bn_relu_apply(raw, scale, shift, dst, None, c=F)
             ops.head_fwd(im["cat1"], None, None, self.w_outc, P["outc.bias"], ws["logits"][i])
         return ws["logits"]

@@ -216,10 +216,24 @@ class WeightSpec:
 # ----------------------------------------------------------------------------- contractions
 @_timed
 def igemm_fwd(x, wpack, rows, taps, y, n_store, bias=None, stats=None, block_n=0, x_c=None, y_c=None,
-              accumulate=False):
+              accumulate=False, fin=None):
+    """fin: a BnFin from bn_fin(...) -> the launch also finalises train-mode BatchNorm (scale / shift / saved and
+    running statistics) in its last CTA; no separate bn_finalize launch is needed."""
     xv, yv = view(x, x_c), view(y, y_c)
     check(_lib.lib().hpri_igemm_fwd(_vp(xv), _ptr(wpack), _DT[wpack.dtype], rows, wpack.shape[1], taps, _vp(yv), n_store, _ptr(bias),
-                                    _ptr(stats), int(accumulate), block_n, _stream()), "hpri_igemm_fwd")
+                                    _ptr(stats), int(accumulate), block_n, None if fin is None else C.byref(fin),
+                                    _stream()), "hpri_igemm_fwd")
+
+
+def bn_fin(count, gamma, beta, conv_bias, rmean, rvar, nbt, scale, shift, smean, sinv, counter, momentum=0.1, eps=1e-5):
+    """hpri_bn_fin_t for igemm_fwd(fin=...): the arguments of bn_finalize(training=True) plus a zero-initialised
+    uint32 ticket counter owned by the layer."""
+    f = _lib.BnFin()
+    f.gamma, f.beta, f.conv_bias = gamma.data_ptr(), beta.data_ptr(), 0 if conv_bias is None else conv_bias.data_ptr()
+    f.running_mean, f.running_var, f.num_batches_tracked = rmean.data_ptr(), rvar.data_ptr(), nbt.data_ptr()
+    f.scale, f.shift, f.save_mean, f.save_invstd = scale.data_ptr(), shift.data_ptr(), smean.data_ptr(), sinv.data_ptr()
+    f.counter, f.count, f.momentum, f.eps = counter.data_ptr(), int(count), float(momentum), float(eps)
+    return f
 
 
 def set_conv_algo(algo: int):

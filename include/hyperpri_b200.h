@@ -48,9 +48,27 @@ long long hpri_launch_count(void);
  * transposed/flipped pack), Conv3d(1,64,(D,3,3)) (models.py:169), nn.Linear (models.py:108,102).
  * stats (nullable): double[w_rows][2] accumulating per-channel sum / sum-of-squares of the bf16
  * outputs for train-mode BatchNorm (model_parts.py:23,26; models.py:113,172,178).
- * accumulate=1: y += result (skip-gradient accumulation), not combinable with stats. */
+ * accumulate=1: y += result (skip-gradient accumulation), not combinable with stats.
+ * fin (nullable, needs stats): train-mode BatchNorm finalisation fused into the launch -- the last CTA to flush its
+ * statistics (ticket counter) does what hpri_bn_finalize(training=1) does and zeroes stats and the counter. */
+typedef struct {
+  const float* gamma;          /* [C] or null (1) */
+  const float* beta;           /* [C] or null (0) */
+  const float* conv_bias;      /* [C] or null: re-added to running_mean (it cancels in the normalised output) */
+  float* running_mean;         /* nullable */
+  float* running_var;          /* nullable */
+  long long* num_batches_tracked; /* nullable */
+  float* scale;                /* out [C]: gamma * invstd */
+  float* shift;                /* out [C]: beta - mean * scale */
+  float* save_mean;            /* out [C], nullable */
+  float* save_invstd;          /* out [C], nullable */
+  unsigned int* counter;       /* one zero-initialised word owned by the layer */
+  long long count;             /* elements per channel */
+  float momentum, eps;
+} hpri_bn_fin_t;
 int hpri_igemm_fwd(const hpri_view_t* x, const void* wpack, int w_dtype, int w_rows, int kpad, int taps, const hpri_view_t* y,
-                   int n_store, const float* bias, double* stats, int accumulate, int block_n, void* stream);
+                   int n_store, const float* bias, double* stats, int accumulate, int block_n, const hpri_bn_fin_t* fin,
+                   void* stream);
 
 /* 3x3 kernel selection: -1 heuristic (default), 0 generic per-tap kernel, 1 halo-reuse kernel. */
 int hpri_set_conv_algo(int algo);
