@@ -41,13 +41,21 @@ class View(C.Structure):
 
 
 _VP = C.POINTER(View)
+
+
+class BnBwd(C.Structure):
+    """hpri_bn_bwd_t (include/hyperpri_b200.h)."""
+    _fields_ = [("x", _VP), ("scale", C.c_void_p), ("shift", C.c_void_p), ("save_mean", C.c_void_p),
+                ("save_invstd", C.c_void_p), ("sums", C.c_void_p)]
+
 _p, _i, _ll, _f = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 
 # name -> argtypes; every symbol include/hyperpri_b200.h declares
 SIGNATURES = {
     "hpri_abi_version": [],
     "hpri_launch_count": [],
-    "hpri_igemm_fwd": [_VP, _p, _i, _i, _i, _i, _VP, _i, _p, _p, _i, _i, C.POINTER(BnFin), _p],
+    "hpri_igemm_fwd": [_VP, _p, _i, _i, _i, _i, _VP, _i, _p, _p, _i, _i, C.POINTER(BnFin), C.POINTER(BnBwd), _p],
+    "hpri_conv3x3_halo_ok": [_i, _i, _i],
     "hpri_set_conv_algo": [_i],
     "hpri_convT2x2_fwd": [_VP, _p, _i, _i, _i, _VP, _p, _i, _p],
     "hpri_convT2x2_dgrad": [_VP, _p, _i, _i, _i, _VP, _i, _p],

@@ -52,6 +52,12 @@ struct IgemmArgs {
   // ---- fused train-mode BatchNorm finalisation (has_fin): done by the last CTA to flush its statistics
   int has_fin;
   hpri_bn_fin_t fin;
+  // ---- fused BatchNorm-backward reduction (dgrad launches of the halo kernel): the tile just produced is dy of the
+  // layer below; with a TMA-loaded tile of that layer's raw conv output x the epilogue accumulates
+  // sum(dz) and sum(dz * x), dz = dy * [x*scale+shift > 0], i.e. pass 1 of hpri_bn_relu_bwd_reduce
+  const float *bw_scale, *bw_shift, *bw_mean, *bw_invstd;
+  double* bw_sums;        // [n_total][3]
+  int xstage_off;         // byte offset of the two 16 KB x staging tiles (after the rings)
 };
 
 constexpr int kThreads = 320;
@@ -92,6 +98,24 @@ __device__ __forceinline__ void stats_rows32(const uint8_t* stage, int r0, int l
   for (int i = 0; i < 32; ++i) {
     const uint32_t u = *reinterpret_cast<const uint32_t*>(base + i * 128 + (((chunk ^ i) & 7) << 4));
     acc_sum_sq2(s, q, unpack2_t<DT>(u));
+  }
+}
+// Same walk over two staged tiles (dy and the raw conv output x of the layer below): lane l owns channels 2l, 2l+1;
+// s1 += dz, s2 += dz * x with dz = dy where x*scale+shift > 0 (the ReLU mask of the forward pass), else 0.
+template <int DT>
+__device__ __forceinline__ void bw_stats_rows32(const uint8_t* stage, const uint8_t* xst, int r0, int lane, float2 sc,
+                                                float2 sh, float2& s1, float2& s2) {
+  const int chunk = lane >> 2;
+  const int off0 = r0 * 128 + (lane & 3) * 4;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int off = off0 + i * 128 + (((chunk ^ i) & 7) << 4);
+    const float2 d = unpack2_t<DT>(*reinterpret_cast<const uint32_t*>(stage + off));
+    const float2 x = unpack2_t<DT>(*reinterpret_cast<const uint32_t*>(xst + off));
+    const float dz0 = fmaf(x.x, sc.x, sh.x) > 0.f ? d.x : 0.f;
+    const float dz1 = fmaf(x.y, sc.y, sh.y) > 0.f ? d.y : 0.f;
+    s1.x += dz0; s1.y += dz1;
+    s2.x = fmaf(dz0, x.x, s2.x); s2.y = fmaf(dz1, x.y, s2.y);
   }
 }
 // TMEM (this warp's 32 lanes, 64 columns at taddr) -> (+bias) -> 16-bit -> staging rows
@@ -538,13 +562,13 @@ struct HaloSmem {
   static constexpr int B_TILE = BLOCK_N * 128;
   static constexpr int B_STAGE = B_TILE;
   static constexpr int STAGING_OFF = 0;
-  static constexpr int BAR_OFF = 2 * kStageTile;       // a_full[2], a_empty[2], b_full[4], b_empty[4], tmem_full[2], tmem_empty[2]
-  static constexpr int TMEMPTR_OFF = BAR_OFF + (2 * kHaloAStages + 2 * kHaloMaxBStages + 4) * 8;
+  static constexpr int BAR_OFF = 2 * kStageTile;       // a_full[2], a_empty[2], b_full[12], b_empty[12], tmem_full[2], tmem_empty[2], x_full[2]
+  static constexpr int TMEMPTR_OFF = BAR_OFF + (2 * kHaloAStages + 2 * kHaloMaxBStages + 6) * 8;
   static constexpr int SSUM_OFF = TMEMPTR_OFF + 8;
   static constexpr int PIPE_OFF = (SSUM_OFF + 2 * kHaloStatCh * 4 + 1023) / 1024 * 1024;
   static constexpr int BUDGET = 227 * 1024 - 1024;                       // after manual 1024 B alignment
-  static int b_stages_for(int a_bytes) {
-    int s = (BUDGET - PIPE_OFF - kHaloAStages * a_bytes) / B_STAGE;
+  static int b_stages_for(int a_bytes, int extra = 0) {
+    int s = (BUDGET - PIPE_OFF - kHaloAStages * a_bytes - extra) / B_STAGE;
     return s > kHaloMaxBStages ? kHaloMaxBStages : s;
   }
 };
@@ -557,7 +581,8 @@ struct HaloGeom {
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmO, const IgemmArgs p, const HaloGeom geo) {
+                    const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmX,
+                    const IgemmArgs p, const HaloGeom geo) {
   using L = HaloSmem<BLOCK_N>;
   constexpr int NCH = BLOCK_N / 64;
   extern __shared__ uint8_t smem_raw[];
@@ -594,6 +619,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     mbar_init(&tmem_full[1], 1);
     mbar_init(&tmem_empty[0], 8);
     mbar_init(&tmem_empty[1], 8);
+    mbar_init(&tmem_empty[2], 1);              // x_full[0], x_full[1]: the fused BN-backward x tiles of the two groups
+    mbar_init(&tmem_empty[3], 1);
     fence_mbar_init();
     fence_proxy_async_smem();
   }
@@ -706,6 +733,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint8_t* stage = smem + L::STAGING_OFF + g * kStageTile;
     const int bar_id = 1 + g;
     const int my_r = geo.hr[g] + (row >> 3), my_c = geo.hc[g] + (row & 7);   // this thread's pixel inside the tile
+    const bool bw = p.bw_sums != nullptr;          // fused BatchNorm-backward reduction (dgrad launches)
+    const bool acc_on = p.stats != nullptr || bw;
+    const uint8_t* xst = smem + p.xstage_off + g * kStageTile;
+    uint64_t* x_full = tmem_empty + 2 + g;
+    uint32_t xph = 0;
     float2 ssv[NCH], sqv[NCH];
 #pragma unroll
     for (int j = 0; j < NCH; ++j) { ssv[j] = make_float2(0.f, 0.f); sqv[j] = make_float2(0.f, 0.f); }
@@ -719,7 +751,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int rr = m_tile - img * tiles_per_img;
       const int h0 = (rr / p.tiles_w) * p.th, w0 = (rr % p.tiles_w) * p.tw;
       const int n0 = n_tile * BLOCK_N;
-      if (p.stats != nullptr && n0 != acc_n0) {
+      if (acc_on && n0 != acc_n0) {
         if (acc_n0 >= 0) {
 #pragma unroll
           for (int j = 0; j < NCH; ++j) flush_stats(ssum, ssq, acc_n0 + j * 64 + 2 * lane, p.n_total, ssv[j], sqv[j]);
@@ -733,7 +765,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
       for (int c64 = 0; c64 < NCH; ++c64) {
         if (elected) bulk_wait_read0();
-        named_bar_sync(bar_id, 128);
+        named_bar_sync(bar_id, 128);           // staging (and the x tile) of the previous chunk are no longer read
+        if (bw && elected) {                   // the matching tile of the layer below's raw conv output
+          mbar_arrive_expect_tx(x_full, kStageTile);
+          tma_load_4d(const_cast<uint8_t*>(xst), &tmX, x_full, n0 + c64 * 64, w0 + geo.hc[g], h0 + geo.hr[g], img);
+        }
         chunk_to_stage(tmem_acc + c64 * 64, stage, row, valid, p.out_dt, nullptr);
         if (c64 == NCH - 1) {
           tc_fence_before();
@@ -750,9 +786,19 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (p.out_dt == DT_F16) stats_rows32<DT_F16>(stage, gw * 32, lane, ssv[c64], sqv[c64]);
           else stats_rows32<DT_BF16>(stage, gw * 32, lane, ssv[c64], sqv[c64]);
         }
+        if (bw) {
+          const int ch = n0 + c64 * 64 + 2 * lane;
+          float2 sc = make_float2(0.f, 0.f), sh = make_float2(0.f, 0.f);
+          if (ch < p.n_total) { sc.x = __ldg(p.bw_scale + ch); sh.x = __ldg(p.bw_shift + ch); }
+          if (ch + 1 < p.n_total) { sc.y = __ldg(p.bw_scale + ch + 1); sh.y = __ldg(p.bw_shift + ch + 1); }
+          mbar_wait(x_full, xph);
+          xph ^= 1;
+          if (p.out_dt == DT_F16) bw_stats_rows32<DT_F16>(stage, xst, gw * 32, lane, sc, sh, ssv[c64], sqv[c64]);
+          else bw_stats_rows32<DT_BF16>(stage, xst, gw * 32, lane, sc, sh, ssv[c64], sqv[c64]);
+        }
       }
     }
-    if (p.stats != nullptr) {
+    if (acc_on) {
       if (acc_n0 >= 0) {
 #pragma unroll
         for (int j = 0; j < NCH; ++j) flush_stats(ssum, ssq, acc_n0 + j * 64 + 2 * lane, p.n_total, ssv[j], sqv[j]);
@@ -761,8 +807,15 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int ch = threadIdx.x - 64; ch < p.n_total; ch += kEpiThreads) {
         const float a = ssum[ch], b = ssq[ch];
         if (a != 0.f || b != 0.f) {
-          atomicAdd(p.stats + 2 * ch, static_cast<double>(a));
-          atomicAdd(p.stats + 2 * ch + 1, static_cast<double>(b));
+          if (bw) {        // sums[c] = {sum dz, invstd * (sum dz*x - mean * sum dz), -} like bn_bwd_reduce_*_k
+            const float mu = __ldg(p.bw_mean + ch), is = __ldg(p.bw_invstd + ch);
+            atomicAdd(p.bw_sums + 3 * ch, static_cast<double>(a));
+            atomicAdd(p.bw_sums + 3 * ch + 1,
+                      static_cast<double>(is) * (static_cast<double>(b) - static_cast<double>(mu) * static_cast<double>(a)));
+          } else {
+            atomicAdd(p.stats + 2 * ch, static_cast<double>(a));
+            atomicAdd(p.stats + 2 * ch + 1, static_cast<double>(b));
+          }
         }
       }
       if (p.has_fin) bn_finalize_tail(p, threadIdx.x - 64, reinterpret_cast<int*>(tmem_ptr + 1));
@@ -1152,8 +1205,8 @@ static int pick_block_n(int n_total, int forced) {
 
 // halo kernel launcher -------------------------------------------------------------------
 template <int BLOCK_N>
-static int launch_halo_t(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const IgemmArgs& args,
-                         const HaloGeom& geo, long long tiles, cudaStream_t stream) {
+static int launch_halo_t(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mx,
+                         const IgemmArgs& args, const HaloGeom& geo, long long tiles, cudaStream_t stream) {
   using L = HaloSmem<BLOCK_N>;
   auto kern = conv3x3_halo_kernel<BLOCK_N>;
   static std::once_flag once;
@@ -1164,8 +1217,9 @@ static int launch_halo_t(const CUtensorMap& ma, const CUtensorMap& mb, const CUt
   if (attr_err != cudaSuccess) return HPRI_ERR_CUDA;
   long long grid = tiles < sm_count() ? tiles : sm_count();
   if (grid <= 0) return HPRI_ERR_ARG;
-  const size_t smem = (size_t)L::PIPE_OFF + (size_t)kHaloAStages * args.a_bytes + (size_t)args.stages * L::B_STAGE + 1024;
-  kern<<<(unsigned)grid, kThreads, smem, stream>>>(ma, mb, mo, args, geo);
+  const size_t smem = (size_t)L::PIPE_OFF + (size_t)kHaloAStages * args.a_bytes + (size_t)args.stages * L::B_STAGE +
+                      (args.bw_sums ? 2 * kStageTile : 0) + 1024;
+  kern<<<(unsigned)grid, kThreads, smem, stream>>>(ma, mb, mo, mx, args, geo);
   ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? HPRI_OK : HPRI_ERR_CUDA;
 }
@@ -1205,6 +1259,17 @@ static int wgrad_algo_override() {
 
 using namespace hpri;
 
+extern "C" int hpri_conv3x3_halo_ok(int h, int w, int w_rows) {
+  if (h <= 0 || w <= 0 || w_rows <= 0) return 0;
+  int hth = 0, htw = 0;
+  const double waste = pick_halo_tile(h, w, &hth, &htw);
+  const int ov = conv_algo_override();
+  const int a_bytes = ((hth + 2) * (htw + 2) * 128 + 1023) / 1024 * 1024;
+  const int stages = w_rows <= 64 ? HaloSmem<64>::b_stages_for(a_bytes, 2 * kStageTile)
+                                  : HaloSmem<128>::b_stages_for(a_bytes, 2 * kStageTile);
+  return (w_rows <= kHaloStatCh && stages >= 2 && (ov == 1 || (ov < 0 && waste <= 1.0))) ? 1 : 0;
+}
+
 extern "C" int hpri_set_conv_algo(int algo) {
   if (algo < -1 || algo > 1) return HPRI_ERR_ARG;
   g_conv_algo = algo;
@@ -1216,7 +1281,7 @@ extern "C" int hpri_set_conv_algo(int algo) {
 // -------------------------------------------------------------------------------------
 extern "C" int hpri_igemm_fwd(const hpri_view_t* x, const void* wpack, int w_dtype, int w_rows, int kpad, int taps,
                               const hpri_view_t* y, int n_store, const float* bias, double* stats, int accumulate,
-                              int block_n, const hpri_bn_fin_t* fin, void* stream_) {
+                              int block_n, const hpri_bn_fin_t* fin, const hpri_bn_bwd_t* bw, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (!x || !y || !wpack) return HPRI_ERR_ARG;
   int rc;
@@ -1255,10 +1320,26 @@ extern "C" int hpri_igemm_fwd(const hpri_view_t* x, const void* wpack, int w_dty
     const bool stats_ok = !stats || w_rows <= kHaloStatCh;
     const int hbn = w_rows <= 64 ? 64 : 128;
     const int a_bytes = ((hth + 2) * (htw + 2) * 128 + 1023) / 1024 * 1024;
-    const int stages = hbn == 64 ? HaloSmem<64>::b_stages_for(a_bytes) : HaloSmem<128>::b_stages_for(a_bytes);
+    const int extra = bw ? 2 * kStageTile : 0;           // x staging tiles of the fused BN-backward reduction
+    const int stages = hbn == 64 ? HaloSmem<64>::b_stages_for(a_bytes, extra) : HaloSmem<128>::b_stages_for(a_bytes, extra);
     if (stats_ok && stages >= 2 && (ov == 1 || (ov < 0 && waste <= 1.0))) {
       set_tile(a, hth, htw);
       a.stages = stages; a.a_bytes = a_bytes;
+      CUtensorMap mx{};
+      if (bw) {
+        if (stats || !bw->x || !bw->scale || !bw->shift || !bw->save_mean || !bw->save_invstd || !bw->sums) return HPRI_ERR_ARG;
+        if ((rc = check_view(*bw->x)) != HPRI_OK) return rc;
+        if (bw->x->n != y->n || bw->x->h != y->h || bw->x->w != y->w || bw->x->c < w_rows || bw->x->dtype != y->dtype)
+          return HPRI_ERR_ARG;
+        if (w_rows > kHaloStatCh) return HPRI_ERR_ARG;
+        hpri_view_t xv = *bw->x;
+        xv.c = w_rows;
+        if ((rc = map_nhwc(&mx, xv, 16, 8)) != HPRI_OK) return rc;
+        a.bw_scale = bw->scale; a.bw_shift = bw->shift; a.bw_mean = bw->save_mean; a.bw_invstd = bw->save_invstd;
+        a.bw_sums = bw->sums;
+        a.xstage_off = (hbn == 64 ? HaloSmem<64>::PIPE_OFF : HaloSmem<128>::PIPE_OFF) + kHaloAStages * a_bytes +
+                       stages * (hbn == 64 ? HaloSmem<64>::B_STAGE : HaloSmem<128>::B_STAGE);
+      }
       HaloGeom geo{};
       geo.wb = htw + 2;
       geo.hr[0] = 0; geo.hc[0] = 0;
@@ -1271,10 +1352,12 @@ extern "C" int hpri_igemm_fwd(const hpri_view_t* x, const void* wpack, int w_dty
       if ((rc = map_weights(&mb, wpack, w_rows, kpad, hbn, w_dtype)) != HPRI_OK) return rc;
       if ((rc = map_out(&mo, *y, n_store, 16, 8)) != HPRI_OK) return rc;
       const long long tiles = (long long)a.N * a.tiles_h * a.tiles_w * ((w_rows + hbn - 1) / hbn);
-      return hbn == 64 ? launch_halo_t<64>(ma, mb, mo, a, geo, tiles, stream)
-                       : launch_halo_t<128>(ma, mb, mo, a, geo, tiles, stream);
+      if (!bw) mx = mo;
+      return hbn == 64 ? launch_halo_t<64>(ma, mb, mo, mx, a, geo, tiles, stream)
+                       : launch_halo_t<128>(ma, mb, mo, mx, a, geo, tiles, stream);
     }
   }
+  if (bw) return HPRI_ERR_ARG;        // the fused reduction exists on the halo kernel only (hpri_conv3x3_halo_ok)
   int th, tw;
   pick_tile(a.H, a.W, 128, &th, &tw);
   set_tile(a, th, tw);

@@ -295,17 +295,28 @@ class UNetEngine(_EngineBase):
         return ops.convert16(x, buf)
 
     def _cbr_bwd(self, L: _CBR, x_in, raw, R, count, dy=None, dpool=None, head_w=None, dlogit=None, dhead_w=None,
-                 dx_out=None):
-        """BN+ReLU backward -> R, wgrad, optional dgrad into dx_out."""
+                 dx_out=None, below=None, reduced=False):
+        """BN+ReLU backward -> R, wgrad, optional dgrad into dx_out.
+        below = (layer, raw) of the BatchNorm+ReLU layer whose output gradient dx_out IS (no other contribution): its
+        backward reduction is fused into this dgrad launch; that layer is then called with reduced=True."""
         P = self.P
         ops.bn_relu_bwd(raw, L.scale, L.shift, L.smean, L.sinv, P[L.bn + ".weight"], R, L.sums, count, dy=dy,
                         dpool=dpool, head_w=head_w, dlogit=dlogit, dgamma=self._grad(L.bn + ".weight", L.scale[:L.cout]),
-                        dbeta=self._grad(L.bn + ".bias", L.scale[:L.cout]), dhead_w=dhead_w)
+                        dbeta=self._grad(L.bn + ".bias", L.scale[:L.cout]), dhead_w=dhead_w, reduced=reduced)
         ops.igemm_wgrad(self._as_grad_dtype(x_in), R, 1, L.cout, L.gw)
         # the packed gradient is unpacked into the arena per bucket (_unpack_bucket); the conv bias gradient is
         # identically zero under train-mode BN
         if dx_out is not None:
-            ops.igemm_fwd(R, L.pp.dgr, L.cin, 9, dx_out, L.cin)
+            bw = None
+            if below is not None:
+                Lb, raw_b = below
+                bw = (raw_b, Lb.scale, Lb.shift, Lb.smean, Lb.sinv, Lb.sums)
+            ops.igemm_fwd(R, L.pp.dgr, L.cin, 9, dx_out, L.cin, bw=bw)
+
+    def _fusable(self, l):
+        """The a-layer of level l gets its whole output gradient from the b-layer's dgrad launch; the reduction can
+        ride in that launch when it runs on the halo kernel."""
+        return ops.conv3x3_halo_ok(self.ws["H"][l], self.ws["W"][l], self.CH[l])
 
     # ------------------------------------------------------------------ forward
     def ingest(self, x: torch.Tensor, ws):
@@ -415,15 +426,17 @@ class UNetEngine(_EngineBase):
         g_in = None                        # gradient wrt the activation feeding the next (deeper-first) stage
         for l in (0, 1, 2, 3):
             a, b = self.dec[l]
+            fuse = self._fusable(l)
+            below = (a, ws[f"dec_raw_a{l}"]) if fuse else None
             if l == 0:
                 dhw = self._grad("outc.conv.weight", P["outc.conv.weight"]).view(-1)
                 self._cbr_bwd(b, ws["dec_act_a0"], ws["dec_raw_b0"], ws["R0"], cnt[0], head_w=head_w, dlogit=dlogit,
-                              dhead_w=dhw, dx_out=ws["A0"])
+                              dhead_w=dhw, dx_out=ws["A0"], below=below)
             else:
                 self._cbr_bwd(b, ws[f"dec_act_a{l}"], ws[f"dec_raw_b{l}"], ws[f"R{l}"], cnt[l], dy=g_in,
-                              dx_out=ws[f"A{l}"])
+                              dx_out=ws[f"A{l}"], below=below)
             self._cbr_bwd(a, ws[f"cat{l}"], ws[f"dec_raw_a{l}"], ws[f"R{l}"], cnt[l], dy=ws[f"A{l}"],
-                          dx_out=ws[f"gcat{l}"])
+                          dx_out=ws[f"gcat{l}"], reduced=fuse)
             # ConvTranspose2d backward: its output is the second half of cat[l] over the 2h x 2w region
             i = 4 - l
             up = self.up[l]
@@ -440,14 +453,17 @@ class UNetEngine(_EngineBase):
         # encoder, deepest first
         for l in (4, 3, 2, 1, 0):
             a, b = self.enc[l]
+            fuse = self._fusable(l)
+            below = (a, ws[f"enc_raw_a{l}"]) if fuse else None
             if l == 4:
-                self._cbr_bwd(b, ws["enc_act_a4"], ws["enc_raw_b4"], ws["R4"], cnt[4], dy=g_in, dx_out=ws["A4"])
+                self._cbr_bwd(b, ws["enc_act_a4"], ws["enc_raw_b4"], ws["R4"], cnt[4], dy=g_in, dx_out=ws["A4"],
+                              below=below)
             else:
                 self._cbr_bwd(b, ws[f"enc_act_a{l}"], ws[f"enc_raw_b{l}"], ws[f"R{l}"], cnt[l],
-                              dy=ws[f"gcat{l}"][..., :C[l]], dpool=ws[f"gpool{l + 1}"], dx_out=ws[f"A{l}"])
+                              dy=ws[f"gcat{l}"][..., :C[l]], dpool=ws[f"gpool{l + 1}"], dx_out=ws[f"A{l}"], below=below)
             x_in = ws[f"pool{l}"] if l > 0 else ws["x"]
             self._cbr_bwd(a, x_in, ws[f"enc_raw_a{l}"], ws[f"R{l}"], cnt[l], dy=ws[f"A{l}"],
-                          dx_out=ws[f"gpool{l}"] if l > 0 else None)
+                          dx_out=ws[f"gpool{l}"] if l > 0 else None, reduced=fuse)
             self._bucket_done(4 + (4 - l))
         if self.first == "cube":               # module registered twice (models.py:169-171): same tensor
             self.grads["inc.0.weight"] = self.grads["first_conv.weight"]

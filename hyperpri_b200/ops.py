@@ -216,13 +216,26 @@ class WeightSpec:
 # ----------------------------------------------------------------------------- contractions
 @_timed
 def igemm_fwd(x, wpack, rows, taps, y, n_store, bias=None, stats=None, block_n=0, x_c=None, y_c=None,
-              accumulate=False, fin=None):
+              accumulate=False, fin=None, bw=None):
     """fin: a BnFin from bn_fin(...) -> the launch also finalises train-mode BatchNorm (scale / shift / saved and
-    running statistics) in its last CTA; no separate bn_finalize launch is needed."""
+    running statistics) in its last CTA; no separate bn_finalize launch is needed.
+    bw: (raw_below, scale, shift, save_mean, save_invstd, sums) of the BatchNorm+ReLU layer whose output gradient this
+    3x3 dgrad launch produces -> its backward reduction (pass 1) is accumulated in the epilogue (sums zeroed here)."""
     xv, yv = view(x, x_c), view(y, y_c)
+    bws = None
+    if bw is not None:
+        raw, sc, sh, mu, iv, sums = bw
+        sums.zero_()
+        rv = view(raw, y_c)
+        bws = _lib.BnBwd(C.pointer(rv), sc.data_ptr(), sh.data_ptr(), mu.data_ptr(), iv.data_ptr(), sums.data_ptr())
     check(_lib.lib().hpri_igemm_fwd(_vp(xv), _ptr(wpack), _DT[wpack.dtype], rows, wpack.shape[1], taps, _vp(yv), n_store, _ptr(bias),
                                     _ptr(stats), int(accumulate), block_n, None if fin is None else C.byref(fin),
-                                    _stream()), "hpri_igemm_fwd")
+                                    None if bws is None else C.byref(bws), _stream()), "hpri_igemm_fwd")
+
+
+def conv3x3_halo_ok(h, w, rows) -> bool:
+    """True when a 3x3 launch of this shape runs on the halo-reuse kernel (needed by igemm_fwd(bw=...))."""
+    return bool(_lib.lib().hpri_conv3x3_halo_ok(int(h), int(w), int(rows)))
 
 
 def bn_fin(count, gamma, beta, conv_bias, rmean, rvar, nbt, scale, shift, smean, sinv, counter, momentum=0.1, eps=1e-5):
@@ -314,11 +327,13 @@ def bn_relu_apply(x, scale, shift, y, pooled=None, c=None):
 
 @_timed
 def bn_relu_bwd(x, scale, shift, smean, sinv, gamma, dx, sums, count, dy=None, dpool=None, head_w=None,
-                dlogit=None, dgamma=None, dbeta=None, dhead_w=None, c=None):
+                dlogit=None, dgamma=None, dbeta=None, dhead_w=None, c=None, reduced=False):
+    """reduced=True: `sums` was already accumulated by the dgrad launch that produced dy (igemm_fwd(bw=...))."""
     xv, dyv, dpv, dxv = view(x, c), view(dy, c), view(dpool, c), view(dx, c)
     L = _lib.lib()
-    check(L.hpri_bn_relu_bwd_reduce(_vp(xv), _ptr(scale), _ptr(shift), _ptr(smean), _ptr(sinv), _vp(dyv), _vp(dpv),
-                                    _ptr(head_w), _ptr(dlogit), _ptr(sums), _stream()), "hpri_bn_relu_bwd_reduce")
+    if not reduced:
+        check(L.hpri_bn_relu_bwd_reduce(_vp(xv), _ptr(scale), _ptr(shift), _ptr(smean), _ptr(sinv), _vp(dyv), _vp(dpv),
+                                        _ptr(head_w), _ptr(dlogit), _ptr(sums), _stream()), "hpri_bn_relu_bwd_reduce")
     check(L.hpri_bn_relu_bwd_apply(_vp(xv), _ptr(scale), _ptr(shift), _ptr(smean), _ptr(sinv), _ptr(gamma), _vp(dyv),
                                    _vp(dpv), _ptr(head_w), _ptr(dlogit), _ptr(sums), count, _vp(dxv), _ptr(dgamma),
                                    _ptr(dbeta), _ptr(dhead_w), _stream()), "hpri_bn_relu_bwd_apply")

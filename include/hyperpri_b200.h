@@ -66,9 +66,24 @@ typedef struct {
   long long count;             /* elements per channel */
   float momentum, eps;
 } hpri_bn_fin_t;
+/* bw (nullable; 3x3 dgrad launches on the halo kernel only, see hpri_conv3x3_halo_ok): the output y is the gradient dy
+ * of the BatchNorm+ReLU layer below; the epilogue also accumulates pass 1 of its backward (what
+ * hpri_bn_relu_bwd_reduce computes from x and dy) into sums, so only hpri_bn_relu_bwd_apply remains.  The caller zeroes
+ * sums before the launch. */
+typedef struct {
+  const hpri_view_t* x;        /* raw conv output of the layer below: same n, h, w, channels and dtype as y */
+  const float* scale;          /* its BatchNorm scale / shift (ReLU mask = x*scale+shift > 0) */
+  const float* shift;
+  const float* save_mean;
+  const float* save_invstd;
+  double* sums;                /* [C][3]: sum dz, invstd * (sum dz*x - mean * sum dz), unused */
+} hpri_bn_bwd_t;
 int hpri_igemm_fwd(const hpri_view_t* x, const void* wpack, int w_dtype, int w_rows, int kpad, int taps, const hpri_view_t* y,
                    int n_store, const float* bias, double* stats, int accumulate, int block_n, const hpri_bn_fin_t* fin,
-                   void* stream);
+                   const hpri_bn_bwd_t* bw, void* stream);
+/* 1 when hpri_igemm_fwd(taps = 9) for an h x w image and w_rows output channels runs on the halo-reuse kernel
+ * (which is what the fused `bw` reduction needs), 0 when it falls to the generic per-tap kernel. */
+int hpri_conv3x3_halo_ok(int h, int w, int w_rows);
 
 /* 3x3 kernel selection: -1 heuristic (default), 0 generic per-tap kernel, 1 halo-reuse kernel. */
 int hpri_set_conv_algo(int algo);

@@ -224,6 +224,37 @@ def test_tiled_conv3x3_pack_matches_generic(cout, cin):
     assert not g.view(cout, 9, -1)[:, :, :cin].any()      # the packed buffer is reset behind the read
 
 
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 32, 24, 64, 64), (1, 40, 50, 128, 64), (2, 16, 33, 64, 128),
+                                            (1, 33, 70, 256, 128)])
+def test_dgrad_fused_bn_backward_reduction(n, h, w, cin, cout):
+    """igemm_fwd(bw=...) on a 3x3 dgrad launch == hpri_bn_relu_bwd_reduce on the dy it produced."""
+    assert ops.conv3x3_halo_ok(h, w, cin)
+    dyn = nhwc(rnd(n, cout, h, w, seed=21), dt=FH)                  # gradient entering the dgrad
+    wt = rnd(cout, cin, 3, 3, scale=1 / math.sqrt(cout * 9), seed=22)
+    wp = ops.WeightSpec("conv3x3", cout, cin).pack_dgrad(wt, dtype=FH)
+    raw = nhwc(rnd(n, cin, h, w, seed=23), dt=FH)                   # raw conv output of the layer below
+    scale = torch.rand(ops.kpad(cin), device=DEV) + 0.5
+    shift = torch.randn(ops.kpad(cin), device=DEV) * 0.3
+    mean = torch.randn(ops.kpad(cin), device=DEV) * 0.1
+    inv = torch.rand(ops.kpad(cin), device=DEV) + 0.5
+    sums = torch.full((cin, 3), 7.0, dtype=torch.float64, device=DEV)
+    dx = torch.empty((n, h, w, cin), dtype=FH, device=DEV)
+    ops.igemm_fwd(dyn, wp, cin, 9, dx, cin, bw=(raw, scale, shift, mean, inv, sums))
+    dx_ref = torch.empty_like(dx)
+    ops.igemm_fwd(dyn, wp, cin, 9, dx_ref, cin)
+    assert torch.equal(dx, dx_ref)                                   # the stored gradient is unchanged
+    ref = torch.zeros((cin, 3), dtype=torch.float64, device=DEV)
+    from hyperpri_b200 import _lib
+    import ctypes as C
+    xv, dv = ops.view(raw), ops.view(dx)
+    ops.check(_lib.lib().hpri_bn_relu_bwd_reduce(C.byref(xv), ops._ptr(scale), ops._ptr(shift), ops._ptr(mean),
+                                                 ops._ptr(inv), C.byref(dv), None, None, None, ops._ptr(ref),
+                                                 ops._stream()), "reduce")
+    torch.cuda.synchronize()
+    tol = 1e-4 * ref[:, :2].abs().max().item() + 1e-6
+    assert (sums[:, :2] - ref[:, :2]).abs().max().item() < tol, (sums[:3], ref[:3])
+
+
 def test_table_driven_pack_and_unpack_match_per_layer():
     """One launch over a device job table == the per-layer kernels, for ragged layer sizes."""
     shapes = [(64, 238), (128, 64), (96, 40), (256, 128)]
