@@ -1308,10 +1308,7 @@ extern "C" int hpri_igemm_fwd(const hpri_view_t* x, const void* wpack, int w_dty
     a.fin = *fin;
   }
   if (bias && (w_rows & 63)) return HPRI_ERR_ARG;   // the epilogue reads the bias in 64-float runs
-  if (n_store <= 0) {                               // timing aid: run the contraction, store nothing
-    n_store = 8;
-    a.n_total = w_rows;
-  }
+  if (n_store <= 0) return HPRI_ERR_ARG;
   if (taps == 9 && bias == nullptr && !accumulate) {
     // halo-reuse kernel (256-pixel tiles)
     int hth = 0, htw = 0;

@@ -28,7 +28,6 @@ def conv_case(n, h, w, cin, cout, taps=9, bn=0):
     res = {}
     res["stats"] = t_ms(lambda: ops.igemm_fwd(x, wp, cout, taps, y, cout, stats=stats, block_n=bn))
     res["nostats"] = t_ms(lambda: ops.igemm_fwd(x, wp, cout, taps, y, cout, block_n=bn))
-    res["nostore"] = t_ms(lambda: ops.igemm_fwd(x, wp, cout, taps, y, 0, block_n=bn))
     # wgrad
     xg = x.to(ops.GRAD); dy = torch.randn((n, h, w, cout), device=DEV).to(ops.GRAD)
     gw = spec.grad_buffer(DEV)
