@@ -121,23 +121,36 @@ __device__ __forceinline__ void bw_stats_rows32(const uint8_t* stage, const uint
 // TMEM (this warp's 32 lanes, 64 columns at taddr) -> (+bias) -> 16-bit -> staging rows
 __device__ __forceinline__ void chunk_to_stage(uint32_t taddr, uint8_t* stage, int row, bool valid, int out_dt,
                                                const float* bias64) {
+  uint32_t v[64];
+  tmem_ld64(taddr, v);                       // all 64 columns of the chunk in one TMEM round trip
+  tmem_ld_wait();
+  if (bias64 != nullptr) {
 #pragma unroll
-  for (int hh = 0; hh < 2; ++hh) {
-    uint32_t v[32];
-    tmem_ld32(taddr + hh * 32, v);
-    tmem_ld_wait();
-    if (bias64 != nullptr) {
+    for (int j = 0; j < 16; ++j) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias64) + j);
+      v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + b.x);
+      v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + b.y);
+      v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + b.z);
+      v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + b.w);
+    }
+  }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(bias64 + hh * 32) + j);
-        v[4 * j + 0] = __float_as_uint(__uint_as_float(v[4 * j + 0]) + b.x);
-        v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + b.y);
-        v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + b.z);
-        v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + b.w);
+  for (int chunk = 0; chunk < 8; ++chunk) {
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (valid) {
+      if (out_dt == DT_F16) {
+        o.x = pack2_t<DT_F16>(__uint_as_float(v[8 * chunk + 0]), __uint_as_float(v[8 * chunk + 1]));
+        o.y = pack2_t<DT_F16>(__uint_as_float(v[8 * chunk + 2]), __uint_as_float(v[8 * chunk + 3]));
+        o.z = pack2_t<DT_F16>(__uint_as_float(v[8 * chunk + 4]), __uint_as_float(v[8 * chunk + 5]));
+        o.w = pack2_t<DT_F16>(__uint_as_float(v[8 * chunk + 6]), __uint_as_float(v[8 * chunk + 7]));
+      } else {
+        o.x = pack2_t<DT_BF16>(__uint_as_float(v[8 * chunk + 0]), __uint_as_float(v[8 * chunk + 1]));
+        o.y = pack2_t<DT_BF16>(__uint_as_float(v[8 * chunk + 2]), __uint_as_float(v[8 * chunk + 3]));
+        o.z = pack2_t<DT_BF16>(__uint_as_float(v[8 * chunk + 4]), __uint_as_float(v[8 * chunk + 5]));
+        o.w = pack2_t<DT_BF16>(__uint_as_float(v[8 * chunk + 6]), __uint_as_float(v[8 * chunk + 7]));
       }
     }
-    if (out_dt == DT_F16) stage_row32<DT_F16>(stage, row, hh, v, valid);
-    else stage_row32<DT_BF16>(stage, row, hh, v, valid);
+    *reinterpret_cast<uint4*>(stage + row * 128 + (((chunk ^ row) & 7) << 4)) = o;
   }
 }
 // per-thread statistics (channels ch, ch+1) -> the CTA's smem partial sums
