@@ -591,13 +591,26 @@ struct HaloGeom {
   int hr[2], hc[2];       // tile-relative origin (row, column) of the two 16 x 8 halves
 };
 
-template <int BLOCK_N>
+template <bool PAIR, uint32_t OFF_A, uint32_t OFF_B>
+__device__ __forceinline__ void halo_mma(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                         uint32_t idesc, uint32_t accumulate) {
+  if constexpr (PAIR) umma2_f16_off_w<OFF_A, OFF_B>(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+  else umma_f16_off_w<OFF_A, OFF_B>(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+}
+template <bool PAIR>
+__device__ __forceinline__ void halo_commit(uint32_t bar) {
+  if constexpr (PAIR) umma2_commit_w(bar);
+  else umma_commit_w(bar);
+}
+
+template <int BLOCK_N, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmX,
                     const IgemmArgs p, const HaloGeom geo) {
   using L = HaloSmem<BLOCK_N>;
   constexpr int NCH = BLOCK_N / 64;
+  constexpr uint32_t B_SLOT = PAIR ? L::B_TILE / 2 : L::B_TILE;   // a CTA of a pair holds half of the weight rows
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
@@ -614,11 +627,18 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   // lane-0 broadcast: makes the role dispatch below provably warp-uniform, which is what lets ptxas keep the producer
   // and MMA warps on the uniform datapath (with a plain threadIdx.x >> 5 it guards every UTCHMMA with ELECT + R2UR)
-  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  // (the cluster rank rides in the same broadcast: a separately read %cluster_ctarank is not treated as warp-uniform)
+  const uint32_t wr = __shfl_sync(0xffffffffu, (threadIdx.x >> 5) | (PAIR ? cluster_ctarank() << 8 : 0u), 0);
+  const int warp = static_cast<int>(wr & 0xffu);
   const int lane = threadIdx.x & 31;
   const int n_tiles = (p.n_total + BLOCK_N - 1) / BLOCK_N;
   const int tiles_per_img = p.tiles_h * p.tiles_w;
-  const long long total_tiles = static_cast<long long>(p.N) * tiles_per_img * n_tiles;
+  // PAIR: the two CTAs of a cluster walk the list of pixel-tile PAIRS together (CTA r owns pixel tile 2*pair + r; an
+  // odd tile count leaves the last pair's second tile past the last image: zero-filled loads, nothing stored)
+  const uint32_t crank = wr >> 8;
+  const long long m_tiles = static_cast<long long>(p.N) * tiles_per_img;
+  const long long total_tiles = (PAIR ? (m_tiles + 1) / 2 : m_tiles) * n_tiles;
+  const long long tile_first = PAIR ? (blockIdx.x >> 1) : blockIdx.x, tile_step = PAIR ? (gridDim.x >> 1) : gridDim.x;
   const int BST = p.stages;
   const uint32_t a_tx = static_cast<uint32_t>((p.th + 2) * geo.wb * 128);
 
@@ -630,20 +650,21 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int s = 0; s < BST; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     mbar_init(&tmem_full[0], 1);
     mbar_init(&tmem_full[1], 1);
-    mbar_init(&tmem_empty[0], 8);
-    mbar_init(&tmem_empty[1], 8);
+    mbar_init(&tmem_empty[0], PAIR ? 16 : 8);     // the leader's MMA warp waits for both CTAs' epilogue warps
+    mbar_init(&tmem_empty[1], PAIR ? 16 : 8);
     mbar_init(&tmem_empty[2], 1);              // x_full[0], x_full[1]: the fused BN-backward x tiles of the two groups
     mbar_init(&tmem_empty[3], 1);
     fence_mbar_init();
     fence_proxy_async_smem();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr, 4 * BLOCK_N);
-    tmem_relinquish();
+    if (PAIR) { tmem_alloc2(tmem_ptr, 4 * BLOCK_N); tmem_relinquish2(); }
+    else { tmem_alloc(tmem_ptr, 4 * BLOCK_N); tmem_relinquish(); }
   }
   for (int i = threadIdx.x; i < 2 * kHaloStatCh; i += kThreads) ssum[i] = 0.f;
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();           // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -653,34 +674,49 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint32_t a_ring_u = uniform_u32(smem_u32(a_ring)), b_ring_u = a_ring_u + kHaloAStages * a_bytes;
       const uint32_t afull_u = uniform_u32(smem_u32(a_full)), aempty_u = afull_u + kHaloAStages * 8;
       const uint32_t bfull_u = aempty_u + kHaloAStages * 8, bempty_u = bfull_u + kHaloMaxBStages * 8;
+      // loads of both CTAs complete on the LEADER's full barriers, which expect the bytes of both
+      const uint32_t afull_l = PAIR ? mapa_u32(afull_u, 0) : afull_u, bfull_l = PAIR ? mapa_u32(bfull_u, 0) : bfull_u;
+      const bool expect = !PAIR || crank == 0;
       uint32_t sa = 0, pha = 0, sb = 0, phb = 0;
-      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (long long tile = tile_first; tile < total_tiles; tile += tile_step) {
         const int n_tile = static_cast<int>(tile % n_tiles);
-        const int m_tile = static_cast<int>(tile / n_tiles);
+        const int m_tile = static_cast<int>(tile / n_tiles) * (PAIR ? 2 : 1) + static_cast<int>(crank);
         const int img = m_tile / tiles_per_img;
         const int rr = m_tile - img * tiles_per_img;
         const int h0 = (rr / p.tiles_w) * p.th, w0 = (rr % p.tiles_w) * p.tw;
         const int n0 = n_tile * BLOCK_N;
         for (int cc = 0; cc < p.kchunks; ++cc) {
           mbar_wait_w(aempty_u + sa * 8, pha ^ 1);
-          mbar_arrive_expect_tx_w(afull_u + sa * 8, a_tx);
-          tma_load_4d_w(a_ring_u + sa * a_bytes, &tmA, afull_u + sa * 8, cc * 64, w0 - 1, h0 - 1, img);
+          if (expect) mbar_arrive_expect_tx_w(afull_u + sa * 8, PAIR ? 2 * a_tx : a_tx);
+          if (PAIR) tma_load_4d_w2(a_ring_u + sa * a_bytes, &tmA, afull_l + sa * 8, cc * 64, w0 - 1, h0 - 1, img);
+          else tma_load_4d_w(a_ring_u + sa * a_bytes, &tmA, afull_u + sa * 8, cc * 64, w0 - 1, h0 - 1, img);
           if (++sa == kHaloAStages) { sa = 0; pha ^= 1; }
 #pragma unroll 1
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait_w(bempty_u + sb * 8, phb ^ 1);
-            const uint32_t fb = bfull_u + sb * 8;
-            mbar_arrive_expect_tx_w(fb, L::B_TILE);
-            tma_load_2d_w(b_ring_u + sb * L::B_TILE, &tmB, fb, (tap * p.kchunks + cc) * 64, n0);
+            if (expect) mbar_arrive_expect_tx_w(bfull_u + sb * 8, L::B_TILE);
+            if (PAIR) tma_load_2d_w2(b_ring_u + sb * B_SLOT, &tmB, bfull_l + sb * 8, (tap * p.kchunks + cc) * 64,
+                                     n0 + static_cast<int>(crank) * (BLOCK_N / 2));
+            else tma_load_2d_w(b_ring_u + sb * B_SLOT, &tmB, bfull_u + sb * 8, (tap * p.kchunks + cc) * 64, n0);
             if (++sb == static_cast<uint32_t>(BST)) { sb = 0; phb ^= 1; }
           }
         }
       }
+      if (PAIR) {      // tail: every multicast commit aimed at this CTA's empty barriers has landed before it may exit
+        for (int i = 0; i < kHaloAStages; ++i) {
+          mbar_wait_w(aempty_u + sa * 8, pha ^ 1);
+          if (++sa == kHaloAStages) { sa = 0; pha ^= 1; }
+        }
+        for (int i = 0; i < BST; ++i) {
+          mbar_wait_w(bempty_u + sb * 8, phb ^ 1);
+          if (++sb == static_cast<uint32_t>(BST)) { sb = 0; phb ^= 1; }
+        }
+      }
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer (whole warp converged) ===========================
-    {
-      const uint32_t idesc = make_idesc_16(128, BLOCK_N, 0, 0, p.a_dt, p.b_dt);
+    // =========================== MMA issuer (whole warp converged; the leader CTA of a pair) ===========================
+    if (!PAIR || crank == 0) {
+      const uint32_t idesc = make_idesc_16(PAIR ? 256 : 128, BLOCK_N, 0, 0, p.a_dt, p.b_dt);
       const uint32_t sbo = static_cast<uint32_t>(geo.wb * 128);
       const uint32_t a_ring_u = uniform_u32(smem_u32(a_ring)), b_ring_u = a_ring_u + kHaloAStages * a_bytes;
       const uint32_t afull_u = uniform_u32(smem_u32(a_full)), aempty_u = afull_u + kHaloAStages * 8;
@@ -693,7 +729,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const uint64_t dA = make_smem_desc_sw128(0, 16, sbo), dB = make_smem_desc_sw128(0, 16, 1024);
       const uint32_t a_hi = static_cast<uint32_t>(dA >> 32), b_hi = static_cast<uint32_t>(dB >> 32);
       uint32_t sa = 0, pha = 0, sb = 0, phb = 0, lt = 0;
-      for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+      for (long long tile = tile_first; tile < total_tiles; tile += tile_step, ++lt) {
         const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
         mbar_wait_w(tempty_u + as * 8, aph ^ 1);
         tc_fence_after();
@@ -713,16 +749,16 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             {                                                                                     \
               mbar_wait_w(bfull_u + sb * 8, phb);                                                 \
               tc_fence_after();                                                                   \
-              const uint32_t b_lo = static_cast<uint32_t>(dB) | ((b_ring_u + sb * L::B_TILE) >> 4); \
-              umma_f16_off_w<S * 8 + 0, 0>(t0, aH0, a_hi, b_lo, b_hi, idesc, ACC);                  \
-              umma_f16_off_w<S * 8 + 2, 2>(t0, aH0, a_hi, b_lo, b_hi, idesc, 1u);                   \
-              umma_f16_off_w<S * 8 + 4, 4>(t0, aH0, a_hi, b_lo, b_hi, idesc, 1u);                   \
-              umma_f16_off_w<S * 8 + 6, 6>(t0, aH0, a_hi, b_lo, b_hi, idesc, 1u);                   \
-              umma_f16_off_w<S * 8 + 0, 0>(t1, aH1, a_hi, b_lo, b_hi, idesc, ACC);                  \
-              umma_f16_off_w<S * 8 + 2, 2>(t1, aH1, a_hi, b_lo, b_hi, idesc, 1u);                   \
-              umma_f16_off_w<S * 8 + 4, 4>(t1, aH1, a_hi, b_lo, b_hi, idesc, 1u);                   \
-              umma_f16_off_w<S * 8 + 6, 6>(t1, aH1, a_hi, b_lo, b_hi, idesc, 1u);                   \
-              umma_commit_w(bempty_u + sb * 8);                                                   \
+              const uint32_t b_lo = static_cast<uint32_t>(dB) | ((b_ring_u + sb * B_SLOT) >> 4); \
+              halo_mma<PAIR, S * 8 + 0, 0>(t0, aH0, a_hi, b_lo, b_hi, idesc, ACC);                  \
+              halo_mma<PAIR, S * 8 + 2, 2>(t0, aH0, a_hi, b_lo, b_hi, idesc, 1u);                   \
+              halo_mma<PAIR, S * 8 + 4, 4>(t0, aH0, a_hi, b_lo, b_hi, idesc, 1u);                   \
+              halo_mma<PAIR, S * 8 + 6, 6>(t0, aH0, a_hi, b_lo, b_hi, idesc, 1u);                   \
+              halo_mma<PAIR, S * 8 + 0, 0>(t1, aH1, a_hi, b_lo, b_hi, idesc, ACC);                  \
+              halo_mma<PAIR, S * 8 + 2, 2>(t1, aH1, a_hi, b_lo, b_hi, idesc, 1u);                   \
+              halo_mma<PAIR, S * 8 + 4, 4>(t1, aH1, a_hi, b_lo, b_hi, idesc, 1u);                   \
+              halo_mma<PAIR, S * 8 + 6, 6>(t1, aH1, a_hi, b_lo, b_hi, idesc, 1u);                   \
+              halo_commit<PAIR>(bempty_u + sb * 8);                                                         \
               if (++sb == static_cast<uint32_t>(BST)) { sb = 0; phb ^= 1; }                       \
             }
             HPRI_TAP(0, acc0)
@@ -730,10 +766,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             HPRI_TAP(2, 1u)
 #undef HPRI_TAP
           }
-          umma_commit_w(aempty_u + sa * 8);   // the halo block is free once all nine taps have read it
+          halo_commit<PAIR>(aempty_u + sa * 8);   // the halo block is free once all nine taps have read it
           if (++sa == kHaloAStages) { sa = 0; pha ^= 1; }
         }
-        umma_commit_w(tfull_u + as * 8);
+        halo_commit<PAIR>(tfull_u + as * 8);
       }
     }
   } else {
@@ -756,10 +792,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     for (int j = 0; j < NCH; ++j) { ssv[j] = make_float2(0.f, 0.f); sqv[j] = make_float2(0.f, 0.f); }
     int acc_n0 = -1;
     uint32_t lt = 0;
-    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+    for (long long tile = tile_first; tile < total_tiles; tile += tile_step, ++lt) {
       const uint32_t as = lt & 1, aph = (lt >> 1) & 1;
       const int n_tile = static_cast<int>(tile % n_tiles);
-      const int m_tile = static_cast<int>(tile / n_tiles);
+      const int m_tile = static_cast<int>(tile / n_tiles) * (PAIR ? 2 : 1) + static_cast<int>(crank);
       const int img = m_tile / tiles_per_img;
       const int rr = m_tile - img * tiles_per_img;
       const int h0 = (rr / p.tiles_w) * p.th, w0 = (rr % p.tiles_w) * p.tw;
@@ -771,7 +807,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         acc_n0 = n0;
       }
-      const bool valid = (h0 + my_r < p.H) && (w0 + my_c < p.W);
+      const bool valid = (img < p.N) && (h0 + my_r < p.H) && (w0 + my_c < p.W);
       const uint32_t tmem_acc = tmem_base + as * (2 * BLOCK_N) + g * BLOCK_N + (static_cast<uint32_t>(q * 32) << 16);
       mbar_wait(&tmem_full[as], aph);
       tc_fence_after();
@@ -787,11 +823,14 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (c64 == NCH - 1) {
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[as]);
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[as]), 0));
+            else mbar_arrive(&tmem_empty[as]);
+          }
         }
         fence_proxy_async_smem();
         named_bar_sync(bar_id, 128);
-        if (elected && n0 + c64 * 64 < p.n_total && h0 + geo.hr[g] < p.H && w0 + geo.hc[g] < p.W) {
+        if (elected && img < p.N && n0 + c64 * 64 < p.n_total && h0 + geo.hr[g] < p.H && w0 + geo.hc[g] < p.W) {
           tma_store_4d(&tmO, stage, n0 + c64 * 64, w0 + geo.hc[g], h0 + geo.hr[g], img);
           bulk_commit();
         }
@@ -838,9 +877,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncwarp();
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();           // no remote arrive / multicast commit may target a CTA that has exited
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 4 * BLOCK_N);
+    if (PAIR) tmem_dealloc2(tmem_base, 4 * BLOCK_N);
+    else tmem_dealloc(tmem_base, 4 * BLOCK_N);
   }
 }
 
@@ -1217,21 +1258,33 @@ static int pick_block_n(int n_total, int forced) {
 
 
 // halo kernel launcher -------------------------------------------------------------------
-template <int BLOCK_N>
+template <int BLOCK_N, bool PAIR>
 static int launch_halo_t(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& mx,
                          const IgemmArgs& args, const HaloGeom& geo, long long tiles, cudaStream_t stream) {
   using L = HaloSmem<BLOCK_N>;
-  auto kern = conv3x3_halo_kernel<BLOCK_N>;
+  auto kern = conv3x3_halo_kernel<BLOCK_N, PAIR>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [&] {
     attr_err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   });
   if (attr_err != cudaSuccess) return HPRI_ERR_CUDA;
-  long long grid = tiles < sm_count() ? tiles : sm_count();
+  // `tiles` counts work items: pixel tiles x channel tiles, or (PAIR) pixel-tile pairs x channel tiles walked by a 2-CTA cluster
+  const long long streams = PAIR ? sm_count() / 2 : sm_count();
+  long long grid = (tiles < streams ? tiles : streams) * (PAIR ? 2 : 1);
   if (grid <= 0) return HPRI_ERR_ARG;
-  const size_t smem = (size_t)L::PIPE_OFF + (size_t)kHaloAStages * args.a_bytes + (size_t)args.stages * L::B_STAGE +
-                      (args.bw_sums ? 2 * kStageTile : 0) + 1024;
+  const size_t smem = (size_t)L::PIPE_OFF + (size_t)kHaloAStages * args.a_bytes +
+                      (size_t)args.stages * (PAIR ? L::B_STAGE / 2 : L::B_STAGE) + (args.bw_sums ? 2 * kStageTile : 0) + 1024;
+  if (PAIR) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    ++g_launch_count;
+    return cudaLaunchKernelEx(&cfg, kern, ma, mb, mo, mx, args, geo) == cudaSuccess ? HPRI_OK : HPRI_ERR_CUDA;
+  }
   kern<<<(unsigned)grid, kThreads, smem, stream>>>(ma, mb, mo, mx, args, geo);
   ++g_launch_count;
   return cudaGetLastError() == cudaSuccess ? HPRI_OK : HPRI_ERR_CUDA;
@@ -1250,7 +1303,7 @@ static double pick_halo_tile(int H, int W, int* th, int* tw) {
   return best / ((double)H * W) - 1.0;
 }
 
-static int g_conv_algo = -2;               // -1 heuristic, 0 generic kernel, 1 halo-reuse kernel
+static int g_conv_algo = -2;               // -1 heuristic, 0 generic kernel, 1 halo-reuse kernel on single CTAs, 2 on CTA pairs
 static int conv_algo_override() {          // env HPRI_CONV_ALGO seeds it; hpri_set_conv_algo overrides
   if (g_conv_algo == -2) {
     const char* e = getenv("HPRI_CONV_ALGO");
@@ -1280,11 +1333,11 @@ extern "C" int hpri_conv3x3_halo_ok(int h, int w, int w_rows) {
   const int a_bytes = ((hth + 2) * (htw + 2) * 128 + 1023) / 1024 * 1024;
   const int stages = w_rows <= 64 ? HaloSmem<64>::b_stages_for(a_bytes, 2 * kStageTile)
                                   : HaloSmem<128>::b_stages_for(a_bytes, 2 * kStageTile);
-  return (w_rows <= kHaloStatCh && stages >= 2 && (ov == 1 || (ov < 0 && waste <= 1.0))) ? 1 : 0;
+  return (w_rows <= kHaloStatCh && stages >= 2 && (ov >= 1 || (ov < 0 && waste <= 1.0))) ? 1 : 0;
 }
 
 extern "C" int hpri_set_conv_algo(int algo) {
-  if (algo < -1 || algo > 1) return HPRI_ERR_ARG;
+  if (algo < -1 || algo > 2) return HPRI_ERR_ARG;
   g_conv_algo = algo;
   return HPRI_OK;
 }
@@ -1331,8 +1384,15 @@ extern "C" int hpri_igemm_fwd(const hpri_view_t* x, const void* wpack, int w_dty
     const int hbn = w_rows <= 64 ? 64 : 128;
     const int a_bytes = ((hth + 2) * (htw + 2) * 128 + 1023) / 1024 * 1024;
     const int extra = bw ? 2 * kStageTile : 0;           // x staging tiles of the fused BN-backward reduction
-    const int stages = hbn == 64 ? HaloSmem<64>::b_stages_for(a_bytes, extra) : HaloSmem<128>::b_stages_for(a_bytes, extra);
-    if (stats_ok && stages >= 2 && (ov == 1 || (ov < 0 && waste <= 1.0))) {
+    // CTA pairs (cta_group::2: each CTA stages and reads half of the weight tile) unless HPRI_CONV_ALGO=1 asks for single
+    // CTAs.  The 64-channel dgrads with the fused BN-backward reduction are epilogue-bound and measured 8 % slower in
+    // pairs (the MMA warp then waits for the slower of two epilogues), so they stay on single CTAs.
+    const bool pair = ov == 2 || (ov != 1 && !(bw && hbn == 64));
+    const int b_slot = hbn * 128 / (pair ? 2 : 1);
+    int stages = ((hbn == 64 ? HaloSmem<64>::BUDGET - HaloSmem<64>::PIPE_OFF : HaloSmem<128>::BUDGET - HaloSmem<128>::PIPE_OFF) -
+                  kHaloAStages * a_bytes - extra) / b_slot;
+    if (stages > kHaloMaxBStages) stages = kHaloMaxBStages;
+    if (stats_ok && stages >= 2 && (ov >= 1 || (ov < 0 && waste <= 1.0))) {
       set_tile(a, hth, htw);
       a.stages = stages; a.a_bytes = a_bytes;
       CUtensorMap mx{};
@@ -1347,8 +1407,7 @@ extern "C" int hpri_igemm_fwd(const hpri_view_t* x, const void* wpack, int w_dty
         if ((rc = map_nhwc(&mx, xv, 16, 8)) != HPRI_OK) return rc;
         a.bw_scale = bw->scale; a.bw_shift = bw->shift; a.bw_mean = bw->save_mean; a.bw_invstd = bw->save_invstd;
         a.bw_sums = bw->sums;
-        a.xstage_off = (hbn == 64 ? HaloSmem<64>::PIPE_OFF : HaloSmem<128>::PIPE_OFF) + kHaloAStages * a_bytes +
-                       stages * (hbn == 64 ? HaloSmem<64>::B_STAGE : HaloSmem<128>::B_STAGE);
+        a.xstage_off = (hbn == 64 ? HaloSmem<64>::PIPE_OFF : HaloSmem<128>::PIPE_OFF) + kHaloAStages * a_bytes + stages * b_slot;
       }
       HaloGeom geo{};
       geo.wb = htw + 2;
@@ -1359,12 +1418,15 @@ extern "C" int hpri_igemm_fwd(const hpri_view_t* x, const void* wpack, int w_dty
       uint64_t str[3] = {(uint64_t)x->pix_stride * 2, (uint64_t)x->row_stride * 2, (uint64_t)x->img_stride * 2};
       uint32_t box[4] = {64, (uint32_t)(htw + 2), (uint32_t)(hth + 2), 1};
       if ((rc = make_map(&ma, x->ptr, 4, dims, str, box, x->dtype)) != HPRI_OK) return rc;
-      if ((rc = map_weights(&mb, wpack, w_rows, kpad, hbn, w_dtype)) != HPRI_OK) return rc;
+      if ((rc = map_weights(&mb, wpack, w_rows, kpad, pair ? hbn / 2 : hbn, w_dtype)) != HPRI_OK) return rc;
       if ((rc = map_out(&mo, *y, n_store, 16, 8)) != HPRI_OK) return rc;
-      const long long tiles = (long long)a.N * a.tiles_h * a.tiles_w * ((w_rows + hbn - 1) / hbn);
+      const long long m_tiles = (long long)a.N * a.tiles_h * a.tiles_w;
+      const long long tiles = (pair ? (m_tiles + 1) / 2 : m_tiles) * ((w_rows + hbn - 1) / hbn);
       if (!bw) mx = mo;
-      return hbn == 64 ? launch_halo_t<64>(ma, mb, mo, mx, a, geo, tiles, stream)
-                       : launch_halo_t<128>(ma, mb, mo, mx, a, geo, tiles, stream);
+      if (pair) return hbn == 64 ? launch_halo_t<64, true>(ma, mb, mo, mx, a, geo, tiles, stream)
+                                 : launch_halo_t<128, true>(ma, mb, mo, mx, a, geo, tiles, stream);
+      return hbn == 64 ? launch_halo_t<64, false>(ma, mb, mo, mx, a, geo, tiles, stream)
+                       : launch_halo_t<128, false>(ma, mb, mo, mx, a, geo, tiles, stream);
     }
   }
   if (bw) return HPRI_ERR_ARG;        // the fused reduction exists on the halo kernel only (hpri_conv3x3_halo_ok)
