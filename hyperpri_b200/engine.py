@@ -22,6 +22,7 @@ Dataflow decisions:
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -94,9 +95,53 @@ class _EngineBase:
         self.overflow = torch.zeros(1, dtype=torch.int32, device=device)
         self._pending_unscale, self._S = False, 1.0
         self._gw_dirty = False
+        self._pending_bucket = None
+        self._init_side_stream(device)
 
     def _gw_buffers(self):
         raise NotImplementedError
+
+    # ------------------------------------------------------------------ weight gradients on a second stream
+    # A weight gradient only feeds the optimizer, so nothing later in backward waits for it.  Launched on a second
+    # (lower-priority) stream it fills the SMs the persistent dgrad kernels leave idle in their last wave and runs
+    # under the HBM-bound BatchNorm-backward kernels of the following layers (tensor pipe vs DRAM: different limits).
+    # HPRI_WGRAD_STREAM=0 keeps everything on one stream.
+    def _init_side_stream(self, device):
+        self._side = None
+        self._side_events = []
+        self._side_used = 0
+        if torch.device(device).type == "cuda" and os.environ.get("HPRI_WGRAD_STREAM", "1") != "0":
+            self._side = torch.cuda.Stream(device=device, priority=0)
+
+    def _event(self):
+        if self._side_used == len(self._side_events):
+            self._side_events.append(torch.cuda.Event())
+        ev = self._side_events[self._side_used]
+        self._side_used += 1
+        return ev
+
+    def _on_side(self, fn):
+        """Run fn's launches on the side stream, ordered after everything launched so far on the current stream."""
+        if self._side is None:
+            fn()
+            return
+        ev = self._event()
+        ev.record()
+        self._side.wait_event(ev)
+        with torch.cuda.stream(self._side):
+            fn()
+
+    def _side_mark(self):
+        """Event marking the side stream's work so far (None without a side stream)."""
+        if self._side is None:
+            return None
+        ev = self._event()
+        ev.record(self._side)
+        return ev
+
+    def _join(self, ev):
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
 
     def invalidate_packed(self):
         """Force a re-pack of every 16-bit weight operand at the next forward (what an optimizer step causes)."""
@@ -110,6 +155,8 @@ class _EngineBase:
             for g in self._gw_buffers():
                 g.zero_()
         self._gw_dirty = True
+        self._side_used = 0
+        self._pending_bucket = None
 
     def _end_backward(self):
         self._gw_dirty = False
@@ -216,6 +263,21 @@ class UNetEngine(_EngineBase):
         del start
 
     def _bucket_done(self, idx):
+        """Bucket idx has been launched.  Its weight gradients run on the side stream, so the unpack + all-reduce hook of
+        a bucket is issued one bucket late (after the NEXT bucket's launches): the join then waits for work that has had
+        a whole bucket of main-stream kernels to finish under."""
+        mark = self._side_mark()
+        if self._pending_bucket is not None:
+            self._flush_bucket()
+        self._pending_bucket = (idx, mark)
+        if idx == 8:
+            self._flush_bucket()
+
+    def _flush_bucket(self):
+        idx, mark = self._pending_bucket
+        self._pending_bucket = None
+        if self.bucket_hook is not None or idx == 8:      # a single process only joins once, before the one unpack launch
+            self._join(mark)
         self._unpack_bucket(idx)
         if self.bucket_hook is not None:
             a, b = self.bucket_bounds[idx]
@@ -252,7 +314,9 @@ class UNetEngine(_EngineBase):
                     ws[f"dec_act_b{l}"] = _e((n, H[l], W[l], C[l]), d)
             else:
                 ws["act_b4"] = _e((n, H[4], W[4], C[4]), d)
-            ws[f"R{l}"] = _e((n, H[l], W[l], C[l]), d, GRAD)      # grad wrt a raw conv output
+            ws[f"R{l}"] = _e((n, H[l], W[l], C[l]), d, GRAD)      # grad wrt a raw conv output (second conv of a block)
+            # the first conv of a block gets its own: the second conv's weight gradient may still be reading R{l}
+            ws[f"Ra{l}"] = _e((n, H[l], W[l], C[l]), d, GRAD) if self._side is not None else ws[f"R{l}"]
             ws[f"A{l}"] = _e((n, H[l], W[l], C[l]), d, GRAD)      # grad wrt an activation
         if GRAD != ACT:
             ws["cvt"] = _e((n * h * w * max(self.cin_pad, 2 * C[0]),), d, GRAD)
@@ -303,7 +367,8 @@ class UNetEngine(_EngineBase):
         ops.bn_relu_bwd(raw, L.scale, L.shift, L.smean, L.sinv, P[L.bn + ".weight"], R, L.sums, count, dy=dy,
                         dpool=dpool, head_w=head_w, dlogit=dlogit, dgamma=self._grad(L.bn + ".weight", L.scale[:L.cout]),
                         dbeta=self._grad(L.bn + ".bias", L.scale[:L.cout]), dhead_w=dhead_w, reduced=reduced)
-        ops.igemm_wgrad(self._as_grad_dtype(x_in), R, 1, L.cout, L.gw)
+        xg = self._as_grad_dtype(x_in)
+        self._on_side(lambda: ops.igemm_wgrad(xg, R, 1, L.cout, L.gw))
         # the packed gradient is unpacked into the arena per bucket (_unpack_bucket); the conv bias gradient is
         # identically zero under train-mode BN
         if dx_out is not None:
@@ -435,7 +500,7 @@ class UNetEngine(_EngineBase):
             else:
                 self._cbr_bwd(b, ws[f"dec_act_a{l}"], ws[f"dec_raw_b{l}"], ws[f"R{l}"], cnt[l], dy=g_in,
                               dx_out=ws[f"A{l}"], below=below)
-            self._cbr_bwd(a, ws[f"cat{l}"], ws[f"dec_raw_a{l}"], ws[f"R{l}"], cnt[l], dy=ws[f"A{l}"],
+            self._cbr_bwd(a, ws[f"cat{l}"], ws[f"dec_raw_a{l}"], ws[f"Ra{l}"], cnt[l], dy=ws[f"A{l}"],
                           dx_out=ws[f"gcat{l}"], reduced=fuse)
             # ConvTranspose2d backward: its output is the second half of cat[l] over the 2h x 2w region
             i = 4 - l
@@ -444,10 +509,13 @@ class UNetEngine(_EngineBase):
             x_up = ws[f"dec_act_b{l + 1}"] if l < 3 else ws["act_b4"]
             ops.convT_dgrad(dy_up, up.dgr, C[l + 1], ws[f"A{l + 1}"])
             gw = self.up_gw[l]
-            ops.igemm_wgrad(self._as_grad_dtype(x_up), dy_up, 2, 4 * C[l], gw)
             wn = f"up{i}.up.weight"
-            up.spec.unpack_grad(gw, self._grad(wn, P[wn]).view(-1))
-            ops.colsum(dy_up, self._grad(f"up{i}.up.bias", P[f"up{i}.up.bias"]))
+
+            def up_wgrad(x_up=self._as_grad_dtype(x_up), dy_up=dy_up, gw=gw, up=up, wn=wn, l=l, i=i):
+                ops.igemm_wgrad(x_up, dy_up, 2, 4 * C[l], gw)
+                up.spec.unpack_grad(gw, self._grad(wn, P[wn]).view(-1))
+                ops.colsum(dy_up, self._grad(f"up{i}.up.bias", P[f"up{i}.up.bias"]))
+            self._on_side(up_wgrad)
             g_in = ws[f"A{l + 1}"]
             self._bucket_done(l)
         # encoder, deepest first
@@ -462,7 +530,7 @@ class UNetEngine(_EngineBase):
                 self._cbr_bwd(b, ws[f"enc_act_a{l}"], ws[f"enc_raw_b{l}"], ws[f"R{l}"], cnt[l],
                               dy=ws[f"gcat{l}"][..., :C[l]], dpool=ws[f"gpool{l + 1}"], dx_out=ws[f"A{l}"], below=below)
             x_in = ws[f"pool{l}"] if l > 0 else ws["x"]
-            self._cbr_bwd(a, x_in, ws[f"enc_raw_a{l}"], ws[f"R{l}"], cnt[l], dy=ws[f"A{l}"],
+            self._cbr_bwd(a, x_in, ws[f"enc_raw_a{l}"], ws[f"Ra{l}"], cnt[l], dy=ws[f"A{l}"],
                           dx_out=ws[f"gpool{l}"] if l > 0 else None, reduced=fuse)
             self._bucket_done(4 + (4 - l))
         if self.first == "cube":               # module registered twice (models.py:169-171): same tensor
