@@ -616,7 +616,9 @@ class SpectralEngine(_EngineBase):
             ws["img"].append(im)
         for k in (2, 3, 4):
             ws[f"gcat{k}"] = _z((1, 1, m, 2 * Fp), d, GRAD)
-        ws["R"] = _z((1, 1, m, Fp), d, GRAD)
+        # gradient wrt a raw GEMM output; three rotate when the weight gradients run on the side stream (the one of
+        # layer k may still be reading its buffer while layers k+1, k+2 are written)
+        ws["R"] = [_z((1, 1, m, Fp), d, GRAD) for _ in range(3 if self._side is not None else 1)]
         if GRAD != ACT:
             ws["cvt"] = _z((1, 1, m, max(2 * Fp, self.Dp)), d, GRAD)
         ws["dlogit_s"] = _e((n, 1, r, c), d, torch.float32)
@@ -706,11 +708,11 @@ class SpectralEngine(_EngineBase):
         ops.sum_f32(dlogit, self._grad("outc.bias", P["outc.bias"]))
         first_img = True
         dwo_acc = torch.zeros_like(self.dw_outc)
+        r_turn, r_busy = 0, {}
         for i in range(ws["n"]):
             im = ws["img"][i]
             dl = dlogit[i].reshape(-1)
             xin = ws["x"][i].reshape(1, 1, m, self.Dp)
-            R = ws["R"]
             # (block, dy source, dgrad destination, accumulate?)
             plan = [("up4", None, ws["gcat2"], False), ("up3", ws["gcat2"][..., Fp:], ws["gcat3"], False),
                     ("up2", ws["gcat3"][..., Fp:], ws["gcat4"], False), ("up1", ws["gcat4"][..., Fp:], ws["g4"], False),
@@ -732,6 +734,10 @@ class SpectralEngine(_EngineBase):
                     dhw = self.dw_outc[off:off + Fp]
                 dg = torch.empty(F, dtype=torch.float32, device=self.dev)
                 db = torch.empty(F, dtype=torch.float32, device=self.dev)
+                k = r_turn % len(ws["R"])
+                r_turn += 1
+                R = ws["R"][k]
+                self._join(r_busy.get(k))          # the weight gradient that last read this buffer has finished
                 ops.bn_relu_bwd(im["raw_" + nm], scale, shift, smean, sinv, P[nm + ".1.weight"], R, L.sums, m, dy=dy,
                                 head_w=hw, dlogit=dl if head else None, dgamma=dg, dbeta=db, dhead_w=dhw, c=F)
                 g_g = self._grad(nm + ".1.weight", P[nm + ".1.weight"])
@@ -741,7 +747,9 @@ class SpectralEngine(_EngineBase):
                 else:
                     g_g.add_(dg); g_b.add_(db)
                 xg = src if src.dtype == GRAD else ops.convert16(src, ws["cvt"][..., :src.shape[-1]])
-                ops.igemm_wgrad(xg, R, 0, F, L.gw, x_c=(self.D if nm == "tail" else None), dy_c=F)
+                self._on_side(lambda xg=xg, R=R, L=L, nm=nm: ops.igemm_wgrad(
+                    xg, R, 0, F, L.gw, x_c=(self.D if nm == "tail" else None), dy_c=F))
+                r_busy[k] = self._side_mark()
                 if dx_dst is not None:
                     if L.pp.spec.split:
                         ops.igemm_fwd(R, L.dgr_cat, 2 * Fp, 1, dx_dst, 2 * Fp, x_c=F, accumulate=acc)
@@ -749,6 +757,7 @@ class SpectralEngine(_EngineBase):
                         ops.igemm_fwd(R, L.pp.dgr, F, 1, dx_dst, Fp, x_c=F, accumulate=acc, block_n=self.bn_tile)
             dwo_acc.add_(self.dw_outc)
             first_img = False
+        self._join(self._side_mark())
         for nm, L in self.L.items():
             wn = nm + ".0.weight"
             L.pp.spec.unpack_grad(L.gw, self._grad(wn, P[wn]).view(-1))
