@@ -120,14 +120,21 @@ class _EngineBase:
         self._side_used += 1
         return ev
 
-    def _on_side(self, fn):
-        """Run fn's launches on the side stream, ordered after everything launched so far on the current stream."""
+    def _fork(self):
+        """Event marking the current stream's work so far, for a later _on_side(fn, after=...)."""
+        if self._side is None:
+            return None
+        ev = self._event()
+        ev.record()
+        return ev
+
+    def _on_side(self, fn, after=None):
+        """Run fn's launches on the side stream, ordered after `after` (default: everything launched so far on the
+        current stream)."""
         if self._side is None:
             fn()
             return
-        ev = self._event()
-        ev.record()
-        self._side.wait_event(ev)
+        self._side.wait_event(after if after is not None else self._fork())
         with torch.cuda.stream(self._side):
             fn()
 
@@ -368,15 +375,18 @@ class UNetEngine(_EngineBase):
                         dpool=dpool, head_w=head_w, dlogit=dlogit, dgamma=self._grad(L.bn + ".weight", L.scale[:L.cout]),
                         dbeta=self._grad(L.bn + ".bias", L.scale[:L.cout]), dhead_w=dhead_w, reduced=reduced)
         xg = self._as_grad_dtype(x_in)
-        self._on_side(lambda: ops.igemm_wgrad(xg, R, 1, L.cout, L.gw))
-        # the packed gradient is unpacked into the arena per bucket (_unpack_bucket); the conv bias gradient is
-        # identically zero under train-mode BN
+        ready = self._fork()                 # R is complete here
+        # the dgrad is on the critical path of backward: it is launched first so that it, not the weight gradient, gets
+        # the SMs; the weight gradient then fills in behind it
         if dx_out is not None:
             bw = None
             if below is not None:
                 Lb, raw_b = below
                 bw = (raw_b, Lb.scale, Lb.shift, Lb.smean, Lb.sinv, Lb.sums)
             ops.igemm_fwd(R, L.pp.dgr, L.cin, 9, dx_out, L.cin, bw=bw)
+        # the packed gradient is unpacked into the arena per bucket (_unpack_bucket); the conv bias gradient is
+        # identically zero under train-mode BN
+        self._on_side(lambda: ops.igemm_wgrad(xg, R, 1, L.cout, L.gw), after=ready)
 
     def _fusable(self, l):
         """The a-layer of level l gets its whole output gradient from the b-layer's dgrad launch; the reduction can
