@@ -229,6 +229,13 @@ class UNetEngine(_EngineBase):
             self.dec[lvl] = [_CBR(p + ".0", p + ".1", 2 * C[lvl], C[lvl], d), _CBR(p + ".3", p + ".4", C[lvl], C[lvl], d)]
             self.up[lvl] = _PackedParam(WeightSpec("convT2x2", C[lvl], C[lvl + 1]), True)
             self.up_gw[lvl] = self.up[lvl].spec.grad_buffer(d)
+        # BN-backward sums of every layer in one buffer: the ones accumulated by dgrad epilogues are cleared by ONE fill
+        layers = [L for grp in list(self.enc) + list(self.dec.values()) for L in grp]
+        self._bw_sums = _z((sum(L.cout for L in layers), 3), d, torch.float64)
+        off = 0
+        for L in layers:
+            L.sums = self._bw_sums[off:off + L.cout]
+            off += L.cout
         # the first conv's real input-channel count differs from the padded view: pack from the true layout
         self.enc[0][0].pp = _PackedParam(_first_spec(in_ch, self.cin_pad), False)
         self.enc[0][0].gw = self.enc[0][0].pp.spec.grad_buffer(d)
@@ -383,7 +390,7 @@ class UNetEngine(_EngineBase):
             if below is not None:
                 Lb, raw_b = below
                 bw = (raw_b, Lb.scale, Lb.shift, Lb.smean, Lb.sinv, Lb.sums)
-            ops.igemm_fwd(R, L.pp.dgr, L.cin, 9, dx_out, L.cin, bw=bw)
+            ops.igemm_fwd(R, L.pp.dgr, L.cin, 9, dx_out, L.cin, bw=bw, zero_sums=False)
         # the packed gradient is unpacked into the arena per bucket (_unpack_bucket); the conv bias gradient is
         # identically zero under train-mode BN
         self._on_side(lambda: ops.igemm_wgrad(xg, R, 1, L.cout, L.gw), after=ready)
@@ -494,6 +501,7 @@ class UNetEngine(_EngineBase):
         ws, P, C = self.ws, self.P, self.CH
         n, H, W = ws["n"], ws["H"], ws["W"]
         self._begin_backward()
+        self._bw_sums.zero_()              # one fill for the BN-backward sums the dgrad epilogues accumulate into
         dlogit = self._scaled_dlogit(dlogit, prescaled)
         cnt = [n * H[l] * W[l] for l in range(5)]
         head_w = P["outc.conv.weight"].detach().reshape(-1)

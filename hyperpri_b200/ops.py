@@ -216,16 +216,18 @@ class WeightSpec:
 # ----------------------------------------------------------------------------- contractions
 @_timed
 def igemm_fwd(x, wpack, rows, taps, y, n_store, bias=None, stats=None, block_n=0, x_c=None, y_c=None,
-              accumulate=False, fin=None, bw=None):
+              accumulate=False, fin=None, bw=None, zero_sums=True):
     """fin: a BnFin from bn_fin(...) -> the launch also finalises train-mode BatchNorm (scale / shift / saved and
     running statistics) in its last CTA; no separate bn_finalize launch is needed.
     bw: (raw_below, scale, shift, save_mean, save_invstd, sums) of the BatchNorm+ReLU layer whose output gradient this
-    3x3 dgrad launch produces -> its backward reduction (pass 1) is accumulated in the epilogue (sums zeroed here)."""
+    3x3 dgrad launch produces -> its backward reduction (pass 1) is accumulated in the epilogue (sums zeroed here
+    unless the caller has already cleared them: zero_sums=False)."""
     xv, yv = view(x, x_c), view(y, y_c)
     bws = None
     if bw is not None:
         raw, sc, sh, mu, iv, sums = bw
-        sums.zero_()
+        if zero_sums:
+            sums.zero_()
         rv = view(raw, y_c)
         bws = _lib.BnBwd(C.pointer(rv), sc.data_ptr(), sh.data_ptr(), mu.data_ptr(), iv.data_ptr(), sums.data_ptr())
     check(_lib.lib().hpri_igemm_fwd(_vp(xv), _ptr(wpack), _DT[wpack.dtype], rows, wpack.shape[1], taps, _vp(yv), n_store, _ptr(bias),
