@@ -281,12 +281,19 @@ def main():
     value = n * world * args.steps / (ms_total / 1e3)
 
     # ---------------- per-kernel durations (CUDA events around every native call; separate pass)
-    prof_steps = 2
+    # The weight-gradient side stream is switched off for this pass: with two streams sharing the SMs an event pair around
+    # one kernel also counts the time it waited for the other stream's kernel, so only serialised launches give a
+    # kernel's own duration.  (The timed region above runs with the overlap on.)
+    prof_steps = 3
+    eng.set_overlap(False)
+    step()
+    torch.cuda.synchronize()
     ops.PROFILE = []
     for _ in range(prof_steps):
         step()
     torch.cuda.synchronize()
     rec, ops.PROFILE = ops.PROFILE, None
+    eng.set_overlap(True)
     per = {}
     per_launch = []
     for name, a, b, desc in rec:
@@ -297,6 +304,12 @@ def main():
         d[0] += t / prof_steps
         d[1] += 1
     tensor_ms = sum(v[0] for k, v in per.items() if k in ops.TENSOR_KERNELS)
+    # median over the profiled steps (a host hiccup between two launches of one step otherwise skews the mean)
+    chunk = len(rec) // prof_steps
+    if chunk * prof_steps == len(rec) and chunk > 0:
+        per_step = sorted(sum(a.elapsed_time(b) for name, a, b, _ in rec[i * chunk:(i + 1) * chunk] if name in ops.TENSOR_KERNELS)
+                          for i in range(prof_steps))
+        tensor_ms = per_step[prof_steps // 2]
     tensor_launches = sum(v[1] for k, v in per.items() if k in ops.TENSOR_KERNELS) // prof_steps
     all_ms = sum(v[0] for v in per.values())
     peak_tf, peak_gbs, peak_src = peaks()
@@ -304,17 +317,19 @@ def main():
     achieved = flops_step / (tensor_ms / 1e3) / 1e12 if tensor_ms > 0 else 0.0
     # DRAM traffic of the same launches from the committed ncu capture (same workload only: CubeNET-64, batch 2, train)
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "traffic_r1g.json")
+    tp = os.path.join(ROOT, "profiles", "traffic_r1h.json")
     if args.model == "CubeNET" and n == 2 and train and os.path.exists(tp):
         with open(tp) as f:
             tj = json.load(f)
-        traffic, traffic_src = tj["tensor_family_dram_bytes_per_launch"], "profiles/traffic_r1g.json (ncu, per launch)"
+        traffic, traffic_src = tj["tensor_family_dram_bytes_per_launch"], "profiles/traffic_r1h.json (ncu, per launch)"
     roofline = {"bound": "tensor", "kernel": "conv3x3_halo_kernel<BLOCK_N> + igemm_kernel<BLOCK_N,STAGES,MODE> (tcgen05 implicit GEMM family: every "
                           "conv3x3 / ConvTranspose / Linear fwd, dgrad and wgrad launch of the step)",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
                 "traffic_source": traffic_src,
                 "peak_source": peak_src, "flops_per_step": flops_step, "kernel_ms_per_step": tensor_ms,
-                "launches_per_step": tensor_launches, "share_of_step": tensor_ms / all_ms if all_ms else None}
+                "launches_per_step": tensor_launches, "share_of_step": tensor_ms / all_ms if all_ms else None,
+                "timing": "CUDA events around every launch, launches serialised (weight-gradient side stream off for this "
+                          "pass); share_of_step is of the serialised sum of kernel times"}
     if args.breakdown and rank == 0:
         with open(args.breakdown, "w") as f:
             json.dump({"ms_per_step_sum_of_kernels": all_ms, "ms_per_step_wall": ms_step,

@@ -180,6 +180,7 @@ __device__ __forceinline__ int find_job(const hpri_conv3x3_job_t* __restrict__ j
   return j;
 }
 __global__ void __launch_bounds__(256) pack_conv3x3_batch_k(const hpri_conv3x3_job_t* __restrict__ jobs, int njobs) {
+  grid_dep_launch();      // a following tcgen05 launch may start its prologue while this grid drains
   __shared__ float tile[32][289];
   const int j = find_job(jobs, njobs, blockIdx.x);
   const hpri_conv3x3_job_t jb = jobs[j];
@@ -319,6 +320,7 @@ __global__ void __launch_bounds__(256)
 hsi_ingest_k(const T* __restrict__ src, int bands_total, int H, int W, int lo, int nb, int i0, int j0, int h,
              int w, int flip_h, int flip_w, float scale, const float* __restrict__ bmean,
              const float* __restrict__ bstd, uint16_t* __restrict__ dst, int dt, int c_pad) {
+  grid_dep_launch();      // a following tcgen05 launch may start its prologue while this grid drains
   extern __shared__ uint4 tile4[];               // [64 pixels][row_chunks] 16-byte chunks
   const int chunks = c_pad >> 3;                 // 8 channels per chunk
   const int row_chunks = (chunks + 7) & ~7;
@@ -433,6 +435,7 @@ __global__ void bn_finalize_k(double* stats, long long count, const float* gamma
 template <int DT>
 __global__ void __launch_bounds__(256)
 bn_relu_apply_k(V x, const float* __restrict__ scale, const float* __restrict__ shift, V y, V pool, int CG, int rows) {
+  grid_dep_launch();      // a following tcgen05 launch may start its prologue while this grid drains
   // grid.x tiles the (window column, channel group) plane, grid.y chunks of `rows` window rows, grid.z the image:
   // a thread keeps its scale / shift in registers and walks rows without index arithmetic
   const int wh = (x.h + 1) >> 1, ww = (x.w + 1) >> 1;
@@ -482,6 +485,7 @@ __global__ void __launch_bounds__(256)
 bn_relu_apply_flat_k(const uint16_t* __restrict__ x, long long sx, int xdt, uint16_t* __restrict__ y, long long sy,
                      int ydt, int C, long long npix, const float* __restrict__ scale, const float* __restrict__ shift,
                      int slots, int CG) {
+  grid_dep_launch();      // a following tcgen05 launch may start its prologue while this grid drains
   const int cg = threadIdx.x % CG, slot = threadIdx.x / CG;
   if (slot >= slots) return;
   const int c0 = cg * 8;
@@ -649,6 +653,7 @@ template <int DT, bool HEAD>
 __global__ void __launch_bounds__(256, 2)
 bn_bwd_apply_k(BwdIn a, const float* __restrict__ gamma, const double* __restrict__ sums, long long count, V dx,
                float* dgamma, float* dbeta, float* dhead_w, int CG, int rows) {
+  grid_dep_launch();      // a following tcgen05 launch may start its prologue while this grid drains
   if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
     for (int c = threadIdx.x; c < a.x.c; c += blockDim.x) {
       if (dbeta) dbeta[c] = (float)sums[3 * c];
@@ -794,6 +799,7 @@ __global__ void __launch_bounds__(256, 2)
 bn_bwd_apply_flat_k(FlatIn a, const float* __restrict__ gamma, const double* __restrict__ sums, long long count,
                     uint16_t* __restrict__ dx, long long sdx, int dxdt, float* dgamma, float* dbeta, float* dhead_w,
                     int slots, int CG) {
+  grid_dep_launch();      // a following tcgen05 launch may start its prologue while this grid drains
   if (blockIdx.x == 0) {
     for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
       if (dbeta) dbeta[c] = (float)sums[3 * c];

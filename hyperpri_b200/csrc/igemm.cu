@@ -281,6 +281,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  grid_dep_launch();
+  grid_dep_wait();            // everything above overlapped the previous kernel's tail; its outputs are visible from here
 
   // decode a tile index into (m_tile, n_tile, [kb_begin, kb_end))
   auto decode = [&](long long tile, int& m_tile, int& n_tile, int& kb_begin, int& kb_end) {
@@ -667,6 +669,8 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (PAIR) cluster_sync_all();           // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  grid_dep_launch();
+  grid_dep_wait();            // everything above overlapped the previous kernel's tail; its outputs are visible from here
 
   if (warp == 0) {
     // =========================== TMA producer (whole warp converged) ===========================
@@ -955,6 +959,8 @@ wgrad3x3_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  grid_dep_launch();
+  grid_dep_wait();            // everything above overlapped the previous kernel's tail; its outputs are visible from here
 
   // work item -> (pair, first unit, unit count, k-block range)
   auto decode = [&](long long item, int& pair, int& u0, int& nu, int& kb_begin, int& kb_end) {
@@ -1218,6 +1224,37 @@ static int sm_count() {
 
 struct OutMaps { CUtensorMap m[4]; };
 
+// Launch with programmatic stream serialisation (the kernels call grid_dep_wait() after their prologue) and, for the
+// CTA-pair kernels, a cluster of two.  HPRI_PDL=0 falls back to plain stream order.
+static bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("HPRI_PDL");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+template <typename K, typename... A>
+static cudaError_t launch_ex(K kern, long long grid, size_t smem, cudaStream_t stream, bool cluster2, A... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  unsigned n = 0;
+  if (cluster2) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = 2; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = at; cfg.numAttrs = n;
+  ++g_launch_count;
+  return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 template <int BLOCK_N, int STAGES, int MODE>
 static int launch_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0, const CUtensorMap& b1,
                     const OutMaps& o, const IgemmArgs& args, long long grid, cudaStream_t stream) {
@@ -1231,9 +1268,8 @@ static int launch_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensor
   if (attr_err != cudaSuccess) return HPRI_ERR_CUDA;
   if (grid <= 0 || grid > 0x7FFFFFFFLL) return HPRI_ERR_ARG;
   if (grid > sm_count()) grid = sm_count();          // persistent: one CTA per SM walks the tile list
-  kern<<<(unsigned)grid, kThreads, L::ALLOC, stream>>>(a0, a1, b0, b1, o.m[0], o.m[1], o.m[2], o.m[3], args);
-  ++g_launch_count;
-  return cudaGetLastError() == cudaSuccess ? HPRI_OK : HPRI_ERR_CUDA;
+  return launch_ex(kern, grid, L::ALLOC, stream, false, a0, a1, b0, b1, o.m[0], o.m[1], o.m[2], o.m[3], args) == cudaSuccess
+             ? HPRI_OK : HPRI_ERR_CUDA;
 }
 
 template <int MODE>
@@ -1275,19 +1311,7 @@ static int launch_halo_t(const CUtensorMap& ma, const CUtensorMap& mb, const CUt
   if (grid <= 0) return HPRI_ERR_ARG;
   const size_t smem = (size_t)L::PIPE_OFF + (size_t)kHaloAStages * args.a_bytes +
                       (size_t)args.stages * (PAIR ? L::B_STAGE / 2 : L::B_STAGE) + (args.bw_sums ? 2 * kStageTile : 0) + 1024;
-  if (PAIR) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    ++g_launch_count;
-    return cudaLaunchKernelEx(&cfg, kern, ma, mb, mo, mx, args, geo) == cudaSuccess ? HPRI_OK : HPRI_ERR_CUDA;
-  }
-  kern<<<(unsigned)grid, kThreads, smem, stream>>>(ma, mb, mo, mx, args, geo);
-  ++g_launch_count;
-  return cudaGetLastError() == cudaSuccess ? HPRI_OK : HPRI_ERR_CUDA;
+  return launch_ex(kern, grid, smem, stream, PAIR, ma, mb, mo, mx, args, geo) == cudaSuccess ? HPRI_OK : HPRI_ERR_CUDA;
 }
 
 // 256-pixel tile = two 16 x 8 halves, stacked (32 x 8) or side by side (16 x 16): minimise padded pixels;
@@ -1582,10 +1606,9 @@ extern "C" int hpri_igemm_wgrad(const hpri_view_t* x, const hpri_view_t* dy, int
           attr_err = cudaFuncSetAttribute(kern128, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
       });
       if (attr_err != cudaSuccess) return HPRI_ERR_CUDA;
-      if (n_total == 64) kern64<<<(unsigned)grid, kThreads, smem, stream>>>(mx, mdy, g);
-      else kern128<<<(unsigned)grid, kThreads, smem, stream>>>(mx, mdy, g);
-      ++g_launch_count;
-      return cudaGetLastError() == cudaSuccess ? HPRI_OK : HPRI_ERR_CUDA;
+      const cudaError_t le = n_total == 64 ? launch_ex(kern64, grid, smem, stream, false, mx, mdy, g)
+                                           : launch_ex(kern128, grid, smem, stream, false, mx, mdy, g);
+      return le == cudaSuccess ? HPRI_OK : HPRI_ERR_CUDA;
     }
   }
   int bn;

@@ -236,6 +236,14 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may be scheduled while its predecessor in
+// the stream is still draining: it runs its prologue (barrier init, TMEM allocation, descriptor prefetch), then
+// grid_dep_wait() blocks until the predecessor grid has completed and its writes are visible.  grid_dep_launch() is the
+// predecessor's side: once every CTA has issued it (or exited) the dependent grid may start being scheduled.
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- CTA pairs (cta_group::2)
 // Two CTAs of a cluster (one TPC) run one M = 256 MMA: each CTA supplies its own 128 A rows and HALF of the B rows
 // from its own shared memory (same offsets in both), the accumulator rows land in each CTA's own TMEM

@@ -113,6 +113,15 @@ class _EngineBase:
         if torch.device(device).type == "cuda" and os.environ.get("HPRI_WGRAD_STREAM", "1") != "0":
             self._side = torch.cuda.Stream(device=device, priority=0)
 
+    def set_overlap(self, enabled: bool):
+        """Turn the side stream off / back on (per-kernel timing needs serialised launches: an event pair around a
+        kernel that shares the SMs with another stream's kernel also counts the time it spent waiting for them)."""
+        if not enabled:
+            if self._side is not None:
+                self._side_saved, self._side = self._side, None
+        elif getattr(self, "_side_saved", None) is not None:
+            self._side, self._side_saved = self._side_saved, None
+
     def _event(self):
         if self._side_used == len(self._side_events):
             self._side_events.append(torch.cuda.Event())
