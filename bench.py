@@ -340,55 +340,38 @@ def main():
 
     # ---------------- end to end through the public API with host inputs
     def run_e2e(host_dtype):
-        """nn.Module API, pinned host cube + mask copied H2D every step (double-buffered copy stream), loss read back."""
+        """nn.Module API, pinned host cube + mask copied H2D every step (hyperpri_b200.prefetch.DevicePrefetcher: copy
+        stream, two device slots), loss read back."""
         crit = torch.nn.BCEWithLogitsLoss()
         xh = [torch.rand(x.shape).to(host_dtype).pin_memory() for _ in range(2)]
         mh = [(torch.rand(mask.shape) > 0.95).float().pin_memory() for _ in range(2)]
-        xd = [torch.empty(x.shape, dtype=host_dtype, device=dev) for _ in range(2)]
-        md = [torch.empty_like(mask) for _ in range(2)]
-        copy_stream = torch.cuda.Stream()
-        ready = [torch.cuda.Event() for _ in range(2)]
-        consumed = [torch.cuda.Event() for _ in range(2)]
+        from hyperpri_b200.prefetch import DevicePrefetcher
+        total = W_ + args.steps
 
-        def prefetch(i):
-            b = i % 2
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(consumed[b])
-                xd[b].copy_(xh[b], non_blocking=True)
-                md[b].copy_(mh[b], non_blocking=True)
-                ready[b].record(copy_stream)
+        def loader():                                   # what a DataLoader with pinned batches hands over
+            for i in range(total):
+                yield {"image": xh[i % 2], "mask": mh[i % 2]}
 
-        def e2e_step(i):
-            b = i % 2
-            prefetch(i + 1)                         # next step's H2D overlaps this step's compute
-            torch.cuda.current_stream().wait_event(ready[b])
+        t0 = None
+        for i, b in enumerate(DevicePrefetcher(loader(), dev)):   # next step's H2D overlaps this step's compute
+            if i == W_:
+                sync()
+                t0 = time.perf_counter()
             if train:
                 net.zero_grad(set_to_none=True)
-                logits = net(xd[b])
-                loss = crit(logits, md[b])
+                logits = net(b["image"])
+                loss = crit(logits, b["mask"])
                 loss.backward()
                 red.finish()
             else:
                 with torch.no_grad():
-                    loss = crit(net(xd[b]), md[b])
-            consumed[b].record()
-            return loss.item()                      # D2H read of the step's result
-
-        total = W_ + args.steps
-        for b in range(2):
-            consumed[b].record()
-        prefetch(0)
-        for i in range(W_):
-            e2e_step(i)
-        sync()
-        t0 = time.perf_counter()
-        for i in range(W_, total):
-            e2e_step(i)
+                    loss = crit(net(b["image"]), b["mask"])
+            loss.item()                                 # D2H read of the step's result
         sync()
         dt = torch.tensor([time.perf_counter() - t0], device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        del xh, mh, xd, md
+        del xh, mh
         return {"value": n * world * args.steps / dt.item(), "unit": "images/s",
                 "h2d_bytes_per_step": x.numel() * xh_bytes[host_dtype] + mask.numel() * 4, "d2h_bytes_per_step": 4,
                 "ms_per_step": dt.item() / args.steps * 1e3}

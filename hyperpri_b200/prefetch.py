@@ -1,0 +1,95 @@
+"""Host -> device staging of data-loader batches, one batch ahead of compute.
+
+The reference moves each batch with a blocking `.to(device)` inside the step (Lightning's default transfer,
+`src/PLTrainer.py:79-86`, loader with `num_workers=0` at `:342`): at 238 x 608 x 968 that is a 1.1 GB pageable copy on
+the critical path of every step.  Here the tensors of a batch are staged in pinned host buffers (two slots) and copied
+on a dedicated copy stream while the previous batch is still being computed on; the consumer stream only waits for the
+slot's "ready" event, and a slot is not overwritten before the consumer has passed its "consumed" mark.  Together with
+`HyperpriDataset(host_dtype=torch.float16)` (bands sliced and converted before the copy) the H2D bytes per image drop
+from 560 MB to 280 MB.
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, Iterator, Tuple
+
+import torch
+
+
+class DevicePrefetcher:
+    def __init__(self, loader: Iterable, device, keys: Tuple[str, ...] = ("image", "mask"), slots: int = 2):
+        self.loader, self.device, self.keys, self.slots = loader, torch.device(device), keys, max(2, int(slots))
+        self.cuda = self.device.type == "cuda"
+        self.h2d_bytes = 0
+        if self.cuda:
+            self.copy_stream = torch.cuda.Stream(device=self.device)
+            self._pinned = [dict() for _ in range(self.slots)]
+            self._dev = [dict() for _ in range(self.slots)]
+            self._ready = [torch.cuda.Event() for _ in range(self.slots)]
+            self._used = [False] * self.slots
+            self._consumed = [None] * self.slots
+
+    def __len__(self):
+        return len(self.loader)
+
+    def _buf(self, store: Dict, key, like: torch.Tensor, **kw):
+        b = store.get(key)
+        if b is None or b.shape != like.shape or b.dtype != like.dtype:
+            b = torch.empty(like.shape, dtype=like.dtype, **kw)
+            store[key] = b
+        return b
+
+    def _stage(self, batch: Dict, slot: int) -> Dict:
+        out = dict(batch)
+        if self._used[slot]:
+            # the host writes the slot's pinned buffers below: the copy that last read them must have finished (this is
+            # also the back-pressure that keeps the loader at most `slots` batches ahead of the device)
+            self._ready[slot].synchronize()
+        self._used[slot] = True
+        with torch.cuda.stream(self.copy_stream):
+            if self._consumed[slot] is not None:
+                self.copy_stream.wait_event(self._consumed[slot])      # the consumer is done with this slot's buffers
+            for k in self.keys:
+                v = batch.get(k)
+                if not torch.is_tensor(v):
+                    continue
+                if v.is_cuda:
+                    out[k] = v
+                    continue
+                src = v.contiguous()
+                if not src.is_pinned():
+                    pin = self._buf(self._pinned[slot], k, src, pin_memory=True)
+                    pin.copy_(src)                                     # pageable -> pinned (host memcpy)
+                    src = pin
+                dst = self._buf(self._dev[slot], k, src, device=self.device)
+                dst.copy_(src, non_blocking=True)
+                self.h2d_bytes += src.numel() * src.element_size()
+                out[k] = dst
+            self._ready[slot].record(self.copy_stream)
+        return out
+
+    def __iter__(self) -> Iterator[Dict]:
+        if not self.cuda:
+            yield from self.loader
+            return
+        it = iter(self.loader)
+        slot = 0
+        try:
+            nxt = self._stage(next(it), slot)
+        except StopIteration:
+            return
+        while nxt is not None:
+            cur, cur_slot = nxt, slot
+            slot = (slot + 1) % self.slots
+            try:
+                nxt = self._stage(next(it), slot)      # the next batch's copies run under this batch's compute
+            except StopIteration:
+                nxt = None
+            consumer = torch.cuda.current_stream(self.device)
+            consumer.wait_event(self._ready[cur_slot])
+            for k in self.keys:
+                if torch.is_tensor(cur.get(k)) and cur[k].is_cuda:
+                    cur[k].record_stream(consumer)         # allocated on the copy stream, used on the consumer's
+            yield cur
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))          # everything the consumer launched on this batch
+            self._consumed[cur_slot] = ev

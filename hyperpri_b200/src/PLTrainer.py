@@ -19,6 +19,7 @@ from torch.utils.data import DataLoader
 
 from .. import metrics as M
 from .. import parallel
+from ..prefetch import DevicePrefetcher
 from .Experiments.models import *        # noqa: F401,F403  (the reference re-exports the models here, :26)
 
 try:                                     # optional: real Lightning
@@ -104,8 +105,14 @@ class RootLightningModel(_Base):
 
 
 def _to_device(batch, dev):
-    return {k: (v.to(dev, non_blocking=True).float() if torch.is_tensor(v) and k in ('image', 'mask') else v)
-            for k, v in batch.items()}
+    """Batches come out of a DevicePrefetcher already on the device (copied one batch ahead on a copy stream); an fp16
+    cube (HyperpriDataset(host_dtype=float16)) stays fp16 -- the ingest kernel reads it as is."""
+    def conv(k, v):
+        if not torch.is_tensor(v) or k not in ('image', 'mask'):
+            return v
+        v = v.to(dev, non_blocking=True)
+        return v if (k == 'image' and v.dtype == torch.float16) else v.float()
+    return {k: conv(k, v) for k, v in batch.items()}
 
 
 class _Loop:
@@ -128,7 +135,7 @@ class _Loop:
         best = float("inf")
         for epoch in range(self.max_epochs):
             model.train(); model.logged.clear()
-            for i, batch in enumerate(train_loader):
+            for i, batch in enumerate(DevicePrefetcher(train_loader, self.device)):
                 opt.zero_grad(set_to_none=True)
                 loss = model.training_step(_to_device(batch, self.device), i)
                 if red is not None:
@@ -141,7 +148,7 @@ class _Loop:
             if val_loader is not None:
                 model.eval(); model.logged.clear()
                 with torch.no_grad():
-                    for i, batch in enumerate(val_loader):
+                    for i, batch in enumerate(DevicePrefetcher(val_loader, self.device)):
                         model.validation_step(_to_device(batch, self.device), i)
                 row.update({k: float(torch.stack([torch.as_tensor(v).float().cpu() for v in vs]).mean()) for k, vs in model.logged.items()})
             row["epoch"] = epoch
@@ -158,7 +165,7 @@ class _Loop:
         model.to(self.device).eval()
         out = []
         with torch.no_grad():
-            for i, batch in enumerate(loader):
+            for i, batch in enumerate(DevicePrefetcher(loader, self.device)):
                 out.append(model.predict_step(_to_device(batch, self.device), i))
         return out if return_predictions else None
 
@@ -213,7 +220,7 @@ def _sweep_device(model, loader, trainer):
     model.to(trainer.device).eval()
     curve = M.DevicePRCurve(trainer.device, 500)
     with torch.no_grad():
-        for batch in loader:
+        for batch in DevicePrefetcher(loader, trainer.device):
             b = _to_device(batch, trainer.device)
             curve.update(model._pred(b), b['mask'])
     return curve

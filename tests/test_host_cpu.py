@@ -169,3 +169,12 @@ def test_metrics_against_bruteforce():
     assert abs(M.dice(*c).item() - 2 * tp / (2 * tp + fp + fn)) < 1e-6
     assert abs(M.jaccard(*c).item() - tp / (tp + fp + fn)) < 1e-6
     assert O.seg_counts(torch.logit(probs), tgt.float()) == (tp, fp, fn, tn)
+
+
+def test_device_prefetcher_is_a_passthrough_on_cpu():
+    import torch
+    from hyperpri_b200.prefetch import DevicePrefetcher
+    batches = [{"image": torch.full((1, 3, 4, 4), float(i)), "mask": torch.zeros(1, 1, 4, 4), "index": i} for i in range(3)]
+    out = list(DevicePrefetcher(batches, "cpu"))
+    assert len(out) == 3 and all(o is b for o, b in zip(out, batches))
+    assert len(DevicePrefetcher(batches, "cpu")) == 3

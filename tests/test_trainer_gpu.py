@@ -63,3 +63,27 @@ def test_train_validate_test_roundtrip(tmp_path):
     out = T.test_net(p.get_test_data(), p, best, pl_trainer=trainer)
     assert set(out) == {"acc", "dice", "pos_iou", "avg_prec"} and all(0.0 <= v <= 1.0 for v in out.values())
     assert out["dice"] > 0.5                                 # six epochs on a trivially separable signal
+
+
+@pytest.mark.gpu
+def test_device_prefetcher_order_contents_and_slot_reuse():
+    """Batches arrive on the device in order, bit-identical, one copy ahead; the two slots are recycled without the
+    consumer ever seeing a later batch's bytes (each batch is reduced on the device well after the next copy was queued)."""
+    import torch
+    from hyperpri_b200.prefetch import DevicePrefetcher
+    g = torch.Generator().manual_seed(3)
+    batches = [{"image": torch.rand((2, 8, 64, 96), generator=g).half() if i % 2 else torch.rand((2, 8, 64, 96), generator=g),
+                "mask": (torch.rand((2, 1, 64, 96), generator=g) > 0.5).float(), "index": torch.tensor([i]), "label": str(i)}
+               for i in range(7)]
+    pf = DevicePrefetcher(batches, "cuda")
+    sums, seen = [], []
+    for b in pf:
+        assert b["image"].is_cuda and b["mask"].is_cuda and not b["index"].is_cuda and isinstance(b["label"], str)
+        torch.cuda._sleep(2_000_000)                       # keep the consumer busy while the next copy lands
+        sums.append((b["image"].clone(), b["mask"].clone()))   # stream-ordered after the sleep
+        seen.append(int(b["index"]))
+    torch.cuda.synchronize()
+    assert seen == list(range(7))
+    for (im, mk), b in zip(sums, batches):
+        assert im.dtype == b["image"].dtype and torch.equal(im.cpu(), b["image"]) and torch.equal(mk.cpu(), b["mask"])
+    assert pf.h2d_bytes == sum(b["image"].numel() * b["image"].element_size() + b["mask"].numel() * 4 for b in batches)
