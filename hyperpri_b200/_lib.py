@@ -74,6 +74,7 @@ SIGNATURES = {
     "hpri_hsi_ingest_f16": [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _i, _i, _p],
     "hpri_absmax": [_p, _ll, _p, _p],
     "hpri_convert16": [_VP, _VP, _p],
+    "hpri_mul16": [_VP, _VP, _VP, _p],
     "hpri_bn_finalize": [_p, _ll, _p, _p, _p, _p, _p, _p, _f, _f, _i, _p, _p, _p, _p, _i, _p],
     "hpri_bn_relu_apply": [_VP, _p, _p, _VP, _VP, _p],
     "hpri_bn_relu_bwd_reduce": [_VP, _p, _p, _p, _p, _VP, _VP, _p, _p, _p, _p],

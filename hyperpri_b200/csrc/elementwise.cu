@@ -394,6 +394,27 @@ __global__ void __launch_bounds__(256) convert16_k(V x, V y) {
   }
 }
 
+// ------------------------------------------------------------------ elementwise product of two views
+// y = a * b, 8 channels (16 bytes) per thread, product in fp32, rounded once (Up with use_attention=True,
+// model_parts.py:84-85: x = x2 * x1, and the two products of its backward).
+__global__ void __launch_bounds__(256) mul16_k(V a, V b, V y) {
+  const int CG = (a.c + 7) >> 3;
+  const long long total = (long long)a.n * a.h * a.w * CG;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    long long j = i / CG;
+    const int xx = (int)(j % a.w); j /= a.w;
+    const int yy = (int)(j % a.h);
+    const int n = (int)(j / a.h);
+    float fa[8], fb[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(at(a, n, yy, xx, cg * 8))), fa, a.dt);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(at(b, n, yy, xx, cg * 8))), fb, b.dt);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) fa[k] *= fb[k];
+    *reinterpret_cast<uint4*>(at(y, n, yy, xx, cg * 8)) = pack8(fa, y.dt);
+  }
+}
+
 // ------------------------------------------------------------------ BatchNorm finalize
 __global__ void bn_finalize_k(double* stats, long long count, const float* gamma, const float* beta,
                               const float* conv_bias, float* rmean, float* rvar, long long* nbt, float momentum,
@@ -1136,7 +1157,7 @@ static inline int grid_for(long long work_items, int per_block, int cap = 148 * 
 
 using namespace hpri;
 
-extern "C" int hpri_abi_version(void) { return 3; }
+extern "C" int hpri_abi_version(void) { return 4; }
 extern "C" long long hpri_launch_count(void) { return g_launch_count; }
 
 extern "C" int hpri_pack_weights(const float* src, void* dst, int dst_dtype, int G, int R, int T, int C, int kc64,
@@ -1274,6 +1295,16 @@ extern "C" int hpri_convert16(const hpri_view_t* x, const hpri_view_t* y, void* 
   if (x->n != y->n || x->h != y->h || x->w != y->w || x->c != y->c) return HPRI_ERR_ARG;
   const long long total = (long long)x->n * x->h * x->w * ((x->c + 7) / 8);
   convert16_k<<<grid_for(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(mk(x), mk(y));
+  return last_err();
+}
+
+extern "C" int hpri_mul16(const hpri_view_t* a, const hpri_view_t* b, const hpri_view_t* y, void* stream) {
+  int rc;
+  if ((rc = check_view_e(a)) != HPRI_OK || (rc = check_view_e(b)) != HPRI_OK || (rc = check_view_e(y)) != HPRI_OK) return rc;
+  if (a->n != b->n || a->h != b->h || a->w != b->w || a->c != b->c) return HPRI_ERR_ARG;
+  if (a->n != y->n || a->h != y->h || a->w != y->w || a->c != y->c) return HPRI_ERR_ARG;
+  const long long total = (long long)a->n * a->h * a->w * ((a->c + 7) / 8);
+  mul16_k<<<grid_for(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(mk(a), mk(b), mk(y));
   return last_err();
 }
 

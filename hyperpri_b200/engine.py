@@ -209,10 +209,13 @@ class _EngineBase:
 class UNetEngine(_EngineBase):
     CH = [64, 128, 256, 512, 1024]
 
-    def __init__(self, params: Dict[str, torch.Tensor], first: str, in_ch: int, device):
+    def __init__(self, params: Dict[str, torch.Tensor], first: str, in_ch: int, device, attention: bool = False):
         """params: name -> Parameter/buffer of the owning module (reference state-dict names).
         first: 'unet' (DoubleConv(in_ch, 64)) or 'cube' (Conv3d over in_ch bands, then inc2)."""
         self.P, self.first, self.in_ch, self.dev = params, first, in_ch, device
+        # use_attention=True (model_parts.py:84-85): the decoder block convolves skip * up (C channels) instead of
+        # cat([skip, up]) (2C); the product and its two backward products are hpri_mul16 launches
+        self.att = bool(attention)
         d = device
         C = self.CH
         if first == "unet":
@@ -235,7 +238,8 @@ class UNetEngine(_EngineBase):
         for i in range(1, 5):
             lvl = 4 - i
             p = f"up{i}.conv.double_conv"
-            self.dec[lvl] = [_CBR(p + ".0", p + ".1", 2 * C[lvl], C[lvl], d), _CBR(p + ".3", p + ".4", C[lvl], C[lvl], d)]
+            self.dec[lvl] = [_CBR(p + ".0", p + ".1", (1 if self.att else 2) * C[lvl], C[lvl], d),
+                             _CBR(p + ".3", p + ".4", C[lvl], C[lvl], d)]
             self.up[lvl] = _PackedParam(WeightSpec("convT2x2", C[lvl], C[lvl + 1]), True)
             self.up_gw[lvl] = self.up[lvl].spec.grad_buffer(d)
         # BN-backward sums of every layer in one buffer: the ones accumulated by dgrad epilogues are cleared by ONE fill
@@ -328,6 +332,9 @@ class UNetEngine(_EngineBase):
             if l < 4:
                 ws[f"cat{l}"] = _z((n, H[l], W[l], 2 * C[l]), d)          # [skip | upsampled], pad stays zero
                 ws[f"gcat{l}"] = _z((n, H[l], W[l], 2 * C[l]), d, GRAD)
+                if self.att:       # cat / gcat hold [skip | up] and [d skip | d up]; the conv works on the products
+                    ws[f"mul{l}"] = _e((n, H[l], W[l], C[l]), d)
+                    ws[f"gmul{l}"] = _e((n, H[l], W[l], C[l]), d, GRAD)
                 ws[f"pool{l + 1}"] = _e((n, H[l + 1], W[l + 1], C[l]), d)
                 ws[f"gpool{l + 1}"] = _e((n, H[l + 1], W[l + 1], C[l]), d, GRAD)
                 ws[f"dec_raw_a{l}"] = _e((n, H[l], W[l], C[l]), d)
@@ -489,7 +496,9 @@ class UNetEngine(_EngineBase):
             up.refresh(P[f"up{i}.up.weight"])
             ops.convT_fwd(cur, up.fwd, C[l], ws[f"cat{l}"][..., C[l]:], bias=P[f"up{i}.up.bias"])
             a, b = self.dec[l]
-            self._cbr_fwd(a, ws[f"cat{l}"], ws[f"dec_raw_a{l}"], ws[f"dec_act_a{l}"], training)
+            if self.att:
+                ops.mul16(ws[f"cat{l}"][..., :C[l]], ws[f"cat{l}"][..., C[l]:], ws[f"mul{l}"])
+            self._cbr_fwd(a, ws[f"mul{l}"] if self.att else ws[f"cat{l}"], ws[f"dec_raw_a{l}"], ws[f"dec_act_a{l}"], training)
             if l > 0:
                 self._cbr_fwd(b, ws[f"dec_act_a{l}"], ws[f"dec_raw_b{l}"], ws[f"dec_act_b{l}"], training)
                 cur = ws[f"dec_act_b{l}"]
@@ -527,8 +536,15 @@ class UNetEngine(_EngineBase):
             else:
                 self._cbr_bwd(b, ws[f"dec_act_a{l}"], ws[f"dec_raw_b{l}"], ws[f"R{l}"], cnt[l], dy=g_in,
                               dx_out=ws[f"A{l}"], below=below)
-            self._cbr_bwd(a, ws[f"cat{l}"], ws[f"dec_raw_a{l}"], ws[f"Ra{l}"], cnt[l], dy=ws[f"A{l}"],
-                          dx_out=ws[f"gcat{l}"], reduced=fuse)
+            if self.att:
+                self._cbr_bwd(a, ws[f"mul{l}"], ws[f"dec_raw_a{l}"], ws[f"Ra{l}"], cnt[l], dy=ws[f"A{l}"],
+                              dx_out=ws[f"gmul{l}"], reduced=fuse)
+                # d skip = g * up, d up = g * skip, written where the concat path keeps them
+                ops.mul16(ws[f"gmul{l}"], ws[f"cat{l}"][..., C[l]:], ws[f"gcat{l}"][..., :C[l]])
+                ops.mul16(ws[f"gmul{l}"], ws[f"cat{l}"][..., :C[l]], ws[f"gcat{l}"][..., C[l]:])
+            else:
+                self._cbr_bwd(a, ws[f"cat{l}"], ws[f"dec_raw_a{l}"], ws[f"Ra{l}"], cnt[l], dy=ws[f"A{l}"],
+                              dx_out=ws[f"gcat{l}"], reduced=fuse)
             # ConvTranspose2d backward: its output is the second half of cat[l] over the 2h x 2w region
             i = 4 - l
             up = self.up[l]

@@ -305,6 +305,14 @@ def convert16(x, y, c=None):
     return y
 
 
+@_timed
+def mul16(a, b, y):
+    """y = a * b over NHWC 16-bit views (Up with use_attention=True, model_parts.py:84-85)."""
+    av, bv, yv = view(a), view(b), view(y)
+    check(_lib.lib().hpri_mul16(_vp(av), _vp(bv), _vp(yv), _stream()), "hpri_mul16")
+    return y
+
+
 def absmax(src):
     out = torch.empty(1, dtype=torch.float32, device=src.device)
     check(_lib.lib().hpri_absmax(_ptr(src), src.numel(), _ptr(out), _stream()), "hpri_absmax")

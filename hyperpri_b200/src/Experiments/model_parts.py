@@ -41,19 +41,17 @@ class Down(nn.Module):
 
 
 class Up(nn.Module):
-    """ConvTranspose2d(k2,s2) -> pad to the skip -> cat([skip, up]) -> DoubleConv
-    (model_parts.py:48-90); keys up.{weight,bias}, conv.double_conv.*."""
+    """ConvTranspose2d(k2,s2) -> pad to the skip -> cat([skip, up]) (use_attention: skip * up, a DoubleConv over
+    in_channels // 2) -> DoubleConv (model_parts.py:48-90); keys up.{weight,bias}, conv.double_conv.*."""
 
     def __init__(self, in_channels, out_channels, bilinear=True, use_attention=False):
         super().__init__()
         if bilinear:
             raise NotImplementedError("bilinear=True (nn.Upsample path, model_parts.py:56-61) is not built: "
                                       "every reference config uses bilinear=False")
-        if use_attention:
-            raise NotImplementedError("use_attention=True (skip*up, model_parts.py:84-85) is not built")
         self.use_attention = use_attention
         self.up = nn.ConvTranspose2d(in_channels, in_channels // 2, kernel_size=2, stride=2)
-        self.conv = DoubleConv(in_channels, out_channels)
+        self.conv = DoubleConv(in_channels // 2 if use_attention else in_channels, out_channels)   # model_parts.py:65-68
 
     def forward(self, x1, x2):
         raise NotImplementedError(_STANDALONE.format("Up"))

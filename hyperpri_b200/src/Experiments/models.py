@@ -108,7 +108,7 @@ class UNet(_EngineNet):
         self.outc = OutConv(w[0], n_classes)
 
     def _make_engine(self, device):
-        return _engine.UNetEngine(self._tensor_table(), "unet", self.n_channels, device)
+        return _engine.UNetEngine(self._tensor_table(), "unet", self.n_channels, device, attention=self.use_attention)
 
     def forward(self, x):
         return self._finish(self._run(x))
@@ -142,7 +142,7 @@ class CubeNET(_EngineNet):
         self.outc = OutConv(64, n_classes)
 
     def _make_engine(self, device):
-        return _engine.UNetEngine(self._tensor_table(), "cube", self.depth, device)
+        return _engine.UNetEngine(self._tensor_table(), "cube", self.depth, device, attention=self.use_attention)
 
     def forward(self, x):
         """x: N x 1 x D x R x C (a depth mismatch is not raised by the reference either, models.py:211)."""

@@ -182,6 +182,10 @@ int hpri_absmax(const float* src, long long numel, float* out_max, void* stream)
  * MMA in the same format: wgrad pairs a bf16 copy of the fp16 activations with the bf16 gradients). */
 int hpri_convert16(const hpri_view_t* x, const hpri_view_t* y, void* stream);
 
+/* y = a * b elementwise over equal-shaped views (fp32 product, rounded once).  Replaces `x = x2 * x1` of Up with
+ * use_attention=True (reference src/Experiments/model_parts.py:84-85) and the two products of its backward. */
+int hpri_mul16(const hpri_view_t* a, const hpri_view_t* b, const hpri_view_t* y, void* stream);
+
 /* ---- BatchNorm / ReLU / MaxPool family ---------------------------------------------------- */
 /* Turn accumulated (sum, sumsq) into scale/shift, saved mean/invstd, and the running-stat update
  * (biased var to normalise, unbiased for running_var, momentum 0.1, conv bias re-added to the mean);

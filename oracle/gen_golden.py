@@ -29,17 +29,21 @@ CASES = {
     "cubenet_1x238x48x72": dict(model="CubeNET", n=1, h=48, w=72, bands=238, seed=2),
     "spectral32_2x238x6x10": dict(model="SpectralUNET", n=2, h=6, w=10, bands=238, seed=3, feats=32),
     "spectral1650_2x238x4x5": dict(model="SpectralUNET", n=2, h=4, w=5, bands=238, seed=4, feats=1650),
+    # use_attention=True (model_parts.py:84-85): skip * up instead of cat([skip, up])
+    "unet_att_2x3x32x40": dict(model="UNET", n=2, h=32, w=40, bands=3, seed=5, attention=True),
+    "cubenet_att_2x238x34x42": dict(model="CubeNET", n=2, h=34, w=42, bands=238, seed=6, attention=True),
 }
 
 
 def build(case):
     m = case["model"]
+    att = case.get("attention", False)
     if m == "UNET":
-        net = UNet(case["bands"], 1, bilinear=False)
-        schema = O.unet_schema(case["bands"], 1, "unet")
+        net = UNet(case["bands"], 1, bilinear=False, use_attention=att)
+        schema = O.unet_schema(case["bands"], 1, "unet", attention=att)
     elif m == "CubeNET":
-        net = CubeNET(case["bands"], 1, first_depth=64, bilinear=False)
-        schema = O.unet_schema(1, 1, "cube", hsi_depth=case["bands"])
+        net = CubeNET(case["bands"], 1, first_depth=64, bilinear=False, use_attention=att)
+        schema = O.unet_schema(1, 1, "cube", hsi_depth=case["bands"], attention=att)
     else:
         net = SpectralUNET(case["bands"], 1, bn_feats=case["feats"])
         schema = O.spectral_schema(case["bands"], 1, case["feats"])
@@ -67,7 +71,8 @@ def run(name, case):
         logits = net(x)
         loss = torch.nn.BCEWithLogitsLoss()(logits, mask)
         loss.backward()
-        ologits, oloss, ograds, ostats = O.forward_backward(case["model"], x, mask, sd, training=(mode == "train"))
+        ologits, oloss, ograds, ostats = O.forward_backward(case["model"], x, mask, sd, training=(mode == "train"),
+                                                            attention=case.get("attention", False))
         scale = logits.abs().max().item()
         err = (ologits - logits).abs().max().item() / scale
         assert err < 2e-4, (name, mode, err)
@@ -113,6 +118,9 @@ def ingest_case():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    only = sys.argv[1:]                      # optional: regenerate just the named cases
     for nm, cs in CASES.items():
-        run(nm, cs)
-    ingest_case()
+        if not only or nm in only:
+            run(nm, cs)
+    if not only:
+        ingest_case()

@@ -79,8 +79,9 @@ def _dc_schema(pre: str, cin: int, cout: int, mid: int | None = None):
     return s
 
 
-def unet_schema(n_channels: int, n_classes: int = 1, first: str = "unet", hsi_depth: int = 0):
-    """State-dict schema of UNet / CubeNET-64, bilinear=False."""
+def unet_schema(n_channels: int, n_classes: int = 1, first: str = "unet", hsi_depth: int = 0, attention: bool = False):
+    """State-dict schema of UNet / CubeNET-64, bilinear=False.  attention=True:
+    Up's DoubleConv takes the product skip*up, i.e. Cin/2 input channels (model_parts.py:65-66)."""
     s: Dict[str, Tuple[int, ...]] = {}
     if first == "unet":
         s.update(_dc_schema("inc.double_conv", n_channels, 64))
@@ -101,7 +102,7 @@ def unet_schema(n_channels: int, n_classes: int = 1, first: str = "unet", hsi_de
         cin = chans[5 - i]
         s[f"up{i}.up.weight"] = (cin, cin // 2, 2, 2)
         s[f"up{i}.up.bias"] = (cin // 2,)
-        s.update(_dc_schema(f"up{i}.conv.double_conv", cin, cin // 2))
+        s.update(_dc_schema(f"up{i}.conv.double_conv", cin // 2 if attention else cin, cin // 2))
     s["outc.conv.weight"] = (n_classes, 64, 1, 1)
     s["outc.conv.bias"] = (n_classes,)
     return s
@@ -252,43 +253,45 @@ def down(x, sd, pre, training, stats_out=None, quant_out=True):
                        quant_out)
 
 
-def up(x1, x2, sd, pre, training, stats_out=None, quant_out=True):
+def up(x1, x2, sd, pre, training, stats_out=None, quant_out=True, attention=False):
     """ConvTranspose2d(k2,s2) -> zero pad to the skip's size (left/top floor(d/2), rest
-    right/bottom) -> cat([skip, up]) -> DoubleConv  (model_parts.py:71-90)."""
+    right/bottom) -> cat([skip, up]) (use_attention: skip * up, model_parts.py:84-85) -> DoubleConv
+    (model_parts.py:71-90)."""
     x1 = q(F.conv_transpose2d(x1, q(sd[pre + ".up.weight"]), sd[pre + ".up.bias"], stride=2))
     dy, dx = x2.shape[2] - x1.shape[2], x2.shape[3] - x1.shape[3]
     x1 = F.pad(x1, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])
-    return double_conv(torch.cat([q(x2), x1], dim=1), sd, pre + ".conv.double_conv", training, stats_out, quant_out)
+    x = q(q(x2) * x1) if attention else torch.cat([q(x2), x1], dim=1)
+    return double_conv(x, sd, pre + ".conv.double_conv", training, stats_out, quant_out)
 
 
-def _unet_body(x1, sd, training, stats_out):
+def _unet_body(x1, sd, training, stats_out, attention=False):
     """x1 and the other encoder outputs are kept fp32 here: their stored copies are the pooled
     tensor (down) and the skip half of the concat buffer (up)."""
     x2 = down(x1, sd, "down1", training, stats_out, quant_out=False)
     x3 = down(x2, sd, "down2", training, stats_out, quant_out=False)
     x4 = down(x3, sd, "down3", training, stats_out, quant_out=False)
     x5 = down(x4, sd, "down4", training, stats_out)
-    x = up(x5, x4, sd, "up1", training, stats_out)
-    x = up(x, x3, sd, "up2", training, stats_out)
-    x = up(x, x2, sd, "up3", training, stats_out)
-    x = up(x, x1, sd, "up4", training, stats_out, quant_out=False)
+    x = up(x5, x4, sd, "up1", training, stats_out, attention=attention)
+    x = up(x, x3, sd, "up2", training, stats_out, attention=attention)
+    x = up(x, x2, sd, "up3", training, stats_out, attention=attention)
+    x = up(x, x1, sd, "up4", training, stats_out, quant_out=False, attention=attention)
     return F.conv2d(x, sd["outc.conv.weight"], sd["outc.conv.bias"])      # model_parts.py:93-99
 
 
-def unet_forward(x, sd, training=True, stats_out=None):
-    """UNet.forward (models.py:53-68), bilinear=False, use_attention=False."""
+def unet_forward(x, sd, training=True, stats_out=None, attention=False):
+    """UNet.forward (models.py:53-68), bilinear=False."""
     return _unet_body(double_conv(q(x), sd, "inc.double_conv", training, stats_out, quant_out=False), sd, training,
-                      stats_out)
+                      stats_out, attention)
 
 
-def cubenet_forward(x, sd, training=True, stats_out=None):
+def cubenet_forward(x, sd, training=True, stats_out=None, attention=False):
     """CubeNET.forward (models.py:202-247), first_depth == 64.  The Conv3d with a kernel
     spanning every band and pad (0,1,1) is restated as the 2-D conv it equals
     (SURVEY.md appendix B.3): x is N x 1 x D x R x C."""
     w = sd["first_conv.weight"]
     x1 = _cbr(q(x[:, 0]), w[:, 0], sd["first_conv.bias"], sd, "inc.1", training, stats_out)
     x1 = _cbr(x1, sd["inc2.0.weight"], sd["inc2.0.bias"], sd, "inc2.1", training, stats_out, quant_out=False)
-    return _unet_body(x1, sd, training, stats_out)
+    return _unet_body(x1, sd, training, stats_out, attention)
 
 
 def spectralunet_forward(x, sd, training=True, stats_out=None):
@@ -345,7 +348,7 @@ FORWARDS = {"UNET": unet_forward, "CubeNET": cubenet_forward, "SpectralUNET": sp
 
 
 def forward_backward(model: str, x: torch.Tensor, mask: torch.Tensor, sd: Dict[str, torch.Tensor],
-                     training: bool = True):
+                     training: bool = True, attention: bool = False):
     """One training-step body (PLTrainer.py:79-98 without metrics): logits, loss, grads per
     state-dict key, updated BN buffers."""
     leaf = {}
@@ -358,7 +361,8 @@ def forward_backward(model: str, x: torch.Tensor, mask: torch.Tensor, sd: Dict[s
         leaf["inc.0.weight"] = leaf["first_conv.weight"]
         leaf["inc.0.bias"] = leaf["first_conv.bias"]
     stats: Dict[str, torch.Tensor] = {}
-    logits = FORWARDS[model](x, leaf, training, stats if training else None)
+    kw = {"attention": True} if attention else {}
+    logits = FORWARDS[model](x, leaf, training, stats if training else None, **kw)
     loss = bce_with_logits(logits, mask)
     loss.backward()
     grads = {k: v.grad for k, v in leaf.items() if isinstance(v, torch.Tensor) and v.requires_grad

@@ -463,3 +463,13 @@ def test_head_and_bce():
     torch.cuda.synchronize()
     ref_dhw = (act * dlogit).sum((0, 2, 3))
     assert relerr(dhw, ref_dhw) < 1e-3
+
+
+def test_mul16_strided_views():
+    """hpri_mul16 on channel-sliced NHWC views (the two halves of a concat buffer) against torch."""
+    torch.manual_seed(0)
+    cat = (torch.randn((2, 9, 13, 128), device="cuda") * 2).half()
+    out = torch.zeros((2, 9, 13, 128), device="cuda", dtype=torch.float16)
+    ops.mul16(cat[..., :64], cat[..., 64:], out[..., 64:])
+    want = (cat[..., :64].float() * cat[..., 64:].float()).half()
+    assert torch.equal(out[..., 64:], want) and float(out[..., :64].abs().max()) == 0.0

@@ -16,14 +16,17 @@ CASES = {
     "cubenet_1x238x48x72": dict(model="CubeNET", n=1, h=48, w=72, bands=238, seed=2),
     "spectral32_2x238x6x10": dict(model="SpectralUNET", n=2, h=6, w=10, bands=238, seed=3, feats=32),
     "spectral1650_2x238x4x5": dict(model="SpectralUNET", n=2, h=4, w=5, bands=238, seed=4, feats=1650),
+    "unet_att_2x3x32x40": dict(model="UNET", n=2, h=32, w=40, bands=3, seed=5, attention=True),
+    "cubenet_att_2x238x34x42": dict(model="CubeNET", n=2, h=34, w=42, bands=238, seed=6, attention=True),
 }
 
 
 def _inputs(c):
+    att = c.get("attention", False)
     if c["model"] == "UNET":
-        schema = O.unet_schema(c["bands"], 1, "unet")
+        schema = O.unet_schema(c["bands"], 1, "unet", attention=att)
     elif c["model"] == "CubeNET":
-        schema = O.unet_schema(1, 1, "cube", hsi_depth=c["bands"])
+        schema = O.unet_schema(1, 1, "cube", hsi_depth=c["bands"], attention=att)
     else:
         schema = O.spectral_schema(c["bands"], 1, c["feats"])
     sd = O.synth_state_dict(schema, c["seed"])
@@ -40,7 +43,8 @@ def test_oracle_matches_reference_golden(name, mode):
     g = np.load(os.path.join(GOLD, name + ".npz"))
     sd, x, mask = _inputs(c)
     torch.set_num_threads(min(8, os.cpu_count()))
-    logits, loss, grads, stats = O.forward_backward(c["model"], x, mask, sd, training=(mode == "train"))
+    logits, loss, grads, stats = O.forward_backward(c["model"], x, mask, sd, training=(mode == "train"),
+                                                    attention=c.get("attention", False))
     ref = torch.from_numpy(g[f"{mode}.logits"])
     assert (logits - ref).abs().max().item() <= 2e-4 * ref.abs().max().item()     # fp32, different op order
     assert abs(loss.item() - float(g[f"{mode}.loss"])) < 1e-5
