@@ -3,9 +3,9 @@ layout (reference src/Experiments/model_parts.py:14-99), re-hosted on the B200 k
 
 The blocks are parameter containers: the arithmetic of a whole network is scheduled by
 ``hyperpri_b200.engine`` (conv+BN-statistics GEMM epilogues, fused BN/ReLU/pool passes, concat by
-placement), so a block does not run layer-by-layer torch ops.  Unsupported reference options
-(`bilinear=True`, `use_attention=True`; unused by every reference config,
-params_HyperPRI.py:53-54,210-211) raise instead of silently falling back.
+placement), so a block does not run layer-by-layer torch ops.  `use_attention=True` (skip * up,
+model_parts.py:84-85) is built; the unsupported reference option `bilinear=True` (unused by every
+reference config, params_HyperPRI.py:53-54,210-211) raises instead of silently falling back.
 """
 import torch.nn as nn
 
