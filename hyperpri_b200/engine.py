@@ -209,10 +209,25 @@ class _EngineBase:
 class UNetEngine(_EngineBase):
     CH = [64, 128, 256, 512, 1024]
 
-    def __init__(self, params: Dict[str, torch.Tensor], first: str, in_ch: int, device, attention: bool = False):
+    def __init__(self, params: Dict[str, torch.Tensor], first: str, in_ch: int, device, attention: bool = False,
+                 first_depth: int = 64):
         """params: name -> Parameter/buffer of the owning module (reference state-dict names).
-        first: 'unet' (DoubleConv(in_ch, 64)) or 'cube' (Conv3d over in_ch bands, then inc2)."""
+        first: 'unet' (DoubleConv(in_ch, 64)) or 'cube' (Conv3d over in_ch bands, then inc2).
+        first_depth: CubeNET's number of first-layer feature maps (models.py:168-178); when it is not 64 the last
+        decoder block is `upsample4` / `upconv4` over cat([x1 (first_depth), up (64)]) (models.py:193-199, 229-240)."""
         self.P, self.first, self.in_ch, self.dev = params, first, in_ch, device
+        F = int(first_depth) if first == "cube" else 64
+        if F % 8 or F <= 0:
+            raise NotImplementedError("CubeNET first_depth must be a positive multiple of 8 (16-byte NHWC channel runs)")
+        # encoder channels per level (decoder channels are CH[l]; they differ only at level 0 when first_depth != 64)
+        self.CE = [F] + self.CH[1:]
+        self.up_name = {l: f"up{4 - l}.up" for l in range(4)}
+        self.dec_name = {l: f"up{4 - l}.conv.double_conv" for l in range(4)}
+        if F != 64:
+            self.up_name[0], self.dec_name[0] = "upsample4", "upconv4.double_conv"
+        # per decoder level: the reference's first_depth != 64 branch concatenates at the last block whatever
+        # use_attention says (models.py:229-240)
+        self.attl = [bool(attention) and not (l == 0 and F != 64) for l in range(4)]
         # use_attention=True (model_parts.py:84-85): the decoder block convolves skip * up (C channels) instead of
         # cat([skip, up]) (2C); the product and its two backward products are hpri_mul16 launches
         self.att = bool(attention)
@@ -225,20 +240,20 @@ class UNetEngine(_EngineBase):
             enc0[0].true_cin = in_ch
         else:
             self.cin_pad = (in_ch + 7) // 8 * 8
-            enc0 = [_CBR("first_conv", "inc.1", self.cin_pad, 64, d, need_dgrad=False),
-                    _CBR("inc2.0", "inc2.1", 64, 64, d)]
+            enc0 = [_CBR("first_conv", "inc.1", self.cin_pad, F, d, need_dgrad=False),
+                    _CBR("inc2.0", "inc2.1", F, F, d)]
             enc0[0].true_cin = in_ch
         self.enc: List[List[_CBR]] = [enc0]
         for i in range(1, 5):
             p = f"down{i}.maxpool_conv.1.double_conv"
-            self.enc.append([_CBR(p + ".0", p + ".1", C[i - 1], C[i], d), _CBR(p + ".3", p + ".4", C[i], C[i], d)])
+            self.enc.append([_CBR(p + ".0", p + ".1", self.CE[i - 1], C[i], d), _CBR(p + ".3", p + ".4", C[i], C[i], d)])
         self.dec: Dict[int, List[_CBR]] = {}
         self.up: Dict[int, _PackedParam] = {}
         self.up_gw: Dict[int, torch.Tensor] = {}
         for i in range(1, 5):
             lvl = 4 - i
-            p = f"up{i}.conv.double_conv"
-            self.dec[lvl] = [_CBR(p + ".0", p + ".1", (1 if self.att else 2) * C[lvl], C[lvl], d),
+            p = self.dec_name[lvl]
+            self.dec[lvl] = [_CBR(p + ".0", p + ".1", C[lvl] if self.attl[lvl] else self.CE[lvl] + C[lvl], C[lvl], d),
                              _CBR(p + ".3", p + ".4", C[lvl], C[lvl], d)]
             self.up[lvl] = _PackedParam(WeightSpec("convT2x2", C[lvl], C[lvl + 1]), True)
             self.up_gw[lvl] = self.up[lvl].spec.grad_buffer(d)
@@ -250,7 +265,7 @@ class UNetEngine(_EngineBase):
             L.sums = self._bw_sums[off:off + L.cout]
             off += L.cout
         # the first conv's real input-channel count differs from the padded view: pack from the true layout
-        self.enc[0][0].pp = _PackedParam(_first_spec(in_ch, self.cin_pad), False)
+        self.enc[0][0].pp = _PackedParam(_first_spec(in_ch, self.cin_pad, F), False)
         self.enc[0][0].gw = self.enc[0][0].pp.spec.grad_buffer(d)
         self.ws = None
         self.ws_key = None
@@ -273,7 +288,7 @@ class UNetEngine(_EngineBase):
         order += ["outc.conv.bias", "outc.conv.weight"]
         for l in (0, 1, 2, 3):
             a, b = self.dec[l]
-            order += cbr_names(b) + cbr_names(a) + [f"up{4 - l}.up.weight", f"up{4 - l}.up.bias"]
+            order += cbr_names(b) + cbr_names(a) + [self.up_name[l] + ".weight", self.up_name[l] + ".bias"]
             buckets.append(len(order))
         for l in (4, 3, 2, 1, 0):
             a, b = self.enc[l]
@@ -316,7 +331,7 @@ class UNetEngine(_EngineBase):
         key = (n, h, w)
         if self.ws_key == key:
             return self.ws
-        d, C = self.dev, self.CH
+        d, C, CE = self.dev, self.CH, self.CE
         H, W = [h], [w]
         for _ in range(4):
             H.append(H[-1] // 2)
@@ -326,17 +341,17 @@ class UNetEngine(_EngineBase):
         ws = {"H": H, "W": W, "n": n}
         ws["x"] = _e((n, h, w, self.cin_pad), d)
         for l in range(5):
-            ws[f"enc_raw_a{l}"] = _e((n, H[l], W[l], C[l]), d)
-            ws[f"enc_act_a{l}"] = _e((n, H[l], W[l], C[l]), d)
-            ws[f"enc_raw_b{l}"] = _e((n, H[l], W[l], C[l]), d)
+            ws[f"enc_raw_a{l}"] = _e((n, H[l], W[l], CE[l]), d)
+            ws[f"enc_act_a{l}"] = _e((n, H[l], W[l], CE[l]), d)
+            ws[f"enc_raw_b{l}"] = _e((n, H[l], W[l], CE[l]), d)
             if l < 4:
-                ws[f"cat{l}"] = _z((n, H[l], W[l], 2 * C[l]), d)          # [skip | upsampled], pad stays zero
-                ws[f"gcat{l}"] = _z((n, H[l], W[l], 2 * C[l]), d, GRAD)
-                if self.att:       # cat / gcat hold [skip | up] and [d skip | d up]; the conv works on the products
+                ws[f"cat{l}"] = _z((n, H[l], W[l], CE[l] + C[l]), d)      # [skip | upsampled], pad stays zero
+                ws[f"gcat{l}"] = _z((n, H[l], W[l], CE[l] + C[l]), d, GRAD)
+                if self.attl[l]:   # cat / gcat hold [skip | up] and [d skip | d up]; the conv works on the products
                     ws[f"mul{l}"] = _e((n, H[l], W[l], C[l]), d)
                     ws[f"gmul{l}"] = _e((n, H[l], W[l], C[l]), d, GRAD)
-                ws[f"pool{l + 1}"] = _e((n, H[l + 1], W[l + 1], C[l]), d)
-                ws[f"gpool{l + 1}"] = _e((n, H[l + 1], W[l + 1], C[l]), d, GRAD)
+                ws[f"pool{l + 1}"] = _e((n, H[l + 1], W[l + 1], CE[l]), d)
+                ws[f"gpool{l + 1}"] = _e((n, H[l + 1], W[l + 1], CE[l]), d, GRAD)
                 ws[f"dec_raw_a{l}"] = _e((n, H[l], W[l], C[l]), d)
                 ws[f"dec_act_a{l}"] = _e((n, H[l], W[l], C[l]), d)
                 ws[f"dec_raw_b{l}"] = _e((n, H[l], W[l], C[l]), d)
@@ -348,6 +363,9 @@ class UNetEngine(_EngineBase):
             # the first conv of a block gets its own: the second conv's weight gradient may still be reading R{l}
             ws[f"Ra{l}"] = _e((n, H[l], W[l], C[l]), d, GRAD) if self._side is not None else ws[f"R{l}"]
             ws[f"A{l}"] = _e((n, H[l], W[l], C[l]), d, GRAD)      # grad wrt an activation
+            # the encoder block of the level shares them unless its channel count differs (first_depth != 64)
+            for nm in ("R", "Ra", "A"):
+                ws[f"{nm}e{l}"] = ws[f"{nm}{l}"] if CE[l] == C[l] else _e((n, H[l], W[l], CE[l]), d, GRAD)
         if GRAD != ACT:
             ws["cvt"] = _e((n * h * w * max(self.cin_pad, 2 * C[0]),), d, GRAD)
         ws["logits"] = _e((n, 1, h, w), d, torch.float32)
@@ -411,10 +429,10 @@ class UNetEngine(_EngineBase):
         # identically zero under train-mode BN
         self._on_side(lambda: ops.igemm_wgrad(xg, R, 1, L.cout, L.gw), after=ready)
 
-    def _fusable(self, l):
+    def _fusable(self, l, enc=False):
         """The a-layer of level l gets its whole output gradient from the b-layer's dgrad launch; the reduction can
         ride in that launch when it runs on the halo kernel."""
-        return ops.conv3x3_halo_ok(self.ws["H"][l], self.ws["W"][l], self.CH[l])
+        return ops.conv3x3_halo_ok(self.ws["H"][l], self.ws["W"][l], (self.CE if enc else self.CH)[l])
 
     # ------------------------------------------------------------------ forward
     def ingest(self, x: torch.Tensor, ws):
@@ -476,7 +494,7 @@ class UNetEngine(_EngineBase):
             ops.unpack_conv3x3_batch(self._table("all", self._conv_layers()))
 
     def forward_ingested(self, ws, training: bool) -> torch.Tensor:
-        P, C = self.P, self.CH
+        P, C, CE = self.P, self.CH, self.CE
         self.training_fwd = training
         self._refresh_packed()
         cur = ws["x"]
@@ -484,7 +502,7 @@ class UNetEngine(_EngineBase):
             a, b = self.enc[l]
             self._cbr_fwd(a, cur, ws[f"enc_raw_a{l}"], ws[f"enc_act_a{l}"], training)
             if l < 4:
-                self._cbr_fwd(b, ws[f"enc_act_a{l}"], ws[f"enc_raw_b{l}"], ws[f"cat{l}"][..., :C[l]], training,
+                self._cbr_fwd(b, ws[f"enc_act_a{l}"], ws[f"enc_raw_b{l}"], ws[f"cat{l}"][..., :CE[l]], training,
                               pooled=ws[f"pool{l + 1}"])
                 cur = ws[f"pool{l + 1}"]
             else:
@@ -493,12 +511,12 @@ class UNetEngine(_EngineBase):
         for l in (3, 2, 1, 0):
             up = self.up[l]
             i = 4 - l
-            up.refresh(P[f"up{i}.up.weight"])
-            ops.convT_fwd(cur, up.fwd, C[l], ws[f"cat{l}"][..., C[l]:], bias=P[f"up{i}.up.bias"])
+            up.refresh(P[self.up_name[l] + ".weight"])
+            ops.convT_fwd(cur, up.fwd, C[l], ws[f"cat{l}"][..., CE[l]:], bias=P[self.up_name[l] + ".bias"])
             a, b = self.dec[l]
-            if self.att:
+            if self.attl[l]:
                 ops.mul16(ws[f"cat{l}"][..., :C[l]], ws[f"cat{l}"][..., C[l]:], ws[f"mul{l}"])
-            self._cbr_fwd(a, ws[f"mul{l}"] if self.att else ws[f"cat{l}"], ws[f"dec_raw_a{l}"], ws[f"dec_act_a{l}"], training)
+            self._cbr_fwd(a, ws[f"mul{l}"] if self.attl[l] else ws[f"cat{l}"], ws[f"dec_raw_a{l}"], ws[f"dec_act_a{l}"], training)
             if l > 0:
                 self._cbr_fwd(b, ws[f"dec_act_a{l}"], ws[f"dec_raw_b{l}"], ws[f"dec_act_b{l}"], training)
                 cur = ws[f"dec_act_b{l}"]
@@ -516,7 +534,7 @@ class UNetEngine(_EngineBase):
         unscaled in the arena by finalize_grads() (called here, or by the all-reduce hook owner)."""
         if not self.training_fwd:
             raise NotImplementedError("backward through eval-mode BatchNorm is not on the hot path")
-        ws, P, C = self.ws, self.P, self.CH
+        ws, P, C, CE = self.ws, self.P, self.CH, self.CE
         n, H, W = ws["n"], ws["H"], ws["W"]
         self._begin_backward()
         self._bw_sums.zero_()              # one fill for the BN-backward sums the dgrad epilogues accumulate into
@@ -536,7 +554,7 @@ class UNetEngine(_EngineBase):
             else:
                 self._cbr_bwd(b, ws[f"dec_act_a{l}"], ws[f"dec_raw_b{l}"], ws[f"R{l}"], cnt[l], dy=g_in,
                               dx_out=ws[f"A{l}"], below=below)
-            if self.att:
+            if self.attl[l]:
                 self._cbr_bwd(a, ws[f"mul{l}"], ws[f"dec_raw_a{l}"], ws[f"Ra{l}"], cnt[l], dy=ws[f"A{l}"],
                               dx_out=ws[f"gmul{l}"], reduced=fuse)
                 # d skip = g * up, d up = g * skip, written where the concat path keeps them
@@ -548,32 +566,32 @@ class UNetEngine(_EngineBase):
             # ConvTranspose2d backward: its output is the second half of cat[l] over the 2h x 2w region
             i = 4 - l
             up = self.up[l]
-            dy_up = ws[f"gcat{l}"][:, :2 * H[l + 1], :2 * W[l + 1], C[l]:]
+            dy_up = ws[f"gcat{l}"][:, :2 * H[l + 1], :2 * W[l + 1], CE[l]:]
             x_up = ws[f"dec_act_b{l + 1}"] if l < 3 else ws["act_b4"]
             ops.convT_dgrad(dy_up, up.dgr, C[l + 1], ws[f"A{l + 1}"])
             gw = self.up_gw[l]
-            wn = f"up{i}.up.weight"
+            wn = self.up_name[l] + ".weight"
 
             def up_wgrad(x_up=self._as_grad_dtype(x_up), dy_up=dy_up, gw=gw, up=up, wn=wn, l=l, i=i):
                 ops.igemm_wgrad(x_up, dy_up, 2, 4 * C[l], gw)
                 up.spec.unpack_grad(gw, self._grad(wn, P[wn]).view(-1))
-                ops.colsum(dy_up, self._grad(f"up{i}.up.bias", P[f"up{i}.up.bias"]))
+                ops.colsum(dy_up, self._grad(self.up_name[l] + ".bias", P[self.up_name[l] + ".bias"]))
             self._on_side(up_wgrad)
             g_in = ws[f"A{l + 1}"]
             self._bucket_done(l)
         # encoder, deepest first
         for l in (4, 3, 2, 1, 0):
             a, b = self.enc[l]
-            fuse = self._fusable(l)
+            fuse = self._fusable(l, enc=True)
             below = (a, ws[f"enc_raw_a{l}"]) if fuse else None
             if l == 4:
-                self._cbr_bwd(b, ws["enc_act_a4"], ws["enc_raw_b4"], ws["R4"], cnt[4], dy=g_in, dx_out=ws["A4"],
+                self._cbr_bwd(b, ws["enc_act_a4"], ws["enc_raw_b4"], ws["Re4"], cnt[4], dy=g_in, dx_out=ws["Ae4"],
                               below=below)
             else:
-                self._cbr_bwd(b, ws[f"enc_act_a{l}"], ws[f"enc_raw_b{l}"], ws[f"R{l}"], cnt[l],
-                              dy=ws[f"gcat{l}"][..., :C[l]], dpool=ws[f"gpool{l + 1}"], dx_out=ws[f"A{l}"], below=below)
+                self._cbr_bwd(b, ws[f"enc_act_a{l}"], ws[f"enc_raw_b{l}"], ws[f"Re{l}"], cnt[l],
+                              dy=ws[f"gcat{l}"][..., :CE[l]], dpool=ws[f"gpool{l + 1}"], dx_out=ws[f"Ae{l}"], below=below)
             x_in = ws[f"pool{l}"] if l > 0 else ws["x"]
-            self._cbr_bwd(a, x_in, ws[f"enc_raw_a{l}"], ws[f"Ra{l}"], cnt[l], dy=ws[f"A{l}"],
+            self._cbr_bwd(a, x_in, ws[f"enc_raw_a{l}"], ws[f"Rae{l}"], cnt[l], dy=ws[f"Ae{l}"],
                           dx_out=ws[f"gpool{l}"] if l > 0 else None, reduced=fuse)
             self._bucket_done(4 + (4 - l))
         if self.first == "cube":               # module registered twice (models.py:169-171): same tensor
@@ -591,9 +609,9 @@ class UNetEngine(_EngineBase):
         return [L.pp for grp in list(self.enc) + list(self.dec.values()) for L in grp] + list(self.up.values())
 
 
-def _first_spec(true_cin: int, cin_pad: int) -> WeightSpec:
+def _first_spec(true_cin: int, cin_pad: int, cout: int = 64) -> WeightSpec:
     """First conv: the parameter has `true_cin` input channels, the activation view `cin_pad`."""
-    s = WeightSpec("conv3x3", 64, true_cin)
+    s = WeightSpec("conv3x3", cout, true_cin)
     assert kpad(true_cin) == kpad(cin_pad)
     return s
 

@@ -115,7 +115,7 @@ class UNet(_EngineNet):
 
 
 class CubeNET(_EngineNet):
-    """models.py:148-247, first_depth=64.  The Conv3d spanning all bands is executed as the 2-D
+    """models.py:148-247 (any first_depth that is a multiple of 8).  The Conv3d spanning all bands is executed as the 2-D
     3x3 conv over `hsi_depth` channels it equals; `first_conv` stays an nn.Conv3d so the
     (64,1,D,3,3) weight and the aliased `first_conv.*` / `inc.0.*` keys are preserved."""
 
@@ -124,8 +124,6 @@ class CubeNET(_EngineNet):
         self.n_channels = 1
         self.depth, self.first_depth, self.n_classes = hsi_depth, first_depth, n_classes
         self.bilinear, self.use_attention, self.analyze = bilinear, use_attention, analyze
-        if first_depth != 64:
-            raise NotImplementedError("CubeNET first_depth != 64 (models.py:193-199) is not built")
         if n_classes != 1:
             raise NotImplementedError("the B200 head kernel is built for n_classes=1 (every reference config)")
         self.first_conv = nn.Conv3d(1, first_depth, kernel_size=(hsi_depth, 3, 3), padding=(0, 1, 1))
@@ -138,11 +136,18 @@ class CubeNET(_EngineNet):
         self.up1 = Up(8 * c, 4 * c, bilinear, use_attention=use_attention)
         self.up2 = Up(4 * c, 2 * c, bilinear, use_attention=use_attention)
         self.up3 = Up(2 * c, c, bilinear, use_attention=use_attention)
-        self.up4 = Up(c, 64, bilinear, use_attention=use_attention)
+        if first_depth == 64:
+            self.up4 = Up(c, 64, bilinear, use_attention=use_attention)
+        else:       # models.py:193-199: the skip has first_depth channels, the up path 64; always concatenated (:229-240)
+            if bilinear:
+                raise NotImplementedError("bilinear=True (nn.Upsample path) is not built")
+            self.upsample4 = nn.ConvTranspose2d(c, 64, kernel_size=2, stride=2)
+            self.upconv4 = DoubleConv(64 + first_depth, 64)
         self.outc = OutConv(64, n_classes)
 
     def _make_engine(self, device):
-        return _engine.UNetEngine(self._tensor_table(), "cube", self.depth, device, attention=self.use_attention)
+        return _engine.UNetEngine(self._tensor_table(), "cube", self.depth, device, attention=self.use_attention,
+                                  first_depth=self.first_depth)
 
     def forward(self, x):
         """x: N x 1 x D x R x C (a depth mismatch is not raised by the reference either, models.py:211)."""

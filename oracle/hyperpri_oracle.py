@@ -79,27 +79,36 @@ def _dc_schema(pre: str, cin: int, cout: int, mid: int | None = None):
     return s
 
 
-def unet_schema(n_channels: int, n_classes: int = 1, first: str = "unet", hsi_depth: int = 0, attention: bool = False):
+def unet_schema(n_channels: int, n_classes: int = 1, first: str = "unet", hsi_depth: int = 0, attention: bool = False,
+                first_depth: int = 64):
     """State-dict schema of UNet / CubeNET-64, bilinear=False.  attention=True:
-    Up's DoubleConv takes the product skip*up, i.e. Cin/2 input channels (model_parts.py:65-66)."""
+    Up's DoubleConv takes the product skip*up, i.e. Cin/2 input channels (model_parts.py:65-66).  first_depth != 64
+    (CubeNET only): first_conv / inc2 have first_depth maps and the last decoder block is upsample4 / upconv4 over
+    cat([x1, up]) whatever `attention` says (models.py:193-199, 229-240)."""
+    fd = first_depth if first != "unet" else 64
     s: Dict[str, Tuple[int, ...]] = {}
     if first == "unet":
         s.update(_dc_schema("inc.double_conv", n_channels, 64))
     else:  # CubeNET: Conv3d registered twice (models.py:169-171) -> aliased keys
         for pre in ("first_conv", "inc.0"):
-            s[f"{pre}.weight"] = (64, 1, hsi_depth, 3, 3)
-            s[f"{pre}.bias"] = (64,)
-        for blk, c in (("inc.1", 64), ("inc2.1", 64)):
+            s[f"{pre}.weight"] = (fd, 1, hsi_depth, 3, 3)
+            s[f"{pre}.bias"] = (fd,)
+        for blk, c in (("inc.1", fd), ("inc2.1", fd)):
             for nm in ("weight", "bias", "running_mean", "running_var"):
                 s[f"{blk}.{nm}"] = (c,)
             s[f"{blk}.num_batches_tracked"] = ()
-        s["inc2.0.weight"] = (64, 64, 3, 3)
-        s["inc2.0.bias"] = (64,)
-    chans = [64, 128, 256, 512, 1024]
+        s["inc2.0.weight"] = (fd, fd, 3, 3)
+        s["inc2.0.bias"] = (fd,)
+    chans = [fd, 128, 256, 512, 1024]
     for i in range(1, 5):
         s.update(_dc_schema(f"down{i}.maxpool_conv.1.double_conv", chans[i - 1], chans[i]))
     for i in range(1, 5):
         cin = chans[5 - i]
+        if i == 4 and fd != 64:
+            s["upsample4.weight"] = (cin, 64, 2, 2)
+            s["upsample4.bias"] = (64,)
+            s.update(_dc_schema("upconv4.double_conv", 64 + fd, 64))
+            continue
         s[f"up{i}.up.weight"] = (cin, cin // 2, 2, 2)
         s[f"up{i}.up.bias"] = (cin // 2,)
         s.update(_dc_schema(f"up{i}.conv.double_conv", cin // 2 if attention else cin, cin // 2))
@@ -253,15 +262,16 @@ def down(x, sd, pre, training, stats_out=None, quant_out=True):
                        quant_out)
 
 
-def up(x1, x2, sd, pre, training, stats_out=None, quant_out=True, attention=False):
+def up(x1, x2, sd, pre, training, stats_out=None, quant_out=True, attention=False, up_key=None, conv_key=None):
     """ConvTranspose2d(k2,s2) -> zero pad to the skip's size (left/top floor(d/2), rest
     right/bottom) -> cat([skip, up]) (use_attention: skip * up, model_parts.py:84-85) -> DoubleConv
     (model_parts.py:71-90)."""
-    x1 = q(F.conv_transpose2d(x1, q(sd[pre + ".up.weight"]), sd[pre + ".up.bias"], stride=2))
+    up_key, conv_key = up_key or pre + ".up", conv_key or pre + ".conv.double_conv"
+    x1 = q(F.conv_transpose2d(x1, q(sd[up_key + ".weight"]), sd[up_key + ".bias"], stride=2))
     dy, dx = x2.shape[2] - x1.shape[2], x2.shape[3] - x1.shape[3]
     x1 = F.pad(x1, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])
     x = q(q(x2) * x1) if attention else torch.cat([q(x2), x1], dim=1)
-    return double_conv(x, sd, pre + ".conv.double_conv", training, stats_out, quant_out)
+    return double_conv(x, sd, conv_key, training, stats_out, quant_out)
 
 
 def _unet_body(x1, sd, training, stats_out, attention=False):
@@ -274,7 +284,10 @@ def _unet_body(x1, sd, training, stats_out, attention=False):
     x = up(x5, x4, sd, "up1", training, stats_out, attention=attention)
     x = up(x, x3, sd, "up2", training, stats_out, attention=attention)
     x = up(x, x2, sd, "up3", training, stats_out, attention=attention)
-    x = up(x, x1, sd, "up4", training, stats_out, quant_out=False, attention=attention)
+    if "upsample4.weight" in sd:              # CubeNET first_depth != 64 (models.py:229-240): always concatenated
+        x = up(x, x1, sd, "up4", training, stats_out, quant_out=False, up_key="upsample4", conv_key="upconv4.double_conv")
+    else:
+        x = up(x, x1, sd, "up4", training, stats_out, quant_out=False, attention=attention)
     return F.conv2d(x, sd["outc.conv.weight"], sd["outc.conv.bias"])      # model_parts.py:93-99
 
 
@@ -285,7 +298,7 @@ def unet_forward(x, sd, training=True, stats_out=None, attention=False):
 
 
 def cubenet_forward(x, sd, training=True, stats_out=None, attention=False):
-    """CubeNET.forward (models.py:202-247), first_depth == 64.  The Conv3d with a kernel
+    """CubeNET.forward (models.py:202-247), any first_depth.  The Conv3d with a kernel
     spanning every band and pad (0,1,1) is restated as the 2-D conv it equals
     (SURVEY.md appendix B.3): x is N x 1 x D x R x C."""
     w = sd["first_conv.weight"]

@@ -71,7 +71,14 @@ def test_factories_and_unsupported_flags():
     with pytest.raises(NotImplementedError):
         mdl.UNet(3, 1, bilinear=True)
     with pytest.raises(NotImplementedError):
-        mdl.CubeNET(238, 1, first_depth=32, bilinear=False)
+        mdl.CubeNET(238, 1, first_depth=32, bilinear=True)
+    # first_depth != 64 and use_attention are built: same state-dict schema as the reference (models.py:193-199)
+    net = mdl.CubeNET(238, 1, first_depth=32, bilinear=False, use_attention=True)
+    sd = net.state_dict()
+    assert sd["first_conv.weight"].shape == (32, 1, 238, 3, 3) and sd["upsample4.weight"].shape == (128, 64, 2, 2)
+    assert sd["upconv4.double_conv.0.weight"].shape == (64, 96, 3, 3) and "up4.up.weight" not in sd
+    assert sd["up1.conv.double_conv.0.weight"].shape == (512, 512, 3, 3)          # attention: skip * up, Cin / 2
+    assert mdl.translate_load_dir("CubeNET", dict(p, **{"3d_featmaps": 32})) == "CubeNET_32"
 
 
 def test_cpu_forward_is_refused_not_emulated():

@@ -20,12 +20,12 @@ from hyperpri_b200.src.Experiments.models import UNet, CubeNET, SpectralUNET   #
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
-def build(model, bands, feats=1650, seed=0, att=False):
+def build(model, bands, feats=1650, seed=0, att=False, fd=64):
     if model == "UNET":
         net, schema = UNet(bands, 1, bilinear=False, use_attention=att), O.unet_schema(bands, 1, "unet", attention=att)
     elif model == "CubeNET":
-        net = CubeNET(bands, 1, first_depth=64, bilinear=False, use_attention=att)
-        schema = O.unet_schema(1, 1, "cube", hsi_depth=bands, attention=att)
+        net = CubeNET(bands, 1, first_depth=fd, bilinear=False, use_attention=att)
+        schema = O.unet_schema(1, 1, "cube", hsi_depth=bands, attention=att, first_depth=fd)
     else:
         net, schema = SpectralUNET(bands, 1, bn_feats=feats), O.spectral_schema(bands, 1, feats)
     sd = O.synth_state_dict(schema, seed)
@@ -84,13 +84,15 @@ def test_train_step_parity_vs_oracle(model, n, bands, h, w, feats):
     ("unet_2x3x32x40", "UNET", 2, 3, 32, 40, 0, 0), ("cubenet_2x238x32x40", "CubeNET", 2, 238, 32, 40, 1, 0),
     ("cubenet_1x238x48x72", "CubeNET", 1, 238, 48, 72, 2, 0), ("spectral32_2x238x6x10", "SpectralUNET", 2, 238, 6, 10, 3, 32),
     ("spectral1650_2x238x4x5", "SpectralUNET", 2, 238, 4, 5, 4, 1650),
-    ("unet_att_2x3x32x40", "UNET", 2, 3, 32, 40, 5, 0), ("cubenet_att_2x238x34x42", "CubeNET", 2, 238, 34, 42, 6, 0)])
+    ("unet_att_2x3x32x40", "UNET", 2, 3, 32, 40, 5, 0), ("cubenet_att_2x238x34x42", "CubeNET", 2, 238, 34, 42, 6, 0),
+    ("cubenet_fd32_2x238x32x40", "CubeNET", 2, 238, 32, 40, 7, 0), ("cubenet_fd128_att_1x238x34x42", "CubeNET", 1, 238, 34, 42, 8, 0)])
 @pytest.mark.parametrize("mode", ["train", "eval"])
 def test_against_reference_golden(name, model, n, bands, h, w, seed, feats, mode):
     """Reference-module outputs (tests/golden, made by oracle/gen_golden.py).  These shapes are tiny (BatchNorm over
     as few as 8 samples), so the tolerance is 3e-2 of max|logit| here; realistic sizes are held to 1e-2 above."""
     g = np.load(os.path.join(GOLD, name + ".npz"))
-    net, _ = build(model, bands, feats, seed, att="_att_" in name)
+    fd = int(name.split("_fd")[1].split("_")[0]) if "_fd" in name else 64
+    net, _ = build(model, bands, feats, seed, att="_att_" in name, fd=fd)
     x = O.synth_cube(seed, n, bands, h, w)
     xin = x[:, None] if model == "CubeNET" else x
     mask = O.synth_mask(seed, n, h, w)
@@ -235,3 +237,32 @@ def test_use_attention_train_step_parity_vs_oracle(model, n, bands, h, w):
     assert cos(torch.cat(flat_g), torch.cat(flat_o)) > 0.97
     for k in ("up1.conv.double_conv.0.weight", "up4.conv.double_conv.0.weight", "up1.up.weight", "down4.maxpool_conv.1.double_conv.3.weight"):
         assert cos(dict(net.named_parameters())[k].grad.cpu(), og[k]) > 0.9, k
+
+
+@pytest.mark.parametrize("fd,att,h,w", [(32, False, 160, 208), (128, False, 97, 131), (16, True, 128, 160)])
+def test_cubenet_first_depth_train_step_parity_vs_oracle(fd, att, h, w):
+    """CubeNET first_depth != 64 (models.py:193-199, 229-240): first_conv / inc2 with first_depth maps (below and above
+    one 64-channel tile), last decoder block `upsample4` / `upconv4` over cat([x1, up]); with use_attention the other
+    three blocks multiply and the last still concatenates."""
+    net, sd = build("CubeNET", 238, att=att, fd=fd)
+    assert ("upsample4.weight" in sd) and ("up4.up.weight" not in sd)
+    x = O.synth_cube(2, 2, 238, h, w)[:, None]
+    mask = O.synth_mask(2, 2, h, w)
+    torch.set_num_threads(os.cpu_count())
+    ol, oloss, og, ostats = O.forward_backward("CubeNET", x, mask, sd, training=True, attention=att)
+    lg, loss = run_ours(net, x, mask)
+    err = (lg - ol).abs()
+    assert err.max().item() <= (3e-2 if att else 1e-2) * ol.abs().max().item()
+    assert abs(loss - oloss.item()) < 2e-4
+    flat_o, flat_g = [], []
+    for k, p in net.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all() and p.grad.shape == og[k].shape, k
+        flat_o.append(og[k].flatten()); flat_g.append(p.grad.cpu().flatten())
+    assert cos(torch.cat(flat_g), torch.cat(flat_o)) > 0.97
+    for k in ("first_conv.weight", "inc2.0.weight", "upsample4.weight", "upconv4.double_conv.0.weight",
+              "down1.maxpool_conv.1.double_conv.0.weight"):
+        assert cos(dict(net.named_parameters())[k].grad.cpu(), og[k]) > 0.9, k
+    bufs = dict(net.named_buffers())
+    for k, v in ostats.items():
+        if "running_" in k:
+            assert torch.allclose(bufs[k].cpu(), v, rtol=5e-3, atol=5e-4), k

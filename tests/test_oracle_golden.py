@@ -18,6 +18,8 @@ CASES = {
     "spectral1650_2x238x4x5": dict(model="SpectralUNET", n=2, h=4, w=5, bands=238, seed=4, feats=1650),
     "unet_att_2x3x32x40": dict(model="UNET", n=2, h=32, w=40, bands=3, seed=5, attention=True),
     "cubenet_att_2x238x34x42": dict(model="CubeNET", n=2, h=34, w=42, bands=238, seed=6, attention=True),
+    "cubenet_fd32_2x238x32x40": dict(model="CubeNET", n=2, h=32, w=40, bands=238, seed=7, first_depth=32),
+    "cubenet_fd128_att_1x238x34x42": dict(model="CubeNET", n=1, h=34, w=42, bands=238, seed=8, first_depth=128, attention=True),
 }
 
 
@@ -26,7 +28,7 @@ def _inputs(c):
     if c["model"] == "UNET":
         schema = O.unet_schema(c["bands"], 1, "unet", attention=att)
     elif c["model"] == "CubeNET":
-        schema = O.unet_schema(1, 1, "cube", hsi_depth=c["bands"], attention=att)
+        schema = O.unet_schema(1, 1, "cube", hsi_depth=c["bands"], attention=att, first_depth=c.get("first_depth", 64))
     else:
         schema = O.spectral_schema(c["bands"], 1, c["feats"])
     sd = O.synth_state_dict(schema, c["seed"])
