@@ -75,6 +75,8 @@ SIGNATURES = {
     "hpri_absmax": [_p, _ll, _p, _p],
     "hpri_convert16": [_VP, _VP, _p],
     "hpri_mul16": [_VP, _VP, _VP, _p],
+    "hpri_upsample2_fwd": [_VP, _VP, _p],
+    "hpri_upsample2_bwd": [_VP, _VP, _p],
     "hpri_bn_finalize": [_p, _ll, _p, _p, _p, _p, _p, _p, _f, _f, _i, _p, _p, _p, _p, _i, _p],
     "hpri_bn_relu_apply": [_VP, _p, _p, _VP, _VP, _p],
     "hpri_bn_relu_bwd_reduce": [_VP, _p, _p, _p, _p, _VP, _VP, _p, _p, _p, _p],

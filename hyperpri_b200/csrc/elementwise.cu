@@ -415,6 +415,86 @@ __global__ void __launch_bounds__(256) mul16_k(V a, V b, V y) {
   }
 }
 
+// ------------------------------------------------------------------ bilinear x2 upsample, align_corners=True
+// nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) (model_parts.py:57): output pixel o reads source
+// coordinate o * (in - 1) / (out - 1); the taps are floor and floor + 1 (clamped), weights 1 - frac and frac.
+// y covers the whole destination view (the skip's size): pixels beyond 2h x 2w are the zero padding of Up.forward.
+__device__ __forceinline__ void bil_tap(int o, int in, int out, int& i0, int& i1, float& w1) {
+  const float s = out > 1 ? static_cast<float>(in - 1) / static_cast<float>(out - 1) : 0.f;
+  const float f = s * static_cast<float>(o);
+  i0 = min(static_cast<int>(f), in - 1);
+  i1 = min(i0 + 1, in - 1);
+  w1 = f - static_cast<float>(i0);
+}
+__global__ void __launch_bounds__(256) upsample2_fwd_k(V x, V y) {
+  const int CG = (x.c + 7) >> 3;
+  const long long total = (long long)y.n * y.h * y.w * CG;
+  const int oh = 2 * x.h, ow = 2 * x.w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    long long j = i / CG;
+    const int ox = (int)(j % y.w); j /= y.w;
+    const int oy = (int)(j % y.h);
+    const int n = (int)(j / y.h);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (oy < oh && ox < ow) {
+      int y0, y1, x0, x1;
+      float wy, wx;
+      bil_tap(oy, x.h, oh, y0, y1, wy);
+      bil_tap(ox, x.w, ow, x0, x1, wx);
+      const int ys[2] = {y0, y1}, xs[2] = {x0, x1};
+      const float wys[2] = {1.f - wy, wy}, wxs[2] = {1.f - wx, wx};
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          float f[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(at(x, n, ys[a], xs[b], cg * 8))), f, x.dt);
+          const float w = wys[a] * wxs[b];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) acc[k] = fmaf(w, f[k], acc[k]);
+        }
+    }
+    *reinterpret_cast<uint4*>(at(y, n, oy, ox, cg * 8)) = pack8(acc, y.dt);
+  }
+}
+// backward as a gather: input pixel (iy, ix) collects every output pixel that tapped it.  The source coordinate grows
+// by (in-1)/(out-1) < 1/2 + 1/out per output pixel, so those lie in [2*i - 2, 2*i + 2]; dy is the destination-sized
+// gradient view (its padding region beyond 2h x 2w is ignored).
+__global__ void __launch_bounds__(256) upsample2_bwd_k(V dy, V dx) {
+  const int CG = (dx.c + 7) >> 3;
+  const long long total = (long long)dx.n * dx.h * dx.w * CG;
+  const int oh = 2 * dx.h, ow = 2 * dx.w;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    long long j = i / CG;
+    const int ix = (int)(j % dx.w); j /= dx.w;
+    const int iy = (int)(j % dx.h);
+    const int n = (int)(j / dx.h);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int oy = max(0, 2 * iy - 2); oy <= min(oh - 1, 2 * iy + 2); ++oy) {
+      int y0, y1;
+      float wy;
+      bil_tap(oy, dx.h, oh, y0, y1, wy);
+      const float a = (y0 == iy ? 1.f - wy : 0.f) + (y1 == iy ? wy : 0.f);
+      if (a == 0.f) continue;
+      for (int ox = max(0, 2 * ix - 2); ox <= min(ow - 1, 2 * ix + 2); ++ox) {
+        int x0, x1;
+        float wx;
+        bil_tap(ox, dx.w, ow, x0, x1, wx);
+        const float b = (x0 == ix ? 1.f - wx : 0.f) + (x1 == ix ? wx : 0.f);
+        if (b == 0.f) continue;
+        float f[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(at(dy, n, oy, ox, cg * 8))), f, dy.dt);
+        const float w = a * b;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = fmaf(w, f[k], acc[k]);
+      }
+    }
+    *reinterpret_cast<uint4*>(at(dx, n, iy, ix, cg * 8)) = pack8(acc, dx.dt);
+  }
+}
+
 // ------------------------------------------------------------------ BatchNorm finalize
 __global__ void bn_finalize_k(double* stats, long long count, const float* gamma, const float* beta,
                               const float* conv_bias, float* rmean, float* rvar, long long* nbt, float momentum,
@@ -1305,6 +1385,23 @@ extern "C" int hpri_mul16(const hpri_view_t* a, const hpri_view_t* b, const hpri
   if (a->n != y->n || a->h != y->h || a->w != y->w || a->c != y->c) return HPRI_ERR_ARG;
   const long long total = (long long)a->n * a->h * a->w * ((a->c + 7) / 8);
   mul16_k<<<grid_for(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(mk(a), mk(b), mk(y));
+  return last_err();
+}
+
+extern "C" int hpri_upsample2_fwd(const hpri_view_t* x, const hpri_view_t* y, void* stream) {
+  int rc;
+  if ((rc = check_view_e(x)) != HPRI_OK || (rc = check_view_e(y)) != HPRI_OK) return rc;
+  if (x->n != y->n || x->c != y->c || y->h < 2 * x->h || y->w < 2 * x->w) return HPRI_ERR_ARG;
+  const long long total = (long long)y->n * y->h * y->w * ((y->c + 7) / 8);
+  upsample2_fwd_k<<<grid_for(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(mk(x), mk(y));
+  return last_err();
+}
+extern "C" int hpri_upsample2_bwd(const hpri_view_t* dy, const hpri_view_t* dx, void* stream) {
+  int rc;
+  if ((rc = check_view_e(dy)) != HPRI_OK || (rc = check_view_e(dx)) != HPRI_OK) return rc;
+  if (dx->n != dy->n || dx->c != dy->c || dy->h < 2 * dx->h || dy->w < 2 * dx->w) return HPRI_ERR_ARG;
+  const long long total = (long long)dx->n * dx->h * dx->w * ((dx->c + 7) / 8);
+  upsample2_bwd_k<<<grid_for(total, 256, 148 * 32), 256, 0, (cudaStream_t)stream>>>(mk(dy), mk(dx));
   return last_err();
 }
 

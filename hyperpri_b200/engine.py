@@ -1,8 +1,9 @@
 """Hand-scheduled forward / backward plans over the native kernels.
 
-``UNetEngine`` runs UNet and CubeNET-64 (reference models.py:23-68, 148-247 with
-model_parts.py:14-99); ``SpectralEngine`` runs SpectralUNET (models.py:71-145).  An engine
-owns the NHWC bf16 activation workspace for one input shape, packed bf16 copies of the fp32
+``UNetEngine`` runs UNet and CubeNET (reference models.py:23-68, 148-247 with
+model_parts.py:14-99, including the `use_attention`, `bilinear` and `first_depth` variants through a
+per-level channel plan); ``SpectralEngine`` runs SpectralUNET (models.py:71-145).  An engine
+owns the NHWC 16-bit activation workspace for one input shape, packed 16-bit copies of the fp32
 master parameters (refreshed when a parameter's version changes) and fp32 gradient buffers.
 The nn.Modules in ``hyperpri_b200.src.Experiments.models`` call it through one
 autograd.Function, so ``loss.backward()`` fills ``.grad`` on the module's own Parameters.
@@ -210,17 +211,27 @@ class UNetEngine(_EngineBase):
     CH = [64, 128, 256, 512, 1024]
 
     def __init__(self, params: Dict[str, torch.Tensor], first: str, in_ch: int, device, attention: bool = False,
-                 first_depth: int = 64):
+                 first_depth: int = 64, bilinear: bool = False):
         """params: name -> Parameter/buffer of the owning module (reference state-dict names).
         first: 'unet' (DoubleConv(in_ch, 64)) or 'cube' (Conv3d over in_ch bands, then inc2).
         first_depth: CubeNET's number of first-layer feature maps (models.py:168-178); when it is not 64 the last
-        decoder block is `upsample4` / `upconv4` over cat([x1 (first_depth), up (64)]) (models.py:193-199, 229-240)."""
+        decoder block is `upsample4` / `upconv4` over cat([x1 (first_depth), up (64)]) (models.py:193-199, 229-240).
+        bilinear: Up uses nn.Upsample(x2, bilinear, align_corners) instead of the ConvTranspose and DoubleConvs with
+        mid channels (model_parts.py:56-61; models.py:33,43-49: down4 and the decoder outputs are halved)."""
         self.P, self.first, self.in_ch, self.dev = params, first, in_ch, device
         F = int(first_depth) if first == "cube" else 64
         if F % 8 or F <= 0:
             raise NotImplementedError("CubeNET first_depth must be a positive multiple of 8 (16-byte NHWC channel runs)")
-        # encoder channels per level (decoder channels are CH[l]; they differ only at level 0 when first_depth != 64)
-        self.CE = [F] + self.CH[1:]
+        self.bilinear = bool(bilinear)
+        if self.bilinear and F != 64:
+            raise ValueError("bilinear=True with first_depth != 64 does not run in the reference either "
+                             "(upconv4 expects 128 + first_depth channels, models.py:195-196)")
+        # channel plan per level: CE encoder block output (= skip), U upsampled operand of the concat, M / D outputs of
+        # the decoder block's first / second conv
+        self.CE = [F] + self.CH[1:4] + [self.CH[4] // (2 if self.bilinear else 1)]
+        self.U = list(self.CH[:4])
+        self.M = list(self.CH[:4])
+        self.D = [64, 64, 128, 256] if self.bilinear else list(self.CH[:4])
         self.up_name = {l: f"up{4 - l}.up" for l in range(4)}
         self.dec_name = {l: f"up{4 - l}.conv.double_conv" for l in range(4)}
         if F != 64:
@@ -232,7 +243,7 @@ class UNetEngine(_EngineBase):
         # cat([skip, up]) (2C); the product and its two backward products are hpri_mul16 launches
         self.att = bool(attention)
         d = device
-        C = self.CH
+        CE, U, M, D = self.CE, self.U, self.M, self.D
         if first == "unet":
             self.cin_pad = (in_ch + 7) // 8 * 8
             enc0 = [_CBR("inc.double_conv.0", "inc.double_conv.1", self.cin_pad, 64, d, need_dgrad=False),
@@ -246,17 +257,18 @@ class UNetEngine(_EngineBase):
         self.enc: List[List[_CBR]] = [enc0]
         for i in range(1, 5):
             p = f"down{i}.maxpool_conv.1.double_conv"
-            self.enc.append([_CBR(p + ".0", p + ".1", self.CE[i - 1], C[i], d), _CBR(p + ".3", p + ".4", C[i], C[i], d)])
+            self.enc.append([_CBR(p + ".0", p + ".1", CE[i - 1], CE[i], d), _CBR(p + ".3", p + ".4", CE[i], CE[i], d)])
         self.dec: Dict[int, List[_CBR]] = {}
         self.up: Dict[int, _PackedParam] = {}
         self.up_gw: Dict[int, torch.Tensor] = {}
         for i in range(1, 5):
             lvl = 4 - i
             p = self.dec_name[lvl]
-            self.dec[lvl] = [_CBR(p + ".0", p + ".1", C[lvl] if self.attl[lvl] else self.CE[lvl] + C[lvl], C[lvl], d),
-                             _CBR(p + ".3", p + ".4", C[lvl], C[lvl], d)]
-            self.up[lvl] = _PackedParam(WeightSpec("convT2x2", C[lvl], C[lvl + 1]), True)
-            self.up_gw[lvl] = self.up[lvl].spec.grad_buffer(d)
+            self.dec[lvl] = [_CBR(p + ".0", p + ".1", U[lvl] if self.attl[lvl] else CE[lvl] + U[lvl], M[lvl], d),
+                             _CBR(p + ".3", p + ".4", M[lvl], D[lvl], d)]
+            if not self.bilinear:
+                self.up[lvl] = _PackedParam(WeightSpec("convT2x2", U[lvl], D[lvl + 1] if lvl < 3 else CE[4]), True)
+                self.up_gw[lvl] = self.up[lvl].spec.grad_buffer(d)
         # BN-backward sums of every layer in one buffer: the ones accumulated by dgrad epilogues are cleared by ONE fill
         layers = [L for grp in list(self.enc) + list(self.dec.values()) for L in grp]
         self._bw_sums = _z((sum(L.cout for L in layers), 3), d, torch.float64)
@@ -288,7 +300,9 @@ class UNetEngine(_EngineBase):
         order += ["outc.conv.bias", "outc.conv.weight"]
         for l in (0, 1, 2, 3):
             a, b = self.dec[l]
-            order += cbr_names(b) + cbr_names(a) + [self.up_name[l] + ".weight", self.up_name[l] + ".bias"]
+            order += cbr_names(b) + cbr_names(a)
+            if not self.bilinear:
+                order += [self.up_name[l] + ".weight", self.up_name[l] + ".bias"]
             buckets.append(len(order))
         for l in (4, 3, 2, 1, 0):
             a, b = self.enc[l]
@@ -331,7 +345,7 @@ class UNetEngine(_EngineBase):
         key = (n, h, w)
         if self.ws_key == key:
             return self.ws
-        d, C, CE = self.dev, self.CH, self.CE
+        d, CE, U, M, D = self.dev, self.CE, self.U, self.M, self.D
         H, W = [h], [w]
         for _ in range(4):
             H.append(H[-1] // 2)
@@ -345,29 +359,41 @@ class UNetEngine(_EngineBase):
             ws[f"enc_act_a{l}"] = _e((n, H[l], W[l], CE[l]), d)
             ws[f"enc_raw_b{l}"] = _e((n, H[l], W[l], CE[l]), d)
             if l < 4:
-                ws[f"cat{l}"] = _z((n, H[l], W[l], CE[l] + C[l]), d)      # [skip | upsampled], pad stays zero
-                ws[f"gcat{l}"] = _z((n, H[l], W[l], CE[l] + C[l]), d, GRAD)
+                ws[f"cat{l}"] = _z((n, H[l], W[l], CE[l] + U[l]), d)      # [skip | upsampled], pad stays zero
+                ws[f"gcat{l}"] = _z((n, H[l], W[l], CE[l] + U[l]), d, GRAD)
                 if self.attl[l]:   # cat / gcat hold [skip | up] and [d skip | d up]; the conv works on the products
-                    ws[f"mul{l}"] = _e((n, H[l], W[l], C[l]), d)
-                    ws[f"gmul{l}"] = _e((n, H[l], W[l], C[l]), d, GRAD)
+                    ws[f"mul{l}"] = _e((n, H[l], W[l], U[l]), d)
+                    ws[f"gmul{l}"] = _e((n, H[l], W[l], U[l]), d, GRAD)
                 ws[f"pool{l + 1}"] = _e((n, H[l + 1], W[l + 1], CE[l]), d)
                 ws[f"gpool{l + 1}"] = _e((n, H[l + 1], W[l + 1], CE[l]), d, GRAD)
-                ws[f"dec_raw_a{l}"] = _e((n, H[l], W[l], C[l]), d)
-                ws[f"dec_act_a{l}"] = _e((n, H[l], W[l], C[l]), d)
-                ws[f"dec_raw_b{l}"] = _e((n, H[l], W[l], C[l]), d)
+                ws[f"dec_raw_a{l}"] = _e((n, H[l], W[l], M[l]), d)
+                ws[f"dec_act_a{l}"] = _e((n, H[l], W[l], M[l]), d)
+                ws[f"dec_raw_b{l}"] = _e((n, H[l], W[l], D[l]), d)
                 if l > 0:
-                    ws[f"dec_act_b{l}"] = _e((n, H[l], W[l], C[l]), d)
+                    ws[f"dec_act_b{l}"] = _e((n, H[l], W[l], D[l]), d)
             else:
-                ws["act_b4"] = _e((n, H[4], W[4], C[4]), d)
-            ws[f"R{l}"] = _e((n, H[l], W[l], C[l]), d, GRAD)      # grad wrt a raw conv output (second conv of a block)
-            # the first conv of a block gets its own: the second conv's weight gradient may still be reading R{l}
-            ws[f"Ra{l}"] = _e((n, H[l], W[l], C[l]), d, GRAD) if self._side is not None else ws[f"R{l}"]
-            ws[f"A{l}"] = _e((n, H[l], W[l], C[l]), d, GRAD)      # grad wrt an activation
-            # the encoder block of the level shares them unless its channel count differs (first_depth != 64)
-            for nm in ("R", "Ra", "A"):
-                ws[f"{nm}e{l}"] = ws[f"{nm}{l}"] if CE[l] == C[l] else _e((n, H[l], W[l], CE[l]), d, GRAD)
+                ws["act_b4"] = _e((n, H[4], W[4], CE[4]), d)
+            # gradient buffers of the level, shared between its decoder and encoder blocks (and between the roles below)
+            # whenever the channel counts agree -- always, except first_depth != 64 (level 0) and bilinear=True
+            pool = {}
+
+            def gbuf(c, tag=""):
+                if (c, tag) not in pool:
+                    pool[(c, tag)] = _e((n, H[l], W[l], c), d, GRAD)
+                return pool[(c, tag)]
+            cd, cm = (D[l], M[l]) if l < 4 else (CE[4], CE[4])
+            side = self._side is not None
+            # grad wrt a raw conv output: one per conv of the level when the weight gradients run on the side stream
+            # (the one of an earlier conv may still be reading its buffer when a later conv's is written), else shared
+            ws[f"R{l}"] = gbuf(cd, "r")                           # second conv of the decoder block
+            ws[f"Ra{l}"] = gbuf(cm, "ra" if side else "r")        # first conv of the decoder block
+            ws[f"Re{l}"] = gbuf(CE[l], "re" if side else "r")     # second / first conv of the encoder block
+            ws[f"Rae{l}"] = gbuf(CE[l], "rae" if side else "r")
+            ws[f"A{l}"] = gbuf(cm, "act")                         # grad wrt the first conv's activation
+            ws[f"G{l}"] = gbuf(cd, "act")                         # grad wrt the block's output (from the level above)
+            ws[f"Ae{l}"] = gbuf(CE[l], "act")
         if GRAD != ACT:
-            ws["cvt"] = _e((n * h * w * max(self.cin_pad, 2 * C[0]),), d, GRAD)
+            ws["cvt"] = _e((n * h * w * max(self.cin_pad, CE[0] + U[0]),), d, GRAD)
         ws["logits"] = _e((n, 1, h, w), d, torch.float32)
         ws["dlogit"] = _e((n, 1, h, w), d, torch.float32)
         ws["dlogit_s"] = _e((n, 1, h, w), d, torch.float32)
@@ -432,7 +458,7 @@ class UNetEngine(_EngineBase):
     def _fusable(self, l, enc=False):
         """The a-layer of level l gets its whole output gradient from the b-layer's dgrad launch; the reduction can
         ride in that launch when it runs on the halo kernel."""
-        return ops.conv3x3_halo_ok(self.ws["H"][l], self.ws["W"][l], (self.CE if enc else self.CH)[l])
+        return ops.conv3x3_halo_ok(self.ws["H"][l], self.ws["W"][l], (self.CE if enc else self.M)[l])
 
     # ------------------------------------------------------------------ forward
     def ingest(self, x: torch.Tensor, ws):
@@ -494,7 +520,7 @@ class UNetEngine(_EngineBase):
             ops.unpack_conv3x3_batch(self._table("all", self._conv_layers()))
 
     def forward_ingested(self, ws, training: bool) -> torch.Tensor:
-        P, C, CE = self.P, self.CH, self.CE
+        P, CE, U = self.P, self.CE, self.U
         self.training_fwd = training
         self._refresh_packed()
         cur = ws["x"]
@@ -509,13 +535,15 @@ class UNetEngine(_EngineBase):
                 self._cbr_fwd(b, ws["enc_act_a4"], ws["enc_raw_b4"], ws["act_b4"], training)
                 cur = ws["act_b4"]
         for l in (3, 2, 1, 0):
-            up = self.up[l]
-            i = 4 - l
-            up.refresh(P[self.up_name[l] + ".weight"])
-            ops.convT_fwd(cur, up.fwd, C[l], ws[f"cat{l}"][..., CE[l]:], bias=P[self.up_name[l] + ".bias"])
+            if self.bilinear:
+                ops.upsample2_fwd(cur, ws[f"cat{l}"][..., CE[l]:])
+            else:
+                up = self.up[l]
+                up.refresh(P[self.up_name[l] + ".weight"])
+                ops.convT_fwd(cur, up.fwd, U[l], ws[f"cat{l}"][..., CE[l]:], bias=P[self.up_name[l] + ".bias"])
             a, b = self.dec[l]
             if self.attl[l]:
-                ops.mul16(ws[f"cat{l}"][..., :C[l]], ws[f"cat{l}"][..., C[l]:], ws[f"mul{l}"])
+                ops.mul16(ws[f"cat{l}"][..., :CE[l]], ws[f"cat{l}"][..., CE[l]:], ws[f"mul{l}"])
             self._cbr_fwd(a, ws[f"mul{l}"] if self.attl[l] else ws[f"cat{l}"], ws[f"dec_raw_a{l}"], ws[f"dec_act_a{l}"], training)
             if l > 0:
                 self._cbr_fwd(b, ws[f"dec_act_a{l}"], ws[f"dec_raw_b{l}"], ws[f"dec_act_b{l}"], training)
@@ -534,7 +562,7 @@ class UNetEngine(_EngineBase):
         unscaled in the arena by finalize_grads() (called here, or by the all-reduce hook owner)."""
         if not self.training_fwd:
             raise NotImplementedError("backward through eval-mode BatchNorm is not on the hot path")
-        ws, P, C, CE = self.ws, self.P, self.CH, self.CE
+        ws, P, CE, U = self.ws, self.P, self.CE, self.U
         n, H, W = ws["n"], ws["H"], ws["W"]
         self._begin_backward()
         self._bw_sums.zero_()              # one fill for the BN-backward sums the dgrad epilogues accumulate into
@@ -542,7 +570,6 @@ class UNetEngine(_EngineBase):
         cnt = [n * H[l] * W[l] for l in range(5)]
         head_w = P["outc.conv.weight"].detach().reshape(-1)
         ops.sum_f32(dlogit, self._grad("outc.conv.bias", P["outc.conv.bias"]))
-        g_in = None                        # gradient wrt the activation feeding the next (deeper-first) stage
         for l in (0, 1, 2, 3):
             a, b = self.dec[l]
             fuse = self._fusable(l)
@@ -552,32 +579,34 @@ class UNetEngine(_EngineBase):
                 self._cbr_bwd(b, ws["dec_act_a0"], ws["dec_raw_b0"], ws["R0"], cnt[0], head_w=head_w, dlogit=dlogit,
                               dhead_w=dhw, dx_out=ws["A0"], below=below)
             else:
-                self._cbr_bwd(b, ws[f"dec_act_a{l}"], ws[f"dec_raw_b{l}"], ws[f"R{l}"], cnt[l], dy=g_in,
+                self._cbr_bwd(b, ws[f"dec_act_a{l}"], ws[f"dec_raw_b{l}"], ws[f"R{l}"], cnt[l], dy=ws[f"G{l}"],
                               dx_out=ws[f"A{l}"], below=below)
             if self.attl[l]:
                 self._cbr_bwd(a, ws[f"mul{l}"], ws[f"dec_raw_a{l}"], ws[f"Ra{l}"], cnt[l], dy=ws[f"A{l}"],
                               dx_out=ws[f"gmul{l}"], reduced=fuse)
                 # d skip = g * up, d up = g * skip, written where the concat path keeps them
-                ops.mul16(ws[f"gmul{l}"], ws[f"cat{l}"][..., C[l]:], ws[f"gcat{l}"][..., :C[l]])
-                ops.mul16(ws[f"gmul{l}"], ws[f"cat{l}"][..., :C[l]], ws[f"gcat{l}"][..., C[l]:])
+                ops.mul16(ws[f"gmul{l}"], ws[f"cat{l}"][..., CE[l]:], ws[f"gcat{l}"][..., :CE[l]])
+                ops.mul16(ws[f"gmul{l}"], ws[f"cat{l}"][..., :CE[l]], ws[f"gcat{l}"][..., CE[l]:])
             else:
                 self._cbr_bwd(a, ws[f"cat{l}"], ws[f"dec_raw_a{l}"], ws[f"Ra{l}"], cnt[l], dy=ws[f"A{l}"],
                               dx_out=ws[f"gcat{l}"], reduced=fuse)
+            if self.bilinear:              # nn.Upsample backward: gather form over the (padded) destination gradient
+                ops.upsample2_bwd(ws[f"gcat{l}"][..., CE[l]:], ws[f"G{l + 1}"])
+                self._bucket_done(l)
+                continue
             # ConvTranspose2d backward: its output is the second half of cat[l] over the 2h x 2w region
-            i = 4 - l
             up = self.up[l]
             dy_up = ws[f"gcat{l}"][:, :2 * H[l + 1], :2 * W[l + 1], CE[l]:]
             x_up = ws[f"dec_act_b{l + 1}"] if l < 3 else ws["act_b4"]
-            ops.convT_dgrad(dy_up, up.dgr, C[l + 1], ws[f"A{l + 1}"])
+            ops.convT_dgrad(dy_up, up.dgr, up.spec.cin, ws[f"G{l + 1}"])
             gw = self.up_gw[l]
             wn = self.up_name[l] + ".weight"
 
-            def up_wgrad(x_up=self._as_grad_dtype(x_up), dy_up=dy_up, gw=gw, up=up, wn=wn, l=l, i=i):
-                ops.igemm_wgrad(x_up, dy_up, 2, 4 * C[l], gw)
+            def up_wgrad(x_up=self._as_grad_dtype(x_up), dy_up=dy_up, gw=gw, up=up, wn=wn, l=l):
+                ops.igemm_wgrad(x_up, dy_up, 2, 4 * U[l], gw)
                 up.spec.unpack_grad(gw, self._grad(wn, P[wn]).view(-1))
                 ops.colsum(dy_up, self._grad(self.up_name[l] + ".bias", P[self.up_name[l] + ".bias"]))
             self._on_side(up_wgrad)
-            g_in = ws[f"A{l + 1}"]
             self._bucket_done(l)
         # encoder, deepest first
         for l in (4, 3, 2, 1, 0):
@@ -585,7 +614,7 @@ class UNetEngine(_EngineBase):
             fuse = self._fusable(l, enc=True)
             below = (a, ws[f"enc_raw_a{l}"]) if fuse else None
             if l == 4:
-                self._cbr_bwd(b, ws["enc_act_a4"], ws["enc_raw_b4"], ws["Re4"], cnt[4], dy=g_in, dx_out=ws["Ae4"],
+                self._cbr_bwd(b, ws["enc_act_a4"], ws["enc_raw_b4"], ws["Re4"], cnt[4], dy=ws["G4"], dx_out=ws["Ae4"],
                               below=below)
             else:
                 self._cbr_bwd(b, ws[f"enc_act_a{l}"], ws[f"enc_raw_b{l}"], ws[f"Re{l}"], cnt[l],

@@ -313,6 +313,21 @@ def mul16(a, b, y):
     return y
 
 
+@_timed
+def upsample2_fwd(x, y):
+    """Bilinear x2, align_corners=True, into the top-left of y; the rest of y is zeroed (Up's padding)."""
+    xv, yv = view(x), view(y)
+    check(_lib.lib().hpri_upsample2_fwd(_vp(xv), _vp(yv), _stream()), "hpri_upsample2_fwd")
+    return y
+
+
+@_timed
+def upsample2_bwd(dy, dx):
+    dv, xv = view(dy), view(dx)
+    check(_lib.lib().hpri_upsample2_bwd(_vp(dv), _vp(xv), _stream()), "hpri_upsample2_bwd")
+    return dx
+
+
 def absmax(src):
     out = torch.empty(1, dtype=torch.float32, device=src.device)
     check(_lib.lib().hpri_absmax(_ptr(src), src.numel(), _ptr(out), _stream()), "hpri_absmax")

@@ -4,8 +4,8 @@ layout (reference src/Experiments/model_parts.py:14-99), re-hosted on the B200 k
 The blocks are parameter containers: the arithmetic of a whole network is scheduled by
 ``hyperpri_b200.engine`` (conv+BN-statistics GEMM epilogues, fused BN/ReLU/pool passes, concat by
 placement), so a block does not run layer-by-layer torch ops.  `use_attention=True` (skip * up,
-model_parts.py:84-85) is built; the unsupported reference option `bilinear=True` (unused by every
-reference config, params_HyperPRI.py:53-54,210-211) raises instead of silently falling back.
+model_parts.py:84-85) and `bilinear=True` (nn.Upsample + mid-channel DoubleConvs, :56-61) are built,
+although every reference config leaves them off (params_HyperPRI.py:53-54,210-211).
 """
 import torch.nn as nn
 
@@ -46,12 +46,14 @@ class Up(nn.Module):
 
     def __init__(self, in_channels, out_channels, bilinear=True, use_attention=False):
         super().__init__()
-        if bilinear:
-            raise NotImplementedError("bilinear=True (nn.Upsample path, model_parts.py:56-61) is not built: "
-                                      "every reference config uses bilinear=False")
         self.use_attention = use_attention
-        self.up = nn.ConvTranspose2d(in_channels, in_channels // 2, kernel_size=2, stride=2)
-        self.conv = DoubleConv(in_channels // 2 if use_attention else in_channels, out_channels)   # model_parts.py:65-68
+        cin = in_channels // 2 if use_attention else in_channels
+        if bilinear:                                                     # model_parts.py:56-61
+            self.up = nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True)
+            self.conv = DoubleConv(cin, out_channels // 2, in_channels // 2)
+        else:                                                            # model_parts.py:62-68
+            self.up = nn.ConvTranspose2d(in_channels, in_channels // 2, kernel_size=2, stride=2)
+            self.conv = DoubleConv(cin, out_channels)
 
     def forward(self, x1, x2):
         raise NotImplementedError(_STANDALONE.format("Up"))

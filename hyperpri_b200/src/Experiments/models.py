@@ -98,17 +98,19 @@ class UNet(_EngineNet):
         if n_classes != 1:
             raise NotImplementedError("the B200 head kernel is built for n_classes=1 (every reference config)")
         w = [64 * 2 ** i for i in range(5)]
+        factor = 2 if bilinear else 1                                   # models.py:33
         self.inc = DoubleConv(n_channels, w[0])
         self.down1, self.down2 = Down(w[0], w[1]), Down(w[1], w[2])
-        self.down3, self.down4 = Down(w[2], w[3]), Down(w[3], w[4])
+        self.down3, self.down4 = Down(w[2], w[3]), Down(w[3], w[4] // factor)
         self.up1 = Up(w[4], w[3], bilinear, use_attention=use_attention)
         self.up2 = Up(w[3], w[2], bilinear, use_attention=use_attention)
         self.up3 = Up(w[2], w[1], bilinear, use_attention=use_attention)
-        self.up4 = Up(w[1], w[0], bilinear, use_attention=use_attention)
+        self.up4 = Up(w[1], w[0] * factor, bilinear, use_attention=use_attention)
         self.outc = OutConv(w[0], n_classes)
 
     def _make_engine(self, device):
-        return _engine.UNetEngine(self._tensor_table(), "unet", self.n_channels, device, attention=self.use_attention)
+        return _engine.UNetEngine(self._tensor_table(), "unet", self.n_channels, device, attention=self.use_attention,
+                                  bilinear=self.bilinear)
 
     def forward(self, x):
         return self._finish(self._run(x))
@@ -132,22 +134,24 @@ class CubeNET(_EngineNet):
                                   nn.BatchNorm2d(first_depth), nn.ReLU(inplace=True))
         c = 128
         self.down1, self.down2 = Down(first_depth, c), Down(c, 2 * c)
-        self.down3, self.down4 = Down(2 * c, 4 * c), Down(4 * c, 8 * c)
+        factor = 2 if bilinear else 1                                   # models.py:166
+        self.down3, self.down4 = Down(2 * c, 4 * c), Down(4 * c, 8 * c // factor)
         self.up1 = Up(8 * c, 4 * c, bilinear, use_attention=use_attention)
         self.up2 = Up(4 * c, 2 * c, bilinear, use_attention=use_attention)
         self.up3 = Up(2 * c, c, bilinear, use_attention=use_attention)
         if first_depth == 64:
-            self.up4 = Up(c, 64, bilinear, use_attention=use_attention)
+            self.up4 = Up(c, 64 * factor, bilinear, use_attention=use_attention)
         else:       # models.py:193-199: the skip has first_depth channels, the up path 64; always concatenated (:229-240)
             if bilinear:
-                raise NotImplementedError("bilinear=True (nn.Upsample path) is not built")
+                raise ValueError("bilinear=True with first_depth != 64 does not run in the reference either: upconv4 expects "
+                                 "128 + first_depth channels but receives 64 + first_depth (models.py:195-196, 229-240)")
             self.upsample4 = nn.ConvTranspose2d(c, 64, kernel_size=2, stride=2)
             self.upconv4 = DoubleConv(64 + first_depth, 64)
         self.outc = OutConv(64, n_classes)
 
     def _make_engine(self, device):
         return _engine.UNetEngine(self._tensor_table(), "cube", self.depth, device, attention=self.use_attention,
-                                  first_depth=self.first_depth)
+                                  first_depth=self.first_depth, bilinear=self.bilinear)
 
     def forward(self, x):
         """x: N x 1 x D x R x C (a depth mismatch is not raised by the reference either, models.py:211)."""

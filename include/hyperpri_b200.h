@@ -186,6 +186,13 @@ int hpri_convert16(const hpri_view_t* x, const hpri_view_t* y, void* stream);
  * use_attention=True (reference src/Experiments/model_parts.py:84-85) and the two products of its backward. */
 int hpri_mul16(const hpri_view_t* a, const hpri_view_t* b, const hpri_view_t* y, void* stream);
 
+/* nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) (reference src/Experiments/model_parts.py:57) of
+ * x (n, h, w, c) into the top-left 2h x 2w of y (n, >=2h, >=2w, c); the rest of y -- the zero padding Up.forward adds
+ * to reach the skip's size (model_parts.py:77-80) -- is written as zeros.  _bwd: dx (n, h, w, c) from the gradient view
+ * dy of y's shape (gather form, no atomics). */
+int hpri_upsample2_fwd(const hpri_view_t* x, const hpri_view_t* y, void* stream);
+int hpri_upsample2_bwd(const hpri_view_t* dy, const hpri_view_t* dx, void* stream);
+
 /* ---- BatchNorm / ReLU / MaxPool family ---------------------------------------------------- */
 /* Turn accumulated (sum, sumsq) into scale/shift, saved mean/invstd, and the running-stat update
  * (biased var to normalise, unbiased for running_var, momentum 0.1, conv bias re-added to the mean);

@@ -35,19 +35,23 @@ CASES = {
     # first_depth != 64 (models.py:193-199, 229-240): upsample4 / upconv4 over cat([x1 (first_depth), up (64)])
     "cubenet_fd32_2x238x32x40": dict(model="CubeNET", n=2, h=32, w=40, bands=238, seed=7, first_depth=32),
     "cubenet_fd128_att_1x238x34x42": dict(model="CubeNET", n=1, h=34, w=42, bands=238, seed=8, first_depth=128, attention=True),
+    # bilinear=True (model_parts.py:56-61): nn.Upsample + mid-channel DoubleConvs, down4 / decoder outputs halved
+    "unet_bil_2x3x34x42": dict(model="UNET", n=2, h=34, w=42, bands=3, seed=9, bilinear=True),
+    "cubenet_bil_att_2x238x32x40": dict(model="CubeNET", n=2, h=32, w=40, bands=238, seed=10, bilinear=True, attention=True),
 }
 
 
 def build(case):
     m = case["model"]
     att = case.get("attention", False)
+    bil = case.get("bilinear", False)
     if m == "UNET":
-        net = UNet(case["bands"], 1, bilinear=False, use_attention=att)
-        schema = O.unet_schema(case["bands"], 1, "unet", attention=att)
+        net = UNet(case["bands"], 1, bilinear=bil, use_attention=att)
+        schema = O.unet_schema(case["bands"], 1, "unet", attention=att, bilinear=bil)
     elif m == "CubeNET":
         fd = case.get("first_depth", 64)
-        net = CubeNET(case["bands"], 1, first_depth=fd, bilinear=False, use_attention=att)
-        schema = O.unet_schema(1, 1, "cube", hsi_depth=case["bands"], attention=att, first_depth=fd)
+        net = CubeNET(case["bands"], 1, first_depth=fd, bilinear=bil, use_attention=att)
+        schema = O.unet_schema(1, 1, "cube", hsi_depth=case["bands"], attention=att, first_depth=fd, bilinear=bil)
     else:
         net = SpectralUNET(case["bands"], 1, bn_feats=case["feats"])
         schema = O.spectral_schema(case["bands"], 1, case["feats"])

@@ -80,12 +80,14 @@ def _dc_schema(pre: str, cin: int, cout: int, mid: int | None = None):
 
 
 def unet_schema(n_channels: int, n_classes: int = 1, first: str = "unet", hsi_depth: int = 0, attention: bool = False,
-                first_depth: int = 64):
+                first_depth: int = 64, bilinear: bool = False):
     """State-dict schema of UNet / CubeNET-64, bilinear=False.  attention=True:
     Up's DoubleConv takes the product skip*up, i.e. Cin/2 input channels (model_parts.py:65-66).  first_depth != 64
     (CubeNET only): first_conv / inc2 have first_depth maps and the last decoder block is upsample4 / upconv4 over
     cat([x1, up]) whatever `attention` says (models.py:193-199, 229-240)."""
     fd = first_depth if first != "unet" else 64
+    if bilinear:
+        assert fd == 64, "the reference's bilinear + first_depth != 64 branch does not run (models.py:195-196)"
     s: Dict[str, Tuple[int, ...]] = {}
     if first == "unet":
         s.update(_dc_schema("inc.double_conv", n_channels, 64))
@@ -101,9 +103,13 @@ def unet_schema(n_channels: int, n_classes: int = 1, first: str = "unet", hsi_de
         s["inc2.0.bias"] = (fd,)
     chans = [fd, 128, 256, 512, 1024]
     for i in range(1, 5):
-        s.update(_dc_schema(f"down{i}.maxpool_conv.1.double_conv", chans[i - 1], chans[i]))
+        s.update(_dc_schema(f"down{i}.maxpool_conv.1.double_conv", chans[i - 1], chans[i] // (2 if bilinear and i == 4 else 1)))
     for i in range(1, 5):
         cin = chans[5 - i]
+        if bilinear:                      # Up(in, out, bilinear): nn.Upsample has no parameters (model_parts.py:56-61)
+            out = 128 if i == 4 else cin // 2          # models.py:46-49: up4 = Up(128, 64 * factor)
+            s.update(_dc_schema(f"up{i}.conv.double_conv", cin // 2 if attention else cin, out // 2, cin // 2))
+            continue
         if i == 4 and fd != 64:
             s["upsample4.weight"] = (cin, 64, 2, 2)
             s["upsample4.bias"] = (64,)
@@ -267,7 +273,10 @@ def up(x1, x2, sd, pre, training, stats_out=None, quant_out=True, attention=Fals
     right/bottom) -> cat([skip, up]) (use_attention: skip * up, model_parts.py:84-85) -> DoubleConv
     (model_parts.py:71-90)."""
     up_key, conv_key = up_key or pre + ".up", conv_key or pre + ".conv.double_conv"
-    x1 = q(F.conv_transpose2d(x1, q(sd[up_key + ".weight"]), sd[up_key + ".bias"], stride=2))
+    if up_key + ".weight" in sd:
+        x1 = q(F.conv_transpose2d(x1, q(sd[up_key + ".weight"]), sd[up_key + ".bias"], stride=2))
+    else:                                 # bilinear=True: nn.Upsample(scale_factor=2, bilinear, align_corners=True)
+        x1 = q(F.interpolate(x1, scale_factor=2, mode="bilinear", align_corners=True))
     dy, dx = x2.shape[2] - x1.shape[2], x2.shape[3] - x1.shape[3]
     x1 = F.pad(x1, [dx // 2, dx - dx // 2, dy // 2, dy - dy // 2])
     x = q(q(x2) * x1) if attention else torch.cat([q(x2), x1], dim=1)

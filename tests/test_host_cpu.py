@@ -68,10 +68,11 @@ def test_factories_and_unsupported_flags():
         mdl.initialize_model("nope", 1, p)
     assert mdl.translate_load_dir("SpectralUNET", p) == "SpectralUNET_1650"
     assert mdl.translate_load_dir("CubeNET", p) == "CubeNET_64" and mdl.translate_load_dir("UNET", p) == "UNET"
-    with pytest.raises(NotImplementedError):
-        mdl.UNet(3, 1, bilinear=True)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):                # does not run in the reference either (models.py:195-196)
         mdl.CubeNET(238, 1, first_depth=32, bilinear=True)
+    bsd = mdl.UNet(3, 1).state_dict()               # the reference's default: bilinear=True
+    assert {k: tuple(v.shape) for k, v in bsd.items()} == {k: tuple(v) for k, v in O.unet_schema(3, 1, "unet", bilinear=True).items()}
+    assert bsd["down4.maxpool_conv.1.double_conv.3.weight"].shape == (512, 512, 3, 3) and "up1.up.weight" not in bsd
     # first_depth != 64 and use_attention are built: same state-dict schema as the reference (models.py:193-199)
     net = mdl.CubeNET(238, 1, first_depth=32, bilinear=False, use_attention=True)
     sd = net.state_dict()

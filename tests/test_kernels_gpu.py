@@ -473,3 +473,30 @@ def test_mul16_strided_views():
     ops.mul16(cat[..., :64], cat[..., 64:], out[..., 64:])
     want = (cat[..., :64].float() * cat[..., 64:].float()).half()
     assert torch.equal(out[..., 64:], want) and float(out[..., :64].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("n,h,w,c,ph,pw", [(2, 5, 7, 64, 0, 0), (1, 9, 6, 24, 1, 1), (2, 1, 3, 8, 0, 1), (1, 38, 60, 128, 0, 1)])
+def test_upsample2_bilinear_align_corners_fwd_bwd(n, h, w, c, ph, pw):
+    """hpri_upsample2_fwd / _bwd against torch's Upsample(align_corners=True) + zero pad and its autograd, writing
+    into / reading from the second half of a concat-shaped buffer."""
+    import torch.nn.functional as F
+    torch.manual_seed(0)
+    x = torch.randn((n, h, w, c), device="cuda").half()
+    H2, W2 = 2 * h + ph, 2 * w + pw
+    cat = torch.full((n, H2, W2, 2 * c), 7.0, device="cuda", dtype=torch.float16)
+    ops.upsample2_fwd(x, cat[..., c:])
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    yr = F.pad(F.interpolate(xr, scale_factor=2, mode="bilinear", align_corners=True), [0, pw, 0, ph])
+    got = cat[..., c:].float().permute(0, 3, 1, 2)
+    assert float((got - yr.detach()).abs().max()) <= 2e-3 * float(yr.detach().abs().max()) + 1e-3
+    assert float((cat[..., :c] - 7.0).abs().max()) == 0.0
+    if ph:
+        assert float(cat[:, 2 * h:, :, c:].abs().max()) == 0.0
+    if pw:
+        assert float(cat[:, :, 2 * w:, c:].abs().max()) == 0.0
+    g = torch.randn((n, H2, W2, 2 * c), device="cuda").half()
+    dx = torch.empty((n, h, w, c), device="cuda", dtype=torch.float16)
+    ops.upsample2_bwd(g[..., c:], dx)
+    yr.backward(g[..., c:].float().permute(0, 3, 1, 2))
+    want = xr.grad.permute(0, 2, 3, 1)
+    assert float((dx.float() - want).abs().max()) <= 3e-3 * float(want.abs().max()) + 1e-3

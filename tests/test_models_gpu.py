@@ -20,12 +20,13 @@ from hyperpri_b200.src.Experiments.models import UNet, CubeNET, SpectralUNET   #
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
-def build(model, bands, feats=1650, seed=0, att=False, fd=64):
+def build(model, bands, feats=1650, seed=0, att=False, fd=64, bil=False):
     if model == "UNET":
-        net, schema = UNet(bands, 1, bilinear=False, use_attention=att), O.unet_schema(bands, 1, "unet", attention=att)
+        net = UNet(bands, 1, bilinear=bil, use_attention=att)
+        schema = O.unet_schema(bands, 1, "unet", attention=att, bilinear=bil)
     elif model == "CubeNET":
-        net = CubeNET(bands, 1, first_depth=fd, bilinear=False, use_attention=att)
-        schema = O.unet_schema(1, 1, "cube", hsi_depth=bands, attention=att, first_depth=fd)
+        net = CubeNET(bands, 1, first_depth=fd, bilinear=bil, use_attention=att)
+        schema = O.unet_schema(1, 1, "cube", hsi_depth=bands, attention=att, first_depth=fd, bilinear=bil)
     else:
         net, schema = SpectralUNET(bands, 1, bn_feats=feats), O.spectral_schema(bands, 1, feats)
     sd = O.synth_state_dict(schema, seed)
@@ -85,14 +86,15 @@ def test_train_step_parity_vs_oracle(model, n, bands, h, w, feats):
     ("cubenet_1x238x48x72", "CubeNET", 1, 238, 48, 72, 2, 0), ("spectral32_2x238x6x10", "SpectralUNET", 2, 238, 6, 10, 3, 32),
     ("spectral1650_2x238x4x5", "SpectralUNET", 2, 238, 4, 5, 4, 1650),
     ("unet_att_2x3x32x40", "UNET", 2, 3, 32, 40, 5, 0), ("cubenet_att_2x238x34x42", "CubeNET", 2, 238, 34, 42, 6, 0),
-    ("cubenet_fd32_2x238x32x40", "CubeNET", 2, 238, 32, 40, 7, 0), ("cubenet_fd128_att_1x238x34x42", "CubeNET", 1, 238, 34, 42, 8, 0)])
+    ("cubenet_fd32_2x238x32x40", "CubeNET", 2, 238, 32, 40, 7, 0), ("cubenet_fd128_att_1x238x34x42", "CubeNET", 1, 238, 34, 42, 8, 0),
+    ("unet_bil_2x3x34x42", "UNET", 2, 3, 34, 42, 9, 0), ("cubenet_bil_att_2x238x32x40", "CubeNET", 2, 238, 32, 40, 10, 0)])
 @pytest.mark.parametrize("mode", ["train", "eval"])
 def test_against_reference_golden(name, model, n, bands, h, w, seed, feats, mode):
     """Reference-module outputs (tests/golden, made by oracle/gen_golden.py).  These shapes are tiny (BatchNorm over
     as few as 8 samples), so the tolerance is 3e-2 of max|logit| here; realistic sizes are held to 1e-2 above."""
     g = np.load(os.path.join(GOLD, name + ".npz"))
     fd = int(name.split("_fd")[1].split("_")[0]) if "_fd" in name else 64
-    net, _ = build(model, bands, feats, seed, att="_att_" in name, fd=fd)
+    net, _ = build(model, bands, feats, seed, att="_att_" in name, fd=fd, bil="_bil_" in name)
     x = O.synth_cube(seed, n, bands, h, w)
     xin = x[:, None] if model == "CubeNET" else x
     mask = O.synth_mask(seed, n, h, w)
@@ -266,3 +268,30 @@ def test_cubenet_first_depth_train_step_parity_vs_oracle(fd, att, h, w):
     for k, v in ostats.items():
         if "running_" in k:
             assert torch.allclose(bufs[k].cpu(), v, rtol=5e-3, atol=5e-4), k
+
+
+@pytest.mark.parametrize("model,att,h,w", [("UNET", False, 162, 210), ("CubeNET", False, 128, 176), ("UNET", True, 192, 272)])
+def test_bilinear_train_step_parity_vs_oracle(model, att, h, w):
+    """bilinear=True (model_parts.py:56-61; models.py:33,43-49): nn.Upsample(x2, bilinear, align_corners) in place of
+    the ConvTranspose, DoubleConvs with mid channels, down4 and the decoder outputs halved."""
+    bands = 3 if model == "UNET" else 238
+    net, sd = build(model, bands, att=att, bil=True)
+    assert not any(".up." in k for k in sd)                          # nn.Upsample has no parameters
+    assert sd["up1.conv.double_conv.3.weight"].shape == (256, 512, 3, 3)
+    x = O.synth_cube(3, 2, bands, h, w)
+    xin = x[:, None] if model == "CubeNET" else x
+    mask = O.synth_mask(3, 2, h, w)
+    torch.set_num_threads(os.cpu_count())
+    ol, oloss, og, ostats = O.forward_backward(model, xin, mask, sd, training=True, attention=att)
+    lg, loss = run_ours(net, xin, mask)
+    err = (lg - ol).abs()
+    assert err.max().item() <= (3e-2 if att else 1e-2) * ol.abs().max().item()
+    assert abs(loss - oloss.item()) < 2e-4
+    flat_o, flat_g = [], []
+    for k, p in net.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all() and p.grad.shape == og[k].shape, k
+        flat_o.append(og[k].flatten()); flat_g.append(p.grad.cpu().flatten())
+    assert cos(torch.cat(flat_g), torch.cat(flat_o)) > 0.97
+    for k in ("up1.conv.double_conv.0.weight", "up4.conv.double_conv.3.weight", "down4.maxpool_conv.1.double_conv.3.weight",
+              "down1.maxpool_conv.1.double_conv.0.weight"):
+        assert cos(dict(net.named_parameters())[k].grad.cpu(), og[k]) > 0.9, k

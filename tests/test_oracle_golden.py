@@ -20,15 +20,18 @@ CASES = {
     "cubenet_att_2x238x34x42": dict(model="CubeNET", n=2, h=34, w=42, bands=238, seed=6, attention=True),
     "cubenet_fd32_2x238x32x40": dict(model="CubeNET", n=2, h=32, w=40, bands=238, seed=7, first_depth=32),
     "cubenet_fd128_att_1x238x34x42": dict(model="CubeNET", n=1, h=34, w=42, bands=238, seed=8, first_depth=128, attention=True),
+    "unet_bil_2x3x34x42": dict(model="UNET", n=2, h=34, w=42, bands=3, seed=9, bilinear=True),
+    "cubenet_bil_att_2x238x32x40": dict(model="CubeNET", n=2, h=32, w=40, bands=238, seed=10, bilinear=True, attention=True),
 }
 
 
 def _inputs(c):
-    att = c.get("attention", False)
+    att, bil = c.get("attention", False), c.get("bilinear", False)
     if c["model"] == "UNET":
-        schema = O.unet_schema(c["bands"], 1, "unet", attention=att)
+        schema = O.unet_schema(c["bands"], 1, "unet", attention=att, bilinear=bil)
     elif c["model"] == "CubeNET":
-        schema = O.unet_schema(1, 1, "cube", hsi_depth=c["bands"], attention=att, first_depth=c.get("first_depth", 64))
+        schema = O.unet_schema(1, 1, "cube", hsi_depth=c["bands"], attention=att, first_depth=c.get("first_depth", 64),
+                               bilinear=bil)
     else:
         schema = O.spectral_schema(c["bands"], 1, c["feats"])
     sd = O.synth_state_dict(schema, c["seed"])
