@@ -336,7 +336,7 @@ def main():
                        "kernels": {k: {"ms_per_step": v[0], "launches_per_step": v[1] / prof_steps} for k, v in
                                    sorted(per.items(), key=lambda kv: -kv[1][0])},
                        "launches_last_step": [{"kernel": k, "args": d_, "ms": t} for k, d_, t in
-                                              per_launch[len(per_launch) // prof_steps:]]}, f, indent=1)
+                                              per_launch[len(per_launch) - len(per_launch) // prof_steps:]]}, f, indent=1)
 
     # ---------------- end to end through the public API with host inputs
     def run_e2e(host_dtype):
