@@ -563,8 +563,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
 // shared-memory address bits (tools/probes/umma_rowshift_probe.cu: any 128-byte row offset and
 // SBO = 1152 / 1280 read back exactly), so the TMA-written block is consumed in place.
 // Activation bytes per MAC drop 3x against per-shift loads, 6.6x against per-tap loads.
-// Two TMA rings: the A ring holds halo blocks (one per channel chunk, alive for three sub-steps), the
-// B ring the three weight tiles of one filter row.  Accumulators: 2 buffers x 2 halves x BLOCK_N TMEM
+// Two TMA rings: the A ring holds halo blocks (one per channel chunk, alive for nine taps), the
+// B ring one weight tap tile per slot.
+// PAIR = true (the default launch): a cluster of two CTAs on one TPC walks the list of pixel-tile pairs together and
+// the leader issues tcgen05.mma.cta_group::2 with M = 256 -- rows 0..127 are CTA 0's pixels, 128..255 CTA 1's, each
+// landing in its own CTA's TMEM.  Each CTA stages only HALF of every weight tile (rows rank*N/2 ...), so the shared-
+// memory operand reads per MMA drop from 4 KB + N*32 B to 4 KB + N*16 B per SM: the N = 64 MMA goes from 48 to 43
+// cycles (tools/probes/umma2_rate_probe.cu) and the weight fill traffic halves.  Both CTAs' loads complete on the
+// leader's full barriers (cp.async.bulk.tensor ... cta_group::2 with the barrier address mapped to rank 0), commits are
+// multicast to the same barrier offset in both CTAs, the peer's epilogue warps arrive remotely on the leader's
+// tmem_empty.  The cluster rank must ride in the same lane-0 broadcast as the warp index: read on its own it is not
+// treated as warp-uniform and every UTCHMMA ends up in an ELECT / BRA.U.ANY loop again.  Accumulators: 2 buffers x 2 halves x BLOCK_N TMEM
 // columns; epilogue group g owns half g.
 // Shared memory: [staging 2 x 16 KB][barriers][stats][A ring: 2 x a_bytes][B ring: p.stages x 3 weight tiles].
 // =====================================================================================
