@@ -370,6 +370,82 @@ hsi_ingest_k(const T* __restrict__ src, int bands_total, int H, int W, int lo, i
   }
 }
 
+// Vector variant (w, j0, W multiples of 4, no horizontal flip): one block = 128 consecutive pixels of a row; a thread
+// loads FOUR consecutive pixels of a band with one 16-byte (fp32) / 8-byte (fp16) load, for 8 bands, so a warp
+// instruction covers 512 contiguous bytes of a band plane instead of 128 (band planes are 2.35 MB apart: every
+// request opens another DRAM row, and longer runs per row are what the memory system rewards); the 8 x 4 values are
+// transposed in registers into four 16-byte pixel chunks.  Swizzle: chunk position q ^ ((px >> 2) & 7).
+__device__ __forceinline__ void ld4_src(const float* p, float (&v)[4]) {
+  const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+  v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+}
+__device__ __forceinline__ void ld4_src(const __half* p, float (&v)[4]) {
+  const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
+  v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+template <typename T, bool PLAIN>
+__global__ void __launch_bounds__(256)
+hsi_ingest_v4_k(const T* __restrict__ src, int bands_total, int H, int W, int lo, int nb, int i0, int j0, int h,
+                int w, int flip_h, float scale, const float* __restrict__ bmean, const float* __restrict__ bstd,
+                uint16_t* __restrict__ dst, int dt, int c_pad) {
+  grid_dep_launch();      // a following tcgen05 launch may start its prologue while this grid drains
+  extern __shared__ uint4 tile4[];               // [128 pixels][row_chunks] 16-byte chunks
+  const int chunks = c_pad >> 3;
+  const int row_chunks = (chunks + 7) & ~7;
+  const int xt = blockIdx.x, y = blockIdx.y, n = blockIdx.z;
+  const int x0 = xt * 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sy = i0 + (flip_h ? h - 1 - y : y);
+  const long long HW = (long long)H * W;
+  const T* img = src + ((long long)n * bands_total + lo) * HW + (long long)sy * W + j0 + x0 + 4 * lane;
+  const bool in = x0 + 4 * lane < w;             // w % 4 == 0: a vector is inside or outside as a whole
+  for (int q = warp; q < chunks; q += 8) {
+    float v[8][4];
+    const T* p = img + (long long)(q * 8) * HW;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (in && q * 8 + k < nb) ld4_src(p, v[k]);
+      else { v[k][0] = v[k][1] = v[k][2] = v[k][3] = 0.f; }
+      p += HW;
+    }
+    if (!PLAIN) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int b = q * 8 + k;
+        const float mu = (bmean != nullptr && b < nb) ? __ldg(bmean + b) : 0.f;
+        const float is = (bmean != nullptr && b < nb) ? 1.f / __ldg(bstd + b) : 1.f;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float a = v[k][e] * scale;
+          if (bmean != nullptr && b < nb) a = (a - mu) * is;
+          v[k][e] = b < nb ? a : 0.f;
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int px = 4 * lane + e;
+      uint4 o;
+      o.x = pack2(v[0][e], v[1][e], dt); o.y = pack2(v[2][e], v[3][e], dt);
+      o.z = pack2(v[4][e], v[5][e], dt); o.w = pack2(v[6][e], v[7][e], dt);
+      tile4[px * row_chunks + (q ^ ((px >> 2) & 7))] = o;
+    }
+  }
+  __syncthreads();
+  const int npix = min(128, w - x0);
+  uint4* out = reinterpret_cast<uint4*>(dst + (((long long)n * h + y) * w + x0) * c_pad);
+  const int total = npix * chunks;
+  int px = threadIdx.x / chunks, q = threadIdx.x - px * chunks;
+  const int dpx = 256 / chunks, dq = 256 - dpx * chunks;
+  for (int i = threadIdx.x; i < total; i += 256) {
+    out[i] = tile4[px * row_chunks + (q ^ ((px >> 2) & 7))];
+    px += dpx; q += dq;
+    if (q >= chunks) { q -= chunks; ++px; }
+  }
+}
+
 __global__ void absmax_k(const float* __restrict__ x, long long n, float* out) {
   float m = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -1343,9 +1419,25 @@ static int ingest_launch(const T* src, int n, int bands_total, int H, int W, int
   static bool attr_done = false;
   if (!attr_done) {
     if (cudaFuncSetAttribute(hsi_ingest_k<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(hsi_ingest_k<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
+        cudaFuncSetAttribute(hsi_ingest_k<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(hsi_ingest_v4_k<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(hsi_ingest_v4_k<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) != cudaSuccess)
       return HPRI_ERR_CUDA;
     attr_done = true;
+  }
+  // 4-pixel vector loads when every row segment is vector-aligned (HPRI_INGEST_V4=0 keeps the scalar kernel)
+  static int v4 = -1;
+  if (v4 < 0) { const char* e = getenv("HPRI_INGEST_V4"); v4 = (e && atoi(e) == 0) ? 0 : 1; }
+  if (v4 && !flip_w && (w & 3) == 0 && (j0 & 3) == 0 && (W & 3) == 0 && 2 * smem <= 100 * 1024 &&
+      (reinterpret_cast<uintptr_t>(src) & 15) == 0 && ((long long)H * W & 3) == 0) {
+    dim3 g4((w + 127) / 128, h, n);
+    if (plain)
+      hsi_ingest_v4_k<T, true><<<g4, 256, 2 * smem, (cudaStream_t)stream>>>(src, bands_total, H, W, lo, nb, i0, j0, h, w, flip_h,
+                                                                            scale, band_mean, band_std, (uint16_t*)dst, dst_dtype, c_pad);
+    else
+      hsi_ingest_v4_k<T, false><<<g4, 256, 2 * smem, (cudaStream_t)stream>>>(src, bands_total, H, W, lo, nb, i0, j0, h, w, flip_h,
+                                                                             scale, band_mean, band_std, (uint16_t*)dst, dst_dtype, c_pad);
+    return last_err();
   }
   dim3 grid((w + 63) / 64, h, n);
   if (plain)
