@@ -25,3 +25,15 @@ def pytest_collection_modifyitems(config, items):
     for it in items:
         if "gpu" in it.keywords:
             it.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _seed_torch_rng():
+    """Every test starts from the same torch RNG state (CPU and CUDA): inputs drawn with torch.rand / randn inside a
+    test do not depend on which tests ran before it, so a borderline draw cannot make the suite order-dependent."""
+    try:
+        import torch
+        torch.manual_seed(20241018)            # seeds the CUDA generators too
+    except Exception:
+        pass
+    yield
