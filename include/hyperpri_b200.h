@@ -85,7 +85,9 @@ int hpri_igemm_fwd(const hpri_view_t* x, const void* wpack, int w_dtype, int w_r
  * (which is what the fused `bw` reduction needs), 0 when it falls to the generic per-tap kernel. */
 int hpri_conv3x3_halo_ok(int h, int w, int w_rows);
 
-/* 3x3 kernel selection: -1 heuristic (default), 0 generic per-tap kernel, 1 halo-reuse kernel. */
+/* 3x3 kernel selection: -1 heuristic (default: halo-reuse kernel on CTA pairs -- tcgen05 cta_group::2, M = 256 --
+ * except the 64-channel dgrads carrying the fused `bw` reduction, which stay on single CTAs), 0 generic per-tap kernel,
+ * 1 halo-reuse kernel on single CTAs, 2 CTA pairs everywhere.  Seeded by the environment variable HPRI_CONV_ALGO. */
 int hpri_set_conv_algo(int algo);
 
 /* nn.ConvTranspose2d(k=2,s=2) fprop writing straight into the concat buffer (model_parts.py:63-64,
