@@ -20,6 +20,7 @@ from torch.utils.data import DataLoader
 from .. import metrics as M
 from .. import parallel
 from ..prefetch import DevicePrefetcher
+from ..zero_ckpt import consolidate_deepspeed_two   # noqa: F401  (the reference exposes it here, PLTrainer.py:186)
 from .Experiments.models import *        # noqa: F401,F403  (the reference re-exports the models here, :26)
 
 try:                                     # optional: real Lightning
@@ -180,7 +181,9 @@ def load_val_model(params, device=None):
         if not cand:
             cand = [os.path.join(ck_dir, f) for f in os.listdir(ck_dir)]
     wts = os.path.join(params.save_path, 'best_wts.pt')
-    if cand:
+    if cand and os.path.isdir(cand[-1]):          # a DeepSpeed ZeRO-2 checkpoint directory (PLTrainer.py:297-307)
+        model.m_network.load_state_dict(consolidate_deepspeed_two(cand[-1]))
+    elif cand:
         ck = torch.load(cand[-1], map_location="cpu")
         sd = ck.get("state_dict", ck)
         sd = {k.replace("_forward_module.", ""): v for k, v in sd.items()}

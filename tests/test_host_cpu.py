@@ -186,3 +186,55 @@ def test_device_prefetcher_is_a_passthrough_on_cpu():
     out = list(DevicePrefetcher(batches, "cpu"))
     assert len(out) == 3 and all(o is b for o, b in zip(out, batches))
     assert len(DevicePrefetcher(batches, "cpu")) == 3
+
+
+def _write_zero2_dir(root, sd, buffer_names, world, groups=2, tag="checkpoint"):
+    """A directory in the DeepSpeed ZeRO-2 layout hyperpri_b200/zero_ckpt.py documents (synthetic: no DeepSpeed here)."""
+    from collections import OrderedDict
+    d = os.path.join(root, tag)
+    os.makedirs(d)
+    with open(os.path.join(root, "latest"), "w") as f:
+        f.write(tag)
+    params = [(k, v) for k, v in sd.items() if k not in buffer_names]
+    cut = len(params) // groups
+    grp = [params[:cut], params[cut:]] if groups == 2 else [params]
+    shapes = [OrderedDict((k, v.shape) for k, v in g) for g in grp]
+    torch.save({"module": {k: (v.half() if v.dtype.is_floating_point else v) for k, v in sd.items()},
+                "buffer_names": list(buffer_names), "param_shapes": shapes, "shared_params": {}, "ds_version": "0.14.2"},
+               os.path.join(d, "mp_rank_00_model_states.pt"))
+    parts = [[] for _ in range(world)]
+    for g in grp:
+        flat = torch.cat([v.reshape(-1).float() for _, v in g])
+        pad = (-flat.numel()) % (2 * world)
+        flat = torch.cat([flat, torch.zeros(pad)])
+        for r, chunk in enumerate(flat.chunk(world)):
+            parts[r].append(chunk.clone())
+    for r in range(world):
+        torch.save({"optimizer_state_dict": {"zero_stage": 2, "partition_count": world,
+                                             "single_partition_of_fp32_groups": parts[r]}},
+                   os.path.join(d, f"bf16_zero_pp_rank_{r}_mp_rank_00_optim_states.pt"))
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_zero2_checkpoint_directory_import(tmp_path, world):
+    """consolidate_deepspeed_two (PLTrainer.py:186-216) on a directory written to the documented ZeRO-2 layout: fp32
+    masters come back exactly (not the 16-bit "module" copies), buffers are kept, keys lose the Lightning prefix."""
+    from hyperpri_b200.zero_ckpt import consolidate_deepspeed_two, fp32_state_dict_from_zero2
+    net = mdl.SpectralUNET(238, 1, bn_feats=24)
+    sd = {k: (torch.randn_like(v) if v.dtype.is_floating_point else v + 3) for k, v in net.state_dict().items()}
+    pref = {"_forward_module.m_network." + k: v for k, v in sd.items()}
+    buffers = [k for k in pref if "running_" in k or "num_batches" in k]
+    _write_zero2_dir(str(tmp_path), pref, buffers, world)
+    got = consolidate_deepspeed_two(str(tmp_path))
+    assert set(got) == set(sd)
+    for k, v in sd.items():
+        if "running_" in k:
+            assert torch.equal(got[k], v.half().float()), k        # buffers live in the 16-bit module copy
+        else:
+            assert torch.equal(got[k], v), k
+    net.load_state_dict(got)
+    full = fp32_state_dict_from_zero2(str(tmp_path), tag="checkpoint")
+    assert all(k.startswith("_forward_module.m_network.") for k in full)
+    os.remove(os.path.join(str(tmp_path), "checkpoint", f"bf16_zero_pp_rank_{world - 1}_mp_rank_00_optim_states.pt"))
+    with pytest.raises((ValueError, FileNotFoundError)):
+        consolidate_deepspeed_two(str(tmp_path))
