@@ -238,3 +238,44 @@ def test_zero2_checkpoint_directory_import(tmp_path, world):
     os.remove(os.path.join(str(tmp_path), "checkpoint", f"bf16_zero_pp_rank_{world - 1}_mp_rank_00_optim_states.pt"))
     with pytest.raises((ValueError, FileNotFoundError)):
         consolidate_deepspeed_two(str(tmp_path))
+
+
+@pytest.mark.parametrize("kind,kw", [
+    ("UNET", {}), ("UNET", {"use_attention": True}), ("UNET", {"bilinear": True}), ("UNET", {"bilinear": True, "use_attention": True}),
+    ("CubeNET", {}), ("CubeNET", {"first_depth": 16}), ("CubeNET", {"first_depth": 128, "use_attention": True}),
+    ("CubeNET", {"bilinear": True}), ("CubeNET", {"use_attention": True}),
+])
+def test_engine_channel_plan_matches_parameters(kind, kw):
+    """Host-side plan of UNetEngine for every constructor-flag combination (no kernels run: the engine is built on the
+    CPU device): each conv unit's (cin, cout) equals its parameter's shape, the flat gradient arena holds every
+    parameter exactly once and the nine buckets tile it in backward-completion order."""
+    from hyperpri_b200 import engine as E
+    kw = dict({"bilinear": False}, **kw)
+    net = mdl.UNet(3, 1, **kw) if kind == "UNET" else mdl.CubeNET(238, 1, **kw)
+    table = net._tensor_table()
+    eng = E.UNetEngine(table, "unet" if kind == "UNET" else "cube", 3 if kind == "UNET" else 238, torch.device("cpu"),
+                       attention=kw.get("use_attention", False), first_depth=kw.get("first_depth", 64),
+                       bilinear=kw["bilinear"])
+    assert eng._side is None                                           # no side stream without CUDA
+    units = [L for grp in list(eng.enc) + [eng.dec[l] for l in range(4)] for L in grp]
+    assert len(units) == 18
+    for L in units:
+        w = table[L.conv + ".weight"]
+        cin_true = getattr(L, "true_cin", L.cin)
+        got = (w.shape[0], w.shape[1] * (w.shape[2] if w.dim() == 5 else 1))
+        assert got == (L.cout, cin_true), (L.conv, tuple(w.shape), L.cin, L.cout)
+        assert table[L.bn + ".weight"].shape == (L.cout,)
+    if kw["bilinear"]:
+        assert not eng.up and eng.CE[4] == 512 and eng.D == [64, 64, 128, 256]
+    else:
+        for l, up in eng.up.items():
+            w = table[eng.up_name[l] + ".weight"]
+            assert tuple(w.shape) == (up.spec.cin, up.spec.cout, 2, 2), (l, tuple(w.shape))
+    names = {k for k, p in net.named_parameters()}
+    arena_names = set(eng.grads)
+    alias = {"inc.0.weight", "inc.0.bias"} if kind == "CubeNET" else set()
+    assert arena_names | alias >= names and arena_names <= names | alias
+    assert eng.arena.numel() == sum(p.numel() for p in net.parameters())
+    b = eng.bucket_bounds
+    assert len(b) == 9 and b[0][0] == 0 and b[-1][1] == eng.arena.numel()
+    assert all(b[i][1] == b[i + 1][0] and b[i][1] > b[i][0] for i in range(8))
