@@ -11,7 +11,8 @@ For N > 1 launch with torchrun (one rank per GPU, NCCL).  Rank 0 prints ONE JSON
             a D2H read of the loss inside the timed region (double-buffered copy stream)
   roofline  the tcgen05 implicit-GEMM family (every conv / convT fwd, dgrad, wgrad launch): algorithmic FLOPs per
             step / summed CUDA-event durations of those launches, against the measured sustained bf16 peak
-  cpu_baseline  the CPU oracle (a port of the reference's arithmetic) on this box's host cores, bounded sample
+  cpu_baseline  the reference's own model code (oracle/_ref, staged by oracle/build_ref.py) on this box's host cores,
+            same batch and frame, bounded number of steps (falls back to the oracle port when the copy is not staged)
 --impl reference times that CPU path alone (the reference is pure Python/PyTorch).
 """
 import argparse
@@ -111,59 +112,97 @@ WORKLOAD = {
 
 
 # ------------------------------------------------------------------------------------------- CPU arm
-def cpu_steps(model, n_img, h, w, steps, warmup, train=True):
-    """Time `steps` passes (fwd+loss+bwd, or eval-mode forward) of the CPU oracle on n_img x bands x h x w."""
-    import torch
+# The CPU leg times the REFERENCE's own modules (oracle/_ref, staged by oracle/build_ref.py from
+# /root/reference/src/Experiments/{models,model_parts}.py; kind "reference") at the benchmark's own batch and frame:
+# batch 2, full 608 rows, fp32, all host threads.  Without the staged copy it falls back to the oracle port (kind
+# "port").  SpectralUNET-1650 needs ~146 GB for batch 2 at full width, so it runs on a fixed 608 x 70 strip (1/10 of
+# the pixels of the 608 x 700 patch; the network is per-pixel) and the throughput is scaled by the pixel fraction.
+CPU_STRIP_W = {"CubeNET": 968, "UNET": 968, "SpectralUNET": 70}
+
+
+def _load_reference():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import hyperpri_oracle as O
+    try:
+        import build_ref
+        return build_ref.load_ref()
+    except Exception:
+        return None
+
+
+def cpu_runner(model, n_img, train=True):
+    """Returns (step_fn, kind, pixel_fraction, description): step_fn() runs one fwd+loss+bwd (or eval forward + loss)
+    over n_img images on the host."""
+    import torch
     torch.set_num_threads(os.cpu_count())
+    Wp, ws = PATCH_W[model], CPU_STRIP_W[model]
+    frac = ws / Wp
+    bands = 3 if model == "UNET" else BANDS
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand((n_img, bands, H, ws), generator=g)
+    mask = (torch.rand((n_img, 1, H, ws), generator=g) > 0.95).float()
+    what = "fwd+loss+bwd, train mode" if train else "eval-mode forward + loss"
+    shape = f"{n_img} x {bands} x {H} x {ws}" + ("" if frac == 1.0 else f" ({ws}/{Wp} of the patch columns; per-pixel network, throughput scaled by the pixel fraction)")
+    ref = _load_reference()
+    if ref is not None:
+        if model == "CubeNET":
+            net, xin = ref.CubeNET(BANDS, 1, first_depth=64, bilinear=False), x[:, None]
+        elif model == "UNET":
+            net, xin = ref.UNet(3, 1, bilinear=False), x
+        else:
+            net, xin = ref.SpectralUNET(BANDS, 1, bn_feats=1650), x
+        net.train(train)
+        crit = torch.nn.BCEWithLogitsLoss()
+
+        def step():
+            if train:
+                net.zero_grad(set_to_none=True)
+                crit(net(xin), mask).backward()
+            else:
+                with torch.no_grad():
+                    crit(net(xin), mask)
+        return step, "reference", frac, f"reference modules (oracle/_ref), fp32, {shape}, {what}"
+    import hyperpri_oracle as O
     if model == "CubeNET":
-        schema, bands = O.unet_schema(1, 1, "cube", hsi_depth=BANDS), BANDS
+        schema, xin = O.unet_schema(1, 1, "cube", hsi_depth=BANDS), x[:, None]
     elif model == "UNET":
-        schema, bands = O.unet_schema(3, 1, "unet"), 3
+        schema, xin = O.unet_schema(3, 1, "unet"), x
     else:
-        schema, bands = O.spectral_schema(BANDS, 1, 1650), BANDS
+        schema, xin = O.spectral_schema(BANDS, 1, 1650), x
     sd = O.synth_state_dict(schema, 0)
-    x = O.synth_cube(0, n_img, bands, h, w)
-    x = x[:, None] if model == "CubeNET" else x
-    mask = O.synth_mask(0, n_img, h, w)
-    times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
+
+    def step():
         if train:
-            O.forward_backward(model, x, mask, sd, training=True)
+            O.forward_backward(model, xin, mask, sd, training=True)
         else:
             with torch.no_grad():
-                O.bce_with_logits(O.FORWARDS[model](x, sd, False, None), mask)
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
-    return times
+                O.bce_with_logits(O.FORWARDS[model](xin, sd, False, None), mask)
+    return step, "port", frac, f"oracle port (oracle/_ref not staged), fp32, {shape}, {what}"
 
 
-def cpu_sample(model, train, steps, warmup, budget_s):
-    """Bounded CPU sample of the same workload: one image per step, cut to a strip of rows (conv nets) or columns'
-    worth of pixels (SpectralUNET is per-pixel) so that all steps fit `budget_s`; throughput is scaled by the pixel
-    fraction.  Returns (images/s, seconds per step, description)."""
-    Wp = PATCH_W[model]
-    probe_rows = 16 if model == "SpectralUNET" else 64
-    t_probe = cpu_steps(model, 1, probe_rows, Wp, 1, 0, train)[0]
-    est_full = t_probe * H / probe_rows
-    rows = H
-    if est_full * (steps + warmup) > budget_s:
-        rows = max(probe_rows, int(H * budget_s / (est_full * (steps + warmup))) // 16 * 16)
-    times = cpu_steps(model, 1, rows, Wp, steps, warmup, train)
+def cpu_time(model, n_img, train, steps, warmup, budget_s):
+    """Time up to `steps` steps after `warmup` untimed ones; the step COUNT (never the frame) is cut so that the whole
+    run fits `budget_s`.  Returns (images/s, seconds per step, steps timed, kind, description)."""
+    step, kind, frac, desc = cpu_runner(model, n_img, train)
+    t0 = time.perf_counter()
+    step()                                            # first call: also the first warm-up step
+    t_first = time.perf_counter() - t0
+    warm = max(0, min(warmup, 1) - 1)                 # one warm-up step is what fits; it has just run
+    for _ in range(warm):
+        step()
+    n_steps = max(1, min(steps, int((budget_s - t_first * (1 + warm)) / max(t_first, 1e-3))))
+    times = []
+    for _ in range(n_steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
     sec = sum(times) / len(times)
-    bands = 3 if model == "UNET" else BANDS
-    what = "fwd+loss+bwd, train mode" if train else "eval-mode forward + loss"
-    sample = (f"{steps} step(s) of 1 image x {bands} x {rows} x {Wp} ({rows}/{H} of the rows of one image; throughput "
-              f"scaled by pixel count), fp32 oracle, {what}")
-    return (rows / H) / sec, sec, sample
+    return n_img * frac / sec, sec, n_steps, kind, desc
 
 
-def cpu_baseline(model, train):
-    v, _, sample = cpu_sample(model, train, 3, 1, 25.0)
-    return {"value": v, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": sample}
+def cpu_baseline(model, train, n_img):
+    v, sec, n_steps, kind, desc = cpu_time(model, n_img, train, 2, 1, 30.0)
+    return {"value": v, "unit": "images/s", "cores": os.cpu_count(), "kind": kind,
+            "sample": f"{n_steps} timed step(s) after 1 warm-up, {sec:.2f} s/step: {desc}"}
 
 
 def run_reference(args):
@@ -172,15 +211,17 @@ def run_reference(args):
         return
     import torch
     train = args.mode == "train"
-    img_s, sec, sample = cpu_sample(args.model, train, args.steps, args.warmup, 150.0)
+    n = args.batch
+    img_s, sec, n_steps, kind, desc = cpu_time(args.model, n, train, args.steps, args.warmup, 170.0)
     line = {
         "impl": "reference", "metric": METRIC[args.mode], "value": img_s, "unit": "images/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "n_gpus": args.gpus, "steps": n_steps, "steps_requested": args.steps, "warmup": 1, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD[args.model].format(n=1) + " -- CPU, reference arithmetic (oracle port: the "
-                               "reference is pure PyTorch + Lightning and cannot be installed offline or travel to "
-                               "the GPU box)", "threads": torch.get_num_threads(), "mode": args.mode},
-        "cpu_baseline": {"value": img_s, "unit": "images/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD[args.model].format(n=n), "global_batch": n, "parallelism": "cpu", "mode": args.mode,
+                   "reference_arm": f"{desc}; {torch.get_num_threads()} host threads; the step count (not the frame) is "
+                                    f"cut to fit the time budget: {n_steps} of the requested {args.steps} steps"},
+        "cpu_baseline": {"value": img_s, "unit": "images/s", "cores": os.cpu_count(), "kind": kind,
+                         "sample": f"{n_steps} timed step(s) after 1 warm-up, {sec:.2f} s/step: {desc}"},
         "e2e": {"value": img_s, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -387,7 +428,7 @@ def main():
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_base = cpu_baseline(args.model, train)
+        cpu_base = cpu_baseline(args.model, train, n)
 
     if rank == 0:
         line = {

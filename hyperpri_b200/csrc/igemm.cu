@@ -1375,6 +1375,12 @@ extern "C" int hpri_set_conv_algo(int algo) {
   return HPRI_OK;
 }
 
+extern "C" int hpri_set_wgrad_algo(int algo) {
+  if (algo < -1 || algo > 0) return HPRI_ERR_ARG;
+  g_wgrad_algo = algo;
+  return HPRI_OK;
+}
+
 // -------------------------------------------------------------------------------------
 // C ABI
 // -------------------------------------------------------------------------------------

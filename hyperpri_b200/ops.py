@@ -252,8 +252,14 @@ def bn_fin(count, gamma, beta, conv_bias, rmean, rvar, nbt, scale, shift, smean,
 
 
 def set_conv_algo(algo: int):
-    """-1 heuristic, 0 generic per-tap kernel, 1 halo-reuse kernel (tests / benchmarks)."""
+    """-1 heuristic, 0 generic per-tap kernel, 1 halo-reuse kernel on single CTAs, 2 halo-reuse kernel on CTA pairs
+    (tests / benchmarks)."""
     check(_lib.lib().hpri_set_conv_algo(int(algo)), "hpri_set_conv_algo")
+
+
+def set_wgrad_algo(algo: int):
+    """-1 heuristic (halo-reuse weight-gradient kernel where it applies), 0 generic per-tap kernel only."""
+    check(_lib.lib().hpri_set_wgrad_algo(int(algo)), "hpri_set_wgrad_algo")
 
 
 @_timed

@@ -89,6 +89,9 @@ int hpri_conv3x3_halo_ok(int h, int w, int w_rows);
  * except the 64-channel dgrads carrying the fused `bw` reduction, which stay on single CTAs), 0 generic per-tap kernel,
  * 1 halo-reuse kernel on single CTAs, 2 CTA pairs everywhere.  Seeded by the environment variable HPRI_CONV_ALGO. */
 int hpri_set_conv_algo(int algo);
+/* 3x3 weight-gradient kernel selection: -1 heuristic (halo-reuse weight-gradient kernel at Cout 64 / 128), 0 generic
+ * per-tap kernel only.  Seeded by the environment variable HPRI_WGRAD_ALGO. */
+int hpri_set_wgrad_algo(int algo);
 
 /* nn.ConvTranspose2d(k=2,s=2) fprop writing straight into the concat buffer (model_parts.py:63-64,
  * 74-87: pad + cat are absorbed by the destination view) and its dgrad. */

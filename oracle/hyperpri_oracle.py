@@ -351,6 +351,63 @@ def spectralunet_forward(x, sd, training=True, stats_out=None):
     return torch.stack(outs, 0)
 
 
+def spectralunet_forward_streaming(x, sd, chunk: int = 16384):
+    """Train-mode SpectralUNET forward (models.py:117-145) for full-width patches without an autograd graph:
+    every block is evaluated over row chunks of the pixel matrix, the per-image BatchNorm1d statistics are
+    accumulated chunk-wise in fp64 (two passes: statistics, then normalise in place), so the peak memory is the
+    five skip tensors plus one pre-activation buffer (~17 GB fp32 per 608 x 700 image at 1650 features) instead of the
+    146 GB the autograd version needs for batch 2.  Returns logits N x 1 x R x C; running statistics are not
+    advanced (forward check only).  tests/test_oracle_golden.py holds it to spectralunet_forward on small cases."""
+    n, d, r, c = x.shape
+    m = r * c
+    outs = []
+    with torch.no_grad():
+        def blk(parts, nm):
+            """parts: list of [m, f_i] tensors whose concatenation (models.py:140-143) is the block input."""
+            w, b = sd[nm + ".0.weight"], sd[nm + ".0.bias"]
+            ws, o = [], 0
+            for t in parts:
+                ws.append(w[:, o:o + t.shape[1]])
+                o += t.shape[1]
+            pre = torch.empty((m, w.shape[0]), dtype=torch.float32)
+            s1 = torch.zeros(w.shape[0], dtype=torch.float64)
+            s2 = torch.zeros(w.shape[0], dtype=torch.float64)
+            for i in range(0, m, chunk):
+                y = b + sum(t[i:i + chunk] @ wi.t() for t, wi in zip(parts, ws))
+                pre[i:i + chunk] = y
+                yd = y.double()
+                s1 += yd.sum(0)
+                s2 += (yd * yd).sum(0)
+            mean = s1 / m
+            var = (s2 / m - mean * mean).clamp_min(0)
+            scale = (sd[nm + ".1.weight"].double() / torch.sqrt(var + BN_EPS)).float()
+            shift = (sd[nm + ".1.bias"].double() - mean * scale.double()).float()
+            for i in range(0, m, chunk):
+                pre[i:i + chunk] = torch.relu(pre[i:i + chunk] * scale + shift)
+            return pre
+
+        rast = x.reshape(n, d, m).permute(0, 2, 1)
+        for i in range(n):
+            x0 = blk([rast[i].contiguous()], "tail")
+            x1 = blk([x0], "down1")
+            x2 = blk([x1], "down2")
+            x3 = blk([x2], "down3")
+            x4 = blk([x3], "down4")
+            t = blk([x4], "up1")
+            del x4
+            t = blk([x3, t], "up2")
+            del x3
+            t = blk([x2, t], "up3")
+            del x2
+            t = blk([x1, t], "up4")
+            del x1
+            wo = sd["outc.weight"]
+            f = x0.shape[1]
+            lg = x0 @ wo[:, :f].t() + t @ wo[:, f:].t() + sd["outc.bias"]
+            outs.append(lg.reshape(-1, r, c))
+    return torch.stack(outs, 0)
+
+
 def bce_with_logits(pred, target):
     """BCEWithLogitsLoss(), mean reduction (params_HyperPRI.py:60,223; PLTrainer.py:86):
     mean(max(x,0) - x t + log1p(exp(-|x|)))."""

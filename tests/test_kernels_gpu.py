@@ -57,11 +57,21 @@ CONV_CASES = [
 ]
 
 
-@pytest.fixture(params=[0, 1], ids=["generic", "halo"])
+@pytest.fixture(params=[0, 1, 2, -1], ids=["generic", "halo", "halo_pair", "default"])
 def conv_algo(request):
+    """Every 3x3 kernel the launcher can pick: generic per-tap, halo-reuse on single CTAs, halo-reuse on CTA pairs
+    (tcgen05 cta_group::2 -- what the heuristic picks for every production layer), and the heuristic itself."""
     ops.set_conv_algo(request.param)
     yield request.param
     ops.set_conv_algo(-1)
+
+
+@pytest.fixture(params=[-1, 0], ids=["wgrad_default", "wgrad_generic"])
+def wgrad_algo(request):
+    """Weight gradients with the halo-reuse kernel allowed (the production choice at Cout 64 / 128) and forced off."""
+    ops.set_wgrad_algo(request.param)
+    yield request.param
+    ops.set_wgrad_algo(-1)
 
 
 HALO_CASES = [(2, 32, 24, 64, 64, 0), (1, 40, 50, 128, 64, 0), (1, 33, 70, 240, 64, 0), (2, 16, 33, 64, 128, 0),
@@ -106,8 +116,8 @@ def test_conv3x3_dgrad(n, h, w, cin, cout, bn, conv_algo):
 
 
 @pytest.mark.parametrize("xdt,gdt", [(BF, BF), (FH, FH)])
-@pytest.mark.parametrize("n,h,w,cin,cout,bn", CONV_CASES)
-def test_conv3x3_wgrad(n, h, w, cin, cout, bn, xdt, gdt):
+@pytest.mark.parametrize("n,h,w,cin,cout,bn", CONV_CASES + HALO_CASES)
+def test_conv3x3_wgrad(n, h, w, cin, cout, bn, xdt, gdt, wgrad_algo):
     """Both operands of one tcgen05.mma kind::f16 must share a format (mixed f16 x bf16 faults on B200)."""
     x = rnd(n, cin, h, w, seed=5)
     dy = rnd(n, cout, h, w, seed=6)

@@ -49,6 +49,15 @@ def cos(a, b):
     return (a.flatten().double() @ b.flatten().double() / (a.norm().double() * b.norm().double() + 1e-300)).item()
 
 
+def record(**kw):
+    """Measured parity figures -> gpurun_out/parity_records.jsonl (when run on the GPU box), for profiles/."""
+    import json
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "parity_records.jsonl"), "a") as f:
+            f.write(json.dumps(kw) + "\n")
+
+
 CASES = [("UNET", 2, 3, 96, 136, 1650), ("CubeNET", 2, 238, 96, 136, 1650), ("CubeNET", 1, 238, 80, 104, 1650),
          ("SpectralUNET", 2, 238, 24, 40, 1650), ("SpectralUNET", 1, 238, 16, 33, 96)]
 
@@ -63,10 +72,16 @@ def test_train_step_parity_vs_oracle(model, n, bands, h, w, feats):
     ol, oloss, og, ostats = O.forward_backward(model, xin, mask, sd, training=True)
     lg, loss = run_ours(net, xin, mask)
     assert lg.shape == ol.shape and lg.dtype == torch.float32
+    record(test="train_step_parity_vs_oracle", model=model, shape=[n, bands, h, w], feats=feats,
+           logit_max_rel_err=(lg - ol).abs().max().item() / ol.abs().max().item(),
+           mask_agreement=((lg > 0) == (ol > 0)).float().mean().item())
     assert (lg - ol).abs().max().item() <= 1e-2 * ol.abs().max().item()
-    # north_star asks >= 99.9 %: met at BASELINE size (profiles/parity_r1.json); at these small random-init shapes a
-    # larger share of logits sits inside the rounding band around 0 and run-to-run atomics order moves it by 1e-4
-    assert ((lg > 0) == (ol > 0)).float().mean().item() >= 0.998
+    # north_star's >= 99.9 % is asserted at BASELINE size in tests/test_zz_full_size_gpu.py.  At these small shapes the
+    # bound is looser for a reason the oracle itself shows: rounding its own stored tensors to fp16 (emulate_bf16_storage)
+    # flips 0.084 % of the 96 x 136 CubeNET masks against its fp32 self (22 of 26112 pixels), so 99.9 % would leave a
+    # margin of four pixels; 960-pixel cases cannot even express 99.9 %.  At most 0.2 % (or 3 pixels) may differ here.
+    flips = ((lg > 0) != (ol > 0)).sum().item()
+    assert flips <= max(3, 2e-3 * lg.numel())
     assert abs(loss - oloss.item()) < 2e-4
     flat_o, flat_g = [], []
     for k, p in net.named_parameters():
@@ -101,6 +116,8 @@ def test_against_reference_golden(name, model, n, bands, h, w, seed, feats, mode
     with torch.set_grad_enabled(mode == "train"):
         lg, loss = run_ours(net, xin, mask, train=(mode == "train"))
     ref = torch.from_numpy(g[f"{mode}.logits"])
+    record(test="against_reference_golden", name=name, mode=mode,
+           logit_max_rel_err=(lg - ref).abs().max().item() / ref.abs().max().item(), loss_abs_err=abs(loss - float(g[f"{mode}.loss"])))
     assert (lg - ref).abs().max().item() <= 3e-2 * ref.abs().max().item()
     assert abs(loss - float(g[f"{mode}.loss"])) < 2e-3
 
@@ -295,3 +312,57 @@ def test_bilinear_train_step_parity_vs_oracle(model, att, h, w):
     for k in ("up1.conv.double_conv.0.weight", "up4.conv.double_conv.3.weight", "down4.maxpool_conv.1.double_conv.3.weight",
               "down1.maxpool_conv.1.double_conv.0.weight"):
         assert cos(dict(net.named_parameters())[k].grad.cpu(), og[k]) > 0.9, k
+
+
+@pytest.mark.parametrize("model,n,bands,h,w", [("CubeNET", 2, 238, 96, 136), ("UNET", 2, 3, 128, 160)])
+def test_gradients_per_parameter_vs_storage_emulating_oracle(model, n, bands, h, w):
+    """Per-parameter gradient error against the oracle run with the B200 path's storage precision emulated (fp16
+    activations / weights, fp16 gradients under the engine's power-of-two loss scale), with a bound calibrated by the
+    oracle itself: random-init ReLU networks have non-smooth, cancellation-dominated gradients -- perturbing the INPUT
+    of the fp32 oracle by 1e-4 (2e-4 relative) already moves its own per-parameter gradients by ~10 % (median), which
+    is why no tight absolute bound exists at the whole-network level (the per-kernel tests in test_kernels_gpu.py hold
+    dgrad / wgrad / BatchNorm-backward to 2e-4 .. 6e-3).  Asserted here, per parameter tensor:
+        relL2(ours, emulated oracle) <= max(0.08, 2.5 * relL2(perturbed fp32 oracle, fp32 oracle)),
+    plus a hard ceiling of 0.35 and a global cosine > 0.97."""
+    import math
+    net, sd = build(model, bands)
+    x = O.synth_cube(0, n, bands, h, w)
+    xin = x[:, None] if model == "CubeNET" else x
+    mask = O.synth_mask(0, n, h, w)
+    torch.set_num_threads(os.cpu_count())
+    _, _, g32, _ = O.forward_backward(model, xin, mask, sd, training=True)
+    g = torch.Generator().manual_seed(7)
+    _, _, gpert, _ = O.forward_backward(model, xin + 1e-4 * torch.randn(xin.shape, generator=g), mask, sd, training=True)
+    S = float(2.0 ** (math.ceil(math.log2(n * h * w)) - 4))            # engine.loss_scale()
+    O.emulate_bf16_storage(True, S)
+    try:
+        _, _, gemu, _ = O.forward_backward(model, xin, mask, sd, training=True)
+    finally:
+        O.emulate_bf16_storage(False)
+    run_ours(net, xin, mask)
+
+    def rel(a, b):
+        return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+    worst, rows = 0.0, []
+    for k, p in net.named_parameters():
+        if k.startswith("inc.0."):
+            continue
+        # conv biases in front of train-mode BatchNorm have an exactly-zero gradient here and ~1e-9 noise in the oracle
+        if k.endswith(".bias") and og_is_noise(g32[k]):
+            assert p.grad.abs().max().item() <= 1e-6
+            continue
+        e, sens = rel(p.grad.cpu(), gemu[k]), rel(gpert[k], g32[k])
+        rows.append((k, e, sens))
+        assert e <= max(0.08, 2.5 * sens), (k, e, sens)
+        assert e <= 0.35, (k, e)
+        worst = max(worst, e)
+    es = sorted(r[1] for r in rows)
+    record(test="gradients_per_parameter", model=model, shape=[n, bands, h, w], median_rel_l2=es[len(es) // 2], max_rel_l2=worst,
+           median_oracle_sensitivity=sorted(r[2] for r in rows)[len(rows) // 2])
+    flat_g = torch.cat([p.grad.cpu().flatten() for k, p in net.named_parameters() if not k.startswith("inc.0.")])
+    flat_o = torch.cat([gemu[k].flatten() for k, p in net.named_parameters() if not k.startswith("inc.0.")])
+    assert cos(flat_g, flat_o) > 0.97
+
+
+def og_is_noise(g):
+    return g.abs().max().item() < 1e-7
