@@ -16,7 +16,7 @@ class Conv3x3Job(C.Structure):
     """hpri_conv3x3_job_t (include/hyperpri_b200.h)."""
     _fields_ = [("w", C.c_void_p), ("dst_fwd", C.c_void_p), ("dst_dgrad", C.c_void_p), ("grad_packed", C.c_void_p),
                 ("grad_dst", C.c_void_p), ("cout", C.c_int), ("cin", C.c_int), ("fwd_dtype", C.c_int),
-                ("dgrad_dtype", C.c_int), ("tile0", C.c_int), ("pad_", C.c_int)]
+                ("dgrad_dtype", C.c_int), ("tile0", C.c_int), ("kind", C.c_int)]
 
 
 class AdamJob(C.Structure):
@@ -62,13 +62,13 @@ SIGNATURES = {
     "hpri_convT2x2_dgrad": [_VP, _p, _i, _i, _i, _VP, _i, _p],
     "hpri_igemm_wgrad": [_VP, _VP, _i, _i, _p, _i, _i, _i, _p],
     "hpri_pack_weights": [_p, _p, _i, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _p],
-    "hpri_unpack_grads": [_p, _p, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _f, _i, _p],
+    "hpri_unpack_grads": [_p, _p, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _i, _f, _i, _f, _p, _p],
     "hpri_pack_conv3x3": [_p, _i, _i, _p, _i, _p, _i, _p],
     "hpri_unpack_conv3x3": [_p, _i, _i, _p, _p],
     "hpri_pr_hist": [_p, _p, _ll, _p, _i, _p, _i, _p, _p, _p, _p, _p, _p],
-    "hpri_adam_step": [_p, _i, _i, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _i, _p],
+    "hpri_adam_step": [_p, _i, _i, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _i, _p, _p],
     "hpri_pack_conv3x3_batch": [_p, _i, _i, _p],
-    "hpri_unpack_conv3x3_batch": [_p, _i, _i, _p],
+    "hpri_unpack_conv3x3_batch": [_p, _i, _i, _f, _p, _p],
     "hpri_pack_convT2x2": [_p, _i, _i, _p, _i, _p],
     "hpri_unpack_convT2x2": [_p, _i, _i, _p, _p],
     "hpri_hsi_ingest": [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _i, _i, _p],
@@ -81,11 +81,11 @@ SIGNATURES = {
     "hpri_bn_finalize": [_p, _ll, _p, _p, _p, _p, _p, _p, _f, _f, _i, _p, _p, _p, _p, _i, _p],
     "hpri_bn_relu_apply": [_VP, _p, _p, _VP, _VP, _p],
     "hpri_bn_relu_bwd_reduce": [_VP, _p, _p, _p, _p, _VP, _VP, _p, _p, _p, _p],
-    "hpri_bn_relu_bwd_apply": [_VP, _p, _p, _p, _p, _p, _VP, _VP, _p, _p, _p, _ll, _VP, _p, _p, _p, _p],
+    "hpri_bn_relu_bwd_apply": [_VP, _p, _p, _p, _p, _p, _VP, _VP, _p, _p, _p, _ll, _VP, _p, _p, _p, _f, _f, _p, _p],
     "hpri_head_fwd": [_VP, _p, _p, _p, _p, _p, _p],
     "hpri_bce_fwd_bwd": [_p, _p, _ll, _f, _f, _p, _p, _p, _p],
-    "hpri_colsum": [_VP, _p, _f, _p],
-    "hpri_sum_f32": [_p, _ll, _p, _p],
+    "hpri_colsum": [_VP, _p, _f, _f, _p],
+    "hpri_sum_f32": [_p, _ll, _p, _f, _p],
     "hpri_scale_check": [_p, _ll, _f, _p, _p],
 }
 

@@ -112,9 +112,14 @@ __global__ void pack_weights_k(const float* __restrict__ src, uint16_t* __restri
     dst[i] = cvt16(v, dt);
   }
 }
+// `scale` removes the loss scale of the fp16 gradient path; a non-finite value raises *flag (overflow of the scaled
+// fp16 gradients somewhere upstream), which the optimizer reads on the device to skip the step
+__device__ __forceinline__ void raise_if_bad(float v, int* flag) {
+  if (flag != nullptr && !isfinite(v)) atomicOr(flag, 1);
+}
 __global__ void unpack_grads_k(float* __restrict__ packed, float* __restrict__ dst, int G, int R, int T, int C,
                                int kc64, long long sg, long long sr, long long st, long long sc, int flip,
-                               float beta, int zero_src) {
+                               float beta, int zero_src, float scale, int* flag) {
   const long long total = (long long)G * R * T * kc64;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % kc64);
@@ -125,7 +130,8 @@ __global__ void unpack_grads_k(float* __restrict__ packed, float* __restrict__ d
     const int g = (int)(row / R), r = (int)(row % R);
     const int tm = flip ? T - 1 - t : t;
     float* d = dst + g * sg + r * sr + tm * st + c * sc;
-    const float v = packed[i];
+    const float v = packed[i] * scale;
+    raise_if_bad(v, flag);
     if (zero_src) packed[i] = 0.f;
     *d = beta == 0.f ? v : beta * (*d) + v;
   }
@@ -179,12 +185,25 @@ __device__ __forceinline__ int find_job(const hpri_conv3x3_job_t* __restrict__ j
   while (j + 1 < njobs && jobs[j + 1].tile0 <= t) ++j;
   return j;
 }
+__device__ __forceinline__ void pack_convT_tile(float (*tile)[129], int bx, int by, const float* __restrict__ w, int Cin,
+                                                int Cout, uint16_t* __restrict__ dst, int kc, int dt,
+                                                uint16_t* __restrict__ dd, int kcd, int ddt);
+__device__ __forceinline__ void unpack_convT_tile(float (*tile)[129], int bx, int by, float* __restrict__ g, int Cin,
+                                                  int Cout, int kc, float* __restrict__ dst, float scale, int* flag);
+// kind 0: conv3x3 job (w [cout][cin][3][3]); kind 1: ConvTranspose2d(k2,s2) job (w [cin][cout][2][2]; 32 x 32 (ci, co)
+// tiles; dst_fwd [4*cout][kpad(cin)], dst_dgrad [cin][4*kpad(cout)])
 __global__ void __launch_bounds__(256) pack_conv3x3_batch_k(const hpri_conv3x3_job_t* __restrict__ jobs, int njobs) {
   grid_dep_launch();      // a following tcgen05 launch may start its prologue while this grid drains
   __shared__ float tile[32][289];
   const int j = find_job(jobs, njobs, blockIdx.x);
   const hpri_conv3x3_job_t jb = jobs[j];
   const int t = blockIdx.x - jb.tile0, tx = (jb.cin + 31) / 32;
+  if (jb.kind == 1) {
+    pack_convT_tile(reinterpret_cast<float (*)[129]>(&tile[0][0]), t % tx, t / tx, jb.w, jb.cin, jb.cout,
+                    static_cast<uint16_t*>(jb.dst_fwd), (jb.cin + 63) / 64 * 64, jb.fwd_dtype,
+                    static_cast<uint16_t*>(jb.dst_dgrad), (jb.cout + 63) / 64 * 64, jb.dgrad_dtype);
+    return;
+  }
   pack_conv3x3_tile(tile, t % tx, t / tx, jb.w, jb.cout, jb.cin, static_cast<uint16_t*>(jb.dst_fwd),
                     (jb.cin + 63) / 64 * 64, jb.fwd_dtype, static_cast<uint16_t*>(jb.dst_dgrad),
                     (jb.cout + 63) / 64 * 64, jb.dgrad_dtype);
@@ -192,7 +211,8 @@ __global__ void __launch_bounds__(256) pack_conv3x3_batch_k(const hpri_conv3x3_j
 // packed fp32 gradient [co][t*kcf + ci] -> W-layout [co][ci][9]; the packed buffer is reset to zero behind the
 // read so that the next split-K weight-gradient launch can accumulate into it without a separate memset.
 __device__ __forceinline__ void unpack_conv3x3_tile(float (*tile)[289], int bx, int by, float* __restrict__ g, int Cout,
-                                                    int Cin, int kcf, float* __restrict__ dst) {
+                                                    int Cin, int kcf, float* __restrict__ dst, float scale = 1.f,
+                                                    int* flag = nullptr) {
   const int ci0 = bx * 32, co0 = by * 32;
   const int nci = min(32, Cin - ci0), nco = min(32, Cout - co0);
 #pragma unroll 1
@@ -208,7 +228,9 @@ __device__ __forceinline__ void unpack_conv3x3_tile(float (*tile)[289], int bx, 
     for (int u = 0; u < 12; ++u) {              // all twelve loads are issued before the first dependent store
       const int i = threadIdx.x + (b * 12 + u) * 256;
       const int l = i & 31, t = (i >> 5) % 9, o = i / 288;
-      tile[o][l * 9 + t] = v[u];
+      const float sv = v[u] * scale;
+      raise_if_bad(sv, flag);
+      tile[o][l * 9 + t] = sv;
       if (o < nco && l < nci) g[(long long)(co0 + o) * (9 * kcf) + t * kcf + ci0 + l] = 0.f;
     }
   }
@@ -223,21 +245,29 @@ unpack_conv3x3_k(float* __restrict__ g, int Cout, int Cin, int kcf, float* __res
   __shared__ float tile[32][289];
   unpack_conv3x3_tile(tile, blockIdx.x, blockIdx.y, g, Cout, Cin, kcf, dst);
 }
-__global__ void __launch_bounds__(256) unpack_conv3x3_batch_k(const hpri_conv3x3_job_t* __restrict__ jobs, int njobs) {
+__global__ void __launch_bounds__(256)
+unpack_conv3x3_batch_k(const hpri_conv3x3_job_t* __restrict__ jobs, int njobs, float scale, int* flag) {
   __shared__ float tile[32][289];
   const int j = find_job(jobs, njobs, blockIdx.x);
   const hpri_conv3x3_job_t jb = jobs[j];
   const int t = blockIdx.x - jb.tile0, tx = (jb.cin + 31) / 32;
-  unpack_conv3x3_tile(tile, t % tx, t / tx, jb.grad_packed, jb.cout, jb.cin, (jb.cin + 63) / 64 * 64, jb.grad_dst);
+  if (jb.kind == 1) {
+    unpack_convT_tile(reinterpret_cast<float (*)[129]>(&tile[0][0]), t % tx, t / tx, jb.grad_packed, jb.cin, jb.cout,
+                      (jb.cin + 63) / 64 * 64, jb.grad_dst, scale, flag);
+    return;
+  }
+  unpack_conv3x3_tile(tile, t % tx, t / tx, jb.grad_packed, jb.cout, jb.cin, (jb.cin + 63) / 64 * 64, jb.grad_dst, scale,
+                      flag);
 }
 
 // ------------------------------------------------------------------ ConvTranspose2d(k2,s2) weight <-> GEMM operand
 // W[ci][co][a][b] fp32  <->  P[(ab*Cout + co)][ci]  (ab = a*2+b; row length kc = kpad(Cin)).  A (ci, co) transpose:
 // 32 x 32 tiles through shared memory so that both sides move whole 128-byte lines.
-__global__ void __launch_bounds__(256)
-pack_convT_k(const float* __restrict__ w, int Cin, int Cout, uint16_t* __restrict__ dst, int kc, int dt) {
-  __shared__ float tile[32][129];
-  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+// dd (optional): the dgrad operand [ci][ab*kcd + co] (kcd = kpad(Cout)), written from the same tile
+__device__ __forceinline__ void pack_convT_tile(float (*tile)[129], int bx, int by, const float* __restrict__ w, int Cin,
+                                                int Cout, uint16_t* __restrict__ dst, int kc, int dt,
+                                                uint16_t* __restrict__ dd, int kcd, int ddt) {
+  const int ci0 = bx * 32, co0 = by * 32;
   for (int i = threadIdx.x; i < 32 * 128; i += 256) {
     const int r = i >> 7, q = i & 127;                      // ci row, (co, ab) column
     float v = 0.f;
@@ -246,17 +276,23 @@ pack_convT_k(const float* __restrict__ w, int Cin, int Cout, uint16_t* __restric
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 32 * 128; i += 256) {
-    const int l = i & 31, q = i >> 5;                        // lanes over ci; q = ab * 32 + co
-    const int ab = q >> 5, co = q & 31;
-    if (ci0 + l < Cin && co0 + co < Cout)
-      dst[((long long)ab * Cout + co0 + co) * kc + ci0 + l] = cvt16(tile[l][co * 4 + ab], dt);
+    const int l = i & 31, q = i >> 5;                        // q = ab * 32 + j
+    const int ab = q >> 5, j = q & 31;
+    if (dst != nullptr && ci0 + l < Cin && co0 + j < Cout)   // lanes over ci, j over co
+      dst[((long long)ab * Cout + co0 + j) * kc + ci0 + l] = cvt16(tile[l][j * 4 + ab], dt);
+    if (dd != nullptr && ci0 + j < Cin && co0 + l < Cout)    // lanes over co, j over ci
+      dd[(long long)(ci0 + j) * (4 * kcd) + ab * kcd + co0 + l] = cvt16(tile[j][l * 4 + ab], ddt);
   }
 }
-// packed fp32 gradient P[(ab*Cout + co)][ci] -> W layout; the packed buffer is zeroed behind the read
 __global__ void __launch_bounds__(256)
-unpack_convT_k(float* __restrict__ g, int Cin, int Cout, int kc, float* __restrict__ dst) {
+pack_convT_k(const float* __restrict__ w, int Cin, int Cout, uint16_t* __restrict__ dst, int kc, int dt) {
   __shared__ float tile[32][129];
-  const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+  pack_convT_tile(tile, blockIdx.x, blockIdx.y, w, Cin, Cout, dst, kc, dt, nullptr, 0, 0);
+}
+// packed fp32 gradient P[(ab*Cout + co)][ci] -> W layout; the packed buffer is zeroed behind the read
+__device__ __forceinline__ void unpack_convT_tile(float (*tile)[129], int bx, int by, float* __restrict__ g, int Cin,
+                                                  int Cout, int kc, float* __restrict__ dst, float scale, int* flag) {
+  const int ci0 = bx * 32, co0 = by * 32;
   // sixteen elements per thread: all loads are issued before the first (possibly aliasing) zeroing store
   float v[16];
 #pragma unroll
@@ -271,7 +307,9 @@ unpack_convT_k(float* __restrict__ g, int Cin, int Cout, int kc, float* __restri
     const int i = threadIdx.x + u * 256;
     const int l = i & 31, q = i >> 5;
     const int ab = q >> 5, co = q & 31;
-    tile[l][co * 4 + ab] = v[u];
+    const float sv = v[u] * scale;
+    raise_if_bad(sv, flag);
+    tile[l][co * 4 + ab] = sv;
     if (ci0 + l < Cin && co0 + co < Cout) g[((long long)ab * Cout + co0 + co) * kc + ci0 + l] = 0.f;
   }
   __syncthreads();
@@ -280,11 +318,18 @@ unpack_convT_k(float* __restrict__ g, int Cin, int Cout, int kc, float* __restri
     if (ci0 + r < Cin && co0 + (q >> 2) < Cout) dst[((long long)(ci0 + r) * Cout + co0) * 4 + q] = tile[r][q];
   }
 }
+__global__ void __launch_bounds__(256)
+unpack_convT_k(float* __restrict__ g, int Cin, int Cout, int kc, float* __restrict__ dst) {
+  __shared__ float tile[32][129];
+  unpack_convT_tile(tile, blockIdx.x, blockIdx.y, g, Cin, Cout, kc, dst, 1.f, nullptr);
+}
 
 // ------------------------------------------------------------------ multi-tensor Adam (torch.optim.Adam semantics)
 __global__ void __launch_bounds__(256)
 adam_k(const hpri_adam_job_t* __restrict__ jobs, int njobs, float lr, float b1, float b2, float omb1, float omb2,
-       float eps, float wd, float inv_bc1, float inv_sqrt_bc2) {
+       float eps, float wd, float inv_bc1, float inv_sqrt_bc2, const int* __restrict__ found_inf) {
+  // a raised overflow flag (non-finite loss-scaled gradients this step) skips the whole update, moments included
+  if (found_inf != nullptr && __ldg(found_inf) != 0) return;
   int j = 0;
   while (j + 1 < njobs && jobs[j + 1].block0 <= (int)blockIdx.x) ++j;
   const hpri_adam_job_t jb = jobs[j];
@@ -825,19 +870,29 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_k(BwdIn a, double* sums,
   }
 }
 
+// BatchNorm parameter gradients from the reduced sums (block 0 of the apply kernels): out = out_beta * out + out_scale * sum.
+// out_scale removes the loss scale of the fp16 gradient path; out_beta = 1 accumulates (SpectralUNET: one launch per image).
+struct ParamGradOut {
+  float *dgamma, *dbeta, *dhead_w;
+  float scale, beta;
+  int* flag;
+};
+__device__ __forceinline__ void write_param_grads(const double* __restrict__ sums, int C, const ParamGradOut& o) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float b = (float)sums[3 * c] * o.scale, g = (float)sums[3 * c + 1] * o.scale, h = (float)sums[3 * c + 2] * o.scale;
+    if (o.dbeta) { o.dbeta[c] = o.beta == 0.f ? b : fmaf(o.beta, o.dbeta[c], b); raise_if_bad(b, o.flag); }
+    if (o.dgamma) { o.dgamma[c] = o.beta == 0.f ? g : fmaf(o.beta, o.dgamma[c], g); raise_if_bad(g, o.flag); }
+    if (o.dhead_w) { o.dhead_w[c] = o.beta == 0.f ? h : fmaf(o.beta, o.dhead_w[c], h); raise_if_bad(h, o.flag); }
+  }
+}
+
 // pass 2: dx = gamma*invstd*(dz - mean(dz) - xhat*mean(dz*xhat)) = ca*dz + cb*x + cc
 template <int DT, bool HEAD>
 __global__ void __launch_bounds__(256, 2)
 bn_bwd_apply_k(BwdIn a, const float* __restrict__ gamma, const double* __restrict__ sums, long long count, V dx,
-               float* dgamma, float* dbeta, float* dhead_w, int CG, int rows) {
+               ParamGradOut pg, int CG, int rows) {
   grid_dep_launch();      // a following tcgen05 launch may start its prologue while this grid drains
-  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
-    for (int c = threadIdx.x; c < a.x.c; c += blockDim.x) {
-      if (dbeta) dbeta[c] = (float)sums[3 * c];
-      if (dgamma) dgamma[c] = (float)sums[3 * c + 1];
-      if (dhead_w) dhead_w[c] = (float)sums[3 * c + 2];
-    }
-  }
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) write_param_grads(sums, a.x.c, pg);
   const int wh = (a.x.h + 1) >> 1, ww = (a.x.w + 1) >> 1;
   const int g = blockIdx.x * 256 + threadIdx.x;
   const int cg = g % CG, wx = g / CG;
@@ -974,16 +1029,9 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_flat_k(FlatIn a, double*
 template <bool HEAD, int DT>
 __global__ void __launch_bounds__(256, 2)
 bn_bwd_apply_flat_k(FlatIn a, const float* __restrict__ gamma, const double* __restrict__ sums, long long count,
-                    uint16_t* __restrict__ dx, long long sdx, int dxdt, float* dgamma, float* dbeta, float* dhead_w,
-                    int slots, int CG) {
+                    uint16_t* __restrict__ dx, long long sdx, int dxdt, ParamGradOut pg, int slots, int CG) {
   grid_dep_launch();      // a following tcgen05 launch may start its prologue while this grid drains
-  if (blockIdx.x == 0) {
-    for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
-      if (dbeta) dbeta[c] = (float)sums[3 * c];
-      if (dgamma) dgamma[c] = (float)sums[3 * c + 1];
-      if (dhead_w) dhead_w[c] = (float)sums[3 * c + 2];
-    }
-  }
+  if (blockIdx.x == 0) write_param_grads(sums, a.C, pg);
   const int cg = threadIdx.x % CG, slot = threadIdx.x / CG;
   if (slot >= slots) return;
   const int c0 = cg * 8;
@@ -1029,6 +1077,180 @@ bn_bwd_apply_flat_k(FlatIn a, const float* __restrict__ gamma, const double* __r
       *reinterpret_cast<uint4*>(dx + pp * sdx + c0) = pack8_t<DT>(o, dxdt);
     }
   }
+}
+
+// ---- "contiguous" fast path: every view is channel-dense AND pixel-dense (one linear run of 16-byte vectors) and
+// 256 % (C/8) == 0, so a thread's channel group never changes while it walks vector index v = base + u*256 + tid.
+// A block instruction covers 4 KB contiguous, U of them back to back: measured 6.1-6.3 TB/s on B200 against 5.3 TB/s
+// for the strided mapping above (tools/probes/stream_probe.cu, profiles/stream_probe_r2a_c64.txt).
+template <bool HEAD, int DT, int U>
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_apply_contig_k(const uint4* __restrict__ x, const uint4* __restrict__ dy, uint4* __restrict__ dx, long long nvec,
+                      int C, const float* __restrict__ scale, const float* __restrict__ shift,
+                      const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ head_w,
+                      const float* __restrict__ dlogit, const float* __restrict__ gamma,
+                      const double* __restrict__ sums, long long count, ParamGradOut pg) {
+  grid_dep_launch();
+  if (blockIdx.x == 0) write_param_grads(sums, C, pg);
+  const int CG = C >> 3;
+  const int c0 = (threadIdx.x % CG) * 8;
+  const float rc = 1.f / (float)count;
+  float sc[8], sh[8], hw[8], ca[8], cb[8], cc[8];
+  ld8v(scale, c0, C, sc);
+  ld8v(shift, c0, C, sh);
+  ld8v(head_w, c0, C, hw);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = c0 + k;
+    const float g = __ldg(gamma + c), mu = __ldg(mean + c), is = __ldg(invstd + c);
+    const float m1 = (float)sums[3 * c] * rc, m2 = (float)sums[3 * c + 1] * rc;
+    ca[k] = g * is;
+    cb[k] = -g * is * is * m2;
+    cc[k] = -g * is * m1 - cb[k] * mu;
+  }
+  const long long step = (long long)gridDim.x * 256 * U;
+  for (long long v0 = (long long)blockIdx.x * 256 * U + threadIdx.x; v0 < nvec; v0 += step) {
+    uint4 xr[U], dr[U];
+    float dl[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long v = v0 + u * 256;
+      xr[u] = make_uint4(0, 0, 0, 0); dr[u] = make_uint4(0, 0, 0, 0); dl[u] = 0.f;
+      if (v < nvec) {
+        xr[u] = __ldg(x + v);
+        if (dy != nullptr) dr[u] = __ldg(dy + v);
+        if (HEAD) dl[u] = __ldg(dlogit + v / CG);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long v = v0 + u * 256;
+      if (v >= nvec) break;
+      float xv[8], dz[8], o[8];
+      unpack8_t<DT>(xr[u], xv, DT);
+      if (dy != nullptr) unpack8_t<DT>(dr[u], dz, DT);
+      else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dz[k] = 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (HEAD) dz[k] = fmaf(dl[u], hw[k], dz[k]);
+        dz[k] = fmaf(xv[k], sc[k], sh[k]) > 0.f ? dz[k] : 0.f;
+        o[k] = fmaf(ca[k], dz[k], fmaf(cb[k], xv[k], cc[k]));
+      }
+      dx[v] = pack8_t<DT>(o, DT);
+    }
+  }
+}
+
+template <bool HEAD, int DT, int U>
+__global__ void __launch_bounds__(256, 2)
+bn_bwd_reduce_contig_k(const uint4* __restrict__ x, const uint4* __restrict__ dy, long long nvec, int C,
+                       const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+                       const float* __restrict__ invstd, const float* __restrict__ head_w,
+                       const float* __restrict__ dlogit, double* sums) {
+  __shared__ float red[256][25];                 // odd stride: conflict-free row writes
+  const int CG = C >> 3;
+  const int c0 = (threadIdx.x % CG) * 8;
+  float sc[8], sh[8], hw[8], s1[8], s2[8], s3[8];
+  ld8v(scale, c0, C, sc);
+  ld8v(shift, c0, C, sh);
+  ld8v(head_w, c0, C, hw);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; s3[k] = 0.f; }
+  const long long step = (long long)gridDim.x * 256 * U;
+  for (long long v0 = (long long)blockIdx.x * 256 * U + threadIdx.x; v0 < nvec; v0 += step) {
+    uint4 xr[U], dr[U];
+    float dl[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long v = v0 + u * 256;
+      xr[u] = make_uint4(0, 0, 0, 0); dr[u] = make_uint4(0, 0, 0, 0); dl[u] = 0.f;
+      if (v < nvec) {
+        xr[u] = __ldg(x + v);
+        if (dy != nullptr) dr[u] = __ldg(dy + v);
+        if (HEAD) dl[u] = __ldg(dlogit + v / CG);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (v0 + u * 256 >= nvec) break;
+      float xv[8], dz[8];
+      unpack8_t<DT>(xr[u], xv, DT);
+      if (dy != nullptr) unpack8_t<DT>(dr[u], dz, DT);
+      else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dz[k] = 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float z = fmaf(xv[k], sc[k], sh[k]);
+        if (HEAD) dz[k] = fmaf(dl[u], hw[k], dz[k]);
+        dz[k] = z > 0.f ? dz[k] : 0.f;
+        s1[k] += dz[k];
+        s2[k] = fmaf(dz[k], xv[k], s2[k]);
+        if (HEAD) s3[k] = fmaf(dl[u], fmaxf(z, 0.f), s3[k]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    red[threadIdx.x][k * 3] = s1[k]; red[threadIdx.x][k * 3 + 1] = s2[k]; red[threadIdx.x][k * 3 + 2] = s3[k];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const int cg = c >> 3, k = c & 7;
+    float t1 = 0.f, t2 = 0.f, t3 = 0.f;
+    for (int t = cg; t < 256; t += CG) { t1 += red[t][k * 3]; t2 += red[t][k * 3 + 1]; t3 += red[t][k * 3 + 2]; }
+    const float mu = __ldg(mean + c), is = __ldg(invstd + c);
+    atomicAdd(sums + 3 * c, (double)t1);
+    atomicAdd(sums + 3 * c + 1, (double)is * ((double)t2 - (double)mu * (double)t1));
+    if (HEAD) atomicAdd(sums + 3 * c + 2, (double)t3);
+  }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(256, 4)
+bn_relu_apply_contig_k(const uint4* __restrict__ x, uint4* __restrict__ y, long long nvec, int C,
+                       const float* __restrict__ scale, const float* __restrict__ shift) {
+  grid_dep_launch();
+  const int CG = C >> 3;
+  const int c0 = (threadIdx.x % CG) * 8;
+  float sc[8], sh[8];
+  ld8v(scale, c0, C, sc);
+  ld8v(shift, c0, C, sh);
+  const long long step = (long long)gridDim.x * 1024;
+  for (long long v0 = (long long)blockIdx.x * 1024 + threadIdx.x; v0 < nvec; v0 += step) {
+    uint4 xr[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long v = v0 + u * 256;
+      xr[u] = make_uint4(0, 0, 0, 0);
+      if (v < nvec) xr[u] = __ldg(x + v);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long v = v0 + u * 256;
+      if (v >= nvec) break;
+      float f[8];
+      unpack8_t<DT>(xr[u], f, DT);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = fmaxf(fmaf(f[k], sc[k], sh[k]), 0.f);
+      y[v] = pack8_t<DT>(f, DT);
+    }
+  }
+}
+
+// true when v is one linear run of 16-byte vectors: channel-dense and pixel-dense, C a multiple of 8 dividing 2048
+static inline bool vec_contig(const hpri_view_t* v) {
+  const int CG = v->c / 8;
+  return (v->c % 8) == 0 && CG > 0 && 256 % CG == 0 && v->pix_stride == v->c &&
+         v->row_stride == (long long)v->w * v->pix_stride && v->img_stride == (long long)v->h * v->row_stride;
+}
+static inline int contig_grid(long long nvec, int per_block, int cap) {
+  long long g = (nvec + per_block - 1) / per_block;
+  return (int)(g < 1 ? 1 : g > cap ? cap : g);
 }
 
 static inline bool pixel_dense(const hpri_view_t* v) {
@@ -1225,7 +1447,7 @@ pr_hist_k(const float* __restrict__ x, const float* __restrict__ t, long long n,
 }
 
 // ------------------------------------------------------------------ channel sums
-__global__ void __launch_bounds__(256) colsum_k(V x, float* out, int slots, int CG) {
+__global__ void __launch_bounds__(256) colsum_k(V x, float* out, int slots, int CG, float scale) {
   extern __shared__ float red[];                 // [slots][CG*8]
   const int cg = threadIdx.x % CG, slot = threadIdx.x / CG;
   if (slot < slots) {
@@ -1261,7 +1483,7 @@ __global__ void __launch_bounds__(256) colsum_k(V x, float* out, int slots, int 
   for (int i = threadIdx.x; i < CG * 8; i += blockDim.x) {
     float t = 0.f;
     for (int s = 0; s < slots; ++s) t += red[(long long)s * CG * 8 + i];
-    if (i < x.c) atomicAdd(out + i, t);
+    if (i < x.c) atomicAdd(out + i, t * scale);
   }
 }
 __global__ void scale_f32_k(float* p, int n, float beta) {
@@ -1286,12 +1508,12 @@ __global__ void __launch_bounds__(256) scale_check_k(float* __restrict__ x, long
   }
   if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
 }
-__global__ void sum_f32_k(const float* __restrict__ x, long long n, float* out) {
+__global__ void sum_f32_k(const float* __restrict__ x, long long n, float* out, float scale) {
   float s = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     s += __ldg(x + i);
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, s * scale);
 }
 
 // common element format of the views of a window kernel (-1: they differ -> runtime unpack)
@@ -1321,7 +1543,7 @@ static inline int grid_for(long long work_items, int per_block, int cap = 148 * 
 
 using namespace hpri;
 
-extern "C" int hpri_abi_version(void) { return 4; }
+extern "C" int hpri_abi_version(void) { return 5; }
 extern "C" long long hpri_launch_count(void) { return g_launch_count; }
 
 extern "C" int hpri_pack_weights(const float* src, void* dst, int dst_dtype, int G, int R, int T, int C, int kc64,
@@ -1335,11 +1557,11 @@ extern "C" int hpri_pack_weights(const float* src, void* dst, int dst_dtype, int
 }
 extern "C" int hpri_unpack_grads(float* packed, float* dst, int G, int R, int T, int C, int kc64, long long sg,
                                  long long sr, long long st, long long sc, int flip, float beta, int zero_src,
-                                 void* stream) {
+                                 float scale, int* flag, void* stream) {
   if (!packed || !dst || G <= 0 || R <= 0 || T <= 0 || C <= 0 || kc64 < C) return HPRI_ERR_ARG;
   const long long total = (long long)G * R * T * kc64;
   unpack_grads_k<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(packed, dst, G, R, T, C, kc64, sg, sr, st,
-                                                                        sc, flip, beta, zero_src);
+                                                                        sc, flip, beta, zero_src, scale, flag);
   return last_err();
 }
 
@@ -1358,9 +1580,10 @@ extern "C" int hpri_pack_conv3x3_batch(const hpri_conv3x3_job_t* jobs, int njobs
   pack_conv3x3_batch_k<<<total_tiles, 256, 0, (cudaStream_t)stream>>>(jobs, njobs);
   return last_err();
 }
-extern "C" int hpri_unpack_conv3x3_batch(const hpri_conv3x3_job_t* jobs, int njobs, int total_tiles, void* stream) {
+extern "C" int hpri_unpack_conv3x3_batch(const hpri_conv3x3_job_t* jobs, int njobs, int total_tiles, float scale,
+                                         int* flag, void* stream) {
   if (!jobs || njobs <= 0 || total_tiles <= 0) return HPRI_ERR_ARG;
-  unpack_conv3x3_batch_k<<<total_tiles, 256, 0, (cudaStream_t)stream>>>(jobs, njobs);
+  unpack_conv3x3_batch_k<<<total_tiles, 256, 0, (cudaStream_t)stream>>>(jobs, njobs, scale, flag);
   return last_err();
 }
 extern "C" int hpri_pr_hist(const float* logits, const float* target, long long numel, const float* thr, int n_thr,
@@ -1374,14 +1597,15 @@ extern "C" int hpri_pr_hist(const float* logits, const float* target, long long 
   return last_err();
 }
 extern "C" int hpri_adam_step(const hpri_adam_job_t* jobs, int njobs, int total_blocks, double lr, double beta1,
-                              double beta2, double eps, double weight_decay, int step, void* stream) {
+                              double beta2, double eps, double weight_decay, int step, const int* found_inf,
+                              void* stream) {
   if (!jobs || njobs <= 0 || total_blocks <= 0 || step <= 0) return HPRI_ERR_ARG;
   // hyper-parameters arrive as doubles and are rounded once, like torch's scalar arguments
   const double bc1 = 1.0 - pow(beta1, (double)step), bc2 = 1.0 - pow(beta2, (double)step);
   adam_k<<<total_blocks, 256, 0, (cudaStream_t)stream>>>(jobs, njobs, (float)lr, (float)beta1, (float)beta2,
                                                         (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps,
                                                         (float)weight_decay, (float)(1.0 / bc1),
-                                                        (float)(1.0 / sqrt(bc2)));
+                                                        (float)(1.0 / sqrt(bc2)), found_inf);
   return last_err();
 }
 extern "C" int hpri_pack_convT2x2(const float* w, int cin, int cout, void* dst_fwd, int fwd_dtype, void* stream) {
@@ -1527,6 +1751,17 @@ extern "C" int hpri_bn_relu_apply(const hpri_view_t* x, const float* scale, cons
   if (pooled && (pooled->n != x->n || pooled->h != x->h / 2 || pooled->w != x->w / 2 || pooled->c != x->c))
     return HPRI_ERR_ARG;
   const int CG = (x->c + 7) / 8;
+  if (!pooled && vec_contig(x) && vec_contig(y) && x->dtype == y->dtype) {
+    const long long nvec = (long long)x->n * x->h * x->w * CG;
+    const int grid = contig_grid(nvec, 1024, 1 << 30);      // one 16 KB chunk per block: measured best for 1 in / 1 out
+    if (x->dtype == DT_F16)
+      bn_relu_apply_contig_k<DT_F16><<<grid, 256, 0, (cudaStream_t)stream>>>(
+          static_cast<const uint4*>(x->ptr), static_cast<uint4*>(y->ptr), nvec, x->c, scale, shift);
+    else
+      bn_relu_apply_contig_k<DT_BF16><<<grid, 256, 0, (cudaStream_t)stream>>>(
+          static_cast<const uint4*>(x->ptr), static_cast<uint4*>(y->ptr), nvec, x->c, scale, shift);
+    return last_err();
+  }
   if (!pooled && CG <= 256 && pixel_dense(x) && pixel_dense(y)) {
     const int slots = 256 / CG;
     const long long npix = (long long)x->n * x->h * x->w;
@@ -1576,6 +1811,18 @@ extern "C" int hpri_bn_relu_bwd_reduce(const hpri_view_t* x, const float* scale,
   const size_t smem = (size_t)slots * CG * 24 * 4;
   if (smem > 48 * 1024) return HPRI_ERR_ARG;
   if (cudaMemsetAsync(sums, 0, sizeof(double) * 3 * x->c, (cudaStream_t)stream) != cudaSuccess) return HPRI_ERR_CUDA;
+  if (!dpool && vec_contig(x) && (!dy || (vec_contig(dy) && dy->dtype == x->dtype))) {
+    const long long nvec = (long long)x->n * x->h * x->w * CG;
+    const uint4* xp = static_cast<const uint4*>(x->ptr);
+    const uint4* dp = dy ? static_cast<const uint4*>(dy->ptr) : nullptr;
+#define HPRI_RC(HD, DT, U)                                                                                        \
+    bn_bwd_reduce_contig_k<HD, DT, U><<<contig_grid(nvec, 256 * U, 148 * 4), 256, 0, (cudaStream_t)stream>>>(       \
+        xp, dp, nvec, x->c, scale, shift, save_mean, save_invstd, head_w, dlogit, sums)
+    if (x->dtype == DT_F16) { if (dlogit) HPRI_RC(true, DT_F16, 4); else HPRI_RC(false, DT_F16, 8); }
+    else { if (dlogit) HPRI_RC(true, DT_BF16, 4); else HPRI_RC(false, DT_BF16, 8); }
+#undef HPRI_RC
+    return last_err();
+  }
   if (!dpool && pixel_dense(x) && (!dy || pixel_dense(dy))) {
     FlatIn f{static_cast<const uint16_t*>(x->ptr), dy ? static_cast<const uint16_t*>(dy->ptr) : nullptr, x->pix_stride,
              dy ? dy->pix_stride : 0, x->dtype, dy ? dy->dtype : 0, x->c, (long long)x->n * x->h * x->w, scale, shift,
@@ -1606,12 +1853,27 @@ extern "C" int hpri_bn_relu_bwd_apply(const hpri_view_t* x, const float* scale, 
                                       const float* save_mean, const float* save_invstd, const float* gamma,
                                       const hpri_view_t* dy, const hpri_view_t* dpool, const float* head_w,
                                       const float* dlogit, double* sums, long long count, const hpri_view_t* dx,
-                                      float* dgamma, float* dbeta, float* dhead_w, void* stream) {
+                                      float* dgamma, float* dbeta, float* dhead_w, float out_scale, float out_beta,
+                                      int* flag, void* stream) {
   int rc;
   if ((rc = bwd_common(x, dy, dpool, head_w, dlogit)) != HPRI_OK) return rc;
   if ((rc = check_view_e(dx)) != HPRI_OK) return rc;
   if (!scale || !shift || !save_mean || !save_invstd || !gamma || !sums || count <= 0) return HPRI_ERR_ARG;
   if (dx->n != x->n || dx->h != x->h || dx->w != x->w || dx->c != x->c) return HPRI_ERR_ARG;
+  const ParamGradOut pg{dgamma, dbeta, dhead_w, out_scale, out_beta, flag};
+  if (!dpool && vec_contig(x) && vec_contig(dx) && dx->dtype == x->dtype && (!dy || (vec_contig(dy) && dy->dtype == x->dtype))) {
+    const long long nvec = (long long)x->n * x->h * x->w * (x->c / 8);
+    const uint4* xp = static_cast<const uint4*>(x->ptr);
+    const uint4* dp = dy ? static_cast<const uint4*>(dy->ptr) : nullptr;
+    uint4* op = static_cast<uint4*>(dx->ptr);
+#define HPRI_PC(HD, DT, U)                                                                                        \
+    bn_bwd_apply_contig_k<HD, DT, U><<<contig_grid(nvec, 256 * U, 148 * 4), 256, 0, (cudaStream_t)stream>>>(        \
+        xp, dp, op, nvec, x->c, scale, shift, save_mean, save_invstd, head_w, dlogit, gamma, sums, count, pg)
+    if (x->dtype == DT_F16) { if (dlogit) HPRI_PC(true, DT_F16, 4); else HPRI_PC(false, DT_F16, 8); }
+    else { if (dlogit) HPRI_PC(true, DT_BF16, 4); else HPRI_PC(false, DT_BF16, 8); }
+#undef HPRI_PC
+    return last_err();
+  }
   if (!dpool && pixel_dense(x) && (!dy || pixel_dense(dy)) && pixel_dense(dx)) {
     FlatIn f{static_cast<const uint16_t*>(x->ptr), dy ? static_cast<const uint16_t*>(dy->ptr) : nullptr, x->pix_stride,
              dy ? dy->pix_stride : 0, x->dtype, dy ? dy->dtype : 0, x->c, (long long)x->n * x->h * x->w, scale, shift,
@@ -1624,7 +1886,7 @@ extern "C" int hpri_bn_relu_bwd_apply(const hpri_view_t* x, const float* scale, 
     const int dtf = win_dtype(x, dy, nullptr, dx);
 #define HPRI_PF(HD, DT)                                                                                            \
     bn_bwd_apply_flat_k<HD, DT><<<grid, 256, 0, (cudaStream_t)stream>>>(f, gamma, sums, count, dxp, dx->pix_stride,   \
-                                                                       dx->dtype, dgamma, dbeta, dhead_w, slots, CG)
+                                                                       dx->dtype, pg, slots, CG)
     if (dtf == DT_F16) { if (dlogit) HPRI_PF(true, DT_F16); else HPRI_PF(false, DT_F16); }
     else if (dtf == DT_BF16) { if (dlogit) HPRI_PF(true, DT_BF16); else HPRI_PF(false, DT_BF16); }
     else { if (dlogit) HPRI_PF(true, -1); else HPRI_PF(false, -1); }
@@ -1638,8 +1900,7 @@ extern "C" int hpri_bn_relu_bwd_apply(const hpri_view_t* x, const float* scale, 
   const int dt = win_dtype(x, dy, dpool, dx);
   const bool head = dlogit != nullptr;
 #define HPRI_APP(DT, HD)                                                                                          \
-  bn_bwd_apply_k<DT, HD><<<grid, 256, 0, (cudaStream_t)stream>>>(a, gamma, sums, count, mk(dx), dgamma, dbeta, dhead_w, \
-                                                                CGw, rows)
+  bn_bwd_apply_k<DT, HD><<<grid, 256, 0, (cudaStream_t)stream>>>(a, gamma, sums, count, mk(dx), pg, CGw, rows)
   if (dt == DT_F16) { if (head) HPRI_APP(DT_F16, true); else HPRI_APP(DT_F16, false); }
   else if (dt == DT_BF16) { if (head) HPRI_APP(DT_BF16, true); else HPRI_APP(DT_BF16, false); }
   else { if (head) HPRI_APP(-1, true); else HPRI_APP(-1, false); }
@@ -1678,7 +1939,7 @@ extern "C" int hpri_bce_fwd_bwd(const float* logits, const float* target, long l
   return last_err();
 }
 
-extern "C" int hpri_colsum(const hpri_view_t* x, float* out, float beta, void* stream) {
+extern "C" int hpri_colsum(const hpri_view_t* x, float* out, float beta, float scale, void* stream) {
   int rc;
   if ((rc = check_view_e(x)) != HPRI_OK) return rc;
   if (!out) return HPRI_ERR_ARG;
@@ -1687,7 +1948,7 @@ extern "C" int hpri_colsum(const hpri_view_t* x, float* out, float beta, void* s
   const int slots = 256 / CG;
   scale_f32_k<<<(x->c + 255) / 256, 256, 0, (cudaStream_t)stream>>>(out, x->c, beta);
   colsum_k<<<grid_for((long long)x->n * x->h, 1, 148 * 8), 256, (size_t)slots * CG * 32, (cudaStream_t)stream>>>(mk(x), out,
-                                                                                                       slots, CG);
+                                                                                                       slots, CG, scale);
   return last_err(2);
 }
 extern "C" int hpri_scale_check(float* x, long long numel, float scale, int* flag, void* stream) {
@@ -1695,9 +1956,9 @@ extern "C" int hpri_scale_check(float* x, long long numel, float scale, int* fla
   scale_check_k<<<grid_for(numel, 256 * 16, 148 * 8), 256, 0, (cudaStream_t)stream>>>(x, numel, scale, flag);
   return last_err();
 }
-extern "C" int hpri_sum_f32(const float* x, long long numel, float* out, void* stream) {
+extern "C" int hpri_sum_f32(const float* x, long long numel, float* out, float scale, void* stream) {
   if (!x || !out || numel <= 0) return HPRI_ERR_ARG;
   if (cudaMemsetAsync(out, 0, sizeof(float), (cudaStream_t)stream) != cudaSuccess) return HPRI_ERR_CUDA;
-  sum_f32_k<<<grid_for(numel, 256 * 8, 148 * 4), 256, 0, (cudaStream_t)stream>>>(x, numel, out);
+  sum_f32_k<<<grid_for(numel, 256 * 8, 148 * 4), 256, 0, (cudaStream_t)stream>>>(x, numel, out, scale);
   return last_err();
 }

@@ -56,6 +56,12 @@ class _PackedParam:
             if self.need_dgrad:
                 self.dgr = torch.zeros((g["R"], 9 * kpad(g["Cc"])), dtype=GRAD, device=device)
 
+    def alloc_convT(self, device):
+        if self.fwd is None:                   # zero once: the tiled pack never writes padding
+            sp = self.spec
+            self.fwd = torch.zeros((4 * sp.cout, kpad(sp.cin)), dtype=ACT, device=device)
+            self.dgr = torch.zeros((sp.cin, 4 * kpad(sp.cout)), dtype=GRAD, device=device)
+
     def stale(self, w: torch.Tensor) -> bool:
         return (w.data_ptr(), w._version) != self.key
 
@@ -93,8 +99,11 @@ class _EngineBase:
     bucket_hook = None
 
     def _init_scaling(self, device):
-        self.overflow = torch.zeros(1, dtype=torch.int32, device=device)
-        self._pending_unscale, self._S = False, 1.0
+        # [0]: overflow flag of the current step's gradients (raised by the unpack / BatchNorm-backward kernels on a
+        # non-finite value, read on the device by FusedAdam, cleared at the start of the next backward)
+        if getattr(self, "overflow", None) is None:
+            self.overflow = torch.zeros(1, dtype=torch.int32, device=device)
+        self._S = 1.0
         self._gw_dirty = False
         self._pending_bucket = None
         self._init_side_stream(device)
@@ -164,6 +173,7 @@ class _EngineBase:
         """Force a re-pack of every 16-bit weight operand at the next forward (what an optimizer step causes)."""
         for pp in self._packed_params():
             pp.key = None
+        self._wo_key = None
 
     def _begin_backward(self):
         """The packed weight-gradient buffers are accumulated into by split-K launches and reset to zero by the
@@ -174,29 +184,47 @@ class _EngineBase:
         self._gw_dirty = True
         self._side_used = 0
         self._pending_bucket = None
+        self._clear_overflow()
 
     def _end_backward(self):
         self._gw_dirty = False
+
+    def _clear_overflow(self):
+        self.overflow.zero_()
+
+    def overflowed(self) -> bool:
+        """True when the last backward produced a non-finite gradient (synchronises; FusedAdam needs no such read:
+        it skips the step on the device).  A trainer may call this occasionally and lower `loss_scale_shift`."""
+        return bool(self.overflow.item())
+
+    loss_scale_shift = 0        # lowers the static loss scale by 2^shift (a trainer's reaction to overflowed())
 
     def loss_scale(self) -> float:
         """Power of two S with |S * dlogit| <= 2^-4 for a mean-reduced BCE (|dlogit| <= 1/numel): keeps the
         fp16 gradient tensors in the normal range with 2^20 headroom before overflow."""
         numel = self.ws["logits"].numel()
-        return float(2.0 ** (math.ceil(math.log2(numel)) - 4))
+        return float(2.0 ** (math.ceil(math.log2(numel)) - 4 - self.loss_scale_shift))
 
     def _scaled_dlogit(self, dlogit, prescaled):
-        self._S = self.loss_scale()
+        """prescaled: dlogit comes from loss_and_dlogit and carries loss_scale() (mean-reduced BCE: the bound on
+        |dlogit| is exact).  Otherwise it is the gradient of an arbitrary criterion: the power-of-two scale is chosen
+        from its measured magnitude (one host read of max|dlogit| -- only on this path, which the reference's
+        configured BCEWithLogitsLoss does not take)."""
         dlogit = dlogit.contiguous().float()
-        if not prescaled:
-            dlogit = torch.mul(dlogit, self._S, out=self.ws["dlogit_s"])
-        self._pending_unscale = True
-        return dlogit
+        if prescaled:
+            self._S = self.loss_scale()
+            return dlogit
+        amax = float(dlogit.abs().amax())
+        if not math.isfinite(amax) or amax <= 0.0:
+            self._S = self.loss_scale()
+        else:
+            self._S = float(2.0 ** max(-40, min(60, math.floor(math.log2(2.0 ** -4 / amax)) - self.loss_scale_shift)))
+        return torch.mul(dlogit, self._S, out=self.ws["dlogit_s"])
 
     def finalize_grads(self):
-        """Unscale the flat gradient arena (and flag non-finite values); called once all buckets are reduced."""
-        if self._pending_unscale:
-            ops.scale_check(self.arena, 1.0 / self._S, self.overflow)
-            self._pending_unscale = False
+        """Kept for callers of the round-1 API: gradients now leave every kernel already unscaled (the unpack,
+        BatchNorm-backward and bias-sum kernels take 1 / loss scale), so there is nothing left to do here."""
+        return None
 
     def loss_and_dlogit(self, logits, mask, grad_scale=1.0, thr=0.5):
         """Fused BCE forward + gradient.  The returned dlogit carries grad_scale * loss_scale():
@@ -271,7 +299,8 @@ class UNetEngine(_EngineBase):
                 self.up_gw[lvl] = self.up[lvl].spec.grad_buffer(d)
         # BN-backward sums of every layer in one buffer: the ones accumulated by dgrad epilogues are cleared by ONE fill
         layers = [L for grp in list(self.enc) + list(self.dec.values()) for L in grp]
-        self._bw_sums = _z((sum(L.cout for L in layers), 3), d, torch.float64)
+        self._bw_sums = _z((sum(L.cout for L in layers) + 1, 3), d, torch.float64)
+        self.overflow = self._bw_sums[-1].view(torch.int32)[:1]       # cleared by the same fill as the sums
         off = 0
         for L in layers:
             L.sums = self._bw_sums[off:off + L.cout]
@@ -440,7 +469,8 @@ class UNetEngine(_EngineBase):
         P = self.P
         ops.bn_relu_bwd(raw, L.scale, L.shift, L.smean, L.sinv, P[L.bn + ".weight"], R, L.sums, count, dy=dy,
                         dpool=dpool, head_w=head_w, dlogit=dlogit, dgamma=self._grad(L.bn + ".weight", L.scale[:L.cout]),
-                        dbeta=self._grad(L.bn + ".bias", L.scale[:L.cout]), dhead_w=dhead_w, reduced=reduced)
+                        dbeta=self._grad(L.bn + ".bias", L.scale[:L.cout]), dhead_w=dhead_w, reduced=reduced,
+                        out_scale=1.0 / self._S, flag=self.overflow)
         xg = self._as_grad_dtype(x_in)
         ready = self._fork()                 # R is complete here
         # the dgrad is on the critical path of backward: it is launched first so that it, not the weight gradient, gets
@@ -480,44 +510,64 @@ class UNetEngine(_EngineBase):
     def _conv_layers(self):
         return [L for grp in list(self.enc) + [self.dec[l] for l in (3, 2, 1, 0)] for L in grp]
 
-    def _jobs(self, layers):
+    def _jobs(self, layers, ups=()):
+        """Job records of the table-driven pack / unpack launches: 3x3 layers and (kind 1) the ConvTranspose2d of the
+        decoder levels in `ups`."""
         jobs = []
         for L in layers:
             w = self.P[L.conv + ".weight"]
             L.pp.alloc3x3(w.device)
             jobs.append(dict(w=w, fwd=L.pp.fwd, dgrad=L.pp.dgr, gpacked=L.gw, gdst=self.grads[L.conv + ".weight"],
                              cout=L.pp.spec.cout, cin=L.pp.spec.cin))
+        for l in ups:
+            up, wn = self.up[l], self.up_name[l] + ".weight"
+            w = self.P[wn]
+            up.alloc_convT(w.device)
+            jobs.append(dict(w=w, fwd=up.fwd, dgrad=up.dgr, gpacked=self.up_gw[l], gdst=self.grads[wn],
+                             cout=up.spec.cout, cin=up.spec.cin, kind=1))
         return jobs
 
-    def _table(self, name, layers):
+    def _table(self, name, layers, ups=()):
         """Cached device job table for a fixed list of layers (rebuilt if a parameter's storage moved)."""
-        key = tuple(self.P[L.conv + ".weight"].data_ptr() for L in layers)
+        key = tuple(self.P[L.conv + ".weight"].data_ptr() for L in layers) + \
+            tuple(self.P[self.up_name[l] + ".weight"].data_ptr() for l in ups)
         t = self._tables.get(name)
         if t is None or t.key != key:
-            t = ops.Conv3x3JobTable(self._jobs(layers), self.dev)
+            t = ops.Conv3x3JobTable(self._jobs(layers, ups), self.dev)
+            t.key = key
             self._tables[name] = t
         return t
+
+    def _up_levels(self):
+        return tuple(sorted(self.up.keys()))
 
     def _refresh_packed(self):
         """Re-pack stale 16-bit weight operands: one table-driven launch when every 3x3 layer is stale (the normal
         case after an optimizer step), per layer otherwise."""
         layers = self._conv_layers()
         P = self.P
-        if all(L.pp.stale(P[L.conv + ".weight"]) for L in layers):
-            ops.pack_conv3x3_batch(self._table("all", layers))
+        ups = self._up_levels()
+        if all(L.pp.stale(P[L.conv + ".weight"]) for L in layers) and \
+                all(self.up[l].stale(P[self.up_name[l] + ".weight"]) for l in ups):
+            ops.pack_conv3x3_batch(self._table("all", layers, ups))
             for L in layers:
                 w = P[L.conv + ".weight"]
                 L.pp.key = (w.data_ptr(), w._version)
+            for l in ups:
+                w = P[self.up_name[l] + ".weight"]
+                self.up[l].key = (w.data_ptr(), w._version)
 
     def _unpack_bucket(self, idx):
         """Gradients of the 3x3 layers of bucket idx: packed fp32 -> arena.  Without an all-reduce hook the nine
         buckets are unpacked by ONE launch at the end of backward."""
+        inv = 1.0 / self._S
         if self.bucket_hook is not None:
             l = idx if idx < 4 else 8 - idx
             grp = self.dec[l] if idx < 4 else self.enc[l]
-            ops.unpack_conv3x3_batch(self._table(f"bucket{idx}", [grp[1], grp[0]]))
+            ups = (l,) if (idx < 4 and l in self.up) else ()
+            ops.unpack_conv3x3_batch(self._table(f"bucket{idx}", [grp[1], grp[0]], ups), inv, self.overflow)
         elif idx == 8:
-            ops.unpack_conv3x3_batch(self._table("all", self._conv_layers()))
+            ops.unpack_conv3x3_batch(self._table("all", self._conv_layers(), self._up_levels()), inv, self.overflow)
 
     def forward_ingested(self, ws, training: bool) -> torch.Tensor:
         P, CE, U = self.P, self.CE, self.U
@@ -569,7 +619,7 @@ class UNetEngine(_EngineBase):
         dlogit = self._scaled_dlogit(dlogit, prescaled)
         cnt = [n * H[l] * W[l] for l in range(5)]
         head_w = P["outc.conv.weight"].detach().reshape(-1)
-        ops.sum_f32(dlogit, self._grad("outc.conv.bias", P["outc.conv.bias"]))
+        ops.sum_f32(dlogit, self._grad("outc.conv.bias", P["outc.conv.bias"]), scale=1.0 / self._S)
         for l in (0, 1, 2, 3):
             a, b = self.dec[l]
             fuse = self._fusable(l)
@@ -602,10 +652,10 @@ class UNetEngine(_EngineBase):
             gw = self.up_gw[l]
             wn = self.up_name[l] + ".weight"
 
-            def up_wgrad(x_up=self._as_grad_dtype(x_up), dy_up=dy_up, gw=gw, up=up, wn=wn, l=l):
+            def up_wgrad(x_up=self._as_grad_dtype(x_up), dy_up=dy_up, gw=gw, l=l):
+                # the packed gradient is unpacked with the bucket's 3x3 layers (_unpack_bucket)
                 ops.igemm_wgrad(x_up, dy_up, 2, 4 * U[l], gw)
-                up.spec.unpack_grad(gw, self._grad(wn, P[wn]).view(-1))
-                ops.colsum(dy_up, self._grad(self.up_name[l] + ".bias", P[self.up_name[l] + ".bias"]))
+                ops.colsum(dy_up, self._grad(self.up_name[l] + ".bias", P[self.up_name[l] + ".bias"]), scale=1.0 / self._S)
             self._on_side(up_wgrad)
             self._bucket_done(l)
         # encoder, deepest first
@@ -627,12 +677,13 @@ class UNetEngine(_EngineBase):
             self.grads["inc.0.weight"] = self.grads["first_conv.weight"]
             self.grads["inc.0.bias"] = self.grads["first_conv.bias"]
         self._end_backward()
-        if self.bucket_hook is None:
-            self.finalize_grads()
         return self.grads
 
     def _gw_buffers(self):
         return [L.gw for grp in list(self.enc) + list(self.dec.values()) for L in grp] + list(self.up_gw.values())
+
+    def _clear_overflow(self):
+        pass                                # backward()'s single fill of _bw_sums clears the flag too
 
     def _packed_params(self):
         return [L.pp for grp in list(self.enc) + list(self.dec.values()) for L in grp] + list(self.up.values())
@@ -682,7 +733,6 @@ class SpectralEngine(_EngineBase):
         self.grads = {k: self.arena[offs[k]: offs[k] + params[k].numel()].view(params[k].shape) for k in names}
         self.bucket_bounds = [(0, total)]
         self.w_outc = _z((2 * self.Fp,), d, torch.float32)
-        self.dw_outc = _z((2 * self.Fp,), d, torch.float32)
 
     def _gw_buffers(self):
         return [L.gw for L in self.L.values()]
@@ -733,10 +783,14 @@ class SpectralEngine(_EngineBase):
                     for half in (0, 1):   # dgrad operand rows follow the cat buffer: [0,F) and [Fp, Fp+F)
                         ops.pack(wc, G=1, R=F, T=1, Cc=F, sg=0, sr=1, st=0, sc=2 * F, src_offset=half * F,
                                  out=L.dgr_cat[half * Fp: half * Fp + F])
-        wo = P["outc.weight"].detach().reshape(-1)
-        self.w_outc.zero_()
-        self.w_outc[:F].copy_(wo[:F])
-        self.w_outc[Fp:Fp + F].copy_(wo[F:])
+        wo_p = P["outc.weight"]
+        wo_key = (wo_p.data_ptr(), wo_p._version)
+        if getattr(self, "_wo_key", None) != wo_key:        # padded copy of the head weights, refreshed when they change
+            wo = wo_p.detach().reshape(-1)
+            self.w_outc.zero_()
+            self.w_outc[:F].copy_(wo[:F])
+            self.w_outc[Fp:Fp + F].copy_(wo[F:])
+            self._wo_key = wo_key
 
     def _grad(self, name, like=None):
         return self.grads[name]
@@ -795,14 +849,15 @@ class SpectralEngine(_EngineBase):
         ws, P, F, Fp, m = self.ws, self.P, self.F, self.Fp, self.ws["m"]
         self._begin_backward()
         dlogit = self._scaled_dlogit(dlogit, prescaled)
-        ops.sum_f32(dlogit, self._grad("outc.bias", P["outc.bias"]))
-        first_img = True
-        dwo_acc = torch.zeros_like(self.dw_outc)
+        inv = 1.0 / self._S
+        ops.sum_f32(dlogit, self._grad("outc.bias", P["outc.bias"]), scale=inv)
+        go = self._grad("outc.weight", P["outc.weight"]).view(-1)      # [x0 features | up4 features] (models.py:143)
         r_turn, r_busy = 0, {}
         for i in range(ws["n"]):
             im = ws["img"][i]
             dl = dlogit[i].reshape(-1)
             xin = ws["x"][i].reshape(1, 1, m, self.Dp)
+            acc_beta = 0.0 if i == 0 else 1.0          # parameter gradients accumulate over the per-image launches
             # (block, dy source, dgrad destination, accumulate?)
             plan = [("up4", None, ws["gcat2"], False), ("up3", ws["gcat2"][..., Fp:], ws["gcat3"], False),
                     ("up2", ws["gcat3"][..., Fp:], ws["gcat4"], False), ("up1", ws["gcat4"][..., Fp:], ws["g4"], False),
@@ -816,26 +871,20 @@ class SpectralEngine(_EngineBase):
                     src = xin
                 scale, shift, smean, sinv = im["bn"][nm]
                 head = nm in ("up4", "tail")
-                hw = None
-                dhw = None
-                if head:
+                hw = dhw = None
+                if head:                               # the OutConv reads cat(x0, up4 output): its two halves
                     off = Fp if nm == "up4" else 0
                     hw = self.w_outc[off:off + Fp]
-                    dhw = self.dw_outc[off:off + Fp]
-                dg = torch.empty(F, dtype=torch.float32, device=self.dev)
-                db = torch.empty(F, dtype=torch.float32, device=self.dev)
+                    dhw = go[F:] if nm == "up4" else go[:F]
                 k = r_turn % len(ws["R"])
                 r_turn += 1
                 R = ws["R"][k]
                 self._join(r_busy.get(k))          # the weight gradient that last read this buffer has finished
                 ops.bn_relu_bwd(im["raw_" + nm], scale, shift, smean, sinv, P[nm + ".1.weight"], R, L.sums, m, dy=dy,
-                                head_w=hw, dlogit=dl if head else None, dgamma=dg, dbeta=db, dhead_w=dhw, c=F)
-                g_g = self._grad(nm + ".1.weight", P[nm + ".1.weight"])
-                g_b = self._grad(nm + ".1.bias", P[nm + ".1.bias"])
-                if first_img:
-                    g_g.copy_(dg); g_b.copy_(db)
-                else:
-                    g_g.add_(dg); g_b.add_(db)
+                                head_w=hw, dlogit=dl if head else None,
+                                dgamma=self._grad(nm + ".1.weight", P[nm + ".1.weight"]),
+                                dbeta=self._grad(nm + ".1.bias", P[nm + ".1.bias"]), dhead_w=dhw, c=F,
+                                out_scale=inv, out_beta=acc_beta, flag=self.overflow)
                 xg = src if src.dtype == GRAD else ops.convert16(src, ws["cvt"][..., :src.shape[-1]])
                 self._on_side(lambda xg=xg, R=R, L=L, nm=nm: ops.igemm_wgrad(
                     xg, R, 0, F, L.gw, x_c=(self.D if nm == "tail" else None), dy_c=F))
@@ -845,19 +894,11 @@ class SpectralEngine(_EngineBase):
                         ops.igemm_fwd(R, L.dgr_cat, 2 * Fp, 1, dx_dst, 2 * Fp, x_c=F, accumulate=acc)
                     else:
                         ops.igemm_fwd(R, L.pp.dgr, F, 1, dx_dst, Fp, x_c=F, accumulate=acc, block_n=self.bn_tile)
-            dwo_acc.add_(self.dw_outc)
-            first_img = False
         self._join(self._side_mark())
         for nm, L in self.L.items():
             wn = nm + ".0.weight"
-            L.pp.spec.unpack_grad(L.gw, self._grad(wn, P[wn]).view(-1))
-            self._grad(nm + ".0.bias", P[nm + ".0.bias"])
-        go = self._grad("outc.weight", P["outc.weight"]).view(-1)
-        go[:F].copy_(dwo_acc[:F])
-        go[F:].copy_(dwo_acc[Fp:Fp + F])
+            L.pp.spec.unpack_grad(L.gw, self._grad(wn, P[wn]).view(-1), scale=inv, flag=self.overflow)
         self._end_backward()
         if self.bucket_hook is not None:
             self.bucket_hook(self.arena)
-        else:
-            self.finalize_grads()
         return self.grads

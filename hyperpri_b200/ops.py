@@ -88,12 +88,13 @@ def pack(src: torch.Tensor, G, R, T, Cc, sg, sr, st, sc, flip=False, out: Option
 
 @_timed
 def unpack(packed: torch.Tensor, dst: torch.Tensor, G, R, T, Cc, sg, sr, st, sc, flip=False, beta=0.0,
-           zero_src=False):
-    """Packed fp32 gradient -> torch layout.  zero_src: reset `packed` to zero behind the read (the split-K
-    weight-gradient kernel accumulates into it, so this replaces a memset before the next step)."""
+           zero_src=False, scale=1.0, flag=None):
+    """Packed fp32 gradient -> torch layout: dst = beta * dst + scale * packed.  zero_src: reset `packed` to zero behind
+    the read (the split-K weight-gradient kernel accumulates into it, so this replaces a memset before the next step).
+    flag (int32 tensor): raised on a non-finite value."""
     assert packed.dtype == torch.float32 and dst.dtype == torch.float32 and dst.is_contiguous()
     check(_lib.lib().hpri_unpack_grads(_ptr(packed), _ptr(dst), G, R, T, Cc, kpad(Cc), sg, sr, st, sc, int(flip),
-                                       float(beta), int(zero_src), _stream()), "hpri_unpack_grads")
+                                       float(beta), int(zero_src), float(scale), _ptr(flag), _stream()), "hpri_unpack_grads")
     return dst
 
 
@@ -114,7 +115,7 @@ def unpack_conv3x3(packed, cout, cin, dst):
 
 class Conv3x3JobTable:
     """Device table of hpri_conv3x3_job_t for the table-driven pack / unpack launches.  jobs: dicts with keys
-    w, fwd, dgrad (or None), gpacked, gdst, cout, cin."""
+    w, fwd, dgrad (or None), gpacked, gdst, cout, cin and optionally kind (0 conv3x3, 1 ConvTranspose2d k2 s2)."""
 
     def __init__(self, jobs, device):
         arr = (_lib.Conv3x3Job * len(jobs))()
@@ -128,6 +129,7 @@ class Conv3x3JobTable:
             arr[i].cout, arr[i].cin = j["cout"], j["cin"]
             arr[i].fwd_dtype = _DT[j["fwd"].dtype]
             arr[i].dgrad_dtype = 0 if j.get("dgrad") is None else _DT[j["dgrad"].dtype]
+            arr[i].kind = int(j.get("kind", 0))
             arr[i].tile0 = tiles
             tiles += ((j["cin"] + 31) // 32) * ((j["cout"] + 31) // 32)
         raw = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
@@ -142,8 +144,10 @@ def pack_conv3x3_batch(table: Conv3x3JobTable):
 
 
 @_timed
-def unpack_conv3x3_batch(table: Conv3x3JobTable):
-    check(_lib.lib().hpri_unpack_conv3x3_batch(_ptr(table.dev), table.n, table.tiles, _stream()),
+def unpack_conv3x3_batch(table: Conv3x3JobTable, scale=1.0, flag=None):
+    """gdst = scale * gpacked for every job of the table (packed buffers zeroed behind the read); flag: raised on a
+    non-finite value."""
+    check(_lib.lib().hpri_unpack_conv3x3_batch(_ptr(table.dev), table.n, table.tiles, float(scale), _ptr(flag), _stream()),
           "hpri_unpack_conv3x3_batch")
 
 
@@ -203,14 +207,14 @@ class WeightSpec:
         f = self.fwd
         return torch.zeros((f["G"] * f["R"], f["T"] * kpad(f["Cc"])), dtype=torch.float32, device=device)
 
-    def unpack_grad(self, packed, dst, beta=0.0):
+    def unpack_grad(self, packed, dst, beta=0.0, scale=1.0, flag=None):
         """Unpack AND reset `packed` to zero (ready for the next accumulation)."""
-        if self.kind == "conv3x3" and beta == 0.0:
+        if self.kind == "conv3x3" and beta == 0.0 and scale == 1.0 and flag is None:
             return unpack_conv3x3(packed, self.cout, self.cin, dst)
-        if self.kind == "convT2x2" and beta == 0.0:
+        if self.kind == "convT2x2" and beta == 0.0 and scale == 1.0 and flag is None:
             return unpack_convT(packed, self.cin, self.cout, dst)
         f = dict(self.fwd)
-        return unpack(packed, dst, beta=beta, zero_src=True, **f)
+        return unpack(packed, dst, beta=beta, zero_src=True, scale=scale, flag=flag, **f)
 
 
 # ----------------------------------------------------------------------------- contractions
@@ -358,8 +362,10 @@ def bn_relu_apply(x, scale, shift, y, pooled=None, c=None):
 
 @_timed
 def bn_relu_bwd(x, scale, shift, smean, sinv, gamma, dx, sums, count, dy=None, dpool=None, head_w=None,
-                dlogit=None, dgamma=None, dbeta=None, dhead_w=None, c=None, reduced=False):
-    """reduced=True: `sums` was already accumulated by the dgrad launch that produced dy (igemm_fwd(bw=...))."""
+                dlogit=None, dgamma=None, dbeta=None, dhead_w=None, c=None, reduced=False, out_scale=1.0, out_beta=0.0,
+                flag=None):
+    """reduced=True: `sums` was already accumulated by the dgrad launch that produced dy (igemm_fwd(bw=...)).
+    dgamma / dbeta / dhead_w = out_beta * (old) + out_scale * (reduced sums); flag: raised on a non-finite value."""
     xv, dyv, dpv, dxv = view(x, c), view(dy, c), view(dpool, c), view(dx, c)
     L = _lib.lib()
     if not reduced:
@@ -367,7 +373,8 @@ def bn_relu_bwd(x, scale, shift, smean, sinv, gamma, dx, sums, count, dy=None, d
                                         _ptr(head_w), _ptr(dlogit), _ptr(sums), _stream()), "hpri_bn_relu_bwd_reduce")
     check(L.hpri_bn_relu_bwd_apply(_vp(xv), _ptr(scale), _ptr(shift), _ptr(smean), _ptr(sinv), _ptr(gamma), _vp(dyv),
                                    _vp(dpv), _ptr(head_w), _ptr(dlogit), _ptr(sums), count, _vp(dxv), _ptr(dgamma),
-                                   _ptr(dbeta), _ptr(dhead_w), _stream()), "hpri_bn_relu_bwd_apply")
+                                   _ptr(dbeta), _ptr(dhead_w), float(out_scale), float(out_beta), _ptr(flag), _stream()),
+          "hpri_bn_relu_bwd_apply")
 
 
 # ----------------------------------------------------------------------------- head / loss
@@ -387,9 +394,10 @@ def bce_fwd_bwd(logits, target, loss_sum, dlogit=None, counts=None, grad_scale=1
 
 
 @_timed
-def colsum(x, out, beta=0.0, c=None):
+def colsum(x, out, beta=0.0, c=None, scale=1.0):
+    """out[c] = beta * out[c] + scale * sum over the pixels of x."""
     xv = view(x, c)
-    check(_lib.lib().hpri_colsum(_vp(xv), _ptr(out), beta, _stream()), "hpri_colsum")
+    check(_lib.lib().hpri_colsum(_vp(xv), _ptr(out), float(beta), float(scale), _stream()), "hpri_colsum")
 
 
 @_timed
@@ -399,8 +407,8 @@ def scale_check(x, scale, flag):
 
 
 @_timed
-def sum_f32(x, out):
-    check(_lib.lib().hpri_sum_f32(_ptr(x), x.numel(), _ptr(out), _stream()), "hpri_sum_f32")
+def sum_f32(x, out, scale=1.0):
+    check(_lib.lib().hpri_sum_f32(_ptr(x), x.numel(), _ptr(out), float(scale), _stream()), "hpri_sum_f32")
 
 
 # ----------------------------------------------------------------------------- validation histograms

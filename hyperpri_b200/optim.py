@@ -16,11 +16,16 @@ from ._lib import check
 
 
 class FusedAdam(torch.optim.Optimizer):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, found_inf=None):
+        """found_inf: optional int32 CUDA tensor (the engine's overflow flag, hyperpri_b200.engine._EngineBase.overflow).
+        While it is non-zero the launch leaves parameters and moments untouched (the step is skipped on the device,
+        without a host synchronisation); `skipped_steps()` reads how often that happened."""
         if lr < 0 or eps < 0 or not 0 <= betas[0] < 1 or not 0 <= betas[1] < 1 or weight_decay < 0:
             raise ValueError("invalid Adam hyper-parameters")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._tables = {}
+        self.found_inf = found_inf
+        self._skipped = None
 
     def _table(self, gi, plist):
         key = tuple((p.data_ptr(), p.grad.data_ptr(), self.state[p]["exp_avg"].data_ptr()) for p in plist)
@@ -64,8 +69,17 @@ class FusedAdam(torch.optim.Optimizer):
             b1, b2 = group["betas"]
             check(_lib.lib().hpri_adam_step(C.c_void_p(dev.data_ptr()), n, blocks, float(group["lr"]), float(b1),
                                             float(b2), float(group["eps"]), float(group["weight_decay"]), step,
+                                            C.c_void_p(0 if self.found_inf is None else self.found_inf.data_ptr()),
                                             C.c_void_p(torch.cuda.current_stream().cuda_stream)), "hpri_adam_step")
+            if self.found_inf is not None:            # device-side tally of skipped steps (no synchronisation)
+                if self._skipped is None:
+                    self._skipped = torch.zeros(1, dtype=torch.int64, device=self.found_inf.device)
+                self._skipped += (self.found_inf != 0)
             for p in plist:
                 self.state[p]["step"] += 1
                 torch.autograd.graph.increment_version(p)     # the engine re-packs operands of changed parameters
         return loss
+
+    def skipped_steps(self) -> int:
+        """Steps the device skipped because the loss-scaled fp16 gradients overflowed (synchronises)."""
+        return 0 if self._skipped is None else int(self._skipped.item())

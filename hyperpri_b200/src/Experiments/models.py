@@ -9,6 +9,7 @@ import torch.nn as nn
 
 from .model_parts import DoubleConv, Down, Up, OutConv
 from ... import engine as _engine
+from ... import ops as _lib_ops
 
 
 def set_parameter_requires_grad(model, feature_extraction):
@@ -17,9 +18,45 @@ def set_parameter_requires_grad(model, feature_extraction):
             param.requires_grad = False
 
 
+def _deliver_grads(net, eng, run_backward):
+    """Run the engine backward and hand its gradients to the module's Parameters WITHOUT copies: the engine keeps every
+    parameter gradient in one flat fp32 arena, and a Parameter whose ``.grad`` is None (what ``zero_grad()`` leaves by
+    default) simply gets the arena view as its ``.grad``.  Returned to autograd: None for those, the view for
+    Parameters that already hold a gradient of their own (autograd then accumulates, as usual).  A ``.grad`` that still
+    aliases the arena from the previous step (``zero_grad(set_to_none=False)``, or deliberate gradient accumulation) is
+    kept exact too: the arena is snapshotted before the engine overwrites it and added back afterwards.
+    Consequences of the zero-copy hand-over: ``p.grad`` is overwritten in place by the next backward, and
+    ``register_post_accumulate_grad_hook`` hooks do not fire for gradients delivered this way."""
+    params = net._hot_params()
+    aliased = any(p.grad is not None and p.grad.data_ptr() == eng.grads[name].data_ptr() for name, p in params
+                  if name in eng.grads)
+    prev = eng.arena.clone() if aliased else None
+    grads = run_backward()
+    if eng.bucket_hook is not None:
+        # data-parallel: buckets were handed to the all-reduce as they completed; finish() waits for them and unscales
+        owner = getattr(eng.bucket_hook, "__self__", None)
+        if owner is not None:
+            owner.finish()
+    if prev is not None:
+        eng.arena.add_(prev)
+    out = []
+    for name, p in params:
+        g = grads[name] if p.requires_grad else None
+        if g is None:
+            out.append(None)
+        elif p.grad is None:
+            p.grad = g
+            out.append(None)
+        elif p.grad.data_ptr() == g.data_ptr():
+            out.append(None)
+        else:
+            out.append(g)
+    return out
+
+
 class _NetFn(torch.autograd.Function):
-    """forward: engine forward (NHWC bf16 workspace) -> fp32 logits; backward: engine backward ->
-    one fp32 gradient per parameter, in the order the parameters were passed."""
+    """forward: engine forward (NHWC 16-bit workspace) -> fp32 logits; backward: engine backward -> gradients delivered
+    by _deliver_grads."""
 
     @staticmethod
     def forward(ctx, net, x, *params):
@@ -32,18 +69,37 @@ class _NetFn(torch.autograd.Function):
     def backward(ctx, dlogits):
         net = ctx.net
         eng = net._get_engine(ctx.dev)
-        grads = eng.backward(dlogits)
-        if eng.bucket_hook is not None:
-            # data-parallel: buckets were handed to the all-reduce as they completed; its owner's finish()
-            # unscales them.  The clones below are taken after that (the caller invokes finish() right after
-            # loss.backward(); clone views stay scaled-consistent because unscaling is in place on the arena).
-            owner = getattr(eng.bucket_hook, "__self__", None)
-            if owner is not None:
-                owner.finish()
-        out = []
-        for name, p in net._hot_params():
-            out.append(grads[name].clone() if p.requires_grad else None)
-        return (None, None, *out)
+        return (None, None, *_deliver_grads(net, eng, lambda: eng.backward(dlogits)))
+
+
+class _NetLossFn(torch.autograd.Function):
+    """Network + mean-reduced BCEWithLogitsLoss in one node (the reference's step body, PLTrainer.py:83-91): the fused
+    head / loss kernel produces the loss, the loss-scaled logit gradient and the TP/FP/FN/TN counts at `thr` in one
+    pass over the logits; backward starts from that stored gradient.  Outputs: (loss, logits, counts); logits and
+    counts are not differentiable (the reference only uses them detached)."""
+
+    @staticmethod
+    def forward(ctx, net, x, target, thr, grad_scale, *params):
+        eng = net._get_engine(x.device)
+        logits = eng.forward(x, True)
+        loss_sum, _, counts = eng.loss_and_dlogit(logits, target, grad_scale=grad_scale, thr=thr)
+        ctx.net, ctx.dev = net, x.device
+        ctx.set_materialize_grads(False)
+        loss = (loss_sum / logits.numel()).float()
+        lg, cn = logits.clone(), counts.clone()
+        ctx.mark_non_differentiable(lg, cn)
+        return loss, lg, cn
+
+    @staticmethod
+    def backward(ctx, gloss, _glogits=None, _gcounts=None):
+        net = ctx.net
+        eng = net._get_engine(ctx.dev)
+        if gloss is None:
+            raise RuntimeError("the fused network + BCE node was differentiated without a loss gradient")
+        ws = eng.ws
+        dl = torch.mul(ws["dlogit"], gloss.to(ws["dlogit"].dtype), out=ws["dlogit_s"])   # 4.7 MB; dlogit carries the loss scale
+        grads = _deliver_grads(net, eng, lambda: eng.backward(dl, prescaled=True))
+        return (None, None, None, None, None, *grads)
 
 
 class _EngineNet(nn.Module):
@@ -80,6 +136,22 @@ class _EngineNet(nn.Module):
         if torch.is_grad_enabled() and any(p.requires_grad for p in params):
             return _NetFn.apply(self, x, *params)
         return self._get_engine(x.device).forward(x, self.training).clone()
+
+    def bce_step(self, x, target, thr=0.5, grad_scale=1.0):
+        """forward + mean BCEWithLogitsLoss (+ its gradient and the segmentation counts at `thr`) through the fused
+        kernels: returns (loss, logits, counts[TP, FP, FN, TN]).  With autograd enabled in train mode, `loss.backward()`
+        runs the engine backward from the stored logit gradient (scaled by `grad_scale`, e.g. 1 / world size)."""
+        if x.device != next(self.parameters()).device:
+            raise RuntimeError("input and parameters are on different devices")
+        target = target.contiguous().float()
+        params = [p for _, p in self._hot_params()]
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            return _NetLossFn.apply(self, x, target, float(thr), float(grad_scale), *params)
+        eng = self._get_engine(x.device)
+        logits = eng.forward(x, self.training)
+        ws = eng.ws
+        _lib_ops.bce_fwd_bwd(logits, target, ws["loss_sum"], None, ws["counts"], thr=float(thr))
+        return (ws["loss_sum"] / logits.numel()).float(), logits.clone(), ws["counts"].clone()
 
     def _finish(self, logits):
         if getattr(self, "analyze", False):

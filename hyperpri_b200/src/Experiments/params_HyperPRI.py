@@ -76,7 +76,9 @@ class ExpRedGreenBluePRI(_ExpBase):
         self._paths(calling_path, comet_logging)
 
     def translate_load_dir(self):
-        return "UNET"
+        if self.model_name.lower() in ('unet', 'unet+'):      # params_HyperPRI.py:108-115: 'UNET+' runs get their own directory
+            return self.model_name
+        raise ValueError(f"{self.model_name} is not in list of possible models\n   (accepted: UNET, UNET+)")
 
     def get_network(self):
         if self.model_name in ('UNET', 'UNET+'):
@@ -116,6 +118,10 @@ class ExpHyperspectralPRI(_ExpBase):
         self.model_name = "CubeNET"
         self.mlp_layers, self.test_deepspeed = [1650] * 10, False
         self.spectral_bn_size, self.cube_featmaps = 1650, 64
+        # extension (not in the reference): the loaders convert HSI cubes to fp16 before the host->device copy; the
+        # ingest kernel rounds fp32 cubes to fp16 anyway, so the network input is bit-identical and the PCIe bytes
+        # halve.  torch.float32 restores the reference's item dtype.
+        self.hsi_host_dtype = torch.float16
         self._paths(calling_path, comet_logging)
 
     def translate_load_dir(self):
@@ -140,7 +146,7 @@ class ExpHyperspectralPRI(_ExpBase):
 
     def _hsi(self, img_tf, gt_tf, split):
         return self._dataset(img_tf, gt_tf, split, 'HSI', unsqueeze_img=self.model_name.lower() == 'cubenet',
-                             hsi_lo=self.hsi_lo, hsi_hi=self.hsi_hi)
+                             hsi_lo=self.hsi_lo, hsi_hi=self.hsi_hi, host_dtype=self.hsi_host_dtype)
 
     def get_train_data(self):
         return self._hsi(self.train_transforms, self.gt_transforms, 'train')

@@ -110,8 +110,11 @@ int hpri_igemm_wgrad(const hpri_view_t* x, const hpri_view_t* dy, int mode, int 
  * pack: fp32 torch-layout parameter -> 16-bit operand (dst_dtype).  unpack: fp32 packed gradient -> fp32 torch layout. */
 int hpri_pack_weights(const float* src, void* dst, int dst_dtype, int G, int R, int T, int C, int kc64, long long sg,
                       long long sr, long long st, long long sc, int flip, void* stream);
+/* unpack: dst = beta * dst + scale * packed (scale removes the power-of-two loss scale of the fp16 gradient path);
+ * a non-finite result sets *flag (nullable) -- the overflow signal hpri_adam_step reads on the device. */
 int hpri_unpack_grads(float* packed, float* dst, int G, int R, int T, int C, int kc64, long long sg,
-                      long long sr, long long st, long long sc, int flip, float beta, int zero_src, void* stream);
+                      long long sr, long long st, long long sc, int flip, float beta, int zero_src, float scale,
+                      int* flag, void* stream);
 
 /* Tiled conv3x3 specialisations: W[co][ci][3][3] -> forward operand and (optional) transposed, tap-flipped dgrad
  * operand in one pass (destination buffers must be zero-initialised once: padding is never written); and the
@@ -125,16 +128,19 @@ int hpri_unpack_conv3x3(float* packed, int cout, int cin, float* dst, void* stre
  * the gradients of a whole bucket (18 launches of ~14 us each were latency-, not bandwidth-bound).  `jobs` is a DEVICE
  * array; tile0 = number of 32x32 (co, ci) tiles of all previous jobs; total_tiles = tiles of all jobs. */
 typedef struct {
-  const float* w;       /* [cout][cin][3][3] */
-  void* dst_fwd;        /* [cout][9*kpad(cin)] or null */
-  void* dst_dgrad;      /* [cin][9*kpad(cout)] or null */
-  float* grad_packed;   /* unpack: [cout][9*kpad(cin)] fp32 (zeroed behind the read) */
-  float* grad_dst;      /* unpack: [cout][cin][3][3] */
+  const float* w;       /* kind 0: [cout][cin][3][3]; kind 1: [cin][cout][2][2] */
+  void* dst_fwd;        /* kind 0: [cout][9*kpad(cin)]; kind 1: [4*cout][kpad(cin)]; or null */
+  void* dst_dgrad;      /* kind 0: [cin][9*kpad(cout)]; kind 1: [cin][4*kpad(cout)]; or null */
+  float* grad_packed;   /* unpack: fp32 in the dst_fwd layout (zeroed behind the read) */
+  float* grad_dst;      /* unpack: fp32 in the layout of w */
   int cout, cin, fwd_dtype, dgrad_dtype;
-  int tile0, pad_;
+  int tile0;            /* number of 32 x 32 (co, ci) tiles of all previous jobs */
+  int kind;             /* 0 conv3x3, 1 ConvTranspose2d(k=2,s=2) */
 } hpri_conv3x3_job_t;
 int hpri_pack_conv3x3_batch(const hpri_conv3x3_job_t* jobs, int njobs, int total_tiles, void* stream);
-int hpri_unpack_conv3x3_batch(const hpri_conv3x3_job_t* jobs, int njobs, int total_tiles, void* stream);
+/* grad_dst = scale * grad_packed for every job; a non-finite value sets *flag (nullable). */
+int hpri_unpack_conv3x3_batch(const hpri_conv3x3_job_t* jobs, int njobs, int total_tiles, float scale, int* flag,
+                              void* stream);
 
 /* ---- validation maths (src/PLTrainer.py:538-583: binned PR curve with thresholds=500, best-Dice threshold, counts) ----
  * One pass over a batch of logits accumulates (+=, caller zeroes once per sweep):
@@ -160,8 +166,10 @@ typedef struct {
   long long numel;
   int block0, pad_;
 } hpri_adam_job_t;
+/* found_inf (nullable, device): when *found_inf != 0 the launch leaves parameters and moments untouched -- the
+ * gradients of this step overflowed the loss-scaled fp16 range (set by the unpack / BatchNorm-backward kernels). */
 int hpri_adam_step(const hpri_adam_job_t* jobs, int njobs, int total_blocks, double lr, double beta1, double beta2,
-                   double eps, double weight_decay, int step, void* stream);
+                   double eps, double weight_decay, int step, const int* found_inf, void* stream);
 
 /* ConvTranspose2d(k=2,s=2): W[ci][co][2][2] <-> forward operand [(a*2+b)*cout + co][kpad(ci)] (a (ci, co) transpose,
  * tiled through shared memory); unpack zeroes the packed gradient behind the read.  Padding columns are not written. */
@@ -212,6 +220,9 @@ int hpri_bn_relu_apply(const hpri_view_t* x, const float* scale, const float* sh
 /* Backward of relu(bn(x)): pass 1 reduces sum(dz), sum(dz*xhat); pass 2 writes dx.
  * dy (nullable) direct gradient; dpool (nullable) gradient of the pooled output, routed to the arg-max;
  * head_w/dlogit (nullable): dy[p,c] += dlogit[p]*head_w[c] (OutConv backward, model_parts.py:96). */
+/* _apply also writes the parameter gradients from the reduced sums: d{gamma,beta,head_w} = out_beta * (old) +
+ * out_scale * sum (out_scale removes the loss scale; out_beta = 1 accumulates over per-image launches); a non-finite
+ * value sets *flag (nullable). */
 int hpri_bn_relu_bwd_reduce(const hpri_view_t* x, const float* scale, const float* shift, const float* save_mean,
                             const float* save_invstd, const hpri_view_t* dy, const hpri_view_t* dpool,
                             const float* head_w, const float* dlogit, double* sums /*[C][3]*/, void* stream);
@@ -219,7 +230,7 @@ int hpri_bn_relu_bwd_apply(const hpri_view_t* x, const float* scale, const float
                            const float* save_invstd, const float* gamma, const hpri_view_t* dy,
                            const hpri_view_t* dpool, const float* head_w, const float* dlogit, double* sums,
                            long long count, const hpri_view_t* dx, float* dgamma, float* dbeta, float* dhead_w,
-                           void* stream);
+                           float out_scale, float out_beta, int* flag, void* stream);
 
 /* ---- head + loss (model_parts.py:96; PLTrainer.py:86) ------------------------------------ */
 /* logits[n,0,h,w] = b + sum_c relu(x*scale+shift)[c]*w[c]; fp32 NCHW output. */
@@ -228,9 +239,10 @@ int hpri_head_fwd(const hpri_view_t* x, const float* scale, const float* shift, 
 /* mean BCE-with-logits and dlogit = grad_scale*(sigmoid(x)-t)/numel; counts = TP,FP,FN,TN at thr. */
 int hpri_bce_fwd_bwd(const float* logits, const float* target, long long numel, float grad_scale, float thr,
                      double* loss_sum, float* dlogit, unsigned long long* counts, void* stream);
-/* out[c] (+)= sum over pixels of the view (ConvT bias grad; Linear bias grad). */
-int hpri_colsum(const hpri_view_t* x, float* out, float beta, void* stream);
-int hpri_sum_f32(const float* x, long long numel, float* out, void* stream);
+/* out[c] = beta * out[c] + scale * sum over pixels of the view (ConvT bias grad; Linear bias grad);
+ * out[0] = scale * sum(x). */
+int hpri_colsum(const hpri_view_t* x, float* out, float beta, float scale, void* stream);
+int hpri_sum_f32(const float* x, long long numel, float* out, float scale, void* stream);
 /* x *= scale in place; *flag |= 1 if any result is non-finite (unscaling of loss-scaled fp16 gradients). */
 int hpri_scale_check(float* x, long long numel, float scale, int* flag, void* stream);
 

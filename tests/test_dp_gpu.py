@@ -1,7 +1,7 @@
 """Two GPUs, NCCL: the data-parallel gradient exchange on the real engine (reference PLTrainer.py:434-442, Lightning
 "ddp": per-rank BatchNorm, gradients averaged over ranks).  Each rank runs CubeNET on its own shard with the bucketed
 all-reduce hook attached (weight gradients on the side stream, buckets flushed one late).  Checked: (1) exactly -- the
-final arena is (sum over ranks of the local bucket contents at hook time) / loss scale, every arena element belongs to
+final arena is the sum over ranks of the local (already unscaled) bucket contents at hook time, every arena element belongs to
 one bucket, both ranks end bit-identical; (2) against the mean of the two shards' single-process gradients by cosine
 similarity (tiny random-init nets amplify fp16 rounding differences between runs, see test_models_gpu.py).
 Skipped on a one-GPU box."""
@@ -75,7 +75,7 @@ def _worker(rank, world, port, q):
         both = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(both, mine)
         off = (ptr - base) // 4
-        want = (both[0] + both[1]) * (1.0 / eng._S)
+        want = both[0] + both[1]           # buckets leave the unpack kernels already unscaled (1 / loss scale folded in)
         exact = exact and torch.equal(eng.arena[off:off + mine.numel()], want)
     q.put((rank, {k: v.cpu() for k, v in out.items()}, int(eng.overflow.item()), exact))
     dist.barrier()

@@ -510,3 +510,122 @@ def test_upsample2_bilinear_align_corners_fwd_bwd(n, h, w, c, ph, pw):
     yr.backward(g[..., c:].float().permute(0, 3, 1, 2))
     want = xr.grad.permute(0, 2, 3, 1)
     assert float((dx.float() - want).abs().max()) <= 3e-3 * float(want.abs().max()) + 1e-3
+
+
+@pytest.mark.parametrize("c,dt", [(64, FH), (256, FH), (128, BF)])
+def test_bn_contiguous_kernels_match_the_strided_ones(c, dt):
+    """Dense tensors take the block-contiguous kernels (bn_*_contig_k); the same values embedded in a wider buffer
+    (pixel stride != C) take the strided flat kernels.  Same arithmetic: forward bit-equal, backward equal up to the
+    order of the fp64 reductions."""
+    n, h, w = 2, 11, 19
+    cnt = n * h * w
+    raw_d = nhwc(rnd(n, c, h, w, seed=80), dt=dt)
+    dy_d = nhwc(rnd(n, c, h, w, seed=81), dt=dt)
+    wide = lambda t: torch.cat([t, torch.zeros_like(t)], -1)[..., :c]          # view with pix_stride = 2c
+    raw_s, dy_s = wide(raw_d), wide(dy_d)
+    assert raw_s.stride(2) == 2 * c and raw_d.stride(2) == c
+    scale = torch.rand(c, device=DEV) + 0.5
+    shift = torch.randn(c, device=DEV) * 0.3
+    mean = torch.randn(c, device=DEV) * 0.1
+    inv = torch.rand(c, device=DEV) + 0.5
+    gamma = torch.rand(c, device=DEV) + 0.5
+    y_d = torch.empty_like(raw_d)
+    y_s = wide(torch.empty_like(raw_d))
+    ops.bn_relu_apply(raw_d, scale, shift, y_d)
+    ops.bn_relu_apply(raw_s, scale, shift, y_s)
+    assert torch.equal(y_d, y_s)
+    out = {}
+    for tag, raw, dy in (("d", raw_d, dy_d), ("s", raw_s, dy_s)):
+        dx = torch.empty_like(raw_d) if tag == "d" else wide(torch.empty_like(raw_d))
+        sums = torch.zeros((c, 3), dtype=torch.float64, device=DEV)
+        dg, db = torch.zeros(c, device=DEV), torch.zeros(c, device=DEV)
+        ops.bn_relu_bwd(raw, scale, shift, mean, inv, gamma, dx, sums, cnt, dy=dy, dgamma=dg, dbeta=db)
+        out[tag] = (dx.float().clone(), sums.clone(), dg, db)
+    torch.cuda.synchronize()
+    assert torch.allclose(out["d"][1], out["s"][1], rtol=1e-9, atol=1e-9)
+    assert relerr(out["d"][0], out["s"][0]) < (2e-3 if dt == FH else 1.6e-2)      # at most an output ulp
+    assert torch.allclose(out["d"][2], out["s"][2], rtol=1e-6) and torch.allclose(out["d"][3], out["s"][3], rtol=1e-6)
+
+
+def test_param_grads_are_unscaled_accumulated_and_flagged():
+    """hpri_bn_relu_bwd_apply writes d{gamma,beta} = out_beta * old + out_scale * sum and raises the overflow flag on a
+    non-finite value; hpri_colsum / hpri_sum_f32 / the unpack kernels take the same 1 / loss-scale factor."""
+    n, h, w, c = 1, 9, 10, 64
+    raw, dy = nhwc(rnd(n, c, h, w, seed=90), dt=FH), nhwc(rnd(n, c, h, w, seed=91), dt=FH)
+    scale = torch.rand(c, device=DEV) + 0.5
+    shift = torch.randn(c, device=DEV) * 0.3
+    mean, inv, gamma = torch.zeros(c, device=DEV), torch.ones(c, device=DEV), torch.ones(c, device=DEV)
+    dx = torch.empty_like(raw)
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+
+    def run(out_scale, out_beta, dg, db, dyv=dy):
+        sums = torch.zeros((c, 3), dtype=torch.float64, device=DEV)
+        ops.bn_relu_bwd(raw, scale, shift, mean, inv, gamma, dx, sums, n * h * w, dy=dyv, dgamma=dg, dbeta=db,
+                        out_scale=out_scale, out_beta=out_beta, flag=flag)
+    g1, b1 = torch.zeros(c, device=DEV), torch.zeros(c, device=DEV)
+    run(1.0, 0.0, g1, b1)
+    g2, b2 = torch.full((c,), 3.0, device=DEV), torch.full((c,), -2.0, device=DEV)
+    run(0.25, 1.0, g2, b2)
+    assert torch.allclose(g2, 3.0 + 0.25 * g1, rtol=1e-6, atol=1e-6) and torch.allclose(b2, -2.0 + 0.25 * b1, rtol=1e-6, atol=1e-6)
+    assert flag.item() == 0
+    bad = dy.clone()
+    bad[0, 0, 0, 5] = float("inf")
+    run(1.0, 0.0, g1, b1, bad)
+    assert flag.item() == 1
+    x = nhwc(rnd(2, 128, 6, 7, seed=92), dt=FH)
+    o = torch.full((128,), 2.0, device=DEV)
+    ops.colsum(x, o, beta=0.5, scale=0.125)
+    assert torch.allclose(o, 1.0 + 0.125 * x.float().sum((0, 1, 2)), rtol=1e-5, atol=1e-5)
+    v = torch.randn(10007, device=DEV)
+    s = torch.empty(1, device=DEV)
+    ops.sum_f32(v, s, scale=0.5)
+    assert abs(s.item() - 0.5 * v.double().sum().item()) < 1e-3
+
+
+def test_batch_tables_with_convT_jobs_scale_and_overflow_flag():
+    """One table-driven launch packs 3x3 and ConvTranspose2d layers together (both operands each) and one unpacks /
+    unscales their packed gradients; == the per-layer kernels.  A non-finite packed value raises the flag."""
+    w3 = rnd(96, 40, 3, 3, seed=100)
+    wt = rnd(128, 64, 2, 2, seed=101)                         # ConvTranspose2d weight [cin][cout][2][2]
+    s3, st = ops.WeightSpec("conv3x3", 96, 40), ops.WeightSpec("convT2x2", 64, 128)
+    f3 = torch.zeros((96, 9 * ops.kpad(40)), dtype=FH, device=DEV)
+    d3 = torch.zeros((40, 9 * ops.kpad(96)), dtype=FH, device=DEV)
+    ft = torch.zeros((4 * 64, ops.kpad(128)), dtype=FH, device=DEV)
+    dtt = torch.zeros((128, 4 * ops.kpad(64)), dtype=FH, device=DEV)
+    g3 = torch.randn((96, 9 * ops.kpad(40)), device=DEV); g3.view(96, 9, -1)[:, :, 40:] = 0
+    gt = torch.randn((4 * 64, ops.kpad(128)), device=DEV)
+    o3, ot = torch.empty_like(w3), torch.empty_like(wt)
+    r3, rt = torch.empty_like(w3), torch.empty_like(wt)
+    ops.unpack(g3.clone(), r3.view(-1), **s3.fwd)
+    ops.unpack(gt.clone(), rt.view(-1), **st.fwd)
+    jobs = [dict(w=w3.reshape(-1), fwd=f3, dgrad=d3, gpacked=g3, gdst=o3, cout=96, cin=40),
+            dict(w=wt.reshape(-1), fwd=ft, dgrad=dtt, gpacked=gt, gdst=ot, cout=64, cin=128, kind=1)]
+    table = ops.Conv3x3JobTable(jobs, DEV)
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    ops.pack_conv3x3_batch(table)
+    ops.unpack_conv3x3_batch(table, 0.5, flag)
+    torch.cuda.synchronize()
+    assert torch.equal(f3, s3.pack_fwd(w3.reshape(-1), dtype=FH)) and torch.equal(d3, s3.pack_dgrad(w3.reshape(-1), dtype=FH))
+    assert torch.equal(ft, st.pack_fwd(wt.reshape(-1), dtype=FH)) and torch.equal(dtt, st.pack_dgrad(wt.reshape(-1), dtype=FH))
+    assert torch.equal(o3, 0.5 * r3) and torch.equal(ot, 0.5 * rt) and flag.item() == 0
+    assert not g3.any() and not gt.any()                      # zeroed behind the read
+    gt[7, 3] = float("nan")
+    ops.unpack_conv3x3_batch(table, 1.0, flag)
+    assert flag.item() == 1
+
+
+def test_fused_adam_skips_the_step_while_the_overflow_flag_is_raised():
+    from hyperpri_b200.optim import FusedAdam
+    p = torch.randn(5000, device=DEV).requires_grad_(True)
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    opt = FusedAdam([p], lr=1e-2, found_inf=flag)
+    before = p.detach().clone()
+    p.grad = torch.full_like(p, float("inf"))
+    flag.fill_(1)
+    opt.step()
+    assert torch.equal(p.detach(), before) and not opt.state[p]["exp_avg"].any()
+    flag.zero_()
+    p.grad = torch.randn_like(p)
+    opt.step()
+    assert not torch.equal(p.detach(), before) and torch.isfinite(p).all()
+    assert opt.skipped_steps() == 1

@@ -46,14 +46,20 @@ def test_train_validate_test_roundtrip(tmp_path):
     p = ExpHyperspectralPRI(root, split_no=1, seed_num=0, comet_logging=False)
     p.epochs, p.patch_size = 6, (32, 48)
     trainer = T.train_net(p)
-    hist = [h["tr_loss"] for h in trainer.history if "tr_loss" in h] if trainer.history else []
+    assert len(trainer.history) == 6 and all("tr_loss" in h and "val_loss" in h and "tr_dice" in h for h in trainer.history)
+    hist = [h["tr_loss"] for h in trainer.history]
     assert trainer.model.m_network.first_conv.weight.is_cuda
-    if hist:
-        assert hist[-1] < hist[0]
+    assert hist[-1] < hist[0]
+    opt_probe = trainer.model.configure_optimizers()              # FusedAdam wired to the engine's overflow flag
+    assert getattr(opt_probe, "found_inf", None) is not None and opt_probe.skipped_steps() == 0
     # device sweep (default on CUDA) vs the host path the reference takes (concatenate predictions, torch ops)
     prec_d, rec_d, thr_d = T.validate_net(p.get_val_data(), p, pl_trainer=trainer)
     best = float(trainer.model.threshold)
-    logits, masks = T._collect(trainer.model, torch.utils.data.DataLoader(p.get_val_data(), batch_size=2), trainer)
+    # the reference evaluates the best val_loss checkpoint, not the trainer's last-epoch weights (PLTrainer.py:476)
+    best_model = T.load_val_model(p)
+    ck = torch.load(os.path.join(p.save_path, "Checkpoints", "best.ckpt"), weights_only=False)
+    assert ck["epoch"] == min(trainer.history, key=lambda h: h["val_loss"])["epoch"]
+    logits, masks = T._collect(best_model, torch.utils.data.DataLoader(p.get_val_data(), batch_size=2), trainer)
     prec_h, rec_h, thr_h = M.binned_pr_curve(torch.sigmoid(logits), masks, 500)
     if prec_h[-2] < 1e-6:
         prec_h[-2] = (1 + prec_h[-3]) / 2
