@@ -241,6 +241,9 @@ def main():
     ap.add_argument("--batch", type=int, default=2)
     ap.add_argument("--mode", default="train", choices=["train", "infer"],
                     help="train: fwd+loss+bwd (headline); infer: eval-mode forward only (kfold_validate-style sweep)")
+    ap.add_argument("--shard", default="batch", choices=["batch", "pixel"],
+                    help="batch: data parallel, every rank its own batch (weak scaling; the headline).  pixel: SpectralUNET's "
+                         "model-sharded option -- every rank a row strip of every image of ONE batch (strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--breakdown", default=None, help="write a per-kernel time breakdown JSON here")
@@ -264,7 +267,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     W_ = max(3, args.warmup)
 
-    torch.manual_seed(1234 + rank)
+    pixel = args.shard == "pixel"
+    if pixel and args.model != "SpectralUNET":
+        raise SystemExit("--shard pixel is the SpectralUNET model-sharded option")
+    torch.manual_seed(1234 + (0 if pixel else rank))      # pixel parallel: every rank holds the same batch
     n = args.batch
     train = args.mode == "train"
     Wp = PATCH_W[args.model]
@@ -279,9 +285,12 @@ def main():
         x = torch.rand((n, BANDS, H, Wp), device=dev)
     net.train(train)
     mask = (torch.rand((n, 1, H, Wp), device=dev) > 0.95).float()
+    if pixel:
+        net.enable_pixel_parallel(None)
     eng = net._get_engine(dev)
-    red = parallel.attach(eng)
-    gscale = red.grad_scale()
+    red = parallel.attach(eng) if not pixel else parallel.BucketedAllReduce(None, None)
+    gscale = red.grad_scale() if not pixel else 1.0
+    jobs = 1 if pixel else world                          # batches processed per step by the whole job
 
     def step():
         if train:
@@ -321,7 +330,7 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = ms.item()
     ms_step = ms_total / args.steps
-    value = n * world * args.steps / (ms_total / 1e3)
+    value = n * jobs * args.steps / (ms_total / 1e3)
 
     # ---------------- per-kernel durations (CUDA events around every native call; separate pass)
     # The weight-gradient side stream is switched off for this pass: with two streams sharing the SMs an event pair around
@@ -356,7 +365,7 @@ def main():
     tensor_launches = sum(v[1] for k, v in per.items() if k in ops.TENSOR_KERNELS) // prof_steps
     all_ms = sum(v[0] for v in per.values())
     peak_tf, peak_burst, peak_gbs, peak_src = peaks()
-    flops_step = GF_PER_IMG[args.model][0 if train else 1] * 1e9 * n
+    flops_step = GF_PER_IMG[args.model][0 if train else 1] * 1e9 * n / (world if pixel else 1)     # this rank's share
     achieved = flops_step / (tensor_ms / 1e3) / 1e12 if tensor_ms > 0 else 0.0
     # DRAM traffic of the same launches from the committed ncu capture (same workload only: CubeNET-64, batch 2, train)
     traffic, traffic_src = None, None
@@ -414,7 +423,7 @@ def main():
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         del xh, mh
-        return {"value": n * world * args.steps / dt.item(), "unit": "images/s",
+        return {"value": n * jobs * args.steps / dt.item(), "unit": "images/s",
                 "h2d_bytes_per_step": x.numel() * xh_bytes[host_dtype] + mask.numel() * 4, "d2h_bytes_per_step": 4,
                 "ms_per_step": dt.item() / args.steps * 1e3}
 
@@ -446,7 +455,7 @@ def main():
         t = torch.tensor([a0.elapsed_time(a1)], device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return {"value": n * world * args.steps / (t.item() / 1e3), "unit": "images/s", "ms_per_step": t.item() / args.steps,
+        return {"value": n * jobs * args.steps / (t.item() / 1e3), "unit": "images/s", "ms_per_step": t.item() / args.steps,
                 "what": "nn.Module.bce_step + loss.backward() (the trainer's step body), inputs resident in HBM"}
 
     api_resident = run_api_resident()
@@ -471,11 +480,13 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC[args.mode], "value": value, "unit": "images/s", "n_gpus": world,
-            "steps": args.steps, "warmup": W_, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "steps": args.steps, "warmup": W_, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if pixel else "weak",
             "vs_baseline": None, "dtype": "f16 (activations, weights, loss-scaled gradients), f32 accumulate (tcgen05 kind::f16)",
             "data": "synthetic",
             "config": {"workload": WORKLOAD[args.model].format(n=n),
-                       "global_batch": n * world, "parallelism": f"dp{world}", "mode": args.mode,
+                       "global_batch": n * jobs, "parallelism": (f"pixel{world} (row strips of every image, per-layer "
+                                                                  "BatchNorm-statistics all-reduce)" if pixel else f"dp{world}"),
+                       "mode": args.mode,
                        "l2": "inputs larger than L2 (>= 0.8 GB fp32 cube + > 3 GB activations per step); no explicit flush",
                        "timed_region": ("weight re-pack + ingest + forward + BCE + backward + grad all-reduce" if train
                                         else "ingest + eval-mode forward (running statistics)")},

@@ -202,8 +202,11 @@ class _EngineBase:
     def loss_scale(self) -> float:
         """Power of two S with |S * dlogit| <= 2^-4 for a mean-reduced BCE (|dlogit| <= 1/numel): keeps the
         fp16 gradient tensors in the normal range with 2^20 headroom before overflow."""
-        numel = self.ws["logits"].numel()
+        numel = self._logit_numel()
         return float(2.0 ** (math.ceil(math.log2(numel)) - 4 - self.loss_scale_shift))
+
+    def _logit_numel(self):
+        return self.ws["logits"].numel()
 
     def _scaled_dlogit(self, dlogit, prescaled):
         """prescaled: dlogit comes from loss_and_dlogit and carries loss_scale() (mean-reduced BCE: the bound on
@@ -219,20 +222,30 @@ class _EngineBase:
             self._S = self.loss_scale()
         else:
             self._S = float(2.0 ** max(-40, min(60, math.floor(math.log2(2.0 ** -4 / amax)) - self.loss_scale_shift)))
-        return torch.mul(dlogit, self._S, out=self.ws["dlogit_s"])
+        return torch.mul(dlogit, self._S, out=self._dlogit_buffers()[1])
 
     def finalize_grads(self):
         """Kept for callers of the round-1 API: gradients now leave every kernel already unscaled (the unpack,
         BatchNorm-backward and bias-sum kernels take 1 / loss scale), so there is nothing left to do here."""
         return None
 
+    def _dlogit_buffers(self):
+        """(dlogit written by the fused BCE kernel, scratch of the same shape)."""
+        return self.ws["dlogit"], self.ws["dlogit_s"]
+
     def loss_and_dlogit(self, logits, mask, grad_scale=1.0, thr=0.5):
         """Fused BCE forward + gradient.  The returned dlogit carries grad_scale * loss_scale():
         pass it to backward(..., prescaled=True)."""
         ws = self.ws
-        ops.bce_fwd_bwd(logits, mask.contiguous().float(), ws["loss_sum"], ws["dlogit"], ws["counts"],
+        dl, _ = self._dlogit_buffers()
+        ops.bce_fwd_bwd(logits, mask.contiguous().float(), ws["loss_sum"], dl, ws["counts"],
                         grad_scale=grad_scale * self.loss_scale(), thr=thr)
-        return ws["loss_sum"], ws["dlogit"], ws["counts"]
+        return ws["loss_sum"], dl, ws["counts"]
+
+    def scaled_stored_dlogit(self, g):
+        """The dlogit loss_and_dlogit stored, times the scalar device tensor g (the gradient flowing into the loss)."""
+        dl, scratch = self._dlogit_buffers()
+        return torch.mul(dl, g.to(dl.dtype), out=scratch)
 
 
 class UNetEngine(_EngineBase):
@@ -722,6 +735,7 @@ class SpectralEngine(_EngineBase):
         self.ws = None
         self.ws_key = None
         self.training_fwd = False
+        self.pp = None                      # hyperpri_b200.parallel.PixelParallel: this rank holds a row strip of every image
         self._init_scaling(device)
         names = [k for nm in self.BLOCKS for k in (nm + ".0.weight", nm + ".0.bias", nm + ".1.weight", nm + ".1.bias")]
         names += ["outc.weight", "outc.bias"]
@@ -740,12 +754,31 @@ class SpectralEngine(_EngineBase):
     def _packed_params(self):
         return [L.pp for L in self.L.values()]
 
-    def _workspace(self, n, r, c):
-        key = (n, r, c)
+    def set_pixel_parallel(self, pp):
+        """Shard every image's pixels over pp's ranks (see PixelParallel); None restores the single-GPU plan."""
+        self.pp = pp if (pp is not None and pp.world > 1) else None
+        self.ws = self.ws_key = None
+
+    def _dlogit_buffers(self):
+        if self.pp is not None:
+            return self.ws["dlogit_full"], self.ws["dlogit_full_s"]
+        return self.ws["dlogit"], self.ws["dlogit_s"]
+
+    def _logit_numel(self):
+        return self.ws["n"] * self.ws["R"] * self.ws["c"]
+
+    def _workspace(self, n, r, c, R=None):
+        """r: rows of this rank's strip; R: rows of the whole image (= r without pixel parallelism)."""
+        R = r if R is None else R
+        key = (n, r, c, R)
         if self.ws_key == key:
             return self.ws
         d, m, Fp = self.dev, r * c, self.Fp
-        ws = {"n": n, "m": m, "r": r, "c": c, "img": []}
+        ws = {"n": n, "m": m, "r": r, "c": c, "R": R, "m_glob": R * c, "img": []}
+        if self.pp is not None:
+            ws["logits_full"] = _e((n, 1, R, c), d, torch.float32)
+            ws["dlogit_full"] = _e((n, 1, R, c), d, torch.float32)
+            ws["dlogit_full_s"] = _e((n, 1, R, c), d, torch.float32)
         ws["x"] = _e((n, r, c, self.Dp), d)
         for _ in range(n):
             im = {nm: _e((1, 1, m, Fp), d) for nm in ("raw_" + b for b in self.BLOCKS)}
@@ -808,13 +841,21 @@ class SpectralEngine(_EngineBase):
 
     def forward(self, x: torch.Tensor, training: bool) -> torch.Tensor:
         n, dch, r, c = x.shape
-        ws = self._workspace(n, r, c)
         x = x.contiguous()
-        ops.hsi_ingest(x if x.dtype == torch.float16 else x.float(), 0, dch, c_pad=self.Dp, out=ws["x"])
+        x = x if x.dtype == torch.float16 else x.float()
+        if self.pp is not None:             # every rank receives the whole batch and ingests its row strip of each image
+            r0, r1 = self.pp.rows(r)
+            ws = self._workspace(n, r1 - r0, c, R=r)
+            ws["r0"] = r0
+            ops.hsi_ingest(x, 0, dch, crop=(r0, 0, r1 - r0, c), c_pad=self.Dp, out=ws["x"])
+        else:
+            ws = self._workspace(n, r, c)
+            ops.hsi_ingest(x, 0, dch, c_pad=self.Dp, out=ws["x"])
         return self.forward_ingested(ws, training)
 
     def forward_ingested(self, ws, training: bool) -> torch.Tensor:
         P, F, Fp, m = self.P, self.F, self.Fp, ws["m"]
+        pp, m_glob = self.pp, ws["m_glob"]
         self.training_fwd = training
         self._refresh()
         for i in range(ws["n"]):
@@ -827,7 +868,15 @@ class SpectralEngine(_EngineBase):
                     src = xin
                 raw = im["raw_" + nm]
                 scale, shift, smean, sinv = im["bn"][nm]
-                if training:
+                if training and pp is not None:
+                    # this rank's partial (sum, sum of squares) -> exact per-image statistics over all strips
+                    ops.igemm_fwd(src, L.pp.fwd, F, 1, raw, Fp, stats=L.stats, x_c=(self.D if nm == "tail" else None),
+                                  block_n=self.bn_tile)
+                    pp.all_reduce_(L.stats)
+                    ops.bn_finalize(L.stats, m_glob, P[nm + ".1.weight"], P[nm + ".1.bias"], P[nm + ".0.bias"],
+                                    P[nm + ".1.running_mean"], P[nm + ".1.running_var"],
+                                    P[nm + ".1.num_batches_tracked"], True, scale, shift, smean, sinv, F)
+                elif training:
                     fin = ops.bn_fin(m, P[nm + ".1.weight"], P[nm + ".1.bias"], P[nm + ".0.bias"],
                                      P[nm + ".1.running_mean"], P[nm + ".1.running_var"],
                                      P[nm + ".1.num_batches_tracked"], scale, shift, smean, sinv, L.ticket)
@@ -841,6 +890,8 @@ class SpectralEngine(_EngineBase):
                                     P[nm + ".1.num_batches_tracked"], False, scale, shift, smean, sinv, F)
                 ops.bn_relu_apply(raw, scale, shift, dst, None, c=F)
             ops.head_fwd(im["cat1"], None, None, self.w_outc, P["outc.bias"], ws["logits"][i])
+        if pp is not None:
+            return pp.gather_rows(ws["logits"], ws["R"], out=ws["logits_full"])
         return ws["logits"]
 
     def backward(self, dlogit: torch.Tensor, prescaled: bool = False) -> Dict[str, torch.Tensor]:
@@ -850,6 +901,14 @@ class SpectralEngine(_EngineBase):
         self._begin_backward()
         dlogit = self._scaled_dlogit(dlogit, prescaled)
         inv = 1.0 / self._S
+        pp, m_glob = self.pp, ws["m_glob"]
+        # pixel parallel: weight and OutConv-bias gradients are partial sums over this rank's pixels (summed over ranks by
+        # the arena all-reduce below); gradients made from the all-reduced BatchNorm sums are the same on every rank, so
+        # they are divided by the world size first
+        inv_bn = inv / pp.world if pp is not None else inv
+        if pp is not None:
+            r0 = ws["r0"]
+            dlogit = torch.mul(dlogit[:, :, r0:r0 + ws["r"]], 1.0, out=ws["dlogit_s"])     # this rank's rows, contiguous
         ops.sum_f32(dlogit, self._grad("outc.bias", P["outc.bias"]), scale=inv)
         go = self._grad("outc.weight", P["outc.weight"]).view(-1)      # [x0 features | up4 features] (models.py:143)
         r_turn, r_busy = 0, {}
@@ -880,11 +939,15 @@ class SpectralEngine(_EngineBase):
                 r_turn += 1
                 R = ws["R"][k]
                 self._join(r_busy.get(k))          # the weight gradient that last read this buffer has finished
-                ops.bn_relu_bwd(im["raw_" + nm], scale, shift, smean, sinv, P[nm + ".1.weight"], R, L.sums, m, dy=dy,
+                if pp is not None:
+                    ops.bn_relu_bwd_reduce(im["raw_" + nm], scale, shift, smean, sinv, L.sums, dy=dy, head_w=hw,
+                                           dlogit=dl if head else None, c=F)
+                    pp.all_reduce_(L.sums)
+                ops.bn_relu_bwd(im["raw_" + nm], scale, shift, smean, sinv, P[nm + ".1.weight"], R, L.sums, m_glob, dy=dy,
                                 head_w=hw, dlogit=dl if head else None,
                                 dgamma=self._grad(nm + ".1.weight", P[nm + ".1.weight"]),
                                 dbeta=self._grad(nm + ".1.bias", P[nm + ".1.bias"]), dhead_w=dhw, c=F,
-                                out_scale=inv, out_beta=acc_beta, flag=self.overflow)
+                                out_scale=inv_bn, out_beta=acc_beta, flag=self.overflow, reduced=pp is not None)
                 xg = src if src.dtype == GRAD else ops.convert16(src, ws["cvt"][..., :src.shape[-1]])
                 self._on_side(lambda xg=xg, R=R, L=L, nm=nm: ops.igemm_wgrad(
                     xg, R, 0, F, L.gw, x_c=(self.D if nm == "tail" else None), dy_c=F))
@@ -899,6 +962,8 @@ class SpectralEngine(_EngineBase):
             wn = nm + ".0.weight"
             L.pp.spec.unpack_grad(L.gw, self._grad(wn, P[wn]).view(-1), scale=inv, flag=self.overflow)
         self._end_backward()
-        if self.bucket_hook is not None:
+        if pp is not None:
+            pp.all_reduce_(self.arena)
+        elif self.bucket_hook is not None:
             self.bucket_hook(self.arena)
         return self.grads

@@ -377,6 +377,15 @@ def bn_relu_bwd(x, scale, shift, smean, sinv, gamma, dx, sums, count, dy=None, d
           "hpri_bn_relu_bwd_apply")
 
 
+@_timed
+def bn_relu_bwd_reduce(x, scale, shift, smean, sinv, sums, dy=None, dpool=None, head_w=None, dlogit=None, c=None):
+    """Pass 1 alone (sums[c] = {sum dz, sum dz * xhat, sum dlogit * act}, zeroed first): the pixel-parallel SpectralUNET
+    all-reduces it over the ranks before bn_relu_bwd(..., reduced=True)."""
+    xv, dyv, dpv = view(x, c), view(dy, c), view(dpool, c)
+    check(_lib.lib().hpri_bn_relu_bwd_reduce(_vp(xv), _ptr(scale), _ptr(shift), _ptr(smean), _ptr(sinv), _vp(dyv), _vp(dpv),
+                                             _ptr(head_w), _ptr(dlogit), _ptr(sums), _stream()), "hpri_bn_relu_bwd_reduce")
+
+
 # ----------------------------------------------------------------------------- head / loss
 @_timed
 def head_fwd(x, scale, shift, w, b, logits, c=None):

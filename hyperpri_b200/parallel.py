@@ -50,3 +50,54 @@ def attach(engine, group=None) -> BucketedAllReduce:
     # a single process has nothing to exchange: leave the engine on its one-launch gradient unpack / unscale path
     engine.bucket_hook = r.hook if r.world_size > 1 else None
     return r
+
+
+class PixelParallel:
+    """The model-sharded option for SpectralUNET (`train_net(..., model_parallel=True)`; the reference runs that model as
+    DeepSpeed ZeRO-2 + bf16-mixed over >= 2 GPUs, PLTrainer.py:409-433, because one image's activations do not fit
+    its GPUs, README.md:82).
+
+    SpectralUNET is a per-pixel MLP (models.py:117-145): the only coupling between pixels is the per-image
+    BatchNorm1d statistics in forward, the two BatchNorm reductions in backward and the sum over pixels in the weight
+    gradients.  So every rank holds a horizontal strip of EVERY image (rows R*rank/world .. R*(rank+1)/world): the
+    activation memory -- the binding constraint -- divides by the world size at any batch size, the weights stay
+    replicated.  Exchange per Linear->BatchNorm->ReLU block and image: one all-reduce of 2 x F doubles in forward (sum,
+    sum of squares -> exact per-image statistics), one of 3 x F doubles in backward; one all-reduce of the gradient
+    arena per step; the logits strips (R x C floats per image) are all-gathered for the loss.  Results equal the
+    single-GPU run up to summation order."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.bytes = 0
+
+    def rows(self, R: int, rank=None):
+        """[r0, r1) of this rank's strip of an R-row image."""
+        k = self.rank if rank is None else rank
+        return (R * k) // self.world, (R * (k + 1)) // self.world
+
+    def all_reduce_(self, t: torch.Tensor) -> torch.Tensor:
+        """In-place SUM over the group, ordered on the current stream."""
+        if self.world > 1:
+            self.bytes += t.numel() * t.element_size()
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def gather_rows(self, local: torch.Tensor, R: int, out: torch.Tensor = None) -> torch.Tensor:
+        """local: [n, 1, r1 - r0, C] strip of every image -> [n, 1, R, C] on every rank."""
+        n, one, _, C = local.shape
+        if out is None:
+            out = torch.empty((n, one, R, C), dtype=local.dtype, device=local.device)
+        if self.world == 1:
+            out.copy_(local)
+            return out
+        rmax = max(self.rows(R, k)[1] - self.rows(R, k)[0] for k in range(self.world))
+        pad = torch.zeros((n, one, rmax, C), dtype=local.dtype, device=local.device)
+        pad[:, :, : local.shape[2]] = local
+        parts = [torch.empty_like(pad) for _ in range(self.world)]
+        dist.all_gather(parts, pad, group=self.group)
+        for k, p in enumerate(parts):
+            r0, r1 = self.rows(R, k)
+            out[:, :, r0:r1] = p[:, :, : r1 - r0]
+        return out

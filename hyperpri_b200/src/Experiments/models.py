@@ -96,8 +96,7 @@ class _NetLossFn(torch.autograd.Function):
         eng = net._get_engine(ctx.dev)
         if gloss is None:
             raise RuntimeError("the fused network + BCE node was differentiated without a loss gradient")
-        ws = eng.ws
-        dl = torch.mul(ws["dlogit"], gloss.to(ws["dlogit"].dtype), out=ws["dlogit_s"])   # 4.7 MB; dlogit carries the loss scale
+        dl = eng.scaled_stored_dlogit(gloss)       # 4.7 MB elementwise; the stored dlogit carries the loss scale
         grads = _deliver_grads(net, eng, lambda: eng.backward(dl, prescaled=True))
         return (None, None, None, None, None, *grads)
 
@@ -254,7 +253,23 @@ class SpectralUNET(_EngineNet):
         return nn.Sequential(nn.Linear(in_feats, out_feats), nn.BatchNorm1d(out_feats), nn.ReLU())
 
     def _make_engine(self, device):
-        return _engine.SpectralEngine(self._tensor_table(), self.hsi_depth, self.layer_feats[0], device)
+        eng = _engine.SpectralEngine(self._tensor_table(), self.hsi_depth, self.layer_feats[0], device)
+        if self.__dict__.get("_pp") is not None:
+            eng.set_pixel_parallel(self.__dict__["_pp"])
+        return eng
+
+    def enable_pixel_parallel(self, group=None):
+        """The model-sharded option (`train_net(..., model_parallel=True)`; the reference: DeepSpeed ZeRO-2 over >= 2
+        GPUs, PLTrainer.py:409-433): every rank of `group` keeps a row strip of every image and the per-image
+        BatchNorm statistics are all-reduced per block (hyperpri_b200.parallel.PixelParallel).  Every rank must be
+        given the same batch.  enable_pixel_parallel(False) returns to the single-GPU plan."""
+        from ...parallel import PixelParallel
+        pp = None if group is False else PixelParallel(group)
+        self.__dict__["_pp"] = pp
+        eng = self.__dict__.get("_eng")
+        if eng is not None:
+            eng.set_pixel_parallel(pp)
+        return pp
 
     def forward(self, x):
         """x: N x D x R x C -> N x n_classes x R x C."""

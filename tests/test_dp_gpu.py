@@ -118,3 +118,89 @@ def test_dp_gradients_equal_mean_of_shards():
             bad.append((k, cos(res[0][k], want)))
     assert not bad, bad
     assert cos(torch.cat(fa), torch.cat(fb)) > 0.97
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SpectralUNET, model-sharded option (train_net(..., model_parallel=True); reference: DeepSpeed ZeRO-2 over >= 2 GPUs,
+# PLTrainer.py:409-433): every rank holds a row strip of every image, per-image BatchNorm statistics all-reduced per
+# block.  Two GPUs must give the single-GPU logits, loss and gradients (up to summation order / fp16 rounding noise).
+def _pp_net(dev, feats):
+    from hyperpri_b200.src.Experiments.models import SpectralUNET
+    torch.manual_seed(11)
+    return SpectralUNET(24, 1, bn_feats=feats).to(dev).train()
+
+
+def _pp_batch(dev):
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand((2, 24, 37, 64), generator=g).to(dev)           # odd row count: strips of 18 and 19 rows
+    m = (torch.rand((2, 1, 37, 64), generator=g) > 0.7).float().to(dev)
+    return x, m
+
+
+def _pp_step(net, x, m):
+    net.zero_grad(set_to_none=True)
+    loss, logits, counts = net.bce_step(x, m)
+    loss.backward()
+    torch.cuda.synchronize()
+    grads = {k: p.grad.detach().float().cpu().clone() for k, p in net.named_parameters()}
+    bufs = {k: v.detach().cpu().clone() for k, v in net.named_buffers()}
+    return loss.item(), logits.cpu(), counts.cpu(), grads, bufs
+
+
+def _pp_worker(rank, world, port, feats, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    net = _pp_net(dev, feats)
+    pp = net.enable_pixel_parallel(None)
+    assert pp.world == world and net._get_engine(dev).pp is pp
+    x, m = _pp_batch(dev)
+    out = None
+    for _ in range(2):                       # twice: workspace / event reuse; the second step sees updated running stats
+        out = _pp_step(net, x, m)
+    q.put((rank,) + out + (int(net._get_engine(dev).overflow.item()), pp.bytes))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("feats", [96, 1650])
+def test_pixel_parallel_spectralunet_equals_single_gpu(feats):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pp_worker, args=(r, 2, port, feats, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in procs:
+        r = q.get(timeout=600)
+        res[r[0]] = r[1:]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    dev = torch.device("cuda", 0)
+    net = _pp_net(dev, feats)
+    x, m = _pp_batch(dev)
+    for _ in range(2):
+        loss1, logits1, counts1, grads1, bufs1 = _pp_step(net, x, m)
+
+    def cos(a, b):
+        return float(torch.dot(a.flatten().double(), b.flatten().double()) / (a.double().norm() * b.double().norm() + 1e-300))
+    for rank in (0, 1):
+        loss, logits, counts, grads, bufs, ovf, nbytes = res[rank]
+        assert ovf == 0 and nbytes > 0
+        assert logits.shape == logits1.shape == (2, 1, 37, 64)
+        assert (logits - logits1).abs().max().item() <= 5e-3 * logits1.abs().max().item()
+        assert abs(loss - loss1) < 1e-5 and (counts - counts1).abs().max().item() <= 4
+        for k in bufs1:
+            if "running_" in k:
+                assert torch.allclose(bufs[k], bufs1[k], rtol=2e-3, atol=2e-4), k
+            elif "num_batches" in k:
+                assert int(bufs[k]) == int(bufs1[k]) == 4                      # two images x two steps
+        fa = torch.cat([grads[k].flatten() for k in sorted(grads1)])
+        fb = torch.cat([grads1[k].flatten() for k in sorted(grads1)])
+        assert cos(fa, fb) > 0.995 and abs(fa.norm().item() / fb.norm().item() - 1.0) < 0.02
+    for k in res[0][3]:
+        assert torch.equal(res[0][3][k], res[1][3][k]), k                      # both ranks hold identical reduced gradients

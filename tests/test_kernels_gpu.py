@@ -542,7 +542,8 @@ def test_bn_contiguous_kernels_match_the_strided_ones(c, dt):
         ops.bn_relu_bwd(raw, scale, shift, mean, inv, gamma, dx, sums, cnt, dy=dy, dgamma=dg, dbeta=db)
         out[tag] = (dx.float().clone(), sums.clone(), dg, db)
     torch.cuda.synchronize()
-    assert torch.allclose(out["d"][1], out["s"][1], rtol=1e-9, atol=1e-9)
+    # fp32 per-thread partials are summed in a different order by the two mappings before the fp64 accumulation
+    assert torch.allclose(out["d"][1], out["s"][1], rtol=1e-4, atol=1e-4 * out["s"][1].abs().max().item())
     assert relerr(out["d"][0], out["s"][0]) < (2e-3 if dt == FH else 1.6e-2)      # at most an output ulp
     assert torch.allclose(out["d"][2], out["s"][2], rtol=1e-6) and torch.allclose(out["d"][3], out["s"][3], rtol=1e-6)
 

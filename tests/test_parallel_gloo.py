@@ -85,3 +85,44 @@ def test_engine_flushes_buckets_one_late_in_order():
         assert log.index(("hook", i)) > log.index(("launched", i + 1))
         assert log.index(("unpack", i)) < log.index(("hook", i))
     assert log[-2:] == [("unpack", 8), ("hook", 8)] and eng._pending_bucket is None
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# PixelParallel (SpectralUNET's model-sharded option): the host-side protocol on CPU tensors -- strips tile the rows,
+# all-reducing the per-strip BatchNorm partial sums gives the whole image's statistics, the logits gather restores the
+# image.  The kernels around it need a GPU (tests/test_dp_gpu.py::test_pixel_parallel_spectralunet_equals_single_gpu).
+def _pp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pp = parallel.PixelParallel()
+    R, C, F = 11, 5, 7                                   # odd row count: strips of 5 and 6 rows
+    g = torch.Generator().manual_seed(3)
+    img = torch.randn((2, 1, R, C), generator=g)          # "logits" of two images, identical on both ranks
+    feat = torch.randn((R * C, F), generator=g, dtype=torch.float64)
+    r0, r1 = pp.rows(R)
+    strips = [pp.rows(R, k) for k in range(world)]
+    loc = feat[r0 * C: r1 * C]
+    stats = torch.stack([loc.sum(0), (loc * loc).sum(0)], 1)
+    pp.all_reduce_(stats)
+    full = pp.gather_rows(img[:, :, r0:r1].contiguous(), R)
+    q.put((rank, strips, stats, full, img, feat, pp.bytes))
+    dist.destroy_process_group()
+
+
+def test_pixel_parallel_protocol_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, strips, stats, full, img, feat, nbytes in res:
+        assert strips == [(0, 5), (5, 11)]                                  # contiguous, disjoint, cover every row
+        want = torch.stack([feat.sum(0), (feat * feat).sum(0)], 1)
+        assert torch.allclose(stats, want, rtol=1e-12, atol=1e-12)          # whole-image statistics on every rank
+        assert torch.equal(full, img)
+        assert nbytes == stats.numel() * 8
