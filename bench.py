@@ -298,6 +298,8 @@ def main():
         logits = eng.forward(x, train)
         if train:
             _, dlogit, _ = eng.loss_and_dlogit(logits, mask, grad_scale=gscale)
+            if hasattr(eng, "set_next_input"):
+                eng.set_next_input(x)                  # the next step's batch (resident in HBM) is ingested under this backward
             eng.backward(dlogit, prescaled=True)
             red.finish()
 
@@ -412,10 +414,13 @@ def main():
                 yield {"image": xh[i % 2], "mask": mh[i % 2]}
 
         t0 = None
-        for i, b in enumerate(DevicePrefetcher(loader(), dev)):   # next step's H2D overlaps this step's compute
+        pf = DevicePrefetcher(loader(), dev)
+        for i, b in enumerate(pf):                      # next step's H2D overlaps this step's compute
             if i == W_:
                 sync()
                 t0 = time.perf_counter()
+            if train and pf.next_batch is not None:     # as the trainer loop does: its ingest runs under this backward
+                net.set_next_input(pf.next_batch["image"], pf.next_ready)
             loss = api_step(b["image"], b["mask"])
             loss.item()                                 # D2H read of the step's result
         sync()
@@ -444,11 +449,13 @@ def main():
     def run_api_resident():
         """The same public API with the batch already in HBM: must match `value` (same kernels, autograd on top)."""
         for _ in range(W_):
+            net.set_next_input(x)
             api_step(x, mask)
         sync()
         a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a0.record()
         for _ in range(args.steps):
+            net.set_next_input(x)
             api_step(x, mask)
         a1.record()
         sync()

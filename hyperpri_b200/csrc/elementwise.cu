@@ -1093,7 +1093,8 @@ bn_bwd_apply_contig_k(const uint4* __restrict__ x, const uint4* __restrict__ dy,
   grid_dep_launch();
   if (blockIdx.x == 0) write_param_grads(sums, C, pg);
   const int CG = C >> 3;
-  const int c0 = (threadIdx.x % CG) * 8;
+  const int cg_shift = 31 - __clz(CG);
+  const int c0 = (threadIdx.x & (CG - 1)) * 8;
   const float rc = 1.f / (float)count;
   float sc[8], sh[8], hw[8], ca[8], cb[8], cc[8];
   ld8v(scale, c0, C, sc);
@@ -1119,7 +1120,7 @@ bn_bwd_apply_contig_k(const uint4* __restrict__ x, const uint4* __restrict__ dy,
       if (v < nvec) {
         xr[u] = __ldg(x + v);
         if (dy != nullptr) dr[u] = __ldg(dy + v);
-        if (HEAD) dl[u] = __ldg(dlogit + v / CG);
+        if (HEAD) dl[u] = __ldg(dlogit + (v >> cg_shift));      // CG is a power of two here (256 % CG == 0)
       }
     }
 #pragma unroll
@@ -1152,7 +1153,8 @@ bn_bwd_reduce_contig_k(const uint4* __restrict__ x, const uint4* __restrict__ dy
                        const float* __restrict__ dlogit, double* sums) {
   __shared__ float red[256][25];                 // odd stride: conflict-free row writes
   const int CG = C >> 3;
-  const int c0 = (threadIdx.x % CG) * 8;
+  const int cg_shift = 31 - __clz(CG);
+  const int c0 = (threadIdx.x & (CG - 1)) * 8;
   float sc[8], sh[8], hw[8], s1[8], s2[8], s3[8];
   ld8v(scale, c0, C, sc);
   ld8v(shift, c0, C, sh);
@@ -1170,7 +1172,7 @@ bn_bwd_reduce_contig_k(const uint4* __restrict__ x, const uint4* __restrict__ dy
       if (v < nvec) {
         xr[u] = __ldg(x + v);
         if (dy != nullptr) dr[u] = __ldg(dy + v);
-        if (HEAD) dl[u] = __ldg(dlogit + v / CG);
+        if (HEAD) dl[u] = __ldg(dlogit + (v >> cg_shift));      // CG is a power of two here (256 % CG == 0)
       }
     }
 #pragma unroll

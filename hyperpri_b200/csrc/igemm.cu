@@ -1221,6 +1221,10 @@ static void set_tile(IgemmArgs& a, int th, int tw) {
   a.tiles_h = (a.H + th - 1) / th; a.tiles_w = (a.W + tw - 1) / tw;
 }
 
+// SMs the persistent tcgen05 grids may fill.  hpri_set_sm_reserve(k) leaves k SMs free for kernels that must run
+// CONCURRENTLY with them -- NCCL's all-reduce CTAs during the data-parallel backward: a persistent grid sized to every
+// SM turns one wave into two as soon as a single CTA is displaced.  Seeded by the environment variable HPRI_SM_RESERVE.
+static int g_sm_reserve = -1;
 static int sm_count() {
   static int num_sms = 0;
   if (num_sms == 0) {
@@ -1228,7 +1232,13 @@ static int sm_count() {
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
   }
-  return num_sms;
+  if (g_sm_reserve < 0) {
+    const char* e = getenv("HPRI_SM_RESERVE");
+    g_sm_reserve = e ? atoi(e) : 0;
+    if (g_sm_reserve < 0) g_sm_reserve = 0;
+  }
+  const int n = num_sms - g_sm_reserve;
+  return n < 2 ? 2 : n;
 }
 
 struct OutMaps { CUtensorMap m[4]; };
@@ -1372,6 +1382,12 @@ extern "C" int hpri_conv3x3_halo_ok(int h, int w, int w_rows) {
 extern "C" int hpri_set_conv_algo(int algo) {
   if (algo < -1 || algo > 2) return HPRI_ERR_ARG;
   g_conv_algo = algo;
+  return HPRI_OK;
+}
+
+extern "C" int hpri_set_sm_reserve(int sms) {
+  if (sms < 0 || sms > 64) return HPRI_ERR_ARG;
+  g_sm_reserve = sms;
   return HPRI_OK;
 }
 

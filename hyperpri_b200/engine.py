@@ -105,7 +105,6 @@ class _EngineBase:
             self.overflow = torch.zeros(1, dtype=torch.int32, device=device)
         self._S = 1.0
         self._gw_dirty = False
-        self._pending_bucket = None
         self._init_side_stream(device)
 
     def _gw_buffers(self):
@@ -126,6 +125,7 @@ class _EngineBase:
     def set_overlap(self, enabled: bool):
         """Turn the side stream off / back on (per-kernel timing needs serialised launches: an event pair around a
         kernel that shares the SMs with another stream's kernel also counts the time it spent waiting for them)."""
+        self._no_prefetch = not enabled
         if not enabled:
             if self._side is not None:
                 self._side_saved, self._side = self._side, None
@@ -149,11 +149,12 @@ class _EngineBase:
 
     def _on_side(self, fn, after=None):
         """Run fn's launches on the side stream, ordered after `after` (default: everything launched so far on the
-        current stream)."""
+        current stream; False: only behind what the side stream already holds)."""
         if self._side is None:
             fn()
             return
-        self._side.wait_event(after if after is not None else self._fork())
+        if after is not False:
+            self._side.wait_event(after if after is not None else self._fork())
         with torch.cuda.stream(self._side):
             fn()
 
@@ -169,6 +170,50 @@ class _EngineBase:
         if ev is not None:
             torch.cuda.current_stream().wait_event(ev)
 
+    # ------------------------------------------------------------------ ingest of the NEXT batch under this batch's backward
+    # The HSI ingest (band slice + NCHW fp32/fp16 -> NHWC fp16, 1.7 GB of HBM traffic at 2 x 238 x 608 x 968) is
+    # bandwidth-bound and has no dependence on the step before it, while backward is dominated by tensor-bound launches:
+    # a caller that knows its next input registers it (set_next_input) and backward() ingests it into the second x
+    # buffer on a third stream; the next forward(x) recognises the tensor and starts from the ready buffer.
+    def set_next_input(self, x, ready_event=None):
+        """x: the tensor the NEXT forward() will be given (None: nothing to prefetch); ready_event: CUDA event after which
+        its contents are valid (e.g. the host->device copy of a DevicePrefetcher slot)."""
+        self._next_input = None if x is None else (x, ready_event)
+
+    def _launch_prefetch(self):
+        nxt, self._next_input = getattr(self, "_next_input", None), None
+        self._prefetched = None
+        if nxt is None or not hasattr(self, "_ingest_into") or getattr(self, "_no_prefetch", False) or \
+                os.environ.get("HPRI_INGEST_PREFETCH", "1") == "0":
+            return
+        x, ready = nxt
+        if x is None or not x.is_cuda or self.ws is None or not self._same_input_shape(x):
+            return
+        if getattr(self, "_ingest_stream", None) is None:
+            self._ingest_stream = torch.cuda.Stream(device=self.dev)
+            self._ingest_event = torch.cuda.Event()
+        ws = self.ws
+        if "x_alt" not in ws:
+            ws["x_alt"] = torch.empty_like(ws["x"])
+        st = self._ingest_stream
+        st.wait_stream(torch.cuda.current_stream())       # x_alt's last reader (the previous step's first-layer wgrad) is done
+        if ready is not None:
+            st.wait_event(ready)
+        with torch.cuda.stream(st):
+            self._ingest_into(x, ws["x_alt"])
+            self._ingest_event.record(st)
+        x.record_stream(st)
+        self._prefetched = (x.data_ptr(), x._version, tuple(x.shape), x.dtype)
+
+    def _take_prefetched(self, x) -> bool:
+        """True when x is the registered next input: its ingested form becomes ws["x"]."""
+        pf, self._prefetched = getattr(self, "_prefetched", None), None
+        if pf is None or pf != (x.data_ptr(), x._version, tuple(x.shape), x.dtype) or "x_alt" not in (self.ws or {}):
+            return False
+        torch.cuda.current_stream().wait_event(self._ingest_event)
+        self.ws["x"], self.ws["x_alt"] = self.ws["x_alt"], self.ws["x"]
+        return True
+
     def invalidate_packed(self):
         """Force a re-pack of every 16-bit weight operand at the next forward (what an optimizer step causes)."""
         for pp in self._packed_params():
@@ -183,7 +228,6 @@ class _EngineBase:
                 g.zero_()
         self._gw_dirty = True
         self._side_used = 0
-        self._pending_bucket = None
         self._clear_overflow()
 
     def _end_backward(self):
@@ -361,26 +405,22 @@ class UNetEngine(_EngineBase):
         del start
 
     def _bucket_done(self, idx):
-        """Bucket idx has been launched.  Its weight gradients run on the side stream, so the unpack + all-reduce hook of
-        a bucket is issued one bucket late (after the NEXT bucket's launches): the join then waits for work that has had
-        a whole bucket of main-stream kernels to finish under."""
-        mark = self._side_mark()
-        if self._pending_bucket is not None:
-            self._flush_bucket()
-        self._pending_bucket = (idx, mark)
-        if idx == 8:
-            self._flush_bucket()
-
-    def _flush_bucket(self):
-        idx, mark = self._pending_bucket
-        self._pending_bucket = None
-        if self.bucket_hook is not None or idx == 8:      # a single process only joins once, before the one unpack launch
-            self._join(mark)
-        self._unpack_bucket(idx)
+        """Every launch of gradient bucket idx has been issued.  With an all-reduce hook the bucket's unpack (packed fp32
+        -> arena, unscaled) and the hook run ON THE SIDE STREAM, stream-ordered behind the bucket's weight gradients: the
+        main stream (dgrads, BatchNorm backward) never waits for them -- the BatchNorm parameter gradients of the bucket
+        are covered by the events the weight-gradient launches already waited for.  Without a hook ONE unpack launch
+        follows the join at the end of backward."""
         if self.bucket_hook is not None:
-            a, b = self.bucket_bounds[idx]
-            if b > a:
-                self.bucket_hook(self.arena[a:b])
+            self._on_side(lambda idx=idx: self._unpack_and_hook(idx), after=False)
+        elif idx == 8:
+            self._join(self._side_mark())
+            self._unpack_bucket(idx)
+
+    def _unpack_and_hook(self, idx):
+        self._unpack_bucket(idx)
+        a, b = self.bucket_bounds[idx]
+        if b > a:
+            self.bucket_hook(self.arena[a:b])
 
     # ------------------------------------------------------------------ workspace
     def _workspace(self, n, h, w):
@@ -504,19 +544,27 @@ class UNetEngine(_EngineBase):
         return ops.conv3x3_halo_ok(self.ws["H"][l], self.ws["W"][l], (self.CE if enc else self.M)[l])
 
     # ------------------------------------------------------------------ forward
-    def ingest(self, x: torch.Tensor, ws):
+    def _ingest_into(self, x: torch.Tensor, dst: torch.Tensor):
         if x.dim() == 5:                       # CubeNET: N x 1 x D x H x W  (reshape is a no-copy squeeze)
             x = x.reshape(x.shape[0], x.shape[2], x.shape[3], x.shape[4])
         x = x.contiguous()
         if x.dtype != torch.float16:          # fp16 cubes (converted by the data loader before H2D) are ingested as is
             x = x.float()
-        ops.hsi_ingest(x, 0, x.shape[1], c_pad=self.cin_pad, out=ws["x"])
+        ops.hsi_ingest(x, 0, x.shape[1], c_pad=self.cin_pad, out=dst)
+
+    def ingest(self, x: torch.Tensor, ws):
+        self._ingest_into(x, ws["x"])
+
+    def _same_input_shape(self, x):
+        return self.ws_key == (x.shape[0], x.shape[-2], x.shape[-1])
 
     def forward(self, x: torch.Tensor, training: bool) -> torch.Tensor:
         n = x.shape[0]
         h, w = x.shape[-2], x.shape[-1]
+        same_ws = self.ws_key == (n, h, w)
         ws = self._workspace(n, h, w)
-        self.ingest(x, ws)
+        if not (same_ws and self._take_prefetched(x)):
+            self.ingest(x, ws)
         return self.forward_ingested(ws, training)
 
     # ------------------------------------------------------------------ table-driven weight pack / gradient unpack
@@ -628,6 +676,7 @@ class UNetEngine(_EngineBase):
         ws, P, CE, U = self.ws, self.P, self.CE, self.U
         n, H, W = ws["n"], ws["H"], ws["W"]
         self._begin_backward()
+        self._launch_prefetch()            # the next batch's ingest runs under this backward (set_next_input)
         self._bw_sums.zero_()              # one fill for the BN-backward sums the dgrad epilogues accumulate into
         dlogit = self._scaled_dlogit(dlogit, prescaled)
         cnt = [n * H[l] * W[l] for l in range(5)]
@@ -765,7 +814,7 @@ class SpectralEngine(_EngineBase):
         return self.ws["dlogit"], self.ws["dlogit_s"]
 
     def _logit_numel(self):
-        return self.ws["n"] * self.ws["R"] * self.ws["c"]
+        return self.ws["n"] * self.ws["rows_full"] * self.ws["c"]
 
     def _workspace(self, n, r, c, R=None):
         """r: rows of this rank's strip; R: rows of the whole image (= r without pixel parallelism)."""
@@ -774,7 +823,7 @@ class SpectralEngine(_EngineBase):
         if self.ws_key == key:
             return self.ws
         d, m, Fp = self.dev, r * c, self.Fp
-        ws = {"n": n, "m": m, "r": r, "c": c, "R": R, "m_glob": R * c, "img": []}
+        ws = {"n": n, "m": m, "r": r, "c": c, "rows_full": R, "m_glob": R * c, "img": []}
         if self.pp is not None:
             ws["logits_full"] = _e((n, 1, R, c), d, torch.float32)
             ws["dlogit_full"] = _e((n, 1, R, c), d, torch.float32)
@@ -891,7 +940,7 @@ class SpectralEngine(_EngineBase):
                 ops.bn_relu_apply(raw, scale, shift, dst, None, c=F)
             ops.head_fwd(im["cat1"], None, None, self.w_outc, P["outc.bias"], ws["logits"][i])
         if pp is not None:
-            return pp.gather_rows(ws["logits"], ws["R"], out=ws["logits_full"])
+            return pp.gather_rows(ws["logits"], ws["rows_full"], out=ws["logits_full"])
         return ws["logits"]
 
     def backward(self, dlogit: torch.Tensor, prescaled: bool = False) -> Dict[str, torch.Tensor]:

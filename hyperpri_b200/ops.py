@@ -266,6 +266,11 @@ def set_wgrad_algo(algo: int):
     check(_lib.lib().hpri_set_wgrad_algo(int(algo)), "hpri_set_wgrad_algo")
 
 
+def set_sm_reserve(sms: int):
+    """Keep `sms` SMs out of the persistent tensor-core grids (room for concurrently running NCCL CTAs)."""
+    check(_lib.lib().hpri_set_sm_reserve(int(sms)), "hpri_set_sm_reserve")
+
+
 @_timed
 def convT_fwd(x, wpack, cout, y, bias=None, block_n=0):
     xv, yv = view(x), view(y)

@@ -27,6 +27,9 @@ class DevicePrefetcher:
             self._ready = [torch.cuda.Event() for _ in range(self.slots)]
             self._used = [False] * self.slots
             self._consumed = [None] * self.slots
+        # while a batch is being consumed: the batch staged behind it (already on its way to the device) and the event
+        # after which its device tensors are valid -- what nn.Module.set_next_input wants
+        self.next_batch, self.next_ready = None, None
 
     def __len__(self):
         return len(self.loader)
@@ -84,6 +87,7 @@ class DevicePrefetcher:
                 nxt = self._stage(next(it), slot)      # the next batch's copies run under this batch's compute
             except StopIteration:
                 nxt = None
+            self.next_batch, self.next_ready = nxt, (self._ready[slot] if nxt is not None else None)
             consumer = torch.cuda.current_stream(self.device)
             consumer.wait_event(self._ready[cur_slot])
             for k in self.keys:

@@ -152,6 +152,13 @@ class _EngineNet(nn.Module):
         _lib_ops.bce_fwd_bwd(logits, target, ws["loss_sum"], None, ws["counts"], thr=float(thr))
         return (ws["loss_sum"] / logits.numel()).float(), logits.clone(), ws["counts"].clone()
 
+    def set_next_input(self, x, ready_event=None):
+        """Tell the engine which tensor the NEXT forward will receive (e.g. the batch a DevicePrefetcher has already
+        staged): its ingest then runs under this step's backward instead of at the head of the next step."""
+        dev = next(self.parameters()).device
+        if dev.type == "cuda" and hasattr(self._get_engine(dev), "set_next_input"):
+            self._get_engine(dev).set_next_input(x, ready_event)
+
     def _finish(self, logits):
         if getattr(self, "analyze", False):
             return (logits, logits, torch.sigmoid(logits))

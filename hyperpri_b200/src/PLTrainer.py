@@ -210,8 +210,12 @@ class _Loop:
         skipped_seen = 0
         for epoch in range(start_epoch, self.max_epochs):
             model.train(); model.logged.clear()
-            for i, batch in enumerate(DevicePrefetcher(self._sharded(train_loader, epoch), self.device)):
+            pf = DevicePrefetcher(self._sharded(train_loader, epoch), self.device)
+            for i, batch in enumerate(pf):
                 opt.zero_grad(set_to_none=True)
+                if hasattr(model.m_network, "set_next_input"):     # the staged next batch is ingested under this backward
+                    nb = pf.next_batch
+                    model.m_network.set_next_input(nb["image"] if nb is not None else None, pf.next_ready)
                 loss = model.training_step(_to_device(batch, self.device), i)
                 loss.backward()
                 if red is not None:

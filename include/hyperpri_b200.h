@@ -92,6 +92,9 @@ int hpri_set_conv_algo(int algo);
 /* 3x3 weight-gradient kernel selection: -1 heuristic (halo-reuse weight-gradient kernel at Cout 64 / 128), 0 generic
  * per-tap kernel only.  Seeded by the environment variable HPRI_WGRAD_ALGO. */
 int hpri_set_wgrad_algo(int algo);
+/* Leave `sms` streaming multiprocessors out of the persistent tcgen05 grids (0 = use every SM): room for kernels that
+ * run concurrently with them, i.e. NCCL's all-reduce CTAs in the data-parallel backward.  Seeded by HPRI_SM_RESERVE. */
+int hpri_set_sm_reserve(int sms);
 
 /* nn.ConvTranspose2d(k=2,s=2) fprop writing straight into the concat buffer (model_parts.py:63-64,
  * 74-87: pad + cat are absorbed by the destination view) and its dgrad. */

@@ -16,6 +16,24 @@ import torch.multiprocessing as mp
 pytestmark = pytest.mark.gpu
 
 
+def _collect(q, procs, timeout=240):
+    """One result per process; fails as soon as a worker has died instead of waiting for the full timeout."""
+    import queue
+    import time
+    out, t0 = [], time.time()
+    while len(out) < len(procs):
+        try:
+            out.append(q.get(timeout=2))
+        except queue.Empty:
+            dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
+            if dead or time.time() - t0 > timeout:
+                for p in procs:
+                    if p.is_alive():
+                        p.kill()
+                raise AssertionError(f"worker failed (exit codes {dead}) or timed out after {time.time() - t0:.0f} s")
+    return out
+
+
 def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
     return p
@@ -91,8 +109,7 @@ def test_dp_gradients_equal_mean_of_shards():
     for p in procs:
         p.start()
     res = {}
-    for _ in procs:
-        rank, g, ovf, exact = q.get(timeout=600)
+    for rank, g, ovf, exact in _collect(q, procs):
         assert ovf == 0 and exact
         res[rank] = g
     for p in procs:
@@ -174,8 +191,7 @@ def test_pixel_parallel_spectralunet_equals_single_gpu(feats):
     for p in procs:
         p.start()
     res = {}
-    for _ in procs:
-        r = q.get(timeout=600)
+    for r in _collect(q, procs):
         res[r[0]] = r[1:]
     for p in procs:
         p.join(timeout=120)

@@ -545,7 +545,8 @@ def test_bn_contiguous_kernels_match_the_strided_ones(c, dt):
     # fp32 per-thread partials are summed in a different order by the two mappings before the fp64 accumulation
     assert torch.allclose(out["d"][1], out["s"][1], rtol=1e-4, atol=1e-4 * out["s"][1].abs().max().item())
     assert relerr(out["d"][0], out["s"][0]) < (2e-3 if dt == FH else 1.6e-2)      # at most an output ulp
-    assert torch.allclose(out["d"][2], out["s"][2], rtol=1e-6) and torch.allclose(out["d"][3], out["s"][3], rtol=1e-6)
+    for i in (2, 3):                                   # dgamma / dbeta follow the sums
+        assert torch.allclose(out["d"][i], out["s"][i], rtol=1e-4, atol=1e-4 * out["s"][i].abs().max().item())
 
 
 def test_param_grads_are_unscaled_accumulated_and_flagged():

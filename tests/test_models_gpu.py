@@ -444,3 +444,38 @@ def test_generic_criterion_route_scales_any_loss_gradient():
     gm = torch.cat([p.grad.flatten().clone() for _, p in sorted(net.named_parameters())])
     assert cos(gs, gm) > 0.999
     assert abs((gs.norm() / gm.norm()).item() / mask.numel() - 1.0) < 0.05
+
+
+def test_next_batch_ingest_prefetch_gives_the_same_network_input():
+    """set_next_input(x2) before a backward: x2 is ingested on a third stream under that backward and the next forward(x2)
+    starts from the ready buffer (bit-identical NHWC input); a forward on any OTHER tensor ignores the prefetched buffer."""
+    net, sd = build("CubeNET", 238)
+    x1 = O.synth_cube(7, 2, 238, 48, 64)[:, None].cuda()
+    x2 = O.synth_cube(8, 2, 238, 48, 64)[:, None].cuda()
+    x3 = O.synth_cube(9, 2, 238, 48, 64)[:, None].cuda()
+    mask = O.synth_mask(7, 2, 48, 64).cuda()
+    net.train()
+    eng = net._get_engine(x1.device)
+    loss, _, _ = net.bce_step(x1, mask)
+    net.set_next_input(x2)
+    loss.backward()
+    assert eng._prefetched is not None
+    other = eng.ws["x_alt"]
+    net.eval()                                   # running statistics: the logits depend on the input only
+    with torch.no_grad():
+        a = net(x2)                              # takes the prefetched buffer
+        assert eng.ws["x"] is other and eng._prefetched is None
+        xin_pref = eng.ws["x"].clone()
+        b = net(x2)                              # plain ingest of the same tensor
+        assert torch.equal(eng.ws["x"], xin_pref) and torch.equal(a, b)
+    net.train()
+    loss, _, _ = net.bce_step(x1, mask)
+    net.set_next_input(x2)
+    loss.backward()
+    net.eval()
+    with torch.no_grad():
+        c = net(x3)                              # not the registered tensor: ingested normally
+        net.load_state_dict(net.state_dict())
+        d = net(x3)
+    assert torch.equal(c, d) and not torch.equal(c, a)
+    torch.cuda.synchronize()

@@ -64,27 +64,32 @@ def test_single_process_is_a_noop():
     assert eng.bucket_hook is None                    # one process: the engine keeps its single-launch unpack path
 
 
-def test_engine_flushes_buckets_one_late_in_order():
-    """UNetEngine._bucket_done defers the unpack + all-reduce hook of bucket i until bucket i+1 has been launched (the
-    side-stream weight gradients of bucket i then had a whole bucket of main-stream work to finish under); every bucket
-    is flushed exactly once, in order, and the last one at the end of backward.  Host logic only: no CUDA."""
+def test_engine_hands_every_bucket_to_the_hook_once_in_order():
+    """UNetEngine._bucket_done: with an all-reduce hook attached, bucket i is unpacked and handed to the hook as soon as
+    its launches are issued (on the side stream, behind its weight gradients -- here, without CUDA, inline), every bucket
+    exactly once and in completion order; without a hook only the final bucket triggers the single unpack launch.
+    Host logic only: no CUDA."""
     from hyperpri_b200.engine import UNetEngine
     eng = object.__new__(UNetEngine)
     eng.arena = torch.arange(90, dtype=torch.float32)
     eng.bucket_bounds = [(10 * i, 10 * i + 10) for i in range(9)]
-    eng._pending_bucket, eng._side, eng._side_events, eng._side_used = None, None, [], 0
+    eng._side, eng._side_events, eng._side_used = None, [], 0
     log = []
     eng._unpack_bucket = lambda idx: log.append(("unpack", idx))
     eng.bucket_hook = lambda flat: log.append(("hook", int(flat[0].item()) // 10))
     for idx in range(9):
         log.append(("launched", idx))
         eng._bucket_done(idx)
-    flushed = [e for e in log if e[0] == "hook"]
-    assert flushed == [("hook", i) for i in range(9)]
-    for i in range(8):                                   # bucket i is flushed only after bucket i+1 was launched
-        assert log.index(("hook", i)) > log.index(("launched", i + 1))
-        assert log.index(("unpack", i)) < log.index(("hook", i))
-    assert log[-2:] == [("unpack", 8), ("hook", 8)] and eng._pending_bucket is None
+    assert [e for e in log if e[0] == "hook"] == [("hook", i) for i in range(9)]
+    for i in range(9):
+        assert log.index(("launched", i)) < log.index(("unpack", i)) < log.index(("hook", i))
+        if i < 8:
+            assert log.index(("hook", i)) < log.index(("launched", i + 1))
+    log.clear()
+    eng.bucket_hook = None
+    for idx in range(9):
+        eng._bucket_done(idx)
+    assert log == [("unpack", 8)]
 
 
 # ---------------------------------------------------------------------------------------------------------------
