@@ -245,6 +245,8 @@ def main():
                     help="batch: data parallel, every rank its own batch (weak scaling; the headline).  pixel: SpectralUNET's "
                          "model-sharded option -- every rank a row strip of every image of ONE batch (strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the short companion measurements the default N=1 run adds (other BASELINE.json configs)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--breakdown", default=None, help="write a per-kernel time breakdown JSON here")
     args = ap.parse_args()
@@ -466,6 +468,35 @@ def main():
                 "what": "nn.Module.bce_step + loss.backward() (the trainer's step body), inputs resident in HBM"}
 
     api_resident = run_api_resident()
+    if train:
+        # the whole training iteration of the reference's loop (PLTrainer.py:79-98 + configure_optimizers :164-174):
+        # zero_grad, step body, backward, Adam -- FusedAdam updates every tensor in one launch and its version bump makes
+        # the next forward re-pack the fp16 operands (no invalidate_packed here)
+        from hyperpri_b200.optim import FusedAdam
+        opt = FusedAdam(net.parameters(), lr=1e-4, found_inf=eng.overflow)
+
+        def full_iter():
+            net.zero_grad(set_to_none=True)
+            net.set_next_input(x)
+            loss, _, _ = net.bce_step(x, mask, grad_scale=gscale)
+            loss.backward()
+            opt.step()
+        for _ in range(W_):
+            full_iter()
+        sync()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(args.steps):
+            full_iter()
+        b1.record()
+        sync()
+        tt = torch.tensor([b0.elapsed_time(b1)], device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        api_resident["with_optimizer"] = {"value": n * jobs * args.steps / (tt.item() / 1e3), "unit": "images/s",
+                                          "ms_per_step": tt.item() / args.steps,
+                                          "what": "zero_grad + bce_step + backward + FusedAdam.step (one launch), inputs resident in HBM"}
+        del opt
     xh_bytes = {torch.float32: 4, torch.float16: 2}
     e2e = e2e32 = None
     if not args.no_e2e:
@@ -479,6 +510,72 @@ def main():
         else:
             e2e = run_e2e(torch.float32)
             e2e["host_format"] = "fp32 RGB image (reference dataset format)"
+
+    # ---------------- companion measurements (default N=1 run only): the other BASELINE.json configurations, a few
+    # steps each, so that they are measured wherever this file is run -- configs[1] SpectralUNET-1650 training at its
+    # 608 x 700 patch and configs[3] the kfold_validate-style eval-mode forward of the three models
+    extras = None
+    if world == 1 and args.model == "CubeNET" and train and not args.no_extras:
+        red.engine, eng.bucket_hook = None, None          # drop the headline model's workspace (~8 GB) before the next ones
+        net.__dict__.pop("_eng", None)
+        eng.ws = None
+        torch.cuda.empty_cache()
+        extras = {}
+
+        def timed(fn, steps, warm=3):
+            for _ in range(warm):
+                fn()
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(steps):
+                fn()
+            a1.record()
+            torch.cuda.synchronize()
+            return a0.elapsed_time(a1) / steps
+
+        def make(model_name):
+            wp = PATCH_W[model_name]
+            if model_name == "CubeNET":
+                m_, x_ = CubeNET(BANDS, 1, first_depth=64, bilinear=False).to(dev), torch.rand((2, 1, BANDS, H, wp), device=dev)
+            elif model_name == "UNET":
+                m_, x_ = UNet(3, 1, bilinear=False).to(dev), torch.rand((2, 3, H, wp), device=dev)
+            else:
+                m_, x_ = SpectralUNET(BANDS, 1, bn_feats=1650).to(dev), torch.rand((2, BANDS, H, wp), device=dev)
+            return m_, x_, (torch.rand((2, 1, H, wp), device=dev) > 0.95).float()
+
+        for model_name in ("CubeNET", "UNET", "SpectralUNET"):
+            m_, x_, k_ = make(model_name)
+            e_ = m_._get_engine(dev)
+            m_.eval()
+
+            def infer():
+                with torch.no_grad():
+                    e_.forward(x_, False)
+            ms_i = timed(infer, 10 if model_name != "SpectralUNET" else 4)
+            gf = GF_PER_IMG[model_name][1] * 2
+            extras[f"infer_{model_name}"] = {
+                "metric": METRIC["infer"], "value": 2e3 / ms_i, "unit": "images/s", "ms_per_step": ms_i,
+                "workload": WORKLOAD[model_name].format(n=2) + "; eval-mode forward (running statistics), ingest included "
+                            "(BASELINE.json configs[3])",
+                "whole_step_tflops": gf / ms_i, "frac_of_sustained_peak": gf / ms_i / peak_tf, "frac_of_burst_peak": gf / ms_i / peak_burst}
+            if model_name == "SpectralUNET":
+                m_.train()
+
+                def train_step():
+                    e_.invalidate_packed()
+                    lg_ = e_.forward(x_, True)
+                    _, dl_, _ = e_.loss_and_dlogit(lg_, k_)
+                    e_.backward(dl_, prescaled=True)
+                ms_t = timed(train_step, 3)
+                gft = GF_PER_IMG[model_name][0] * 2
+                extras["train_SpectralUNET"] = {
+                    "metric": METRIC["train"], "value": 2e3 / ms_t, "unit": "images/s", "ms_per_step": ms_t,
+                    "workload": WORKLOAD[model_name].format(n=2), "whole_step_tflops": gft / ms_t,
+                    "frac_of_sustained_peak": gft / ms_t / peak_tf, "frac_of_burst_peak": gft / ms_t / peak_burst}
+            m_.__dict__.pop("_eng", None)
+            del e_, m_, x_, k_
+            torch.cuda.empty_cache()
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -497,7 +594,7 @@ def main():
                        "l2": "inputs larger than L2 (>= 0.8 GB fp32 cube + > 3 GB activations per step); no explicit flush",
                        "timed_region": ("weight re-pack + ingest + forward + BCE + backward + grad all-reduce" if train
                                         else "ingest + eval-mode forward (running statistics)")},
-            "e2e": e2e, "e2e_fp32_host": e2e32, "api_resident": api_resident, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_base, "clocks": clocks,
+            "e2e": e2e, "e2e_fp32_host": e2e32, "api_resident": api_resident, "extras": extras, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_base, "clocks": clocks,
         }
         print(json.dumps(line))
     if world > 1:

@@ -30,7 +30,8 @@ class BnFin(C.Structure):
     _fields_ = [("gamma", C.c_void_p), ("beta", C.c_void_p), ("conv_bias", C.c_void_p), ("running_mean", C.c_void_p),
                 ("running_var", C.c_void_p), ("num_batches_tracked", C.c_void_p), ("scale", C.c_void_p),
                 ("shift", C.c_void_p), ("save_mean", C.c_void_p), ("save_invstd", C.c_void_p),
-                ("counter", C.c_void_p), ("count", C.c_longlong), ("momentum", C.c_float), ("eps", C.c_float)]
+                ("counter", C.c_void_p), ("count", C.c_longlong), ("momentum", C.c_float), ("eps", C.c_float),
+                ("partials", C.c_void_p)]
 
 
 class View(C.Structure):

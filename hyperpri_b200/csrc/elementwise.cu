@@ -1083,7 +1083,7 @@ bn_bwd_apply_flat_k(FlatIn a, const float* __restrict__ gamma, const double* __r
 // 256 % (C/8) == 0, so a thread's channel group never changes while it walks vector index v = base + u*256 + tid.
 // A block instruction covers 4 KB contiguous, U of them back to back: measured 6.1-6.3 TB/s on B200 against 5.3 TB/s
 // for the strided mapping above (tools/probes/stream_probe.cu, profiles/stream_probe_r2a_c64.txt).
-template <bool HEAD, int DT, int U>
+template <bool HEAD, int DT, int U, bool HASDY>
 __global__ void __launch_bounds__(256, 2)
 bn_bwd_apply_contig_k(const uint4* __restrict__ x, const uint4* __restrict__ dy, uint4* __restrict__ dx, long long nvec,
                       int C, const float* __restrict__ scale, const float* __restrict__ shift,
@@ -1111,15 +1111,17 @@ bn_bwd_apply_contig_k(const uint4* __restrict__ x, const uint4* __restrict__ dy,
   }
   const long long step = (long long)gridDim.x * 256 * U;
   for (long long v0 = (long long)blockIdx.x * 256 * U + threadIdx.x; v0 < nvec; v0 += step) {
-    uint4 xr[U], dr[U];
-    float dl[U];
+    uint4 xr[U], dr[HASDY ? U : 1];
+    float dl[HEAD ? U : 1];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long v = v0 + u * 256;
-      xr[u] = make_uint4(0, 0, 0, 0); dr[u] = make_uint4(0, 0, 0, 0); dl[u] = 0.f;
+      xr[u] = make_uint4(0, 0, 0, 0);
+      if (HASDY) dr[u] = make_uint4(0, 0, 0, 0);
+      if (HEAD) dl[u] = 0.f;
       if (v < nvec) {
         xr[u] = __ldg(x + v);
-        if (dy != nullptr) dr[u] = __ldg(dy + v);
+        if (HASDY) dr[u] = __ldg(dy + v);
         if (HEAD) dl[u] = __ldg(dlogit + (v >> cg_shift));      // CG is a power of two here (256 % CG == 0)
       }
     }
@@ -1129,14 +1131,14 @@ bn_bwd_apply_contig_k(const uint4* __restrict__ x, const uint4* __restrict__ dy,
       if (v >= nvec) break;
       float xv[8], dz[8], o[8];
       unpack8_t<DT>(xr[u], xv, DT);
-      if (dy != nullptr) unpack8_t<DT>(dr[u], dz, DT);
+      if (HASDY) unpack8_t<DT>(dr[HASDY ? u : 0], dz, DT);
       else {
 #pragma unroll
         for (int k = 0; k < 8; ++k) dz[k] = 0.f;
       }
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        if (HEAD) dz[k] = fmaf(dl[u], hw[k], dz[k]);
+        if (HEAD) dz[k] = fmaf(dl[HEAD ? u : 0], hw[k], dz[k]);
         dz[k] = fmaf(xv[k], sc[k], sh[k]) > 0.f ? dz[k] : 0.f;
         o[k] = fmaf(ca[k], dz[k], fmaf(cb[k], xv[k], cc[k]));
       }
@@ -1145,7 +1147,7 @@ bn_bwd_apply_contig_k(const uint4* __restrict__ x, const uint4* __restrict__ dy,
   }
 }
 
-template <bool HEAD, int DT, int U>
+template <bool HEAD, int DT, int U, bool HASDY>
 __global__ void __launch_bounds__(256, 2)
 bn_bwd_reduce_contig_k(const uint4* __restrict__ x, const uint4* __restrict__ dy, long long nvec, int C,
                        const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
@@ -1163,15 +1165,17 @@ bn_bwd_reduce_contig_k(const uint4* __restrict__ x, const uint4* __restrict__ dy
   for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; s3[k] = 0.f; }
   const long long step = (long long)gridDim.x * 256 * U;
   for (long long v0 = (long long)blockIdx.x * 256 * U + threadIdx.x; v0 < nvec; v0 += step) {
-    uint4 xr[U], dr[U];
-    float dl[U];
+    uint4 xr[U], dr[HASDY ? U : 1];
+    float dl[HEAD ? U : 1];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long v = v0 + u * 256;
-      xr[u] = make_uint4(0, 0, 0, 0); dr[u] = make_uint4(0, 0, 0, 0); dl[u] = 0.f;
+      xr[u] = make_uint4(0, 0, 0, 0);
+      if (HASDY) dr[u] = make_uint4(0, 0, 0, 0);
+      if (HEAD) dl[u] = 0.f;
       if (v < nvec) {
         xr[u] = __ldg(x + v);
-        if (dy != nullptr) dr[u] = __ldg(dy + v);
+        if (HASDY) dr[u] = __ldg(dy + v);
         if (HEAD) dl[u] = __ldg(dlogit + (v >> cg_shift));      // CG is a power of two here (256 % CG == 0)
       }
     }
@@ -1180,7 +1184,7 @@ bn_bwd_reduce_contig_k(const uint4* __restrict__ x, const uint4* __restrict__ dy
       if (v0 + u * 256 >= nvec) break;
       float xv[8], dz[8];
       unpack8_t<DT>(xr[u], xv, DT);
-      if (dy != nullptr) unpack8_t<DT>(dr[u], dz, DT);
+      if (HASDY) unpack8_t<DT>(dr[HASDY ? u : 0], dz, DT);
       else {
 #pragma unroll
         for (int k = 0; k < 8; ++k) dz[k] = 0.f;
@@ -1188,11 +1192,11 @@ bn_bwd_reduce_contig_k(const uint4* __restrict__ x, const uint4* __restrict__ dy
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const float z = fmaf(xv[k], sc[k], sh[k]);
-        if (HEAD) dz[k] = fmaf(dl[u], hw[k], dz[k]);
+        if (HEAD) dz[k] = fmaf(dl[HEAD ? u : 0], hw[k], dz[k]);
         dz[k] = z > 0.f ? dz[k] : 0.f;
         s1[k] += dz[k];
         s2[k] = fmaf(dz[k], xv[k], s2[k]);
-        if (HEAD) s3[k] = fmaf(dl[u], fmaxf(z, 0.f), s3[k]);
+        if (HEAD) s3[k] = fmaf(dl[HEAD ? u : 0], fmaxf(z, 0.f), s3[k]);
       }
     }
   }
@@ -1300,7 +1304,7 @@ head_fwd_k(V x, const float* __restrict__ scale, const float* __restrict__ shift
 }
 
 // Pixel-dense fast path: offset = pixel * pix_stride, no index arithmetic; when one pass of the LPP lanes covers all
-// channels the per-channel constants stay in registers and four pixels are in flight per thread.
+// channels the per-channel constants stay in registers and eight pixels are in flight per thread.
 __global__ void __launch_bounds__(256)
 head_fwd_dense_k(const uint16_t* __restrict__ x, long long sp, int dt, int C, long long npix,
                  const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ w,
@@ -1319,17 +1323,17 @@ head_fwd_dense_k(const uint16_t* __restrict__ x, long long sp, int dt, int C, lo
     ld8v(shift, sub * 8, mine ? C : 0, sh);
     const bool bn = scale != nullptr;
     // block-uniform trip count (full-mask shuffles below); pixel validity is checked per access
-    for (long long base = (long long)blockIdx.x * ppb; base < npix; base += 4 * stride) {
+    for (long long base = (long long)blockIdx.x * ppb; base < npix; base += 8 * stride) {
       const long long p0 = base + slot;
-      uint4 xr[4];
+      uint4 xr[8];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         const long long pp = p0 + u * stride;
         xr[u] = make_uint4(0, 0, 0, 0);
         if (mine && pp < npix) xr[u] = __ldg(reinterpret_cast<const uint4*>(x + pp * sp + sub * 8));
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         const long long pp = p0 + u * stride;
         float f[8], acc = 0.f;
         unpack8(xr[u], f, dt);
@@ -1817,11 +1821,13 @@ extern "C" int hpri_bn_relu_bwd_reduce(const hpri_view_t* x, const float* scale,
     const long long nvec = (long long)x->n * x->h * x->w * CG;
     const uint4* xp = static_cast<const uint4*>(x->ptr);
     const uint4* dp = dy ? static_cast<const uint4*>(dy->ptr) : nullptr;
-#define HPRI_RC(HD, DT, U)                                                                                        \
-    bn_bwd_reduce_contig_k<HD, DT, U><<<contig_grid(nvec, 256 * U, 148 * 4), 256, 0, (cudaStream_t)stream>>>(       \
+#define HPRI_RC(HD, DT, U, HASDY)                                                                                 \
+    bn_bwd_reduce_contig_k<HD, DT, U, HASDY><<<contig_grid(nvec, 256 * U, 148 * 4), 256, 0, (cudaStream_t)stream>>>( \
         xp, dp, nvec, x->c, scale, shift, save_mean, save_invstd, head_w, dlogit, sums)
-    if (x->dtype == DT_F16) { if (dlogit) HPRI_RC(true, DT_F16, 4); else HPRI_RC(false, DT_F16, 8); }
-    else { if (dlogit) HPRI_RC(true, DT_BF16, 4); else HPRI_RC(false, DT_BF16, 8); }
+#define HPRI_RC_DT(DT)                                                                                            \
+    if (dlogit && !dp) HPRI_RC(true, DT, 8, false); else if (dlogit) HPRI_RC(true, DT, 4, true); else HPRI_RC(false, DT, 8, true)
+    if (x->dtype == DT_F16) { HPRI_RC_DT(DT_F16); } else { HPRI_RC_DT(DT_BF16); }
+#undef HPRI_RC_DT
 #undef HPRI_RC
     return last_err();
   }
@@ -1868,11 +1874,13 @@ extern "C" int hpri_bn_relu_bwd_apply(const hpri_view_t* x, const float* scale, 
     const uint4* xp = static_cast<const uint4*>(x->ptr);
     const uint4* dp = dy ? static_cast<const uint4*>(dy->ptr) : nullptr;
     uint4* op = static_cast<uint4*>(dx->ptr);
-#define HPRI_PC(HD, DT, U)                                                                                        \
-    bn_bwd_apply_contig_k<HD, DT, U><<<contig_grid(nvec, 256 * U, 148 * 4), 256, 0, (cudaStream_t)stream>>>(        \
+#define HPRI_PC(HD, DT, U, HASDY)                                                                                 \
+    bn_bwd_apply_contig_k<HD, DT, U, HASDY><<<contig_grid(nvec, 256 * U, 148 * 4), 256, 0, (cudaStream_t)stream>>>( \
         xp, dp, op, nvec, x->c, scale, shift, save_mean, save_invstd, head_w, dlogit, gamma, sums, count, pg)
-    if (x->dtype == DT_F16) { if (dlogit) HPRI_PC(true, DT_F16, 4); else HPRI_PC(false, DT_F16, 8); }
-    else { if (dlogit) HPRI_PC(true, DT_BF16, 4); else HPRI_PC(false, DT_BF16, 8); }
+#define HPRI_PC_DT(DT)                                                                                            \
+    if (dlogit && !dp) HPRI_PC(true, DT, 8, false); else if (dlogit) HPRI_PC(true, DT, 4, true); else HPRI_PC(false, DT, 8, true)
+    if (x->dtype == DT_F16) { HPRI_PC_DT(DT_F16); } else { HPRI_PC_DT(DT_BF16); }
+#undef HPRI_PC_DT
 #undef HPRI_PC
     return last_err();
   }

@@ -161,6 +161,24 @@ __device__ __forceinline__ void flush_stats(float* ssum, float* ssq, int ch, int
   q = make_float2(0.f, 0.f);
 }
 
+// Deterministic variant (hpri_bn_fin_t::partials set): the NW warps that own the same channels add their registers to
+// the CTA's partial sums one after the other (plain read-modify-write, lanes own distinct channels) instead of through
+// shared-memory atomics in arrival order.  Called by all NW * 32 threads of barrier `bar`.
+template <int NW>
+__device__ __forceinline__ void flush_stats_ordered(float* ssum, float* ssq, int ch, int n_total, float2& s, float2& q,
+                                                    int my_warp, int bar) {
+#pragma unroll 1
+  for (int w = 0; w < NW; ++w) {
+    if (my_warp == w) {
+      if (ch < n_total) { ssum[ch] += s.x; ssq[ch] += q.x; }
+      if (ch + 1 < n_total) { ssum[ch + 1] += s.y; ssq[ch + 1] += q.y; }
+    }
+    named_bar_sync(bar, NW * 32);
+  }
+  s = make_float2(0.f, 0.f);
+  q = make_float2(0.f, 0.f);
+}
+
 // Called by the 256 epilogue threads after their CTA's statistics went to global memory: the last CTA of the grid
 // (ticket counter) turns (sum, sumsq) into scale / shift / saved mean / invstd and the running-stat update -- the
 // arithmetic of bn_finalize_k -- and leaves stats and the counter zeroed for the next step.
@@ -173,7 +191,17 @@ __device__ __forceinline__ void bn_finalize_tail(const IgemmArgs& p, int et, int
   __threadfence();
   const hpri_bn_fin_t& f = p.fin;
   for (int c = et; c < p.n_total; c += kEpiThreads) {
-    const double s = __ldcg(p.stats + 2 * c), ss = __ldcg(p.stats + 2 * c + 1);
+    double s, ss;
+    if (f.partials != nullptr) {            // deterministic: the CTAs' slots in CTA order
+      s = 0.0; ss = 0.0;
+      for (unsigned b = 0; b < gridDim.x; ++b) {
+        const float2 v = __ldcg(reinterpret_cast<const float2*>(f.partials) + static_cast<size_t>(b) * p.n_total + c);
+        s += static_cast<double>(v.x);
+        ss += static_cast<double>(v.y);
+      }
+    } else {
+      s = __ldcg(p.stats + 2 * c); ss = __ldcg(p.stats + 2 * c + 1);
+    }
     const double mean = s / (double)f.count;
     double var = ss / (double)f.count - mean * mean;
     if (var < 0) var = 0;
@@ -423,6 +451,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
     const bool elected = gw == 0 && lane == 0;
     uint8_t* stage = smem + L::STAGING_OFF + g * kStageTile;
     const int bar_id = 1 + g;
+    const bool det = p.has_fin && p.fin.partials != nullptr;     // deterministic BatchNorm statistics
     uint32_t lt = 0;
     if (MODE == MODE_FWD) {
       constexpr int MYCH = (NCH + 1) / 2;   // chunks of one accumulator this group handles (at most)
@@ -441,8 +470,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
           if (p.stats != nullptr && n0 != acc_n0) {       // this CTA moved to other output channels: flush
             if (acc_n0 >= 0) {
 #pragma unroll
-              for (int j = 0; j < MYCH; ++j)
-                flush_stats(ssum, ssq, acc_n0 + (2 * j + g) * 64 + 2 * lane, p.n_total, ssv[j], sqv[j]);
+              for (int j = 0; j < MYCH; ++j) {
+                if (det) flush_stats_ordered<4>(ssum, ssq, acc_n0 + (2 * j + g) * 64 + 2 * lane, p.n_total, ssv[j], sqv[j], gw, bar_id);
+                else flush_stats(ssum, ssq, acc_n0 + (2 * j + g) * 64 + 2 * lane, p.n_total, ssv[j], sqv[j]);
+              }
             }
             acc_n0 = n0;
           }
@@ -486,8 +517,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
         }
         if (p.stats != nullptr && acc_n0 >= 0) {
 #pragma unroll
-          for (int j = 0; j < MYCH; ++j)
-            flush_stats(ssum, ssq, acc_n0 + (2 * j + g) * 64 + 2 * lane, p.n_total, ssv[j], sqv[j]);
+          for (int j = 0; j < MYCH; ++j) {
+            if (det) flush_stats_ordered<4>(ssum, ssq, acc_n0 + (2 * j + g) * 64 + 2 * lane, p.n_total, ssv[j], sqv[j], gw, bar_id);
+            else flush_stats(ssum, ssq, acc_n0 + (2 * j + g) * 64 + 2 * lane, p.n_total, ssv[j], sqv[j]);
+          }
         }
         if (elected) bulk_wait_read0();
       }
@@ -532,7 +565,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
       named_bar_sync(3, kEpiThreads);
       for (int ch = threadIdx.x - 64; ch < p.n_total; ch += kEpiThreads) {
         const float a = ssum[ch], b = ssq[ch];
-        if (a != 0.f || b != 0.f) {
+        if (det) {
+          reinterpret_cast<float2*>(p.fin.partials)[static_cast<size_t>(blockIdx.x) * p.n_total + ch] = make_float2(a, b);
+        } else if (a != 0.f || b != 0.f) {
           atomicAdd(p.stats + 2 * ch, static_cast<double>(a));
           atomicAdd(p.stats + 2 * ch + 1, static_cast<double>(b));
         }
@@ -797,6 +832,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int my_r = geo.hr[g] + (row >> 3), my_c = geo.hc[g] + (row & 7);   // this thread's pixel inside the tile
     const bool bw = p.bw_sums != nullptr;          // fused BatchNorm-backward reduction (dgrad launches)
     const bool acc_on = p.stats != nullptr || bw;
+    const bool det = !bw && p.has_fin && p.fin.partials != nullptr;     // deterministic BatchNorm statistics
     const uint8_t* xst = smem + p.xstage_off + g * kStageTile;
     uint64_t* x_full = tmem_empty + 2 + g;
     uint32_t xph = 0;
@@ -816,7 +852,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (acc_on && n0 != acc_n0) {
         if (acc_n0 >= 0) {
 #pragma unroll
-          for (int j = 0; j < NCH; ++j) flush_stats(ssum, ssq, acc_n0 + j * 64 + 2 * lane, p.n_total, ssv[j], sqv[j]);
+          for (int j = 0; j < NCH; ++j) {
+            if (det) flush_stats_ordered<8>(ssum, ssq, acc_n0 + j * 64 + 2 * lane, p.n_total, ssv[j], sqv[j], warp - 2, 3);
+            else flush_stats(ssum, ssq, acc_n0 + j * 64 + 2 * lane, p.n_total, ssv[j], sqv[j]);
+          }
         }
         acc_n0 = n0;
       }
@@ -866,12 +905,17 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (acc_on) {
       if (acc_n0 >= 0) {
 #pragma unroll
-        for (int j = 0; j < NCH; ++j) flush_stats(ssum, ssq, acc_n0 + j * 64 + 2 * lane, p.n_total, ssv[j], sqv[j]);
+        for (int j = 0; j < NCH; ++j) {
+          if (det) flush_stats_ordered<8>(ssum, ssq, acc_n0 + j * 64 + 2 * lane, p.n_total, ssv[j], sqv[j], warp - 2, 3);
+          else flush_stats(ssum, ssq, acc_n0 + j * 64 + 2 * lane, p.n_total, ssv[j], sqv[j]);
+        }
       }
       named_bar_sync(3, kEpiThreads);
       for (int ch = threadIdx.x - 64; ch < p.n_total; ch += kEpiThreads) {
         const float a = ssum[ch], b = ssq[ch];
-        if (a != 0.f || b != 0.f) {
+        if (det) {
+          reinterpret_cast<float2*>(p.fin.partials)[static_cast<size_t>(blockIdx.x) * p.n_total + ch] = make_float2(a, b);
+        } else if (a != 0.f || b != 0.f) {
           if (bw) {        // sums[c] = {sum dz, invstd * (sum dz*x - mean * sum dz), -} like bn_bwd_reduce_*_k
             const float mu = __ldg(p.bw_mean + ch), is = __ldg(p.bw_invstd + ch);
             atomicAdd(p.bw_sums + 3 * ch, static_cast<double>(a));

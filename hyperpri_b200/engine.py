@@ -132,6 +132,17 @@ class _EngineBase:
         elif getattr(self, "_side_saved", None) is not None:
             self._side, self._side_saved = self._side_saved, None
 
+    def _partials(self, cout):
+        """Scratch of the deterministic-statistics mode (ops.set_deterministic / HPRI_DETERMINISTIC=1), else None."""
+        if not ops.DETERMINISTIC:
+            return None
+        need = 148 * 2 * int(cout)
+        buf = getattr(self, "_det_partials", None)
+        if buf is None or buf.numel() < need:
+            buf = torch.zeros(max(need, 148 * 2 * 2048), dtype=torch.float32, device=self.dev)
+            self._det_partials = buf
+        return buf
+
     def _event(self):
         if self._side_used == len(self._side_events):
             self._side_events.append(torch.cuda.Event())
@@ -492,7 +503,7 @@ class UNetEngine(_EngineBase):
         if training:     # statistics in the GEMM epilogue, finalised by the launch's last CTA
             fin = ops.bn_fin(n * h * w, P[L.bn + ".weight"], P[L.bn + ".bias"], P[L.conv + ".bias"],
                              P[L.bn + ".running_mean"], P[L.bn + ".running_var"], P[L.bn + ".num_batches_tracked"],
-                             L.scale, L.shift, L.smean, L.sinv, L.ticket)
+                             L.scale, L.shift, L.smean, L.sinv, L.ticket, partials=self._partials(L.cout))
             ops.igemm_fwd(x, L.pp.fwd, L.cout, 9, raw, L.cout, stats=L.stats, fin=fin)
         else:
             ops.igemm_fwd(x, L.pp.fwd, L.cout, 9, raw, L.cout)
@@ -770,6 +781,9 @@ class SpectralEngine(_EngineBase):
         # against 96 of operand fetch) while 128-column ones sit on the shared-memory operand bandwidth; 1650 features
         # are 6.45 such tiles (7 with the ragged last one), measured 15 % faster than 13 tiles of 128
         self.bn_tile = 256
+        # weight gradients: 128-column tiles re-read X and dY from L2 at 128 B / cycle / SM (ncu: 9.1 GB of DRAM reads for
+        # 2.8 GB of operands, tensor pipe 56 %); 256-column tiles need 94 B / cycle
+        self.wgrad_tile = int(os.environ.get("HPRI_SPECTRAL_WGRAD_TILE", "256"))
         self.Fp = kpad(feats)
         self.Dp = (hsi_depth + 7) // 8 * 8
         d = device
@@ -928,7 +942,8 @@ class SpectralEngine(_EngineBase):
                 elif training:
                     fin = ops.bn_fin(m, P[nm + ".1.weight"], P[nm + ".1.bias"], P[nm + ".0.bias"],
                                      P[nm + ".1.running_mean"], P[nm + ".1.running_var"],
-                                     P[nm + ".1.num_batches_tracked"], scale, shift, smean, sinv, L.ticket)
+                                     P[nm + ".1.num_batches_tracked"], scale, shift, smean, sinv, L.ticket,
+                                     partials=self._partials(F))
                     ops.igemm_fwd(src, L.pp.fwd, F, 1, raw, Fp, stats=L.stats, x_c=(self.D if nm == "tail" else None),
                                   block_n=self.bn_tile, fin=fin)
                 else:
@@ -999,7 +1014,7 @@ class SpectralEngine(_EngineBase):
                                 out_scale=inv_bn, out_beta=acc_beta, flag=self.overflow, reduced=pp is not None)
                 xg = src if src.dtype == GRAD else ops.convert16(src, ws["cvt"][..., :src.shape[-1]])
                 self._on_side(lambda xg=xg, R=R, L=L, nm=nm: ops.igemm_wgrad(
-                    xg, R, 0, F, L.gw, x_c=(self.D if nm == "tail" else None), dy_c=F))
+                    xg, R, 0, F, L.gw, x_c=(self.D if nm == "tail" else None), dy_c=F, block_n=self.wgrad_tile))
                 r_busy[k] = self._side_mark()
                 if dx_dst is not None:
                     if L.pp.spec.split:

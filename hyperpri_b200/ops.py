@@ -244,10 +244,25 @@ def conv3x3_halo_ok(h, w, rows) -> bool:
     return bool(_lib.lib().hpri_conv3x3_halo_ok(int(h), int(w), int(rows)))
 
 
-def bn_fin(count, gamma, beta, conv_bias, rmean, rvar, nbt, scale, shift, smean, sinv, counter, momentum=0.1, eps=1e-5):
+DETERMINISTIC = __import__("os").environ.get("HPRI_DETERMINISTIC", "0") == "1"
+
+
+def set_deterministic(on: bool):
+    """Deterministic BatchNorm statistics in the forward pass: every CTA's partial sums go to its own slot (warps added
+    in a fixed order) and the last CTA adds the slots in CTA order, instead of fp64 atomics in arrival order.  Two
+    forward passes on the same input and weights then give bit-identical logits (the backward pass keeps its
+    atomics: split-K weight gradients, BatchNorm-backward sums)."""
+    global DETERMINISTIC
+    DETERMINISTIC = bool(on)
+
+
+def bn_fin(count, gamma, beta, conv_bias, rmean, rvar, nbt, scale, shift, smean, sinv, counter, momentum=0.1, eps=1e-5,
+           partials=None):
     """hpri_bn_fin_t for igemm_fwd(fin=...): the arguments of bn_finalize(training=True) plus a zero-initialised
-    uint32 ticket counter owned by the layer."""
+    uint32 ticket counter owned by the layer.  partials: fp32 scratch (>= 148 * C * 2) selecting the deterministic
+    statistics path."""
     f = _lib.BnFin()
+    f.partials = 0 if partials is None else partials.data_ptr()
     f.gamma, f.beta, f.conv_bias = gamma.data_ptr(), beta.data_ptr(), 0 if conv_bias is None else conv_bias.data_ptr()
     f.running_mean, f.running_var, f.num_batches_tracked = rmean.data_ptr(), rvar.data_ptr(), nbt.data_ptr()
     f.scale, f.shift, f.save_mean, f.save_invstd = scale.data_ptr(), shift.data_ptr(), smean.data_ptr(), sinv.data_ptr()

@@ -65,6 +65,10 @@ typedef struct {
   unsigned int* counter;       /* one zero-initialised word owned by the layer */
   long long count;             /* elements per channel */
   float momentum, eps;
+  float* partials;             /* nullable.  Deterministic statistics: scratch of >= 148 * w_rows * 2 floats.  Every CTA
+                                * stores its per-channel partial (sum, sumsq) in its own slot -- its warps' contributions
+                                * added in a fixed order -- and the last CTA adds the slots in CTA order (fp64), instead of
+                                * fp64 atomics in arrival order: two runs on the same input give bit-identical outputs. */
 } hpri_bn_fin_t;
 /* bw (nullable; 3x3 dgrad launches on the halo kernel only, see hpri_conv3x3_halo_ok): the output y is the gradient dy
  * of the BatchNorm+ReLU layer below; the epilogue also accumulates pass 1 of its backward (what

@@ -10,7 +10,8 @@ from hyperpri_b200.src.PLTrainer import train_net, validate_net
 if __name__ == "__main__":
     rel_call_path = os.path.dirname(os.path.abspath(__file__))
     RANDOM_STATE = 1
-    MODEL_SHARD = False      # reference: DeepSpeed ZeRO-2 for SpectralUNET; here: the same data-parallel path
+    MODEL_SHARD = False      # reference: DeepSpeed ZeRO-2 for SpectralUNET; here: the pixel-parallel SpectralUNET option
+                             # (every rank a row strip of every image); raises for the other models
     LOAD_CKPT = False
     DATA_AUG = False
     n_seeds, start_split, num_splits = 1, 0, 5
