@@ -400,6 +400,9 @@ def _sweep_device(model, loader, trainer):
 
 
 def _use_device_sweep(trainer, save_segmaps):
+    if save_segmaps:
+        warnings.warn("save_segmaps=True: rendering segmentation maps to PNG (reference PLTrainer.py:219-267, matplotlib) is "
+                      "outside this path; predictions are collected on the host as in the reference, no figures are written")
     return isinstance(trainer, _Loop) and trainer.device.type == "cuda" and not save_segmaps
 
 

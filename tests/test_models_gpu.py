@@ -105,8 +105,10 @@ def test_train_step_parity_vs_oracle(model, n, bands, h, w, feats):
     ("unet_bil_2x3x34x42", "UNET", 2, 3, 34, 42, 9, 0), ("cubenet_bil_att_2x238x32x40", "CubeNET", 2, 238, 32, 40, 10, 0)])
 @pytest.mark.parametrize("mode", ["train", "eval"])
 def test_against_reference_golden(name, model, n, bands, h, w, seed, feats, mode):
-    """Reference-module outputs (tests/golden, made by oracle/gen_golden.py).  These shapes are tiny (BatchNorm over
-    as few as 8 samples), so the tolerance is 3e-2 of max|logit| here; realistic sizes are held to 1e-2 above."""
+    """Reference-module outputs (tests/golden, made by oracle/gen_golden.py), held to the north_star 1e-2 of max|logit|
+    in train mode and 3e-3 in eval mode (running statistics; measured <= 9.2e-4).  Exception: use_attention=True in train
+    mode stays at 3e-2 -- two fp16-stored operands are multiplied at every decoder level and these shapes normalise over
+    as few as 8 samples per channel (measured 1.4e-2 .. 2.0e-2; 7.2e-3 at most for every other case)."""
     g = np.load(os.path.join(GOLD, name + ".npz"))
     fd = int(name.split("_fd")[1].split("_")[0]) if "_fd" in name else 64
     net, _ = build(model, bands, feats, seed, att="_att_" in name, fd=fd, bil="_bil_" in name)
@@ -118,8 +120,9 @@ def test_against_reference_golden(name, model, n, bands, h, w, seed, feats, mode
     ref = torch.from_numpy(g[f"{mode}.logits"])
     record(test="against_reference_golden", name=name, mode=mode,
            logit_max_rel_err=(lg - ref).abs().max().item() / ref.abs().max().item(), loss_abs_err=abs(loss - float(g[f"{mode}.loss"])))
-    assert (lg - ref).abs().max().item() <= 3e-2 * ref.abs().max().item()
-    assert abs(loss - float(g[f"{mode}.loss"])) < 2e-3
+    tol = 3e-3 if mode == "eval" else (3e-2 if "_att_" in name else 1e-2)
+    assert (lg - ref).abs().max().item() <= tol * ref.abs().max().item()
+    assert abs(loss - float(g[f"{mode}.loss"])) < (2e-3 if "_att_" in name else 3e-4)
 
 
 def test_odd_sizes_pad_and_pool_floor():
