@@ -5,6 +5,8 @@
 #include "ptx.cuh"
 #include "hyperpri_b200.h"
 
+#include <cstdlib>
+
 namespace hpri {
 
 long long g_launch_count = 0;
@@ -672,21 +674,22 @@ __global__ void bn_finalize_k(double* stats, long long count, const float* gamma
 // One thread = one 2x2 pixel window x 8 channels.
 template <int DT>
 __global__ void __launch_bounds__(256)
-bn_relu_apply_k(V x, const float* __restrict__ scale, const float* __restrict__ shift, V y, V pool, int CG, int rows) {
+bn_relu_apply_k(V x, const float* __restrict__ scale, const float* __restrict__ shift, V y, V pool, int CG, int rows, int rev) {
   grid_dep_launch();      // a following tcgen05 launch may start its prologue while this grid drains
+  const int bly = rev ? gridDim.y - 1 - blockIdx.y : blockIdx.y, blz = rev ? gridDim.z - 1 - blockIdx.z : blockIdx.z;
   // grid.x tiles the (window column, channel group) plane, grid.y chunks of `rows` window rows, grid.z the image:
   // a thread keeps its scale / shift in registers and walks rows without index arithmetic
   const int wh = (x.h + 1) >> 1, ww = (x.w + 1) >> 1;
   const int g = blockIdx.x * 256 + threadIdx.x;
   const int cg = g % CG, wx = g / CG;
   if (wx >= ww) return;
-  const int n = blockIdx.z;
+  const int n = blz;
   const int c0 = cg * 8;
   float sc[8], sh[8];
   ld8v(scale, c0, x.c, sc);
   ld8v(shift, c0, x.c, sh);
-  const int wy1 = min(wh, (int)(blockIdx.y + 1) * rows);
-  for (int wy = blockIdx.y * rows; wy < wy1; ++wy) {
+  const int wy1 = min(wh, (bly + 1) * rows);
+  for (int wy = bly * rows; wy < wy1; ++wy) {
     uint4 r[4];
     bool inb[4];
 #pragma unroll
@@ -831,12 +834,13 @@ __device__ __forceinline__ void window_word(const BwdIn& a, const Win& w, int j,
 // constants loaded once.
 // pass 1: sums[c] = {sum dz, sum dz*xhat, sum dlogit*act}
 template <int DT, bool HEAD>
-__global__ void __launch_bounds__(256, 2) bn_bwd_reduce_k(BwdIn a, double* sums, int CG, int rows) {
+__global__ void __launch_bounds__(256, 2) bn_bwd_reduce_k(BwdIn a, double* sums, int CG, int rows, int rev) {
   __shared__ float red[256][25];                 // odd stride: conflict-free row writes
+  const int bly = rev ? gridDim.y - 1 - blockIdx.y : blockIdx.y, blz = rev ? gridDim.z - 1 - blockIdx.z : blockIdx.z;
   const int wh = (a.x.h + 1) >> 1, ww = (a.x.w + 1) >> 1;
   const int g = blockIdx.x * 256 + threadIdx.x;
   const int cg = g % CG, wx = g / CG;
-  const int n = blockIdx.z;
+  const int n = blz;
   const int c0 = cg * 8;
   float s1[8], s2[8], s3[8];                     // s2 holds sum dz*x; centred and scaled at the end
 #pragma unroll
@@ -846,8 +850,8 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_k(BwdIn a, double* sums,
     ld8v(a.scale, c0, a.x.c, sc);
     ld8v(a.shift, c0, a.x.c, sh);
     ld8v(a.head_w, c0, a.x.c, hwv);
-    const int wy1 = min(wh, (int)(blockIdx.y + 1) * rows);
-    for (int wy = blockIdx.y * rows; wy < wy1; ++wy) {
+    const int wy1 = min(wh, (bly + 1) * rows);
+    for (int wy = bly * rows; wy < wy1; ++wy) {
       Win w;
       load_window(a, n, wy, wx, c0, w);
 #pragma unroll
@@ -906,14 +910,15 @@ __device__ __forceinline__ void write_param_grads(const double* __restrict__ sum
 template <int DT, bool HEAD>
 __global__ void __launch_bounds__(256, 2)
 bn_bwd_apply_k(BwdIn a, const float* __restrict__ gamma, const double* __restrict__ sums, long long count, V dx,
-               ParamGradOut pg, int CG, int rows) {
+               ParamGradOut pg, int CG, int rows, int rev) {
   grid_dep_launch();      // a following tcgen05 launch may start its prologue while this grid drains
   if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) write_param_grads(sums, a.x.c, pg);
+  const int bly = rev ? gridDim.y - 1 - blockIdx.y : blockIdx.y, blz = rev ? gridDim.z - 1 - blockIdx.z : blockIdx.z;
   const int wh = (a.x.h + 1) >> 1, ww = (a.x.w + 1) >> 1;
   const int g = blockIdx.x * 256 + threadIdx.x;
   const int cg = g % CG, wx = g / CG;
   if (wx >= ww) return;
-  const int n = blockIdx.z;
+  const int n = blz;
   const int c0 = cg * 8;
   const float rc = 1.f / (float)count;
   float sc[8], sh[8], hwv[8], ca[8], cb[8], cc[8];
@@ -932,8 +937,8 @@ bn_bwd_apply_k(BwdIn a, const float* __restrict__ gamma, const double* __restric
     cb[k] = -gm * is * is * m2;
     cc[k] = -gm * is * m1 - cb[k] * mu;
   }
-  const int wy1 = min(wh, (int)(blockIdx.y + 1) * rows);
-  for (int wy = blockIdx.y * rows; wy < wy1; ++wy) {
+  const int wy1 = min(wh, (bly + 1) * rows);
+  for (int wy = bly * rows; wy < wy1; ++wy) {
     Win w;
     load_window(a, n, wy, wx, c0, w);
     uint32_t o[4][4];
@@ -1105,7 +1110,7 @@ bn_bwd_apply_contig_k(const uint4* __restrict__ x, const uint4* __restrict__ dy,
                       int C, const float* __restrict__ scale, const float* __restrict__ shift,
                       const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ head_w,
                       const float* __restrict__ dlogit, const float* __restrict__ gamma,
-                      const double* __restrict__ sums, long long count, ParamGradOut pg) {
+                      const double* __restrict__ sums, long long count, ParamGradOut pg, int rev) {
   grid_dep_launch();
   if (blockIdx.x == 0) write_param_grads(sums, C, pg);
   const int CG = C >> 3;
@@ -1125,8 +1130,11 @@ bn_bwd_apply_contig_k(const uint4* __restrict__ x, const uint4* __restrict__ dy,
     cb[k] = -g * is * is * m2;
     cc[k] = -g * is * m1 - cb[k] * mu;
   }
-  const long long step = (long long)gridDim.x * 256 * U;
-  for (long long v0 = (long long)blockIdx.x * 256 * U + threadIdx.x; v0 < nvec; v0 += step) {
+  // chunk c of 256 * U vectors; rev: the LAST chunk first -- the tensor a tcgen05 kernel has just written in ascending
+  // tile order is then read starting with the part that is still in L2 (126 MB against 150 MB tensors at full resolution)
+  const long long nchunks = (nvec + 256 * U - 1) / (256 * U);
+  for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const long long v0 = (rev ? nchunks - 1 - c : c) * (256 * U) + threadIdx.x;
     uint4 xr[U], dr[HASDY ? U : 1];
     float dl[HEAD ? U : 1];
 #pragma unroll
@@ -1168,7 +1176,7 @@ __global__ void __launch_bounds__(256, 2)
 bn_bwd_reduce_contig_k(const uint4* __restrict__ x, const uint4* __restrict__ dy, long long nvec, int C,
                        const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
                        const float* __restrict__ invstd, const float* __restrict__ head_w,
-                       const float* __restrict__ dlogit, double* sums) {
+                       const float* __restrict__ dlogit, double* sums, int rev) {
   __shared__ float red[256][25];                 // odd stride: conflict-free row writes
   const int CG = C >> 3;
   const int cg_shift = 31 - __clz(CG);
@@ -1179,8 +1187,11 @@ bn_bwd_reduce_contig_k(const uint4* __restrict__ x, const uint4* __restrict__ dy
   ld8v(head_w, c0, C, hw);
 #pragma unroll
   for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; s3[k] = 0.f; }
-  const long long step = (long long)gridDim.x * 256 * U;
-  for (long long v0 = (long long)blockIdx.x * 256 * U + threadIdx.x; v0 < nvec; v0 += step) {
+  // chunk c of 256 * U vectors; rev: the LAST chunk first -- the tensor a tcgen05 kernel has just written in ascending
+  // tile order is then read starting with the part that is still in L2 (126 MB against 150 MB tensors at full resolution)
+  const long long nchunks = (nvec + 256 * U - 1) / (256 * U);
+  for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const long long v0 = (rev ? nchunks - 1 - c : c) * (256 * U) + threadIdx.x;
     uint4 xr[U], dr[HASDY ? U : 1];
     float dl[HEAD ? U : 1];
 #pragma unroll
@@ -1235,15 +1246,16 @@ bn_bwd_reduce_contig_k(const uint4* __restrict__ x, const uint4* __restrict__ dy
 template <int DT>
 __global__ void __launch_bounds__(256, 4)
 bn_relu_apply_contig_k(const uint4* __restrict__ x, uint4* __restrict__ y, long long nvec, int C,
-                       const float* __restrict__ scale, const float* __restrict__ shift) {
+                       const float* __restrict__ scale, const float* __restrict__ shift, int rev) {
   grid_dep_launch();
   const int CG = C >> 3;
   const int c0 = (threadIdx.x % CG) * 8;
   float sc[8], sh[8];
   ld8v(scale, c0, C, sc);
   ld8v(shift, c0, C, sh);
-  const long long step = (long long)gridDim.x * 1024;
-  for (long long v0 = (long long)blockIdx.x * 1024 + threadIdx.x; v0 < nvec; v0 += step) {
+  const long long nchunks = (nvec + 1023) / 1024;
+  for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    const long long v0 = (rev ? nchunks - 1 - c : c) * 1024 + threadIdx.x;
     uint4 xr[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -1273,6 +1285,18 @@ static inline bool vec_contig(const hpri_view_t* v) {
 static inline int contig_grid(long long nvec, int per_block, int cap) {
   long long g = (nvec + per_block - 1) / per_block;
   return (int)(g < 1 ? 1 : g > cap ? cap : g);
+}
+
+// Traversal order of the HBM-bound BatchNorm kernels (see the chunk loop above): 1 = last chunk first.  Default 0:
+// measured on B200 the reversed order changes nothing (7.66 vs 7.64 ms per step, tools/ab_step.py) -- the 126 MB L2 keeps
+// too little of a 150 MB tensor across a kernel boundary for the order to matter.
+static int g_reverse = -1;
+static inline int reverse_on() {
+  if (g_reverse < 0) {
+    const char* e = getenv("HPRI_REVERSE_ELEMENTWISE");
+    g_reverse = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  return g_reverse;
 }
 
 static inline bool pixel_dense(const hpri_view_t* v) {
@@ -1565,7 +1589,11 @@ static inline int grid_for(long long work_items, int per_block, int cap = 148 * 
 
 using namespace hpri;
 
-extern "C" int hpri_abi_version(void) { return 5; }
+extern "C" int hpri_abi_version(void) { return 6; }
+extern "C" int hpri_set_reverse_elementwise(int on) {
+  g_reverse = on ? 1 : 0;
+  return HPRI_OK;
+}
 extern "C" long long hpri_launch_count(void) { return g_launch_count; }
 
 extern "C" int hpri_pack_weights(const float* src, void* dst, int dst_dtype, int G, int R, int T, int C, int kc64,
@@ -1778,10 +1806,10 @@ extern "C" int hpri_bn_relu_apply(const hpri_view_t* x, const float* scale, cons
     const int grid = contig_grid(nvec, 1024, 1 << 30);      // one 16 KB chunk per block: measured best for 1 in / 1 out
     if (x->dtype == DT_F16)
       bn_relu_apply_contig_k<DT_F16><<<grid, 256, 0, (cudaStream_t)stream>>>(
-          static_cast<const uint4*>(x->ptr), static_cast<uint4*>(y->ptr), nvec, x->c, scale, shift);
+          static_cast<const uint4*>(x->ptr), static_cast<uint4*>(y->ptr), nvec, x->c, scale, shift, reverse_on());
     else
       bn_relu_apply_contig_k<DT_BF16><<<grid, 256, 0, (cudaStream_t)stream>>>(
-          static_cast<const uint4*>(x->ptr), static_cast<uint4*>(y->ptr), nvec, x->c, scale, shift);
+          static_cast<const uint4*>(x->ptr), static_cast<uint4*>(y->ptr), nvec, x->c, scale, shift, reverse_on());
     return last_err();
   }
   if (!pooled && CG <= 256 && pixel_dense(x) && pixel_dense(y)) {
@@ -1799,7 +1827,7 @@ extern "C" int hpri_bn_relu_apply(const hpri_view_t* x, const float* scale, cons
   int rows = 0;
   const dim3 wgrid = win_grid(x, CG, &rows);
 #define HPRI_AW(DT) \
-  bn_relu_apply_k<DT><<<wgrid, 256, 0, (cudaStream_t)stream>>>(mk(x), scale, shift, mk(y), mk(pooled), CG, rows)
+  bn_relu_apply_k<DT><<<wgrid, 256, 0, (cudaStream_t)stream>>>(mk(x), scale, shift, mk(y), mk(pooled), CG, rows, reverse_on())
   const int dtw = win_dtype(x, y, pooled, nullptr);
   if (dtw == DT_F16) HPRI_AW(DT_F16); else if (dtw == DT_BF16) HPRI_AW(DT_BF16); else HPRI_AW(-1);
 #undef HPRI_AW
@@ -1839,7 +1867,7 @@ extern "C" int hpri_bn_relu_bwd_reduce(const hpri_view_t* x, const float* scale,
     const uint4* dp = dy ? static_cast<const uint4*>(dy->ptr) : nullptr;
 #define HPRI_RC(HD, DT, U, HASDY)                                                                                 \
     bn_bwd_reduce_contig_k<HD, DT, U, HASDY><<<contig_grid(nvec, 256 * U, 148 * 4), 256, 0, (cudaStream_t)stream>>>( \
-        xp, dp, nvec, x->c, scale, shift, save_mean, save_invstd, head_w, dlogit, sums)
+        xp, dp, nvec, x->c, scale, shift, save_mean, save_invstd, head_w, dlogit, sums, reverse_on())
 #define HPRI_RC_DT(DT)                                                                                            \
     if (dlogit && !dp) HPRI_RC(true, DT, 8, false); else if (dlogit) HPRI_RC(true, DT, 4, true); else HPRI_RC(false, DT, 8, true)
     if (x->dtype == DT_F16) { HPRI_RC_DT(DT_F16); } else { HPRI_RC_DT(DT_BF16); }
@@ -1865,7 +1893,7 @@ extern "C" int hpri_bn_relu_bwd_reduce(const hpri_view_t* x, const float* scale,
   const dim3 grid = win_grid(x, CG, &rows);
   const int dt = win_dtype(x, dy, dpool, nullptr);
   const bool head = dlogit != nullptr;
-#define HPRI_RED(DT, HD) bn_bwd_reduce_k<DT, HD><<<grid, 256, 0, (cudaStream_t)stream>>>(a, sums, CG, rows)
+#define HPRI_RED(DT, HD) bn_bwd_reduce_k<DT, HD><<<grid, 256, 0, (cudaStream_t)stream>>>(a, sums, CG, rows, reverse_on())
   if (dt == DT_F16) { if (head) HPRI_RED(DT_F16, true); else HPRI_RED(DT_F16, false); }
   else if (dt == DT_BF16) { if (head) HPRI_RED(DT_BF16, true); else HPRI_RED(DT_BF16, false); }
   else { if (head) HPRI_RED(-1, true); else HPRI_RED(-1, false); }
@@ -1892,7 +1920,7 @@ extern "C" int hpri_bn_relu_bwd_apply(const hpri_view_t* x, const float* scale, 
     uint4* op = static_cast<uint4*>(dx->ptr);
 #define HPRI_PC(HD, DT, U, HASDY)                                                                                 \
     bn_bwd_apply_contig_k<HD, DT, U, HASDY><<<contig_grid(nvec, 256 * U, 148 * 4), 256, 0, (cudaStream_t)stream>>>( \
-        xp, dp, op, nvec, x->c, scale, shift, save_mean, save_invstd, head_w, dlogit, gamma, sums, count, pg)
+        xp, dp, op, nvec, x->c, scale, shift, save_mean, save_invstd, head_w, dlogit, gamma, sums, count, pg, reverse_on())
 #define HPRI_PC_DT(DT)                                                                                            \
     if (dlogit && !dp) HPRI_PC(true, DT, 8, false); else if (dlogit) HPRI_PC(true, DT, 4, true); else HPRI_PC(false, DT, 8, true)
     if (x->dtype == DT_F16) { HPRI_PC_DT(DT_F16); } else { HPRI_PC_DT(DT_BF16); }
@@ -1926,7 +1954,7 @@ extern "C" int hpri_bn_relu_bwd_apply(const hpri_view_t* x, const float* scale, 
   const int dt = win_dtype(x, dy, dpool, dx);
   const bool head = dlogit != nullptr;
 #define HPRI_APP(DT, HD)                                                                                          \
-  bn_bwd_apply_k<DT, HD><<<grid, 256, 0, (cudaStream_t)stream>>>(a, gamma, sums, count, mk(dx), pg, CGw, rows)
+  bn_bwd_apply_k<DT, HD><<<grid, 256, 0, (cudaStream_t)stream>>>(a, gamma, sums, count, mk(dx), pg, CGw, rows, reverse_on())
   if (dt == DT_F16) { if (head) HPRI_APP(DT_F16, true); else HPRI_APP(DT_F16, false); }
   else if (dt == DT_BF16) { if (head) HPRI_APP(DT_BF16, true); else HPRI_APP(DT_BF16, false); }
   else { if (head) HPRI_APP(-1, true); else HPRI_APP(-1, false); }

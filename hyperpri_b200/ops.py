@@ -281,6 +281,11 @@ def set_wgrad_algo(algo: int):
     check(_lib.lib().hpri_set_wgrad_algo(int(algo)), "hpri_set_wgrad_algo")
 
 
+def set_reverse_elementwise(on: bool):
+    """Traversal order of the HBM-bound BatchNorm kernels: last chunk first, or ascending (default; no measured gain)."""
+    check(_lib.lib().hpri_set_reverse_elementwise(int(bool(on))), "hpri_set_reverse_elementwise")
+
+
 def set_sm_reserve(sms: int):
     """Keep `sms` SMs out of the persistent tensor-core grids (room for concurrently running NCCL CTAs)."""
     check(_lib.lib().hpri_set_sm_reserve(int(sms)), "hpri_set_sm_reserve")

@@ -221,6 +221,11 @@ int hpri_bn_finalize(double* stats, long long count, const float* gamma, const f
                      float* running_mean, float* running_var, long long* num_batches_tracked, float momentum,
                      float eps, int training, float* scale, float* shift, float* save_mean, float* save_invstd,
                      int C, void* stream);
+/* Traversal order of the HBM-bound BatchNorm kernels: 1 = last chunk first, so that a tensor a tcgen05 kernel has just
+ * written in ascending tile order is read starting with the part still in L2; 0 (default) = ascending -- measured, the
+ * reversed order gains nothing on B200.  Seeded by the environment variable HPRI_REVERSE_ELEMENTWISE.  Values are
+ * unchanged (reductions differ in summation order only). */
+int hpri_set_reverse_elementwise(int on);
 /* y = relu(x*scale+shift) (model_parts.py:23-24); optional fused MaxPool2d(2) output (model_parts.py:40). */
 int hpri_bn_relu_apply(const hpri_view_t* x, const float* scale, const float* shift, const hpri_view_t* y,
                        const hpri_view_t* pooled, void* stream);

@@ -35,8 +35,9 @@ def main():
             eng.set_next_input(x)
         eng.backward(dlogit, prescaled=True)
 
-    def cfg(prefetch=True, overlap=True, conv=-1, wgrad=-1):
+    def cfg(prefetch=True, overlap=True, conv=-1, wgrad=-1, reverse=False):
         def apply():
+            ops.set_reverse_elementwise(reverse)
             state["prefetch"] = prefetch
             eng.set_overlap(overlap)
             eng._no_prefetch = not prefetch
@@ -44,7 +45,7 @@ def main():
             ops.set_wgrad_algo(wgrad)
         return apply
     configs = {"default": cfg(), "no_prefetch": cfg(prefetch=False), "no_overlap": cfg(prefetch=False, overlap=False),
-               "single_cta_convs": cfg(conv=1), "generic_wgrad": cfg(wgrad=0)}
+               "single_cta_convs": cfg(conv=1), "generic_wgrad": cfg(wgrad=0), "reversed_elementwise": cfg(reverse=True)}
     if which:
         configs = {k: v for k, v in configs.items() if k in which}
     res = {k: [] for k in configs}
