@@ -220,3 +220,81 @@ def test_pixel_parallel_spectralunet_equals_single_gpu(feats):
         assert cos(fa, fb) > 0.995 and abs(fa.norm().item() / fb.norm().item() - 1.0) < 0.02
     for k in res[0][3]:
         assert torch.equal(res[0][3][k], res[1][3][k]), k                      # both ranks hold identical reduced gradients
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The reference's entry function under torchrun-style launch on two GPUs (PLTrainer.py:333-460): train_net with the
+# engine-backed models -- data parallel (CubeNET: sharded sampler, bucketed all-reduce on the side stream, FusedAdam) and
+# model_parallel=True (SpectralUNET: pixel-parallel strips).  Replicas must stay bit-identical, the loss must fall,
+# checkpoints are written by rank 0 only.
+def _write_tiny_dataset(root, n_train=4, n_val=2, h=32, w=48):
+    import json as _json
+    import numpy as np
+    from PIL import Image
+    from hyperpri_b200 import envi
+    base = os.path.join(root, "Datasets", "HyperPRI", "Peanut_968x608")
+    for d in ("rgb_files", "hsi_files", "mask_files"):
+        os.makedirs(os.path.join(base, d), exist_ok=True)
+    os.makedirs(os.path.join(root, "Datasets", "HyperPRI", "data_splits"), exist_ok=True)
+    rs = np.random.RandomState(0)
+    for split, cnt, day0 in (("train", n_train, 1), ("val", n_val, 11)):
+        dates = [f"202207{day0 + i:02d}" for i in range(cnt)]
+        for date in dates:
+            stem = f"{date}_box37_ref"
+            mask = np.zeros((h, w), np.uint8)
+            mask[:, w // 3: w // 3 + 6] = 3
+            cube = rs.random_sample((h, w, 299)).astype(np.float32) * 0.2
+            cube[mask > 0, 100:180] += 0.6
+            envi.save(os.path.join(base, "hsi_files", "hinalea_hsi.hdr"), os.path.join(base, "hsi_files", stem + ".dat"), cube)
+            Image.fromarray(mask).save(os.path.join(base, "mask_files", stem + "_mask.png"))
+            Image.fromarray((rs.random_sample((h, w, 3)) * 255).astype(np.uint8)).save(os.path.join(base, "rgb_files", stem + ".png"))
+        js = {"img_dir": "rgb_files", "hsi_dir": "hsi_files", "mask_dir": "mask_files", "notes": "synthetic",
+              "box37": {"plant_folder": "Peanut", "resolution": "968x608", "box_no": 37, "phenotype": 1, "dates": dates,
+                        "weights": None}}
+        with open(os.path.join(root, "Datasets", "HyperPRI", "data_splits", f"{split}1.json"), "w") as f:
+            _json.dump(js, f)
+
+
+def _train_worker(rank, world, port, root, model_name, model_parallel, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from hyperpri_b200.src import PLTrainer as T
+    from hyperpri_b200.src.Experiments.params_HyperPRI import ExpHyperspectralPRI
+    torch.manual_seed(1000 + rank)                       # replicas start DIFFERENT: train_net must synchronise them
+    p = ExpHyperspectralPRI(root, split_no=1, seed_num=0, comet_logging=False)
+    p.epochs, p.patch_size, p.spectral_bn_size = 3, (32, 48), 64
+    p.change_network_param(model_name, root, 1)
+    trainer = T.train_net(p, model_parallel=model_parallel)
+    net = trainer.model.m_network
+    flat = torch.cat([t.detach().float().flatten() for t in net.parameters()]).cpu()
+    eng = net._get_engine(torch.device("cuda", rank))
+    q.put((rank, flat, [h["tr_loss"] for h in trainer.history], [h["val_loss"] for h in trainer.history],
+           int(eng.overflow.item()), sorted(os.listdir(os.path.join(p.save_path, "Checkpoints")))))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("model_name,model_parallel", [("CubeNET", False), ("SpectralUNET", True)])
+def test_train_net_on_two_gpus(tmp_path, model_name, model_parallel):
+    root = str(tmp_path)
+    _write_tiny_dataset(root)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_worker, args=(r, 2, port, root, model_name, model_parallel, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {r[0]: r[1:] for r in _collect(q, procs, timeout=400)}
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert torch.equal(res[0][0], res[1][0])                       # replicas bit-identical after three epochs
+    assert res[0][1][-1] < res[0][1][0]                           # training loss falls
+    assert res[0][2] == res[1][2]                                  # the monitored loss is the same number on both ranks
+    assert res[0][3] == 0 and res[1][3] == 0                       # no fp16 gradient overflow
+    assert res[0][4] == ["best.ckpt", "last.ckpt"]
+    if model_parallel:                                             # both ranks saw the whole batch: identical training losses
+        assert res[0][1] == res[1][1]
