@@ -9,7 +9,7 @@ The nn.Modules in ``hyperpri_b200.src.Experiments.models`` call it through one
 autograd.Function, so ``loss.backward()`` fills ``.grad`` on the module's own Parameters.
 
 Dataflow decisions:
-  * conv -> (raw bf16 + per-channel sum/sumsq in the GEMM epilogue) -> bn_finalize ->
+  * conv -> (raw fp16 + per-channel sum/sumsq in the GEMM epilogue, finalised by the launch's last CTA) ->
     bn_relu_apply writes the activation straight into its consumer's buffer (the first half of
     the decoder's concat buffer for skips, plus the 2x2-pooled tensor in the same pass);
   * ConvTranspose2d writes the second half of the concat buffer (pixel-shuffle epilogue); the
@@ -17,8 +17,11 @@ Dataflow decisions:
   * the train-mode conv bias is cancelled by BatchNorm: it is skipped in the GEMM and re-added to
     running_mean; its gradient is identically zero and returned as zeros;
   * backward recomputes ReLU masks / pool arg-max from the saved raw conv outputs;
-  * forward tensors (activations, forward weight operands) are fp16, gradients and dgrad weight
-    operands bf16, every accumulation fp32 (wgrad multiplies fp16 x by bf16 dy in one tcgen05.mma).
+  * everything stored between kernels is fp16 (activations, weight operands, loss-scaled gradients), every
+    accumulation fp32 / fp64; parameter gradients land unscaled in one flat fp32 arena ordered by backward completion
+    (the data-parallel buckets), whose views are handed to the Parameters as their .grad;
+  * weight gradients run on a second stream, the bucketed all-reduce hook behind them on that stream; the next batch's
+    ingest may run on a third (set_next_input).
 """
 from __future__ import annotations
 
@@ -41,7 +44,7 @@ def _e(shape, dev, dtype=ACT):
 
 
 class _PackedParam:
-    """bf16 GEMM operand(s) of one fp32 parameter, re-packed when the parameter changes."""
+    """16-bit GEMM operand(s) of one fp32 parameter, re-packed when the parameter changes."""
 
     def __init__(self, spec: WeightSpec, need_dgrad: bool):
         self.spec, self.need_dgrad = spec, need_dgrad
