@@ -778,8 +778,13 @@ class SpectralEngine(_EngineBase):
     (models.py:105-115,132-144), concat by writing into halves of shared buffers."""
     BLOCKS = ["tail", "down1", "down2", "down3", "down4", "up1", "up2", "up3", "up4"]
 
-    def __init__(self, params: Dict[str, torch.Tensor], hsi_depth: int, feats: int, device):
+    def __init__(self, params: Dict[str, torch.Tensor], hsi_depth: int, feats: int, device, bnorm: bool = True):
+        """bnorm=False (models.py:72,105-110): every block is Linear -> ReLU.  The same kernels run it: the GEMM stores
+        W x, the "BatchNorm apply" pass runs with scale = 1 and shift = the Linear bias, the backward apply pass with
+        gamma = invstd = 1, mean = 0 and zero reduction sums is exactly the ReLU backward, and the (now non-zero) bias
+        gradient is a column sum of its output."""
         self.P, self.D, self.F, self.dev = params, hsi_depth, feats, device
+        self.bnorm = bool(bnorm)
         # N-tile of the forward / dgrad GEMMs: 256-column tcgen05.mma tiles are tensor-pipe bound (128 cycles per MMA
         # against 96 of operand fetch) while 128-column ones sit on the shared-memory operand bandwidth; 1650 features
         # are 6.45 such tiles (7 with the ragged last one), measured 15 % faster than 13 tiles of 128
@@ -803,8 +808,15 @@ class SpectralEngine(_EngineBase):
         self.training_fwd = False
         self.pp = None                      # hyperpri_b200.parallel.PixelParallel: this rank holds a row strip of every image
         self._init_scaling(device)
-        names = [k for nm in self.BLOCKS for k in (nm + ".0.weight", nm + ".0.bias", nm + ".1.weight", nm + ".1.bias")]
+        per_block = (".0.weight", ".0.bias", ".1.weight", ".1.bias") if self.bnorm else (".0.weight", ".0.bias")
+        names = [nm + k for nm in self.BLOCKS for k in per_block]
         names += ["outc.weight", "outc.bias"]
+        if not self.bnorm:
+            self._ones = torch.ones(self.Fp, dtype=torch.float32, device=d)
+            self._zeros = _z((self.Fp,), d, torch.float32)
+            for L in self.L.values():
+                L.shift_nb = _z((self.Fp,), d, torch.float32)        # the Linear bias, padded: the "shift" of the apply pass
+                L.bias_key = None
         offs, total = {}, 0
         for k in names:
             offs[k] = total
@@ -822,6 +834,8 @@ class SpectralEngine(_EngineBase):
 
     def set_pixel_parallel(self, pp):
         """Shard every image's pixels over pp's ranks (see PixelParallel); None restores the single-GPU plan."""
+        if pp is not None and pp.world > 1 and not self.bnorm:
+            raise NotImplementedError("pixel-parallel SpectralUNET is built for bnorm=True (the configured model)")
         self.pp = pp if (pp is not None and pp.world > 1) else None
         self.ws = self.ws_key = None
 
@@ -882,6 +896,13 @@ class SpectralEngine(_EngineBase):
                     for half in (0, 1):   # dgrad operand rows follow the cat buffer: [0,F) and [Fp, Fp+F)
                         ops.pack(wc, G=1, R=F, T=1, Cc=F, sg=0, sr=1, st=0, sc=2 * F, src_offset=half * F,
                                  out=L.dgr_cat[half * Fp: half * Fp + F])
+        if not self.bnorm:
+            for nm, L in self.L.items():
+                b = P[nm + ".0.bias"]
+                key = (b.data_ptr(), b._version)
+                if L.bias_key != key:
+                    L.shift_nb[:F].copy_(b.detach())
+                    L.bias_key = key
         wo_p = P["outc.weight"]
         wo_key = (wo_p.data_ptr(), wo_p._version)
         if getattr(self, "_wo_key", None) != wo_key:        # padded copy of the head weights, refreshed when they change
@@ -934,6 +955,11 @@ class SpectralEngine(_EngineBase):
                     src = xin
                 raw = im["raw_" + nm]
                 scale, shift, smean, sinv = im["bn"][nm]
+                if not self.bnorm:
+                    ops.igemm_fwd(src, L.pp.fwd, F, 1, raw, Fp, x_c=(self.D if nm == "tail" else None),
+                                  block_n=self.bn_tile)
+                    ops.bn_relu_apply(raw, self._ones, L.shift_nb, dst, None, c=F)
+                    continue
                 if training and pp is not None:
                     # this rank's partial (sum, sum of squares) -> exact per-image statistics over all strips
                     ops.igemm_fwd(src, L.pp.fwd, F, 1, raw, Fp, stats=L.stats, x_c=(self.D if nm == "tail" else None),
@@ -1006,15 +1032,26 @@ class SpectralEngine(_EngineBase):
                 r_turn += 1
                 R = ws["R"][k]
                 self._join(r_busy.get(k))          # the weight gradient that last read this buffer has finished
-                if pp is not None:
+                if not self.bnorm:
+                    if head:                       # d(outc weight) half = sum_p dlogit * act: third column of the reduction
+                        ops.bn_relu_bwd_reduce(im["raw_" + nm], self._ones, L.shift_nb, self._zeros, self._ones, L.sums,
+                                               dy=dy, head_w=hw, dlogit=dl, c=F)
+                        part = L.sums[:F, 2].float() * inv
+                        dhw.copy_(part) if i == 0 else dhw.add_(part)
+                        L.sums.zero_()             # the apply pass must see zero sums: plain ReLU backward
+                    ops.bn_relu_bwd(im["raw_" + nm], self._ones, L.shift_nb, self._zeros, self._ones, self._ones, R, L.sums,
+                                    m_glob, dy=dy, head_w=hw, dlogit=dl if head else None, c=F, reduced=True)
+                    ops.colsum(R, self._grad(nm + ".0.bias", P[nm + ".0.bias"]), beta=acc_beta, scale=inv, c=F)
+                elif pp is not None:
                     ops.bn_relu_bwd_reduce(im["raw_" + nm], scale, shift, smean, sinv, L.sums, dy=dy, head_w=hw,
                                            dlogit=dl if head else None, c=F)
                     pp.all_reduce_(L.sums)
-                ops.bn_relu_bwd(im["raw_" + nm], scale, shift, smean, sinv, P[nm + ".1.weight"], R, L.sums, m_glob, dy=dy,
-                                head_w=hw, dlogit=dl if head else None,
-                                dgamma=self._grad(nm + ".1.weight", P[nm + ".1.weight"]),
-                                dbeta=self._grad(nm + ".1.bias", P[nm + ".1.bias"]), dhead_w=dhw, c=F,
-                                out_scale=inv_bn, out_beta=acc_beta, flag=self.overflow, reduced=pp is not None)
+                if self.bnorm:
+                    ops.bn_relu_bwd(im["raw_" + nm], scale, shift, smean, sinv, P[nm + ".1.weight"], R, L.sums, m_glob, dy=dy,
+                                    head_w=hw, dlogit=dl if head else None,
+                                    dgamma=self._grad(nm + ".1.weight", P[nm + ".1.weight"]),
+                                    dbeta=self._grad(nm + ".1.bias", P[nm + ".1.bias"]), dhead_w=dhw, c=F,
+                                    out_scale=inv_bn, out_beta=acc_beta, flag=self.overflow, reduced=pp is not None)
                 xg = src if src.dtype == GRAD else ops.convert16(src, ws["cvt"][..., :src.shape[-1]])
                 self._on_side(lambda xg=xg, R=R, L=L, nm=nm: ops.igemm_wgrad(
                     xg, R, 0, F, L.gw, x_c=(self.D if nm == "tail" else None), dy_c=F, block_n=self.wgrad_tile))

@@ -243,24 +243,26 @@ class SpectralUNET(_EngineNet):
         super().__init__()
         self.hsi_depth = self.n_channels = hsi_depth
         self.n_classes = n_classes
-        if not bnorm:
-            raise NotImplementedError("bnorm=False is not used by the reference factories and is not built")
+        self.bnorm = bool(bnorm)
         if n_classes != 1:
             raise NotImplementedError("the B200 head kernel is built for n_classes=1 (every reference config)")
         f = bn_feats
         self.layer_feats = [f] * 5
-        self.tail = self._basic_module(hsi_depth, f)
-        self.down1, self.down2 = self._basic_module(f, f), self._basic_module(f, f)
-        self.down3, self.down4 = self._basic_module(f, f), self._basic_module(f, f)
-        self.up1 = self._basic_module(f, f)
-        self.up2, self.up3, self.up4 = (self._basic_module(2 * f, f) for _ in range(3))
+        bn = self.bnorm
+        self.tail = self._basic_module(hsi_depth, f, bn)
+        self.down1, self.down2 = self._basic_module(f, f, bn), self._basic_module(f, f, bn)
+        self.down3, self.down4 = self._basic_module(f, f, bn), self._basic_module(f, f, bn)
+        self.up1 = self._basic_module(f, f, bn)
+        self.up2, self.up3, self.up4 = (self._basic_module(2 * f, f, bn) for _ in range(3))
         self.outc = nn.Linear(2 * f, n_classes)
 
     def _basic_module(self, in_feats, out_feats, bn=True):
+        if not bn:                                   # models.py:105-110
+            return nn.Sequential(nn.Linear(in_feats, out_feats), nn.ReLU())
         return nn.Sequential(nn.Linear(in_feats, out_feats), nn.BatchNorm1d(out_feats), nn.ReLU())
 
     def _make_engine(self, device):
-        eng = _engine.SpectralEngine(self._tensor_table(), self.hsi_depth, self.layer_feats[0], device)
+        eng = _engine.SpectralEngine(self._tensor_table(), self.hsi_depth, self.layer_feats[0], device, bnorm=self.bnorm)
         if self.__dict__.get("_pp") is not None:
             eng.set_pixel_parallel(self.__dict__["_pp"])
         return eng

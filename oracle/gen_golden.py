@@ -29,6 +29,8 @@ CASES = {
     "cubenet_1x238x48x72": dict(model="CubeNET", n=1, h=48, w=72, bands=238, seed=2),
     "spectral32_2x238x6x10": dict(model="SpectralUNET", n=2, h=6, w=10, bands=238, seed=3, feats=32),
     "spectral1650_2x238x4x5": dict(model="SpectralUNET", n=2, h=4, w=5, bands=238, seed=4, feats=1650),
+    # bnorm=False (models.py:72,105-110): Linear -> ReLU blocks
+    "spectral32_nobn_2x238x6x10": dict(model="SpectralUNET", n=2, h=6, w=10, bands=238, seed=11, feats=32, bnorm=False),
     # use_attention=True (model_parts.py:84-85): skip * up instead of cat([skip, up])
     "unet_att_2x3x32x40": dict(model="UNET", n=2, h=32, w=40, bands=3, seed=5, attention=True),
     "cubenet_att_2x238x34x42": dict(model="CubeNET", n=2, h=34, w=42, bands=238, seed=6, attention=True),
@@ -53,8 +55,8 @@ def build(case):
         net = CubeNET(case["bands"], 1, first_depth=fd, bilinear=bil, use_attention=att)
         schema = O.unet_schema(1, 1, "cube", hsi_depth=case["bands"], attention=att, first_depth=fd, bilinear=bil)
     else:
-        net = SpectralUNET(case["bands"], 1, bn_feats=case["feats"])
-        schema = O.spectral_schema(case["bands"], 1, case["feats"])
+        net = SpectralUNET(case["bands"], 1, bn_feats=case["feats"], bnorm=case.get("bnorm", True))
+        schema = O.spectral_schema(case["bands"], 1, case["feats"], bnorm=case.get("bnorm", True))
     ref_sd = net.state_dict()
     assert {k: tuple(v.shape) for k, v in ref_sd.items()} == {k: tuple(s) for k, s in schema.items()}, \
         "schema drifted from the reference state_dict"

@@ -123,7 +123,8 @@ def unet_schema(n_channels: int, n_classes: int = 1, first: str = "unet", hsi_de
     return s
 
 
-def spectral_schema(hsi_depth: int, n_classes: int = 1, bn_feats: int = 16):
+def spectral_schema(hsi_depth: int, n_classes: int = 1, bn_feats: int = 16, bnorm: bool = True):
+    """bnorm=False: every block is Linear -> ReLU (models.py:105-110), no BatchNorm1d entries."""
     s: Dict[str, Tuple[int, ...]] = {}
     f = bn_feats
     dims = {"tail": (hsi_depth, f), "down1": (f, f), "down2": (f, f), "down3": (f, f), "down4": (f, f),
@@ -131,6 +132,8 @@ def spectral_schema(hsi_depth: int, n_classes: int = 1, bn_feats: int = 16):
     for nm, (i, o) in dims.items():
         s[f"{nm}.0.weight"] = (o, i)
         s[f"{nm}.0.bias"] = (o,)
+        if not bnorm:
+            continue
         for q in ("weight", "bias", "running_mean", "running_var"):
             s[f"{nm}.1.{q}"] = (o,)
         s[f"{nm}.1.num_batches_tracked"] = ()
@@ -327,6 +330,8 @@ def spectralunet_forward(x, sd, training=True, stats_out=None):
     def blk(t, nm):
         so = {} if stats_out is not None else None
         t = q(F.linear(t, q(sd[nm + ".0.weight"]), None)) + sd[nm + ".0.bias"]
+        if nm + ".1.weight" not in sd:            # bnorm=False: Linear -> ReLU (models.py:105-110)
+            return q(torch.relu(t))
         t = q(torch.relu(batch_norm(t, cur, nm + ".1", training, so, ch_axis=1)))
         if so:
             cur.update(so)        # running stats advance once per image
@@ -378,10 +383,13 @@ def spectralunet_forward_streaming(x, sd, chunk: int = 16384):
                 yd = y.double()
                 s1 += yd.sum(0)
                 s2 += (yd * yd).sum(0)
-            mean = s1 / m
-            var = (s2 / m - mean * mean).clamp_min(0)
-            scale = (sd[nm + ".1.weight"].double() / torch.sqrt(var + BN_EPS)).float()
-            shift = (sd[nm + ".1.bias"].double() - mean * scale.double()).float()
+            if nm + ".1.weight" not in sd:        # bnorm=False
+                scale, shift = torch.ones(w.shape[0]), torch.zeros(w.shape[0])
+            else:
+                mean = s1 / m
+                var = (s2 / m - mean * mean).clamp_min(0)
+                scale = (sd[nm + ".1.weight"].double() / torch.sqrt(var + BN_EPS)).float()
+                shift = (sd[nm + ".1.bias"].double() - mean * scale.double()).float()
             for i in range(0, m, chunk):
                 pre[i:i + chunk] = torch.relu(pre[i:i + chunk] * scale + shift)
             return pre

@@ -43,6 +43,8 @@ def test_missing_library_fails_loudly(monkeypatch):
     (lambda: mdl.UNet(3, 1, bilinear=False), lambda: O.unet_schema(3, 1, "unet"), 31043521),
     (lambda: mdl.CubeNET(238, 1, bilinear=False), lambda: O.unet_schema(1, 1, "cube", 238), 31178881),
     (lambda: mdl.SpectralUNET(238, 1, bn_feats=1650), lambda: O.spectral_schema(238, 1, 1650), 30388051),
+    (lambda: mdl.SpectralUNET(238, 1, bn_feats=32, bnorm=False), lambda: O.spectral_schema(238, 1, 32, bnorm=False),
+     32 * 238 + 32 + 5 * (32 * 32 + 32) + 3 * (64 * 32 + 32) + 65),
 ])
 def test_state_dict_schema_matches_reference(net, schema, nparam):
     n, s = net(), schema()

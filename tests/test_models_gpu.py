@@ -33,7 +33,7 @@ def _deterministic_statistics():
     ops.set_deterministic(False)
 
 
-def build(model, bands, feats=1650, seed=0, att=False, fd=64, bil=False):
+def build(model, bands, feats=1650, seed=0, att=False, fd=64, bil=False, bnorm=True):
     if model == "UNET":
         net = UNet(bands, 1, bilinear=bil, use_attention=att)
         schema = O.unet_schema(bands, 1, "unet", attention=att, bilinear=bil)
@@ -41,7 +41,7 @@ def build(model, bands, feats=1650, seed=0, att=False, fd=64, bil=False):
         net = CubeNET(bands, 1, first_depth=fd, bilinear=bil, use_attention=att)
         schema = O.unet_schema(1, 1, "cube", hsi_depth=bands, attention=att, first_depth=fd, bilinear=bil)
     else:
-        net, schema = SpectralUNET(bands, 1, bn_feats=feats), O.spectral_schema(bands, 1, feats)
+        net, schema = SpectralUNET(bands, 1, bn_feats=feats, bnorm=bnorm), O.spectral_schema(bands, 1, feats, bnorm=bnorm)
     sd = O.synth_state_dict(schema, seed)
     net.load_state_dict(sd)
     return net.cuda(), sd
@@ -113,6 +113,7 @@ def test_train_step_parity_vs_oracle(model, n, bands, h, w, feats):
     ("unet_2x3x32x40", "UNET", 2, 3, 32, 40, 0, 0), ("cubenet_2x238x32x40", "CubeNET", 2, 238, 32, 40, 1, 0),
     ("cubenet_1x238x48x72", "CubeNET", 1, 238, 48, 72, 2, 0), ("spectral32_2x238x6x10", "SpectralUNET", 2, 238, 6, 10, 3, 32),
     ("spectral1650_2x238x4x5", "SpectralUNET", 2, 238, 4, 5, 4, 1650),
+    ("spectral32_nobn_2x238x6x10", "SpectralUNET", 2, 238, 6, 10, 11, 32),
     ("unet_att_2x3x32x40", "UNET", 2, 3, 32, 40, 5, 0), ("cubenet_att_2x238x34x42", "CubeNET", 2, 238, 34, 42, 6, 0),
     ("cubenet_fd32_2x238x32x40", "CubeNET", 2, 238, 32, 40, 7, 0), ("cubenet_fd128_att_1x238x34x42", "CubeNET", 1, 238, 34, 42, 8, 0),
     ("unet_bil_2x3x34x42", "UNET", 2, 3, 34, 42, 9, 0), ("cubenet_bil_att_2x238x32x40", "CubeNET", 2, 238, 32, 40, 10, 0)])
@@ -124,7 +125,7 @@ def test_against_reference_golden(name, model, n, bands, h, w, seed, feats, mode
     as few as 8 samples per channel (measured 1.4e-2 .. 2.0e-2; 7.2e-3 at most for every other case)."""
     g = np.load(os.path.join(GOLD, name + ".npz"))
     fd = int(name.split("_fd")[1].split("_")[0]) if "_fd" in name else 64
-    net, _ = build(model, bands, feats, seed, att="_att_" in name, fd=fd, bil="_bil_" in name)
+    net, _ = build(model, bands, feats, seed, att="_att_" in name, fd=fd, bil="_bil_" in name, bnorm="_nobn_" not in name)
     x = O.synth_cube(seed, n, bands, h, w)
     xin = x[:, None] if model == "CubeNET" else x
     mask = O.synth_mask(seed, n, h, w)
@@ -534,3 +535,28 @@ def test_deterministic_statistics_mode_is_bit_reproducible(model, bands, h, w, f
     with torch.no_grad():
         plain = net(xin)
     assert (plain - outs[0]).abs().max().item() <= 5e-3 * outs[0].abs().max().item()
+
+
+@pytest.mark.parametrize("feats,h,w", [(96, 24, 40), (1650, 16, 33)])
+def test_spectralunet_without_batchnorm_train_step_parity_vs_oracle(feats, h, w):
+    """SpectralUNET(bnorm=False) (models.py:72,105-110): Linear -> ReLU blocks through the same kernels (apply pass with
+    scale 1 / shift = bias; backward apply with zero sums = ReLU backward; bias gradients by column sums)."""
+    net, sd = build("SpectralUNET", 238, feats, bnorm=False)
+    assert not any(".1." in k for k in sd) and len(sd) == 20
+    x = O.synth_cube(5, 2, 238, h, w)
+    mask = O.synth_mask(5, 2, h, w)
+    torch.set_num_threads(os.cpu_count())
+    ol, oloss, og, _ = O.forward_backward("SpectralUNET", x, mask, sd, training=True)
+    lg, loss = run_ours(net, x, mask)
+    assert (lg - ol).abs().max().item() <= 1e-2 * ol.abs().max().item()
+    assert abs(loss - oloss.item()) < 2e-4
+    fo, fg = [], []
+    for k, p in net.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all() and p.grad.shape == og[k].shape, k
+        fo.append(og[k].flatten()); fg.append(p.grad.cpu().flatten())
+        if og[k].norm() > 0:
+            assert cos(p.grad.cpu(), og[k]) > 0.98, k            # no BatchNorm: smooth, well-conditioned gradients
+    assert cos(torch.cat(fg), torch.cat(fo)) > 0.995
+    # second step accumulates nothing stale (bias gradients are written with beta = 0 for the first image)
+    lg2, loss2 = run_ours(net, x, mask)
+    assert abs(loss2 - loss) < 1e-6

@@ -16,6 +16,7 @@ CASES = {
     "cubenet_1x238x48x72": dict(model="CubeNET", n=1, h=48, w=72, bands=238, seed=2),
     "spectral32_2x238x6x10": dict(model="SpectralUNET", n=2, h=6, w=10, bands=238, seed=3, feats=32),
     "spectral1650_2x238x4x5": dict(model="SpectralUNET", n=2, h=4, w=5, bands=238, seed=4, feats=1650),
+    "spectral32_nobn_2x238x6x10": dict(model="SpectralUNET", n=2, h=6, w=10, bands=238, seed=11, feats=32, bnorm=False),
     "unet_att_2x3x32x40": dict(model="UNET", n=2, h=32, w=40, bands=3, seed=5, attention=True),
     "cubenet_att_2x238x34x42": dict(model="CubeNET", n=2, h=34, w=42, bands=238, seed=6, attention=True),
     "cubenet_fd32_2x238x32x40": dict(model="CubeNET", n=2, h=32, w=40, bands=238, seed=7, first_depth=32),
@@ -33,7 +34,7 @@ def _inputs(c):
         schema = O.unet_schema(1, 1, "cube", hsi_depth=c["bands"], attention=att, first_depth=c.get("first_depth", 64),
                                bilinear=bil)
     else:
-        schema = O.spectral_schema(c["bands"], 1, c["feats"])
+        schema = O.spectral_schema(c["bands"], 1, c["feats"], bnorm=c.get("bnorm", True))
     sd = O.synth_state_dict(schema, c["seed"])
     x = O.synth_cube(c["seed"], c["n"], c["bands"], c["h"], c["w"])
     if c["model"] == "CubeNET":
@@ -101,7 +102,7 @@ def test_emulation_is_off_by_default_and_close():
     assert 0 < (l1 - l0).abs().max().item() < 5e-2 * l0.abs().max().item()
 
 
-@pytest.mark.parametrize("name", ["spectral32_2x238x6x10", "spectral1650_2x238x4x5"])
+@pytest.mark.parametrize("name", ["spectral32_2x238x6x10", "spectral1650_2x238x4x5", "spectral32_nobn_2x238x6x10"])
 def test_streaming_spectral_oracle_matches_reference_golden(name):
     """The chunk-wise two-pass SpectralUNET forward (fp64 statistics, no autograd graph; used for the full-width
     608 x 700 GPU parity check) against the REFERENCE module's train-mode logits, with a chunk size that does not
