@@ -720,7 +720,7 @@ bn_relu_apply_k(V x, const float* __restrict__ scale, const float* __restrict__ 
 }
 
 // "flat" fast path (no pooled output, pixel-dense views): a thread keeps one channel group (its scale / shift stay in
-// registers) and walks pixels with four 16-byte loads in flight; no index arithmetic per element.
+// registers) and walks pixels with eight 16-byte loads in flight; no index arithmetic per element.
 template <int DT>
 __global__ void __launch_bounds__(256)
 bn_relu_apply_flat_k(const uint16_t* __restrict__ x, long long sx, int xdt, uint16_t* __restrict__ y, long long sy,
@@ -734,16 +734,16 @@ bn_relu_apply_flat_k(const uint16_t* __restrict__ x, long long sx, int xdt, uint
   ld8v(scale, c0, C, sc);
   ld8v(shift, c0, C, sh);
   const long long stride = (long long)gridDim.x * slots;
-  for (long long p0 = (long long)blockIdx.x * slots + slot; p0 < npix; p0 += 4 * stride) {
-    uint4 xr[4];
+  for (long long p0 = (long long)blockIdx.x * slots + slot; p0 < npix; p0 += 8 * stride) {
+    uint4 xr[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       const long long pp = p0 + u * stride;
       xr[u] = make_uint4(0, 0, 0, 0);
       if (pp < npix) xr[u] = __ldg(reinterpret_cast<const uint4*>(x + pp * sx + c0));
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       const long long pp = p0 + u * stride;
       if (pp >= npix) break;
       float f[8];
@@ -988,6 +988,9 @@ __device__ __forceinline__ void flat_dz(const FlatIn& a, const uint4& xr, const 
   }
 }
 
+// pixels in flight per thread in the strided flat kernels: 8 (4 in round 1: 70 % of DRAM peak), 4 with the OutConv head
+// terms, whose extra constants would spill
+template <bool HEAD> struct FlatUnroll { static constexpr int v = HEAD ? 4 : 8; };
 template <bool HEAD, int DT>
 __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_flat_k(FlatIn a, double* sums, int slots, int CG) {
   extern __shared__ float red[];                 // [slots][CG*8][3]
@@ -1002,11 +1005,11 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_flat_k(FlatIn a, double*
 #pragma unroll
     for (int k = 0; k < 8; ++k) { s1[k] = 0.f; s2[k] = 0.f; s3[k] = 0.f; }
     const long long stride = (long long)gridDim.x * slots;
-    for (long long p0 = (long long)blockIdx.x * slots + slot; p0 < a.npix; p0 += 4 * stride) {
-      uint4 xr[4], dr[4];
-      float dl[4];
+    for (long long p0 = (long long)blockIdx.x * slots + slot; p0 < a.npix; p0 += FlatUnroll<HEAD>::v * stride) {
+      uint4 xr[FlatUnroll<HEAD>::v], dr[FlatUnroll<HEAD>::v];
+      float dl[FlatUnroll<HEAD>::v];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < FlatUnroll<HEAD>::v; ++u) {
         const long long pp = p0 + u * stride;
         xr[u] = make_uint4(0, 0, 0, 0); dr[u] = make_uint4(0, 0, 0, 0); dl[u] = 0.f;
         if (pp < a.npix) {
@@ -1016,7 +1019,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_flat_k(FlatIn a, double*
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < FlatUnroll<HEAD>::v; ++u) {
         if (p0 + u * stride >= a.npix) break;
         float xv[8], z[8], dz[8];
         flat_dz<HEAD, DT>(a, xr[u], dr[u], dl[u], sc, sh, hw, xv, z, dz);
@@ -1074,11 +1077,11 @@ bn_bwd_apply_flat_k(FlatIn a, const float* __restrict__ gamma, const double* __r
     cc[k] = -g * is * m1 - cb[k] * mu;
   }
   const long long stride = (long long)gridDim.x * slots;
-  for (long long p0 = (long long)blockIdx.x * slots + slot; p0 < a.npix; p0 += 4 * stride) {
-    uint4 xr[4], dr[4];
-    float dl[4];
+  for (long long p0 = (long long)blockIdx.x * slots + slot; p0 < a.npix; p0 += FlatUnroll<HEAD>::v * stride) {
+    uint4 xr[FlatUnroll<HEAD>::v], dr[FlatUnroll<HEAD>::v];
+    float dl[FlatUnroll<HEAD>::v];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < FlatUnroll<HEAD>::v; ++u) {
       const long long pp = p0 + u * stride;
       xr[u] = make_uint4(0, 0, 0, 0); dr[u] = make_uint4(0, 0, 0, 0); dl[u] = 0.f;
       if (pp < a.npix) {
@@ -1088,7 +1091,7 @@ bn_bwd_apply_flat_k(FlatIn a, const float* __restrict__ gamma, const double* __r
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < FlatUnroll<HEAD>::v; ++u) {
       const long long pp = p0 + u * stride;
       if (pp >= a.npix) break;
       float xv[8], z[8], dz[8], o[8];
