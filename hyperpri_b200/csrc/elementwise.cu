@@ -1396,6 +1396,7 @@ head_fwd_dense_k(const uint16_t* __restrict__ x, long long sp, int dt, int C, lo
       float acc = 0.f;
       if (pp < npix) {
         const uint16_t* px = x + pp * sp;
+#pragma unroll 4                                   // four independent 16-byte loads in flight per lane (was one)
         for (int cg = sub; cg < CG; cg += LPP) {
           float f[8], wv[8];
           unpack8(__ldg(reinterpret_cast<const uint4*>(px + cg * 8)), f, dt);
