@@ -281,3 +281,40 @@ def test_engine_channel_plan_matches_parameters(kind, kw):
     b = eng.bucket_bounds
     assert len(b) == 9 and b[0][0] == 0 and b[-1][1] == eng.arena.numel()
     assert all(b[i][1] == b[i + 1][0] and b[i][1] > b[i][0] for i in range(8))
+
+
+def test_ctypes_structs_match_the_c_header_layout(tmp_path):
+    """The ctypes mirrors in hyperpri_b200/_lib.py against the structs of include/hyperpri_b200.h as gcc lays them out:
+    size and the offset of every field (an ABI drift between the header and the Python binding would corrupt launches
+    silently)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    structs = {"hpri_view_t": (_lib.View, ["ptr", "n", "h", "w", "c", "pix_stride", "row_stride", "img_stride", "dtype"]),
+               "hpri_bn_fin_t": (_lib.BnFin, ["gamma", "beta", "conv_bias", "running_mean", "running_var", "num_batches_tracked",
+                                              "scale", "shift", "save_mean", "save_invstd", "counter", "count", "momentum",
+                                              "eps", "partials"]),
+               "hpri_bn_bwd_t": (_lib.BnBwd, ["x", "scale", "shift", "save_mean", "save_invstd", "sums"]),
+               "hpri_conv3x3_job_t": (_lib.Conv3x3Job, ["w", "dst_fwd", "dst_dgrad", "grad_packed", "grad_dst", "cout", "cin",
+                                                        "fwd_dtype", "dgrad_dtype", "tile0", "kind"]),
+               "hpri_adam_job_t": (_lib.AdamJob, ["param", "grad", "exp_avg", "exp_avg_sq", "numel", "block0"])}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "hyperpri_b200.h"', 'int main(void) {']
+    for cname, (_, fields) in structs.items():
+        lines.append(f'  printf("{cname} size %zu\\n", sizeof({cname}));')
+        for f in fields:
+            lines.append(f'  printf("{cname} {f} %zu\\n", offsetof({cname}, {f}));')
+    lines += ['  return 0;', '}']
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    want = {}
+    for line in out.splitlines():
+        cname, key, val = line.split()
+        want[(cname, key)] = int(val)
+    for cname, (cls, fields) in structs.items():
+        assert ctypes.sizeof(cls) == want[(cname, "size")], cname
+        for f in fields:
+            assert getattr(cls, f).offset == want[(cname, f)], (cname, f)
