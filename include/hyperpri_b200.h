@@ -7,8 +7,8 @@
  *   - enqueue work on that stream and return immediately (no allocation, no host sync),
  *   - return HPRI_OK (0) or a negative HPRI_ERR_* code; they never fall back to a CPU path.
  *
- * Activations are NHWC bf16, described by hpri_view_t so that channel sub-ranges of a concat
- * buffer and cropped windows are expressed with strides instead of copies.
+ * Activations are NHWC 16-bit (fp16 in the engine; bf16 is accepted), described by hpri_view_t so that channel
+ * sub-ranges of a concat buffer and cropped windows are expressed with strides instead of copies.
  */
 #ifndef HYPERPRI_B200_H
 #define HYPERPRI_B200_H
