@@ -48,7 +48,7 @@ struct IgemmArgs {
   int dw_ld, splits, total_chunks;
   int a_dt, b_dt, out_dt; // element formats (DT_BF16 / DT_F16) of the A, B operands and the fwd output
   // ---- halo kernel pipeline shape (runtime: depends on the tile aspect)
-  int stages, a_bytes;
+  int stages, a_bytes, a_stages;
   // ---- fused train-mode BatchNorm finalisation (has_fin): done by the last CTA to flush its statistics
   int has_fin;
   hpri_bn_fin_t fin;
@@ -613,7 +613,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ C
 // Shared memory: [staging 2 x 16 KB][barriers][stats][A ring: 2 x a_bytes][B ring: p.stages x 3 weight tiles].
 // =====================================================================================
 constexpr int kHaloStatCh = 1024;
-constexpr int kHaloAStages = 2;
+constexpr int kHaloAStages = 2;        // default depth of the halo-block ring
+constexpr int kHaloMaxAStages = 3;     // barrier slots reserved (IgemmArgs::a_stages picks 2 or 3 per launch)
 constexpr int kHaloMaxBStages = 12;     // weight ring slots: ONE tap tile each (fine-grained: more bytes in flight)
 
 template <int BLOCK_N>
@@ -622,7 +623,7 @@ struct HaloSmem {
   static constexpr int B_STAGE = B_TILE;
   static constexpr int STAGING_OFF = 0;
   static constexpr int BAR_OFF = 2 * kStageTile;       // a_full[2], a_empty[2], b_full[12], b_empty[12], tmem_full[2], tmem_empty[2], x_full[2]
-  static constexpr int TMEMPTR_OFF = BAR_OFF + (2 * kHaloAStages + 2 * kHaloMaxBStages + 6) * 8;
+  static constexpr int TMEMPTR_OFF = BAR_OFF + (2 * kHaloMaxAStages + 2 * kHaloMaxBStages + 6) * 8;
   static constexpr int SSUM_OFF = TMEMPTR_OFF + 8;
   static constexpr int PIPE_OFF = (SSUM_OFF + 2 * kHaloStatCh * 4 + 1023) / 1024 * 1024;
   static constexpr int BUDGET = 227 * 1024 - 1024;                       // after manual 1024 B alignment
@@ -660,8 +661,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
-  uint64_t* a_empty = a_full + kHaloAStages;
-  uint64_t* b_full = a_empty + kHaloAStages;
+  uint64_t* a_empty = a_full + kHaloMaxAStages;
+  uint64_t* b_full = a_empty + kHaloMaxAStages;
+  const int AST = p.a_stages;                 // halo-block ring depth of this launch (2 or 3)
   uint64_t* b_empty = b_full + kHaloMaxBStages;
   uint64_t* tmem_full = b_empty + kHaloMaxBStages;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -692,7 +694,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     tma_prefetch_desc(&tmO);
-    for (int s = 0; s < kHaloAStages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < kHaloMaxAStages; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < BST; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
     mbar_init(&tmem_full[0], 1);
     mbar_init(&tmem_full[1], 1);
@@ -719,9 +721,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 0) {
     // =========================== TMA producer (whole warp converged) ===========================
     {
-      const uint32_t a_ring_u = uniform_u32(smem_u32(a_ring)), b_ring_u = a_ring_u + kHaloAStages * a_bytes;
-      const uint32_t afull_u = uniform_u32(smem_u32(a_full)), aempty_u = afull_u + kHaloAStages * 8;
-      const uint32_t bfull_u = aempty_u + kHaloAStages * 8, bempty_u = bfull_u + kHaloMaxBStages * 8;
+      const uint32_t a_ring_u = uniform_u32(smem_u32(a_ring)), b_ring_u = a_ring_u + AST * a_bytes;
+      const uint32_t afull_u = uniform_u32(smem_u32(a_full)), aempty_u = afull_u + kHaloMaxAStages * 8;
+      const uint32_t bfull_u = aempty_u + kHaloMaxAStages * 8, bempty_u = bfull_u + kHaloMaxBStages * 8;
       // loads of both CTAs complete on the LEADER's full barriers, which expect the bytes of both
       const uint32_t afull_l = PAIR ? mapa_u32(afull_u, 0) : afull_u, bfull_l = PAIR ? mapa_u32(bfull_u, 0) : bfull_u;
       const bool expect = !PAIR || crank == 0;
@@ -738,7 +740,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (expect) mbar_arrive_expect_tx_w(afull_u + sa * 8, PAIR ? 2 * a_tx : a_tx);
           if (PAIR) tma_load_4d_w2(a_ring_u + sa * a_bytes, &tmA, afull_l + sa * 8, cc * 64, w0 - 1, h0 - 1, img);
           else tma_load_4d_w(a_ring_u + sa * a_bytes, &tmA, afull_u + sa * 8, cc * 64, w0 - 1, h0 - 1, img);
-          if (++sa == kHaloAStages) { sa = 0; pha ^= 1; }
+          if (++sa == static_cast<uint32_t>(AST)) { sa = 0; pha ^= 1; }
 #pragma unroll 1
           for (int tap = 0; tap < 9; ++tap) {
             mbar_wait_w(bempty_u + sb * 8, phb ^ 1);
@@ -751,9 +753,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
       if (PAIR) {      // tail: every multicast commit aimed at this CTA's empty barriers has landed before it may exit
-        for (int i = 0; i < kHaloAStages; ++i) {
+        for (int i = 0; i < AST; ++i) {
           mbar_wait_w(aempty_u + sa * 8, pha ^ 1);
-          if (++sa == kHaloAStages) { sa = 0; pha ^= 1; }
+          if (++sa == static_cast<uint32_t>(AST)) { sa = 0; pha ^= 1; }
         }
         for (int i = 0; i < BST; ++i) {
           mbar_wait_w(bempty_u + sb * 8, phb ^ 1);
@@ -766,9 +768,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (!PAIR || crank == 0) {
       const uint32_t idesc = make_idesc_16(PAIR ? 256 : 128, BLOCK_N, 0, 0, p.a_dt, p.b_dt);
       const uint32_t sbo = static_cast<uint32_t>(geo.wb * 128);
-      const uint32_t a_ring_u = uniform_u32(smem_u32(a_ring)), b_ring_u = a_ring_u + kHaloAStages * a_bytes;
-      const uint32_t afull_u = uniform_u32(smem_u32(a_full)), aempty_u = afull_u + kHaloAStages * 8;
-      const uint32_t bfull_u = aempty_u + kHaloAStages * 8, bempty_u = bfull_u + kHaloMaxBStages * 8;
+      const uint32_t a_ring_u = uniform_u32(smem_u32(a_ring)), b_ring_u = a_ring_u + AST * a_bytes;
+      const uint32_t afull_u = uniform_u32(smem_u32(a_full)), aempty_u = afull_u + kHaloMaxAStages * 8;
+      const uint32_t bfull_u = aempty_u + kHaloMaxAStages * 8, bempty_u = bfull_u + kHaloMaxBStages * 8;
       const uint32_t tfull_u = bempty_u + kHaloMaxBStages * 8, tempty_u = tfull_u + 16;
       const uint32_t tmem_u = uniform_u32(tmem_base);
       // descriptor offsets (16-byte units) of the two halves' first pixel inside the halo block
@@ -815,7 +817,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #undef HPRI_TAP
           }
           halo_commit<PAIR>(aempty_u + sa * 8);   // the halo block is free once all nine taps have read it
-          if (++sa == kHaloAStages) { sa = 0; pha ^= 1; }
+          if (++sa == static_cast<uint32_t>(AST)) { sa = 0; pha ^= 1; }
         }
         halo_commit<PAIR>(tfull_u + as * 8);
       }
@@ -1372,7 +1374,7 @@ static int launch_halo_t(const CUtensorMap& ma, const CUtensorMap& mb, const CUt
   const long long streams = PAIR ? sm_count() / 2 : sm_count();
   long long grid = (tiles < streams ? tiles : streams) * (PAIR ? 2 : 1);
   if (grid <= 0) return HPRI_ERR_ARG;
-  const size_t smem = (size_t)L::PIPE_OFF + (size_t)kHaloAStages * args.a_bytes +
+  const size_t smem = (size_t)L::PIPE_OFF + (size_t)args.a_stages * args.a_bytes +
                       (size_t)args.stages * (PAIR ? L::B_STAGE / 2 : L::B_STAGE) + (args.bw_sums ? 2 * kStageTile : 0) + 1024;
   return launch_ex(kern, grid, smem, stream, PAIR, ma, mb, mo, mx, args, geo) == cudaSuccess ? HPRI_OK : HPRI_ERR_CUDA;
 }
@@ -1397,6 +1399,15 @@ static int conv_algo_override() {          // env HPRI_CONV_ALGO seeds it; hpri_
     g_conv_algo = e ? atoi(e) : -1;
   }
   return g_conv_algo;
+}
+
+static int g_halo_a_stages = -1;           // depth of the halo-block ring: 2 (default) or 3; env HPRI_HALO_A_STAGES
+static int halo_a_stages_override() {
+  if (g_halo_a_stages < 0) {
+    const char* e = getenv("HPRI_HALO_A_STAGES");
+    g_halo_a_stages = (e && atoi(e) == 3) ? 3 : 2;
+  }
+  return g_halo_a_stages;
 }
 
 static int g_wgrad_algo = -2;              // -1 heuristic, 0 generic kernel only
@@ -1426,6 +1437,12 @@ extern "C" int hpri_conv3x3_halo_ok(int h, int w, int w_rows) {
 extern "C" int hpri_set_conv_algo(int algo) {
   if (algo < -1 || algo > 2) return HPRI_ERR_ARG;
   g_conv_algo = algo;
+  return HPRI_OK;
+}
+
+extern "C" int hpri_set_halo_a_stages(int stages) {
+  if (stages != 2 && stages != 3) return HPRI_ERR_ARG;
+  g_halo_a_stages = stages;
   return HPRI_OK;
 }
 
@@ -1488,12 +1505,17 @@ extern "C" int hpri_igemm_fwd(const hpri_view_t* x, const void* wpack, int w_dty
     // pairs (the MMA warp then waits for the slower of two epilogues), so they stay on single CTAs.
     const bool pair = ov == 2 || (ov != 1 && !(bw && hbn == 64));
     const int b_slot = hbn * 128 / (pair ? 2 : 1);
-    int stages = ((hbn == 64 ? HaloSmem<64>::BUDGET - HaloSmem<64>::PIPE_OFF : HaloSmem<128>::BUDGET - HaloSmem<128>::PIPE_OFF) -
-                  kHaloAStages * a_bytes - extra) / b_slot;
+    const int pipe_budget = hbn == 64 ? HaloSmem<64>::BUDGET - HaloSmem<64>::PIPE_OFF : HaloSmem<128>::BUDGET - HaloSmem<128>::PIPE_OFF;
+    int a_stages = kHaloAStages;
+    int stages = (pipe_budget - a_stages * a_bytes - extra) / b_slot;
+    if (halo_a_stages_override() == 3 && (pipe_budget - 3 * a_bytes - extra) / b_slot >= 4) {   // a third halo block if >= 4 weight slots remain
+      a_stages = 3;
+      stages = (pipe_budget - 3 * a_bytes - extra) / b_slot;
+    }
     if (stages > kHaloMaxBStages) stages = kHaloMaxBStages;
     if (stats_ok && stages >= 2 && (ov >= 1 || (ov < 0 && waste <= 1.0))) {
       set_tile(a, hth, htw);
-      a.stages = stages; a.a_bytes = a_bytes;
+      a.stages = stages; a.a_bytes = a_bytes; a.a_stages = a_stages;
       CUtensorMap mx{};
       if (bw) {
         if (stats || !bw->x || !bw->scale || !bw->shift || !bw->save_mean || !bw->save_invstd || !bw->sums) return HPRI_ERR_ARG;
@@ -1506,7 +1528,7 @@ extern "C" int hpri_igemm_fwd(const hpri_view_t* x, const void* wpack, int w_dty
         if ((rc = map_nhwc(&mx, xv, 16, 8)) != HPRI_OK) return rc;
         a.bw_scale = bw->scale; a.bw_shift = bw->shift; a.bw_mean = bw->save_mean; a.bw_invstd = bw->save_invstd;
         a.bw_sums = bw->sums;
-        a.xstage_off = (hbn == 64 ? HaloSmem<64>::PIPE_OFF : HaloSmem<128>::PIPE_OFF) + kHaloAStages * a_bytes + stages * b_slot;
+        a.xstage_off = (hbn == 64 ? HaloSmem<64>::PIPE_OFF : HaloSmem<128>::PIPE_OFF) + a_stages * a_bytes + stages * b_slot;
       }
       HaloGeom geo{};
       geo.wb = htw + 2;

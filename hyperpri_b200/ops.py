@@ -286,6 +286,11 @@ def set_reverse_elementwise(on: bool):
     check(_lib.lib().hpri_set_reverse_elementwise(int(bool(on))), "hpri_set_reverse_elementwise")
 
 
+def set_halo_a_stages(stages: int):
+    """Depth of the 3x3 halo kernel's halo-block ring: 2 (default) or 3."""
+    check(_lib.lib().hpri_set_halo_a_stages(int(stages)), "hpri_set_halo_a_stages")
+
+
 def set_sm_reserve(sms: int):
     """Keep `sms` SMs out of the persistent tensor-core grids (room for concurrently running NCCL CTAs)."""
     check(_lib.lib().hpri_set_sm_reserve(int(sms)), "hpri_set_sm_reserve")

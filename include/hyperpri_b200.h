@@ -99,6 +99,9 @@ int hpri_set_wgrad_algo(int algo);
 /* Leave `sms` streaming multiprocessors out of the persistent tcgen05 grids (0 = use every SM): room for kernels that
  * run concurrently with them, i.e. NCCL's all-reduce CTAs in the data-parallel backward.  Seeded by HPRI_SM_RESERVE. */
 int hpri_set_sm_reserve(int sms);
+/* Depth of the halo-block ring of the 3x3 halo kernel: 2 (default) or 3 (taken when at least four weight-tap slots still
+ * fit in shared memory).  Seeded by HPRI_HALO_A_STAGES. */
+int hpri_set_halo_a_stages(int stages);
 
 /* nn.ConvTranspose2d(k=2,s=2) fprop writing straight into the concat buffer (model_parts.py:63-64,
  * 74-87: pad + cat are absorbed by the destination view) and its dgrad. */

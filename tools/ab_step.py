@@ -35,8 +35,9 @@ def main():
             eng.set_next_input(x)
         eng.backward(dlogit, prescaled=True)
 
-    def cfg(prefetch=True, overlap=True, conv=-1, wgrad=-1, reverse=False):
+    def cfg(prefetch=True, overlap=True, conv=-1, wgrad=-1, reverse=False, a_stages=2):
         def apply():
+            ops.set_halo_a_stages(a_stages)
             ops.set_reverse_elementwise(reverse)
             state["prefetch"] = prefetch
             eng.set_overlap(overlap)
@@ -45,7 +46,7 @@ def main():
             ops.set_wgrad_algo(wgrad)
         return apply
     configs = {"default": cfg(), "no_prefetch": cfg(prefetch=False), "no_overlap": cfg(prefetch=False, overlap=False),
-               "single_cta_convs": cfg(conv=1), "generic_wgrad": cfg(wgrad=0), "reversed_elementwise": cfg(reverse=True)}
+               "single_cta_convs": cfg(conv=1), "generic_wgrad": cfg(wgrad=0), "reversed_elementwise": cfg(reverse=True), "halo_a_stages3": cfg(a_stages=3)}
     if which:
         configs = {k: v for k, v in configs.items() if k in which}
     res = {k: [] for k in configs}
