@@ -1,7 +1,8 @@
 """Out-of-bounds and uninitialised-memory check of a whole training step, without a sanitizer.
 
-Every workspace tensor the engines allocate (hyperpri_b200/engine.py `_z` / `_e`: activations, gradients, concat
-buffers, logits, loss scalars) is replaced by the interior of a larger byte buffer with a 64 KiB guard band on either
+Every device tensor the engines allocate (hyperpri_b200/engine.py `_z` / `_e`: activations, gradients, concat buffers,
+logits, loss scalars; and, through a stand-in for the `torch` factory functions engine.py and ops.py call, the packed
+16-bit weights, gradient packs, the flat gradient arena and the statistics slots) is replaced by the interior of a larger byte buffer with a 64 KiB guard band on either
 side.  The guard bands, and the interior of every buffer the engine asks for UNINITIALISED, are filled with 0xFF bytes:
 NaN as fp16 / bf16 / fp32 / fp64.  One forward + BCE + backward then has to
 
@@ -58,6 +59,34 @@ class Guarded:
             assert bool((hi == 0xFF).all()), ("store past the tensor", shape, dtype, int((hi != 0xFF).nonzero()[0]))
 
 
+class TorchShim:
+    """`torch` as engine.py / ops.py see it, with the factory functions they allocate device buffers with (packed
+    weights, gradient packs, the gradient arena, statistics slots, the second ingest buffer) routed to Guarded."""
+
+    def __init__(self, g):
+        self._g = g
+
+    def __getattr__(self, k):
+        return getattr(torch, k)
+
+    def _new(self, size, dtype, device, zero):
+        if device is None or torch.device(device).type != "cuda":
+            return (torch.zeros if zero else torch.empty)(*size, dtype=dtype, device=device)
+        return self._g.alloc(size[0] if len(size) == 1 else size, device, dtype or torch.float32, zero)
+
+    def zeros(self, *size, dtype=None, device=None):
+        return self._new(size, dtype, device, True)
+
+    def empty(self, *size, dtype=None, device=None):
+        return self._new(size, dtype, device, False)
+
+    def ones(self, *size, dtype=None, device=None):
+        return self._new(size, dtype, device, True).fill_(1)
+
+    def empty_like(self, t):
+        return self._g.alloc(tuple(t.shape), t.device, t.dtype, False)
+
+
 def step(net, xin, mask, fused):
     net.train()
     net.zero_grad(set_to_none=True)
@@ -100,6 +129,8 @@ def test_training_step_stays_inside_its_buffers_and_ignores_stale_memory(model, 
         g = Guarded()
         monkeypatch.setattr(E, "_z", g.z)
         monkeypatch.setattr(E, "_e", g.e)
+        monkeypatch.setattr(E, "torch", TorchShim(g))
+        monkeypatch.setattr(ops, "torch", TorchShim(g))
         net, _ = build(model, bands, feats or 1650, seed=2, **flags)
         lg1, loss1, g1 = step(net, xin, mask, fused)
         g.check()
