@@ -62,6 +62,7 @@ SIGNATURES = {
     "hpri_set_sm_reserve": [_i],
     "hpri_set_halo_a_stages": [_i],
     "hpri_set_reverse_elementwise": [_i],
+    "hpri_set_deterministic": [_i],
     "hpri_convT2x2_fwd": [_VP, _p, _i, _i, _i, _VP, _p, _i, _p],
     "hpri_convT2x2_dgrad": [_VP, _p, _i, _i, _i, _VP, _i, _p],
     "hpri_igemm_wgrad": [_VP, _VP, _i, _i, _p, _i, _i, _i, _p],

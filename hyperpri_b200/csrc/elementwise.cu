@@ -885,7 +885,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_k(BwdIn a, double* sums,
     }
     const float mu = __ldg(a.mean + c), is = __ldg(a.invstd + c);
     atomicAdd(sums + 3 * c, (double)t1);
-    atomicAdd(sums + 3 * c + 1, (double)is * ((double)t2 - (double)mu * (double)t1));
+    atomicAdd(sums + 3 * c + 1, (double)(float)((double)is * ((double)t2 - (double)mu * (double)t1)));
     if (HEAD) atomicAdd(sums + 3 * c + 2, (double)t3);
   }
 }
@@ -1045,7 +1045,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_flat_k(FlatIn a, double*
     }
     const float mu = __ldg(a.mean + c), is = __ldg(a.invstd + c);
     atomicAdd(sums + 3 * c, (double)t1);
-    atomicAdd(sums + 3 * c + 1, (double)is * ((double)t2 - (double)mu * (double)t1));
+    atomicAdd(sums + 3 * c + 1, (double)(float)((double)is * ((double)t2 - (double)mu * (double)t1)));
     if (HEAD) atomicAdd(sums + 3 * c + 2, (double)t3);
   }
 }
@@ -1241,7 +1241,7 @@ bn_bwd_reduce_contig_k(const uint4* __restrict__ x, const uint4* __restrict__ dy
     for (int t = cg; t < 256; t += CG) { t1 += red[t][k * 3]; t2 += red[t][k * 3 + 1]; t3 += red[t][k * 3 + 2]; }
     const float mu = __ldg(mean + c), is = __ldg(invstd + c);
     atomicAdd(sums + 3 * c, (double)t1);
-    atomicAdd(sums + 3 * c + 1, (double)is * ((double)t2 - (double)mu * (double)t1));
+    atomicAdd(sums + 3 * c + 1, (double)(float)((double)is * ((double)t2 - (double)mu * (double)t1)));
     if (HEAD) atomicAdd(sums + 3 * c + 2, (double)t3);
   }
 }
@@ -1293,6 +1293,17 @@ static inline int contig_grid(long long nvec, int per_block, int cap) {
 // Traversal order of the HBM-bound BatchNorm kernels (see the chunk loop above): 1 = last chunk first.  Default 0:
 // measured on B200 the reversed order changes nothing (7.66 vs 7.64 ms per step, tools/ab_step.py) -- the 126 MB L2 keeps
 // too little of a 150 MB tensor across a kernel boundary for the order to matter.
+// hpri_set_deterministic: the column / scalar sums whose CTAs meet in fp32 atomics run on ONE CTA (fixed order).  The
+// BatchNorm-backward reductions need no switch: each CTA forms its partials in a fixed order and contributes fp32-valued
+// addends to fp64 atomics -- an exact, hence order-independent, sum unless an addend is below 2^-29 of the total.
+static int g_deterministic = -1;           // seeded by the environment variable HPRI_DETERMINISTIC
+static inline int deterministic_on() {
+  if (g_deterministic < 0) {
+    const char* e = getenv("HPRI_DETERMINISTIC");
+    g_deterministic = (e && atoi(e) != 0) ? 1 : 0;
+  }
+  return g_deterministic;
+}
 static int g_reverse = -1;
 static inline int reverse_on() {
   if (g_reverse < 0) {
@@ -1563,7 +1574,14 @@ __global__ void sum_f32_k(const float* __restrict__ x, long long n, float* out, 
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     s += __ldg(x + i);
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if ((threadIdx.x & 31) == 0) atomicAdd(out, s * scale);
+  __shared__ float wsum[32];
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += wsum[w];
+    atomicAdd(out, t * scale);
+  }
 }
 
 // common element format of the views of a window kernel (-1: they differ -> runtime unpack)
@@ -1593,7 +1611,11 @@ static inline int grid_for(long long work_items, int per_block, int cap = 148 * 
 
 using namespace hpri;
 
-extern "C" int hpri_abi_version(void) { return 6; }
+extern "C" int hpri_abi_version(void) { return 7; }
+extern "C" int hpri_set_deterministic(int on) {
+  g_deterministic = on ? 1 : 0;
+  return HPRI_OK;
+}
 extern "C" int hpri_set_reverse_elementwise(int on) {
   g_reverse = on ? 1 : 0;
   return HPRI_OK;
@@ -2005,7 +2027,7 @@ extern "C" int hpri_colsum(const hpri_view_t* x, float* out, float beta, float s
   if (CG > 256) return HPRI_ERR_ARG;
   const int slots = 256 / CG;
   scale_f32_k<<<(x->c + 255) / 256, 256, 0, (cudaStream_t)stream>>>(out, x->c, beta);
-  colsum_k<<<grid_for((long long)x->n * x->h, 1, 148 * 8), 256, (size_t)slots * CG * 32, (cudaStream_t)stream>>>(mk(x), out,
+  colsum_k<<<deterministic_on() ? 1 : grid_for((long long)x->n * x->h, 1, 148 * 8), 256, (size_t)slots * CG * 32, (cudaStream_t)stream>>>(mk(x), out,
                                                                                                        slots, CG, scale);
   return last_err(2);
 }
@@ -2017,6 +2039,6 @@ extern "C" int hpri_scale_check(float* x, long long numel, float scale, int* fla
 extern "C" int hpri_sum_f32(const float* x, long long numel, float* out, float scale, void* stream) {
   if (!x || !out || numel <= 0) return HPRI_ERR_ARG;
   if (cudaMemsetAsync(out, 0, sizeof(float), (cudaStream_t)stream) != cudaSuccess) return HPRI_ERR_CUDA;
-  sum_f32_k<<<grid_for(numel, 256 * 8, 148 * 4), 256, 0, (cudaStream_t)stream>>>(x, numel, out, scale);
+  sum_f32_k<<<deterministic_on() ? 1 : grid_for(numel, 256 * 8, 148 * 4), 256, 0, (cudaStream_t)stream>>>(x, numel, out, scale);
   return last_err();
 }

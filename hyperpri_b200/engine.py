@@ -135,6 +135,12 @@ class _EngineBase:
         elif getattr(self, "_side_saved", None) is not None:
             self._side, self._side_saved = self._side_saved, None
 
+    @staticmethod
+    def _wgrad_splits():
+        """0: the launcher picks the pixel-range split (partial products meet in fp32 red.add, in arrival order);
+        deterministic mode: 1, every element of a weight gradient is summed by one CTA in a fixed order."""
+        return 1 if ops.DETERMINISTIC_BWD else 0
+
     def _partials(self, cout):
         """Scratch of the deterministic-statistics mode (ops.set_deterministic / HPRI_DETERMINISTIC=1), else None."""
         if not ops.DETERMINISTIC:
@@ -550,11 +556,13 @@ class UNetEngine(_EngineBase):
             ops.igemm_fwd(R, L.pp.dgr, L.cin, 9, dx_out, L.cin, bw=bw, zero_sums=False)
         # the packed gradient is unpacked into the arena per bucket (_unpack_bucket); the conv bias gradient is
         # identically zero under train-mode BN
-        self._on_side(lambda: ops.igemm_wgrad(xg, R, 1, L.cout, L.gw), after=ready)
+        self._on_side(lambda: ops.igemm_wgrad(xg, R, 1, L.cout, L.gw, splits=self._wgrad_splits()), after=ready)
 
     def _fusable(self, l, enc=False):
         """The a-layer of level l gets its whole output gradient from the b-layer's dgrad launch; the reduction can
         ride in that launch when it runs on the halo kernel."""
+        if ops.DETERMINISTIC_BWD:   # the fused epilogue adds its warps' partial sums in arrival order
+            return False
         return ops.conv3x3_halo_ok(self.ws["H"][l], self.ws["W"][l], (self.CE if enc else self.M)[l])
 
     # ------------------------------------------------------------------ forward
@@ -730,7 +738,7 @@ class UNetEngine(_EngineBase):
 
             def up_wgrad(x_up=self._as_grad_dtype(x_up), dy_up=dy_up, gw=gw, l=l):
                 # the packed gradient is unpacked with the bucket's 3x3 layers (_unpack_bucket)
-                ops.igemm_wgrad(x_up, dy_up, 2, 4 * U[l], gw)
+                ops.igemm_wgrad(x_up, dy_up, 2, 4 * U[l], gw, splits=self._wgrad_splits())
                 ops.colsum(dy_up, self._grad(self.up_name[l] + ".bias", P[self.up_name[l] + ".bias"]), scale=1.0 / self._S)
             self._on_side(up_wgrad)
             self._bucket_done(l)
@@ -1054,7 +1062,8 @@ class SpectralEngine(_EngineBase):
                                     out_scale=inv_bn, out_beta=acc_beta, flag=self.overflow, reduced=pp is not None)
                 xg = src if src.dtype == GRAD else ops.convert16(src, ws["cvt"][..., :src.shape[-1]])
                 self._on_side(lambda xg=xg, R=R, L=L, nm=nm: ops.igemm_wgrad(
-                    xg, R, 0, F, L.gw, x_c=(self.D if nm == "tail" else None), dy_c=F, block_n=self.wgrad_tile))
+                    xg, R, 0, F, L.gw, x_c=(self.D if nm == "tail" else None), dy_c=F, block_n=self.wgrad_tile,
+                    splits=self._wgrad_splits()))
                 r_busy[k] = self._side_mark()
                 if dx_dst is not None:
                     if L.pp.spec.split:

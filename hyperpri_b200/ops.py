@@ -244,16 +244,24 @@ def conv3x3_halo_ok(h, w, rows) -> bool:
     return bool(_lib.lib().hpri_conv3x3_halo_ok(int(h), int(w), int(rows)))
 
 
-DETERMINISTIC = __import__("os").environ.get("HPRI_DETERMINISTIC", "0") == "1"
+DETERMINISTIC = __import__("os").environ.get("HPRI_DETERMINISTIC", "0") in ("1", "fwd")     # forward statistics
+DETERMINISTIC_BWD = __import__("os").environ.get("HPRI_DETERMINISTIC", "0") == "1"           # and the backward pass
 
 
-def set_deterministic(on: bool):
-    """Deterministic BatchNorm statistics in the forward pass: every CTA's partial sums go to its own slot (warps added
-    in a fixed order) and the last CTA adds the slots in CTA order, instead of fp64 atomics in arrival order.  Two
-    forward passes on the same input and weights then give bit-identical logits (the backward pass keeps its
-    atomics: split-K weight gradients, BatchNorm-backward sums)."""
-    global DETERMINISTIC
+def set_deterministic(on: bool, backward: Optional[bool] = None):
+    """Run-to-run reproducible training steps (the reference's Trainer(deterministic='warn'), PLTrainer.py:430,439,447).
+    Forward: every CTA's BatchNorm partial sums go to its own slot (warps added in a fixed order) and the last CTA adds
+    the slots in CTA order, instead of fp64 atomics in arrival order -- bit-identical logits.  Backward: the
+    BatchNorm-backward reduction runs as its own kernels (fixed-order per-CTA partials whose fp32-valued addends are
+    combined exactly in fp64) instead of in the dgrad epilogue, weight gradients are not split over pixel ranges
+    (splits=1: one CTA sums each element), ConvTranspose / OutConv bias sums run on one CTA.  Slower (the full-resolution
+    weight gradients lose most of their parallelism); same values up to summation order.
+    backward=False keeps the production backward pass (HPRI_DETERMINISTIC=fwd): what the parity tests use, whose
+    assertions are on the logits but which should exercise the kernels training runs."""
+    global DETERMINISTIC, DETERMINISTIC_BWD
     DETERMINISTIC = bool(on)
+    DETERMINISTIC_BWD = DETERMINISTIC if backward is None else bool(backward) and DETERMINISTIC
+    check(_lib.lib().hpri_set_deterministic(int(DETERMINISTIC_BWD)), "hpri_set_deterministic")
 
 
 def bn_fin(count, gamma, beta, conv_bias, rmean, rvar, nbt, scale, shift, smean, sinv, counter, momentum=0.1, eps=1e-5,

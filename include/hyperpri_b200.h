@@ -229,6 +229,12 @@ int hpri_bn_finalize(double* stats, long long count, const float* gamma, const f
  * reversed order gains nothing on B200.  Seeded by the environment variable HPRI_REVERSE_ELEMENTWISE.  Values are
  * unchanged (reductions differ in summation order only). */
 int hpri_set_reverse_elementwise(int on);
+/* Run-to-run reproducible reductions (the reference builds its Trainer with deterministic='warn', PLTrainer.py:430,439,447):
+ * 1 = hpri_colsum / hpri_sum_f32 run on one CTA (their CTAs otherwise meet in fp32 atomics in arrival order).  The other
+ * order-dependent sums are selected per call: BatchNorm statistics by hpri_bn_fin_t::partials, split-K weight gradients
+ * by splits = 1, the fused dgrad + BatchNorm-backward reduction by bw = NULL; hpri_bn_relu_bwd_reduce is reproducible as
+ * it is (fixed-order per-CTA partials, fp32-valued addends combined exactly in fp64). */
+int hpri_set_deterministic(int on);
 /* y = relu(x*scale+shift) (model_parts.py:23-24); optional fused MaxPool2d(2) output (model_parts.py:40). */
 int hpri_bn_relu_apply(const hpri_view_t* x, const float* scale, const float* shift, const hpri_view_t* y,
                        const hpri_view_t* pooled, void* stream);

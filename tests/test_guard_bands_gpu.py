@@ -120,7 +120,7 @@ def test_training_step_stays_inside_its_buffers_and_ignores_stale_memory(model, 
     x = O.synth_cube(3, n, bands, h, w)
     xin = x[:, None] if model == "CubeNET" else x
     mask = O.synth_mask(3, n, h, w)
-    ops.set_deterministic(True)
+    ops.set_deterministic(True, backward=False)
     ops.set_conv_algo(algo)
     try:
         net, _ = build(model, bands, feats or 1650, seed=2, **flags)

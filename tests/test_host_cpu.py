@@ -28,7 +28,7 @@ def test_library_exports_every_header_symbol():
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.hpri_abi_version() == 6
+    assert lib.hpri_abi_version() == 7
     assert ctypes.sizeof(_lib.View) == 56          # ptr, 4 ints, 3 int64, dtype (+pad)
 
 

@@ -28,7 +28,7 @@ def _deterministic_statistics():
     measured separately (tools/parity_noise.py; test_deterministic_statistics_mode_is_bit_reproducible compares the two
     modes; tests/test_zz_full_size_gpu.py also asserts the default mode at full size)."""
     from hyperpri_b200 import ops
-    ops.set_deterministic(True)
+    ops.set_deterministic(True, backward=False)
     yield
     ops.set_deterministic(False)
 
@@ -526,7 +526,8 @@ def test_deterministic_statistics_mode_is_bit_reproducible(model, bands, h, w, f
         assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
         ol = O.forward_backward(model, xin.cpu(), mask, sd, training=True)[0]
         assert (outs[0].cpu() - ol).abs().max().item() <= 1e-2 * ol.abs().max().item()
-        # a full training step still runs (backward keeps its atomics) and leaves finite gradients
+        # a full training step in the fully deterministic mode leaves finite gradients (its reproducibility:
+        # test_deterministic_mode_training_is_bit_reproducible)
         lg, loss = run_ours(net, xin.cpu(), mask)
         assert all(torch.isfinite(p.grad).all() for p in net.parameters())
     finally:
@@ -535,6 +536,66 @@ def test_deterministic_statistics_mode_is_bit_reproducible(model, bands, h, w, f
     with torch.no_grad():
         plain = net(xin)
     assert (plain - outs[0]).abs().max().item() <= 5e-3 * outs[0].abs().max().item()
+
+
+DET_CASES = [("CubeNET", 238, 2, 37, 51, 0, {}), ("CubeNET", 238, 1, 96, 136, 0, dict(att=True, fd=32)),
+             ("UNET", 3, 2, 50, 34, 0, dict(bil=True)), ("UNET", 3, 2, 160, 200, 0, {}),
+             ("SpectralUNET", 238, 2, 9, 13, 96, {}), ("SpectralUNET", 238, 2, 24, 40, 1650, dict(bnorm=False))]
+
+
+@pytest.mark.parametrize("model,bands,n,h,w,feats,flags", DET_CASES)
+def test_deterministic_mode_training_is_bit_reproducible(model, bands, n, h, w, feats, flags):
+    """ops.set_deterministic(True) (HPRI_DETERMINISTIC=1; the reference's Trainer(deterministic='warn'),
+    PLTrainer.py:430,439,447): three training steps -- fused BCE step, backward, FusedAdam -- from the same weights on
+    the same batches give bit-identical losses, logits, gradients and updated parameters on every run, and the
+    gradients of this mode (unfused BatchNorm-backward reduction, unsplit weight gradients, single-CTA bias sums)
+    agree with the production backward pass to the fp16-rounding level of its run-to-run spread."""
+    from hyperpri_b200 import ops
+    from hyperpri_b200.optim import FusedAdam
+    x = O.synth_cube(5, n, bands, h, w)
+    xin = (x[:, None] if model == "CubeNET" else x).cuda()
+    mask = O.synth_mask(5, n, h, w).cuda()
+
+    def train():
+        net, _ = build(model, bands, feats or 1650, seed=4, **flags)
+        net.train()
+        opt = FusedAdam(net.parameters(), lr=1e-3)
+        trace = []
+        for it in range(3):
+            opt.zero_grad(set_to_none=True)
+            loss, logits, counts = net.bce_step(xin.roll(it, -1), mask.roll(it, -1), 0.5)
+            loss.backward()
+            trace.append((loss.detach().clone(), logits.detach().clone(), counts.clone(),
+                          [p.grad.detach().clone() for p in net.parameters()]))
+            opt.step()
+        torch.cuda.synchronize()
+        return trace, [p.detach().clone() for p in net.parameters()], [k for k, _ in net.named_parameters()]
+
+    ops.set_deterministic(True)
+    try:
+        ta, pa, names = train()
+        tb, pb, _ = train()
+    finally:
+        ops.set_deterministic(False)
+    for it, ((la, lga, ca, ga), (lb, lgb, cb, gb)) in enumerate(zip(ta, tb)):
+        assert torch.equal(la, lb) and torch.equal(lga, lgb) and torch.equal(ca, cb), it
+        for k, u, v in zip(names, ga, gb):
+            assert torch.isfinite(u).all(), (it, k)
+            assert torch.equal(u, v), (it, k, (u - v).abs().max().item())
+    for k, u, v in zip(names, pa, pb):
+        assert torch.equal(u, v), k
+    ops.set_deterministic(True, backward=False)          # the production backward pass behind the same forward pass
+    try:
+        tc, _, _ = train()
+    finally:
+        ops.set_deterministic(False)
+    assert torch.equal(tc[0][1], ta[0][1])
+    flat = lambda g: torch.cat([t.flatten() for t in g]).double()
+    d, c = flat(ta[0][3]), flat(tc[0][3])
+    rel = ((d - c).norm() / c.norm()).item()
+    record(test="deterministic_mode_training", model=model, shape=[n, bands, h, w], flags=str(flags),
+           grad_rel_l2_vs_production_backward=rel)
+    assert rel <= 5e-3
 
 
 @pytest.mark.parametrize("feats,h,w", [(96, 24, 40), (1650, 16, 33)])

@@ -18,7 +18,7 @@ from test_models_gpu import build                                      # noqa: E
 model = sys.argv[1] if len(sys.argv) > 1 else "CubeNET"
 h, w = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (37, 51)
 bands = 238 if model == "CubeNET" else 3
-ops.set_deterministic(True)
+ops.set_deterministic(True, backward=os.environ.get("DET_BWD", "0") == "1")
 net, _ = build(model, bands, seed=2)
 x = O.synth_cube(3, 2, bands, h, w)
 xin = (x[:, None] if model == "CubeNET" else x).cuda()
