@@ -122,6 +122,9 @@ class ExpHyperspectralPRI(_ExpBase):
         # ingest kernel rounds fp32 cubes to fp16 anyway, so the network input is bit-identical and the PCIe bytes
         # halve.  torch.float32 restores the reference's item dtype.
         self.hsi_host_dtype = torch.float16
+        # extension: run-to-run reproducible training steps (the reference's Trainer(deterministic='warn'),
+        # PLTrainer.py:430,439,447); slower kernels for the order-dependent sums, so off unless asked for
+        self.deterministic = False
         self._paths(calling_path, comet_logging)
 
     def translate_load_dir(self):

@@ -344,6 +344,10 @@ def train_net(params, checkpoint=None, model_parallel: bool = False):
     train_loader = DataLoader(params.get_train_data(), batch_size=params.b_size['train'], shuffle=True, num_workers=0)
     val_loader = DataLoader(params.get_val_data(), batch_size=params.b_size['val'], shuffle=False, num_workers=0)
     model = RootLightningModel(params)
+    if getattr(params, "deterministic", False) and getattr(params, "device", "gpu") == "gpu":
+        # the reference builds every Trainer with deterministic='warn' (:430,439,447); here it is a knob, default off
+        from .. import ops as _ops
+        _ops.set_deterministic(True)
     ckpt = None
     if checkpoint:
         last = os.path.join(params.save_path, 'Checkpoints', 'last.ckpt')

@@ -71,6 +71,30 @@ def test_train_validate_test_roundtrip(tmp_path):
     assert out["dice"] > 0.5                                 # six epochs on a trivially separable signal
 
 
+def test_deterministic_knob_makes_train_net_bit_reproducible(tmp_path):
+    """params.deterministic = True (the reference's Trainer(deterministic='warn'), PLTrainer.py:430,439,447): two
+    train_net runs from the same seed end with identical loss histories and identical weights."""
+    from hyperpri_b200 import ops
+    runs = []
+    try:
+        for r in range(2):
+            root = str(tmp_path / f"run{r}")
+            _write_split(root, "train", ["20220701", "20220702", "20220703", "20220704"], 32, 48, 0)
+            _write_split(root, "val", ["20220711", "20220712"], 32, 48, 1)
+            torch.manual_seed(0)
+            p = ExpHyperspectralPRI(root, split_no=1, seed_num=0, comet_logging=False)
+            p.epochs, p.patch_size, p.deterministic = 3, (32, 48), True
+            trainer = T.train_net(p)
+            assert ops.DETERMINISTIC and ops.DETERMINISTIC_BWD
+            runs.append(([(h["tr_loss"], h["val_loss"]) for h in trainer.history],
+                         {k: v.detach().clone() for k, v in trainer.model.m_network.state_dict().items()}))
+    finally:
+        ops.set_deterministic(False)
+    assert runs[0][0] == runs[1][0]
+    for k, v in runs[0][1].items():
+        assert torch.equal(v, runs[1][1][k]), k
+
+
 @pytest.mark.gpu
 def test_device_prefetcher_order_contents_and_slot_reuse():
     """Batches arrive on the device in order, bit-identical, one copy ahead; the two slots are recycled without the
