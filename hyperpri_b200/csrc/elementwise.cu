@@ -884,6 +884,8 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_k(BwdIn a, double* sums,
       t1 += red[t][k * 3]; t2 += red[t][k * 3 + 1]; t3 += red[t][k * 3 + 2];
     }
     const float mu = __ldg(a.mean + c), is = __ldg(a.invstd + c);
+    // every addend is an fp32 value (the centred term is rounded to one): the CTAs' fp64 atomics then add exactly, so
+    // the sums do not depend on the order the CTAs arrive in (same in the two kernels below)
     atomicAdd(sums + 3 * c, (double)t1);
     atomicAdd(sums + 3 * c + 1, (double)(float)((double)is * ((double)t2 - (double)mu * (double)t1)));
     if (HEAD) atomicAdd(sums + 3 * c + 2, (double)t3);
