@@ -318,3 +318,23 @@ def test_ctypes_structs_match_the_c_header_layout(tmp_path):
         assert ctypes.sizeof(cls) == want[(cname, "size")], cname
         for f in fields:
             assert getattr(cls, f).offset == want[(cname, f)], (cname, f)
+
+
+def test_deterministic_switch_levels():
+    """ops.set_deterministic: off / forward statistics only / forward + backward, mirrored into the library's own switch
+    (hpri_set_deterministic accepts the call without a GPU) and read by the engine's launch plan."""
+    from hyperpri_b200 import engine as E, ops
+    try:
+        ops.set_deterministic(True, backward=False)
+        assert ops.DETERMINISTIC and not ops.DETERMINISTIC_BWD and E._EngineBase._wgrad_splits() == 0
+        ops.set_deterministic(True)
+        assert ops.DETERMINISTIC and ops.DETERMINISTIC_BWD and E._EngineBase._wgrad_splits() == 1
+        net = mdl.UNet(3, 1, bilinear=False)
+        eng = E.UNetEngine(net._tensor_table(), "unet", 3, torch.device("cpu"))
+        eng.ws = {"H": [608, 304, 152, 76, 38], "W": [968, 484, 242, 121, 60]}
+        assert not any(eng._fusable(l) for l in range(4))          # no fused dgrad + BatchNorm-backward epilogue
+        ops.set_deterministic(False, backward=True)
+        assert not ops.DETERMINISTIC and not ops.DETERMINISTIC_BWD and E._EngineBase._wgrad_splits() == 0
+        assert all(eng._fusable(l) for l in range(4))              # the production plan at BASELINE size
+    finally:
+        ops.set_deterministic(False)
