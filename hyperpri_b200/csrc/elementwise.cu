@@ -1295,7 +1295,8 @@ static inline int contig_grid(long long nvec, int per_block, int cap) {
 // Traversal order of the HBM-bound BatchNorm kernels (see the chunk loop above): 1 = last chunk first.  Default 0:
 // measured on B200 the reversed order changes nothing (7.66 vs 7.64 ms per step, tools/ab_step.py) -- the 126 MB L2 keeps
 // too little of a 150 MB tensor across a kernel boundary for the order to matter.
-// hpri_set_deterministic: the column / scalar sums whose CTAs meet in fp32 atomics run on ONE CTA (fixed order).  The
+// hpri_set_deterministic: the column / scalar sums whose CTAs meet in fp32 atomics run with ONE CTA per output element
+// (colsum: one per eight channels; sum_f32: one), i.e. in a fixed order.  The
 // BatchNorm-backward reductions need no switch: each CTA forms its partials in a fixed order and contributes fp32-valued
 // addends to fp64 atomics -- an exact, hence order-independent, sum unless an addend is below 2^-29 of the total.
 static int g_deterministic = -1;           // seeded by the environment variable HPRI_DETERMINISTIC
@@ -1513,6 +1514,7 @@ pr_hist_k(const float* __restrict__ x, const float* __restrict__ t, long long n,
 __global__ void __launch_bounds__(256) colsum_k(V x, float* out, int slots, int CG, float scale) {
   extern __shared__ float red[];                 // [slots][CG*8]
   const int cg = threadIdx.x % CG, slot = threadIdx.x / CG;
+  const int cg0 = blockIdx.y * CG;               // blockIdx.y: which CG channel groups this block owns (0 unless deterministic)
   if (slot < slots) {
     float s[8];
 #pragma unroll
@@ -1521,7 +1523,7 @@ __global__ void __launch_bounds__(256) colsum_k(V x, float* out, int slots, int 
     const int rows = x.n * x.h;
     for (int r = blockIdx.x; r < rows; r += gridDim.x) {
       const int n = r / x.h, yy = r - n * x.h;
-      const uint16_t* base = at(x, n, yy, 0, cg * 8);
+      const uint16_t* base = at(x, n, yy, 0, (cg0 + cg) * 8);
       for (int x0 = slot; x0 < x.w; x0 += 4 * slots) {
         uint4 v[4];
 #pragma unroll
@@ -1546,7 +1548,7 @@ __global__ void __launch_bounds__(256) colsum_k(V x, float* out, int slots, int 
   for (int i = threadIdx.x; i < CG * 8; i += blockDim.x) {
     float t = 0.f;
     for (int s = 0; s < slots; ++s) t += red[(long long)s * CG * 8 + i];
-    if (i < x.c) atomicAdd(out + i, t * scale);
+    if (cg0 * 8 + i < x.c) atomicAdd(out + cg0 * 8 + i, t * scale);
   }
 }
 __global__ void scale_f32_k(float* p, int n, float beta) {
@@ -2029,8 +2031,11 @@ extern "C" int hpri_colsum(const hpri_view_t* x, float* out, float beta, float s
   if (CG > 256) return HPRI_ERR_ARG;
   const int slots = 256 / CG;
   scale_f32_k<<<(x->c + 255) / 256, 256, 0, (cudaStream_t)stream>>>(out, x->c, beta);
-  colsum_k<<<deterministic_on() ? 1 : grid_for((long long)x->n * x->h, 1, 148 * 8), 256, (size_t)slots * CG * 32, (cudaStream_t)stream>>>(mk(x), out,
-                                                                                                       slots, CG, scale);
+  if (deterministic_on())       // one CTA per group of eight channels: every output element has a single, fixed-order writer
+    colsum_k<<<dim3(1, CG), 256, 256 * 32, (cudaStream_t)stream>>>(mk(x), out, 256, 1, scale);
+  else
+    colsum_k<<<grid_for((long long)x->n * x->h, 1, 148 * 8), 256, (size_t)slots * CG * 32, (cudaStream_t)stream>>>(mk(x), out,
+                                                                                                         slots, CG, scale);
   return last_err(2);
 }
 extern "C" int hpri_scale_check(float* x, long long numel, float scale, int* flag, void* stream) {

@@ -230,7 +230,8 @@ int hpri_bn_finalize(double* stats, long long count, const float* gamma, const f
  * unchanged (reductions differ in summation order only). */
 int hpri_set_reverse_elementwise(int on);
 /* Run-to-run reproducible reductions (the reference builds its Trainer with deterministic='warn', PLTrainer.py:430,439,447):
- * 1 = hpri_colsum / hpri_sum_f32 run on one CTA (their CTAs otherwise meet in fp32 atomics in arrival order).  The other
+ * 1 = hpri_colsum runs one CTA per eight channels and hpri_sum_f32 one CTA (their CTAs otherwise meet in fp32 atomics in
+ * arrival order).  The other
  * order-dependent sums are selected per call: BatchNorm statistics by hpri_bn_fin_t::partials, split-K weight gradients
  * by splits = 1, the fused dgrad + BatchNorm-backward reduction by bw = NULL; hpri_bn_relu_bwd_reduce is reproducible as
  * it is (fixed-order per-CTA partials, fp32-valued addends combined exactly in fp64). */

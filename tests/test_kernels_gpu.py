@@ -584,6 +584,34 @@ def test_param_grads_are_unscaled_accumulated_and_flagged():
     assert abs(s.item() - 0.5 * v.double().sum().item()) < 1e-3
 
 
+@pytest.mark.parametrize("n,h,w,c,strided", [(2, 37, 51, 64, False), (1, 20, 33, 512, True), (2, 9, 13, 1024, False),
+                                             (1, 64, 70, 128, True)])
+def test_deterministic_column_and_scalar_sums(n, h, w, c, strided):
+    """hpri_set_deterministic: hpri_colsum with one CTA per eight channels, hpri_sum_f32 on one CTA -- same values as the
+    multi-CTA launches up to fp32 summation order, bit-identical from run to run; also on the channel-sliced, cropped
+    views ConvTranspose's bias gradient is taken from."""
+    full = nhwc(rnd(n, 2 * c if strided else c, h + 2, w + 1, seed=7), dt=FH)
+    x = full[:, :h, :w, c:] if strided else full[:, :h, :w]
+    ref = x.float().sum((0, 1, 2))
+    v = torch.randn(123457, device=DEV)
+    outs = []
+    try:
+        for det in (False, True, True):
+            ops.set_deterministic(det)
+            o = torch.full((c,), 3.0, device=DEV)
+            ops.colsum(x, o, beta=1.0, scale=0.5)
+            s1 = torch.empty(1, device=DEV)
+            ops.sum_f32(v, s1, scale=2.0)
+            torch.cuda.synchronize()
+            outs.append((o, s1))
+    finally:
+        ops.set_deterministic(False)
+    for o, s1 in outs:
+        assert torch.allclose(o, 3.0 + 0.5 * ref, rtol=1e-4, atol=1e-3)
+        assert abs(s1.item() - 2.0 * v.double().sum().item()) < 2e-2
+    assert torch.equal(outs[1][0], outs[2][0]) and torch.equal(outs[1][1], outs[2][1])
+
+
 def test_batch_tables_with_convT_jobs_scale_and_overflow_flag():
     """One table-driven launch packs 3x3 and ConvTranspose2d layers together (both operands each) and one unpacks /
     unscales their packed gradients; == the per-layer kernels.  A non-finite packed value raises the flag."""
