@@ -13,6 +13,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
+from _mp import from_plain, to_plain
+
 pytestmark = pytest.mark.gpu
 
 
@@ -23,7 +25,7 @@ def _collect(q, procs, timeout=240):
     out, t0 = [], time.time()
     while len(out) < len(procs):
         try:
-            out.append(q.get(timeout=2))
+            out.append(from_plain(q.get(timeout=2)))
         except queue.Empty:
             dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
             if dead or time.time() - t0 > timeout:
@@ -95,7 +97,7 @@ def _worker(rank, world, port, q):
         off = (ptr - base) // 4
         want = both[0] + both[1]           # buckets leave the unpack kernels already unscaled (1 / loss scale folded in)
         exact = exact and torch.equal(eng.arena[off:off + mine.numel()], want)
-    q.put((rank, {k: v.cpu() for k, v in out.items()}, int(eng.overflow.item()), exact))
+    q.put(to_plain((rank, {k: v.cpu() for k, v in out.items()}, int(eng.overflow.item()), exact)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -176,7 +178,7 @@ def _pp_worker(rank, world, port, feats, q):
     out = None
     for _ in range(2):                       # twice: workspace / event reuse; the second step sees updated running stats
         out = _pp_step(net, x, m)
-    q.put((rank,) + out + (int(net._get_engine(dev).overflow.item()), pp.bytes))
+    q.put(to_plain((rank,) + out + (int(net._get_engine(dev).overflow.item()), pp.bytes)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -270,8 +272,8 @@ def _train_worker(rank, world, port, root, model_name, model_parallel, q):
     net = trainer.model.m_network
     flat = torch.cat([t.detach().float().flatten() for t in net.parameters()]).cpu()
     eng = net._get_engine(torch.device("cuda", rank))
-    q.put((rank, flat, [h["tr_loss"] for h in trainer.history], [h["val_loss"] for h in trainer.history],
-           int(eng.overflow.item()), sorted(os.listdir(os.path.join(p.save_path, "Checkpoints")))))
+    q.put(to_plain((rank, flat, [h["tr_loss"] for h in trainer.history], [h["val_loss"] for h in trainer.history],
+                    int(eng.overflow.item()), sorted(os.listdir(os.path.join(p.save_path, "Checkpoints"))))))
     dist.barrier()
     dist.destroy_process_group()
 

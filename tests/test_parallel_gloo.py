@@ -7,6 +7,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from hyperpri_b200 import parallel
+from _mp import from_plain, to_plain
 
 
 def _free_port():
@@ -35,7 +36,7 @@ def _worker(rank, world, port, q):
     eng.arena.mul_(red.grad_scale())          # the engine folds 1/world into the loss gradient
     eng.backward()
     red.finish()
-    q.put((rank, eng.arena.clone(), red.bytes))
+    q.put(to_plain((rank, eng.arena.clone(), red.bytes)))
     dist.destroy_process_group()
 
 
@@ -46,7 +47,7 @@ def test_bucketed_allreduce_world2():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=120) for _ in procs]
+    res = [from_plain(q.get(timeout=120)) for _ in procs]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -110,7 +111,7 @@ def _pp_worker(rank, world, port, q):
     stats = torch.stack([loc.sum(0), (loc * loc).sum(0)], 1)
     pp.all_reduce_(stats)
     full = pp.gather_rows(img[:, :, r0:r1].contiguous(), R)
-    q.put((rank, strips, stats, full, img, feat, pp.bytes))
+    q.put(to_plain((rank, strips, stats, full, img, feat, pp.bytes)))
     dist.destroy_process_group()
 
 
@@ -121,7 +122,7 @@ def test_pixel_parallel_protocol_world2():
     procs = [ctx.Process(target=_pp_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=120) for _ in procs]
+    res = [from_plain(q.get(timeout=120)) for _ in procs]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -131,3 +132,18 @@ def test_pixel_parallel_protocol_world2():
         assert torch.allclose(stats, want, rtol=1e-12, atol=1e-12)          # whole-image statistics on every rank
         assert torch.equal(full, img)
         assert nbytes == stats.numel() * 8
+
+
+def test_worker_results_travel_by_value():
+    """tests/_mp.py: nested results with tensors of every dtype the workers return survive the plain round trip."""
+    import pickle
+    obj = (1, {"a": torch.arange(6, dtype=torch.int64).view(2, 3), "b": [torch.tensor(2.5, dtype=torch.float64)]},
+           torch.randn(4, 5).to(torch.bfloat16), [0.25, "x"], torch.zeros((), dtype=torch.int64))
+    plain = to_plain(obj)
+    assert b"torch" not in pickle.dumps(plain).replace(b"torch.", b"")      # no tensor objects left, only dtype names
+    back = from_plain(pickle.loads(pickle.dumps(plain)))
+    assert back[0] == 1 and back[3] == [0.25, "x"]
+    assert torch.equal(back[1]["a"], obj[1]["a"]) and back[1]["a"].dtype == torch.int64
+    assert torch.equal(back[1]["b"][0], obj[1]["b"][0]) and back[1]["b"][0].dtype == torch.float64
+    assert torch.equal(back[2], obj[2]) and back[2].dtype == torch.bfloat16
+    assert back[4].dim() == 0 and back[4].dtype == torch.int64

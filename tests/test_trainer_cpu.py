@@ -14,6 +14,7 @@ import torch.multiprocessing as mp
 from torch.utils.data import DataLoader, Dataset
 
 from hyperpri_b200.src import PLTrainer as T
+from _mp import from_plain, to_plain
 from hyperpri_b200.src.Experiments.params_HyperPRI import ExpHyperspectralPRI, ExpRedGreenBluePRI
 
 
@@ -182,7 +183,7 @@ def _dp_worker(rank, world, port, root, q):
     va = DataLoader(_Pixels(4, 1), batch_size=2)
     loop = T._Loop(p, 2, device=torch.device("cpu"))
     loop.fit(model, tr, va)
-    q.put((rank, seen, [t.detach().clone() for t in model.parameters()], loop.history))
+    q.put(to_plain((rank, seen, [t.detach().clone() for t in model.parameters()], loop.history)))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -196,7 +197,7 @@ def test_loop_ddp_semantics_world2(tmp_path):
         pr.start()
     res = {}
     for _ in procs:
-        rank, seen, params, hist = q.get(timeout=180)
+        rank, seen, params, hist = from_plain(q.get(timeout=180))
         res[rank] = (seen, params, hist)
     for pr in procs:
         pr.join(timeout=60)
